@@ -1,0 +1,206 @@
+/*
+ * vlpet.h — C ABI of libvlpet.so: the B200-native (sm_100a) PET hot path of VL-PET.
+ *
+ * The reference (HenryHZY/VL-PET) is pure PyTorch: there is no native interface to mirror, so each entry
+ * point below cites the reference Python lines whose op sequence it replaces (paths relative to
+ * /root/reference/src).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer to a contiguous row-major tensor, 16-byte aligned.
+ *  - nn.Linear weights are [out_features, in_features] row-major exactly as PyTorch stores them.
+ *  - All calls are asynchronous on the caller's stream (`stream` is a cudaStream_t passed as void*),
+ *    allocate nothing and keep no state besides an immutable per-process function-pointer cache.
+ *    Scratch memory is caller-owned: query *_workspace_bytes first.
+ *  - Return value: 0 = ok, >0 = cudaError_t, <0 = VLPET_E_* argument error.  vlpet_last_error() returns a
+ *    thread-local human-readable message for the last non-zero return.  Nothing throws across the boundary.
+ *  - Weight gradients are fp32 and are ACCUMULATED into (`+=`) the caller's buffers, so they can alias
+ *    views of one flat all-reduce bucket.  Activation gradients are overwritten.
+ *  - There is no CPU fallback: without a CUDA device every compute entry returns an error.
+ */
+#ifndef VLPET_H_
+#define VLPET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VLPET_API __attribute__((visibility("default")))
+#else
+#define VLPET_API
+#endif
+
+#define VLPET_VERSION 100 /* major*100 + minor */
+
+/* activation / weight element type of a call (weights, biases and activations share it) */
+enum { VLPET_F32 = 0, VLPET_BF16 = 1 };
+
+/* granularity-control matrix G (paper Fig. 2; my_transformers/modeling_bart.py:1195-1231) */
+enum {
+  VLPET_GATE_NONE = 0,     /* no gate: h = y1                                                           */
+  VLPET_GATE_LARGE = 1,    /* N x d : sigmoid(GUp(gelu_new(GDown x1)))            modeling_bart.py:1195-1209 */
+  VLPET_GATE_MIDDLE_X = 2, /* N x 1 : sigmoid(Linear(d,1)(x1 + y1))               modeling_bart.py:1219-1226 */
+  VLPET_GATE_MIDDLE_Y = 3, /* 1 x d : h = y1 + y1*z (no sigmoid)                  modeling_bart.py:1227-1231 */
+  VLPET_GATE_SMALL = 4     /* 1 x 1 : mean_L sigmoid(Linear(2d,1)([x1;y1]))       modeling_bart.py:1210-1218 */
+};
+
+/* error codes (negative returns) */
+enum {
+  VLPET_E_BADARG = -1,     /* null pointer / bad enum / non-positive size */
+  VLPET_E_UNSUPPORTED = -2,/* shape outside what the kernels implement (never silently falls back to CPU) */
+  VLPET_E_WORKSPACE = -3,  /* workspace too small */
+  VLPET_E_NODEVICE = -4,   /* no sm_100 device / driver entry point missing */
+  VLPET_E_ALIGN = -5       /* pointer not 16-byte aligned */
+};
+
+/* which implementation a call may use */
+enum {
+  VLPET_IMPL_AUTO = 0,     /* fused tcgen05/TMA kernel when the shape qualifies, else the generic kernels */
+  VLPET_IMPL_GENERIC = 1,  /* shape-generic CUDA-core kernels (any d, r, gate, dtype)                     */
+  VLPET_IMPL_FUSED = 2     /* fused sm_100a kernel only; VLPET_E_UNSUPPORTED if the shape does not qualify */
+};
+
+/* ---- K1: granularity-controlled PET module -------------------------------------------------------------
+ * Replaces the inline op sequence of BartEncoderLayer.forward (my_transformers/modeling_bart.py:1145-1155
+ * adapter, 1195-1231 gate, 1256-1260 scale+residual; FFN twin 1268-1278,1317-1325,1372-1376) and of
+ * T5LayerSelfAttention.forward / T5LayerFF.forward (my_transformers/modeling_t5.py:777-824, 359-409):
+ *
+ *     y1  = kappa*x2 + alpha*(gelu_new(x2 Wd^T + bd) Wu^T + bu)
+ *     out = x1 + dropout_p(s * gate(x1, y1))
+ *
+ * The multi-head down projection is passed as its row-concatenation Wd [r,d].            */
+typedef struct VlpetK1Desc {
+  int64_t M;        /* tokens = B*L                                                           */
+  int32_t L;        /* sequence length; required (M % L == 0) for VLPET_GATE_SMALL, else may be 0 */
+  int32_t d;        /* d_model                                                                */
+  int32_t r;        /* adapter rank  (adapter_down_dim)                                       */
+  int32_t rg;       /* gate rank     (adapter_gating_down_dim); VLPET_GATE_LARGE only         */
+  int32_t gate;     /* VLPET_GATE_*                                                           */
+  int32_t add_gate; /* --use_encoder_adapter_gating_add: h = y1 + G instead of y1 * G         */
+  int32_t dtype;    /* VLPET_F32 | VLPET_BF16                                                 */
+  int32_t impl;     /* VLPET_IMPL_*                                                           */
+  float s;          /* encoder_gating_scaling_factor (1 when the flag is off)                 */
+  float alpha;      /* encoder_adapter_scaling_factor                                         */
+  float kappa;      /* encoder_x2_scaling_factor                                              */
+  float p_drop;     /* dropout between gate and residual (modeling_bart.py:1259); 0 = identity (eval / parity) */
+  uint64_t seed;    /* dropout stream: keep(m,c) is a pure function of (seed, m*d+c), so the backward regenerates
+                       the forward mask from the same seed; the mask is NOT torch's Philox stream            */
+} VlpetK1Desc;
+
+typedef struct VlpetK1Params { /* dtype = desc.dtype; unused members NULL */
+  const void* Wd;  /* [r,d]   attn_adapter_multihead_down.{h}.weight row-concatenated */
+  const void* bd;  /* [r]                                                             */
+  const void* Wu;  /* [d,r]   attn_adapter_multihead_up.weight                        */
+  const void* bu;  /* [d]                                                             */
+  const void* Gd;  /* [rg,d]  encoder_attn_adapter_gating_large_x_down.weight         */
+  const void* gbd; /* [rg]                                                            */
+  const void* Gu;  /* [d,rg]  encoder_attn_adapter_gating_large_x_up.weight           */
+  const void* gbu; /* [d]                                                             */
+  const void* gw;  /* [d] middle_x | [2d] small : gating Linear(.,1).weight           */
+  const void* gb;  /* [1]                                                             */
+  const void* gz;  /* [d] middle_y parameter                                          */
+} VlpetK1Params;
+
+typedef struct VlpetK1Grads { /* fp32, accumulated into; members mirror VlpetK1Params; NULL = skip */
+  float *dWd, *dbd, *dWu, *dbu, *dGd, *dgbd, *dGu, *dgbu, *dgw, *dgb, *dgz;
+} VlpetK1Grads;
+
+VLPET_API size_t vlpet_k1_fwd_workspace_bytes(const VlpetK1Desc* desc);
+VLPET_API size_t vlpet_k1_bwd_workspace_bytes(const VlpetK1Desc* desc);
+VLPET_API int vlpet_k1_fwd(const VlpetK1Desc* desc, const void* x1, const void* x2, const VlpetK1Params* w, void* out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* Recomputes the forward intermediates from x1/x2 (nothing is saved by the forward). */
+VLPET_API int vlpet_k1_bwd(const VlpetK1Desc* desc, const void* x1, const void* x2, const void* dout,
+                 const VlpetK1Params* w, void* dx1, void* dx2, const VlpetK1Grads* g, void* workspace,
+                 size_t workspace_bytes, void* stream);
+/* 1 if vlpet_k1_fwd / _bwd would run the fused tcgen05 kernel for this desc under VLPET_IMPL_AUTO */
+VLPET_API int vlpet_k1_fwd_is_fused(const VlpetK1Desc* desc);
+VLPET_API int vlpet_k1_bwd_is_fused(const VlpetK1Desc* desc);
+
+/* ---- K2: decoder cross-attention value parallel adapter -----------------------------------------------
+ * Replaces AdapterController.forward(inputs, task, y) + Adapter.forward (adapters/adapter_controller.py:131-162,
+ * adapters/adapter_modeling.py:55-61) as called at my_transformers/modeling_bart.py:427-430 and
+ * my_transformers/modeling_t5.py:600-603:     out = y + sf * (gelu_new(kv Wd^T + bd) Wu^T + bu)
+ * (pass y = kv for the non-parallel residual of adapter_controller.py:160-161).                     */
+typedef struct VlpetK2Desc {
+  int64_t M;
+  int32_t d, r;
+  int32_t dtype, impl;
+  float sf; /* scaling_factor (1 when use_scaling_factor is off) */
+} VlpetK2Desc;
+typedef struct VlpetK2Params { const void *Wd, *bd, *Wu, *bu; } VlpetK2Params;
+typedef struct VlpetK2Grads { float *dWd, *dbd, *dWu, *dbu; } VlpetK2Grads;
+
+VLPET_API size_t vlpet_k2_fwd_workspace_bytes(const VlpetK2Desc* desc);
+VLPET_API size_t vlpet_k2_bwd_workspace_bytes(const VlpetK2Desc* desc);
+VLPET_API int vlpet_k2_fwd(const VlpetK2Desc* desc, const void* kv, const void* y, const VlpetK2Params* w, void* out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* dkv receives ONLY the adapter-path gradient (autograd adds the frozen k/v_proj paths); dy == dout. */
+VLPET_API int vlpet_k2_bwd(const VlpetK2Desc* desc, const void* kv, const void* dout, const VlpetK2Params* w, void* dkv,
+                 const VlpetK2Grads* g, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K3: visual projection -----------------------------------------------------------------------------
+ * Replaces VisualEmbedding.forward (src/modeling_bart.py:143-192; T5: src/modeling_t5.py:124-174):
+ *     out = LN(feats Wf^T + bf) + LN([pos,area] Wp^T + bp) + E_img[img_ids] + E_obj[V-1-obj_ids]
+ * rms = 1 selects T5LayerNorm (my_transformers/modeling_t5.py:235-252: no mean, no bias).           */
+typedef struct VlpetK3Desc {
+  int64_t M;      /* B*N visual tokens                                                     */
+  int32_t N;      /* boxes per sample (ids default to 0 / arange(N) when the id pointers are NULL) */
+  int32_t F;      /* feat_dim                                                              */
+  int32_t d;
+  int32_t V;      /* rows of E_obj (vocabulary size)                                       */
+  int32_t n_img;  /* rows of E_img                                                         */
+  int32_t rms;
+  int32_t dtype, impl;
+  float eps;
+} VlpetK3Desc;
+typedef struct VlpetK3Params {
+  const void *Wf, *bf, *ln_f_w, *ln_f_b; /* [d,F],[d],[d],[d] (ln_*_b NULL when rms)     */
+  const void *Wp, *bp, *ln_p_w, *ln_p_b; /* [d,5],[d],[d],[d]                            */
+  const void *E_img, *E_obj;             /* [n_img,d], [V,d]                             */
+} VlpetK3Params;
+typedef struct VlpetK3Grads {
+  float *dWf, *dbf, *dln_f_w, *dln_f_b, *dWp, *dbp, *dln_p_w, *dln_p_b, *dE_img;
+} VlpetK3Grads;
+
+VLPET_API size_t vlpet_k3_fwd_workspace_bytes(const VlpetK3Desc* desc);
+VLPET_API size_t vlpet_k3_bwd_workspace_bytes(const VlpetK3Desc* desc);
+/* pos [M,4] (x1,x2,y1,y2); img_ids / obj_ids int64 [M] or NULL.
+ * save (fp32, >= vlpet_k3_save_floats(desc) floats) keeps the pre-norm projections for the backward. */
+VLPET_API size_t vlpet_k3_save_floats(const VlpetK3Desc* desc);
+VLPET_API int vlpet_k3_fwd(const VlpetK3Desc* desc, const void* feats, const void* pos, const int64_t* img_ids,
+                 const int64_t* obj_ids, const VlpetK3Params* w, void* out, float* save, void* workspace,
+                 size_t workspace_bytes, void* stream);
+VLPET_API int vlpet_k3_bwd(const VlpetK3Desc* desc, const void* feats, const void* pos, const int64_t* img_ids,
+                 const void* dout, const VlpetK3Params* w, const float* save, void* dfeats /* may be NULL */,
+                 const VlpetK3Grads* g, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- PET parameter/gradient bucket helpers (rows a9 / C1 of SURVEY §8) -------------------------------- */
+/* dst_bf16[i] = bf16(src_f32[i]) : one launch refreshes the bf16 shadow of the whole flat PET bucket.    */
+VLPET_API int vlpet_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* Fused AdamW on a flat fp32 bucket (transformers.optimization.AdamW semantics used at trainer_base.py:633:
+ * decoupled weight decay, bias correction on); wd_mask (uint8 per 1024-element block, may be NULL = all
+ * decayed) selects the no-decay group ("bias", "LayerNorm.weight": trainer_base.py:640-660).
+ * grad_scale multiplies the gradient first (1/world_size and/or the clip factor).                        */
+VLPET_API int vlpet_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const uint8_t* wd_mask,
+                     int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                     const float* grad_scale_dev /* device scalar or NULL */, void* bf16_shadow /* or NULL */,
+                     void* stream);
+/* sum of squares of a flat fp32 buffer accumulated into *out_dev (device scalar; caller zeroes it)       */
+VLPET_API int vlpet_sumsq(const float* x, int64_t n, float* out_dev, void* stream);
+
+/* ---- misc ---------------------------------------------------------------------------------------------- */
+VLPET_API int vlpet_version(void);
+VLPET_API const char* vlpet_last_error(void);
+/* number of kernels this library has launched in this process (all streams); for bench.py's gpu_launches */
+VLPET_API uint64_t vlpet_launch_count(void);
+/* device info the host side needs: returns 0 and fills sm_count / cc_major / cc_minor */
+VLPET_API int vlpet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLPET_H_ */

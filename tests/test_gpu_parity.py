@@ -1,0 +1,300 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI of libvlpet.so via
+vlpet_b200's autograd functions and is compared with the oracle / the golden vectors of the reference.
+
+Tolerances (north_star): fp32 path 1e-5 relative; bf16 path 1e-3 relative.  "relative" = Frobenius-norm relative
+error.  For bf16 the oracle is evaluated in fp64 on the bf16-rounded inputs/weights and its result is rounded to
+bf16 for activation-typed outputs (the final rounding alone is ~8e-4 Frobenius, so comparing against the unrounded
+fp64 result would test nothing but the output format); fp32 weight gradients are compared unrounded.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pet_oracle as O
+from tests.helpers import golden_files, k1_case, load, rel
+
+pytestmark = pytest.mark.gpu
+TOL_F32 = 1e-5
+TOL_BF16 = 1e-3
+
+
+@pytest.fixture(scope="module")
+def V():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import vlpet_b200
+    return vlpet_b200
+
+
+def dev(a, dtype):
+    return torch.tensor(np.asarray(a), dtype=dtype, device="cuda")
+
+
+def bf16_round(a):
+    return torch.tensor(np.asarray(a), dtype=torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
+
+
+def gate_param_list(p, gate):
+    if gate == "large":
+        return ["Gd", "gbd", "Gu", "gbu"]
+    if gate in ("middle_x", "small"):
+        return ["gw", "gb"]
+    if gate == "middle_y":
+        return ["gz"]
+    return []
+
+
+def run_k1(V, x1, x2, dout, p, cfg, heads, dtype, impl, shape3):
+    """Run fwd+bwd through vlpet_b200.gated_pet; returns (out, dx1, dx2, grads dict) as float64 numpy."""
+    r = p["Wd"].shape[0]
+    hr = r // heads
+    tx1 = dev(x1, dtype).reshape(shape3).requires_grad_()
+    tx2 = dev(x2, dtype).reshape(shape3).requires_grad_()
+    P = {k: dev(np.atleast_1d(v), dtype).requires_grad_() for k, v in p.items() if k not in ("Wd", "bd")}
+    down_ws = [dev(p["Wd"][h * hr:(h + 1) * hr], dtype).requires_grad_() for h in range(heads)]
+    down_bs = [dev(p["bd"][h * hr:(h + 1) * hr], dtype).requires_grad_() for h in range(heads)]
+    gnames = gate_param_list(p, cfg.gate)
+    scfg = V.PetSiteConfig(gate=cfg.gate, add_gate=cfg.add_gate, s=cfg.s, alpha=cfg.alpha, kappa=cfg.kappa, impl=impl)
+    out = V.gated_pet(tx1, tx2, down_ws, down_bs, P["Wu"], P["bu"], [P[k] for k in gnames], scfg)
+    out.backward(dev(dout, dtype).reshape(shape3))
+    torch.cuda.synchronize()
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    gr = {"Wd": np.concatenate([f(w.grad) for w in down_ws]), "bd": np.concatenate([f(b.grad) for b in down_bs]),
+          "Wu": f(P["Wu"].grad), "bu": f(P["bu"].grad)}
+    for k in gnames:
+        gr[k] = f(P[k].grad).reshape(np.shape(p[k]))
+    d = x1.shape[-1]
+    return f(out).reshape(-1, d), f(tx1.grad).reshape(-1, d), f(tx2.grad).reshape(-1, d), gr
+
+
+# ------------------------------------------------------------------------------------------------ K1, fp32 vs golden
+@pytest.mark.parametrize("path", golden_files("k1_"), ids=os.path.basename)
+def test_k1_fp32_matches_reference_golden(V, path):
+    g = load(path)
+    x1, x2, dout, p, cfg = k1_case(g)
+    B, L, d = int(g["meta_B"]), int(g["meta_L"]), int(g["meta_d"])
+    out, dx1, dx2, gr = run_k1(V, x1, x2, dout, p, cfg, int(g["meta_heads"]), torch.float32, "auto", (B, L, d))
+    assert rel(out, g["out"].reshape(out.shape)) < TOL_F32
+    assert rel(dx1, g["dx1"].reshape(dx1.shape)) < TOL_F32
+    assert rel(dx2, g["dx2"].reshape(dx2.shape)) < TOL_F32
+    for k, v in gr.items():
+        assert rel(v, g["d" + k].reshape(np.shape(v))) < TOL_F32, k
+
+
+# ------------------------------------------------------------------------------------------------ K1, bf16
+def oracle_bf16(x1, x2, dout, p, cfg):
+    x1r, x2r, dor = bf16_round(x1), bf16_round(x2), bf16_round(dout)
+    pr = {k: bf16_round(v).reshape(np.shape(v)) for k, v in p.items()}
+    out, cache = O.gated_pet_fwd(x1r, x2r, pr, cfg)
+    dx1, dx2, gr = O.gated_pet_bwd(dor, pr, cfg, cache)
+    return out, dx1, dx2, gr
+
+
+@pytest.mark.parametrize("impl", ["generic", "auto"])
+@pytest.mark.parametrize("path", golden_files("k1_"), ids=os.path.basename)
+def test_k1_bf16_matches_oracle(V, path, impl):
+    g = load(path)
+    x1, x2, dout, p, cfg = k1_case(g)
+    B, L, d = int(g["meta_B"]), int(g["meta_L"]), int(g["meta_d"])
+    out, dx1, dx2, gr = run_k1(V, x1, x2, dout, p, cfg, int(g["meta_heads"]), torch.bfloat16, impl, (B, L, d))
+    o_out, o_dx1, o_dx2, o_gr = oracle_bf16(x1, x2, dout, p, cfg)
+    assert rel(out, bf16_round(o_out)) < TOL_BF16
+    assert rel(dx1, bf16_round(o_dx1)) < TOL_BF16
+    assert rel(dx2, bf16_round(o_dx2)) < TOL_BF16
+    for k, v in gr.items():
+        assert rel(v, o_gr[k].reshape(np.shape(v))) < TOL_BF16, k
+
+
+def random_large_case(rng, M, d, r, rg, trained_like=True):
+    ws, bs = (0.05, 0.02) if trained_like else (0.02, 0.0)
+    p = {"Wd": rng.standard_normal((r, d)) * ws, "bd": rng.standard_normal(r) * bs,
+         "Wu": rng.standard_normal((d, r)) * ws, "bu": rng.standard_normal(d) * bs,
+         "Gd": rng.standard_normal((rg, d)) * ws, "gbd": rng.standard_normal(rg) * bs,
+         "Gu": rng.standard_normal((d, rg)) * ws, "gbu": rng.standard_normal(d) * bs}
+    return rng.standard_normal((M, d)), 0.5 * rng.standard_normal((M, d)), rng.standard_normal((M, d)), p
+
+
+@pytest.mark.parametrize("M,d,r,rg,add_gate,s", [
+    (1, 768, 96, 96, False, 1.0),          # a single token (one partial tile)
+    (129, 768, 96, 96, False, 1.0),        # one full + one 1-row tile
+    (1000, 768, 96, 96, False, 0.3),       # T5-style scaling
+    (777, 768, 96, 96, True, 1.0),         # add-gate
+    (300, 768, 48, 96, False, 1.0),        # r != rg, padded rank
+    (260, 768, 128, 128, False, 1.0),
+    (515, 512, 64, 32, False, 1.0),        # video-feature width / other d
+    (200, 64, 16, 8, False, 1.0),
+    (148 * 128 * 2 + 77, 768, 96, 96, False, 1.0),   # > 2 tiles per SM: exercises ring wrap-around across tiles
+])
+def test_k1_fused_forward_matches_oracle(V, M, d, r, rg, add_gate, s):
+    assert V.fwd_is_fused(M, d, r, rg), "fused tcgen05 kernel must cover this shape"
+    rng = np.random.default_rng(M + d + r)
+    x1, x2, _, p = random_large_case(rng, M, d, r, rg)
+    cfg = O.PetConfig(gate="large", add_gate=add_gate, s=s)
+    bf = torch.bfloat16
+    scfg = V.PetSiteConfig(gate="large", add_gate=add_gate, s=s, impl="fused")
+    with torch.no_grad():
+        out = V.gated_pet(dev(x1, bf), dev(x2, bf), [dev(p["Wd"], bf)], [dev(p["bd"], bf)], dev(p["Wu"], bf),
+                          dev(p["bu"], bf), [dev(p[k], bf) for k in ("Gd", "gbd", "Gu", "gbu")], scfg)
+        gen = V.gated_pet(dev(x1, bf), dev(x2, bf), [dev(p["Wd"], bf)], [dev(p["bd"], bf)], dev(p["Wu"], bf),
+                          dev(p["bu"], bf), [dev(p[k], bf) for k in ("Gd", "gbd", "Gu", "gbu")],
+                          V.PetSiteConfig(gate="large", add_gate=add_gate, s=s, impl="generic"))
+    torch.cuda.synchronize()
+    out = out.to(torch.float64).cpu().numpy()
+    gen = gen.to(torch.float64).cpu().numpy()
+    rows = np.unique(np.concatenate([np.arange(min(M, 300)), np.arange(max(0, M - 300), M),
+                                     rng.integers(0, M, size=min(M, 2000))]))   # token-wise op: check a row sample
+    pr = {k: bf16_round(v).reshape(np.shape(v)) for k, v in p.items()}
+    ref, _ = O.gated_pet_fwd(bf16_round(x1[rows]), bf16_round(x2[rows]), pr, cfg)
+    assert rel(out[rows], bf16_round(ref)) < TOL_BF16
+    assert rel(gen[rows], bf16_round(ref)) < TOL_BF16
+    assert rel(out, gen) < TOL_BF16          # every row: fused vs generic CUDA path
+
+
+def test_k1_full_size_properties(V):
+    """BASELINE target shape B=300, L=320, d=768, r=96 (M=96000): token-wise independence (a row permutation of
+    the inputs permutes the outputs), oracle parity on a row sample, and all-finite output."""
+    M, d, r = 300 * 320, 768, 96
+    g = torch.Generator(device="cuda").manual_seed(0)
+    bf = torch.bfloat16
+    x1 = torch.randn(M, d, device="cuda", generator=g).to(bf)
+    x2 = (0.5 * torch.randn(M, d, device="cuda", generator=g)).to(bf)
+    mk = lambda *sh, std: (torch.randn(*sh, device="cuda", generator=g) * std).to(bf)  # noqa: E731
+    Wd, bd, Wu, bu = mk(r, d, std=0.05), mk(r, std=0.02), mk(d, r, std=0.05), mk(d, std=0.02)
+    Gd, gbd, Gu, gbu = mk(r, d, std=0.05), mk(r, std=0.02), mk(d, r, std=0.05), mk(d, std=0.02)
+    scfg = V.PetSiteConfig(gate="large", impl="fused")
+    with torch.no_grad():
+        out = V.gated_pet(x1.view(300, 320, d), x2.view(300, 320, d), [Wd], [bd], Wu, bu, [Gd, gbd, Gu, gbu], scfg).view(M, d)
+        perm = torch.randperm(M, device="cuda", generator=g)
+        outp = V.gated_pet(x1[perm].contiguous(), x2[perm].contiguous(), [Wd], [bd], Wu, bu, [Gd, gbd, Gu, gbu], scfg)
+    assert torch.isfinite(out.float()).all()
+    assert torch.equal(outp, out[perm])        # bit-exact: every token is computed independently of its tile
+    rows = torch.randint(0, M, (1500,), device="cuda", generator=g)
+    f = lambda t: t.to(torch.float64).cpu().numpy()  # noqa: E731
+    p = dict(Wd=f(Wd), bd=f(bd), Wu=f(Wu), bu=f(bu), Gd=f(Gd), gbd=f(gbd), Gu=f(Gu), gbu=f(gbu))
+    ref, _ = O.gated_pet_fwd(f(x1[rows]), f(x2[rows]), p, O.PetConfig(gate="large"))
+    assert rel(f(out[rows]), bf16_round(ref)) < TOL_BF16
+
+
+def test_k1_dropout_stream(V):
+    """Dropout sits between gate and residual (modeling_bart.py:1259): kept fraction, 1/(1-p) scaling, forward /
+    backward mask agreement, fused == generic for the same seed."""
+    M, d, r = 640, 768, 96
+    rng = np.random.default_rng(5)
+    x1, x2, dout, p = random_large_case(rng, M, d, r, r)
+    bf = torch.bfloat16
+    import vlpet_b200.functional as F_
+    args = lambda: (dev(x1, bf).requires_grad_(), dev(x2, bf).requires_grad_(), dev(p["Wd"], bf), dev(p["bd"], bf),  # noqa: E731
+                    dev(p["Wu"], bf), dev(p["bu"], bf), dev(p["Gd"], bf), dev(p["gbd"], bf), dev(p["Gu"], bf), dev(p["gbu"], bf))
+    outs = {}
+    for impl in ("fused", "generic"):
+        a = args()
+        cfg = V.PetSiteConfig(gate="large", p_drop=0.1, impl=impl)
+        out = F_.GatedPETFn.apply(cfg, 1234, 0, 1, *a)
+        base = F_.GatedPETFn.apply(V.PetSiteConfig(gate="large", impl=impl), 0, 0, 1, *a)
+        delta = (out.float() - a[0].float())               # dropout(s*h)
+        h = (base.float() - a[0].float())                  # s*h
+        dropped = (delta == 0) & (h.abs() > 1e-2)
+        kept = (h.abs() > 1e-2) & ~dropped
+        frac = dropped.sum().item() / max(1, (h.abs() > 1e-2).sum().item())
+        assert abs(frac - 0.1) < 0.01, frac
+        ratio = (delta[kept] / h[kept]).median().item()
+        assert abs(ratio - 1.0 / 0.9) < 0.02, ratio
+        out.backward(dev(dout, bf))
+        outs[impl] = (out.detach().float(), h.detach(), dropped)
+    assert rel(outs["fused"][0].cpu().numpy(), outs["generic"][0].cpu().numpy()) < TOL_BF16
+    # same seed => identical mask in both implementations (compared where s*h is clearly non-zero in both)
+    big = (outs["fused"][1].abs() > 5e-2) & (outs["generic"][1].abs() > 5e-2)
+    assert torch.equal(outs["fused"][2][big], outs["generic"][2][big])
+    # a different seed gives a different mask; the same seed reproduces it (the backward relies on this)
+    a = args()
+    cfg = V.PetSiteConfig(gate="large", p_drop=0.1, impl="fused")
+    o1 = F_.GatedPETFn.apply(cfg, 1234, 0, 1, *a)
+    o2 = F_.GatedPETFn.apply(cfg, 1234, 0, 1, *a)
+    o3 = F_.GatedPETFn.apply(cfg, 99, 0, 1, *a)
+    assert torch.equal(o1, o2) and not torch.equal(o1, o3)
+
+
+# ------------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)])
+@pytest.mark.parametrize("path", golden_files("k2_"), ids=os.path.basename)
+def test_k2_matches_reference_golden(V, path, dtype, tol):
+    g = load(path)
+    d = int(g["meta_d"])
+    sf = float(g["meta_sf"])
+    rnd = (lambda a: a) if dtype == torch.float32 else bf16_round
+    p = {k: rnd(g[k]) for k in ("Wd", "bd", "Wu", "bu")}
+    ref_out, c = O.vpa_fwd(rnd(g["kv"]).reshape(-1, d), rnd(g["y"]).reshape(-1, d), p, sf)
+    ref_dkv, _, ref_gr = O.vpa_bwd(rnd(g["dout"]).reshape(-1, d), p, c, sf)
+    kv = dev(g["kv"], dtype).requires_grad_()
+    y = dev(g["y"], dtype).requires_grad_()
+    P = {k: dev(g[k], dtype).requires_grad_() for k in ("Wd", "bd", "Wu", "bu")}
+    out = V.vpa(kv, y, P["Wd"], P["bd"], P["Wu"], P["bu"], sf)
+    out.backward(dev(g["dout"], dtype))
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    act = (lambda a: a) if dtype == torch.float32 else bf16_round
+    assert rel(f(out).reshape(-1, d), act(ref_out)) < tol
+    assert rel(f(kv.grad).reshape(-1, d), act(ref_dkv)) < tol
+    assert rel(f(y.grad), rnd(g["dout"])) < tol
+    for k in ("Wd", "bd", "Wu", "bu"):
+        assert rel(f(P[k].grad), ref_gr[k]) < tol, k
+
+
+def test_k2_adapter_controller_api(V):
+    """Same constructor / forward / aliasing contract as the reference AdapterController (adapter_controller.py)."""
+    g = load(golden_files("k2_vpa_d64")[0])
+    cfg = V.AdapterConfig(tasks=["vqa", "gqa", "nlvr", "caption"], d_model=64, input_dim=64, use_single_adapter=True,
+                          use_adapter_down_dim=True, adapter_down_dim=16, use_parallel_adapter=True)
+    ctrl = V.AdapterController(cfg).cuda()
+    assert sorted(ctrl.state_dict().keys()) == list(g["meta_state_keys"])
+    assert [n for n, _ in ctrl.named_parameters()] == list(g["meta_param_names"])
+    ad = ctrl.adapters["vqa"]
+    with torch.no_grad():
+        ad.down_sampler.weight.copy_(dev(g["Wd"], torch.float32)); ad.down_sampler.bias.copy_(dev(g["bd"], torch.float32))
+        ad.up_sampler.weight.copy_(dev(g["Wu"], torch.float32)); ad.up_sampler.bias.copy_(dev(g["bu"], torch.float32))
+    out = ctrl(dev(g["kv"], torch.float32), "gqa", y=dev(g["y"], torch.float32))
+    assert rel(out.detach().cpu().numpy(), g["out"]) < TOL_F32
+    with pytest.raises(KeyError):
+        ctrl(dev(g["kv"], torch.float32), "not_a_task", y=dev(g["y"], torch.float32))
+    with pytest.raises(TypeError):
+        ctrl(dev(g["kv"], torch.float32), "vqa")
+
+
+# ------------------------------------------------------------------------------------------------ K3
+@pytest.mark.parametrize("path", golden_files("k3_"), ids=os.path.basename)
+def test_k3_matches_reference_golden(V, path):
+    g = load(path)
+    rms = str(g["meta_kind"]) == "t5"
+    t32 = torch.float32
+    names = ["Wf", "bf", "ln_f_w", "ln_f_b", "Wp", "bp", "ln_p_w", "ln_p_b", "E_img"]
+    P = {k: (dev(g[k], t32).requires_grad_() if k in g else None) for k in names}
+    E_obj = dev(g["E_obj"], t32)
+    feats = dev(g["feats"], t32).requires_grad_()
+    img = torch.tensor(g["img_ids"], device="cuda") if "img_ids" in g else None
+    obj = torch.tensor(g["obj_ids"], device="cuda") if "obj_ids" in g else None
+    out = V.visual_projection(feats, dev(g["pos"], t32), img, obj, *[P[k] for k in names], E_obj, rms=rms,
+                              eps=float(g["meta_eps"]))
+    out.backward(dev(g["dout"], t32))
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    assert rel(f(out), g["out"]) < TOL_F32
+    assert rel(f(feats.grad), g["dfeats"]) < TOL_F32
+    for k in names:
+        if P[k] is not None:
+            assert rel(f(P[k].grad), g["d" + k]) < TOL_F32, k
+
+
+# ------------------------------------------------------------------------------------------------ misc C-ABI behaviour
+def test_abi_errors_are_loud(V):
+    x = torch.zeros(4, 64, device="cuda")
+    with pytest.raises(V.VlpetError):       # fused requested for a shape/dtype it does not cover
+        V.gated_pet(x, x, [torch.zeros(8, 64, device="cuda")], [torch.zeros(8, device="cuda")],
+                    torch.zeros(64, 8, device="cuda"), torch.zeros(64, device="cuda"), [],
+                    V.PetSiteConfig(gate="none", impl="fused"))
+    with pytest.raises(ValueError):
+        V.gated_pet(x, x[:2], [torch.zeros(8, 64, device="cuda")], [torch.zeros(8, device="cuda")],
+                    torch.zeros(64, 8, device="cuda"), torch.zeros(64, device="cuda"), [], V.PetSiteConfig(gate="none"))
+    n0 = V.launch_count()
+    V.gated_pet(x, x, [torch.zeros(8, 64, device="cuda")], [torch.zeros(8, device="cuda")],
+                torch.zeros(64, 8, device="cuda"), torch.zeros(64, device="cuda"), [], V.PetSiteConfig(gate="none"))
+    assert V.launch_count() > n0

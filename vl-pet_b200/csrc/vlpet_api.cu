@@ -1,0 +1,242 @@
+// C-ABI entry points of libvlpet.so (declared in include/vlpet.h): argument validation, dispatch between the
+// fused sm_100a kernels and the generic CUDA-core kernels, and the flat-bucket helpers (cast / AdamW / sumsq).
+#include "vlpet_common.cuh"
+
+namespace vlpet {
+std::atomic<uint64_t> g_launches{0};
+char* tls_error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+namespace {
+int check_k1(const VlpetK1Desc* D, const VlpetK1Params* w) {
+  if (!D || !w) return fail(VLPET_E_BADARG, "k1: null desc/params");
+  if (D->M <= 0 || D->d <= 0 || D->r <= 0) return fail(VLPET_E_BADARG, "k1: M, d, r must be positive");
+  if (D->dtype != VLPET_F32 && D->dtype != VLPET_BF16) return fail(VLPET_E_BADARG, "k1: bad dtype %d", D->dtype);
+  if (D->gate < VLPET_GATE_NONE || D->gate > VLPET_GATE_SMALL) return fail(VLPET_E_BADARG, "k1: bad gate %d", D->gate);
+  if (!w->Wd || !w->bd || !w->Wu || !w->bu) return fail(VLPET_E_BADARG, "k1: adapter weights missing");
+  if (D->gate == VLPET_GATE_LARGE && (D->rg <= 0 || !w->Gd || !w->gbd || !w->Gu || !w->gbu))
+    return fail(VLPET_E_BADARG, "k1: large gate needs rg > 0 and Gd/gbd/Gu/gbu");
+  if ((D->gate == VLPET_GATE_MIDDLE_X || D->gate == VLPET_GATE_SMALL) && (!w->gw || !w->gb))
+    return fail(VLPET_E_BADARG, "k1: middle_x/small gate needs gw/gb");
+  if (D->gate == VLPET_GATE_MIDDLE_Y && !w->gz) return fail(VLPET_E_BADARG, "k1: middle_y gate needs gz");
+  if (!(D->p_drop >= 0.f && D->p_drop < 1.f)) return fail(VLPET_E_BADARG, "k1: p_drop must be in [0,1)");
+  if (D->gate == VLPET_GATE_SMALL && (D->L <= 0 || D->M % D->L != 0))
+    return fail(VLPET_E_BADARG, "k1: small gate needs L > 0 dividing M");
+  return 0;
+}
+bool use_fused_fwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && fused_k1_fwd_supported(D); }
+}  // namespace
+}  // namespace vlpet
+
+using namespace vlpet;
+
+extern "C" {
+
+int vlpet_version(void) { return VLPET_VERSION; }
+const char* vlpet_last_error(void) { return tls_error_buffer(); }
+uint64_t vlpet_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int vlpet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  int dev = 0;
+  VLPET_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  VLPET_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return 0;
+}
+
+// ---- K1 ----------------------------------------------------------------------------------------------------
+int vlpet_k1_fwd_is_fused(const VlpetK1Desc* D) { return D && use_fused_fwd(*D) ? 1 : 0; }
+int vlpet_k1_bwd_is_fused(const VlpetK1Desc*) { return 0; }
+
+size_t vlpet_k1_fwd_workspace_bytes(const VlpetK1Desc* D) {
+  if (!D) return 0;
+  return use_fused_fwd(*D) ? fused_k1_fwd_ws(*D) : generic_k1_fwd_ws(*D);
+}
+size_t vlpet_k1_bwd_workspace_bytes(const VlpetK1Desc* D) { return D ? generic_k1_bwd_ws(*D) : 0; }
+
+int vlpet_k1_fwd(const VlpetK1Desc* D, const void* x1, const void* x2, const VlpetK1Params* w, void* out, void* ws,
+                 size_t ws_bytes, void* stream) {
+  VLPET_TRY(check_k1(D, w));
+  if (!x1 || !x2 || !out) return fail(VLPET_E_BADARG, "k1_fwd: null activation pointer");
+  if (!aligned16(x1) || !aligned16(x2) || !aligned16(out)) return fail(VLPET_E_ALIGN, "k1_fwd: activations must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_fused_fwd(*D)) return fused_k1_fwd(*D, x1, x2, *w, out, ws, ws_bytes, st);
+  if (D->impl == VLPET_IMPL_FUSED)
+    return fail(VLPET_E_UNSUPPORTED, "k1_fwd: fused kernel does not cover d=%d r=%d rg=%d gate=%d dtype=%d", D->d, D->r,
+                D->rg, D->gate, D->dtype);
+  return generic_k1_fwd(*D, x1, x2, *w, out, ws, ws_bytes, st);
+}
+
+int vlpet_k1_bwd(const VlpetK1Desc* D, const void* x1, const void* x2, const void* dout, const VlpetK1Params* w,
+                 void* dx1, void* dx2, const VlpetK1Grads* g, void* ws, size_t ws_bytes, void* stream) {
+  VLPET_TRY(check_k1(D, w));
+  if (!x1 || !x2 || !dout || !dx1 || !dx2 || !g) return fail(VLPET_E_BADARG, "k1_bwd: null pointer");
+  if (!aligned16(x1) || !aligned16(x2) || !aligned16(dout) || !aligned16(dx1) || !aligned16(dx2))
+    return fail(VLPET_E_ALIGN, "k1_bwd: activations must be 16-byte aligned");
+  if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k1_bwd: no fused backward kernel yet");
+  return generic_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// ---- K2 ----------------------------------------------------------------------------------------------------
+static int check_k2(const VlpetK2Desc* D, const VlpetK2Params* w) {
+  if (!D || !w) return fail(VLPET_E_BADARG, "k2: null desc/params");
+  if (D->M <= 0 || D->d <= 0 || D->r <= 0) return fail(VLPET_E_BADARG, "k2: M, d, r must be positive");
+  if (D->dtype != VLPET_F32 && D->dtype != VLPET_BF16) return fail(VLPET_E_BADARG, "k2: bad dtype %d", D->dtype);
+  if (!w->Wd || !w->bd || !w->Wu || !w->bu) return fail(VLPET_E_BADARG, "k2: weights missing");
+  if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k2: no fused kernel yet");
+  return 0;
+}
+size_t vlpet_k2_fwd_workspace_bytes(const VlpetK2Desc* D) { return D ? generic_k2_fwd_ws(*D) : 0; }
+size_t vlpet_k2_bwd_workspace_bytes(const VlpetK2Desc* D) { return D ? generic_k2_bwd_ws(*D) : 0; }
+int vlpet_k2_fwd(const VlpetK2Desc* D, const void* kv, const void* y, const VlpetK2Params* w, void* out, void* ws,
+                 size_t ws_bytes, void* stream) {
+  VLPET_TRY(check_k2(D, w));
+  if (!kv || !out) return fail(VLPET_E_BADARG, "k2_fwd: null activation pointer"); /* y may be NULL: no residual */
+  return generic_k2_fwd(*D, kv, y, *w, out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int vlpet_k2_bwd(const VlpetK2Desc* D, const void* kv, const void* dout, const VlpetK2Params* w, void* dkv,
+                 const VlpetK2Grads* g, void* ws, size_t ws_bytes, void* stream) {
+  VLPET_TRY(check_k2(D, w));
+  if (!kv || !dout || !g) return fail(VLPET_E_BADARG, "k2_bwd: null pointer");
+  return generic_k2_bwd(*D, kv, dout, *w, dkv, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// ---- K3 ----------------------------------------------------------------------------------------------------
+static int check_k3(const VlpetK3Desc* D, const VlpetK3Params* w) {
+  if (!D || !w) return fail(VLPET_E_BADARG, "k3: null desc/params");
+  if (D->M <= 0 || D->d <= 0 || D->F <= 0 || D->N <= 0 || D->V <= 0 || D->n_img <= 0)
+    return fail(VLPET_E_BADARG, "k3: M, N, F, d, V, n_img must be positive");
+  if (D->dtype != VLPET_F32 && D->dtype != VLPET_BF16) return fail(VLPET_E_BADARG, "k3: bad dtype %d", D->dtype);
+  if (!w->Wf || !w->bf || !w->ln_f_w || !w->Wp || !w->bp || !w->ln_p_w || !w->E_img || !w->E_obj)
+    return fail(VLPET_E_BADARG, "k3: weights missing");
+  if (!D->rms && (!w->ln_f_b || !w->ln_p_b)) return fail(VLPET_E_BADARG, "k3: LayerNorm biases missing");
+  if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k3: no fused kernel yet");
+  return 0;
+}
+size_t vlpet_k3_fwd_workspace_bytes(const VlpetK3Desc* D) { return D ? generic_k3_fwd_ws(*D) : 0; }
+size_t vlpet_k3_bwd_workspace_bytes(const VlpetK3Desc* D) { return D ? generic_k3_bwd_ws(*D) : 0; }
+size_t vlpet_k3_save_floats(const VlpetK3Desc* D) { return D ? (size_t)D->M * D->d : 0; }
+int vlpet_k3_fwd(const VlpetK3Desc* D, const void* feats, const void* pos, const int64_t* img_ids,
+                 const int64_t* obj_ids, const VlpetK3Params* w, void* out, float* save, void* ws, size_t ws_bytes,
+                 void* stream) {
+  VLPET_TRY(check_k3(D, w));
+  if (!feats || !pos || !out || !save) return fail(VLPET_E_BADARG, "k3_fwd: null pointer");
+  return generic_k3_fwd(*D, feats, pos, img_ids, obj_ids, *w, out, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int vlpet_k3_bwd(const VlpetK3Desc* D, const void* feats, const void* pos, const int64_t* img_ids, const void* dout,
+                 const VlpetK3Params* w, const float* save, void* dfeats, const VlpetK3Grads* g, void* ws,
+                 size_t ws_bytes, void* stream) {
+  VLPET_TRY(check_k3(D, w));
+  if (!feats || !pos || !dout || !save || !g) return fail(VLPET_E_BADARG, "k3_bwd: null pointer");
+  return generic_k3_bwd(*D, feats, pos, img_ids, dout, *w, save, dfeats, *g, ws, ws_bytes,
+                        static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+// ---- flat-bucket helpers -----------------------------------------------------------------------------------
+namespace vlpet {
+namespace flat {
+__global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    float4 v = *reinterpret_cast<const float4*>(src + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst + i) = o;
+  }
+  // tail (n % 4) handled by the first threads of the grid
+  int64_t tail0 = n / 4 * 4;
+  int64_t t = tail0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = __float2bfloat16_rn(src[t]);
+}
+
+// AdamW as transformers.optimization.AdamW (used at trainer_base.py:633): m,v update; p -= lr*sqrt(bc2)/bc1 * m/(sqrt(v)+eps);
+// then decoupled decay p -= lr*wd*p.
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, const uint8_t* __restrict__ wd_mask, int64_t n, float lr, float b1,
+                             float b2, float eps, float wd, float step_size, const float* __restrict__ gscale,
+                             __nv_bfloat16* __restrict__ shadow) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float gs = gscale ? *gscale : 1.0f;
+  for (; i < n; i += stride) {
+    float gi = g[i] * gs;
+    float mi = b1 * m[i] + (1.0f - b1) * gi;
+    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    float pi = p[i];
+    pi -= step_size * mi / (sqrtf(vi) + eps);
+    float w = wd_mask ? (wd_mask[i >> 10] ? wd : 0.0f) : wd;
+    pi -= lr * w * pi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (; i < n; i += stride) acc += x[i] * x[i];
+  acc = warp_sum(acc);
+  __shared__ float s[8];
+  if (threadIdx.x % 32 == 0) s[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < blockDim.x / 32 ? s[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+inline int flat_blocks(int64_t n, int per_thread) {
+  int64_t b = (n + 256LL * per_thread - 1) / (256LL * per_thread);
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+}  // namespace flat
+}  // namespace vlpet
+using namespace vlpet::flat;
+
+extern "C" {
+int vlpet_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (!src || !dst || n < 0) return fail(VLPET_E_BADARG, "cast: bad arguments");
+  if (n == 0) return 0;
+  if (!aligned16(src) || (reinterpret_cast<uintptr_t>(dst) & 7u)) return fail(VLPET_E_ALIGN, "cast: misaligned buffers");
+  cast_kernel<<<flat_blocks(n, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+
+int vlpet_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const uint8_t* wd_mask,
+                     int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                     const float* grad_scale_dev, void* bf16_shadow, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return fail(VLPET_E_BADARG, "adamw: bad arguments");
+  if (n == 0) return 0;
+  double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  float step_size = (float)(lr * sqrt(bc2) / bc1);
+  adamw_kernel<<<flat_blocks(n, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, wd_mask, n, lr, beta1, beta2, eps, weight_decay, step_size, grad_scale_dev,
+      static_cast<__nv_bfloat16*>(bf16_shadow));
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+
+int vlpet_sumsq(const float* x, int64_t n, float* out_dev, void* stream) {
+  if (!x || !out_dev || n < 0) return fail(VLPET_E_BADARG, "sumsq: bad arguments");
+  if (n == 0) return 0;
+  sumsq_kernel<<<flat_blocks(n, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out_dev);
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+}  // extern "C"

@@ -1,0 +1,143 @@
+// Shared helpers for libvlpet.so (sm_100a only).  No torch types anywhere in this library.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/vlpet.h"
+
+namespace vlpet {
+
+// ---- error plumbing ------------------------------------------------------------------------------------
+char* tls_error_buffer();  // 512 bytes, thread local (vlpet_api.cu)
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tls_error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define VLPET_CUDA_OK(expr)                                                                           \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return ::vlpet::fail((int)_e, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                                 \
+  } while (0)
+#define VLPET_LAUNCH_OK()                                                                                   \
+  do {                                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                                    \
+    if (_e != cudaSuccess)                                                                                  \
+      return ::vlpet::fail((int)_e, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__,   \
+                           __LINE__);                                                                       \
+    ::vlpet::count_launch();                                                                                \
+  } while (0)
+#define VLPET_TRY(expr)     \
+  do {                      \
+    int _r = (expr);        \
+    if (_r != 0) return _r; \
+  } while (0)
+
+inline size_t esize(int dtype) { return dtype == VLPET_BF16 ? 2 : 4; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace (256-byte granules)
+struct Arena {
+  char* base;
+  size_t cap, off;
+  Arena(void* p, size_t n) : base(static_cast<char*>(p)), cap(n), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T), 256);
+    char* r = base ? base + off : nullptr;
+    off += bytes;
+    return reinterpret_cast<T*>(r);
+  }
+  bool ok() const { return off <= cap && (base != nullptr || off == 0); }
+};
+
+// ---- device math ---------------------------------------------------------------------------------------
+// gelu_new = transformers.activations.NewGELUActivation: 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))
+__device__ __forceinline__ float gelu_new_f(float t) {
+  const float c = 0.7978845608028654f, k = 0.044715f;
+  return 0.5f * t * (1.0f + tanhf(c * (t + k * t * t * t)));
+}
+__device__ __forceinline__ float gelu_new_grad_f(float t) {
+  const float c = 0.7978845608028654f, k = 0.044715f;
+  float th = tanhf(c * (t + k * t * t * t));
+  return 0.5f * (1.0f + th) + 0.5f * t * (1.0f - th * th) * c * (1.0f + 3.0f * k * t * t);
+}
+__device__ __forceinline__ float sigmoid_f(float t) { return 1.0f / (1.0f + expf(-t)); }
+
+// Counter-based dropout: one splitmix64 hash per 4 consecutive elements, 16 bits per element.
+// keep(idx) = bits16 >= thr16 with thr16 = round(p * 65536); kept values are scaled by 1/(1-p).
+__device__ __forceinline__ uint64_t drop_hash4(uint64_t seed, uint64_t idx4) {
+  uint64_t z = idx4 + seed * 0x9E3779B97F4A7C15ull + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint32_t drop_thr16(float p) {
+  float t = p * 65536.0f + 0.5f;
+  return t <= 0.f ? 0u : (t >= 65535.f ? 65535u : (uint32_t)t);
+}
+// multiplicative mask value for element idx: 0 or inv_keep
+__device__ __forceinline__ float drop_scale(uint64_t seed, uint32_t thr16, float inv_keep, int64_t idx) {
+  if (thr16 == 0) return 1.0f;
+  uint64_t h = drop_hash4(seed, (uint64_t)idx >> 2);
+  uint32_t bits = (uint32_t)(h >> (16 * ((uint32_t)idx & 3u))) & 0xffffu;
+  return bits >= thr16 ? inv_keep : 0.0f;
+}
+
+__device__ __forceinline__ float ld_as_float(const void* p, int64_t i, bool bf16) {
+  return bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]) : static_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st_from_float(void* p, int64_t i, float v, bool bf16) {
+  if (bf16)
+    static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else
+    static_cast<float*>(p)[i] = v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- generic (CUDA-core) building blocks, vlpet_generic.cu --------------------------------------------------
+int generic_k1_fwd(const VlpetK1Desc&, const void* x1, const void* x2, const VlpetK1Params&, void* out, void* ws,
+                   size_t ws_bytes, cudaStream_t);
+int generic_k1_bwd(const VlpetK1Desc&, const void* x1, const void* x2, const void* dout, const VlpetK1Params&,
+                   void* dx1, void* dx2, const VlpetK1Grads&, void* ws, size_t ws_bytes, cudaStream_t);
+size_t generic_k1_fwd_ws(const VlpetK1Desc&);
+size_t generic_k1_bwd_ws(const VlpetK1Desc&);
+int generic_k2_fwd(const VlpetK2Desc&, const void* kv, const void* y, const VlpetK2Params&, void* out, void* ws,
+                   size_t ws_bytes, cudaStream_t);
+int generic_k2_bwd(const VlpetK2Desc&, const void* kv, const void* dout, const VlpetK2Params&, void* dkv,
+                   const VlpetK2Grads&, void* ws, size_t ws_bytes, cudaStream_t);
+size_t generic_k2_fwd_ws(const VlpetK2Desc&);
+size_t generic_k2_bwd_ws(const VlpetK2Desc&);
+int generic_k3_fwd(const VlpetK3Desc&, const void* feats, const void* pos, const int64_t* img_ids,
+                   const int64_t* obj_ids, const VlpetK3Params&, void* out, float* save, void* ws, size_t ws_bytes,
+                   cudaStream_t);
+int generic_k3_bwd(const VlpetK3Desc&, const void* feats, const void* pos, const int64_t* img_ids, const void* dout,
+                   const VlpetK3Params&, const float* save, void* dfeats, const VlpetK3Grads&, void* ws,
+                   size_t ws_bytes, cudaStream_t);
+size_t generic_k3_fwd_ws(const VlpetK3Desc&);
+size_t generic_k3_bwd_ws(const VlpetK3Desc&);
+
+// ---- fused sm_100a kernels (tcgen05 + TMA), vlpet_k1_sm100.cu ----------------------------------------------
+bool fused_k1_fwd_supported(const VlpetK1Desc&);
+size_t fused_k1_fwd_ws(const VlpetK1Desc&);
+int fused_k1_fwd(const VlpetK1Desc&, const void* x1, const void* x2, const VlpetK1Params&, void* out, void* ws,
+                 size_t ws_bytes, cudaStream_t);
+
+}  // namespace vlpet

@@ -1,0 +1,439 @@
+// K1 forward, fused, sm_100a: the granularity-controlled PET module with the "large" gate in ONE launch.
+//
+//   out = x1 + s * ((kappa*x2 + alpha*(gelu_new(x2 Wd^T + bd) Wu^T + bu)) (*|+) sigmoid(gelu_new(x1 Gd^T + gbd) Gu^T + gbu))
+//
+// (my_transformers/modeling_bart.py:1145-1155, 1195-1209, 1256-1260; T5: my_transformers/modeling_t5.py:777-824, 359-409)
+//
+// Design.  Persistent CTAs, one per SM, each walks 128-token tiles.  Per tile:
+//   phase A  (contraction over d):   A[128,R] = x2 Wd^T,  P[128,R] = x1 Gd^T        tcgen05.mma, fp32 accum in TMEM
+//   epilogue 1:                      z = gelu_new(A + bd), q = gelu_new(P + gbd)    TMEM -> regs -> bf16 -> swizzled smem
+//   phase B  (per 64-column chunk):  U = z Wu_n^T, T = q Gu_n^T                     tcgen05.mma, double-buffered TMEM
+//   epilogue 2:                      out_n = x1_n + s*(kappa*x2_n + alpha*(U+bu)) (*|+) sigmoid(T+gbu)   -> smem -> TMA store
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warp 2 = TMA-store issuer, warp 3 idle,
+// warps 4..11 = epilogue (two warpgroups; warp%4 selects the TMEM lane quarter).
+// Two smem rings fed by TMA: an x-ring (x1/x2 64-column chunks, used as MMA operands in phase A and as the residual
+// inputs + output staging in phase B) and a w-ring (weight chunks, always L2 hits).  Weights are padded to R rows /
+// columns by TMA out-of-bounds zero fill, so any r, rg <= R that is a multiple of 8 runs on the same instantiation.
+#include "sm100_ptx.cuh"
+#include "vlpet_common.cuh"
+
+namespace vlpet {
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int CH = 64;  // chunk width in elements: 64 bf16 = one 128-byte swizzle row
+constexpr int SX = 3;   // x-ring stages
+constexpr int SW = 2;   // w-ring stages
+constexpr int XCH_BYTES = TILE_M * CH * 2;  // 16 KB: one [128 x 64] bf16 chunk
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int TM_A = 0, TM_P = 128, TM_UT = 256;  // TMEM column offsets
+
+template <int R>
+struct Cfg {
+  static constexpr int KB = (R + 63) / 64;             // 64-wide K blocks of z / q
+  static constexpr int WA_BYTES = R * CH * 2;          // one [R x 64] weight chunk (phase A)
+  static constexpr int WB_BYTES = KB * CH * CH * 2;    // one [64 x (KB*64)] weight chunk (phase B)
+  static constexpr int WSLOT = (2 * WA_BYTES > 2 * WB_BYTES) ? 2 * WA_BYTES : 2 * WB_BYTES;
+  static constexpr int ZQ_BYTES = KB * XCH_BYTES;      // z (or q): KB blocks of [128 x 64]
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_W = OFF_X + SX * 2 * XCH_BYTES;
+  static constexpr int OFF_Z = OFF_W + SW * WSLOT;
+  static constexpr int OFF_Q = OFF_Z + ZQ_BYTES;
+  static constexpr int OFF_BAR = OFF_Q + ZQ_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // barriers + slack for the manual 1024-B alignment
+};
+
+struct Params {
+  int64_t M;
+  int d, r, rg;
+  int add_gate;
+  float s, alpha, kappa;
+  const __nv_bfloat16 *bd, *bu, *gbd, *gbu;
+  uint64_t seed;      // dropout stream (vlpet_common.cuh: drop_hash4)
+  uint32_t thr16;     // 0 = no dropout
+  float inv_keep;
+};
+
+// barrier slots (8 bytes each) inside the barrier block
+enum { B_XFULL = 0, B_XEMPTY = B_XFULL + SX, B_WFULL = B_XEMPTY + SX, B_WEMPTY = B_WFULL + SW, B_APFULL = B_WEMPTY + SW,
+       B_ZQFULL, B_UTFULL, B_UTEMPTY = B_UTFULL + 2, B_OUTRDY = B_UTEMPTY + 2, B_COUNT = B_OUTRDY + SX };
+
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float gelu_new_fast(float v) {
+  const float c = 0.7978845608028654f, ck = 0.7978845608028654f * 0.044715f;
+  float t = ptx::tanh_approx(v * fmaf(ck, v * v, c));
+  float hv = 0.5f * v;
+  return fmaf(hv, t, hv);
+}
+__device__ __forceinline__ float sigmoid_fast(float v) { return fmaf(0.5f, ptx::tanh_approx(0.5f * v), 0.5f); }
+
+template <int R>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
+                    const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_wd,
+                    const __grid_constant__ CUtensorMap tm_gd, const __grid_constant__ CUtensorMap tm_wu,
+                    const __grid_constant__ CUtensorMap tm_gu, const Params p) {
+  using C = Cfg<R>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::OFF_BAR;
+  auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
+  const uint32_t tmem_slot = bar_base + 8u * B_COUNT;  // 4 bytes: TMEM base address written by tcgen05.alloc
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const int nkc = p.d / CH;  // chunks along d (phase A: K chunks; phase B: N chunks)
+  const int64_t num_tiles = (p.M + TILE_M - 1) / TILE_M;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SX; ++i) { ptx::mbar_init(bar(B_XFULL + i), 1); ptx::mbar_init(bar(B_XEMPTY + i), 1); ptx::mbar_init(bar(B_OUTRDY + i), EPI_THREADS); }
+    for (int i = 0; i < SW; ++i) { ptx::mbar_init(bar(B_WFULL + i), 1); ptx::mbar_init(bar(B_WEMPTY + i), 1); }
+    ptx::mbar_init(bar(B_APFULL), 1);
+    ptx::mbar_init(bar(B_ZQFULL), EPI_THREADS);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(B_UTFULL + i), 1); ptx::mbar_init(bar(B_UTEMPTY + i), EPI_THREADS); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_out); ptx::prefetch_tmap(&tm_wd);
+    ptx::prefetch_tmap(&tm_gd); ptx::prefetch_tmap(&tm_wu); ptx::prefetch_tmap(&tm_gu);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t xi = 0, wi = 0;  // ring step counters
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = (int)(tile * TILE_M);
+        for (int ph = 0; ph < 2; ++ph) {
+          for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
+            const uint32_t sx = xi % SX, sw = wi % SW;
+            ptx::mbar_wait(bar(B_XEMPTY + sx), ((xi / SX) & 1) ^ 1);
+            const uint32_t xdst = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
+            ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), 2 * XCH_BYTES);
+            ptx::tma_load_2d(xdst, &tm_x1, c * CH, row0, bar(B_XFULL + sx));
+            ptx::tma_load_2d(xdst + XCH_BYTES, &tm_x2, c * CH, row0, bar(B_XFULL + sx));
+            ptx::mbar_wait(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1);
+            const uint32_t wdst = smem_base + C::OFF_W + sw * C::WSLOT;
+            if (ph == 0) {
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), 2 * C::WA_BYTES);
+              ptx::tma_load_2d(wdst, &tm_wd, c * CH, 0, bar(B_WFULL + sw));
+              ptx::tma_load_2d(wdst + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
+            } else {
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), 2 * C::WB_BYTES);
+#pragma unroll
+              for (int kb = 0; kb < C::KB; ++kb) {
+                ptx::tma_load_2d(wdst + kb * (CH * CH * 2), &tm_wu, kb * CH, c * CH, bar(B_WFULL + sw));
+                ptx::tma_load_2d(wdst + C::WB_BYTES + kb * (CH * CH * 2), &tm_gu, kb * CH, c * CH, bar(B_WFULL + sw));
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_A = ptx::umma_idesc_bf16_m128(R);
+      constexpr uint32_t IDESC_B = ptx::umma_idesc_bf16_m128(CH);
+      uint32_t xi = 0, wi = 0, ui = 0, ti = 0;
+      const uint32_t z_base = smem_base + C::OFF_Z, q_base = smem_base + C::OFF_Q;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        // ---- phase A: A += x2_c Wd_c^T ; P += x1_c Gd_c^T
+        for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
+          const uint32_t sx = xi % SX, sw = wi % SW;
+          ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+          ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
+          ptx::tc_fence_after();
+          const uint32_t x1s = smem_base + C::OFF_X + sx * (2 * XCH_BYTES), x2s = x1s + XCH_BYTES;
+          const uint32_t wds = smem_base + C::OFF_W + sw * C::WSLOT, gds = wds + C::WA_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < CH / 16; ++ks) {
+            const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
+            ptx::umma_bf16_ss(tmem_base + TM_A, ptx::umma_desc_kmajor_sw128(x2s + ks * 32),
+                              ptx::umma_desc_kmajor_sw128(wds + ks * 32), IDESC_A, acc);
+            ptx::umma_bf16_ss(tmem_base + TM_P, ptx::umma_desc_kmajor_sw128(x1s + ks * 32),
+                              ptx::umma_desc_kmajor_sw128(gds + ks * 32), IDESC_A, acc);
+          }
+          ptx::umma_commit(bar(B_XEMPTY + sx));
+          ptx::umma_commit(bar(B_WEMPTY + sw));
+        }
+        ptx::umma_commit(bar(B_APFULL));
+        // ---- phase B: U_n = z Wu_n^T ; T_n = q Gu_n^T
+        ptx::mbar_wait(bar(B_ZQFULL), ti & 1);
+        ptx::tc_fence_after();
+        for (int c = 0; c < nkc; ++c, ++xi, ++wi, ++ui) {
+          const uint32_t sw = wi % SW, ub = ui & 1;
+          ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
+          ptx::mbar_wait(bar(B_UTEMPTY + ub), ((ui >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT, gus = wus + C::WB_BYTES;
+          const uint32_t tU = tmem_base + TM_UT + ub * 128, tT = tU + 64;
+#pragma unroll
+          for (int ks = 0; ks < R / 16; ++ks) {
+            const uint32_t kb = ks / 4, kin = ks % 4;
+            ptx::umma_bf16_ss(tU, ptx::umma_desc_kmajor_sw128(z_base + kb * XCH_BYTES + kin * 32),
+                              ptx::umma_desc_kmajor_sw128(wus + kb * (CH * CH * 2) + kin * 32), IDESC_B, ks > 0);
+            ptx::umma_bf16_ss(tT, ptx::umma_desc_kmajor_sw128(q_base + kb * XCH_BYTES + kin * 32),
+                              ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_B, ks > 0);
+          }
+          ptx::umma_commit(bar(B_WEMPTY + sw));
+          ptx::umma_commit(bar(B_UTFULL + ub));
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================== TMA store issuer =====================================
+    if (lane == 0) {
+      uint32_t xi = 0, oi = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = (int)(tile * TILE_M);
+        xi += nkc;  // phase A steps of the x-ring are consumed by the MMA warp
+        for (int c = 0; c < nkc; ++c, ++xi, ++oi) {
+          const uint32_t sx = xi % SX, so = oi % SX;
+          ptx::mbar_wait(bar(B_OUTRDY + so), (oi / SX) & 1);
+          ptx::tma_store_2d(&tm_out, smem_base + C::OFF_X + sx * (2 * XCH_BYTES), c * CH, row0);
+          ptx::tma_store_commit();
+          ptx::tma_store_wait_read0();
+          ptx::mbar_arrive(bar(B_XEMPTY + sx));
+        }
+      }
+      ptx::tma_store_wait_all0();
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue warps =====================================
+    const int quarter = warp % 4;            // TMEM lanes [32*quarter, 32*quarter+32)
+    const int half = (warp - 4) / 4;         // 0: adapter branch / left 32 columns, 1: gate branch / right 32 columns
+    const int row = quarter * 32 + lane;     // row inside the 128-token tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t swz = (uint32_t)(row & 7);
+    uint32_t xi = 0, ui = 0, oi = 0, ti = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      // ---- epilogue 1: z = gelu_new(A + bd) (half 0) / q = gelu_new(P + gbd) (half 1) -> swizzled K-major smem
+      ptx::mbar_wait(bar(B_APFULL), ti & 1);
+      ptx::tc_fence_after();
+      {
+        const uint32_t tsrc = lane_addr + (half ? TM_P : TM_A);
+        const uint32_t dst = smem_base + (half ? C::OFF_Q : C::OFF_Z) + (uint32_t)row * 128u;
+        const __nv_bfloat16* bias = half ? p.gbd : p.bd;
+        const int rr = half ? p.rg : p.r;
+#pragma unroll
+        for (int j0 = 0; j0 < R; j0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tsrc + j0, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {  // 8 columns -> one 16-byte swizzled store
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j0 + g * 8 + e * 2;
+              float b0 = (j < rr) ? __bfloat162float(bias[j]) : 0.f;
+              float b1 = (j + 1 < rr) ? __bfloat162float(bias[j + 1]) : 0.f;
+              o[e] = pack_bf16(gelu_new_fast(__uint_as_float(v[g * 8 + e * 2]) + b0),
+                               gelu_new_fast(__uint_as_float(v[g * 8 + e * 2 + 1]) + b1));
+            }
+            const int k = j0 + g * 8;                       // first column of this 16-byte group
+            const uint32_t kb = (uint32_t)k / 64, c16 = ((uint32_t)k % 64) / 8;
+            const uint32_t addr = dst + kb * XCH_BYTES + ((c16 ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+          }
+        }
+      }
+      ptx::fence_proxy_async_smem();  // z/q were written by the generic proxy and are read by tcgen05.mma
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(B_ZQFULL));
+      xi += nkc;
+      // ---- epilogue 2, per 64-column chunk
+      for (int c = 0; c < nkc; ++c, ++xi, ++ui, ++oi) {
+        const uint32_t sx = xi % SX, ub = ui & 1, so = oi % SX;
+        ptx::mbar_wait(bar(B_UTFULL + ub), (ui >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t u[32], t[32];
+        const uint32_t tU = lane_addr + TM_UT + ub * 128 + half * 32;
+        ptx::tmem_ld_32x32b_x32(tU, u);
+        ptx::tmem_ld_32x32b_x32(tU + 64, t);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(bar(B_UTEMPTY + ub));  // accumulators are in registers: the MMA warp may overwrite them
+        ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+        const uint32_t x1row = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
+        const uint32_t x2row = x1row + XCH_BYTES;
+        const int col0 = c * CH + half * 32;  // first of this thread's 32 output columns
+        const int64_t idx0 = ((int64_t)tile * TILE_M + row) * p.d + col0;  // flat element index (dropout stream)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint64_t hsh[2] = {0, 0};
+          if (p.thr16) {
+            hsh[0] = drop_hash4(p.seed, (uint64_t)(idx0 + g * 8) >> 2);
+            hsh[1] = drop_hash4(p.seed, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
+          }
+          const uint32_t off = (((uint32_t)(half * 4 + g)) ^ swz) << 4;
+          uint32_t a[4], b[4], o[4];
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(x1row + off));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(x2row + off));
+          const uint4 bu4 = __ldg(reinterpret_cast<const uint4*>(p.bu + col0 + g * 8));
+          const uint4 gb4 = __ldg(reinterpret_cast<const uint4*>(p.gbu + col0 + g * 8));
+          const uint32_t buw[4] = {bu4.x, bu4.y, bu4.z, bu4.w}, gbw[4] = {gb4.x, gb4.y, gb4.z, gb4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = g * 8 + e * 2;
+            float y0 = fmaf(p.kappa, bf_lo(b[e]), p.alpha * (__uint_as_float(u[j]) + bf_lo(buw[e])));
+            float y1 = fmaf(p.kappa, bf_hi(b[e]), p.alpha * (__uint_as_float(u[j + 1]) + bf_hi(buw[e])));
+            float g0 = sigmoid_fast(__uint_as_float(t[j]) + bf_lo(gbw[e]));
+            float g1 = sigmoid_fast(__uint_as_float(t[j + 1]) + bf_hi(gbw[e]));
+            float h0 = p.add_gate ? y0 + g0 : y0 * g0;
+            float h1 = p.add_gate ? y1 + g1 : y1 * g1;
+            float s0 = p.s, s1 = p.s;
+            if (p.thr16) {
+              const uint32_t two = (uint32_t)(hsh[e >> 1] >> (32 * (e & 1)));  // 16 bits for column j, 16 for j+1
+              s0 = ((two & 0xffffu) >= p.thr16) ? p.s * p.inv_keep : 0.f;
+              s1 = ((two >> 16) >= p.thr16) ? p.s * p.inv_keep : 0.f;
+            }
+            o[e] = pack_bf16(fmaf(s0, h0, bf_lo(a[e])), fmaf(s1, h1, bf_hi(a[e])));
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(x1row + off), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+        }
+        ptx::fence_proxy_async_smem();  // out chunk (in the x1 slot) is read by the TMA store
+        ptx::mbar_arrive(bar(B_OUTRDY + so));
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] (row pitch = cols elements), box = [box_rows x 64 cols], 128-byte swizzle
+int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool weight) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(VLPET_E_NODEVICE, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)CH, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   weight ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VLPET_E_BADARG, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box=%u", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  return 0;
+}
+
+int pick_R(const VlpetK1Desc& D) {
+  int m = D.r > D.rg ? D.r : D.rg;
+  if (m <= 32) return 32;
+  if (m <= 64) return 64;
+  if (m <= 96) return 96;
+  if (m <= 128) return 128;
+  return 0;
+}
+
+struct DevInfo { int ok, sms, major; };
+const DevInfo& dev_info() {
+  static DevInfo di = []() {
+    DevInfo d{0, 0, 0};
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
+      d.ok = 1; d.sms = p.multiProcessorCount; d.major = p.major;
+    }
+    return d;
+  }();
+  return di;
+}
+
+template <int R>
+int launch(const VlpetK1Desc& D, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
+  using C = Cfg<R>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLPET_CUDA_OK(cudaFuncSetAttribute(k1_fwd_sm100_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
+  int grid = (int)(tiles < dev_info().sms ? tiles : dev_info().sms);
+  k1_fwd_sm100_kernel<R><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+                                                                  maps[6], p);
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+bool fused_k1_fwd_supported(const VlpetK1Desc& D) {
+  if (D.dtype != VLPET_BF16 || D.gate != VLPET_GATE_LARGE) return false;
+  if (D.d % CH != 0 || D.d < CH) return false;
+  if (D.r % 8 != 0 || D.rg % 8 != 0 || pick_R(D) == 0) return false;
+  if (D.M <= 0 || D.M > (int64_t)0x7fffff00) return false;
+  const DevInfo& di = dev_info();
+  return di.ok && di.major == 10;
+}
+
+size_t fused_k1_fwd_ws(const VlpetK1Desc&) { return 0; }
+
+int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const VlpetK1Params& w, void* out, void*, size_t,
+                 cudaStream_t st) {
+  if (!aligned16(w.Wd) || !aligned16(w.Wu) || !aligned16(w.Gd) || !aligned16(w.Gu) || !aligned16(w.bu) || !aligned16(w.gbu))
+    return fail(VLPET_E_ALIGN, "k1_fwd(fused): weights must be 16-byte aligned");
+  const int R = pick_R(D);
+  CUtensorMap maps[7];
+  VLPET_TRY(make_map(&maps[0], x1, (uint64_t)D.M, (uint64_t)D.d, TILE_M, false));
+  VLPET_TRY(make_map(&maps[1], x2, (uint64_t)D.M, (uint64_t)D.d, TILE_M, false));
+  VLPET_TRY(make_map(&maps[2], out, (uint64_t)D.M, (uint64_t)D.d, TILE_M, false));
+  VLPET_TRY(make_map(&maps[3], w.Wd, (uint64_t)D.r, (uint64_t)D.d, (uint32_t)R, true));
+  VLPET_TRY(make_map(&maps[4], w.Gd, (uint64_t)D.rg, (uint64_t)D.d, (uint32_t)R, true));
+  VLPET_TRY(make_map(&maps[5], w.Wu, (uint64_t)D.d, (uint64_t)D.r, CH, true));
+  VLPET_TRY(make_map(&maps[6], w.Gu, (uint64_t)D.d, (uint64_t)D.rg, CH, true));
+  Params p;
+  p.M = D.M; p.d = D.d; p.r = D.r; p.rg = D.rg; p.add_gate = D.add_gate;
+  p.s = D.s; p.alpha = D.alpha; p.kappa = D.kappa;
+  p.bd = static_cast<const __nv_bfloat16*>(w.bd); p.bu = static_cast<const __nv_bfloat16*>(w.bu);
+  p.gbd = static_cast<const __nv_bfloat16*>(w.gbd); p.gbu = static_cast<const __nv_bfloat16*>(w.gbu);
+  p.seed = D.seed;
+  p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
+  p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
+  switch (R) {
+    case 32: return launch<32>(D, maps, p, st);
+    case 64: return launch<64>(D, maps, p, st);
+    case 96: return launch<96>(D, maps, p, st);
+    case 128: return launch<128>(D, maps, p, st);
+  }
+  return fail(VLPET_E_UNSUPPORTED, "k1_fwd(fused): unsupported rank");
+}
+
+}  // namespace vlpet

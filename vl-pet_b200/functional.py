@@ -1,0 +1,343 @@
+"""torch.autograd bindings of the libvlpet.so kernels (PyTorch is plumbing here: device memory, streams, autograd
+graph).  Every function requires CUDA tensors and raises otherwise -- there is no CPU path in the product."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+_workspaces = {}
+_seed_counter = [0]
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vlpet: CUDA tensors required -- the PET kernels have no CPU fallback")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only per-device scratch buffer; safe because every call is ordered on the current stream."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _as(t: Optional[torch.Tensor], dtype) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    sh = getattr(t, "_vlpet_shadow", None)  # bf16 shadow kept fresh by PetBucket
+    if sh is not None and sh.dtype == dtype:
+        return sh
+    t = t.detach()
+    return (t if t.dtype == dtype else t.to(dtype)).contiguous()
+
+
+def _stack_rows(ts: Sequence[torch.Tensor], dtype) -> torch.Tensor:
+    """Row-concatenate head tensors.  Free when the heads are adjacent slices of one buffer."""
+    ts = [_as(t, dtype) for t in ts]
+    if len(ts) == 1:
+        return ts[0]
+    t0 = ts[0]
+    step = t0.numel() * t0.element_size()
+    if all(t.shape == t0.shape and t.data_ptr() == t0.data_ptr() + i * step for i, t in enumerate(ts)):
+        rows = t0.shape[0] * len(ts)
+        try:
+            return torch.as_strided(t0, (rows,) + tuple(t0.shape[1:]), t0.stride())
+        except RuntimeError:
+            pass
+    return torch.cat(ts, dim=0)
+
+
+def next_dropout_seed() -> int:
+    _seed_counter[0] += 1
+    return (torch.initial_seed() * 0x9E3779B1 + _seed_counter[0]) & 0xFFFFFFFFFFFFFFFF
+
+
+@dataclass(frozen=True)
+class PetSiteConfig:
+    """Flags the reference reads off ``layer.config`` at a PET site (param.py:262-376)."""
+    gate: str = "large"         # large | middle_x | middle_y | small | none
+    add_gate: bool = False      # use_encoder_adapter_gating_add
+    s: float = 1.0              # encoder_gating_scaling_factor (1 when use_encoder_gating_scaling is off)
+    alpha: float = 1.0          # encoder_adapter_scaling_factor
+    kappa: float = 1.0          # encoder_x2_scaling_factor
+    p_drop: float = 0.0         # dropout between gate and residual; applied only when training=True
+    impl: str = "auto"          # auto | generic | fused
+
+
+_GATE_NPARAMS = {"none": 0, "large": 4, "middle_x": 2, "small": 2, "middle_y": 1}
+
+
+class GatedPETFn(torch.autograd.Function):
+    """out = x1 + dropout(s * gate(x1, kappa*x2 + alpha*Up(gelu_new(Down(x2)))))   -- include/vlpet.h K1.
+
+    Tensor args after ``nheads``: down_w[0..h), down_b[0..h), up_w, up_b, then the gate parameters
+    (large: gd_w, gd_b, gu_w, gu_b; middle_x / small: gw, gb; middle_y: gz)."""
+
+    @staticmethod
+    def forward(ctx, cfg: PetSiteConfig, seed: int, seq_len: int, nheads: int, x1, x2, *params):
+        _require_cuda(x1, x2, *params)
+        if x1.shape != x2.shape or x1.dtype != x2.dtype or x1.dtype not in _DT:
+            raise ValueError(f"vlpet.gated_pet: x1/x2 must share shape and be fp32/bf16, got {x1.shape} {x1.dtype} / {x2.shape} {x2.dtype}")
+        ng = _GATE_NPARAMS[cfg.gate]
+        if len(params) != 2 * nheads + 2 + ng:
+            raise ValueError(f"vlpet.gated_pet: expected {2 * nheads + 2 + ng} parameter tensors, got {len(params)}")
+        dt = x1.dtype
+        d = x1.shape[-1]
+        x1c, x2c = x1.contiguous(), x2.contiguous()
+        M = x1c.numel() // d
+        Wd = _stack_rows(params[:nheads], dt)
+        bd = _stack_rows(params[nheads:2 * nheads], dt)
+        Wu, bu = _as(params[2 * nheads], dt), _as(params[2 * nheads + 1], dt)
+        gp = [_as(t, dt) for t in params[2 * nheads + 2:]]
+        r = Wd.shape[0]
+        if Wd.shape != (r, d) or Wu.shape != (d, r) or bd.numel() != r or bu.numel() != d:
+            raise ValueError(f"vlpet.gated_pet: inconsistent adapter shapes Wd{tuple(Wd.shape)} Wu{tuple(Wu.shape)}")
+        rg = gp[0].shape[0] if cfg.gate == "large" else 0
+        desc = L.K1Desc(M=M, L=seq_len, d=d, r=r, rg=rg, gate=L.GATE_IDS[cfg.gate], add_gate=int(cfg.add_gate),
+                        dtype=_DT[dt], impl=L.IMPL_IDS[cfg.impl], s=cfg.s, alpha=cfg.alpha, kappa=cfg.kappa,
+                        p_drop=cfg.p_drop if seed else 0.0, seed=seed)
+        w = L.K1Params(Wd=_p(Wd), bd=_p(bd), Wu=_p(Wu), bu=_p(bu))
+        if cfg.gate == "large":
+            w.Gd, w.gbd, w.Gu, w.gbu = _p(gp[0]), _p(gp[1]), _p(gp[2]), _p(gp[3])
+        elif cfg.gate in ("middle_x", "small"):
+            w.gw, w.gb = _p(gp[0]), _p(gp[1])
+        elif cfg.gate == "middle_y":
+            w.gz = _p(gp[0])
+        out = torch.empty_like(x1c)
+        nws = L.lib.vlpet_k1_fwd_workspace_bytes(C.byref(desc))
+        ws = _workspace(nws, x1.device)
+        L.check(L.lib.vlpet_k1_fwd(C.byref(desc), _p(x1c), _p(x2c), C.byref(w), _p(out), _p(ws), ws.numel(), _stream()),
+                "vlpet_k1_fwd")
+        ctx.desc, ctx.nheads, ctx.cfg = desc, nheads, cfg
+        ctx.param_meta = [(tuple(t.shape), t.dtype) for t in params]
+        ctx.save_for_backward(x1c, x2c, Wd, bd, Wu, bu, *gp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x1, x2, Wd, bd, Wu, bu, *gp = ctx.saved_tensors
+        desc, nheads, cfg = ctx.desc, ctx.nheads, ctx.cfg
+        dout = dout.contiguous()
+        if dout.dtype != x1.dtype:
+            dout = dout.to(x1.dtype)
+        d, r, rg = desc.d, desc.r, desc.rg
+        sizes = [r * d, r, d * r, d]
+        if cfg.gate == "large":
+            sizes += [rg * d, rg, d * rg, d]
+        elif cfg.gate == "middle_x":
+            sizes += [d, 1]
+        elif cfg.gate == "small":
+            sizes += [2 * d, 1]
+        elif cfg.gate == "middle_y":
+            sizes += [d]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 3) // 4 * 4)      # keep every grad 16-byte aligned
+        gbuf = torch.zeros(offs[-1], dtype=torch.float32, device=x1.device)
+        gv = [gbuf[offs[i]:offs[i] + sizes[i]] for i in range(len(sizes))]
+        g = L.K1Grads(dWd=_p(gv[0]), dbd=_p(gv[1]), dWu=_p(gv[2]), dbu=_p(gv[3]))
+        if cfg.gate == "large":
+            g.dGd, g.dgbd, g.dGu, g.dgbu = _p(gv[4]), _p(gv[5]), _p(gv[6]), _p(gv[7])
+        elif cfg.gate in ("middle_x", "small"):
+            g.dgw, g.dgb = _p(gv[4]), _p(gv[5])
+        elif cfg.gate == "middle_y":
+            g.dgz = _p(gv[4])
+        w = L.K1Params(Wd=_p(Wd), bd=_p(bd), Wu=_p(Wu), bu=_p(bu))
+        if cfg.gate == "large":
+            w.Gd, w.gbd, w.Gu, w.gbu = _p(gp[0]), _p(gp[1]), _p(gp[2]), _p(gp[3])
+        elif cfg.gate in ("middle_x", "small"):
+            w.gw, w.gb = _p(gp[0]), _p(gp[1])
+        elif cfg.gate == "middle_y":
+            w.gz = _p(gp[0])
+        dx1, dx2 = torch.empty_like(x1), torch.empty_like(x2)
+        nws = L.lib.vlpet_k1_bwd_workspace_bytes(C.byref(desc))
+        ws = _workspace(nws, x1.device)
+        L.check(L.lib.vlpet_k1_bwd(C.byref(desc), _p(x1), _p(x2), _p(dout), C.byref(w), _p(dx1), _p(dx2), C.byref(g),
+                                   _p(ws), ws.numel(), _stream()), "vlpet_k1_bwd")
+        # scatter the flat fp32 grads back onto the parameter list (heads are row slices of dWd / dbd)
+        meta = ctx.param_meta
+        grads: List[Optional[torch.Tensor]] = []
+        hr = r // nheads
+        dWd, dbd = gv[0].view(r, d), gv[1]
+        for h in range(nheads):
+            grads.append(dWd[h * hr:(h + 1) * hr])
+        for h in range(nheads):
+            grads.append(dbd[h * hr:(h + 1) * hr])
+        grads += [gv[2].view(d, r), gv[3]]
+        for i in range(4, len(sizes)):
+            grads.append(gv[i])
+        outg = []
+        for gt, (shape, dtype) in zip(grads, meta):
+            gt = gt.reshape(shape)
+            outg.append(gt if dtype == torch.float32 else gt.to(dtype))
+        return (None, None, None, None, dx1, dx2, *outg)
+
+
+def gated_pet(x1, x2, down_ws, down_bs, up_w, up_b, gate_params=(), cfg: PetSiteConfig = PetSiteConfig(),
+              training: bool = False):
+    """Functional form of one encoder PET site (include/vlpet.h K1).  x1, x2: [B, L, d] (or [M, d])."""
+    seed = next_dropout_seed() if (training and cfg.p_drop > 0.0) else 0
+    seq_len = x1.shape[-2] if x1.dim() >= 2 else 0
+    if cfg.gate == "small" and x1.dim() < 3:
+        raise ValueError("vlpet.gated_pet: the small gate averages over the sequence: pass [B, L, d]")
+    return GatedPETFn.apply(cfg, seed, int(seq_len), len(down_ws), x1, x2, *down_ws, *down_bs, up_w, up_b, *gate_params)
+
+
+class VpaFn(torch.autograd.Function):
+    """out = y + sf * Up(gelu_new(Down(kv)))   -- include/vlpet.h K2 (y may be None: no residual)."""
+
+    @staticmethod
+    def forward(ctx, sf: float, impl: str, kv, y, Wd, bd, Wu, bu):
+        _require_cuda(kv, y, Wd, bd, Wu, bu)
+        if kv.dtype not in _DT or (y is not None and (y.shape != kv.shape or y.dtype != kv.dtype)):
+            raise ValueError("vlpet.vpa: kv / y must share shape and be fp32/bf16")
+        dt, d = kv.dtype, kv.shape[-1]
+        kvc = kv.contiguous()
+        yc = y.contiguous() if y is not None else None
+        Wdc, bdc, Wuc, buc = (_as(t, dt) for t in (Wd, bd, Wu, bu))
+        r = Wdc.shape[0]
+        if Wdc.shape != (r, d) or Wuc.shape != (d, r):
+            raise ValueError(f"vlpet.vpa: inconsistent shapes Wd{tuple(Wdc.shape)} Wu{tuple(Wuc.shape)} d={d}")
+        desc = L.K2Desc(M=kvc.numel() // d, d=d, r=r, dtype=_DT[dt], impl=L.IMPL_IDS[impl], sf=sf)
+        w = L.K2Params(Wd=_p(Wdc), bd=_p(bdc), Wu=_p(Wuc), bu=_p(buc))
+        out = torch.empty_like(kvc)
+        ws = _workspace(L.lib.vlpet_k2_fwd_workspace_bytes(C.byref(desc)), kv.device)
+        L.check(L.lib.vlpet_k2_fwd(C.byref(desc), _p(kvc), _p(yc), C.byref(w), _p(out), _p(ws), ws.numel(), _stream()),
+                "vlpet_k2_fwd")
+        ctx.desc, ctx.has_y = desc, y is not None
+        ctx.param_meta = [(tuple(t.shape), t.dtype) for t in (Wd, bd, Wu, bu)]
+        ctx.save_for_backward(kvc, Wdc, bdc, Wuc, buc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        kv, Wd, bd, Wu, bu = ctx.saved_tensors
+        desc = ctx.desc
+        dout = dout.contiguous()
+        if dout.dtype != kv.dtype:
+            dout = dout.to(kv.dtype)
+        d, r = desc.d, desc.r
+        sizes = [r * d, r, d * r, d]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 3) // 4 * 4)
+        gbuf = torch.zeros(offs[-1], dtype=torch.float32, device=kv.device)
+        gv = [gbuf[offs[i]:offs[i] + sizes[i]] for i in range(4)]
+        g = L.K2Grads(dWd=_p(gv[0]), dbd=_p(gv[1]), dWu=_p(gv[2]), dbu=_p(gv[3]))
+        w = L.K2Params(Wd=_p(Wd), bd=_p(bd), Wu=_p(Wu), bu=_p(bu))
+        dkv = torch.empty_like(kv) if ctx.needs_input_grad[2] else None
+        ws = _workspace(L.lib.vlpet_k2_bwd_workspace_bytes(C.byref(desc)), kv.device)
+        L.check(L.lib.vlpet_k2_bwd(C.byref(desc), _p(kv), _p(dout), C.byref(w), _p(dkv), C.byref(g), _p(ws), ws.numel(),
+                                   _stream()), "vlpet_k2_bwd")
+        outg = []
+        for gt, (shape, dtype) in zip(gv, ctx.param_meta):
+            gt = gt.reshape(shape)
+            outg.append(gt if dtype == torch.float32 else gt.to(dtype))
+        return (None, None, dkv, dout if ctx.has_y else None, *outg)
+
+
+def vpa(kv, y, down_w, down_b, up_w, up_b, scaling_factor: float = 1.0, impl: str = "auto"):
+    """Decoder value-parallel-adapter (adapter_controller.py:149-162): y + sf * Up(gelu_new(Down(kv)))."""
+    return VpaFn.apply(float(scaling_factor), impl, kv, y, down_w, down_b, up_w, up_b)
+
+
+class VisProjFn(torch.autograd.Function):
+    """VisualEmbedding.forward (src/modeling_bart.py:143-192) -- include/vlpet.h K3."""
+
+    @staticmethod
+    def forward(ctx, rms: bool, eps: float, impl: str, feats, pos, img_ids, obj_ids, Wf, bf, lnfw, lnfb, Wp, bp, lnpw,
+                lnpb, E_img, E_obj):
+        _require_cuda(feats, pos, Wf, E_img, E_obj)
+        if feats.dim() != 3 or feats.dtype not in _DT:
+            raise ValueError("vlpet.visual_projection: feats must be [B, N, F] fp32/bf16")
+        B, N, F = feats.shape
+        if tuple(pos.shape) != (B, N, 4):
+            raise ValueError(f"vlpet.visual_projection: pos must be [{B}, {N}, 4], got {tuple(pos.shape)}")
+        dt = feats.dtype
+        d = Wf.shape[0]
+        fc = feats.contiguous()
+        pc = pos.to(dt).contiguous()
+
+        def ids(t):
+            if t is None:
+                return None
+            return t.to(torch.int64).expand(B, N).contiguous()
+
+        img, obj = ids(img_ids), ids(obj_ids)
+        ws_ = [_as(t, dt) for t in (Wf, bf, lnfw, lnfb, Wp, bp, lnpw, lnpb, E_img, E_obj)]
+        desc = L.K3Desc(M=B * N, N=N, F=F, d=d, V=E_obj.shape[0], n_img=E_img.shape[0], rms=int(rms), dtype=_DT[dt],
+                        impl=L.IMPL_IDS[impl], eps=eps)
+        w = L.K3Params(*[_p(t) for t in ws_])
+        out = torch.empty(B, N, d, dtype=dt, device=feats.device)
+        save = torch.empty(L.lib.vlpet_k3_save_floats(C.byref(desc)), dtype=torch.float32, device=feats.device)
+        ws = _workspace(L.lib.vlpet_k3_fwd_workspace_bytes(C.byref(desc)), feats.device)
+        L.check(L.lib.vlpet_k3_fwd(C.byref(desc), _p(fc), _p(pc), _p(img), _p(obj), C.byref(w), _p(out), _p(save), _p(ws),
+                                   ws.numel(), _stream()), "vlpet_k3_fwd")
+        ctx.desc = desc
+        ctx.param_meta = [None if t is None else (tuple(t.shape), t.dtype) for t in (Wf, bf, lnfw, lnfb, Wp, bp, lnpw, lnpb, E_img)]
+        ctx.save_for_backward(fc, pc, img, save, *[t for t in ws_ if t is not None])
+        ctx.present = [t is not None for t in ws_]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        fc, pc, img, save, *rest = ctx.saved_tensors
+        it = iter(rest)
+        ws_ = [next(it) if p else None for p in ctx.present]
+        desc = ctx.desc
+        dout = dout.contiguous()
+        if dout.dtype != fc.dtype:
+            dout = dout.to(fc.dtype)
+        d, F = desc.d, desc.F
+        sizes = [d * F, d, d, d, d * 5, d, d, d, desc.n_img * d]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 3) // 4 * 4)
+        gbuf = torch.zeros(offs[-1], dtype=torch.float32, device=fc.device)
+        gv = [gbuf[offs[i]:offs[i] + sizes[i]] for i in range(len(sizes))]
+        present = ctx.present
+        g = L.K3Grads(*[_p(gv[i]) if present[i] else C.c_void_p(0) for i in range(9)])
+        w = L.K3Params(*[_p(t) for t in ws_])
+        dfeats = torch.empty_like(fc) if ctx.needs_input_grad[3] else None
+        ws = _workspace(L.lib.vlpet_k3_bwd_workspace_bytes(C.byref(desc)), fc.device)
+        L.check(L.lib.vlpet_k3_bwd(C.byref(desc), _p(fc), _p(pc), _p(img), _p(dout), C.byref(w), _p(save), _p(dfeats),
+                                   C.byref(g), _p(ws), ws.numel(), _stream()), "vlpet_k3_bwd")
+        outg = []
+        for gt, meta in zip(gv, ctx.param_meta):
+            if meta is None:
+                outg.append(None)
+                continue
+            shape, dtype = meta
+            gt = gt.reshape(shape)
+            outg.append(gt if dtype == torch.float32 else gt.to(dtype))
+        return (None, None, None, dfeats, None, None, None, *outg, None)
+
+
+def visual_projection(feats, pos, img_order_ids, obj_order_ids, Wf, bf, ln_f_w, ln_f_b, Wp, bp, ln_p_w, ln_p_b, E_img,
+                      E_obj, rms: bool = False, eps: float = 1e-5, impl: str = "auto"):
+    return VisProjFn.apply(bool(rms), float(eps), impl, feats, pos, img_order_ids, obj_order_ids, Wf, bf, ln_f_w, ln_f_b,
+                           Wp, bp, ln_p_w, ln_p_b, E_img, E_obj.detach())
+
+
+def fwd_is_fused(M: int, d: int, r: int, rg: int, dtype=torch.bfloat16, gate: str = "large") -> bool:
+    desc = L.K1Desc(M=M, L=0, d=d, r=r, rg=rg, gate=L.GATE_IDS[gate], add_gate=0, dtype=_DT[dtype], impl=L.IMPL_AUTO,
+                    s=1.0, alpha=1.0, kappa=1.0, p_drop=0.0, seed=0)
+    return bool(L.lib.vlpet_k1_fwd_is_fused(C.byref(desc)))
