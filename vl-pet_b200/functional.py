@@ -79,7 +79,8 @@ class PetSiteConfig:
     alpha: float = 1.0          # encoder_adapter_scaling_factor
     kappa: float = 1.0          # encoder_x2_scaling_factor
     p_drop: float = 0.0         # dropout between gate and residual; applied only when training=True
-    impl: str = "auto"          # auto | generic | fused
+    impl: str = "auto"          # forward kernel: auto | generic | fused
+    bwd_impl: str = "auto"      # backward kernel: auto | generic | fused
 
 
 _GATE_NPARAMS = {"none": 0, "large": 4, "middle_x": 2, "small": 2, "middle_y": 1}
@@ -135,6 +136,7 @@ class GatedPETFn(torch.autograd.Function):
     def backward(ctx, dout):
         x1, x2, Wd, bd, Wu, bu, *gp = ctx.saved_tensors
         desc, nheads, cfg = ctx.desc, ctx.nheads, ctx.cfg
+        desc.impl = L.IMPL_IDS[cfg.bwd_impl]
         dout = dout.contiguous()
         if dout.dtype != x1.dtype:
             dout = dout.to(x1.dtype)
