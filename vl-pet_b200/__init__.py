@@ -10,6 +10,7 @@ from .functional import PetSiteConfig, gated_pet, vpa, visual_projection, fwd_is
 from .adapters import AdapterConfig, Activations, Adapter, AdapterController
 from .encoder import encoder_pet, gate_kind, patch_layer, patch_reference_model, site_config, site_params
 from .visual import VisualEmbedding, T5LayerNorm, adopt_reference_visual_embedding
+from . import host
 
 __all__ = ["LIB_PATH", "VlpetError", "launch_count", "PetSiteConfig", "gated_pet", "vpa", "visual_projection",
            "fwd_is_fused", "AdapterConfig", "Activations", "Adapter", "AdapterController", "encoder_pet", "gate_kind",

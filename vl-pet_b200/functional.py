@@ -13,6 +13,37 @@ from . import _lib as L
 _DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
 _workspaces = {}
 _seed_counter = [0]
+_prof = None   # when profiling: list of (kernel name, algorithmic bytes, start event, end event)
+
+
+def profile_kernels(enable: bool):
+    """Bracket every C-ABI compute call with CUDA events on the launching stream (bench.py's roofline leg).
+    Returns the records collected so far when disabling."""
+    global _prof
+    old, _prof = _prof, ([] if enable else None)
+    return old
+
+
+def profile_summary(records):
+    """-> {kernel: {"launches", "ms", "bytes"}} (call after torch.cuda.synchronize())."""
+    out = {}
+    for name, nbytes, s, e in records or []:
+        d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+        d["launches"] += 1
+        d["ms"] += s.elapsed_time(e)
+        d["bytes"] += nbytes
+    return out
+
+
+def _call(name: str, nbytes: int, fn, *args):
+    if _prof is None:
+        return fn(*args)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    r = fn(*args)
+    e.record()
+    _prof.append((name, nbytes, s, e))
+    return r
 
 
 def _require_cuda(*ts):
@@ -125,8 +156,8 @@ class GatedPETFn(torch.autograd.Function):
         out = torch.empty_like(x1c)
         nws = L.lib.vlpet_k1_fwd_workspace_bytes(C.byref(desc))
         ws = _workspace(nws, x1.device)
-        L.check(L.lib.vlpet_k1_fwd(C.byref(desc), _p(x1c), _p(x2c), C.byref(w), _p(out), _p(ws), ws.numel(), _stream()),
-                "vlpet_k1_fwd")
+        L.check(_call("k1_fwd", 3 * x1c.numel() * x1c.element_size(), L.lib.vlpet_k1_fwd, C.byref(desc), _p(x1c), _p(x2c),
+                      C.byref(w), _p(out), _p(ws), ws.numel(), _stream()), "vlpet_k1_fwd")
         ctx.desc, ctx.nheads, ctx.cfg = desc, nheads, cfg
         ctx.param_meta = [(tuple(t.shape), t.dtype) for t in params]
         ctx.save_for_backward(x1c, x2c, Wd, bd, Wu, bu, *gp)
@@ -172,8 +203,8 @@ class GatedPETFn(torch.autograd.Function):
         dx1, dx2 = torch.empty_like(x1), torch.empty_like(x2)
         nws = L.lib.vlpet_k1_bwd_workspace_bytes(C.byref(desc))
         ws = _workspace(nws, x1.device)
-        L.check(L.lib.vlpet_k1_bwd(C.byref(desc), _p(x1), _p(x2), _p(dout), C.byref(w), _p(dx1), _p(dx2), C.byref(g),
-                                   _p(ws), ws.numel(), _stream()), "vlpet_k1_bwd")
+        L.check(_call("k1_bwd", 5 * x1.numel() * x1.element_size(), L.lib.vlpet_k1_bwd, C.byref(desc), _p(x1), _p(x2),
+                      _p(dout), C.byref(w), _p(dx1), _p(dx2), C.byref(g), _p(ws), ws.numel(), _stream()), "vlpet_k1_bwd")
         # scatter the flat fp32 grads back onto the parameter list (heads are row slices of dWd / dbd)
         meta = ctx.param_meta
         grads: List[Optional[torch.Tensor]] = []
@@ -222,8 +253,8 @@ class VpaFn(torch.autograd.Function):
         w = L.K2Params(Wd=_p(Wdc), bd=_p(bdc), Wu=_p(Wuc), bu=_p(buc))
         out = torch.empty_like(kvc)
         ws = _workspace(L.lib.vlpet_k2_fwd_workspace_bytes(C.byref(desc)), kv.device)
-        L.check(L.lib.vlpet_k2_fwd(C.byref(desc), _p(kvc), _p(yc), C.byref(w), _p(out), _p(ws), ws.numel(), _stream()),
-                "vlpet_k2_fwd")
+        L.check(_call("k2_fwd", (3 if yc is not None else 2) * kvc.numel() * kvc.element_size(), L.lib.vlpet_k2_fwd,
+                      C.byref(desc), _p(kvc), _p(yc), C.byref(w), _p(out), _p(ws), ws.numel(), _stream()), "vlpet_k2_fwd")
         ctx.desc, ctx.has_y = desc, y is not None
         ctx.param_meta = [(tuple(t.shape), t.dtype) for t in (Wd, bd, Wu, bu)]
         ctx.save_for_backward(kvc, Wdc, bdc, Wuc, buc)
@@ -247,8 +278,8 @@ class VpaFn(torch.autograd.Function):
         w = L.K2Params(Wd=_p(Wd), bd=_p(bd), Wu=_p(Wu), bu=_p(bu))
         dkv = torch.empty_like(kv) if ctx.needs_input_grad[2] else None
         ws = _workspace(L.lib.vlpet_k2_bwd_workspace_bytes(C.byref(desc)), kv.device)
-        L.check(L.lib.vlpet_k2_bwd(C.byref(desc), _p(kv), _p(dout), C.byref(w), _p(dkv), C.byref(g), _p(ws), ws.numel(),
-                                   _stream()), "vlpet_k2_bwd")
+        L.check(_call("k2_bwd", 3 * kv.numel() * kv.element_size(), L.lib.vlpet_k2_bwd, C.byref(desc), _p(kv), _p(dout),
+                      C.byref(w), _p(dkv), C.byref(g), _p(ws), ws.numel(), _stream()), "vlpet_k2_bwd")
         outg = []
         for gt, (shape, dtype) in zip(gv, ctx.param_meta):
             gt = gt.reshape(shape)
@@ -291,8 +322,8 @@ class VisProjFn(torch.autograd.Function):
         out = torch.empty(B, N, d, dtype=dt, device=feats.device)
         save = torch.empty(L.lib.vlpet_k3_save_floats(C.byref(desc)), dtype=torch.float32, device=feats.device)
         ws = _workspace(L.lib.vlpet_k3_fwd_workspace_bytes(C.byref(desc)), feats.device)
-        L.check(L.lib.vlpet_k3_fwd(C.byref(desc), _p(fc), _p(pc), _p(img), _p(obj), C.byref(w), _p(out), _p(save), _p(ws),
-                                   ws.numel(), _stream()), "vlpet_k3_fwd")
+        L.check(_call("k3_fwd", (fc.numel() + out.numel()) * fc.element_size(), L.lib.vlpet_k3_fwd, C.byref(desc), _p(fc),
+                      _p(pc), _p(img), _p(obj), C.byref(w), _p(out), _p(save), _p(ws), ws.numel(), _stream()), "vlpet_k3_fwd")
         ctx.desc = desc
         ctx.param_meta = [None if t is None else (tuple(t.shape), t.dtype) for t in (Wf, bf, lnfw, lnfb, Wp, bp, lnpw, lnpb, E_img)]
         ctx.save_for_backward(fc, pc, img, save, *[t for t in ws_ if t is not None])
@@ -320,8 +351,9 @@ class VisProjFn(torch.autograd.Function):
         w = L.K3Params(*[_p(t) for t in ws_])
         dfeats = torch.empty_like(fc) if ctx.needs_input_grad[3] else None
         ws = _workspace(L.lib.vlpet_k3_bwd_workspace_bytes(C.byref(desc)), fc.device)
-        L.check(L.lib.vlpet_k3_bwd(C.byref(desc), _p(fc), _p(pc), _p(img), _p(dout), C.byref(w), _p(save), _p(dfeats),
-                                   C.byref(g), _p(ws), ws.numel(), _stream()), "vlpet_k3_bwd")
+        L.check(_call("k3_bwd", (fc.numel() + dout.numel()) * fc.element_size(), L.lib.vlpet_k3_bwd, C.byref(desc), _p(fc),
+                      _p(pc), _p(img), _p(dout), C.byref(w), _p(save), _p(dfeats), C.byref(g), _p(ws), ws.numel(), _stream()),
+                "vlpet_k3_bwd")
         outg = []
         for gt, meta in zip(gv, ctx.param_meta):
             if meta is None:

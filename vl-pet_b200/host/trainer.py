@@ -1,0 +1,191 @@
+"""PET-only data-parallel training step (SURVEY §8 rows a9 / e / f-2).
+
+What the reference intends (multitask.py:117-138, 217-342; trainer_base.py:308-542, 627-732) and what runs here:
+  * freeze everything, then unfreeze by NAME SUBSTRING ("visual_embedding", "gating", "adapter", encoder layer
+    norms) -- the same rules, so the trainable set is the reference's (6 052 416 parameters for BART-base r=96);
+  * AdamW (transformers.optimization.AdamW semantics: eps 1e-6, decoupled decay 0.01 except "bias" /
+    "LayerNorm.weight"), linear warm-up 10 % then linear decay, gradient-norm clip 5;
+  * one process per GPU; the batch is sharded by sample; gradients of the PET parameters ONLY are summed with ONE
+    all-reduce per step.  (In the reference the DDP reducer never fires -- SURVEY F5 -- so this collective is new
+    behaviour north_star asks for, not something to match.)
+
+B200-first layout: every trainable parameter is a view into ONE flat fp32 bucket (``flat_param``), its gradient a
+view into ``flat_grad`` (so autograd accumulates straight into the all-reduce payload), and a bf16 shadow of the
+bucket (what the kernels read) is refreshed by the fused AdamW kernel itself (vlpet_adamw_step).  Frozen backbone
+weights are stored in bf16 once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .. import _lib as L
+
+_NO_DECAY = ("bias", "LayerNorm.weight")     # trainer_base.py:640-660
+
+
+def trainable_names(model: nn.Module, config) -> List[str]:
+    """Names the reference's ``unfreeze_parameters`` (trainer_base.py:308-542) would mark trainable for the VL-PET
+    flag set carried by ``config``."""
+    gating = any(getattr(config, f, False) for f in (
+        "use_encoder_adapter_gating_large_x_lowrank", "use_encoder_adapter_gating_small_xy_cat",
+        "use_encoder_adapter_gating_middle_xy_add", "use_encoder_adapter_gating_middle_ia3_add"))
+    adapter = getattr(config, "use_encoder_adapter_down_multihead", False) or \
+        getattr(config, "use_decoder_enc_attn_value_parallel_adapter_down_dim", False)
+    out = []
+    for n, _ in model.named_parameters():
+        t = False
+        if not getattr(config, "freeze_vis_emb", False) and "visual_embedding" in n:
+            t = True
+        if getattr(config, "unfreeze_encoder_layer_norms", False) and "encoder." in n and \
+                ("layer_norm" in n or "layernorm" in n):
+            t = True
+        if gating and "gating" in n:
+            t = True
+        if adapter and "adapter" in n:
+            t = True
+        if t:
+            out.append(n)
+    return out
+
+
+def _align(n: int, a: int = 1024) -> int:
+    return (n + a - 1) // a * a
+
+
+class PetBucket:
+    """Flat fp32 parameter / gradient / AdamW-state buffers + bf16 shadow for the trainable set.
+    Each parameter starts on a 1024-element boundary so the per-block weight-decay mask of vlpet_adamw_step applies
+    and every view is 16-byte aligned (TMA)."""
+
+    def __init__(self, named_params, device, shadow_dtype: Optional[torch.dtype] = torch.bfloat16):
+        # decayed parameters first, then (from a 1024 boundary) the no-decay group; inside a group parameters keep
+        # registration order on 8-element boundaries, so the head slices of a multi-head down projection
+        # (weights in one group, biases in the other) stay ADJACENT and are read as one [r,d] / [r] tensor for free
+        decay = [(n, p) for n, p in named_params if not any(nd in n for nd in _NO_DECAY)]
+        nodecay = [(n, p) for n, p in named_params if any(nd in n for nd in _NO_DECAY)]
+        self.names = [n for n, _ in decay + nodecay]
+        self.params = [p for _, p in decay + nodecay]
+        offs, total = [], 0
+        for i, p in enumerate(self.params):
+            if i == len(decay):
+                total = _align(total)
+            offs.append(total)
+            total += _align(p.numel(), 8)
+        self.n_decay_elems = _align(offs[len(decay)] if nodecay else total)
+        total = _align(total)
+        self.offsets, self.numel = offs, total
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=device)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=device)
+        self.shadow = torch.zeros(total, dtype=shadow_dtype, device=device) if shadow_dtype is not None else None
+        mask = torch.zeros(total // 1024, dtype=torch.uint8)
+        mask[:self.n_decay_elems // 1024] = 1
+        for n, p, o in zip(self.names, self.params, offs):
+            view = self.flat_param[o:o + p.numel()].view_as(p)
+            view.copy_(p.data.to(device=device, dtype=torch.float32))
+            p.data = view
+            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+            p.requires_grad_(True)
+            if self.shadow is not None:
+                p._vlpet_shadow = self.shadow[o:o + p.numel()].view_as(p)
+        self.wd_mask = mask.to(device)
+        self.n_trainable = sum(p.numel() for p in self.params)
+        self.refresh_shadow()
+
+    def refresh_shadow(self):
+        if self.shadow is None:
+            return
+        L.check(L.lib.vlpet_cast_f32_to_bf16(C.c_void_p(self.flat_param.data_ptr()), C.c_void_p(self.shadow.data_ptr()),
+                                             self.numel, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                "vlpet_cast_f32_to_bf16")
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        for p, o in zip(self.params, self.offsets):        # autograd may have replaced .grad; re-pin the views
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+
+
+def linear_warmup_lr(step: int, total_steps: int, warmup_ratio: float, base_lr: float) -> float:
+    """get_linear_schedule_with_warmup (trainer_base.py:633, 716-718): step counts from 0."""
+    warm = int(total_steps * warmup_ratio)
+    if step < warm:
+        return base_lr * step / max(1, warm)
+    return base_lr * max(0.0, (total_steps - step) / max(1, total_steps - warm))
+
+
+class PetTrainer:
+    """Owns the bucket, the fused optimizer and the gradient exchange for one rank."""
+
+    def __init__(self, model: nn.Module, config, device, lr: float = 1e-3, weight_decay: float = 0.01,
+                 betas=(0.9, 0.999), eps: float = 1e-6, clip_grad_norm: float = 5.0, warmup_ratio: float = 0.1,
+                 total_steps: int = 10000, compute_dtype: torch.dtype = torch.bfloat16, process_group=None):
+        self.model, self.config, self.device = model, config, torch.device(device)
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.clip, self.warmup_ratio, self.total_steps = clip_grad_norm, warmup_ratio, total_steps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.step_idx = 0
+        names = set(trainable_names(model, config))
+        named = [(n, p) for n, p in model.named_parameters() if n in names]
+        for _, p in model.named_parameters():
+            p.requires_grad_(False)
+        model.to(self.device)
+        trainable_ids = {id(p) for _, p in named}
+        for p in model.parameters():                              # frozen backbone -> compute dtype, once
+            if id(p) not in trainable_ids and p.is_floating_point():
+                p.data = p.data.to(compute_dtype)
+        for b in model.buffers():
+            if b.is_floating_point():
+                b.data = b.data.to(compute_dtype)
+        self.bucket = PetBucket(named, self.device, torch.bfloat16 if compute_dtype == torch.bfloat16 else None)
+        self._norm_sq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._scale = torch.ones(1, dtype=torch.float32, device=self.device)
+        if self.world > 1:                                        # identical start on every rank
+            dist.broadcast(self.bucket.flat_param, src=0, group=self.pg)
+            self.bucket.refresh_shadow()
+
+    # -- the three phases of a step, separable so callers can capture / overlap them
+    def forward_backward(self, batch: Dict) -> torch.Tensor:
+        self.bucket.zero_grad()
+        loss = self.model.train_step(batch)["loss"]
+        loss.backward()
+        return loss.detach()
+
+    def exchange(self):
+        """ONE collective per step: SUM of the flat PET-gradient bucket over ranks (mean folded into the scale)."""
+        if self.world > 1:
+            dist.all_reduce(self.bucket.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def optimizer_step(self):
+        b = self.bucket
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        # global-norm clip factor on the device (no host sync): scale = min(1, clip / (||g||/world + 1e-6)) / world
+        self._norm_sq.zero_()
+        L.check(L.lib.vlpet_sumsq(C.c_void_p(b.flat_grad.data_ptr()), b.numel, C.c_void_p(self._norm_sq.data_ptr()), st),
+                "vlpet_sumsq")
+        w = float(self.world)
+        norm = self._norm_sq.sqrt() / w
+        torch.clamp(self.clip / (norm + 1e-6), max=1.0, out=self._scale)
+        self._scale.div_(w)
+        lr = linear_warmup_lr(self.step_idx, self.total_steps, self.warmup_ratio, self.lr)
+        self.step_idx += 1
+        L.check(L.lib.vlpet_adamw_step(C.c_void_p(b.flat_param.data_ptr()), C.c_void_p(b.flat_grad.data_ptr()),
+                                       C.c_void_p(b.exp_avg.data_ptr()), C.c_void_p(b.exp_avg_sq.data_ptr()),
+                                       C.c_void_p(b.wd_mask.data_ptr()), b.numel, lr, self.betas[0], self.betas[1],
+                                       self.eps, self.wd, self.step_idx, C.c_void_p(self._scale.data_ptr()),
+                                       C.c_void_p(b.shadow.data_ptr()) if b.shadow is not None else C.c_void_p(0), st),
+                "vlpet_adamw_step")
+
+    def train_step(self, batch: Dict) -> torch.Tensor:
+        loss = self.forward_backward(batch)
+        self.exchange()
+        self.optimizer_step()
+        return loss

@@ -1,0 +1,368 @@
+"""Host model that CALLS the PET hot path: a frozen BART-base encoder/decoder in stock PyTorch whose module tree,
+parameter names and op order follow the reference's VLBart (src/modeling_bart.py:696-898 JointEncoder, 1296-1455
+VLBartModel, 1458-1602 VLBart; src/my_transformers/modeling_bart.py:143-280 attention, 882-1388 encoder layer,
+1391-1788 decoder layer, 1953-2358 encoder / decoder stacks), so a reference ``state_dict`` loads key-for-key and
+the name-substring unfreezing rules of trainer_base.py:308-542 select the same parameters.
+
+Only the three PET op groups are ours (CUDA, include/vlpet.h): the two encoder PET sites per layer (K1), the
+decoder cross-attention value parallel adapter (K2) and the visual projection (K3).  Everything else here is
+plumbing in stock PyTorch (nn.Linear -> cuBLAS, F.scaled_dot_product_attention, nn.LayerNorm): it exists so that
+BASELINE.json's metric (multitask samples/s on BART-base) can be measured and so that the drop-in claim is tested
+end to end; it is not a re-implementation of the reference's trainer, data pipeline or generation code.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import encoder as E
+from ..adapters import AdapterController
+from ..visual import VisualEmbedding
+from .config import VLPetConfig
+
+
+def _ln(ln: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+    """LayerNorm whose (trainable, fp32-master) affine parameters may be wider than the activation dtype."""
+    w, b = ln.weight, ln.bias
+    if w.dtype != x.dtype:
+        w, b = w.to(x.dtype), b.to(x.dtype)
+    return F.layer_norm(x, ln.normalized_shape, w, b, ln.eps)
+
+
+def shift_tokens_right(input_ids: torch.Tensor, pad_token_id: int, decoder_start_token_id: int) -> torch.Tensor:
+    """Decoder inputs from labels (my_transformers/modeling_bart.py:63-77): shift right, start token first,
+    -100 -> pad."""
+    shifted = input_ids.new_empty(input_ids.shape)
+    shifted[:, 1:] = input_ids[:, :-1]
+    shifted[:, 0] = decoder_start_token_id
+    return shifted.masked_fill(shifted == -100, pad_token_id)
+
+
+class BartLearnedPositionalEmbedding(nn.Embedding):
+    """Learned positions with BART's +2 offset (my_transformers/modeling_bart.py:122-140)."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, padding_idx: int):
+        self.offset = 2
+        super().__init__(num_embeddings + self.offset, embedding_dim, padding_idx=padding_idx)
+
+    def forward(self, seq_len: int, past: int = 0):
+        pos = torch.arange(past, past + seq_len, dtype=torch.long, device=self.weight.device)
+        return super().forward(pos + self.offset)
+
+
+class BartAttention(nn.Module):
+    """Multi-head attention with the reference's parameter names (q/k/v/out_proj).  Cross-attention instances carry
+    ``attn_value_parallel_adapter`` (AdapterController, K2) exactly where BartAttentionWithValueAdapter does
+    (my_transformers/modeling_bart.py:329-340, 427-430)."""
+
+    def __init__(self, config: VLPetConfig, num_heads: int, is_decoder: bool, value_adapter: bool):
+        super().__init__()
+        d = config.d_model
+        self.embed_dim, self.num_heads, self.head_dim = d, num_heads, d // num_heads
+        self.dropout = config.attention_dropout
+        self.is_decoder = is_decoder
+        self.k_proj = nn.Linear(d, d)
+        self.v_proj = nn.Linear(d, d)
+        self.q_proj = nn.Linear(d, d)
+        self.out_proj = nn.Linear(d, d)
+        self.attn_value_parallel_adapter = AdapterController(config.vpa_adapter_config()) if value_adapter else None
+
+    def _heads(self, t: torch.Tensor) -> torch.Tensor:
+        B, L, _ = t.shape
+        return t.view(B, L, self.num_heads, self.head_dim).transpose(1, 2)
+
+    def forward(self, hidden_states, key_value_states=None, attn_mask=None, is_causal=False, task=None):
+        src = hidden_states if key_value_states is None else key_value_states
+        q = self.q_proj(hidden_states)
+        k = self.k_proj(src)
+        v = self.v_proj(src)
+        if key_value_states is not None and self.attn_value_parallel_adapter is not None:
+            v = self.attn_value_parallel_adapter(key_value_states, task, y=v)          # K2
+        o = F.scaled_dot_product_attention(self._heads(q), self._heads(k), self._heads(v), attn_mask=attn_mask,
+                                           dropout_p=self.dropout if self.training else 0.0, is_causal=is_causal)
+        B, L, _ = hidden_states.shape
+        return self.out_proj(o.transpose(1, 2).reshape(B, L, self.embed_dim))
+
+
+def _act(name: str):
+    if name == "gelu":
+        return F.gelu
+    if name == "relu":
+        return F.relu
+    raise ValueError(name)
+
+
+class BartEncoderLayer(nn.Module):
+    """Post-LN encoder block with the two VL-PET sites.  PET parameters live on the layer under the reference's
+    attribute names (my_transformers/modeling_bart.py:976-1056); the forward replaces the inline
+    op sequence of modeling_bart.py:1145-1261 / 1268-1377 by ``encoder_pet`` (K1)."""
+
+    def __init__(self, config: VLPetConfig):
+        super().__init__()
+        self.config = config
+        d = config.d_model
+        self.embed_dim = d
+        self.self_attn = BartAttention(config, config.encoder_attention_heads, is_decoder=False, value_adapter=False)
+        self.self_attn_layer_norm = nn.LayerNorm(d)
+        self.dropout = config.dropout
+        self.activation_fn = _act(config.activation_function)
+        self.activation_dropout = config.activation_dropout
+        self.fc1 = nn.Linear(d, config.encoder_ffn_dim)
+        self.fc2 = nn.Linear(config.encoder_ffn_dim, d)
+        self.final_layer_norm = nn.LayerNorm(d)
+        if not config.use_encoder_adapter_down_multihead:
+            raise NotImplementedError("vlpet host model: the encoder PET path needs use_encoder_adapter_down_multihead")
+        h = config.encoder_adapter_multihead_num_head
+        hr = int(config.adapter_down_dim / h)
+        for site in ("attn", "ff"):
+            setattr(self, f"{site}_adapter_multihead_down", nn.ModuleList([nn.Linear(d, hr) for _ in range(h)]))
+            setattr(self, f"{site}_adapter_multihead_up", nn.Linear(config.adapter_down_dim, d))
+            stem = f"encoder_{site}_adapter_gating"
+            if config.use_encoder_adapter_gating_large_x_lowrank:
+                setattr(self, stem + "_large_x_down", nn.Linear(d, config.adapter_gating_down_dim))
+                setattr(self, stem + "_large_x_up", nn.Linear(config.adapter_gating_down_dim, d))
+            if config.use_encoder_adapter_gating_small_xy_cat:
+                setattr(self, stem + "_small_xy_cat", nn.Linear(2 * d, 1))
+            if config.use_encoder_adapter_gating_middle_xy_add:
+                setattr(self, stem + "_middle_xy_add", nn.Linear(d, 1))
+            if config.use_encoder_adapter_gating_middle_ia3_add:
+                setattr(self, stem + "_middle_ia3_add", nn.Parameter(torch.zeros(d).normal_(std=0.02)))
+        self._vlpet_site_cfg = E.site_config(config, is_t5=False, impl=config.pet_impl)
+        if config.pet_bwd_impl != "auto":
+            import dataclasses
+            self._vlpet_site_cfg = dataclasses.replace(self._vlpet_site_cfg, bwd_impl=config.pet_bwd_impl)
+
+    def _pet(self, site: str, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+        return E.encoder_pet(self, site, x1, x2)
+
+    def forward(self, hidden_states, attn_mask=None, task=None):
+        x1 = hidden_states
+        x2 = self.self_attn(hidden_states, attn_mask=attn_mask)
+        hidden_states = _ln(self.self_attn_layer_norm, self._pet("attn", x1, x2))
+        x1 = hidden_states
+        h = self.activation_fn(self.fc1(hidden_states))
+        h = F.dropout(h, p=self.activation_dropout, training=self.training)
+        x2 = self.fc2(h)
+        return _ln(self.final_layer_norm, self._pet("ff", x1, x2))
+
+
+class BartDecoderLayer(nn.Module):
+    """Frozen post-LN decoder block; the only PET op is the value parallel adapter inside ``encoder_attn``
+    (my_transformers/modeling_bart.py:1452-1464 wiring, 1611-1788 forward)."""
+
+    def __init__(self, config: VLPetConfig):
+        super().__init__()
+        d = config.d_model
+        self.self_attn = BartAttention(config, config.decoder_attention_heads, is_decoder=True, value_adapter=False)
+        self.dropout = config.dropout
+        self.activation_fn = _act(config.activation_function)
+        self.activation_dropout = config.activation_dropout
+        self.self_attn_layer_norm = nn.LayerNorm(d)
+        self.encoder_attn = BartAttention(config, config.decoder_attention_heads, is_decoder=True,
+                                          value_adapter=config.use_decoder_enc_attn_value_parallel_adapter_down_dim)
+        self.encoder_attn_layer_norm = nn.LayerNorm(d)
+        self.fc1 = nn.Linear(d, config.decoder_ffn_dim)
+        self.fc2 = nn.Linear(config.decoder_ffn_dim, d)
+        self.final_layer_norm = nn.LayerNorm(d)
+
+    def forward(self, hidden_states, encoder_hidden_states, self_mask=None, cross_mask=None, task=None):
+        drop = lambda t: F.dropout(t, p=self.dropout, training=self.training)  # noqa: E731
+        h = self.self_attn(hidden_states, attn_mask=self_mask, is_causal=self_mask is None)
+        hidden_states = _ln(self.self_attn_layer_norm, hidden_states + drop(h))
+        h = self.encoder_attn(hidden_states, key_value_states=encoder_hidden_states, attn_mask=cross_mask, task=task)
+        hidden_states = _ln(self.encoder_attn_layer_norm, hidden_states + drop(h))
+        h = self.activation_fn(self.fc1(hidden_states))
+        h = F.dropout(h, p=self.activation_dropout, training=self.training)
+        h = self.fc2(h)
+        return _ln(self.final_layer_norm, hidden_states + drop(h))
+
+
+class Downsample(nn.Module):
+    """CLIP 7x7 grid -> sqrt(n_boxes)^2 by adaptive max-pool (src/modeling_bart.py:556-613); the NLVR 4-tuple pools
+    each of the two images separately."""
+
+    def __init__(self, output_size: Tuple[int, int]):
+        super().__init__()
+        self.output_size = output_size
+
+    def _pool(self, x):
+        B, L, dim = x.shape
+        s = int(L ** 0.5)
+        x = F.adaptive_max_pool2d(x.permute(0, 2, 1).reshape(B, dim, s, s), self.output_size)
+        return x.reshape(B, dim, -1).permute(0, 2, 1)
+
+    def forward(self, vis_inputs):
+        if len(vis_inputs) == 4:
+            feats, boxes, img_ids, obj_ids = vis_inputs
+            B, L2, dim = feats.shape
+            pooled = self._pool(feats.reshape(B * 2, L2 // 2, dim))
+            n = pooled.shape[1]
+            cut = lambda t: t.reshape(B, 2, L2 // 2, *t.shape[2:])[:, :, :n].reshape(B, 2 * n, *t.shape[2:])  # noqa: E731
+            return pooled.reshape(B, 2 * n, dim), cut(boxes), cut(img_ids), cut(obj_ids)
+        feats, boxes = vis_inputs
+        feats = self._pool(feats)
+        return feats, boxes[:, :feats.shape[1]]
+
+
+def _pad_mask(mask_2d: Optional[torch.Tensor], dtype, tgt_len: int):
+    """[B, S] 1/0 mask -> boolean [B, 1, T, S] for SDPA (True = attend); None stays None."""
+    if mask_2d is None:
+        return None
+    B, S = mask_2d.shape
+    return mask_2d.bool()[:, None, None, :].expand(B, 1, tgt_len, S)
+
+
+class JointEncoder(nn.Module):
+    """Text tokens (+ visual tokens appended) through the encoder stack (src/modeling_bart.py:696-898)."""
+
+    def __init__(self, config: VLPetConfig, embed_tokens: nn.Embedding):
+        super().__init__()
+        self.config = config
+        d = config.d_model
+        self.dropout = config.dropout
+        self.embed_scale = math.sqrt(d) if config.scale_embedding else 1.0
+        self.embed_tokens = embed_tokens
+        self.embed_positions = BartLearnedPositionalEmbedding(config.max_position_embeddings, d, config.pad_token_id)
+        self.layers = nn.ModuleList([BartEncoderLayer(config) for _ in range(config.encoder_layers)])
+        self.layernorm_embedding = nn.LayerNorm(d)
+        self.visual_embedding = VisualEmbedding(config, self.embed_tokens)
+        self.downsample = None
+        if config.downsample:
+            s = int(config.n_boxes ** 0.5)
+            self.downsample = Downsample((s, s))
+
+    def forward(self, input_ids, vis_inputs, attention_mask=None, vis_attention_mask=None, task=None):
+        B, L = input_ids.shape
+        x = self.embed_tokens(input_ids) * self.embed_scale + self.embed_positions(L)
+        if self.downsample is not None:
+            vis_inputs = self.downsample(vis_inputs)
+        feats, boxes = vis_inputs[0], vis_inputs[1]
+        img_ids = vis_inputs[2] if len(vis_inputs) >= 3 else None
+        obj_ids = vis_inputs[3] if len(vis_inputs) == 4 else None
+        vis = self.visual_embedding(feats.to(x.dtype), boxes, img_ids, obj_ids)                  # K3
+        if self.config.share_vis_lang_layer_norm:
+            x = _ln(self.layernorm_embedding, torch.cat([x, vis], dim=1))
+        else:
+            x = torch.cat([_ln(self.layernorm_embedding, x), vis], dim=1)
+        mask = None
+        if not self.config.assume_no_padding or attention_mask is not None or vis_attention_mask is not None:
+            if attention_mask is None:
+                attention_mask = input_ids.ne(self.config.pad_token_id)
+            if vis_attention_mask is None:
+                vis_attention_mask = attention_mask.new_ones(B, vis.shape[1])
+            mask = torch.cat([attention_mask.to(vis_attention_mask.dtype), vis_attention_mask], dim=1)
+        x = F.dropout(x, p=self.dropout, training=self.training)
+        sdpa_mask = _pad_mask(mask, x.dtype, x.shape[1])
+        for layer in self.layers:
+            x = layer(x, attn_mask=sdpa_mask, task=task)
+        return x, mask
+
+
+class BartDecoder(nn.Module):
+    def __init__(self, config: VLPetConfig, embed_tokens: nn.Embedding):
+        super().__init__()
+        self.config = config
+        d = config.d_model
+        self.dropout = config.dropout
+        self.embed_scale = math.sqrt(d) if config.scale_embedding else 1.0
+        self.embed_tokens = embed_tokens
+        self.embed_positions = BartLearnedPositionalEmbedding(config.max_position_embeddings, d, config.pad_token_id)
+        self.layers = nn.ModuleList([BartDecoderLayer(config) for _ in range(config.decoder_layers)])
+        self.layernorm_embedding = nn.LayerNorm(d)
+
+    def forward(self, input_ids, encoder_hidden_states, encoder_mask=None, task=None):
+        B, T = input_ids.shape
+        x = self.embed_tokens(input_ids) * self.embed_scale + self.embed_positions(T)
+        x = _ln(self.layernorm_embedding, x)
+        x = F.dropout(x, p=self.dropout, training=self.training)
+        cross = _pad_mask(encoder_mask, x.dtype, T)
+        for layer in self.layers:
+            x = layer(x, encoder_hidden_states, self_mask=None, cross_mask=cross, task=task)
+        return x
+
+
+class VLBartModel(nn.Module):
+    def __init__(self, config: VLPetConfig):
+        super().__init__()
+        self.config = config
+        self.shared = nn.Embedding(config.vocab_size, config.d_model, config.pad_token_id)
+        self.encoder = JointEncoder(config, self.shared)
+        self.decoder = BartDecoder(config, self.shared)
+
+    def forward(self, input_ids, vis_inputs, decoder_input_ids, attention_mask=None, vis_attention_mask=None, task=None):
+        enc, mask = self.encoder(input_ids, vis_inputs, attention_mask, vis_attention_mask, task=task)
+        return self.decoder(decoder_input_ids, enc, encoder_mask=mask, task=task)
+
+
+class VLBart(nn.Module):
+    """LM head + token-level cross-entropy with reduction='none' (src/modeling_bart.py:1522-1602) and the task
+    ``train_step`` loss shaping of vqa_model.py:167-233 / nlvr_model.py:140-262 / caption (plain mean over tokens)."""
+
+    def __init__(self, config: VLPetConfig):
+        super().__init__()
+        self.config = config
+        self.model = VLBartModel(config)
+        self.register_buffer("final_logits_bias", torch.zeros(1, config.vocab_size))
+        self.lm_head = nn.Linear(config.d_model, config.vocab_size, bias=False)
+        self.apply(self._init_weights)
+        self.lm_head.weight = self.model.shared.weight           # tied, as BartForConditionalGeneration
+
+    def _init_weights(self, m):
+        std = self.config.init_std                               # my_transformers/modeling_bart.py:1819-1828
+        if isinstance(m, nn.Linear):
+            m.weight.data.normal_(mean=0.0, std=std)
+            if m.bias is not None:
+                m.bias.data.zero_()
+        elif isinstance(m, nn.Embedding):
+            m.weight.data.normal_(mean=0.0, std=std)
+            if m.padding_idx is not None:
+                m.weight.data[m.padding_idx].zero_()
+
+    def forward(self, input_ids, vis_inputs, labels, attention_mask=None, vis_attention_mask=None, task=None):
+        """-> per-token loss [B*T] (reduction='none', ignore_index=-100) and logits."""
+        cfg = self.config
+        dec_in = shift_tokens_right(labels, cfg.pad_token_id, cfg.decoder_start_token_id)
+        h = self.model(input_ids, vis_inputs, dec_in, attention_mask, vis_attention_mask, task=task)
+        logits = F.linear(h, self.lm_head.weight) + self.final_logits_bias.to(h.dtype)
+        lg = logits.view(-1, cfg.vocab_size)
+        if lg.dtype in (torch.bfloat16, torch.float16):
+            lg = lg.float()
+        loss = F.cross_entropy(lg, labels.reshape(-1), ignore_index=-100, reduction="none")
+        return loss, logits
+
+    def train_step(self, batch: dict) -> dict:
+        """One task batch -> {'loss': scalar}.  Batch schema = the reference collate (vqa_clip_data.py:365-390):
+        input_ids [B,Lt] int64, vis_feats [B,N,F] ([B,2,N,F] for nlvr), boxes [B,N,4], target_ids [B,T] int64 with
+        -100 padding, optional scores [B], task str."""
+        dev = self.model.shared.weight.device
+        task = batch["task"]
+        input_ids = batch["input_ids"].to(dev, non_blocking=True)
+        feats = batch["vis_feats"].to(dev, non_blocking=True)
+        boxes = batch["boxes"].to(dev, non_blocking=True)
+        labels = batch["target_ids"].to(dev, non_blocking=True)
+        B = input_ids.shape[0]
+        if task == "nlvr":                                       # nlvr_model.py:156-176
+            V_L = feats.shape[2]
+            feats = feats.reshape(B, 2 * V_L, -1)
+            boxes = boxes.reshape(B, 2 * V_L, 4)
+            img_ids = torch.tensor([0] * V_L + [1] * V_L, dtype=torch.long, device=dev).view(1, -1).expand(B, -1)
+            obj_ids = torch.arange(V_L, dtype=torch.long, device=dev).view(1, 1, V_L).expand(B, 2, -1).reshape(B, 2 * V_L)
+            vis_inputs = (feats, boxes, img_ids, obj_ids)
+        else:
+            vis_inputs = (feats, boxes)
+        loss, _ = self(input_ids, vis_inputs, labels, task=task)
+        T = labels.shape[1]
+        mask = (labels != -100).float()
+        loss = loss.view(B, T) * mask
+        if task == "caption":                                    # caption_model.py: sum / count over the whole batch
+            loss = loss.sum() / mask.sum().clamp(min=1)
+        else:
+            loss = loss.sum(dim=1) / mask.sum(dim=1).clamp(min=1)
+            if "scores" in batch and batch["scores"] is not None:
+                loss = loss * batch["scores"].to(dev, non_blocking=True)
+            loss = loss.mean()
+        return {"loss": loss}
