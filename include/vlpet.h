@@ -178,6 +178,25 @@ VLPET_API int vlpet_k3_bwd(const VlpetK3Desc* desc, const void* feats, const voi
                  const void* dout, const VlpetK3Params* w, const float* save, void* dfeats /* may be NULL */,
                  const VlpetK3Grads* g, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- token-contracted weight-gradient GEMM (building block of the fused backward) -----------------------
+ * out_p[c, n] += scale_p * sum_tok A_p[tok, c] * B_p[tok, n]   (transposed_p: out_p[n, c] instead), up to 4 pairs per
+ * launch, bf16 operands, fp32 accumulate on the tensor cores (tcgen05), fp32 reductions into out.  These are the dW
+ * GEMMs the reference's autograd runs as separate addmm calls for every nn.Linear of a PET site
+ * (my_transformers/modeling_bart.py:1045-1056).  If nb_valid == nout + 1, column nout of B must be
+ * all ones and bias_p[c] += scale_p * sum_tok A_p[tok, c].  Requires d % 128 == 0, 8 <= nout <= 127.            */
+typedef struct VlpetWgradPair {
+  const void* A;     /* [Mtok, d] bf16, row pitch lda elements (multiple of 8)            */
+  int64_t lda;
+  const void* B;     /* [Mtok, nb_valid] bf16, row pitch ldb elements (multiple of 8)     */
+  int64_t ldb;
+  int32_t nb_valid;  /* nout or nout + 1                                                  */
+  int32_t transposed;
+  float* out;        /* fp32 [d, nout] or [nout, d], accumulated into                     */
+  float* bias;       /* fp32 [d] or NULL                                                  */
+  float scale;
+} VlpetWgradPair;
+VLPET_API int vlpet_wgrad_bf16(const VlpetWgradPair* pairs, int32_t npairs, int64_t Mtok, int32_t d, int32_t nout, void* stream);
+
 /* ---- PET parameter/gradient bucket helpers (rows a9 / C1 of SURVEY §8) -------------------------------- */
 /* dst_bf16[i] = bf16(src_f32[i]) : one launch refreshes the bf16 shadow of the whole flat PET bucket.    */
 VLPET_API int vlpet_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);

@@ -35,6 +35,11 @@ class K1Grads(C.Structure):
     _fields_ = [(n, _fp) for n in ("dWd", "dbd", "dWu", "dbu", "dGd", "dgbd", "dGu", "dgbu", "dgw", "dgb", "dgz")]
 
 
+class WgradPair(C.Structure):
+    _fields_ = [("A", _vp), ("lda", C.c_int64), ("B", _vp), ("ldb", C.c_int64), ("nb_valid", C.c_int32),
+                ("transposed", C.c_int32), ("out", _fp), ("bias", _fp), ("scale", C.c_float)]
+
+
 class K2Desc(C.Structure):
     _fields_ = [("M", C.c_int64), ("d", C.c_int32), ("r", C.c_int32), ("dtype", C.c_int32), ("impl", C.c_int32),
                 ("sf", C.c_float)]
@@ -83,6 +88,7 @@ SYMBOLS = {
                                _vp]),
     "vlpet_k3_bwd": (C.c_int, [C.POINTER(K3Desc), _vp, _vp, _vp, _vp, C.POINTER(K3Params), _vp, _vp,
                                C.POINTER(K3Grads), _vp, C.c_size_t, _vp]),
+    "vlpet_wgrad_bf16": (C.c_int, [C.POINTER(WgradPair), C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp]),
     "vlpet_cast_f32_to_bf16": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "vlpet_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_float, C.c_int32, _vp, _vp, _vp]),

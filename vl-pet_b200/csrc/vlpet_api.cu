@@ -9,6 +9,16 @@ char* tls_error_buffer() {
   return buf;
 }
 
+int device_sm_count() {
+  static int sms = []() {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+    return p.major == 10 ? p.multiProcessorCount : -1;
+  }();
+  return sms;
+}
+
 namespace {
 int check_k1(const VlpetK1Desc* D, const VlpetK1Params* w) {
   if (!D || !w) return fail(VLPET_E_BADARG, "k1: null desc/params");
@@ -80,6 +90,28 @@ int vlpet_k1_bwd(const VlpetK1Desc* D, const void* x1, const void* x2, const voi
     return fail(VLPET_E_ALIGN, "k1_bwd: activations must be 16-byte aligned");
   if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k1_bwd: no fused backward kernel yet");
   return generic_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// ---- weight-gradient GEMM ------------------------------------------------------------------------------------
+int vlpet_wgrad_bf16(const VlpetWgradPair* pairs, int32_t npairs, int64_t Mtok, int32_t d, int32_t nout, void* stream) {
+  if (!pairs || npairs < 1 || npairs > 4 || Mtok <= 0) return fail(VLPET_E_BADARG, "wgrad: bad arguments");
+  const void *A[4], *B[4];
+  int64_t lda[4], ldb[4];
+  int nbv[4], tr[4];
+  float *out[4], *bias[4], sc[4];
+  for (int i = 0; i < npairs; ++i) {
+    const VlpetWgradPair& q = pairs[i];
+    if (!q.A || !q.B || !q.out) return fail(VLPET_E_BADARG, "wgrad: null pointer in pair %d", i);
+    if (!aligned16(q.A) || !aligned16(q.B) || !aligned16(q.out) || (q.lda & 7) || (q.ldb & 7))
+      return fail(VLPET_E_ALIGN, "wgrad: operands must be 16-byte aligned with pitches that are multiples of 8");
+    if (q.nb_valid != nout && q.nb_valid != nout + 1) return fail(VLPET_E_BADARG, "wgrad: nb_valid must be nout or nout+1");
+    if (q.bias && q.nb_valid != nout + 1) return fail(VLPET_E_BADARG, "wgrad: bias needs the ones column (nb_valid = nout+1)");
+    A[i] = q.A; B[i] = q.B; lda[i] = q.lda; ldb[i] = q.ldb; nbv[i] = q.nb_valid; tr[i] = q.transposed;
+    out[i] = q.out; bias[i] = q.bias; sc[i] = q.scale;
+  }
+  int sms = device_sm_count();
+  if (sms <= 0) return fail(VLPET_E_NODEVICE, "wgrad: no CUDA device");
+  return wgrad_sm100(npairs, A, lda, B, ldb, nbv, out, bias, sc, tr, Mtok, d, nout, sms, static_cast<cudaStream_t>(stream));
 }
 
 // ---- K2 ----------------------------------------------------------------------------------------------------

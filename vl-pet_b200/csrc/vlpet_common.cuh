@@ -140,4 +140,11 @@ size_t fused_k1_fwd_ws(const VlpetK1Desc&);
 int fused_k1_fwd(const VlpetK1Desc&, const void* x1, const void* x2, const VlpetK1Params&, void* out, void* ws,
                  size_t ws_bytes, cudaStream_t);
 
+// ---- token-contracted weight-gradient GEMM (tcgen05), vlpet_wgrad_sm100.cu -----------------------------------
+bool wgrad_sm100_supported(int d, int nout);
+int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void* const* B, const int64_t* ldb,
+                const int* nb_valid, float* const* out, float* const* bias, const float* scale, const int* transposed,
+                int64_t Mtok, int d, int nout, int sm_count, cudaStream_t st);
+int device_sm_count();
+
 }  // namespace vlpet
