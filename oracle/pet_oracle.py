@@ -71,7 +71,7 @@ def stack_heads(head_weights, head_biases):
 # --------------------------------------------------------------------------------------------------------
 # K1: granularity-controlled PET module (encoder, after self-attention and after the FFN)
 # --------------------------------------------------------------------------------------------------------
-def gated_pet_fwd(x1, x2, p: Dict[str, np.ndarray], cfg: PetConfig):
+def gated_pet_fwd(x1, x2, p: Dict[str, np.ndarray], cfg: PetConfig, rnd=None):
     """out = x1 + s * gate(x1, y1),  y1 = kappa*x2 + alpha*Up(gelu_new(Down(x2))).
 
     Restates my_transformers/modeling_bart.py:1145-1155 (adapter), 1195-1231 (gates), 1256-1260 (scale,
@@ -84,16 +84,21 @@ def gated_pet_fwd(x1, x2, p: Dict[str, np.ndarray], cfg: PetConfig):
       middle_y: gz [d]                  (bare parameter)
       small:    gw [2d], gb []          (Linear(2d,1))
     Returns (out [M,d], cache).
+
+    ``rnd`` (optional, large gate only): a rounding function applied to the activations that feed the second GEMM
+    of each branch (z, q) -- and in the backward to du, dt, da, dp -- i.e. the points where a reference run in
+    bf16 stores an activation before the next nn.Linear consumes it.  rnd=None is exact arithmetic in the input dtype.
     """
+    R = rnd if (rnd is not None and cfg.gate == GATE_LARGE) else (lambda t: t)
     a = x2 @ p["Wd"].T + p["bd"]
-    z = gelu_new(a)
+    z = R(gelu_new(a))
     u = z @ p["Wu"].T + p["bu"]
     y1 = cfg.kappa * x2 + cfg.alpha * u
     c = dict(x1=x1, x2=x2, a=a, z=z, y1=y1)
     g = cfg.gate
     if g == GATE_LARGE:
         pp = x1 @ p["Gd"].T + p["gbd"]
-        q = gelu_new(pp)
+        q = R(gelu_new(pp))
         t = q @ p["Gu"].T + p["gbu"]
         G = sigmoid(t)
         c.update(p=pp, q=q, G=G)
@@ -123,10 +128,11 @@ def gated_pet_fwd(x1, x2, p: Dict[str, np.ndarray], cfg: PetConfig):
     return out, c
 
 
-def gated_pet_bwd(dout, p: Dict[str, np.ndarray], cfg: PetConfig, c):
+def gated_pet_bwd(dout, p: Dict[str, np.ndarray], cfg: PetConfig, c, rnd=None):
     """Analytic backward of gated_pet_fwd (SURVEY Appendix A for the large gate; the middle/small gates
     route an extra gradient through y1 and x1 into the gate).  Returns (dx1, dx2, grads dict)."""
     x1, x2, a, z, y1 = c["x1"], c["x2"], c["a"], c["z"], c["y1"]
+    R = rnd if (rnd is not None and cfg.gate == GATE_LARGE) else (lambda t: t)
     dh = cfg.s * dout
     gr: Dict[str, np.ndarray] = {}
     dx1 = dout.copy()
@@ -137,13 +143,14 @@ def gated_pet_bwd(dout, p: Dict[str, np.ndarray], cfg: PetConfig, c):
             dy1, dG = dh, dh
         else:
             dy1, dG = dh * G, dh * y1
-        dt = dG * G * (1.0 - G)
+        dt = R(dG * G * (1.0 - G))
         gr["Gu"] = dt.T @ c["q"]
         gr["gbu"] = dt.sum(0)
         dq = dt @ p["Gu"]
-        dp = dq * gelu_new_grad(c["p"])
+        dp_exact = dq * gelu_new_grad(c["p"])
+        dp = R(dp_exact)
         gr["Gd"] = dp.T @ x1
-        gr["gbd"] = dp.sum(0)
+        gr["gbd"] = dp_exact.sum(0)
         dx1 = dx1 + dp @ p["Gd"]
     elif g == GATE_MIDDLE_X:
         G = c["G"]
@@ -184,13 +191,14 @@ def gated_pet_bwd(dout, p: Dict[str, np.ndarray], cfg: PetConfig, c):
         dy1 = dh
     else:
         raise ValueError(g)
-    du = cfg.alpha * dy1
+    du = R(cfg.alpha * dy1)
     gr["Wu"] = du.T @ z
     gr["bu"] = du.sum(0)
     dz = du @ p["Wu"]
-    da = dz * gelu_new_grad(a)
+    da_exact = dz * gelu_new_grad(a)
+    da = R(da_exact)
     gr["Wd"] = da.T @ x2
-    gr["bd"] = da.sum(0)
+    gr["bd"] = da_exact.sum(0)
     dx2 = cfg.kappa * dy1 + da @ p["Wd"]
     return dx1, dx2, gr
 

@@ -39,14 +39,16 @@ def bf16_round(a):
     return torch.tensor(np.asarray(a), dtype=torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
 
 
-def bf16_check(ours, ref, tol):
+def bf16_check(ours, ref, tol, outlier=5.0):
     """Parity of a bf16-typed result `ours` (as float64) against the unrounded fp64 oracle `ref`.
 
     Storing a value in bf16 costs ~1.6e-3 rms relative by itself, so a 1e-3 bar can only be about the value BEFORE
     the final rounding.  That error delta is observable through the rounding flips: ours != round_bf16(ref) happens
     only when a rounding boundary lies between ref and ref+delta (so |ref - boundary| <= |delta|), and for a boundary
     uniformly placed inside that interval E|ref - boundary| = E|delta| / 2.  We therefore require
-      (1) every mismatch is between ADJACENT bf16 values, or (near-zero outputs) smaller than 5*tol*rms(ref) -- no outliers,
+      (1) every mismatch is between ADJACENT bf16 values, or (near-zero outputs) smaller than outlier*tol*rms(ref) -- no
+          outliers (outlier = 5; the tensor-core backward uses 20: a one-ulp flip of a bf16-STORED intermediate such as
+          da (|da| ~ 2 -> ulp 0.016) times |Wd| ~ 0.05 legitimately moves a whole row of dx2 by ~1e-3),
       (2) the estimated mean pre-rounding error  2 * mean_mismatch |ref - boundary| / rms(ref)  <= tol,
       (3) Frobenius error vs the correctly-rounded oracle <= 2 * tol  (a flip costs a whole ulp, which amplifies
           delta to ~sqrt(delta * ulp); two exact-to-1e-4 bf16 kernels disagree at the 1e-3 level for this reason).
@@ -63,7 +65,7 @@ def bf16_check(ours, ref, tol):
     big = np.maximum(np.abs(a), np.abs(b))
     ulp = 2.0 ** (np.floor(np.log2(np.maximum(big, 1e-38))) - 7)
     diff = np.abs(a - b)
-    assert np.all((diff <= ulp * 1.0001) | (diff <= 5 * tol * rms)), \
+    assert np.all((diff <= ulp * 1.0001) | (diff <= outlier * tol * rms)), \
         "bf16 outlier: %g ulp / %g of rms" % (float(np.max(diff / ulp)), float(np.max(diff) / rms))
     eff = 2.0 * float(np.mean(np.abs(ref[mism] - 0.5 * (a + b)))) / rms
     assert eff <= tol, "estimated pre-rounding error %g exceeds %g (relative to rms)" % (eff, tol)

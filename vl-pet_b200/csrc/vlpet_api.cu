@@ -37,6 +37,7 @@ int check_k1(const VlpetK1Desc* D, const VlpetK1Params* w) {
   return 0;
 }
 bool use_fused_fwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && fused_k1_fwd_supported(D); }
+bool use_fused_bwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && fused_k1_bwd_supported(D); }
 }  // namespace
 }  // namespace vlpet
 
@@ -61,13 +62,16 @@ int vlpet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
 
 // ---- K1 ----------------------------------------------------------------------------------------------------
 int vlpet_k1_fwd_is_fused(const VlpetK1Desc* D) { return D && use_fused_fwd(*D) ? 1 : 0; }
-int vlpet_k1_bwd_is_fused(const VlpetK1Desc*) { return 0; }
+int vlpet_k1_bwd_is_fused(const VlpetK1Desc* D) { return D && use_fused_bwd(*D) ? 1 : 0; }
 
 size_t vlpet_k1_fwd_workspace_bytes(const VlpetK1Desc* D) {
   if (!D) return 0;
   return use_fused_fwd(*D) ? fused_k1_fwd_ws(*D) : generic_k1_fwd_ws(*D);
 }
-size_t vlpet_k1_bwd_workspace_bytes(const VlpetK1Desc* D) { return D ? generic_k1_bwd_ws(*D) : 0; }
+size_t vlpet_k1_bwd_workspace_bytes(const VlpetK1Desc* D) {
+  if (!D) return 0;
+  return use_fused_bwd(*D) ? fused_k1_bwd_ws(*D) : generic_k1_bwd_ws(*D);
+}
 
 int vlpet_k1_fwd(const VlpetK1Desc* D, const void* x1, const void* x2, const VlpetK1Params* w, void* out, void* ws,
                  size_t ws_bytes, void* stream) {
@@ -88,7 +92,11 @@ int vlpet_k1_bwd(const VlpetK1Desc* D, const void* x1, const void* x2, const voi
   if (!x1 || !x2 || !dout || !dx1 || !dx2 || !g) return fail(VLPET_E_BADARG, "k1_bwd: null pointer");
   if (!aligned16(x1) || !aligned16(x2) || !aligned16(dout) || !aligned16(dx1) || !aligned16(dx2))
     return fail(VLPET_E_ALIGN, "k1_bwd: activations must be 16-byte aligned");
-  if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k1_bwd: no fused backward kernel yet");
+  if (use_fused_bwd(*D))
+    return fused_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  if (D->impl == VLPET_IMPL_FUSED)
+    return fail(VLPET_E_UNSUPPORTED, "k1_bwd: fused kernel does not cover d=%d r=%d rg=%d gate=%d dtype=%d", D->d, D->r,
+                D->rg, D->gate, D->dtype);
   return generic_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 

@@ -140,6 +140,12 @@ size_t fused_k1_fwd_ws(const VlpetK1Desc&);
 int fused_k1_fwd(const VlpetK1Desc&, const void* x1, const void* x2, const VlpetK1Params&, void* out, void* ws,
                  size_t ws_bytes, cudaStream_t);
 
+// fused K1 backward (activation gradients, vlpet_k1_bwd_sm100.cu) + the weight-gradient GEMMs below
+bool fused_k1_bwd_supported(const VlpetK1Desc&);
+size_t fused_k1_bwd_ws(const VlpetK1Desc&);
+int fused_k1_bwd(const VlpetK1Desc&, const void* x1, const void* x2, const void* dout, const VlpetK1Params&, void* dx1,
+                 void* dx2, const VlpetK1Grads&, void* ws, size_t ws_bytes, cudaStream_t);
+
 // ---- token-contracted weight-gradient GEMM (tcgen05), vlpet_wgrad_sm100.cu -----------------------------------
 bool wgrad_sm100_supported(int d, int nout);
 int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void* const* B, const int64_t* ldb,

@@ -1,0 +1,736 @@
+// K1 backward, fused, sm_100a ("B1"): activation gradients of the granularity-controlled PET module, large gate, in ONE
+// launch; the four token-contracted weight-gradient GEMMs run right after it in vlpet_wgrad_sm100.cu ("B2") from the
+// small intermediates this kernel leaves behind.  Math: SURVEY Appendix A / oracle gated_pet_bwd
+// (my_transformers/modeling_bart.py:1145-1155, 1195-1209, 1256-1260 differentiated).
+//
+// Persistent CTAs, one per SM, each walks 128-token tiles.  Per tile (nothing is saved by the forward: everything is
+// recomputed from x1 / x2):
+//   phase 1  (K = d)        A = x2 Wd^T, P = x1 Gd^T                                  tcgen05, fp32 accum in TMEM (kept)
+//   epi 1                   z = gelu_new(A+bd), q = gelu_new(P+gbd)                  -> swizzled smem (bf16) + scratch
+//   phase 2  (64-col chunks) U_c = z Wu_c^T, T_c = q Gu_c^T                           tcgen05
+//   epi 2                   y1 = k x2 + a(U+bu), G = sig(T+gbu), dh = s m dout,
+//                           du = a dh G, dt = dh y1 G(1-G)   (add-gate: du = a dh, dt = dh G(1-G))
+//                                                                                     -> in place over x2_c / dout_c in smem
+//            MMA            dz += du_c Wu_c, dq += dt_c Gu_c   (B operands MN-major from the SAME smem tiles of Wu_c/Gu_c)
+//            store          du_c, dt_c -> scratch (TMA store) for the weight-gradient GEMMs
+//   epi 3                   da = dz gelu_new'(A+bd), dp = dq gelu_new'(P+gbd)        -> smem (over z) + scratch; dbd, dgbd
+//   phase 3  (64-col chunks) T_c again (only G is needed; recompute beats keeping [128 x 768] gates),
+//                           DX2_c = da Wd[:,c], DX1_c = dp Gd[:,c]                    tcgen05 (B MN-major from Wd_c/Gd_c tiles)
+//   epi 4                   dx2 = k dh G + DX2, dx1 = dout + DX1                      -> smem -> TMA store
+// Warp roles: 0 TMA producer, 1 MMA issuer (TMEM owner), 2 TMA-store issuer, 3 idle, 4..11 epilogue (warp%4 = TMEM
+// lane quarter; (warp-4)/4 = "half": adapter branch / gate branch in epi 1/3, left / right 32 columns in epi 2/4).
+#include "sm100_ptx.cuh"
+#include "vlpet_common.cuh"
+
+namespace vlpet {
+int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows,
+                  uint32_t box_cols, bool weight);
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int CH = 64;
+constexpr int SX = 2;
+constexpr int SW = 2;
+constexpr int XCH_BYTES = TILE_M * CH * 2;  // 16 KB
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr int TM_A = 0, TM_P = 96, TM_DZ = 192, TM_DQ = 288, TM_UT = 384;  // phase 1-2 TMEM columns
+constexpr int TM_ACC = 128, ACC_STRIDE = 192;                              // phase 3: {T, DX2, DX1} x 2 buffers
+
+template <int R>
+struct BCfg {
+  static constexpr int KB = (R + 63) / 64;
+  static constexpr int WA_BYTES = R * CH * 2;        // [R x 64] chunk of Wd / Gd
+  static constexpr int WB_BYTES = KB * CH * CH * 2;  // [64 x KB*64] chunk of Wu / Gu
+  static constexpr int W3 = WB_BYTES + 2 * WA_BYTES;
+  static constexpr int W12 = (2 * WA_BYTES > 2 * WB_BYTES) ? 2 * WA_BYTES : 2 * WB_BYTES;
+  static constexpr int WSLOT = W3 > W12 ? W3 : W12;
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_W = OFF_X + SX * 2 * XCH_BYTES;
+  static constexpr int OFF_Z0 = OFF_W + SW * WSLOT;                      // z (later da), columns 0..63
+  static constexpr int OFF_Q0 = OFF_Z0 + XCH_BYTES;                      // q, columns 0..63
+  static constexpr int OFF_ZQ1 = OFF_Q0 + XCH_BYTES;                     // columns 64..95: z/da in bytes 0..63 of each row, q in 64..127
+  static constexpr int OFF_DP0 = OFF_ZQ1 + (KB == 2 ? XCH_BYTES : 0);
+  static constexpr int OFF_DP1 = OFF_DP0 + XCH_BYTES;
+  static constexpr int OFF_BAR = OFF_DP1 + (KB == 2 ? XCH_BYTES : 0);
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static_assert(R <= 96 && R % 16 == 0, "fused backward covers ranks up to 96");
+  static_assert(WSLOT % 1024 == 0 && WA_BYTES % 1024 == 0, "swizzle atoms must stay 1024-byte aligned");
+};
+
+struct BParams {
+  int64_t M;
+  int d, r, rg;
+  int add_gate;
+  float s, alpha, kappa;
+  const __nv_bfloat16 *bd, *bu, *gbd, *gbu;
+  __nv_bfloat16 *zs, *qs, *das, *dps;   // scratch [M, pz] / [M, pq]
+  int pz, pq;                           // scratch row pitches (elements)
+  float *dbd, *dgbd;                    // fp32 bias gradients (accumulated into) or nullptr
+  uint64_t seed;
+  uint32_t thr16;
+  float inv_keep;
+};
+
+enum { B_XFULL = 0, B_XEMPTY = B_XFULL + SX, B_WFULL = B_XEMPTY + SX, B_WEMPTY = B_WFULL + SW, B_APFULL = B_WEMPTY + SW,
+       B_ZQFULL, B_UTFULL, B_UTEMPTY, B_DUDT, B_DZQDONE = B_DUDT + SX, B_DZFULL = B_DZQDONE + SX, B_DAPFULL,
+       B_ACCFULL, B_ACCEMPTY = B_ACCFULL + 2, B_OUTRDY = B_ACCEMPTY + 2, B_COUNT = B_OUTRDY + SX };
+
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void gelu_new_both(float v, float& g, float& dg) {
+  const float c = 0.7978845608028654f, ck = 0.7978845608028654f * 0.044715f;
+  const float v2 = v * v;
+  const float th = ptx::tanh_approx(v * fmaf(ck, v2, c));
+  const float hv = 0.5f * v;
+  g = fmaf(hv, th, hv);
+  dg = fmaf(hv * (1.0f - th * th), fmaf(3.0f * ck, v2, c), 0.5f + 0.5f * th);
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t (&v)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t (&v)[4]) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+// Column sums over the 32 lanes of a warp: lane l enters with its row's 32 values, leaves with sum_rows column l in v[0].
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? v[i] : v[i + off];
+      const float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int R>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
+                    const __grid_constant__ CUtensorMap tm_dout, const __grid_constant__ CUtensorMap tm_dx1,
+                    const __grid_constant__ CUtensorMap tm_dx2, const __grid_constant__ CUtensorMap tm_du,
+                    const __grid_constant__ CUtensorMap tm_dt, const __grid_constant__ CUtensorMap tm_wd,
+                    const __grid_constant__ CUtensorMap tm_gd, const __grid_constant__ CUtensorMap tm_wu,
+                    const __grid_constant__ CUtensorMap tm_gu, const BParams p) {
+  using C = BCfg<R>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::OFF_BAR;
+  auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
+  const uint32_t tmem_slot = bar_base + 8u * B_COUNT;
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const int nkc = p.d / CH;
+  const int64_t num_tiles = (p.M + TILE_M - 1) / TILE_M;
+  const bool mulgate = p.add_gate == 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SX; ++i) {
+      ptx::mbar_init(bar(B_XFULL + i), 1); ptx::mbar_init(bar(B_XEMPTY + i), 1);
+      ptx::mbar_init(bar(B_DUDT + i), EPI_THREADS); ptx::mbar_init(bar(B_DZQDONE + i), 1);
+      ptx::mbar_init(bar(B_OUTRDY + i), EPI_THREADS);
+    }
+    for (int i = 0; i < SW; ++i) { ptx::mbar_init(bar(B_WFULL + i), 1); ptx::mbar_init(bar(B_WEMPTY + i), 1); }
+    ptx::mbar_init(bar(B_APFULL), 1);
+    ptx::mbar_init(bar(B_ZQFULL), EPI_THREADS);
+    ptx::mbar_init(bar(B_UTFULL), 1);
+    ptx::mbar_init(bar(B_UTEMPTY), EPI_THREADS);
+    ptx::mbar_init(bar(B_DZFULL), 1);
+    ptx::mbar_init(bar(B_DAPFULL), EPI_THREADS);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(B_ACCFULL + i), 1); ptx::mbar_init(bar(B_ACCEMPTY + i), EPI_THREADS); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_dout); ptx::prefetch_tmap(&tm_wd);
+    ptx::prefetch_tmap(&tm_gd); ptx::prefetch_tmap(&tm_wu); ptx::prefetch_tmap(&tm_gu);
+  }
+  if (warp == 2 && lane == 0) {
+    ptx::prefetch_tmap(&tm_dx1); ptx::prefetch_tmap(&tm_dx2); ptx::prefetch_tmap(&tm_du); ptx::prefetch_tmap(&tm_dt);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // K-major A-operand descriptor start of the k-th 16-element K step of z/da (which=0), q (1), dp (2)
+  auto small_a = [&](int which, int ks) -> uint32_t {
+    const uint32_t b0 = smem_base + (which == 0 ? C::OFF_Z0 : (which == 1 ? C::OFF_Q0 : C::OFF_DP0));
+    if (ks < 4) return b0 + (uint32_t)ks * 32u;
+    const uint32_t b1 = smem_base + (which == 2 ? C::OFF_DP1 : C::OFF_ZQ1) + (which == 1 ? 64u : 0u);
+    return b1 + (uint32_t)(ks - 4) * 32u;
+  };
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t xi = 0, wi = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = (int)(tile * TILE_M);
+        for (int ph = 0; ph < 3; ++ph) {
+          for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
+            const uint32_t sx = xi % SX, sw = wi % SW;
+            ptx::mbar_wait(bar(B_XEMPTY + sx), ((xi / SX) & 1) ^ 1);
+            const uint32_t xdst = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
+            if (ph == 0) {
+              ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), 2 * XCH_BYTES);
+              ptx::tma_load_2d(xdst, &tm_x1, c * CH, row0, bar(B_XFULL + sx));
+              ptx::tma_load_2d(xdst + XCH_BYTES, &tm_x2, c * CH, row0, bar(B_XFULL + sx));
+            } else if (ph == 1) {
+              ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), 2 * XCH_BYTES);
+              ptx::tma_load_2d(xdst, &tm_x2, c * CH, row0, bar(B_XFULL + sx));
+              ptx::tma_load_2d(xdst + XCH_BYTES, &tm_dout, c * CH, row0, bar(B_XFULL + sx));
+            } else {
+              ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), XCH_BYTES);
+              ptx::tma_load_2d(xdst, &tm_dout, c * CH, row0, bar(B_XFULL + sx));
+            }
+            ptx::mbar_wait(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1);
+            const uint32_t wdst = smem_base + C::OFF_W + sw * C::WSLOT;
+            if (ph == 0) {
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), 2 * C::WA_BYTES);
+              ptx::tma_load_2d(wdst, &tm_wd, c * CH, 0, bar(B_WFULL + sw));
+              ptx::tma_load_2d(wdst + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
+            } else if (ph == 1) {
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), 2 * C::WB_BYTES);
+#pragma unroll
+              for (int kb = 0; kb < C::KB; ++kb) {
+                ptx::tma_load_2d(wdst + kb * (CH * CH * 2), &tm_wu, kb * CH, c * CH, bar(B_WFULL + sw));
+                ptx::tma_load_2d(wdst + C::WB_BYTES + kb * (CH * CH * 2), &tm_gu, kb * CH, c * CH, bar(B_WFULL + sw));
+              }
+            } else {
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (mulgate ? C::WB_BYTES : 0) + 2 * C::WA_BYTES);
+              if (mulgate) {
+#pragma unroll
+                for (int kb = 0; kb < C::KB; ++kb)
+                  ptx::tma_load_2d(wdst + kb * (CH * CH * 2), &tm_gu, kb * CH, c * CH, bar(B_WFULL + sw));
+              }
+              ptx::tma_load_2d(wdst + C::WB_BYTES, &tm_wd, c * CH, 0, bar(B_WFULL + sw));
+              ptx::tma_load_2d(wdst + C::WB_BYTES + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_AP = ptx::umma_idesc_bf16_m128(R);                       // A/P: N = R, K-major x K-major
+      constexpr uint32_t IDESC_UT = ptx::umma_idesc_bf16_m128(CH);                      // U/T: N = 64
+      constexpr uint32_t IDESC_DZ = ptx::umma_idesc_bf16_m128_major(R, 0u, 1u);         // dz/dq: B MN-major, N = R
+      constexpr uint32_t IDESC_DX = ptx::umma_idesc_bf16_m128_major(CH, 0u, 1u);        // DX: B MN-major, N = 64
+      uint32_t xi = 0, wi = 0, ui = 0, p2i = 0, ai = 0, ti = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        // the phase-3 accumulators of the previous tile overlap P / DZ / DQ / UT: wait until the epilogue drained them
+        if (ai > 0) {
+          for (uint32_t b = 0; b < 2; ++b) {
+            const uint32_t nb = (ai + 1 - b) >> 1;
+            if (nb > 0) ptx::mbar_wait(bar(B_ACCEMPTY + b), (nb - 1) & 1);
+          }
+          ptx::tc_fence_after();
+        }
+        // ---- phase 1
+        for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
+          const uint32_t sx = xi % SX, sw = wi % SW;
+          ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+          ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
+          ptx::tc_fence_after();
+          const uint32_t x1s = smem_base + C::OFF_X + sx * (2 * XCH_BYTES), x2s = x1s + XCH_BYTES;
+          const uint32_t wds = smem_base + C::OFF_W + sw * C::WSLOT, gds = wds + C::WA_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < CH / 16; ++ks) {
+            const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
+            ptx::umma_bf16_ss(tmem_base + TM_A, ptx::umma_desc_kmajor_sw128(x2s + ks * 32),
+                              ptx::umma_desc_kmajor_sw128(wds + ks * 32), IDESC_AP, acc);
+            ptx::umma_bf16_ss(tmem_base + TM_P, ptx::umma_desc_kmajor_sw128(x1s + ks * 32),
+                              ptx::umma_desc_kmajor_sw128(gds + ks * 32), IDESC_AP, acc);
+          }
+          ptx::umma_commit(bar(B_XEMPTY + sx));
+          ptx::umma_commit(bar(B_WEMPTY + sw));
+        }
+        ptx::umma_commit(bar(B_APFULL));
+        // ---- phase 2
+        ptx::mbar_wait(bar(B_ZQFULL), ti & 1);
+        ptx::tc_fence_after();
+        const uint32_t xi2 = xi, wi2 = wi, p2i0 = p2i;
+        auto issue_dzdq = [&](int cc) {
+          const uint32_t sx = (xi2 + cc) % SX, sw = (wi2 + cc) % SW, k = (p2i0 + cc) % SX;
+          ptx::mbar_wait(bar(B_DUDT + k), ((p2i0 + cc) / SX) & 1);
+          ptx::tc_fence_after();
+          const uint32_t dus = smem_base + C::OFF_X + sx * (2 * XCH_BYTES), dts = dus + XCH_BYTES;
+          const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT, gus = wus + C::WB_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < CH / 16; ++ks) {
+            const uint32_t acc = (cc > 0 || ks > 0) ? 1u : 0u;
+            ptx::umma_bf16_ss(tmem_base + TM_DZ, ptx::umma_desc_kmajor_sw128(dus + ks * 32),
+                              ptx::umma_desc_mnmajor_sw128(wus + ks * 2048, CH * CH * 2), IDESC_DZ, acc);
+            ptx::umma_bf16_ss(tmem_base + TM_DQ, ptx::umma_desc_kmajor_sw128(dts + ks * 32),
+                              ptx::umma_desc_mnmajor_sw128(gus + ks * 2048, CH * CH * 2), IDESC_DZ, acc);
+          }
+          ptx::umma_commit(bar(B_DZQDONE + k));
+          ptx::umma_commit(bar(B_WEMPTY + sw));
+        };
+        for (int c = 0; c < nkc; ++c, ++xi, ++wi, ++ui, ++p2i) {
+          const uint32_t sw = wi % SW;
+          ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
+          ptx::mbar_wait(bar(B_UTEMPTY), (ui & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT, gus = wus + C::WB_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < R / 16; ++ks) {
+            const uint32_t kb = ks / 4, kin = ks % 4;
+            ptx::umma_bf16_ss(tmem_base + TM_UT, ptx::umma_desc_kmajor_sw128(small_a(0, ks)),
+                              ptx::umma_desc_kmajor_sw128(wus + kb * (CH * CH * 2) + kin * 32), IDESC_UT, ks > 0);
+            ptx::umma_bf16_ss(tmem_base + TM_UT + CH, ptx::umma_desc_kmajor_sw128(small_a(1, ks)),
+                              ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_UT, ks > 0);
+          }
+          ptx::umma_commit(bar(B_UTFULL));
+          if (c > 0) issue_dzdq(c - 1);
+        }
+        issue_dzdq(nkc - 1);
+        ptx::umma_commit(bar(B_DZFULL));
+        // ---- phase 3
+        ptx::mbar_wait(bar(B_DAPFULL), ti & 1);
+        ptx::tc_fence_after();
+        for (int c = 0; c < nkc; ++c, ++xi, ++wi, ++ai) {
+          const uint32_t sw = wi % SW, b = ai & 1;
+          ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
+          ptx::mbar_wait(bar(B_ACCEMPTY + b), ((ai >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t gus = smem_base + C::OFF_W + sw * C::WSLOT, wds = gus + C::WB_BYTES, gds = wds + C::WA_BYTES;
+          const uint32_t tacc = tmem_base + TM_ACC + b * ACC_STRIDE;
+#pragma unroll
+          for (int ks = 0; ks < R / 16; ++ks) {
+            const uint32_t kb = ks / 4, kin = ks % 4;
+            if (mulgate)
+              ptx::umma_bf16_ss(tacc, ptx::umma_desc_kmajor_sw128(small_a(1, ks)),
+                                ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_UT, ks > 0);
+            ptx::umma_bf16_ss(tacc + CH, ptx::umma_desc_kmajor_sw128(small_a(0, ks)),
+                              ptx::umma_desc_mnmajor_sw128(wds + ks * 2048, C::WA_BYTES), IDESC_DX, ks > 0);
+            ptx::umma_bf16_ss(tacc + 2 * CH, ptx::umma_desc_kmajor_sw128(small_a(2, ks)),
+                              ptx::umma_desc_mnmajor_sw128(gds + ks * 2048, C::WA_BYTES), IDESC_DX, ks > 0);
+          }
+          ptx::umma_commit(bar(B_WEMPTY + sw));
+          ptx::umma_commit(bar(B_ACCFULL + b));
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================== TMA store issuer =====================================
+    if (lane == 0) {
+      uint32_t xi = 0, p2i = 0, p3i = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = (int)(tile * TILE_M);
+        xi += nkc;  // phase-1 stages are released by the MMA warp
+        for (int c = 0; c < nkc; ++c, ++xi, ++p2i) {
+          const uint32_t sx = xi % SX, k = p2i % SX;
+          ptx::mbar_wait(bar(B_DUDT + k), (p2i / SX) & 1);
+          const uint32_t src = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
+          ptx::tma_store_2d(&tm_du, src, c * CH, row0);
+          ptx::tma_store_2d(&tm_dt, src + XCH_BYTES, c * CH, row0);
+          ptx::tma_store_commit();
+          ptx::mbar_wait(bar(B_DZQDONE + k), (p2i / SX) & 1);   // dz/dq MMAs finished reading du_c / dt_c
+          ptx::tma_store_wait_read0();
+          ptx::mbar_arrive(bar(B_XEMPTY + sx));
+        }
+        for (int c = 0; c < nkc; ++c, ++xi, ++p3i) {
+          const uint32_t sx = xi % SX, k = p3i % SX;
+          ptx::mbar_wait(bar(B_OUTRDY + k), (p3i / SX) & 1);
+          const uint32_t src = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
+          ptx::tma_store_2d(&tm_dx1, src, c * CH, row0);
+          ptx::tma_store_2d(&tm_dx2, src + XCH_BYTES, c * CH, row0);
+          ptx::tma_store_commit();
+          ptx::tma_store_wait_read0();
+          ptx::mbar_arrive(bar(B_XEMPTY + sx));
+        }
+      }
+      ptx::tma_store_wait_all0();
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue warps =====================================
+    const int quarter = warp % 4;
+    const int half = (warp - 4) / 4;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t swz = (uint32_t)(row & 7);
+    float bias_acc[R / 32 > 0 ? R / 32 : 1];
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) bias_acc[i] = 0.f;
+    // smem address of the 16-byte group holding columns [k, k+8) of this thread's row in z/da (which=0), q (1), dp (2)
+    auto small_addr = [&](int which, int k) -> uint32_t {
+      if (k < 64) {
+        const uint32_t b0 = smem_base + (which == 0 ? C::OFF_Z0 : (which == 1 ? C::OFF_Q0 : C::OFF_DP0));
+        return b0 + (uint32_t)row * 128u + ((((uint32_t)k >> 3) ^ swz) << 4);
+      }
+      const uint32_t b1 = smem_base + (which == 2 ? C::OFF_DP1 : C::OFF_ZQ1);
+      const uint32_t c16 = (((uint32_t)k - 64u) >> 3) + (which == 1 ? 4u : 0u);
+      return b1 + (uint32_t)row * 128u + ((c16 ^ swz) << 4);
+    };
+    uint32_t xi = 0, ui = 0, p2i = 0, ai = 0, ti = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      const int64_t grow = tile * TILE_M + row;
+      const bool row_ok = grow < p.M;
+      // ---- epilogue 1 (APFULL also implies that every MMA of the previous tile, which read z/q/da/dp, has completed)
+      ptx::mbar_wait(bar(B_APFULL), ti & 1);
+      ptx::tc_fence_after();
+      {
+        const uint32_t tsrc = lane_addr + (half ? TM_P : TM_A);
+        const __nv_bfloat16* bias = half ? p.gbd : p.bd;
+        const int rr = half ? p.rg : p.r;
+        __nv_bfloat16* srow = (half ? p.qs + grow * p.pq : p.zs + grow * p.pz);
+#pragma unroll
+        for (int j0 = 0; j0 < R; j0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tsrc + j0, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j0 + g * 8 + e * 2;
+              const float b0 = (j < rr) ? __bfloat162float(bias[j]) : 0.f;
+              const float b1 = (j + 1 < rr) ? __bfloat162float(bias[j + 1]) : 0.f;
+              float z0, z1, d0, d1;
+              gelu_new_both(__uint_as_float(v[g * 8 + e * 2]) + b0, z0, d0);
+              gelu_new_both(__uint_as_float(v[g * 8 + e * 2 + 1]) + b1, z1, d1);
+              o[e] = pack_bf16(z0, z1);
+            }
+            const int k = j0 + g * 8;
+            sts128(small_addr(half, k), o);
+            if (row_ok && k < rr) *reinterpret_cast<uint4*>(srow + k) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        if (row_ok) {  // ones column (bias-gradient trick of the weight-gradient GEMM) + zero pad up to the pitch
+          const uint4 one = make_uint4(0x00003F80u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(srow + rr) = one;
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(B_ZQFULL));
+      xi += nkc;
+      // ---- epilogue 2, per 64-column chunk: du, dt
+      for (int c = 0; c < nkc; ++c, ++xi, ++ui, ++p2i) {
+        const uint32_t sx = xi % SX;
+        ptx::mbar_wait(bar(B_UTFULL), ui & 1);
+        ptx::tc_fence_after();
+        uint32_t u[32], t[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_UT + half * 32, u);
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_UT + CH + half * 32, t);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(bar(B_UTEMPTY));
+        ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+        const uint32_t x2row = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
+        const uint32_t dorow = x2row + XCH_BYTES;
+        const int col0 = c * CH + half * 32;
+        const int64_t idx0 = grow * p.d + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint64_t hsh[2] = {0, 0};
+          if (p.thr16) {
+            hsh[0] = drop_hash4(p.seed, (uint64_t)(idx0 + g * 8) >> 2);
+            hsh[1] = drop_hash4(p.seed, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
+          }
+          const uint32_t off = (((uint32_t)(half * 4 + g)) ^ swz) << 4;
+          uint32_t xv[4], dv[4], ou[4], ot[4];
+          lds128(x2row + off, xv);
+          lds128(dorow + off, dv);
+          const uint4 bu4 = __ldg(reinterpret_cast<const uint4*>(p.bu + col0 + g * 8));
+          const uint4 gb4 = __ldg(reinterpret_cast<const uint4*>(p.gbu + col0 + g * 8));
+          const uint32_t buw[4] = {bu4.x, bu4.y, bu4.z, bu4.w}, gbw[4] = {gb4.x, gb4.y, gb4.z, gb4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float du2[2], dt2[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int j = g * 8 + e * 2 + h2;
+              const float x2f = h2 ? bf_hi(xv[e]) : bf_lo(xv[e]);
+              const float dof = h2 ? bf_hi(dv[e]) : bf_lo(dv[e]);
+              const float buf = h2 ? bf_hi(buw[e]) : bf_lo(buw[e]);
+              const float gbf = h2 ? bf_hi(gbw[e]) : bf_lo(gbw[e]);
+              float sc = p.s;
+              if (p.thr16) {
+                const uint32_t two = (uint32_t)(hsh[e >> 1] >> (32 * (e & 1)));
+                const uint32_t bits = h2 ? (two >> 16) : (two & 0xffffu);
+                sc = (bits >= p.thr16) ? p.s * p.inv_keep : 0.f;
+              }
+              const float dh = sc * dof;
+              const float th = ptx::tanh_approx(0.5f * (__uint_as_float(t[j]) + gbf));
+              const float G = fmaf(0.5f, th, 0.5f);
+              const float gg = 0.25f * (1.0f - th * th);  // G (1 - G)
+              if (mulgate) {
+                const float y1 = fmaf(p.kappa, x2f, p.alpha * (__uint_as_float(u[j]) + buf));
+                du2[h2] = p.alpha * dh * G;
+                dt2[h2] = dh * y1 * gg;
+              } else {
+                du2[h2] = p.alpha * dh;
+                dt2[h2] = dh * gg;
+              }
+            }
+            ou[e] = pack_bf16(du2[0], du2[1]);
+            ot[e] = pack_bf16(dt2[0], dt2[1]);
+          }
+          sts128(x2row + off, ou);
+          sts128(dorow + off, ot);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(bar(B_DUDT + (p2i % SX)));
+      }
+      // ---- epilogue 3: da = dz * gelu_new'(A + bd) (half 0), dp = dq * gelu_new'(P + gbd) (half 1)
+      ptx::mbar_wait(bar(B_DZFULL), ti & 1);
+      ptx::tc_fence_after();
+      {
+        const uint32_t tpre = lane_addr + (half ? TM_P : TM_A);
+        const uint32_t tdz = lane_addr + (half ? TM_DQ : TM_DZ);
+        const __nv_bfloat16* bias = half ? p.gbd : p.bd;
+        const int rr = half ? p.rg : p.r;
+        __nv_bfloat16* srow = (half ? p.dps + grow * p.pq : p.das + grow * p.pz);
+#pragma unroll
+        for (int j0 = 0; j0 < R; j0 += 32) {
+          uint32_t a[32], dz[32];
+          ptx::tmem_ld_32x32b_x32(tpre + j0, a);
+          ptx::tmem_ld_32x32b_x32(tdz + j0, dz);
+          ptx::tmem_ld_wait();
+          float da[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float b = (j0 + j < rr) ? __bfloat162float(bias[j0 + j]) : 0.f;
+            float gz, dg;
+            gelu_new_both(__uint_as_float(a[j]) + b, gz, dg);
+            da[j] = __uint_as_float(dz[j]) * dg;
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = pack_bf16(da[g * 8 + e * 2], da[g * 8 + e * 2 + 1]);
+            const int k = j0 + g * 8;
+            sts128(small_addr(half ? 2 : 0, k), o);
+            if (row_ok && k < rr) *reinterpret_cast<uint4*>(srow + k) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          bias_acc[j0 / 32] += warp_colsum32(da, lane);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(B_DAPFULL));
+      // ---- epilogue 4, per 64-column chunk: dx1, dx2
+      for (int c = 0; c < nkc; ++c, ++xi, ++ai) {
+        const uint32_t sx = xi % SX, b = ai & 1;
+        ptx::mbar_wait(bar(B_ACCFULL + b), (ai >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t tacc = lane_addr + TM_ACC + b * ACC_STRIDE + half * 32;
+        uint32_t t[32], g2[32], g1[32];
+        if (mulgate) ptx::tmem_ld_32x32b_x32(tacc, t);
+        ptx::tmem_ld_32x32b_x32(tacc + CH, g2);
+        ptx::tmem_ld_32x32b_x32(tacc + 2 * CH, g1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(bar(B_ACCEMPTY + b));
+        ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+        const uint32_t dorow = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
+        const uint32_t o2row = dorow + XCH_BYTES;
+        const int col0 = c * CH + half * 32;
+        const int64_t idx0 = grow * p.d + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint64_t hsh[2] = {0, 0};
+          if (p.thr16) {
+            hsh[0] = drop_hash4(p.seed, (uint64_t)(idx0 + g * 8) >> 2);
+            hsh[1] = drop_hash4(p.seed, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
+          }
+          const uint32_t off = (((uint32_t)(half * 4 + g)) ^ swz) << 4;
+          uint32_t dv[4], o1[4], o2[4];
+          lds128(dorow + off, dv);
+          uint32_t gbw[4] = {0, 0, 0, 0};
+          if (mulgate) {
+            const uint4 gb4 = __ldg(reinterpret_cast<const uint4*>(p.gbu + col0 + g * 8));
+            gbw[0] = gb4.x; gbw[1] = gb4.y; gbw[2] = gb4.z; gbw[3] = gb4.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float r1[2], r2[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int j = g * 8 + e * 2 + h2;
+              const float dof = h2 ? bf_hi(dv[e]) : bf_lo(dv[e]);
+              float sc = p.s;
+              if (p.thr16) {
+                const uint32_t two = (uint32_t)(hsh[e >> 1] >> (32 * (e & 1)));
+                const uint32_t bits = h2 ? (two >> 16) : (two & 0xffffu);
+                sc = (bits >= p.thr16) ? p.s * p.inv_keep : 0.f;
+              }
+              float dy1 = sc * dof;
+              if (mulgate) {
+                const float gbf = h2 ? bf_hi(gbw[e]) : bf_lo(gbw[e]);
+                const float th = ptx::tanh_approx(0.5f * (__uint_as_float(t[j]) + gbf));
+                dy1 *= fmaf(0.5f, th, 0.5f);
+              }
+              r2[h2] = fmaf(p.kappa, dy1, __uint_as_float(g2[j]));
+              r1[h2] = dof + __uint_as_float(g1[j]);
+            }
+            o1[e] = pack_bf16(r1[0], r1[1]);
+            o2[e] = pack_bf16(r2[0], r2[1]);
+          }
+          sts128(dorow + off, o1);
+          sts128(o2row + off, o2);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(bar(B_OUTRDY + (ai % SX)));
+      }
+    }
+    // ---- bias gradients of the two down projections: one atomic per warp and column
+    float* dst = half ? p.dgbd : p.dbd;
+    const int rr = half ? p.rg : p.r;
+    if (dst) {
+#pragma unroll
+      for (int i = 0; i < R / 32; ++i)
+        if (i * 32 + lane < rr) atomicAdd(dst + i * 32 + lane, bias_acc[i]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int pick_R(const VlpetK1Desc& D) {
+  const int m = D.r > D.rg ? D.r : D.rg;
+  if (m <= 32) return 32;
+  if (m <= 64) return 64;
+  if (m <= 96) return 96;
+  return 0;
+}
+
+struct Scratch {
+  __nv_bfloat16 *zs, *qs, *das, *dps, *dus, *dts;
+  int pz, pq;
+  size_t bytes;
+};
+Scratch carve(const VlpetK1Desc& D, void* ws) {
+  Scratch s;
+  s.pz = (D.r + 1 + 7) / 8 * 8;
+  s.pq = (D.rg + 1 + 7) / 8 * 8;
+  Arena a(ws, (size_t)-1);
+  s.zs = a.take<__nv_bfloat16>((size_t)D.M * s.pz);
+  s.qs = a.take<__nv_bfloat16>((size_t)D.M * s.pq);
+  s.das = a.take<__nv_bfloat16>((size_t)D.M * s.pz);
+  s.dps = a.take<__nv_bfloat16>((size_t)D.M * s.pq);
+  s.dus = a.take<__nv_bfloat16>((size_t)D.M * D.d);
+  s.dts = a.take<__nv_bfloat16>((size_t)D.M * D.d);
+  s.bytes = a.off;
+  return s;
+}
+
+template <int R>
+int launch(const VlpetK1Desc& D, const CUtensorMap* m, const BParams& p, int sms, cudaStream_t st) {
+  using C = BCfg<R>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLPET_CUDA_OK(cudaFuncSetAttribute(k1_bwd_sm100_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  k1_bwd_sm100_kernel<R><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9],
+                                                                  m[10], p);
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+bool fused_k1_bwd_supported(const VlpetK1Desc& D) {
+  if (D.dtype != VLPET_BF16 || D.gate != VLPET_GATE_LARGE) return false;
+  if (D.d % 128 != 0 || D.d < 128) return false;
+  if (D.r % 8 != 0 || D.rg % 8 != 0 || D.r < 8 || D.rg < 8 || pick_R(D) == 0) return false;
+  if (D.M <= 0 || D.M > (int64_t)0x7fffff00) return false;
+  return device_sm_count() > 0 && wgrad_sm100_supported(D.d, D.r) && wgrad_sm100_supported(D.d, D.rg);
+}
+
+size_t fused_k1_bwd_ws(const VlpetK1Desc& D) { return carve(D, nullptr).bytes; }
+
+int fused_k1_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const void* dout, const VlpetK1Params& w, void* dx1,
+                 void* dx2, const VlpetK1Grads& G, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!aligned16(w.Wd) || !aligned16(w.Wu) || !aligned16(w.Gd) || !aligned16(w.Gu) || !aligned16(w.bu) || !aligned16(w.gbu))
+    return fail(VLPET_E_ALIGN, "k1_bwd(fused): weights must be 16-byte aligned");
+  Scratch s = carve(D, ws);
+  if (!ws || ws_bytes < s.bytes) return fail(VLPET_E_WORKSPACE, "k1_bwd(fused): workspace %zu < %zu bytes", ws_bytes, s.bytes);
+  const int R = pick_R(D);
+  const int sms = device_sm_count();
+  CUtensorMap m[11];
+  const uint64_t M = (uint64_t)D.M, d = (uint64_t)D.d;
+  VLPET_TRY(make_map_bf16(&m[0], x1, M, d, d, TILE_M, CH, false));
+  VLPET_TRY(make_map_bf16(&m[1], x2, M, d, d, TILE_M, CH, false));
+  VLPET_TRY(make_map_bf16(&m[2], dout, M, d, d, TILE_M, CH, false));
+  VLPET_TRY(make_map_bf16(&m[3], dx1, M, d, d, TILE_M, CH, false));
+  VLPET_TRY(make_map_bf16(&m[4], dx2, M, d, d, TILE_M, CH, false));
+  VLPET_TRY(make_map_bf16(&m[5], s.dus, M, d, d, TILE_M, CH, false));
+  VLPET_TRY(make_map_bf16(&m[6], s.dts, M, d, d, TILE_M, CH, false));
+  VLPET_TRY(make_map_bf16(&m[7], w.Wd, (uint64_t)D.r, d, d, (uint32_t)R, CH, true));
+  VLPET_TRY(make_map_bf16(&m[8], w.Gd, (uint64_t)D.rg, d, d, (uint32_t)R, CH, true));
+  VLPET_TRY(make_map_bf16(&m[9], w.Wu, d, (uint64_t)D.r, (uint64_t)D.r, CH, CH, true));
+  VLPET_TRY(make_map_bf16(&m[10], w.Gu, d, (uint64_t)D.rg, (uint64_t)D.rg, CH, CH, true));
+  BParams p;
+  p.M = D.M; p.d = D.d; p.r = D.r; p.rg = D.rg; p.add_gate = D.add_gate;
+  p.s = D.s; p.alpha = D.alpha; p.kappa = D.kappa;
+  p.bd = static_cast<const __nv_bfloat16*>(w.bd); p.bu = static_cast<const __nv_bfloat16*>(w.bu);
+  p.gbd = static_cast<const __nv_bfloat16*>(w.gbd); p.gbu = static_cast<const __nv_bfloat16*>(w.gbu);
+  p.zs = s.zs; p.qs = s.qs; p.das = s.das; p.dps = s.dps; p.pz = s.pz; p.pq = s.pq;
+  p.dbd = G.dbd; p.dgbd = G.dgbd;
+  p.seed = D.seed;
+  p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
+  p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
+  int rc = 0;
+  switch (R) {
+    case 32: rc = launch<32>(D, m, p, sms, st); break;
+    case 64: rc = launch<64>(D, m, p, sms, st); break;
+    case 96: rc = launch<96>(D, m, p, sms, st); break;
+    default: return fail(VLPET_E_UNSUPPORTED, "k1_bwd(fused): unsupported rank");
+  }
+  if (rc) return rc;
+  // ---- weight gradients: dWu = du^T z (+dbu), dGu = dt^T q (+dgbu), dWd = (x2^T da)^T, dGd = (x1^T dp)^T
+  const void* A[4]; const void* B[4]; int64_t lda[4], ldb[4]; int nbv[4], tr[4]; float* out[4]; float* bias[4]; float sc[4];
+  auto run = [&](const int* which, int n, int nout) -> int {
+    int k = 0;
+    for (int i = 0; i < n; ++i) {
+      const int q = which[i];
+      float* o = q == 0 ? G.dWu : (q == 1 ? G.dGu : (q == 2 ? G.dWd : G.dGd));
+      float* b = q == 0 ? G.dbu : (q == 1 ? G.dgbu : nullptr);
+      if (!o && !b) continue;
+      if (!o) return fail(VLPET_E_BADARG, "k1_bwd(fused): a bias gradient needs its weight gradient buffer");
+      A[k] = q == 0 ? (const void*)s.dus : (q == 1 ? (const void*)s.dts : (q == 2 ? x2 : x1));
+      lda[k] = D.d;
+      B[k] = q == 0 ? s.zs : (q == 1 ? s.qs : (q == 2 ? s.das : s.dps));
+      ldb[k] = (q == 0 || q == 2) ? s.pz : s.pq;
+      nbv[k] = (q < 2) ? nout + 1 : nout;
+      tr[k] = q >= 2;
+      out[k] = o; bias[k] = b; sc[k] = 1.0f;
+      ++k;
+    }
+    if (k == 0) return 0;
+    return wgrad_sm100(k, A, lda, B, ldb, nbv, out, bias, sc, tr, D.M, D.d, nout, sms, st);
+  };
+  if (D.r == D.rg) {
+    const int all[4] = {0, 1, 2, 3};
+    return run(all, 4, D.r);
+  }
+  const int ad[2] = {0, 2}, ga[2] = {1, 3};
+  VLPET_TRY(run(ad, 2, D.r));
+  return run(ga, 2, D.rg);
+}
+
+}  // namespace vlpet
