@@ -138,6 +138,8 @@ VLPET_API size_t vlpet_k2_fwd_workspace_bytes(const VlpetK2Desc* desc);
 VLPET_API size_t vlpet_k2_bwd_workspace_bytes(const VlpetK2Desc* desc);
 VLPET_API int vlpet_k2_fwd(const VlpetK2Desc* desc, const void* kv, const void* y, const VlpetK2Params* w, void* out,
                  void* workspace, size_t workspace_bytes, void* stream);
+/* 1 if vlpet_k2_fwd (with y != NULL) / vlpet_k2_bwd (with dkv != NULL) run the fused tcgen05 kernels for this desc */
+VLPET_API int vlpet_k2_is_fused(const VlpetK2Desc* desc);
 /* dkv receives ONLY the adapter-path gradient (autograd adds the frozen k/v_proj paths); dy == dout. */
 VLPET_API int vlpet_k2_bwd(const VlpetK2Desc* desc, const void* kv, const void* dout, const VlpetK2Params* w, void* dkv,
                  const VlpetK2Grads* g, void* workspace, size_t workspace_bytes, void* stream);

@@ -85,11 +85,11 @@ def gated_pet_fwd(x1, x2, p: Dict[str, np.ndarray], cfg: PetConfig, rnd=None):
       small:    gw [2d], gb []          (Linear(2d,1))
     Returns (out [M,d], cache).
 
-    ``rnd`` (optional, large gate only): a rounding function applied to the activations that feed the second GEMM
+    ``rnd`` (optional, large gate and ungated form only): a rounding function applied to the activations that feed the second GEMM
     of each branch (z, q) -- and in the backward to du, dt, da, dp -- i.e. the points where a reference run in
     bf16 stores an activation before the next nn.Linear consumes it.  rnd=None is exact arithmetic in the input dtype.
     """
-    R = rnd if (rnd is not None and cfg.gate == GATE_LARGE) else (lambda t: t)
+    R = rnd if (rnd is not None and cfg.gate in (GATE_LARGE, GATE_NONE)) else (lambda t: t)
     a = x2 @ p["Wd"].T + p["bd"]
     z = R(gelu_new(a))
     u = z @ p["Wu"].T + p["bu"]
@@ -132,7 +132,7 @@ def gated_pet_bwd(dout, p: Dict[str, np.ndarray], cfg: PetConfig, c, rnd=None):
     """Analytic backward of gated_pet_fwd (SURVEY Appendix A for the large gate; the middle/small gates
     route an extra gradient through y1 and x1 into the gate).  Returns (dx1, dx2, grads dict)."""
     x1, x2, a, z, y1 = c["x1"], c["x2"], c["a"], c["z"], c["y1"]
-    R = rnd if (rnd is not None and cfg.gate == GATE_LARGE) else (lambda t: t)
+    R = rnd if (rnd is not None and cfg.gate in (GATE_LARGE, GATE_NONE)) else (lambda t: t)
     dh = cfg.s * dout
     gr: Dict[str, np.ndarray] = {}
     dx1 = dout.copy()
@@ -191,7 +191,8 @@ def gated_pet_bwd(dout, p: Dict[str, np.ndarray], cfg: PetConfig, c, rnd=None):
         dy1 = dh
     else:
         raise ValueError(g)
-    du = R(cfg.alpha * dy1)
+    # ungated form (the K2 value parallel adapter): du = alpha * dout is never stored, dout itself feeds the GEMMs
+    du = R(cfg.alpha * dy1) if g != GATE_NONE else cfg.alpha * dy1
     gr["Wu"] = du.T @ z
     gr["bu"] = du.sum(0)
     dz = du @ p["Wu"]

@@ -342,6 +342,54 @@ def test_k2_matches_reference_golden(V, path, dtype, tol):
         assert rel(f(P[k].grad), ref_gr[k]) < tol, k
 
 
+@pytest.mark.parametrize("M,d,r,sf", [(1, 768, 96, 1.0), (200, 768, 96, 1.0), (1300, 768, 96, 0.7), (333, 768, 48, 1.0),
+                                      (640, 256, 32, 2.0), (148 * 128 + 500, 768, 96, 1.0)])
+def test_k2_fused_matches_oracle(V, M, d, r, sf):
+    """Decoder value parallel adapter through the fused tcgen05 kernels (ungated form of K1: x1 = y, x2 = kv, kappa = 0,
+    alpha = sf).  Same bars as the gated backward: bf16_check at 1e-3 for out / dkv against the fp64 oracle with bf16
+    storage of z and da, 1e-3 for the fp32 weight gradients, 6e-3 against exact intermediates."""
+    import ctypes as C
+    import vlpet_b200._lib as L
+    desc = L.K2Desc(M=M, d=d, r=r, dtype=L.BF16, impl=L.IMPL_AUTO, sf=sf)
+    assert L.lib.vlpet_k2_is_fused(C.byref(desc)) == 1
+    rng = np.random.default_rng(M + d + r + 7)
+    kv, y, dout = rng.standard_normal((M, d)), 0.5 * rng.standard_normal((M, d)), rng.standard_normal((M, d))
+    p = {"Wd": rng.standard_normal((r, d)) * 0.05, "bd": rng.standard_normal(r) * 0.02,
+         "Wu": rng.standard_normal((d, r)) * 0.05, "bu": rng.standard_normal(d) * 0.02}
+    bf = torch.bfloat16
+    tkv, ty = dev(kv, bf).requires_grad_(), dev(y, bf).requires_grad_()
+    P = {k: dev(v, bf).float().requires_grad_() for k, v in p.items()}
+    out = V.vpa(tkv, ty, P["Wd"], P["bd"], P["Wu"], P["bu"], sf)
+    out.backward(dev(dout, bf))
+    torch.cuda.synchronize()
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    kvr, yr, dor = bf16_round(kv), bf16_round(y), bf16_round(dout)
+    pr = {k: bf16_round(v).reshape(np.shape(v)) for k, v in p.items()}
+    cfg = O.PetConfig(gate="none", s=1.0, alpha=sf, kappa=0.0)
+    ref_out, _ = O.gated_pet_fwd(yr, kvr, pr, cfg)
+    vout, _ = O.vpa_fwd(kvr, yr, pr, sf)
+    assert rel(ref_out, vout) < 1e-14                      # the ungated K1 form IS the VPA (adapter_controller.py:149-162)
+    # forward: z = gelu_new(kv Wd^T + bd) reaches |z| ~ 6 here and is STORED in bf16 before the up projection (as in any
+    # bf16 run of the reference); without a gate nothing attenuates that rounding, so the 1e-3 bar is held against the
+    # oracle with bf16 storage of z, and 3e-3 (Frobenius, 1.6e-3 of which is the output's own bf16 storage) against exact z
+    r_out, cr = O.gated_pet_fwd(yr, kvr, pr, cfg, rnd=bf16_round)
+    bf16_check(f(out), r_out, TOL_BF16, outlier=20.0)
+    assert rel(f(out), ref_out) < 3e-3
+    _, r_dkv, g_r = O.gated_pet_bwd(dor, pr, cfg, cr, rnd=bf16_round)
+    _, cx = O.gated_pet_fwd(yr, kvr, pr, cfg)
+    _, x_dkv, g_x = O.gated_pet_bwd(dor, pr, cfg, cx)
+    assert torch.equal(ty.grad, dev(dout, bf))             # dy == dout
+    dkv = f(tkv.grad)
+    if M >= 64:
+        assert rel(dkv, r_dkv) < 3e-3 and rel(dkv, x_dkv) < 6e-3
+        bf16_check(dkv, r_dkv, TOL_BF16, outlier=20.0)
+    for k in ("Wd", "bd", "Wu", "bu"):
+        e_r, e_x = rel(f(P[k].grad), g_r[k]), rel(f(P[k].grad), g_x[k])
+        print(f"{k}: vs bf16-storage oracle {e_r:.2e}, vs exact oracle {e_x:.2e}")
+        if M >= 64:
+            assert e_r < TOL_BF16 and e_x < 6e-3, (k, e_r, e_x)
+
+
 def test_k2_adapter_controller_api(V):
     """Same constructor / forward / aliasing contract as the reference AdapterController (adapter_controller.py)."""
     g = load(golden_files("k2_vpa_d64")[0])

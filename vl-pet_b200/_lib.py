@@ -81,6 +81,7 @@ SYMBOLS = {
     "vlpet_k2_fwd": (C.c_int, [C.POINTER(K2Desc), _vp, _vp, C.POINTER(K2Params), _vp, _vp, C.c_size_t, _vp]),
     "vlpet_k2_bwd": (C.c_int, [C.POINTER(K2Desc), _vp, _vp, C.POINTER(K2Params), _vp, C.POINTER(K2Grads), _vp,
                                C.c_size_t, _vp]),
+    "vlpet_k2_is_fused": (C.c_int, [C.POINTER(K2Desc)]),
     "vlpet_k3_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(K3Desc)]),
     "vlpet_k3_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(K3Desc)]),
     "vlpet_k3_save_floats": (C.c_size_t, [C.POINTER(K3Desc)]),

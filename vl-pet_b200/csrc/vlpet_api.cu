@@ -128,21 +128,32 @@ static int check_k2(const VlpetK2Desc* D, const VlpetK2Params* w) {
   if (D->M <= 0 || D->d <= 0 || D->r <= 0) return fail(VLPET_E_BADARG, "k2: M, d, r must be positive");
   if (D->dtype != VLPET_F32 && D->dtype != VLPET_BF16) return fail(VLPET_E_BADARG, "k2: bad dtype %d", D->dtype);
   if (!w->Wd || !w->bd || !w->Wu || !w->bu) return fail(VLPET_E_BADARG, "k2: weights missing");
-  if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k2: no fused kernel yet");
   return 0;
 }
+static bool use_fused_k2(const VlpetK2Desc& D) { return D.impl != VLPET_IMPL_GENERIC && fused_k2_supported(D); }
 size_t vlpet_k2_fwd_workspace_bytes(const VlpetK2Desc* D) { return D ? generic_k2_fwd_ws(*D) : 0; }
-size_t vlpet_k2_bwd_workspace_bytes(const VlpetK2Desc* D) { return D ? generic_k2_bwd_ws(*D) : 0; }
+size_t vlpet_k2_bwd_workspace_bytes(const VlpetK2Desc* D) {
+  if (!D) return 0;
+  const size_t a = generic_k2_bwd_ws(*D), b = use_fused_k2(*D) ? fused_k2_bwd_ws(*D) : 0;
+  return a > b ? a : b;   // dkv == NULL falls back to the generic path even when the shape qualifies
+}
+int vlpet_k2_is_fused(const VlpetK2Desc* D) { return D && use_fused_k2(*D) ? 1 : 0; }
 int vlpet_k2_fwd(const VlpetK2Desc* D, const void* kv, const void* y, const VlpetK2Params* w, void* out, void* ws,
                  size_t ws_bytes, void* stream) {
   VLPET_TRY(check_k2(D, w));
   if (!kv || !out) return fail(VLPET_E_BADARG, "k2_fwd: null activation pointer"); /* y may be NULL: no residual */
+  if (y && use_fused_k2(*D) && aligned16(kv) && aligned16(y) && aligned16(out))
+    return fused_k2_fwd(*D, kv, y, *w, out, static_cast<cudaStream_t>(stream));
+  if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k2_fwd: fused kernel needs bf16, y != NULL, d %% 128 == 0, r %% 8 == 0, r <= 96");
   return generic_k2_fwd(*D, kv, y, *w, out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int vlpet_k2_bwd(const VlpetK2Desc* D, const void* kv, const void* dout, const VlpetK2Params* w, void* dkv,
                  const VlpetK2Grads* g, void* ws, size_t ws_bytes, void* stream) {
   VLPET_TRY(check_k2(D, w));
   if (!kv || !dout || !g) return fail(VLPET_E_BADARG, "k2_bwd: null pointer");
+  if (dkv && use_fused_k2(*D) && aligned16(kv) && aligned16(dout) && aligned16(dkv))
+    return fused_k2_bwd(*D, kv, dout, *w, dkv, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k2_bwd: fused kernel needs bf16, dkv != NULL, d %% 128 == 0, r %% 8 == 0, r <= 96");
   return generic_k2_bwd(*D, kv, dout, *w, dkv, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 

@@ -146,6 +146,13 @@ size_t fused_k1_bwd_ws(const VlpetK1Desc&);
 int fused_k1_bwd(const VlpetK1Desc&, const void* x1, const void* x2, const void* dout, const VlpetK1Params&, void* dx1,
                  void* dx2, const VlpetK1Grads&, void* ws, size_t ws_bytes, cudaStream_t);
 
+// K2 through the same fused kernels (ungated form)
+bool fused_k2_supported(const VlpetK2Desc&);
+size_t fused_k2_bwd_ws(const VlpetK2Desc&);
+int fused_k2_fwd(const VlpetK2Desc&, const void* kv, const void* y, const VlpetK2Params&, void* out, cudaStream_t);
+int fused_k2_bwd(const VlpetK2Desc&, const void* kv, const void* dout, const VlpetK2Params&, void* dkv, const VlpetK2Grads&,
+                 void* ws, size_t ws_bytes, cudaStream_t);
+
 // ---- token-contracted weight-gradient GEMM (tcgen05), vlpet_wgrad_sm100.cu -----------------------------------
 bool wgrad_sm100_supported(int d, int nout);
 int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void* const* B, const int64_t* ldb,

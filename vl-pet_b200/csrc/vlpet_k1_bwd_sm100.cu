@@ -111,7 +111,9 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int R>
+// GATED = false is the ungated form used for the decoder value parallel adapter (K2): out = x1 + alpha*(Up(gelu_new(Down x2)))
+// -> dx2 = (alpha * (dout Wu) * gelu_new'(A)) Wd, no gate branch, no U/T recompute, no du/dt scratch (du = alpha*dout).
+template <int R, bool GATED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                     const __grid_constant__ CUtensorMap tm_dout, const __grid_constant__ CUtensorMap tm_dx1,
@@ -182,39 +184,46 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             ptx::mbar_wait(bar(B_XEMPTY + sx), ((xi / SX) & 1) ^ 1);
             const uint32_t xdst = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
             if (ph == 0) {
-              ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), 2 * XCH_BYTES);
-              ptx::tma_load_2d(xdst, &tm_x1, c * CH, row0, bar(B_XFULL + sx));
+              ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), (GATED ? 2 : 1) * XCH_BYTES);
+              if (GATED) ptx::tma_load_2d(xdst, &tm_x1, c * CH, row0, bar(B_XFULL + sx));
               ptx::tma_load_2d(xdst + XCH_BYTES, &tm_x2, c * CH, row0, bar(B_XFULL + sx));
             } else if (ph == 1) {
-              ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), 2 * XCH_BYTES);
-              ptx::tma_load_2d(xdst, &tm_x2, c * CH, row0, bar(B_XFULL + sx));
-              ptx::tma_load_2d(xdst + XCH_BYTES, &tm_dout, c * CH, row0, bar(B_XFULL + sx));
-            } else {
+              ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), (GATED ? 2 : 1) * XCH_BYTES);
+              if (GATED) {
+                ptx::tma_load_2d(xdst, &tm_x2, c * CH, row0, bar(B_XFULL + sx));
+                ptx::tma_load_2d(xdst + XCH_BYTES, &tm_dout, c * CH, row0, bar(B_XFULL + sx));
+              } else {
+                ptx::tma_load_2d(xdst, &tm_dout, c * CH, row0, bar(B_XFULL + sx));   // du = alpha*dout: consumed as is
+              }
+            } else if (GATED) {
               ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), XCH_BYTES);
               ptx::tma_load_2d(xdst, &tm_dout, c * CH, row0, bar(B_XFULL + sx));
+            } else {
+              ptx::mbar_arrive(bar(B_XFULL + sx));   // the stage is only the staging buffer of dx2_c
             }
             ptx::mbar_wait(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1);
             const uint32_t wdst = smem_base + C::OFF_W + sw * C::WSLOT;
             if (ph == 0) {
-              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), 2 * C::WA_BYTES);
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (GATED ? 2 : 1) * C::WA_BYTES);
               ptx::tma_load_2d(wdst, &tm_wd, c * CH, 0, bar(B_WFULL + sw));
-              ptx::tma_load_2d(wdst + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
+              if (GATED) ptx::tma_load_2d(wdst + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
             } else if (ph == 1) {
-              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), 2 * C::WB_BYTES);
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (GATED ? 2 : 1) * C::WB_BYTES);
 #pragma unroll
               for (int kb = 0; kb < C::KB; ++kb) {
                 ptx::tma_load_2d(wdst + kb * (CH * CH * 2), &tm_wu, kb * CH, c * CH, bar(B_WFULL + sw));
-                ptx::tma_load_2d(wdst + C::WB_BYTES + kb * (CH * CH * 2), &tm_gu, kb * CH, c * CH, bar(B_WFULL + sw));
+                if (GATED)
+                  ptx::tma_load_2d(wdst + C::WB_BYTES + kb * (CH * CH * 2), &tm_gu, kb * CH, c * CH, bar(B_WFULL + sw));
               }
             } else {
-              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (mulgate ? C::WB_BYTES : 0) + 2 * C::WA_BYTES);
-              if (mulgate) {
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), ((GATED && mulgate) ? C::WB_BYTES : 0) + (GATED ? 2 : 1) * C::WA_BYTES);
+              if (GATED && mulgate) {
 #pragma unroll
                 for (int kb = 0; kb < C::KB; ++kb)
                   ptx::tma_load_2d(wdst + kb * (CH * CH * 2), &tm_gu, kb * CH, c * CH, bar(B_WFULL + sw));
               }
               ptx::tma_load_2d(wdst + C::WB_BYTES, &tm_wd, c * CH, 0, bar(B_WFULL + sw));
-              ptx::tma_load_2d(wdst + C::WB_BYTES + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
+              if (GATED) ptx::tma_load_2d(wdst + C::WB_BYTES + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
             }
           }
         }
@@ -250,14 +259,33 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
             ptx::umma_bf16_ss(tmem_base + TM_A, ptx::umma_desc_kmajor_sw128(x2s + ks * 32),
                               ptx::umma_desc_kmajor_sw128(wds + ks * 32), IDESC_AP, acc);
-            ptx::umma_bf16_ss(tmem_base + TM_P, ptx::umma_desc_kmajor_sw128(x1s + ks * 32),
-                              ptx::umma_desc_kmajor_sw128(gds + ks * 32), IDESC_AP, acc);
+            if (GATED)
+              ptx::umma_bf16_ss(tmem_base + TM_P, ptx::umma_desc_kmajor_sw128(x1s + ks * 32),
+                                ptx::umma_desc_kmajor_sw128(gds + ks * 32), IDESC_AP, acc);
           }
           ptx::umma_commit(bar(B_XEMPTY + sx));
           ptx::umma_commit(bar(B_WEMPTY + sw));
         }
         ptx::umma_commit(bar(B_APFULL));
         // ---- phase 2
+        if (!GATED) {
+          for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
+            const uint32_t sx = xi % SX, sw = wi % SW;
+            ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+            ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
+            ptx::tc_fence_after();
+            const uint32_t dos = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
+            const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT;
+#pragma unroll
+            for (int ks = 0; ks < CH / 16; ++ks)
+              ptx::umma_bf16_ss(tmem_base + TM_DZ, ptx::umma_desc_kmajor_sw128(dos + ks * 32),
+                                ptx::umma_desc_mnmajor_sw128(wus + ks * 2048, CH * CH * 2), IDESC_DZ, (c > 0 || ks > 0) ? 1u : 0u);
+            ptx::umma_commit(bar(B_XEMPTY + sx));
+            ptx::umma_commit(bar(B_WEMPTY + sw));
+          }
+          ptx::umma_commit(bar(B_DZFULL));
+        }
+        if (GATED) {
         ptx::mbar_wait(bar(B_ZQFULL), ti & 1);
         ptx::tc_fence_after();
         const uint32_t xi2 = xi, wi2 = wi, p2i0 = p2i;
@@ -297,6 +325,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         }
         issue_dzdq(nkc - 1);
         ptx::umma_commit(bar(B_DZFULL));
+        }
         // ---- phase 3
         ptx::mbar_wait(bar(B_DAPFULL), ti & 1);
         ptx::tc_fence_after();
@@ -310,13 +339,14 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
 #pragma unroll
           for (int ks = 0; ks < R / 16; ++ks) {
             const uint32_t kb = ks / 4, kin = ks % 4;
-            if (mulgate)
+            if (GATED && mulgate)
               ptx::umma_bf16_ss(tacc, ptx::umma_desc_kmajor_sw128(small_a(1, ks)),
                                 ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_UT, ks > 0);
             ptx::umma_bf16_ss(tacc + CH, ptx::umma_desc_kmajor_sw128(small_a(0, ks)),
                               ptx::umma_desc_mnmajor_sw128(wds + ks * 2048, C::WA_BYTES), IDESC_DX, ks > 0);
-            ptx::umma_bf16_ss(tacc + 2 * CH, ptx::umma_desc_kmajor_sw128(small_a(2, ks)),
-                              ptx::umma_desc_mnmajor_sw128(gds + ks * 2048, C::WA_BYTES), IDESC_DX, ks > 0);
+            if (GATED)
+              ptx::umma_bf16_ss(tacc + 2 * CH, ptx::umma_desc_kmajor_sw128(small_a(2, ks)),
+                                ptx::umma_desc_mnmajor_sw128(gds + ks * 2048, C::WA_BYTES), IDESC_DX, ks > 0);
           }
           ptx::umma_commit(bar(B_WEMPTY + sw));
           ptx::umma_commit(bar(B_ACCFULL + b));
@@ -330,7 +360,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = (int)(tile * TILE_M);
         xi += nkc;  // phase-1 stages are released by the MMA warp
-        for (int c = 0; c < nkc; ++c, ++xi, ++p2i) {
+        if (!GATED) xi += nkc;  // ungated: phase-2 stages are released by the MMA warp as well
+        for (int c = 0; GATED && c < nkc; ++c, ++xi, ++p2i) {
           const uint32_t sx = xi % SX, k = p2i % SX;
           ptx::mbar_wait(bar(B_DUDT + k), (p2i / SX) & 1);
           const uint32_t src = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
@@ -345,7 +376,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           const uint32_t sx = xi % SX, k = p3i % SX;
           ptx::mbar_wait(bar(B_OUTRDY + k), (p3i / SX) & 1);
           const uint32_t src = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
-          ptx::tma_store_2d(&tm_dx1, src, c * CH, row0);
+          if (GATED) ptx::tma_store_2d(&tm_dx1, src, c * CH, row0);
           ptx::tma_store_2d(&tm_dx2, src + XCH_BYTES, c * CH, row0);
           ptx::tma_store_commit();
           ptx::tma_store_wait_read0();
@@ -381,7 +412,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       // ---- epilogue 1 (APFULL also implies that every MMA of the previous tile, which read z/q/da/dp, has completed)
       ptx::mbar_wait(bar(B_APFULL), ti & 1);
       ptx::tc_fence_after();
-      {
+      if (GATED || half == 0) {
         const uint32_t tsrc = lane_addr + (half ? TM_P : TM_A);
         const __nv_bfloat16* bias = half ? p.gbd : p.bd;
         const int rr = half ? p.rg : p.r;
@@ -419,7 +450,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       ptx::mbar_arrive(bar(B_ZQFULL));
       xi += nkc;
       // ---- epilogue 2, per 64-column chunk: du, dt
-      for (int c = 0; c < nkc; ++c, ++xi, ++ui, ++p2i) {
+      if (!GATED) xi += nkc;
+      for (int c = 0; GATED && c < nkc; ++c, ++xi, ++ui, ++p2i) {
         const uint32_t sx = xi % SX;
         ptx::mbar_wait(bar(B_UTFULL), ui & 1);
         ptx::tc_fence_after();
@@ -489,7 +521,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       // ---- epilogue 3: da = dz * gelu_new'(A + bd) (half 0), dp = dq * gelu_new'(P + gbd) (half 1)
       ptx::mbar_wait(bar(B_DZFULL), ti & 1);
       ptx::tc_fence_after();
-      {
+      if (GATED || half == 0) {
+        const float dzscale = GATED ? 1.0f : p.alpha;   // ungated: du = alpha*dout was fed unscaled
         const uint32_t tpre = lane_addr + (half ? TM_P : TM_A);
         const uint32_t tdz = lane_addr + (half ? TM_DQ : TM_DZ);
         const __nv_bfloat16* bias = half ? p.gbd : p.bd;
@@ -507,7 +540,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             const float b = (j0 + j < rr) ? __bfloat162float(bias[j0 + j]) : 0.f;
             float gz, dg;
             gelu_new_both(__uint_as_float(a[j]) + b, gz, dg);
-            da[j] = __uint_as_float(dz[j]) * dg;
+            da[j] = dzscale * __uint_as_float(dz[j]) * dg;
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -531,9 +564,9 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         ptx::tc_fence_after();
         const uint32_t tacc = lane_addr + TM_ACC + b * ACC_STRIDE + half * 32;
         uint32_t t[32], g2[32], g1[32];
-        if (mulgate) ptx::tmem_ld_32x32b_x32(tacc, t);
+        if (GATED && mulgate) ptx::tmem_ld_32x32b_x32(tacc, t);
         ptx::tmem_ld_32x32b_x32(tacc + CH, g2);
-        ptx::tmem_ld_32x32b_x32(tacc + 2 * CH, g1);
+        if (GATED) ptx::tmem_ld_32x32b_x32(tacc + 2 * CH, g1);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_ACCEMPTY + b));
@@ -550,10 +583,10 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             hsh[1] = drop_hash4(p.seed, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
           }
           const uint32_t off = (((uint32_t)(half * 4 + g)) ^ swz) << 4;
-          uint32_t dv[4], o1[4], o2[4];
-          lds128(dorow + off, dv);
+          uint32_t dv[4] = {0, 0, 0, 0}, o1[4], o2[4];
+          if (GATED) lds128(dorow + off, dv);
           uint32_t gbw[4] = {0, 0, 0, 0};
-          if (mulgate) {
+          if (GATED && mulgate) {
             const uint4 gb4 = __ldg(reinterpret_cast<const uint4*>(p.gbu + col0 + g * 8));
             gbw[0] = gb4.x; gbw[1] = gb4.y; gbw[2] = gb4.z; gbw[3] = gb4.w;
           }
@@ -571,18 +604,18 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
                 sc = (bits >= p.thr16) ? p.s * p.inv_keep : 0.f;
               }
               float dy1 = sc * dof;
-              if (mulgate) {
+              if (GATED && mulgate) {
                 const float gbf = h2 ? bf_hi(gbw[e]) : bf_lo(gbw[e]);
                 const float th = ptx::tanh_approx(0.5f * (__uint_as_float(t[j]) + gbf));
                 dy1 *= fmaf(0.5f, th, 0.5f);
               }
-              r2[h2] = fmaf(p.kappa, dy1, __uint_as_float(g2[j]));
-              r1[h2] = dof + __uint_as_float(g1[j]);
+              r2[h2] = GATED ? fmaf(p.kappa, dy1, __uint_as_float(g2[j])) : __uint_as_float(g2[j]);
+              r1[h2] = GATED ? dof + __uint_as_float(g1[j]) : 0.f;
             }
             o1[e] = pack_bf16(r1[0], r1[1]);
             o2[e] = pack_bf16(r2[0], r2[1]);
           }
-          sts128(dorow + off, o1);
+          if (GATED) sts128(dorow + off, o1);
           sts128(o2row + off, o2);
         }
         ptx::fence_proxy_async_smem();
@@ -607,102 +640,100 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   }
 }
 
-int pick_R(const VlpetK1Desc& D) {
-  const int m = D.r > D.rg ? D.r : D.rg;
-  if (m <= 32) return 32;
-  if (m <= 64) return 64;
-  if (m <= 96) return 96;
-  return 0;
-}
-
 struct Scratch {
   __nv_bfloat16 *zs, *qs, *das, *dps, *dus, *dts;
   int pz, pq;
   size_t bytes;
 };
-Scratch carve(const VlpetK1Desc& D, void* ws) {
+Scratch carve(int64_t M, int d, int r, int rg, bool gated, void* ws) {
   Scratch s;
-  s.pz = (D.r + 1 + 7) / 8 * 8;
-  s.pq = (D.rg + 1 + 7) / 8 * 8;
+  s.pz = (r + 1 + 7) / 8 * 8;
+  s.pq = (rg + 1 + 7) / 8 * 8;
   Arena a(ws, (size_t)-1);
-  s.zs = a.take<__nv_bfloat16>((size_t)D.M * s.pz);
-  s.qs = a.take<__nv_bfloat16>((size_t)D.M * s.pq);
-  s.das = a.take<__nv_bfloat16>((size_t)D.M * s.pz);
-  s.dps = a.take<__nv_bfloat16>((size_t)D.M * s.pq);
-  s.dus = a.take<__nv_bfloat16>((size_t)D.M * D.d);
-  s.dts = a.take<__nv_bfloat16>((size_t)D.M * D.d);
+  s.zs = a.take<__nv_bfloat16>((size_t)M * s.pz);
+  s.das = a.take<__nv_bfloat16>((size_t)M * s.pz);
+  s.qs = s.dps = s.dus = s.dts = nullptr;
+  if (gated) {
+    s.qs = a.take<__nv_bfloat16>((size_t)M * s.pq);
+    s.dps = a.take<__nv_bfloat16>((size_t)M * s.pq);
+    s.dus = a.take<__nv_bfloat16>((size_t)M * d);
+    s.dts = a.take<__nv_bfloat16>((size_t)M * d);
+  }
   s.bytes = a.off;
   return s;
 }
 
-template <int R>
+template <int R, bool GATED>
 int launch(const VlpetK1Desc& D, const CUtensorMap* m, const BParams& p, int sms, cudaStream_t st) {
   using C = BCfg<R>;
   static bool attr_set = false;
   if (!attr_set) {
-    VLPET_CUDA_OK(cudaFuncSetAttribute(k1_bwd_sm100_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    VLPET_CUDA_OK(cudaFuncSetAttribute(k1_bwd_sm100_kernel<R, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  k1_bwd_sm100_kernel<R><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9],
+  k1_bwd_sm100_kernel<R, GATED><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9],
                                                                   m[10], p);
   VLPET_LAUNCH_OK();
   return 0;
 }
 
-}  // namespace
-
-bool fused_k1_bwd_supported(const VlpetK1Desc& D) {
-  if (D.dtype != VLPET_BF16 || D.gate != VLPET_GATE_LARGE) return false;
-  if (D.d % 128 != 0 || D.d < 128) return false;
-  if (D.r % 8 != 0 || D.rg % 8 != 0 || D.r < 8 || D.rg < 8 || pick_R(D) == 0) return false;
-  if (D.M <= 0 || D.M > (int64_t)0x7fffff00) return false;
-  return device_sm_count() > 0 && wgrad_sm100_supported(D.d, D.r) && wgrad_sm100_supported(D.d, D.rg);
+int pick_R2(int r, int rg) {
+  const int m = r > rg ? r : rg;
+  return m <= 32 ? 32 : (m <= 64 ? 64 : (m <= 96 ? 96 : 0));
 }
 
-size_t fused_k1_bwd_ws(const VlpetK1Desc& D) { return carve(D, nullptr).bytes; }
-
-int fused_k1_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const void* dout, const VlpetK1Params& w, void* dx1,
-                 void* dx2, const VlpetK1Grads& G, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (!aligned16(w.Wd) || !aligned16(w.Wu) || !aligned16(w.Gd) || !aligned16(w.Gu) || !aligned16(w.bu) || !aligned16(w.gbu))
-    return fail(VLPET_E_ALIGN, "k1_bwd(fused): weights must be 16-byte aligned");
-  Scratch s = carve(D, ws);
-  if (!ws || ws_bytes < s.bytes) return fail(VLPET_E_WORKSPACE, "k1_bwd(fused): workspace %zu < %zu bytes", ws_bytes, s.bytes);
-  const int R = pick_R(D);
+// shared driver of the gated (K1, large gate) and ungated (K2) backward
+int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, const void* dout, const VlpetK1Params& w,
+            void* dx1, void* dx2, const VlpetK1Grads& G, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int rg = gated ? D.rg : D.r;
+  Scratch s = carve(D.M, D.d, D.r, rg, gated, ws);
+  if (!ws || ws_bytes < s.bytes) return fail(VLPET_E_WORKSPACE, "bwd(fused): workspace %zu < %zu bytes", ws_bytes, s.bytes);
+  const int R = pick_R2(D.r, rg);
   const int sms = device_sm_count();
   CUtensorMap m[11];
   const uint64_t M = (uint64_t)D.M, d = (uint64_t)D.d;
-  VLPET_TRY(make_map_bf16(&m[0], x1, M, d, d, TILE_M, CH, false));
+  VLPET_TRY(make_map_bf16(&m[0], gated ? x1 : x2, M, d, d, TILE_M, CH, false));
   VLPET_TRY(make_map_bf16(&m[1], x2, M, d, d, TILE_M, CH, false));
   VLPET_TRY(make_map_bf16(&m[2], dout, M, d, d, TILE_M, CH, false));
-  VLPET_TRY(make_map_bf16(&m[3], dx1, M, d, d, TILE_M, CH, false));
+  VLPET_TRY(make_map_bf16(&m[3], gated ? dx1 : dx2, M, d, d, TILE_M, CH, false));
   VLPET_TRY(make_map_bf16(&m[4], dx2, M, d, d, TILE_M, CH, false));
-  VLPET_TRY(make_map_bf16(&m[5], s.dus, M, d, d, TILE_M, CH, false));
-  VLPET_TRY(make_map_bf16(&m[6], s.dts, M, d, d, TILE_M, CH, false));
+  VLPET_TRY(make_map_bf16(&m[5], gated ? (void*)s.dus : dx2, M, d, d, TILE_M, CH, false));
+  VLPET_TRY(make_map_bf16(&m[6], gated ? (void*)s.dts : dx2, M, d, d, TILE_M, CH, false));
   VLPET_TRY(make_map_bf16(&m[7], w.Wd, (uint64_t)D.r, d, d, (uint32_t)R, CH, true));
-  VLPET_TRY(make_map_bf16(&m[8], w.Gd, (uint64_t)D.rg, d, d, (uint32_t)R, CH, true));
+  VLPET_TRY(make_map_bf16(&m[8], gated ? w.Gd : w.Wd, (uint64_t)rg, d, d, (uint32_t)R, CH, true));
   VLPET_TRY(make_map_bf16(&m[9], w.Wu, d, (uint64_t)D.r, (uint64_t)D.r, CH, CH, true));
-  VLPET_TRY(make_map_bf16(&m[10], w.Gu, d, (uint64_t)D.rg, (uint64_t)D.rg, CH, CH, true));
+  VLPET_TRY(make_map_bf16(&m[10], gated ? w.Gu : w.Wu, d, (uint64_t)rg, (uint64_t)rg, CH, CH, true));
   BParams p;
-  p.M = D.M; p.d = D.d; p.r = D.r; p.rg = D.rg; p.add_gate = D.add_gate;
+  p.M = D.M; p.d = D.d; p.r = D.r; p.rg = rg; p.add_gate = D.add_gate;
   p.s = D.s; p.alpha = D.alpha; p.kappa = D.kappa;
   p.bd = static_cast<const __nv_bfloat16*>(w.bd); p.bu = static_cast<const __nv_bfloat16*>(w.bu);
-  p.gbd = static_cast<const __nv_bfloat16*>(w.gbd); p.gbu = static_cast<const __nv_bfloat16*>(w.gbu);
+  p.gbd = static_cast<const __nv_bfloat16*>(gated ? w.gbd : w.bd); p.gbu = static_cast<const __nv_bfloat16*>(gated ? w.gbu : w.bu);
   p.zs = s.zs; p.qs = s.qs; p.das = s.das; p.dps = s.dps; p.pz = s.pz; p.pq = s.pq;
-  p.dbd = G.dbd; p.dgbd = G.dgbd;
+  p.dbd = G.dbd; p.dgbd = gated ? G.dgbd : nullptr;
   p.seed = D.seed;
   p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
   p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
   int rc = 0;
-  switch (R) {
-    case 32: rc = launch<32>(D, m, p, sms, st); break;
-    case 64: rc = launch<64>(D, m, p, sms, st); break;
-    case 96: rc = launch<96>(D, m, p, sms, st); break;
-    default: return fail(VLPET_E_UNSUPPORTED, "k1_bwd(fused): unsupported rank");
+  if (gated) {
+    switch (R) {
+      case 32: rc = launch<32, true>(D, m, p, sms, st); break;
+      case 64: rc = launch<64, true>(D, m, p, sms, st); break;
+      case 96: rc = launch<96, true>(D, m, p, sms, st); break;
+      default: return fail(VLPET_E_UNSUPPORTED, "bwd(fused): unsupported rank");
+    }
+  } else {
+    switch (R) {
+      case 32: rc = launch<32, false>(D, m, p, sms, st); break;
+      case 64: rc = launch<64, false>(D, m, p, sms, st); break;
+      case 96: rc = launch<96, false>(D, m, p, sms, st); break;
+      default: return fail(VLPET_E_UNSUPPORTED, "bwd(fused): unsupported rank");
+    }
   }
   if (rc) return rc;
   // ---- weight gradients: dWu = du^T z (+dbu), dGu = dt^T q (+dgbu), dWd = (x2^T da)^T, dGd = (x1^T dp)^T
+  //      (ungated: du = alpha*dout, so A = dout with scale alpha)
   const void* A[4]; const void* B[4]; int64_t lda[4], ldb[4]; int nbv[4], tr[4]; float* out[4]; float* bias[4]; float sc[4];
   auto run = [&](const int* which, int n, int nout) -> int {
     int k = 0;
@@ -711,19 +742,23 @@ int fused_k1_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const voi
       float* o = q == 0 ? G.dWu : (q == 1 ? G.dGu : (q == 2 ? G.dWd : G.dGd));
       float* b = q == 0 ? G.dbu : (q == 1 ? G.dgbu : nullptr);
       if (!o && !b) continue;
-      if (!o) return fail(VLPET_E_BADARG, "k1_bwd(fused): a bias gradient needs its weight gradient buffer");
-      A[k] = q == 0 ? (const void*)s.dus : (q == 1 ? (const void*)s.dts : (q == 2 ? x2 : x1));
+      if (!o) return fail(VLPET_E_BADARG, "bwd(fused): a bias gradient needs its weight gradient buffer");
+      A[k] = q == 0 ? (gated ? (const void*)s.dus : dout) : (q == 1 ? (const void*)s.dts : (q == 2 ? x2 : x1));
       lda[k] = D.d;
       B[k] = q == 0 ? s.zs : (q == 1 ? s.qs : (q == 2 ? s.das : s.dps));
       ldb[k] = (q == 0 || q == 2) ? s.pz : s.pq;
       nbv[k] = (q < 2) ? nout + 1 : nout;
       tr[k] = q >= 2;
-      out[k] = o; bias[k] = b; sc[k] = 1.0f;
+      out[k] = o; bias[k] = b; sc[k] = (q == 0 && !gated) ? D.alpha : 1.0f;
       ++k;
     }
     if (k == 0) return 0;
     return wgrad_sm100(k, A, lda, B, ldb, nbv, out, bias, sc, tr, D.M, D.d, nout, sms, st);
   };
+  if (!gated) {
+    const int ad[2] = {0, 2};
+    return run(ad, 2, D.r);
+  }
   if (D.r == D.rg) {
     const int all[4] = {0, 1, 2, 3};
     return run(all, 4, D.r);
@@ -731,6 +766,63 @@ int fused_k1_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const voi
   const int ad[2] = {0, 2}, ga[2] = {1, 3};
   VLPET_TRY(run(ad, 2, D.r));
   return run(ga, 2, D.rg);
+}
+
+}  // namespace
+
+bool fused_k1_bwd_supported(const VlpetK1Desc& D) {
+  if (D.dtype != VLPET_BF16 || D.gate != VLPET_GATE_LARGE) return false;
+  if (D.d % 128 != 0 || D.d < 128) return false;
+  if (D.r % 8 != 0 || D.rg % 8 != 0 || D.r < 8 || D.rg < 8 || pick_R2(D.r, D.rg) == 0) return false;
+  if (D.M <= 0 || D.M > (int64_t)0x7fffff00) return false;
+  return device_sm_count() > 0 && wgrad_sm100_supported(D.d, D.r) && wgrad_sm100_supported(D.d, D.rg);
+}
+
+size_t fused_k1_bwd_ws(const VlpetK1Desc& D) { return carve(D.M, D.d, D.r, D.rg, true, nullptr).bytes; }
+
+int fused_k1_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const void* dout, const VlpetK1Params& w, void* dx1,
+                 void* dx2, const VlpetK1Grads& G, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!aligned16(w.Wd) || !aligned16(w.Wu) || !aligned16(w.Gd) || !aligned16(w.Gu) || !aligned16(w.bu) || !aligned16(w.gbu))
+    return fail(VLPET_E_ALIGN, "k1_bwd(fused): weights must be 16-byte aligned");
+  return run_bwd(true, D, x1, x2, dout, w, dx1, dx2, G, ws, ws_bytes, st);
+}
+
+// ---- K2 (decoder value parallel adapter) through the same kernels, ungated ---------------------------------------
+static VlpetK1Desc k2_as_k1(const VlpetK2Desc& D) {
+  VlpetK1Desc K;
+  memset(&K, 0, sizeof(K));
+  K.M = D.M; K.d = D.d; K.r = D.r; K.rg = 0; K.gate = VLPET_GATE_NONE; K.dtype = D.dtype; K.impl = D.impl;
+  K.s = 1.0f; K.alpha = D.sf; K.kappa = 0.0f;     // out = y + 1 * (0 * kv + sf * (Up(gelu_new(Down kv)) + bu))
+  return K;
+}
+
+bool fused_k2_supported(const VlpetK2Desc& D) {
+  if (D.dtype != VLPET_BF16) return false;
+  if (D.d % 128 != 0 || D.d < 128 || D.r % 8 != 0 || D.r < 8 || pick_R2(D.r, D.r) == 0) return false;
+  if (D.M <= 0 || D.M > (int64_t)0x7fffff00) return false;
+  return device_sm_count() > 0 && wgrad_sm100_supported(D.d, D.r) && fused_k1_fwd_supported(k2_as_k1(D));
+}
+
+size_t fused_k2_bwd_ws(const VlpetK2Desc& D) { return carve(D.M, D.d, D.r, D.r, false, nullptr).bytes; }
+
+int fused_k2_fwd(const VlpetK2Desc& D, const void* kv, const void* y, const VlpetK2Params& w, void* out, cudaStream_t st) {
+  VlpetK1Params P;
+  memset(&P, 0, sizeof(P));
+  P.Wd = w.Wd; P.bd = w.bd; P.Wu = w.Wu; P.bu = w.bu;
+  return fused_k1_fwd(k2_as_k1(D), y, kv, P, out, nullptr, 0, st);
+}
+
+int fused_k2_bwd(const VlpetK2Desc& D, const void* kv, const void* dout, const VlpetK2Params& w, void* dkv,
+                 const VlpetK2Grads& g, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!aligned16(w.Wd) || !aligned16(w.Wu) || !aligned16(w.bu))
+    return fail(VLPET_E_ALIGN, "k2_bwd(fused): weights must be 16-byte aligned");
+  VlpetK1Params P;
+  memset(&P, 0, sizeof(P));
+  P.Wd = w.Wd; P.bd = w.bd; P.Wu = w.Wu; P.bu = w.bu;
+  VlpetK1Grads G;
+  memset(&G, 0, sizeof(G));
+  G.dWd = g.dWd; G.dbd = g.dbd; G.dWu = g.dWu; G.dbu = g.dbu;
+  return run_bwd(false, k2_as_k1(D), nullptr, kv, dout, P, nullptr, dkv, G, ws, ws_bytes, st);
 }
 
 }  // namespace vlpet

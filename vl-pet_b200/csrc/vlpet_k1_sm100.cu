@@ -86,6 +86,7 @@ struct Params {
   int64_t M;
   int d, r, rg;
   int add_gate;
+  int gated;          // 0: no gate (h = y1; the K2 value-parallel-adapter form), 1: large gate
   float s, alpha, kappa;
   const __nv_bfloat16 *bd, *bu, *gbd, *gbu;
   uint64_t seed;      // dropout stream (vlpet_common.cuh: drop_hash4)
@@ -165,15 +166,16 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             ptx::mbar_wait(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1);
             const uint32_t wdst = smem_base + C::OFF_W + sw * C::WSLOT;
             if (ph == 0) {
-              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), 2 * C::WA_BYTES);
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (p.gated ? 2 : 1) * C::WA_BYTES);
               ptx::tma_load_2d(wdst, &tm_wd, c * CH, 0, bar(B_WFULL + sw));
-              ptx::tma_load_2d(wdst + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
+              if (p.gated) ptx::tma_load_2d(wdst + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
             } else {
-              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), 2 * C::WB_BYTES);
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (p.gated ? 2 : 1) * C::WB_BYTES);
 #pragma unroll
               for (int kb = 0; kb < C::KB; ++kb) {
                 ptx::tma_load_2d(wdst + kb * (CH * CH * 2), &tm_wu, kb * CH, c * CH, bar(B_WFULL + sw));
-                ptx::tma_load_2d(wdst + C::WB_BYTES + kb * (CH * CH * 2), &tm_gu, kb * CH, c * CH, bar(B_WFULL + sw));
+                if (p.gated)
+                  ptx::tma_load_2d(wdst + C::WB_BYTES + kb * (CH * CH * 2), &tm_gu, kb * CH, c * CH, bar(B_WFULL + sw));
               }
             }
           }
@@ -201,8 +203,9 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
             ptx::umma_bf16_ss(tmem_base + TM_A, ptx::umma_desc_kmajor_sw128(x2s + ks * 32),
                               ptx::umma_desc_kmajor_sw128(wds + ks * 32), IDESC_A, acc);
-            ptx::umma_bf16_ss(tmem_base + TM_P, ptx::umma_desc_kmajor_sw128(x1s + ks * 32),
-                              ptx::umma_desc_kmajor_sw128(gds + ks * 32), IDESC_A, acc);
+            if (p.gated)
+              ptx::umma_bf16_ss(tmem_base + TM_P, ptx::umma_desc_kmajor_sw128(x1s + ks * 32),
+                                ptx::umma_desc_kmajor_sw128(gds + ks * 32), IDESC_A, acc);
           }
           ptx::umma_commit(bar(B_XEMPTY + sx));
           ptx::umma_commit(bar(B_WEMPTY + sw));
@@ -223,8 +226,9 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             const uint32_t kb = ks / 4, kin = ks % 4;
             ptx::umma_bf16_ss(tU, ptx::umma_desc_kmajor_sw128(z_base + kb * XCH_BYTES + kin * 32),
                               ptx::umma_desc_kmajor_sw128(wus + kb * (CH * CH * 2) + kin * 32), IDESC_B, ks > 0);
-            ptx::umma_bf16_ss(tT, ptx::umma_desc_kmajor_sw128(q_base + kb * XCH_BYTES + kin * 32),
-                              ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_B, ks > 0);
+            if (p.gated)
+              ptx::umma_bf16_ss(tT, ptx::umma_desc_kmajor_sw128(q_base + kb * XCH_BYTES + kin * 32),
+                                ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_B, ks > 0);
           }
           ptx::umma_commit(bar(B_WEMPTY + sw));
           ptx::umma_commit(bar(B_UTFULL + ub));
@@ -261,7 +265,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       // ---- epilogue 1: z = gelu_new(A + bd) (half 0) / q = gelu_new(P + gbd) (half 1) -> swizzled K-major smem
       ptx::mbar_wait(bar(B_APFULL), ti & 1);
       ptx::tc_fence_after();
-      {
+      if (p.gated || half == 0) {
         const uint32_t tsrc = lane_addr + (half ? TM_P : TM_A);
         const uint32_t dst = smem_base + (half ? C::OFF_Q : C::OFF_Z) + (uint32_t)row * 128u;
         const __nv_bfloat16* bias = half ? p.gbd : p.bd;
@@ -301,7 +305,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         uint32_t u[32], t[32];
         const uint32_t tU = lane_addr + TM_UT + ub * 128 + half * 32;
         ptx::tmem_ld_32x32b_x32(tU, u);
-        ptx::tmem_ld_32x32b_x32(tU + 64, t);
+        if (p.gated) ptx::tmem_ld_32x32b_x32(tU + 64, t);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_UTEMPTY + ub));  // accumulators are in registers: the MMA warp may overwrite them
@@ -322,17 +326,20 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(x1row + off));
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(x2row + off));
           const uint4 bu4 = __ldg(reinterpret_cast<const uint4*>(p.bu + col0 + g * 8));
-          const uint4 gb4 = __ldg(reinterpret_cast<const uint4*>(p.gbu + col0 + g * 8));
+          const uint4 gb4 = p.gated ? __ldg(reinterpret_cast<const uint4*>(p.gbu + col0 + g * 8)) : make_uint4(0, 0, 0, 0);
           const uint32_t buw[4] = {bu4.x, bu4.y, bu4.z, bu4.w}, gbw[4] = {gb4.x, gb4.y, gb4.z, gb4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = g * 8 + e * 2;
             float y0 = fmaf(p.kappa, bf_lo(b[e]), p.alpha * (__uint_as_float(u[j]) + bf_lo(buw[e])));
             float y1 = fmaf(p.kappa, bf_hi(b[e]), p.alpha * (__uint_as_float(u[j + 1]) + bf_hi(buw[e])));
-            float g0 = sigmoid_fast(__uint_as_float(t[j]) + bf_lo(gbw[e]));
-            float g1 = sigmoid_fast(__uint_as_float(t[j + 1]) + bf_hi(gbw[e]));
-            float h0 = p.add_gate ? y0 + g0 : y0 * g0;
-            float h1 = p.add_gate ? y1 + g1 : y1 * g1;
+            float h0 = y0, h1 = y1;
+            if (p.gated) {
+              float g0 = sigmoid_fast(__uint_as_float(t[j]) + bf_lo(gbw[e]));
+              float g1 = sigmoid_fast(__uint_as_float(t[j + 1]) + bf_hi(gbw[e]));
+              h0 = p.add_gate ? y0 + g0 : y0 * g0;
+              h1 = p.add_gate ? y1 + g1 : y1 * g1;
+            }
             float s0 = p.s, s1 = p.s;
             if (p.thr16) {
               const uint32_t two = (uint32_t)(hsh[e >> 1] >> (32 * (e & 1)));  // 16 bits for column j, 16 for j+1
@@ -363,7 +370,7 @@ int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uin
 }
 
 int pick_R(const VlpetK1Desc& D) {
-  int m = D.r > D.rg ? D.r : D.rg;
+  int m = (D.gate == VLPET_GATE_LARGE && D.rg > D.r) ? D.rg : D.r;
   if (m <= 32) return 32;
   if (m <= 64) return 64;
   if (m <= 96) return 96;
@@ -404,9 +411,10 @@ int launch(const VlpetK1Desc& D, const CUtensorMap* maps, const Params& p, cudaS
 }  // namespace
 
 bool fused_k1_fwd_supported(const VlpetK1Desc& D) {
-  if (D.dtype != VLPET_BF16 || D.gate != VLPET_GATE_LARGE) return false;
+  if (D.dtype != VLPET_BF16 || (D.gate != VLPET_GATE_LARGE && D.gate != VLPET_GATE_NONE)) return false;
   if (D.d % CH != 0 || D.d < CH) return false;
-  if (D.r % 8 != 0 || D.rg % 8 != 0 || pick_R(D) == 0) return false;
+  const bool gated = D.gate == VLPET_GATE_LARGE;
+  if (D.r % 8 != 0 || (gated && D.rg % 8 != 0) || pick_R(D) == 0) return false;
   if (D.M <= 0 || D.M > (int64_t)0x7fffff00) return false;
   const DevInfo& di = dev_info();
   return di.ok && di.major == 10;
@@ -416,7 +424,9 @@ size_t fused_k1_fwd_ws(const VlpetK1Desc&) { return 0; }
 
 int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const VlpetK1Params& w, void* out, void*, size_t,
                  cudaStream_t st) {
-  if (!aligned16(w.Wd) || !aligned16(w.Wu) || !aligned16(w.Gd) || !aligned16(w.Gu) || !aligned16(w.bu) || !aligned16(w.gbu))
+  const bool gated = D.gate == VLPET_GATE_LARGE;
+  if (!aligned16(w.Wd) || !aligned16(w.Wu) || !aligned16(w.bu) ||
+      (gated && (!aligned16(w.Gd) || !aligned16(w.Gu) || !aligned16(w.gbu))))
     return fail(VLPET_E_ALIGN, "k1_fwd(fused): weights must be 16-byte aligned");
   const int R = pick_R(D);
   CUtensorMap maps[7];
@@ -424,14 +434,14 @@ int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const Vlp
   VLPET_TRY(make_map(&maps[1], x2, (uint64_t)D.M, (uint64_t)D.d, TILE_M, false));
   VLPET_TRY(make_map(&maps[2], out, (uint64_t)D.M, (uint64_t)D.d, TILE_M, false));
   VLPET_TRY(make_map(&maps[3], w.Wd, (uint64_t)D.r, (uint64_t)D.d, (uint32_t)R, true));
-  VLPET_TRY(make_map(&maps[4], w.Gd, (uint64_t)D.rg, (uint64_t)D.d, (uint32_t)R, true));
+  VLPET_TRY(make_map(&maps[4], gated ? w.Gd : w.Wd, (uint64_t)(gated ? D.rg : D.r), (uint64_t)D.d, (uint32_t)R, true));
   VLPET_TRY(make_map(&maps[5], w.Wu, (uint64_t)D.d, (uint64_t)D.r, CH, true));
-  VLPET_TRY(make_map(&maps[6], w.Gu, (uint64_t)D.d, (uint64_t)D.rg, CH, true));
+  VLPET_TRY(make_map(&maps[6], gated ? w.Gu : w.Wu, (uint64_t)D.d, (uint64_t)(gated ? D.rg : D.r), CH, true));
   Params p;
-  p.M = D.M; p.d = D.d; p.r = D.r; p.rg = D.rg; p.add_gate = D.add_gate;
+  p.M = D.M; p.d = D.d; p.r = D.r; p.rg = gated ? D.rg : D.r; p.add_gate = D.add_gate; p.gated = gated ? 1 : 0;
   p.s = D.s; p.alpha = D.alpha; p.kappa = D.kappa;
   p.bd = static_cast<const __nv_bfloat16*>(w.bd); p.bu = static_cast<const __nv_bfloat16*>(w.bu);
-  p.gbd = static_cast<const __nv_bfloat16*>(w.gbd); p.gbu = static_cast<const __nv_bfloat16*>(w.gbu);
+  p.gbd = static_cast<const __nv_bfloat16*>(gated ? w.gbd : w.bd); p.gbu = static_cast<const __nv_bfloat16*>(gated ? w.gbu : w.bu);
   p.seed = D.seed;
   p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
   p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
