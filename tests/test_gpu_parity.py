@@ -433,6 +433,42 @@ def test_k3_matches_reference_golden(V, path):
             assert rel(f(P[k].grad), g["d" + k]) < TOL_F32, k
 
 
+@pytest.mark.parametrize("B,N,F,d,nlvr", [(7, 36, 2048, 768, False), (3, 72, 512, 768, True), (40, 36, 2048, 768, False)])
+def test_k3_bf16_tensor_core_path_matches_oracle(V, B, N, F, d, nlvr):
+    """bf16 visual projection: tcgen05 feat GEMM (fp32 accumulate, fp32 pre-norm) + row kernel; backward dWf through the
+    token-contracted tensor-core GEMM with a bf16 copy of dF.  fp64 oracle on the bf16-rounded inputs / weights:
+    out passes bf16_check at 1e-3; fp32 gradients within 1e-3 except dWf (bf16 storage of dF feeding the GEMM) 6e-3."""
+    rng = np.random.default_rng(B + N + F)
+    Vv = 500
+    p = {"Wf": rng.standard_normal((d, F)) * 0.02, "bf": rng.standard_normal(d) * 0.02,
+         "ln_f_w": 1 + 0.1 * rng.standard_normal(d), "ln_f_b": 0.1 * rng.standard_normal(d),
+         "Wp": rng.standard_normal((d, 5)) * 0.5, "bp": rng.standard_normal(d) * 0.5,
+         "ln_p_w": 1 + 0.1 * rng.standard_normal(d), "ln_p_b": 0.1 * rng.standard_normal(d),
+         "E_img": rng.standard_normal((2, d)) * 0.02, "E_obj": rng.standard_normal((Vv, d)) * 0.02}
+    feats = rng.standard_normal((B, N, F))
+    pos = np.abs(rng.standard_normal((B, N, 4))) * (1.0 if nlvr else 0.0)
+    dout = rng.standard_normal((B, N, d))
+    img = np.tile(np.array([0] * (N // 2) + [1] * (N - N // 2)), (B, 1)) if nlvr else None
+    obj = np.tile(np.concatenate([np.arange(N // 2), np.arange(N - N // 2)]), (B, 1)) if nlvr else None
+    bf = torch.bfloat16
+    names = ["Wf", "bf", "ln_f_w", "ln_f_b", "Wp", "bp", "ln_p_w", "ln_p_b", "E_img"]
+    P = {k: dev(p[k], bf).float().requires_grad_() for k in names}
+    out = V.visual_projection(dev(feats, bf), dev(pos, bf), None if img is None else torch.tensor(img, device="cuda"),
+                              None if obj is None else torch.tensor(obj, device="cuda"), *[P[k] for k in names],
+                              dev(p["E_obj"], bf))
+    out.backward(dev(dout, bf))
+    torch.cuda.synchronize()
+    pr = {k: bf16_round(v).reshape(np.shape(v)) for k, v in p.items()}
+    ref, c = O.visproj_fwd(bf16_round(feats), bf16_round(pos), pr, img, obj, rms=False, eps=1e-5)
+    _, gr = O.visproj_bwd(bf16_round(dout), pr, c, rms=False)
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    bf16_check(f(out), ref, TOL_BF16)
+    for k in names:
+        e = rel(f(P[k].grad), gr[k])
+        print(k, "%.2e" % e)
+        assert e < (6e-3 if k == "Wf" else TOL_BF16), (k, e)
+
+
 # ------------------------------------------------------------------------------------------------ misc C-ABI behaviour
 def test_abi_errors_are_loud(V):
     x = torch.zeros(4, 64, device="cuda")

@@ -166,7 +166,6 @@ static int check_k3(const VlpetK3Desc* D, const VlpetK3Params* w) {
   if (!w->Wf || !w->bf || !w->ln_f_w || !w->Wp || !w->bp || !w->ln_p_w || !w->E_img || !w->E_obj)
     return fail(VLPET_E_BADARG, "k3: weights missing");
   if (!D->rms && (!w->ln_f_b || !w->ln_p_b)) return fail(VLPET_E_BADARG, "k3: LayerNorm biases missing");
-  if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k3: no fused kernel yet");
   return 0;
 }
 size_t vlpet_k3_fwd_workspace_bytes(const VlpetK3Desc* D) { return D ? generic_k3_fwd_ws(*D) : 0; }

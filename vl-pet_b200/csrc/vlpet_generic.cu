@@ -643,7 +643,7 @@ namespace {
 __global__ void visproj_row_kernel(const float* F, const void* pos, int bf16, const int64_t* img_ids,
                                    const int64_t* obj_ids, VlpetK3Params w, int64_t M, int N, int d, int V, int rms,
                                    float eps, void* out, const void* dout, float* dF, float* dA, float* XF, float* XA,
-                                   float* P5) {
+                                   float* P5, __nv_bfloat16* dFb) {
   int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   int lane = threadIdx.x % 32;
   if (row >= M) return;
@@ -710,7 +710,9 @@ __global__ void visproj_row_kernel(const float* F, const void* pos, int bf16, co
     float go = ld_as_float(dout, row * d + c, bf16);
     float xf = (f - mf) * rf, xa = (a - ma) * ra;
     float g1 = go * ld_as_float(w.ln_f_w, c, bf16), g2 = go * ld_as_float(w.ln_p_w, c, bf16);
-    dF[row * d + c] = rf * (g1 - gf - xf * gfx);
+    const float dfv = rf * (g1 - gf - xf * gfx);
+    dF[row * d + c] = dfv;
+    if (dFb) dFb[row * d + c] = __float2bfloat16_rn(dfv);   // bf16 copy: operand of the tensor-core dWf GEMM
     dA[row * d + c] = ra * (g2 - ga - xa * gax);
     XF[row * d + c] = xf;
     XA[row * d + c] = xa;
@@ -720,18 +722,32 @@ __global__ void visproj_row_kernel(const float* F, const void* pos, int bf16, co
 }  // namespace
 
 size_t generic_k3_fwd_ws(const VlpetK3Desc&) { return 0; }
+// tensor-core paths of K3 (bf16 only): the feat projection GEMM (vlpet_gemm_sm100.cu) and dWf through the
+// token-contracted weight-gradient GEMM (vlpet_wgrad_sm100.cu) in column blocks of `k3_wgrad_block(d)` outputs
+static int k3_wgrad_block(int d) { return d % 96 == 0 ? 96 : (d % 64 == 0 ? 64 : 0); }
+static bool k3_tc_fwd(const VlpetK3Desc& D) {
+  return D.dtype == VLPET_BF16 && D.impl != VLPET_IMPL_GENERIC && gemm_sm100_supported(D.M, D.d, D.F, D.d);
+}
+static bool k3_tc_bwd(const VlpetK3Desc& D) {
+  return D.dtype == VLPET_BF16 && D.impl != VLPET_IMPL_GENERIC && k3_wgrad_block(D.d) != 0 && D.F % 8 == 0 &&
+         wgrad_sm100_supported(D.F, k3_wgrad_block(D.d)) && device_sm_count() > 0;
+}
 size_t generic_k3_bwd_ws(const VlpetK3Desc& D) {
-  return 4 * align_up((size_t)D.M * D.d * 4, 256) + align_up((size_t)D.M * 5 * 4, 256);
+  return 4 * align_up((size_t)D.M * D.d * 4, 256) + align_up((size_t)D.M * 5 * 4, 256) +
+         (k3_tc_bwd(D) ? align_up((size_t)D.M * D.d * 2, 256) : 0);
 }
 
 int generic_k3_fwd(const VlpetK3Desc& D, const void* feats, const void* pos, const int64_t* img_ids,
                    const int64_t* obj_ids, const VlpetK3Params& w, void* out, float* save, void*, size_t,
                    cudaStream_t st) {
   const int bf = D.dtype == VLPET_BF16;
-  VLPET_TRY(launch_gemm(linear_nt(feats, bf, w.Wf, w.bf, bf, save, 0, D.M, D.d, D.F), st));
+  if (k3_tc_fwd(D) && aligned16(feats) && aligned16(w.Wf) && aligned16(save))
+    VLPET_TRY(gemm_sm100(feats, D.F, w.Wf, D.F, w.bf, save, D.d, D.M, D.d, D.F, st));
+  else
+    VLPET_TRY(launch_gemm(linear_nt(feats, bf, w.Wf, w.bf, bf, save, 0, D.M, D.d, D.F), st));
   visproj_row_kernel<<<warp_rows_blocks(D.M), 256, 0, st>>>(save, pos, bf, img_ids, obj_ids, w, D.M, D.N, D.d, D.V,
                                                            D.rms, D.eps, out, nullptr, nullptr, nullptr, nullptr,
-                                                           nullptr, nullptr);
+                                                           nullptr, nullptr, nullptr);
   VLPET_LAUNCH_OK();
   return 0;
 }
@@ -748,9 +764,11 @@ int generic_k3_bwd(const VlpetK3Desc& D, const void* feats, const void* pos, con
   float* XF = a.take<float>(M * d);
   float* XA = a.take<float>(M * d);
   float* P5 = a.take<float>(M * 5);
+  const bool tc = k3_tc_bwd(D) && aligned16(feats) && G.dWf && aligned16(G.dWf);
+  __nv_bfloat16* dFb = tc ? a.take<__nv_bfloat16>(M * d) : nullptr;
   if (!a.ok()) return fail(VLPET_E_WORKSPACE, "k3_bwd: workspace %zu < %zu bytes", ws_bytes, a.off);
   visproj_row_kernel<<<warp_rows_blocks(M), 256, 0, st>>>(save, pos, bf, img_ids, nullptr, w, M, D.N, d, D.V, D.rms,
-                                                         D.eps, nullptr, dout, dF, dA, XF, XA, P5);
+                                                         D.eps, nullptr, dout, dF, dA, XF, XA, P5, dFb);
   VLPET_LAUNCH_OK();
   VLPET_TRY(launch_colsum(dout, bf, XF, 0, nullptr, 0, M, d, 1.f, G.dln_f_w, st));
   VLPET_TRY(launch_colsum(dout, bf, XA, 0, nullptr, 0, M, d, 1.f, G.dln_p_w, st));
@@ -758,7 +776,22 @@ int generic_k3_bwd(const VlpetK3Desc& D, const void* feats, const void* pos, con
     VLPET_TRY(launch_colsum(dout, bf, nullptr, 0, nullptr, 0, M, d, 1.f, G.dln_f_b, st));
     VLPET_TRY(launch_colsum(dout, bf, nullptr, 0, nullptr, 0, M, d, 1.f, G.dln_p_b, st));
   }
-  VLPET_TRY(launch_wgrad(dF, 0, d, feats, bf, D.F, M, G.dWf, 1.f, st));
+  if (tc) {
+    // dWf[n, f] = sum_tok dF[tok, n] feats[tok, f], produced transposed (rows = f) in column blocks of nb outputs
+    const int nb = k3_wgrad_block(d), nblk = d / nb, sms = device_sm_count();
+    for (int b0 = 0; b0 < nblk; b0 += 4) {
+      const int np = (nblk - b0) < 4 ? (nblk - b0) : 4;
+      const void* A[4]; const void* B[4]; int64_t lda[4], ldb[4]; int nbv[4], tr[4]; float* out[4]; float* bias[4]; float sc[4];
+      for (int i = 0; i < np; ++i) {
+        A[i] = feats; lda[i] = D.F;
+        B[i] = dFb + (size_t)(b0 + i) * nb; ldb[i] = d; nbv[i] = nb; tr[i] = 1;
+        out[i] = G.dWf + (size_t)(b0 + i) * nb * D.F; bias[i] = nullptr; sc[i] = 1.0f;
+      }
+      VLPET_TRY(wgrad_sm100(np, A, lda, B, ldb, nbv, out, bias, sc, tr, M, D.F, nb, sms, st));
+    }
+  } else {
+    VLPET_TRY(launch_wgrad(dF, 0, d, feats, bf, D.F, M, G.dWf, 1.f, st));
+  }
   VLPET_TRY(launch_colsum(dF, 0, nullptr, 0, nullptr, 0, M, d, 1.f, G.dbf, st));
   VLPET_TRY(launch_wgrad(dA, 0, d, P5, 0, 5, M, G.dWp, 1.f, st));
   VLPET_TRY(launch_colsum(dA, 0, nullptr, 0, nullptr, 0, M, d, 1.f, G.dbp, st));

@@ -310,6 +310,7 @@ class VLBart(nn.Module):
         self.lm_head = nn.Linear(config.d_model, config.vocab_size, bias=False)
         self.apply(self._init_weights)
         self.lm_head.weight = self.model.shared.weight           # tied, as BartForConditionalGeneration
+        self._lm_pad = None                                      # (key, padded weight, padded bias) cache, see _lm_operands
 
     def _init_weights(self, m):
         std = self.config.init_std                               # my_transformers/modeling_bart.py:1819-1828
@@ -322,17 +323,36 @@ class VLBart(nn.Module):
             if m.padding_idx is not None:
                 m.weight.data[m.padding_idx].zero_()
 
+    def _lm_operands(self, dtype):
+        """LM-head weight / bias for the logits GEMM.  The reference vocabulary (50 265 + 200 = 50 465 rows) is odd, which
+        sends cuBLAS to an unaligned legacy kernel; while the table is frozen on the GPU (always, under the VL-PET flags)
+        the GEMM runs on a copy padded to a multiple of 64 rows whose extra logits get a -1e4 bias, i.e. exp() == 0: the
+        cross-entropy over the padded width equals the reference's over `vocab_size` classes."""
+        w, V = self.lm_head.weight, self.config.vocab_size
+        if w.requires_grad or not w.is_cuda or V % 64 == 0:
+            return w, self.final_logits_bias.to(dtype), V
+        key = (w.data_ptr(), w.dtype, w._version, self.final_logits_bias._version)
+        if self._lm_pad is None or self._lm_pad[0] != key:
+            Vp = (V + 63) // 64 * 64
+            wp = w.new_zeros(Vp, w.shape[1])
+            wp[:V] = w.detach()
+            bp = torch.full((1, Vp), -1e4, dtype=w.dtype, device=w.device)
+            bp[:, :V] = self.final_logits_bias.to(w.dtype)
+            self._lm_pad = (key, wp, bp)
+        return self._lm_pad[1], self._lm_pad[2].to(dtype), self._lm_pad[1].shape[0]
+
     def forward(self, input_ids, vis_inputs, labels, attention_mask=None, vis_attention_mask=None, task=None):
         """-> per-token loss [B*T] (reduction='none', ignore_index=-100) and logits."""
         cfg = self.config
         dec_in = shift_tokens_right(labels, cfg.pad_token_id, cfg.decoder_start_token_id)
         h = self.model(input_ids, vis_inputs, dec_in, attention_mask, vis_attention_mask, task=task)
-        logits = F.linear(h, self.lm_head.weight) + self.final_logits_bias.to(h.dtype)
-        lg = logits.view(-1, cfg.vocab_size)
+        w, b, width = self._lm_operands(h.dtype)
+        logits = F.linear(h, w) + b
+        lg = logits.view(-1, width)
         if lg.dtype in (torch.bfloat16, torch.float16):
             lg = lg.float()
         loss = F.cross_entropy(lg, labels.reshape(-1), ignore_index=-100, reduction="none")
-        return loss, logits
+        return loss, logits[..., :cfg.vocab_size]
 
     def train_step(self, batch: dict) -> dict:
         """One task batch -> {'loss': scalar}.  Batch schema = the reference collate (vqa_clip_data.py:365-390):
