@@ -63,7 +63,8 @@ class PetBucket:
     Each parameter starts on a 1024-element boundary so the per-block weight-decay mask of vlpet_adamw_step applies
     and every view is 16-byte aligned (TMA)."""
 
-    def __init__(self, named_params, device, shadow_dtype: Optional[torch.dtype] = torch.bfloat16):
+    def __init__(self, named_params, device, shadow_dtype: Optional[torch.dtype] = torch.bfloat16,
+                 master_dtype: torch.dtype = torch.float32):
         # decayed parameters first, then (from a 1024 boundary) the no-decay group; inside a group parameters keep
         # registration order on 8-element boundaries, so the head slices of a multi-head down projection
         # (weights in one group, biases in the other) stay ADJACENT and are read as one [r,d] / [r] tensor for free
@@ -80,16 +81,16 @@ class PetBucket:
         self.n_decay_elems = _align(offs[len(decay)] if nodecay else total)
         total = _align(total)
         self.offsets, self.numel = offs, total
-        self.flat_param = torch.zeros(total, dtype=torch.float32, device=device)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=device)
-        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=device)
-        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=device)
+        self.flat_param = torch.zeros(total, dtype=master_dtype, device=device)
+        self.flat_grad = torch.zeros(total, dtype=master_dtype, device=device)
+        self.exp_avg = torch.zeros(total, dtype=master_dtype, device=device)
+        self.exp_avg_sq = torch.zeros(total, dtype=master_dtype, device=device)
         self.shadow = torch.zeros(total, dtype=shadow_dtype, device=device) if shadow_dtype is not None else None
         mask = torch.zeros(total // 1024, dtype=torch.uint8)
         mask[:self.n_decay_elems // 1024] = 1
         for n, p, o in zip(self.names, self.params, offs):
             view = self.flat_param[o:o + p.numel()].view_as(p)
-            view.copy_(p.data.to(device=device, dtype=torch.float32))
+            view.copy_(p.data.to(device=device, dtype=master_dtype))
             p.data = view
             p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
             p.requires_grad_(True)
@@ -109,7 +110,7 @@ class PetBucket:
     def zero_grad(self):
         self.flat_grad.zero_()
         for p, o in zip(self.params, self.offsets):        # autograd may have replaced .grad; re-pin the views
-            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + self.flat_grad.element_size() * o:
                 p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
 
 
@@ -145,7 +146,8 @@ class PetTrainer:
         for b in model.buffers():
             if b.is_floating_point():
                 b.data = b.data.to(compute_dtype)
-        self.bucket = PetBucket(named, self.device, torch.bfloat16 if compute_dtype == torch.bfloat16 else None)
+        self.bucket = PetBucket(named, self.device, torch.bfloat16 if compute_dtype == torch.bfloat16 else None,
+                                torch.float64 if compute_dtype == torch.float64 else torch.float32)
         self._norm_sq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._scale = torch.ones(1, dtype=torch.float32, device=self.device)
         if self.world > 1:                                        # identical start on every rank
