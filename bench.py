@@ -223,8 +223,9 @@ def run_ours(a):
     cfg = H.bart_base_vlpet_large(r=a.rank_r, rg=a.rank_r, dec_r=a.rank_r, assume_no_padding=True)
     model = H.VLBart(cfg).train()
     total_steps = 20 * 1000
-    trainer = H.PetTrainer(model, cfg, dev, lr=1e-3, total_steps=total_steps)
-    trainer.step_idx = total_steps // 10          # past warm-up: a non-zero learning rate
+    Trainer = H.GraphedPetTrainer if a.graphs else H.PetTrainer
+    trainer = Trainer(model, cfg, dev, lr=1e-3, total_steps=total_steps)
+    trainer.set_step(total_steps // 10)           # past warm-up: a non-zero learning rate
     host_cycle = H.multitask_cycle(a.batch_size, TASKS, seed=0, pin=True, rank=rank, world=world)
     dev_cycle = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()} for b in host_cycle]
     global_sizes = H.task_batch_sizes(a.batch_size)
@@ -280,7 +281,7 @@ def run_ours(a):
     # ---- roofline leg: the same steps with every PET kernel launch bracketed by CUDA events on its stream
     F_.profile_kernels(True)
     for i in range(nb):
-        step_resident(i)
+        H.PetTrainer.train_step(trainer, dev_cycle[i % nb])      # eager path: graph replays cannot carry the event pairs
     torch.cuda.synchronize()
     prof = F_.profile_summary(F_.profile_kernels(False))
     peak, peak_src = peaks()
@@ -313,7 +314,8 @@ def run_ours(a):
             "config": {"workload": workload_name(a.batch_size, a.rank_r), "global_batch_per_task": global_sizes,
                        "parallelism": f"dp{world} (batch sharded by sample, 1 all-reduce of {trainer.bucket.n_trainable} PET grads/step)",
                        "l2": "per-step working set (weights + activations) exceeds the 126 MB L2; no explicit flush",
-                       "trainable_params": trainer.bucket.n_trainable, "optimizer": "fused AdamW on the flat PET bucket"},
+                       "trainable_params": trainer.bucket.n_trainable, "optimizer": "fused AdamW on the flat PET bucket",
+                       "cuda_graphs": bool(a.graphs)},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / a.steps, 3), "last_loss": losses[-1] if losses else None},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "k1_micro": micro}

@@ -88,6 +88,9 @@ typedef struct VlpetK1Desc {
   float p_drop;     /* dropout between gate and residual (modeling_bart.py:1259); 0 = identity (eval / parity) */
   uint64_t seed;    /* dropout stream: keep(m,c) is a pure function of (seed, m*d+c), so the backward regenerates
                        the forward mask from the same seed; the mask is NOT torch's Philox stream            */
+  const uint64_t* seed_dev; /* optional DEVICE scalar added to `seed` when the kernel starts: lets a CUDA graph that
+                       captured this call draw a fresh mask on every replay (bump it on the stream between replays;
+                       forward and backward of one step must see the same value)                              */
 } VlpetK1Desc;
 
 typedef struct VlpetK1Params { /* dtype = desc.dtype; unused members NULL */
@@ -210,6 +213,11 @@ VLPET_API int vlpet_adamw_step(float* param, const float* grad, float* exp_avg, 
                      int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                      const float* grad_scale_dev /* device scalar or NULL */, void* bf16_shadow /* or NULL */,
                      void* stream);
+/* Same step with the step-dependent scalars read from DEVICE memory, so the launch can live in a CUDA graph:
+ * hyper_dev[0] = lr, hyper_dev[1] = lr * sqrt(1 - beta2^t) / (1 - beta1^t).                                   */
+VLPET_API int vlpet_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const uint8_t* wd_mask,
+                         int64_t n, const float* hyper_dev, float beta1, float beta2, float eps, float weight_decay,
+                         const float* grad_scale_dev, void* bf16_shadow, void* stream);
 /* sum of squares of a flat fp32 buffer accumulated into *out_dev (device scalar; caller zeroes it)       */
 VLPET_API int vlpet_sumsq(const float* x, int64_t n, float* out_dev, void* stream);
 

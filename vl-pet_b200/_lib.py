@@ -24,7 +24,7 @@ class K1Desc(C.Structure):
     _fields_ = [("M", C.c_int64), ("L", C.c_int32), ("d", C.c_int32), ("r", C.c_int32), ("rg", C.c_int32),
                 ("gate", C.c_int32), ("add_gate", C.c_int32), ("dtype", C.c_int32), ("impl", C.c_int32),
                 ("s", C.c_float), ("alpha", C.c_float), ("kappa", C.c_float), ("p_drop", C.c_float),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("seed_dev", C.c_void_p)]
 
 
 class K1Params(C.Structure):
@@ -93,6 +93,8 @@ SYMBOLS = {
     "vlpet_cast_f32_to_bf16": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "vlpet_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_float, C.c_int32, _vp, _vp, _vp]),
+    "vlpet_adamw_step_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_float, C.c_float, C.c_float, C.c_float,
+                                       _vp, _vp, _vp]),
     "vlpet_sumsq": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
     "vlpet_version": (C.c_int, []),
     "vlpet_last_error": (C.c_char_p, []),

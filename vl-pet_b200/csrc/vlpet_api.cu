@@ -233,6 +233,29 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+__global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, const uint8_t* __restrict__ wd_mask, int64_t n,
+                                 const float* __restrict__ hyper, float b1, float b2, float eps, float wd,
+                                 const float* __restrict__ gscale, __nv_bfloat16* __restrict__ shadow) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float gs = gscale ? *gscale : 1.0f;
+  const float lr = hyper[0], step_size = hyper[1];
+  for (; i < n; i += stride) {
+    float gi = g[i] * gs;
+    float mi = b1 * m[i] + (1.0f - b1) * gi;
+    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    float pi = p[i];
+    pi -= step_size * mi / (sqrtf(vi) + eps);
+    float w = wd_mask ? (wd_mask[i >> 10] ? wd : 0.0f) : wd;
+    pi -= lr * w * pi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+  }
+}
+
 __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -277,6 +300,18 @@ int vlpet_adamw_step(float* param, const float* grad, float* exp_avg, float* exp
   float step_size = (float)(lr * sqrt(bc2) / bc1);
   adamw_kernel<<<flat_blocks(n, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, grad, exp_avg, exp_avg_sq, wd_mask, n, lr, beta1, beta2, eps, weight_decay, step_size, grad_scale_dev,
+      static_cast<__nv_bfloat16*>(bf16_shadow));
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+
+int vlpet_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const uint8_t* wd_mask,
+                         int64_t n, const float* hyper_dev, float beta1, float beta2, float eps, float weight_decay,
+                         const float* grad_scale_dev, void* bf16_shadow, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper_dev || n < 0) return fail(VLPET_E_BADARG, "adamw_dev: bad arguments");
+  if (n == 0) return 0;
+  adamw_dev_kernel<<<flat_blocks(n, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, wd_mask, n, hyper_dev, beta1, beta2, eps, weight_decay, grad_scale_dev,
       static_cast<__nv_bfloat16*>(bf16_shadow));
   VLPET_LAUNCH_OK();
   return 0;

@@ -189,10 +189,13 @@ struct Drop {  // dropout stream of one K1 call (thr16 == 0: identity)
   uint64_t seed = 0;
   uint32_t thr16 = 0;
   float inv_keep = 1.f;
+  const uint64_t* seed_dev = nullptr;
+  __device__ __forceinline__ uint64_t eff() const { return seed + ((thr16 && seed_dev) ? *seed_dev : 0ull); }
 };
 inline Drop make_drop(const VlpetK1Desc& D) {
   Drop x;
   x.seed = D.seed;
+  x.seed_dev = D.seed_dev;
   x.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
   x.inv_keep = x.thr16 ? 1.0f / (1.0f - (float)x.thr16 / 65536.0f) : 1.0f;
   return x;
@@ -210,7 +213,7 @@ __global__ void colsum_kernel(const void* A, int a_bf16, const void* B, int b_bf
     if (ids && ids[m] != match) continue;
     float v = ld_as_float(A, m * C + c, a_bf16);
     if (B) v *= ld_as_float(B, m * C + c, b_bf16);
-    acc += v * drop_scale(dr.seed, dr.thr16, dr.inv_keep, m * C + c);
+    acc += v * drop_scale(dr.eff(), dr.thr16, dr.inv_keep, m * C + c);
   }
   atomicAdd(out + c, acc * scale);
 }
@@ -282,7 +285,7 @@ __global__ void k1_out_kernel(const void* x1, int bf16, const float* Y1, const f
     } else {
       h = y1;
     }
-    st_from_float(out, i, ld_as_float(x1, i, bf16) + s * h * drop_scale(dr.seed, dr.thr16, dr.inv_keep, i), bf16);
+    st_from_float(out, i, ld_as_float(x1, i, bf16) + s * h * drop_scale(dr.eff(), dr.thr16, dr.inv_keep, i), bf16);
   }
 }
 // large / none / middle_y backward, elementwise, in place:  Y1 <- dy1,  Tg <- dt (large);  dx1 <- dout (non-large)
@@ -293,7 +296,7 @@ __global__ void k1_bwd_elem_kernel(const void* dout, int bf16, float* Y1, float*
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     float go = ld_as_float(dout, i, bf16);
-    float dh = s * go * drop_scale(dr.seed, dr.thr16, dr.inv_keep, i);
+    float dh = s * go * drop_scale(dr.eff(), dr.thr16, dr.inv_keep, i);
     if (gate == VLPET_GATE_LARGE) {
       float G = sigmoid_f(Tg[i]);
       float y1 = Y1[i];
@@ -319,7 +322,7 @@ __global__ void rowsum_dh_kernel(const void* dout, int bf16, const float* Y1, in
   if (row >= M) return;
   float acc = 0.f;
   for (int c = lane; c < d; c += 32) {
-    float dh = s * ld_as_float(dout, row * d + c, bf16) * drop_scale(dr.seed, dr.thr16, dr.inv_keep, row * d + c);
+    float dh = s * ld_as_float(dout, row * d + c, bf16) * drop_scale(dr.eff(), dr.thr16, dr.inv_keep, row * d + c);
     acc += add_gate ? dh : dh * Y1[row * d + c];
   }
   acc = warp_sum(acc);
@@ -358,7 +361,7 @@ __global__ void k1_bwd_rowgate_elem_kernel(const void* dout, int bf16, float* Y1
     int64_t m = i / d;
     int c = (int)(i - m * d);
     float go = ld_as_float(dout, i, bf16);
-    float dh = s * go * drop_scale(dr.seed, dr.thr16, dr.inv_keep, i);
+    float dh = s * go * drop_scale(dr.eff(), dr.thr16, dr.inv_keep, i);
     float g = G[m / L_or_1];
     float dt = dtrow[m];
     Y1[i] = (add_gate ? dh : dh * g) + dt * ld_as_float(w2, c, bf16);

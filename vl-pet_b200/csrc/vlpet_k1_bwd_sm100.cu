@@ -68,6 +68,7 @@ struct BParams {
   int pz, pq;                           // scratch row pitches (elements)
   float *dbd, *dgbd;                    // fp32 bias gradients (accumulated into) or nullptr
   uint64_t seed;
+  const uint64_t* seed_dev;
   uint32_t thr16;
   float inv_keep;
 };
@@ -392,6 +393,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t swz = (uint32_t)(row & 7);
+    const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
     float bias_acc[R / 32 > 0 ? R / 32 : 1];
 #pragma unroll
     for (int i = 0; i < R / 32; ++i) bias_acc[i] = 0.f;
@@ -470,8 +472,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         for (int g = 0; g < 4; ++g) {
           uint64_t hsh[2] = {0, 0};
           if (p.thr16) {
-            hsh[0] = drop_hash4(p.seed, (uint64_t)(idx0 + g * 8) >> 2);
-            hsh[1] = drop_hash4(p.seed, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
+            hsh[0] = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
+            hsh[1] = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
           }
           const uint32_t off = (((uint32_t)(half * 4 + g)) ^ swz) << 4;
           uint32_t xv[4], dv[4], ou[4], ot[4];
@@ -579,8 +581,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         for (int g = 0; g < 4; ++g) {
           uint64_t hsh[2] = {0, 0};
           if (p.thr16) {
-            hsh[0] = drop_hash4(p.seed, (uint64_t)(idx0 + g * 8) >> 2);
-            hsh[1] = drop_hash4(p.seed, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
+            hsh[0] = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
+            hsh[1] = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
           }
           const uint32_t off = (((uint32_t)(half * 4 + g)) ^ swz) << 4;
           uint32_t dv[4] = {0, 0, 0, 0}, o1[4], o2[4];
@@ -713,6 +715,7 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   p.zs = s.zs; p.qs = s.qs; p.das = s.das; p.dps = s.dps; p.pz = s.pz; p.pq = s.pq;
   p.dbd = G.dbd; p.dgbd = gated ? G.dgbd : nullptr;
   p.seed = D.seed;
+  p.seed_dev = D.seed_dev;
   p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
   p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
   int rc = 0;

@@ -90,6 +90,7 @@ struct Params {
   float s, alpha, kappa;
   const __nv_bfloat16 *bd, *bu, *gbd, *gbu;
   uint64_t seed;      // dropout stream (vlpet_common.cuh: drop_hash4)
+  const uint64_t* seed_dev;  // optional device scalar added to seed (CUDA-graph replays)
   uint32_t thr16;     // 0 = no dropout
   float inv_keep;
 };
@@ -260,6 +261,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     const int row = quarter * 32 + lane;     // row inside the 128-token tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t swz = (uint32_t)(row & 7);
+    const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
     uint32_t xi = 0, ui = 0, oi = 0, ti = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
       // ---- epilogue 1: z = gelu_new(A + bd) (half 0) / q = gelu_new(P + gbd) (half 1) -> swizzled K-major smem
@@ -318,8 +320,8 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         for (int g = 0; g < 4; ++g) {
           uint64_t hsh[2] = {0, 0};
           if (p.thr16) {
-            hsh[0] = drop_hash4(p.seed, (uint64_t)(idx0 + g * 8) >> 2);
-            hsh[1] = drop_hash4(p.seed, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
+            hsh[0] = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
+            hsh[1] = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
           }
           const uint32_t off = (((uint32_t)(half * 4 + g)) ^ swz) << 4;
           uint32_t a[4], b[4], o[4];
@@ -443,6 +445,7 @@ int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const Vlp
   p.bd = static_cast<const __nv_bfloat16*>(w.bd); p.bu = static_cast<const __nv_bfloat16*>(w.bu);
   p.gbd = static_cast<const __nv_bfloat16*>(gated ? w.gbd : w.bd); p.gbu = static_cast<const __nv_bfloat16*>(gated ? w.gbu : w.bu);
   p.seed = D.seed;
+  p.seed_dev = D.seed_dev;
   p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
   p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
   switch (R) {

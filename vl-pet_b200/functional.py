@@ -13,7 +13,18 @@ from . import _lib as L
 _DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
 _workspaces = {}
 _seed_counter = [0]
+_seed_dev = None   # optional device int64 scalar added to every dropout seed (CUDA-graph replays), see set_device_seed
 _prof = None   # when profiling: list of (kernel name, algorithmic bytes, start event, end event)
+
+
+def set_device_seed(t: Optional[torch.Tensor]):
+    """Register a device int64 scalar that the K1 kernels add to their dropout seed at run time (VlpetK1Desc.seed_dev).
+    A CUDA graph that captured the calls then draws a fresh mask on every replay once the caller bumps the scalar
+    (on the stream, between replays).  None switches back to host-side seeds."""
+    global _seed_dev
+    if t is not None and (not t.is_cuda or t.dtype != torch.int64 or t.numel() != 1):
+        raise ValueError("vlpet.set_device_seed: expected a CUDA int64 scalar tensor")
+    _seed_dev = t
 
 
 def profile_kernels(enable: bool):
@@ -57,7 +68,11 @@ def _stream():
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only per-device scratch buffer; safe because every call is ordered on the current stream."""
+    """Grow-only per-(device, stream) scratch buffer; safe because every call is ordered on the current stream.
+    Under CUDA-graph capture the buffer comes from the graph's private pool instead (its address is baked into the
+    captured launches, so it must not be a cached tensor that a later, larger request could replace)."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
@@ -145,7 +160,8 @@ class GatedPETFn(torch.autograd.Function):
         rg = gp[0].shape[0] if cfg.gate == "large" else 0
         desc = L.K1Desc(M=M, L=seq_len, d=d, r=r, rg=rg, gate=L.GATE_IDS[cfg.gate], add_gate=int(cfg.add_gate),
                         dtype=_DT[dt], impl=L.IMPL_IDS[cfg.impl], s=cfg.s, alpha=cfg.alpha, kappa=cfg.kappa,
-                        p_drop=cfg.p_drop if seed else 0.0, seed=seed)
+                        p_drop=cfg.p_drop if seed else 0.0, seed=seed,
+                        seed_dev=(_seed_dev.data_ptr() if (seed and _seed_dev is not None) else None))
         w = L.K1Params(Wd=_p(Wd), bd=_p(bd), Wu=_p(Wu), bu=_p(bu))
         if cfg.gate == "large":
             w.Gd, w.gbd, w.Gu, w.gbu = _p(gp[0]), _p(gp[1]), _p(gp[2]), _p(gp[3])

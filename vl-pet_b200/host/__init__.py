@@ -2,10 +2,10 @@
 (flat bucket + one all-reduce + fused AdamW) and the synthetic multitask batches of BASELINE.json's configs."""
 from .config import VLPetConfig, bart_base_vlpet_large, tiny_test_config, TASKS
 from .vlbart import VLBart, VLBartModel, JointEncoder, BartDecoder, BartEncoderLayer, BartDecoderLayer, Downsample
-from .trainer import PetTrainer, PetBucket, trainable_names, linear_warmup_lr
+from .trainer import PetTrainer, GraphedPetTrainer, PetBucket, trainable_names, linear_warmup_lr
 from .synthetic import task_batch_sizes, make_task_batch, multitask_cycle, shard_batch, batch_nbytes
 
 __all__ = ["VLPetConfig", "bart_base_vlpet_large", "tiny_test_config", "TASKS", "VLBart", "VLBartModel", "JointEncoder",
-           "BartDecoder", "BartEncoderLayer", "BartDecoderLayer", "Downsample", "PetTrainer", "PetBucket",
+           "BartDecoder", "BartEncoderLayer", "BartDecoderLayer", "Downsample", "PetTrainer", "GraphedPetTrainer", "PetBucket",
            "trainable_names", "linear_warmup_lr", "task_batch_sizes", "make_task_batch", "multitask_cycle",
            "shard_batch", "batch_nbytes"]

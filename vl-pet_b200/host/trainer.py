@@ -154,6 +154,9 @@ class PetTrainer:
             dist.broadcast(self.bucket.flat_param, src=0, group=self.pg)
             self.bucket.refresh_shadow()
 
+    def set_step(self, n: int):
+        self.step_idx = int(n)
+
     # -- the three phases of a step, separable so callers can capture / overlap them
     def forward_backward(self, batch: Dict) -> torch.Tensor:
         self.bucket.zero_grad()
@@ -191,3 +194,110 @@ class PetTrainer:
         self.exchange()
         self.optimizer_step()
         return loss
+
+
+class GraphedPetTrainer(PetTrainer):
+    """The same step replayed from CUDA graphs (static shapes make it possible): one
+    forward+backward graph per batch signature, one optimizer graph, the gradient all-reduce launched eagerly in
+    between.  Everything step-dependent lives on the device so that replays differ: the dropout seed of the PET kernels
+    (VlpetK1Desc.seed_dev), torch's own graph-safe Philox state, the step counter and the learning-rate schedule
+    (recomputed in-graph from the counter, vlpet_adamw_step_dev)."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        from .. import functional as F_
+        dev = self.device
+        self._F = F_
+        self._seed = torch.zeros(1, dtype=torch.int64, device=dev)
+        F_.set_device_seed(self._seed)
+        self._t = torch.full((1,), float(self.step_idx), dtype=torch.float32, device=dev)   # optimizer steps taken so far
+        self._hyper = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._pool = torch.cuda.graph_pool_handle()
+        self._fb = {}
+        self._opt = None
+        self._stream = torch.cuda.Stream(device=dev)
+        self._loss_out = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def set_step(self, n: int):
+        self.step_idx = int(n)
+        self._t.fill_(float(n))
+
+    @staticmethod
+    def _signature(batch: Dict):
+        return tuple((k, tuple(v.shape), str(v.dtype)) if torch.is_tensor(v) else (k, v) for k, v in sorted(batch.items()))
+
+    def _capture_fb(self, batch: Dict):
+        static = {k: (torch.empty(v.shape, dtype=v.dtype, device=self.device) if torch.is_tensor(v) else v)
+                  for k, v in batch.items()}
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                static[k].copy_(v)
+        torch.cuda.synchronize()
+        self._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._stream):
+            for _ in range(2):                     # eager warm-up on the side stream (lazy initialisation, workspaces)
+                self.forward_backward(static)
+        torch.cuda.current_stream().wait_stream(self._stream)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self._pool, stream=self._stream):
+            self._seed.add_(1000003)
+            loss = self.forward_backward(static)
+        return g, static, loss
+
+    def _optimizer_ops(self):
+        b = self.bucket
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self._norm_sq.zero_()
+        L.check(L.lib.vlpet_sumsq(C.c_void_p(b.flat_grad.data_ptr()), b.numel, C.c_void_p(self._norm_sq.data_ptr()), st),
+                "vlpet_sumsq")
+        w = float(self.world)
+        torch.clamp(self.clip / (self._norm_sq.sqrt() / w + 1e-6), max=1.0, out=self._scale)
+        self._scale.div_(w)
+        # schedule + bias correction from the device-side step counter (get_linear_schedule_with_warmup semantics)
+        warm = float(int(self.total_steps * self.warmup_ratio))
+        s_ = self._t                                                   # scheduler step = optimizer steps taken so far
+        up = s_ / max(1.0, warm)
+        down = (float(self.total_steps) - s_) / max(1.0, float(self.total_steps) - warm)
+        lr = self.lr * torch.where(s_ < warm, up, down).clamp(min=0.0)
+        self._t.add_(1.0)
+        bc1 = 1.0 - torch.pow(torch.full_like(self._t, self.betas[0]), self._t)
+        bc2 = 1.0 - torch.pow(torch.full_like(self._t, self.betas[1]), self._t)
+        self._hyper[0:1].copy_(lr)
+        self._hyper[1:2].copy_(lr * bc2.sqrt() / bc1)
+        L.check(L.lib.vlpet_adamw_step_dev(C.c_void_p(b.flat_param.data_ptr()), C.c_void_p(b.flat_grad.data_ptr()),
+                                           C.c_void_p(b.exp_avg.data_ptr()), C.c_void_p(b.exp_avg_sq.data_ptr()),
+                                           C.c_void_p(b.wd_mask.data_ptr()), b.numel, C.c_void_p(self._hyper.data_ptr()),
+                                           self.betas[0], self.betas[1], self.eps, self.wd,
+                                           C.c_void_p(self._scale.data_ptr()),
+                                           C.c_void_p(b.shadow.data_ptr()) if b.shadow is not None else C.c_void_p(0), st),
+                "vlpet_adamw_step_dev")
+
+    def _capture_opt(self):
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self._pool, stream=self._stream):
+            self._optimizer_ops()
+        return g
+
+    def train_step(self, batch: Dict) -> torch.Tensor:
+        sig = self._signature(batch)
+        ent = self._fb.get(sig)
+        if ent is None:
+            ent = self._fb[sig] = self._capture_fb(batch)
+            # the capture ran forward+backward (not the optimizer) on real data: harmless, parameters are untouched
+        g, static, loss = ent
+        for k, v in batch.items():
+            if torch.is_tensor(v) and v.data_ptr() != static[k].data_ptr():
+                static[k].copy_(v, non_blocking=True)
+        g.replay()
+        # `loss` lives in the pool the graphs share: later replays (the optimizer graph's temporaries) may reuse its
+        # storage, so the value is copied out to an ordinary tensor right behind the replay
+        self._loss_out.copy_(loss)
+        self.exchange()
+        if self._opt is None:
+            # first use: capture consumes the current gradients once eagerly inside the capture warm-up path
+            self._opt = self._capture_opt()
+        self._opt.replay()
+        self.step_idx += 1
+        return self._loss_out

@@ -311,6 +311,7 @@ class VLBart(nn.Module):
         self.apply(self._init_weights)
         self.lm_head.weight = self.model.shared.weight           # tied, as BartForConditionalGeneration
         self._lm_pad = None                                      # (key, padded weight, padded bias) cache, see _lm_operands
+        self._nlvr_ids = {}
 
     def _init_weights(self, m):
         std = self.config.init_std                               # my_transformers/modeling_bart.py:1819-1828
@@ -369,8 +370,12 @@ class VLBart(nn.Module):
             V_L = feats.shape[2]
             feats = feats.reshape(B, 2 * V_L, -1)
             boxes = boxes.reshape(B, 2 * V_L, 4)
-            img_ids = torch.tensor([0] * V_L + [1] * V_L, dtype=torch.long, device=dev).view(1, -1).expand(B, -1)
-            obj_ids = torch.arange(V_L, dtype=torch.long, device=dev).view(1, 1, V_L).expand(B, 2, -1).reshape(B, 2 * V_L)
+            key = (V_L, str(dev))
+            if key not in self._nlvr_ids:                        # built once: no host->device copy inside a step
+                self._nlvr_ids[key] = (torch.tensor([0] * V_L + [1] * V_L, dtype=torch.long, device=dev).view(1, -1),
+                                       torch.arange(V_L, dtype=torch.long, device=dev).repeat(2).view(1, -1))
+            img_ids = self._nlvr_ids[key][0].expand(B, -1)
+            obj_ids = self._nlvr_ids[key][1].expand(B, -1)
             vis_inputs = (feats, boxes, img_ids, obj_ids)
         else:
             vis_inputs = (feats, boxes)
