@@ -100,6 +100,11 @@ int vlpet_k1_bwd(const VlpetK1Desc* D, const void* x1, const void* x2, const voi
   return generic_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+// developer hook (not part of include/vlpet.h): phase timestamps of the fused K1 forward, see tools/trace_k1.py
+__attribute__((visibility("default"))) int vlpet_debug_set_k1_trace(void* dev_buf) {
+  return vlpet::set_k1_trace(static_cast<unsigned long long*>(dev_buf));
+}
+
 // ---- weight-gradient GEMM ------------------------------------------------------------------------------------
 int vlpet_wgrad_bf16(const VlpetWgradPair* pairs, int32_t npairs, int64_t Mtok, int32_t d, int32_t nout, void* stream) {
   if (!pairs || npairs < 1 || npairs > 4 || Mtok <= 0) return fail(VLPET_E_BADARG, "wgrad: bad arguments");

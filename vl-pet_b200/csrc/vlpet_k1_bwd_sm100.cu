@@ -17,7 +17,7 @@
 //   phase 3  (64-col chunks) T_c again (only G is needed; recompute beats keeping [128 x 768] gates),
 //                           DX2_c = da Wd[:,c], DX1_c = dp Gd[:,c]                    tcgen05 (B MN-major from Wd_c/Gd_c tiles)
 //   epi 4                   dx2 = k dh G + DX2, dx1 = dout + DX1                      -> smem -> TMA store
-// Warp roles: 0 TMA producer, 1 MMA issuer (TMEM owner), 2 TMA-store issuer, 3 idle, 4..11 epilogue (warp%4 = TMEM
+// Warp roles: 0 TMA producer (activations), 3 TMA producer (weights), 1 MMA issuer (TMEM owner), 2 TMA-store issuer, 4..11 epilogue (warp%4 = TMEM
 // lane quarter; (warp-4)/4 = "half": adapter branch / gate branch in epi 1/3, left / right 32 columns in epi 2/4).
 #include "sm100_ptx.cuh"
 #include "vlpet_common.cuh"
@@ -151,9 +151,9 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(B_ACCFULL + i), 1); ptx::mbar_init(bar(B_ACCEMPTY + i), EPI_THREADS); }
     ptx::fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_dout); ptx::prefetch_tmap(&tm_wd);
-    ptx::prefetch_tmap(&tm_gd); ptx::prefetch_tmap(&tm_wu); ptx::prefetch_tmap(&tm_gu);
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_dout); }
+  if (warp == 3 && lane == 0) {
+    ptx::prefetch_tmap(&tm_wd); ptx::prefetch_tmap(&tm_gd); ptx::prefetch_tmap(&tm_wu); ptx::prefetch_tmap(&tm_gu);
   }
   if (warp == 2 && lane == 0) {
     ptx::prefetch_tmap(&tm_dx1); ptx::prefetch_tmap(&tm_dx2); ptx::prefetch_tmap(&tm_du); ptx::prefetch_tmap(&tm_dt);
@@ -174,14 +174,14 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   };
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
+    // ===================================== TMA producer: activations =====================================
     if (lane == 0) {
-      uint32_t xi = 0, wi = 0;
+      uint32_t xi = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = (int)(tile * TILE_M);
         for (int ph = 0; ph < 3; ++ph) {
-          for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
-            const uint32_t sx = xi % SX, sw = wi % SW;
+          for (int c = 0; c < nkc; ++c, ++xi) {
+            const uint32_t sx = xi % SX;
             ptx::mbar_wait(bar(B_XEMPTY + sx), ((xi / SX) & 1) ^ 1);
             const uint32_t xdst = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
             if (ph == 0) {
@@ -202,6 +202,18 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             } else {
               ptx::mbar_arrive(bar(B_XFULL + sx));   // the stage is only the staging buffer of dx2_c
             }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================== TMA producer: weights (always L2 hits) =====================================
+    if (lane == 0) {
+      uint32_t wi = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int ph = 0; ph < 3; ++ph) {
+          for (int c = 0; c < nkc; ++c, ++wi) {
+            const uint32_t sw = wi % SW;
             ptx::mbar_wait(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1);
             const uint32_t wdst = smem_base + C::OFF_W + sw * C::WSLOT;
             if (ph == 0) {

@@ -9,7 +9,8 @@
 //   epilogue 1:                      z = gelu_new(A + bd), q = gelu_new(P + gbd)    TMEM -> regs -> bf16 -> swizzled smem
 //   phase B  (per 64-column chunk):  U = z Wu_n^T, T = q Gu_n^T                     tcgen05.mma, double-buffered TMEM
 //   epilogue 2:                      out_n = x1_n + s*(kappa*x2_n + alpha*(U+bu)) (*|+) sigmoid(T+gbu)   -> smem -> TMA store
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warp 2 = TMA-store issuer, warp 3 idle,
+// Warp roles: warp 0 = TMA producer (activations), warp 3 = TMA producer (weights), warp 1 = MMA issuer (+ TMEM owner),
+// warp 2 = TMA-store issuer,
 // warps 4..11 = epilogue (two warpgroups; warp%4 selects the TMEM lane quarter).
 // Two smem rings fed by TMA: an x-ring (x1/x2 64-column chunks, used as MMA operands in phase A and as the residual
 // inputs + output staging in phase B) and a w-ring (weight chunks, always L2 hits).  Weights are padded to R rows /
@@ -62,8 +63,8 @@ constexpr int CH = 64;  // chunk width in elements: 64 bf16 = one 128-byte swizz
 constexpr int SX = 3;   // x-ring stages
 constexpr int SW = 2;   // w-ring stages
 constexpr int XCH_BYTES = TILE_M * CH * 2;  // 16 KB: one [128 x 64] bf16 chunk
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_THREADS = 256;
+constexpr int NUM_THREADS = 640;   // 4 role warps + 16 epilogue warps
+constexpr int EPI_THREADS = 512;
 constexpr int TMEM_COLS = 512;
 constexpr int TM_A = 0, TM_P = 128, TM_UT = 256;  // TMEM column offsets
 
@@ -81,6 +82,19 @@ struct Cfg {
   static constexpr int OFF_BAR = OFF_Q + ZQ_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // barriers + slack for the manual 1024-B alignment
 };
+
+// Optional phase-timestamp trace (tools/trace_k1.py): when non-null, thread 128 (epilogue warp 4, lane 0) of every CTA
+// appends %globaltimer values at the phase boundaries of its tiles: [cta][64] slots.
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define VLPET_TRACE(slot)                                                                      \
+  do {                                                                                         \
+    if (g_trace && threadIdx.x == 128 && tile == blockIdx.x && (slot) < 64) g_trace[blockIdx.x * 64 + (slot)] = gtimer(); \
+  } while (0)
 
 struct Params {
   int64_t M;
@@ -139,9 +153,9 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(B_UTFULL + i), 1); ptx::mbar_init(bar(B_UTEMPTY + i), EPI_THREADS); }
     ptx::fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_out); ptx::prefetch_tmap(&tm_wd);
-    ptx::prefetch_tmap(&tm_gd); ptx::prefetch_tmap(&tm_wu); ptx::prefetch_tmap(&tm_gu);
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_out); }
+  if (warp == 3 && lane == 0) {
+    ptx::prefetch_tmap(&tm_wd); ptx::prefetch_tmap(&tm_gd); ptx::prefetch_tmap(&tm_wu); ptx::prefetch_tmap(&tm_gu);
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
   ptx::tc_fence_before();
@@ -151,19 +165,32 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
+    // ===================================== TMA producer: activations =====================================
     if (lane == 0) {
-      uint32_t xi = 0, wi = 0;  // ring step counters
+      uint32_t xi = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = (int)(tile * TILE_M);
         for (int ph = 0; ph < 2; ++ph) {
-          for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
-            const uint32_t sx = xi % SX, sw = wi % SW;
+          for (int c = 0; c < nkc; ++c, ++xi) {
+            const uint32_t sx = xi % SX;
             ptx::mbar_wait(bar(B_XEMPTY + sx), ((xi / SX) & 1) ^ 1);
             const uint32_t xdst = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
             ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), 2 * XCH_BYTES);
             ptx::tma_load_2d(xdst, &tm_x1, c * CH, row0, bar(B_XFULL + sx));
             ptx::tma_load_2d(xdst + XCH_BYTES, &tm_x2, c * CH, row0, bar(B_XFULL + sx));
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================== TMA producer: weights (always L2 hits) =====================================
+    // its own thread, so that the weight ring runs ahead independently of the activation ring's (later) releases
+    if (lane == 0) {
+      uint32_t wi = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int ph = 0; ph < 2; ++ph) {
+          for (int c = 0; c < nkc; ++c, ++wi) {
+            const uint32_t sw = wi % SW;
             ptx::mbar_wait(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1);
             const uint32_t wdst = smem_base + C::OFF_W + sw * C::WSLOT;
             if (ph == 0) {
@@ -256,29 +283,38 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================================== epilogue warps =====================================
+    // 16 warps: warp%4 = TMEM lane quarter (hardware rule), cg = (warp-4)/4 = column group.  Four warps per scheduler
+    // keep the issue slots busy while tcgen05.ld / ld.shared / MUFU latencies are in flight (the 8-warp version spent
+    // 1.4 us of pure math per chunk at ~45 % issue utilisation, tools/trace_k1.py).
     const int quarter = warp % 4;            // TMEM lanes [32*quarter, 32*quarter+32)
-    const int half = (warp - 4) / 4;         // 0: adapter branch / left 32 columns, 1: gate branch / right 32 columns
+    const int cg = (warp - 4) / 4;           // epilogue 1: branch = cg/2 (z | q), half of its columns = cg%2; epilogue 2: 16 of 64 columns
     const int row = quarter * 32 + lane;     // row inside the 128-token tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t swz = (uint32_t)(row & 7);
     const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
     uint32_t xi = 0, ui = 0, oi = 0, ti = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
-      // ---- epilogue 1: z = gelu_new(A + bd) (half 0) / q = gelu_new(P + gbd) (half 1) -> swizzled K-major smem
+      // ---- epilogue 1: z = gelu_new(A + bd) (cg 0,1) / q = gelu_new(P + gbd) (cg 2,3) -> swizzled K-major smem
+      VLPET_TRACE(0);
       ptx::mbar_wait(bar(B_APFULL), ti & 1);
+      VLPET_TRACE(1);
       ptx::tc_fence_after();
-      if (p.gated || half == 0) {
-        const uint32_t tsrc = lane_addr + (half ? TM_P : TM_A);
-        const uint32_t dst = smem_base + (half ? C::OFF_Q : C::OFF_Z) + (uint32_t)row * 128u;
-        const __nv_bfloat16* bias = half ? p.gbd : p.bd;
-        const int rr = half ? p.rg : p.r;
+      const int branch = cg >> 1;
+      if (p.gated || branch == 0) {
+        const uint32_t tsrc = lane_addr + (branch ? TM_P : TM_A);
+        const uint32_t dst = smem_base + (branch ? C::OFF_Q : C::OFF_Z) + (uint32_t)row * 128u;
+        const __nv_bfloat16* bias = branch ? p.gbd : p.bd;
+        const int rr = branch ? p.rg : p.r;
+        constexpr int HALF = R / 2;            // columns per warp (R % 32 == 0 -> a multiple of 16)
+        const int jbeg = (cg & 1) * HALF;
 #pragma unroll
-        for (int j0 = 0; j0 < R; j0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tsrc + j0, v);
+        for (int jj = 0; jj < HALF; jj += 16) {
+          const int j0 = jbeg + jj;
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(tsrc + j0, v);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {  // 8 columns -> one 16-byte swizzled store
+          for (int g = 0; g < 2; ++g) {  // 8 columns -> one 16-byte swizzled store
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -298,32 +334,36 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       ptx::fence_proxy_async_smem();  // z/q were written by the generic proxy and are read by tcgen05.mma
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(B_ZQFULL));
+      VLPET_TRACE(2);
       xi += nkc;
-      // ---- epilogue 2, per 64-column chunk
+      // ---- epilogue 2, per 64-column chunk: this warp owns columns [cg*16, cg*16+16) of the chunk
       for (int c = 0; c < nkc; ++c, ++xi, ++ui, ++oi) {
         const uint32_t sx = xi % SX, ub = ui & 1, so = oi % SX;
         ptx::mbar_wait(bar(B_UTFULL + ub), (ui >> 1) & 1);
+        VLPET_TRACE(3 + 4 * c);
         ptx::tc_fence_after();
-        uint32_t u[32], t[32];
-        const uint32_t tU = lane_addr + TM_UT + ub * 128 + half * 32;
-        ptx::tmem_ld_32x32b_x32(tU, u);
-        if (p.gated) ptx::tmem_ld_32x32b_x32(tU + 64, t);
+        uint32_t u[16], t[16];
+        const uint32_t tU = lane_addr + TM_UT + ub * 128 + cg * 16;
+        ptx::tmem_ld_32x32b_x16(tU, u);
+        if (p.gated) ptx::tmem_ld_32x32b_x16(tU + 64, t);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_UTEMPTY + ub));  // accumulators are in registers: the MMA warp may overwrite them
+        VLPET_TRACE(4 + 4 * c);
         ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+        VLPET_TRACE(5 + 4 * c);
         const uint32_t x1row = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t x2row = x1row + XCH_BYTES;
-        const int col0 = c * CH + half * 32;  // first of this thread's 32 output columns
+        const int col0 = c * CH + cg * 16;  // first of this thread's 16 output columns
         const int64_t idx0 = ((int64_t)tile * TILE_M + row) * p.d + col0;  // flat element index (dropout stream)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint64_t hsh[2] = {0, 0};
           if (p.thr16) {
             hsh[0] = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
             hsh[1] = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
           }
-          const uint32_t off = (((uint32_t)(half * 4 + g)) ^ swz) << 4;
+          const uint32_t off = (((uint32_t)(cg * 2 + g)) ^ swz) << 4;
           uint32_t a[4], b[4], o[4];
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(x1row + off));
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(x2row + off));
@@ -354,6 +394,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         }
         ptx::fence_proxy_async_smem();  // out chunk (in the x1 slot) is read by the TMA store
         ptx::mbar_arrive(bar(B_OUTRDY + so));
+        VLPET_TRACE(6 + 4 * c);
       }
     }
   }
@@ -411,6 +452,11 @@ int launch(const VlpetK1Desc& D, const CUtensorMap* maps, const Params& p, cudaS
 }
 
 }  // namespace
+
+int set_k1_trace(unsigned long long* dev_buf) {
+  VLPET_CUDA_OK(cudaMemcpyToSymbol(g_trace, &dev_buf, sizeof(dev_buf)));
+  return 0;
+}
 
 bool fused_k1_fwd_supported(const VlpetK1Desc& D) {
   if (D.dtype != VLPET_BF16 || (D.gate != VLPET_GATE_LARGE && D.gate != VLPET_GATE_NONE)) return false;
