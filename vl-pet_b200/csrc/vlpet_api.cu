@@ -104,6 +104,9 @@ int vlpet_k1_bwd(const VlpetK1Desc* D, const void* x1, const void* x2, const voi
 __attribute__((visibility("default"))) int vlpet_debug_set_k1_trace(void* dev_buf) {
   return vlpet::set_k1_trace(static_cast<unsigned long long*>(dev_buf));
 }
+__attribute__((visibility("default"))) int vlpet_debug_set_k1_bwd_trace(void* dev_buf) {
+  return vlpet::set_k1_bwd_trace(static_cast<unsigned long long*>(dev_buf));
+}
 
 // ---- weight-gradient GEMM ------------------------------------------------------------------------------------
 int vlpet_wgrad_bf16(const VlpetWgradPair* pairs, int32_t npairs, int64_t Mtok, int32_t d, int32_t nout, void* stream) {

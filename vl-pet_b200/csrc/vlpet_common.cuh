@@ -160,6 +160,7 @@ int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void
                 int64_t Mtok, int d, int nout, int sm_count, cudaStream_t st);
 int device_sm_count();
 int set_k1_trace(unsigned long long* dev_buf);   // developer hook, tools/trace_k1.py
+int set_k1_bwd_trace(unsigned long long* dev_buf);
 // dense projection GEMM (tcgen05), vlpet_gemm_sm100.cu: C fp32 = A bf16 * W^T bf16 + bias
 bool gemm_sm100_supported(int64_t M, int N, int K, int64_t ldc);
 int gemm_sm100(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, float* C, int64_t ldc, int64_t M,

@@ -32,8 +32,8 @@ constexpr int CH = 64;
 constexpr int SX = 2;
 constexpr int SW = 2;
 constexpr int XCH_BYTES = TILE_M * CH * 2;  // 16 KB
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_THREADS = 256;
+constexpr int NUM_THREADS = 640;   // 4 role warps + 16 epilogue warps
+constexpr int EPI_THREADS = 512;
 constexpr int TM_A = 0, TM_P = 96, TM_DZ = 192, TM_DQ = 288, TM_UT = 384;  // phase 1-2 TMEM columns
 constexpr int TM_ACC = 128, ACC_STRIDE = 192;                              // phase 3: {T, DX2, DX1} x 2 buffers
 
@@ -53,10 +53,23 @@ struct BCfg {
   static constexpr int OFF_DP0 = OFF_ZQ1 + (KB == 2 ? XCH_BYTES : 0);
   static constexpr int OFF_DP1 = OFF_DP0 + XCH_BYTES;
   static constexpr int OFF_BAR = OFF_DP1 + (KB == 2 ? XCH_BYTES : 0);
-  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static constexpr int SMEM_BYTES = OFF_BAR + 1024 + 2 * R * 4 + 256 + 1024;   // barriers | fp32 bd, gbd | slack + alignment
   static_assert(R <= 96 && R % 16 == 0, "fused backward covers ranks up to 96");
   static_assert(WSLOT % 1024 == 0 && WA_BYTES % 1024 == 0, "swizzle atoms must stay 1024-byte aligned");
 };
+
+// Optional phase-timestamp trace (tools/trace_k1.py --bwd): thread 128 of every CTA stamps %globaltimer at the phase
+// boundaries of its first tile into [cta][128] slots.
+__device__ unsigned long long* g_trace_b = nullptr;
+__device__ __forceinline__ unsigned long long gtimer_b() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define VLPET_TRACE_B(slot)                                                                                               \
+  do {                                                                                                                    \
+    if (g_trace_b && threadIdx.x == 128 && tile == blockIdx.x && (slot) < 128) g_trace_b[blockIdx.x * 128 + (slot)] = gtimer_b(); \
+  } while (0)
 
 struct BParams {
   int64_t M;
@@ -114,6 +127,23 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 
 // GATED = false is the ungated form used for the decoder value parallel adapter (K2): out = x1 + alpha*(Up(gelu_new(Down x2)))
 // -> dx2 = (alpha * (dout Wu) * gelu_new'(A)) Wd, no gate branch, no U/T recompute, no du/dt scratch (du = alpha*dout).
+// Same over 16 columns: every lane enters with its row's 16 values; lanes l and l^16 end up with sum_rows column (l & 15).
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? v[i] : v[i + off];
+      const float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 template <int R, bool GATED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
@@ -400,15 +430,31 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================================== epilogue warps =====================================
+    // 16 warps: warp%4 = TMEM lane quarter, cg = (warp-4)/4.  Epilogues 1 / 3: branch = cg/2 (adapter | gate), column half =
+    // cg%2; epilogues 2 / 4: columns [cg*16, cg*16+16) of the 64-column chunk.
     const int quarter = warp % 4;
-    const int half = (warp - 4) / 4;
+    const int cg = (warp - 4) / 4;
+    const int branch = cg >> 1;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t swz = (uint32_t)(row & 7);
     const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
-    float bias_acc[R / 32 > 0 ? R / 32 : 1];
-#pragma unroll
-    for (int i = 0; i < R / 32; ++i) bias_acc[i] = 0.f;
+    constexpr int HALF = R / 2;                // columns per warp in epilogues 1 / 3 (a multiple of 16)
+    const int jbeg = (cg & 1) * HALF;
+    // fp32 copies of the down-projection biases in shared memory (broadcast reads instead of scalar global loads)
+    const uint32_t sb_base = bar_base + 1024;   // [2][R] floats behind the barrier block
+    for (int i = threadIdx.x - 128; i < 2 * R; i += EPI_THREADS) {
+      const int br = i / R, j = i % R;
+      const int rr = br ? p.rg : p.r;
+      const __nv_bfloat16* src = br ? p.gbd : p.bd;
+      const float v = (j < rr && (GATED || br == 0)) ? __bfloat162float(src[j]) : 0.f;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_base + 4u * (uint32_t)i), "f"(v) : "memory");
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // epilogue warps only
+    auto sbias4 = [&](int br, int j, float (&o)[4]) {
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+                   : "r"(sb_base + 4u * (uint32_t)(br * R + j)));
+    };
     // smem address of the 16-byte group holding columns [k, k+8) of this thread's row in z/da (which=0), q (1), dp (2)
     auto small_addr = [&](int which, int k) -> uint32_t {
       if (k < 64) {
@@ -424,37 +470,40 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       const int64_t grow = tile * TILE_M + row;
       const bool row_ok = grow < p.M;
       // ---- epilogue 1 (APFULL also implies that every MMA of the previous tile, which read z/q/da/dp, has completed)
+      VLPET_TRACE_B(0);
       ptx::mbar_wait(bar(B_APFULL), ti & 1);
+      VLPET_TRACE_B(1);
       ptx::tc_fence_after();
-      if (GATED || half == 0) {
-        const uint32_t tsrc = lane_addr + (half ? TM_P : TM_A);
-        const __nv_bfloat16* bias = half ? p.gbd : p.bd;
-        const int rr = half ? p.rg : p.r;
-        __nv_bfloat16* srow = (half ? p.qs + grow * p.pq : p.zs + grow * p.pz);
+      if (GATED || branch == 0) {
+        const uint32_t tsrc = lane_addr + (branch ? TM_P : TM_A);
+        const int rr = branch ? p.rg : p.r;
+        __nv_bfloat16* srow = (branch ? p.qs + grow * p.pq : p.zs + grow * p.pz);
 #pragma unroll
-        for (int j0 = 0; j0 < R; j0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tsrc + j0, v);
+        for (int jj = 0; jj < HALF; jj += 16) {
+          const int j0 = jbeg + jj;
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(tsrc + j0, v);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 2; ++g) {
+            float b0[4], b1[4];
+            sbias4(branch, j0 + g * 8, b0);
+            sbias4(branch, j0 + g * 8 + 4, b1);
+            const float bb[8] = {b0[0], b0[1], b0[2], b0[3], b1[0], b1[1], b1[2], b1[3]};
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int j = j0 + g * 8 + e * 2;
-              const float b0 = (j < rr) ? __bfloat162float(bias[j]) : 0.f;
-              const float b1 = (j + 1 < rr) ? __bfloat162float(bias[j + 1]) : 0.f;
               float z0, z1, d0, d1;
-              gelu_new_both(__uint_as_float(v[g * 8 + e * 2]) + b0, z0, d0);
-              gelu_new_both(__uint_as_float(v[g * 8 + e * 2 + 1]) + b1, z1, d1);
+              gelu_new_both(__uint_as_float(v[g * 8 + e * 2]) + bb[e * 2], z0, d0);
+              gelu_new_both(__uint_as_float(v[g * 8 + e * 2 + 1]) + bb[e * 2 + 1], z1, d1);
               o[e] = pack_bf16(z0, z1);
             }
             const int k = j0 + g * 8;
-            sts128(small_addr(half, k), o);
+            sts128(small_addr(branch, k), o);
             if (row_ok && k < rr) *reinterpret_cast<uint4*>(srow + k) = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
-        if (row_ok) {  // ones column (bias-gradient trick of the weight-gradient GEMM) + zero pad up to the pitch
+        if (row_ok && (cg & 1) == 1) {  // ones column (bias-gradient trick of the weight-gradient GEMM) + zero pad up to the pitch
           const uint4 one = make_uint4(0x00003F80u, 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(srow + rr) = one;
         }
@@ -462,32 +511,35 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(B_ZQFULL));
+      VLPET_TRACE_B(2);
       xi += nkc;
       // ---- epilogue 2, per 64-column chunk: du, dt
       if (!GATED) xi += nkc;
       for (int c = 0; GATED && c < nkc; ++c, ++xi, ++ui, ++p2i) {
         const uint32_t sx = xi % SX;
         ptx::mbar_wait(bar(B_UTFULL), ui & 1);
+        VLPET_TRACE_B(3 + 3 * c);
         ptx::tc_fence_after();
-        uint32_t u[32], t[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + TM_UT + half * 32, u);
-        ptx::tmem_ld_32x32b_x32(lane_addr + TM_UT + CH + half * 32, t);
+        uint32_t u[16], t[16];
+        ptx::tmem_ld_32x32b_x16(lane_addr + TM_UT + cg * 16, u);
+        ptx::tmem_ld_32x32b_x16(lane_addr + TM_UT + CH + cg * 16, t);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_UTEMPTY));
         ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+        VLPET_TRACE_B(4 + 3 * c);
         const uint32_t x2row = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t dorow = x2row + XCH_BYTES;
-        const int col0 = c * CH + half * 32;
+        const int col0 = c * CH + cg * 16;
         const int64_t idx0 = grow * p.d + col0;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint64_t hsh[2] = {0, 0};
           if (p.thr16) {
             hsh[0] = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
             hsh[1] = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
           }
-          const uint32_t off = (((uint32_t)(half * 4 + g)) ^ swz) << 4;
+          const uint32_t off = (((uint32_t)(cg * 2 + g)) ^ swz) << 4;
           uint32_t xv[4], dv[4], ou[4], ot[4];
           lds128(x2row + off, xv);
           lds128(dorow + off, dv);
@@ -531,72 +583,81 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(bar(B_DUDT + (p2i % SX)));
+        VLPET_TRACE_B(5 + 3 * c);
       }
-      // ---- epilogue 3: da = dz * gelu_new'(A + bd) (half 0), dp = dq * gelu_new'(P + gbd) (half 1)
+      // ---- epilogue 3: da = dz * gelu_new'(A + bd) (branch 0), dp = dq * gelu_new'(P + gbd) (branch 1)
+      VLPET_TRACE_B(40);
       ptx::mbar_wait(bar(B_DZFULL), ti & 1);
+      VLPET_TRACE_B(41);
       ptx::tc_fence_after();
-      if (GATED || half == 0) {
+      if (GATED || branch == 0) {
         const float dzscale = GATED ? 1.0f : p.alpha;   // ungated: du = alpha*dout was fed unscaled
-        const uint32_t tpre = lane_addr + (half ? TM_P : TM_A);
-        const uint32_t tdz = lane_addr + (half ? TM_DQ : TM_DZ);
-        const __nv_bfloat16* bias = half ? p.gbd : p.bd;
-        const int rr = half ? p.rg : p.r;
-        __nv_bfloat16* srow = (half ? p.dps + grow * p.pq : p.das + grow * p.pz);
+        const uint32_t tpre = lane_addr + (branch ? TM_P : TM_A);
+        const uint32_t tdz = lane_addr + (branch ? TM_DQ : TM_DZ);
+        const int rr = branch ? p.rg : p.r;
+        __nv_bfloat16* srow = (branch ? p.dps + grow * p.pq : p.das + grow * p.pz);
 #pragma unroll
-        for (int j0 = 0; j0 < R; j0 += 32) {
-          uint32_t a[32], dz[32];
-          ptx::tmem_ld_32x32b_x32(tpre + j0, a);
-          ptx::tmem_ld_32x32b_x32(tdz + j0, dz);
+        for (int jj = 0; jj < HALF; jj += 16) {
+          const int j0 = jbeg + jj;
+          uint32_t a[16], dz[16];
+          ptx::tmem_ld_32x32b_x16(tpre + j0, a);
+          ptx::tmem_ld_32x32b_x16(tdz + j0, dz);
           ptx::tmem_ld_wait();
-          float da[32];
+          float da[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float b = (j0 + j < rr) ? __bfloat162float(bias[j0 + j]) : 0.f;
-            float gz, dg;
-            gelu_new_both(__uint_as_float(a[j]) + b, gz, dg);
-            da[j] = dzscale * __uint_as_float(dz[j]) * dg;
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float bb[4];
+            sbias4(branch, j0 + q4 * 4, bb);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float gz, dg;
+              gelu_new_both(__uint_as_float(a[q4 * 4 + e]) + bb[e], gz, dg);
+              da[q4 * 4 + e] = dzscale * __uint_as_float(dz[q4 * 4 + e]) * dg;
+            }
           }
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 2; ++g) {
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = pack_bf16(da[g * 8 + e * 2], da[g * 8 + e * 2 + 1]);
             const int k = j0 + g * 8;
-            sts128(small_addr(half ? 2 : 0, k), o);
+            sts128(small_addr(branch ? 2 : 0, k), o);
             if (row_ok && k < rr) *reinterpret_cast<uint4*>(srow + k) = make_uint4(o[0], o[1], o[2], o[3]);
           }
-          bias_acc[j0 / 32] += warp_colsum32(da, lane);
         }
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(B_DAPFULL));
+      VLPET_TRACE_B(42);
       // ---- epilogue 4, per 64-column chunk: dx1, dx2
       for (int c = 0; c < nkc; ++c, ++xi, ++ai) {
         const uint32_t sx = xi % SX, b = ai & 1;
         ptx::mbar_wait(bar(B_ACCFULL + b), (ai >> 1) & 1);
+        VLPET_TRACE_B(43 + 3 * c);
         ptx::tc_fence_after();
-        const uint32_t tacc = lane_addr + TM_ACC + b * ACC_STRIDE + half * 32;
-        uint32_t t[32], g2[32], g1[32];
-        if (GATED && mulgate) ptx::tmem_ld_32x32b_x32(tacc, t);
-        ptx::tmem_ld_32x32b_x32(tacc + CH, g2);
-        if (GATED) ptx::tmem_ld_32x32b_x32(tacc + 2 * CH, g1);
+        const uint32_t tacc = lane_addr + TM_ACC + b * ACC_STRIDE + cg * 16;
+        uint32_t t[16], g2[16], g1[16];
+        if (GATED && mulgate) ptx::tmem_ld_32x32b_x16(tacc, t);
+        ptx::tmem_ld_32x32b_x16(tacc + CH, g2);
+        if (GATED) ptx::tmem_ld_32x32b_x16(tacc + 2 * CH, g1);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_ACCEMPTY + b));
         ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+        VLPET_TRACE_B(44 + 3 * c);
         const uint32_t dorow = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t o2row = dorow + XCH_BYTES;
-        const int col0 = c * CH + half * 32;
+        const int col0 = c * CH + cg * 16;
         const int64_t idx0 = grow * p.d + col0;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint64_t hsh[2] = {0, 0};
           if (p.thr16) {
             hsh[0] = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
             hsh[1] = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
           }
-          const uint32_t off = (((uint32_t)(half * 4 + g)) ^ swz) << 4;
+          const uint32_t off = (((uint32_t)(cg * 2 + g)) ^ swz) << 4;
           uint32_t dv[4] = {0, 0, 0, 0}, o1[4], o2[4];
           if (GATED) lds128(dorow + off, dv);
           uint32_t gbw[4] = {0, 0, 0, 0};
@@ -634,15 +695,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(bar(B_OUTRDY + (ai % SX)));
+        VLPET_TRACE_B(45 + 3 * c);
       }
-    }
-    // ---- bias gradients of the two down projections: one atomic per warp and column
-    float* dst = half ? p.dgbd : p.dbd;
-    const int rr = half ? p.rg : p.r;
-    if (dst) {
-#pragma unroll
-      for (int i = 0; i < R / 32; ++i)
-        if (i * 32 + lane < rr) atomicAdd(dst + i * 32 + lane, bias_acc[i]);
     }
   }
 
@@ -652,6 +706,29 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
+}
+
+// dbd / dgbd = column sums of the da / dp scratch ([M, pitch] bf16, first ncols columns).  Kept out of the tile kernel: a
+// warp-shuffle transpose-reduce there cost ~5 us per tile on its critical path (tools/trace_k1_bwd.py).
+__global__ void __launch_bounds__(128) colsum_scratch_kernel(const __nv_bfloat16* __restrict__ A, int pitch, int ncols,
+                                                             int64_t M, int rows_per_block, float* __restrict__ out) {
+  const int c = threadIdx.x;
+  if (c >= ncols) return;
+  const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float acc = 0.f;
+  for (int64_t m = m0; m < m1; ++m) acc += __bfloat162float(A[m * pitch + c]);
+  atomicAdd(out + c, acc);
+}
+int launch_colsum_scratch(const __nv_bfloat16* A, int pitch, int ncols, int64_t M, float* out, cudaStream_t st) {
+  if (!out) return 0;
+  int64_t rpb = (M + 295) / 296;
+  if (rpb < 32) rpb = 32;
+  const int64_t blocks = (M + rpb - 1) / rpb;
+  colsum_scratch_kernel<<<(unsigned)blocks, 128, 0, st>>>(A, pitch, ncols, M, (int)rpb, out);
+  VLPET_LAUNCH_OK();
+  return 0;
 }
 
 struct Scratch {
@@ -747,6 +824,8 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
     }
   }
   if (rc) return rc;
+  VLPET_TRY(launch_colsum_scratch(s.das, s.pz, D.r, D.M, G.dbd, st));
+  if (gated) VLPET_TRY(launch_colsum_scratch(s.dps, s.pq, rg, D.M, G.dgbd, st));
   // ---- weight gradients: dWu = du^T z (+dbu), dGu = dt^T q (+dgbu), dWd = (x2^T da)^T, dGd = (x1^T dp)^T
   //      (ungated: du = alpha*dout, so A = dout with scale alpha)
   const void* A[4]; const void* B[4]; int64_t lda[4], ldb[4]; int nbv[4], tr[4]; float* out[4]; float* bias[4]; float sc[4];
@@ -784,6 +863,11 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
 }
 
 }  // namespace
+
+int set_k1_bwd_trace(unsigned long long* dev_buf) {
+  VLPET_CUDA_OK(cudaMemcpyToSymbol(g_trace_b, &dev_buf, sizeof(dev_buf)));
+  return 0;
+}
 
 bool fused_k1_bwd_supported(const VlpetK1Desc& D) {
   if (D.dtype != VLPET_BF16 || D.gate != VLPET_GATE_LARGE) return false;
