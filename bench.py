@@ -269,12 +269,20 @@ def run_ours(a):
     h2d = sum(H.batch_nbytes(host_cycle[i % nb]) for i in range(a.steps)) / a.steps
     losses = []
 
-    def step_e2e(i):
-        losses.append(float(trainer.train_step(host_cycle[i % nb]).item()))
+    # the copy of step i+1 is issued (copy stream) before step i runs; every step's H2D copy and loss read-back lie
+    # inside the timed region
+    pending = {}
 
-    for i in range(min(2, a.warmup)):
+    def step_e2e(i):
+        cur = pending.pop(i, None) or trainer.prefetch(host_cycle[i % nb])
+        pending[i + 1] = trainer.prefetch(host_cycle[(i + 1) % nb])
+        losses.append(float(trainer.train_step(cur).item()))
+
+    for i in range(max(nb, min(a.warmup, 2 * nb))):      # every task signature once: staging buffers exist before timing
         step_e2e(i)
+    pending.clear()
     ms_e2e = timed(step_e2e, a.steps)
+    pending.clear()
     clk = clocks.stop() if rank == 0 else None
     e2e_value = samples / (ms_e2e * 1e-3)
 

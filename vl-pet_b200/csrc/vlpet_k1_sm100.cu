@@ -93,13 +93,15 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #define VLPET_TRACE(slot)                                                                      \
   do {                                                                                         \
-    if (g_trace && threadIdx.x == 128 && tile == blockIdx.x && (slot) < 64) g_trace[blockIdx.x * 64 + (slot)] = gtimer(); \
+    if (g_trace && threadIdx.x == 128 && w == blockIdx.x && (slot) < 64) g_trace[blockIdx.x * 64 + (slot)] = gtimer(); \
   } while (0)
 
 struct Params {
   int64_t M;
   int d, r, rg;
   int add_gate;
+  int nsplit;         // > 1 (small M): every tile is handled by nsplit CTAs, each redoing phase A and owning nkc/nsplit
+                      // of the phase-B column chunks -- trades redundant L2 reads for a shorter critical path
   int gated;          // 0: no gate (h = y1; the K2 value-parallel-adapter form), 1: large gate
   float s, alpha, kappa;
   const __nv_bfloat16 *bd, *bu, *gbd, *gbu;
@@ -144,6 +146,12 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   const int lane = threadIdx.x % 32;
   const int nkc = p.d / CH;  // chunks along d (phase A: K chunks; phase B: N chunks)
   const int64_t num_tiles = (p.M + TILE_M - 1) / TILE_M;
+  const int64_t num_items = num_tiles * p.nsplit;
+  const int cps = nkc / p.nsplit;   // phase-B chunks per work item (nsplit divides nkc)
+#define WORK_ITEM()                                  \
+  const int64_t tile = w / p.nsplit;                 \
+  const int cb = (int)(w % p.nsplit) * cps, ce = cb + cps; \
+  (void)tile; (void)cb; (void)ce
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SX; ++i) { ptx::mbar_init(bar(B_XFULL + i), 1); ptx::mbar_init(bar(B_XEMPTY + i), 1); ptx::mbar_init(bar(B_OUTRDY + i), EPI_THREADS); }
@@ -168,10 +176,11 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     // ===================================== TMA producer: activations =====================================
     if (lane == 0) {
       uint32_t xi = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x) {
+        WORK_ITEM();
         const int row0 = (int)(tile * TILE_M);
         for (int ph = 0; ph < 2; ++ph) {
-          for (int c = 0; c < nkc; ++c, ++xi) {
+          for (int c = (ph ? cb : 0); c < (ph ? ce : nkc); ++c, ++xi) {
             const uint32_t sx = xi % SX;
             ptx::mbar_wait(bar(B_XEMPTY + sx), ((xi / SX) & 1) ^ 1);
             const uint32_t xdst = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
@@ -187,9 +196,10 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     // its own thread, so that the weight ring runs ahead independently of the activation ring's (later) releases
     if (lane == 0) {
       uint32_t wi = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x) {
+        WORK_ITEM();
         for (int ph = 0; ph < 2; ++ph) {
-          for (int c = 0; c < nkc; ++c, ++wi) {
+          for (int c = (ph ? cb : 0); c < (ph ? ce : nkc); ++c, ++wi) {
             const uint32_t sw = wi % SW;
             ptx::mbar_wait(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1);
             const uint32_t wdst = smem_base + C::OFF_W + sw * C::WSLOT;
@@ -217,7 +227,8 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       constexpr uint32_t IDESC_B = ptx::umma_idesc_bf16_m128(CH);
       uint32_t xi = 0, wi = 0, ui = 0, ti = 0;
       const uint32_t z_base = smem_base + C::OFF_Z, q_base = smem_base + C::OFF_Q;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x, ++ti) {
+        WORK_ITEM();
         // ---- phase A: A += x2_c Wd_c^T ; P += x1_c Gd_c^T
         for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
           const uint32_t sx = xi % SX, sw = wi % SW;
@@ -242,7 +253,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         // ---- phase B: U_n = z Wu_n^T ; T_n = q Gu_n^T
         ptx::mbar_wait(bar(B_ZQFULL), ti & 1);
         ptx::tc_fence_after();
-        for (int c = 0; c < nkc; ++c, ++xi, ++wi, ++ui) {
+        for (int c = cb; c < ce; ++c, ++xi, ++wi, ++ui) {
           const uint32_t sw = wi % SW, ub = ui & 1;
           ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
           ptx::mbar_wait(bar(B_UTEMPTY + ub), ((ui >> 1) & 1) ^ 1);
@@ -267,10 +278,11 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     // ===================================== TMA store issuer =====================================
     if (lane == 0) {
       uint32_t xi = 0, oi = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x) {
+        WORK_ITEM();
         const int row0 = (int)(tile * TILE_M);
         xi += nkc;  // phase A steps of the x-ring are consumed by the MMA warp
-        for (int c = 0; c < nkc; ++c, ++xi, ++oi) {
+        for (int c = cb; c < ce; ++c, ++xi, ++oi) {
           const uint32_t sx = xi % SX, so = oi % SX;
           ptx::mbar_wait(bar(B_OUTRDY + so), (oi / SX) & 1);
           ptx::tma_store_2d(&tm_out, smem_base + C::OFF_X + sx * (2 * XCH_BYTES), c * CH, row0);
@@ -293,7 +305,8 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     const uint32_t swz = (uint32_t)(row & 7);
     const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
     uint32_t xi = 0, ui = 0, oi = 0, ti = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+    for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x, ++ti) {
+        WORK_ITEM();
       // ---- epilogue 1: z = gelu_new(A + bd) (cg 0,1) / q = gelu_new(P + gbd) (cg 2,3) -> swizzled K-major smem
       VLPET_TRACE(0);
       ptx::mbar_wait(bar(B_APFULL), ti & 1);
@@ -337,10 +350,10 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       VLPET_TRACE(2);
       xi += nkc;
       // ---- epilogue 2, per 64-column chunk: this warp owns columns [cg*16, cg*16+16) of the chunk
-      for (int c = 0; c < nkc; ++c, ++xi, ++ui, ++oi) {
+      for (int c = cb; c < ce; ++c, ++xi, ++ui, ++oi) {
         const uint32_t sx = xi % SX, ub = ui & 1, so = oi % SX;
         ptx::mbar_wait(bar(B_UTFULL + ub), (ui >> 1) & 1);
-        VLPET_TRACE(3 + 4 * c);
+        VLPET_TRACE(3 + 4 * (c - cb));
         ptx::tc_fence_after();
         uint32_t u[16], t[16];
         const uint32_t tU = lane_addr + TM_UT + ub * 128 + cg * 16;
@@ -349,9 +362,9 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_UTEMPTY + ub));  // accumulators are in registers: the MMA warp may overwrite them
-        VLPET_TRACE(4 + 4 * c);
+        VLPET_TRACE(4 + 4 * (c - cb));
         ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
-        VLPET_TRACE(5 + 4 * c);
+        VLPET_TRACE(5 + 4 * (c - cb));
         const uint32_t x1row = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t x2row = x1row + XCH_BYTES;
         const int col0 = c * CH + cg * 16;  // first of this thread's 16 output columns
@@ -394,7 +407,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         }
         ptx::fence_proxy_async_smem();  // out chunk (in the x1 slot) is read by the TMA store
         ptx::mbar_arrive(bar(B_OUTRDY + so));
-        VLPET_TRACE(6 + 4 * c);
+        VLPET_TRACE(6 + 4 * (c - cb));
       }
     }
   }
@@ -443,8 +456,9 @@ int launch(const VlpetK1Desc& D, const CUtensorMap* maps, const Params& p, cudaS
     VLPET_CUDA_OK(cudaFuncSetAttribute(k1_fwd_sm100_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
-  int grid = (int)(tiles < dev_info().sms ? tiles : dev_info().sms);
+  const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
+  const int64_t items = tiles * p.nsplit;
+  int grid = (int)(items < dev_info().sms ? items : dev_info().sms);
   k1_fwd_sm100_kernel<R><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
                                                                   maps[6], p);
   VLPET_LAUNCH_OK();
@@ -492,6 +506,13 @@ int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const Vlp
   p.gbd = static_cast<const __nv_bfloat16*>(gated ? w.gbd : w.bd); p.gbu = static_cast<const __nv_bfloat16*>(gated ? w.gbu : w.bu);
   p.seed = D.seed;
   p.seed_dev = D.seed_dev;
+  {  // small M: split every tile's phase-B columns over several CTAs (largest divisor of nkc that still fits one wave)
+    const int nkc = D.d / CH;
+    const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
+    p.nsplit = 1;
+    for (int ns = 2; ns <= nkc; ++ns)
+      if (nkc % ns == 0 && tiles * ns <= dev_info().sms) p.nsplit = ns;
+  }
   p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
   p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
   switch (R) {

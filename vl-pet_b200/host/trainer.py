@@ -122,6 +122,17 @@ def linear_warmup_lr(step: int, total_steps: int, warmup_ratio: float, base_lr: 
     return base_lr * max(0.0, (total_steps - step) / max(1, total_steps - warm))
 
 
+class Prefetched:
+    """A host batch whose host->device copy was issued ahead of time on the copy stream (PetTrainer.prefetch)."""
+
+    def __init__(self, batch, ready, key):
+        self.batch, self.ready, self.key = batch, ready, key
+
+
+def batch_signature(batch: Dict):
+    return tuple((k, tuple(v.shape), str(v.dtype)) if torch.is_tensor(v) else (k, v) for k, v in sorted(batch.items()))
+
+
 class PetTrainer:
     """Owns the bucket, the fused optimizer and the gradient exchange for one rank."""
 
@@ -153,6 +164,43 @@ class PetTrainer:
         if self.world > 1:                                        # identical start on every rank
             dist.broadcast(self.bucket.flat_param, src=0, group=self.pg)
             self.bucket.refresh_shadow()
+        self._staging, self._staging_free, self._pf_count = {}, {}, 0
+        self._copy_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+
+    # -- input pipeline: the host->device copy of step i+1 overlaps the compute of step i
+    def prefetch(self, batch: Dict) -> "Prefetched":
+        """Issue the H2D copy of a (pinned) host batch on the copy stream into one of two device staging sets and return
+        a handle for train_step.  Call it for step i+1 before train_step(i)."""
+        sig = batch_signature(batch)
+        key = (sig, self._pf_count % 2)
+        self._pf_count += 1
+        if key not in self._staging:                            # both ping-pong sets at once: no allocation in steady state
+            for slot in (0, 1):
+                self._staging[(sig, slot)] = {k: (torch.empty(v.shape, dtype=v.dtype, device=self.device) if torch.is_tensor(v) else v)
+                                              for k, v in batch.items()}
+        bufs = self._staging[key]
+        with torch.cuda.stream(self._copy_stream):
+            free = self._staging_free.get(key)
+            if free is not None:
+                self._copy_stream.wait_event(free)              # the step that last used this set has finished with it
+            for k, v in batch.items():
+                if torch.is_tensor(v):
+                    bufs[k].copy_(v, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        return Prefetched(bufs, ready, key)
+
+    def _consume(self, x):
+        if isinstance(x, Prefetched):
+            torch.cuda.current_stream().wait_event(x.ready)
+            return x.batch, x.key
+        return x, None
+
+    def _release(self, key):
+        if key is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._staging_free[key] = ev
 
     def set_step(self, n: int):
         self.step_idx = int(n)
@@ -189,10 +237,12 @@ class PetTrainer:
                                        C.c_void_p(b.shadow.data_ptr()) if b.shadow is not None else C.c_void_p(0), st),
                 "vlpet_adamw_step")
 
-    def train_step(self, batch: Dict) -> torch.Tensor:
+    def train_step(self, batch) -> torch.Tensor:
+        batch, key = self._consume(batch)
         loss = self.forward_backward(batch)
         self.exchange()
         self.optimizer_step()
+        self._release(key)
         return loss
 
 
@@ -222,9 +272,7 @@ class GraphedPetTrainer(PetTrainer):
         self.step_idx = int(n)
         self._t.fill_(float(n))
 
-    @staticmethod
-    def _signature(batch: Dict):
-        return tuple((k, tuple(v.shape), str(v.dtype)) if torch.is_tensor(v) else (k, v) for k, v in sorted(batch.items()))
+    _signature = staticmethod(batch_signature)
 
     def _capture_fb(self, batch: Dict):
         static = {k: (torch.empty(v.shape, dtype=v.dtype, device=self.device) if torch.is_tensor(v) else v)
@@ -280,7 +328,8 @@ class GraphedPetTrainer(PetTrainer):
             self._optimizer_ops()
         return g
 
-    def train_step(self, batch: Dict) -> torch.Tensor:
+    def train_step(self, batch) -> torch.Tensor:
+        batch, key = self._consume(batch)
         sig = self._signature(batch)
         ent = self._fb.get(sig)
         if ent is None:
@@ -290,6 +339,7 @@ class GraphedPetTrainer(PetTrainer):
         for k, v in batch.items():
             if torch.is_tensor(v) and v.data_ptr() != static[k].data_ptr():
                 static[k].copy_(v, non_blocking=True)
+        self._release(key)                    # the staging set is free again once the copies into the static inputs ran
         g.replay()
         # `loss` lives in the pool the graphs share: later replays (the optimizer graph's temporaries) may reuse its
         # storage, so the value is copied out to an ordinary tensor right behind the replay
