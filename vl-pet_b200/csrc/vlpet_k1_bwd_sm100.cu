@@ -481,7 +481,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
 #pragma unroll
         for (int jj = 0; jj < HALF; jj += 16) {
           const int j0 = jbeg + jj;
-          uint32_t v[16];
+          uint32_t v[16], dgv[16];
           ptx::tmem_ld_32x32b_x16(tsrc + j0, v);
           ptx::tmem_ld_wait();
 #pragma unroll
@@ -497,12 +497,16 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
               gelu_new_both(__uint_as_float(v[g * 8 + e * 2]) + bb[e * 2], z0, d0);
               gelu_new_both(__uint_as_float(v[g * 8 + e * 2 + 1]) + bb[e * 2 + 1], z1, d1);
               o[e] = pack_bf16(z0, z1);
+              dgv[g * 8 + e * 2] = __float_as_uint(d0);
+              dgv[g * 8 + e * 2 + 1] = __float_as_uint(d1);
             }
             const int k = j0 + g * 8;
             sts128(small_addr(branch, k), o);
             if (row_ok && k < rr) *reinterpret_cast<uint4*>(srow + k) = make_uint4(o[0], o[1], o[2], o[3]);
           }
+          ptx::tmem_st_32x32b_x16(tsrc + j0, dgv);   // gelu_new'(pre-activation) replaces the pre-activation in TMEM: epilogue 3 only multiplies
         }
+        ptx::tmem_st_wait();
         if (row_ok && (cg & 1) == 1) {  // ones column (bias-gradient trick of the weight-gradient GEMM) + zero pad up to the pitch
           const uint4 one = make_uint4(0x00003F80u, 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(srow + rr) = one;
@@ -600,21 +604,12 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         for (int jj = 0; jj < HALF; jj += 16) {
           const int j0 = jbeg + jj;
           uint32_t a[16], dz[16];
-          ptx::tmem_ld_32x32b_x16(tpre + j0, a);
+          ptx::tmem_ld_32x32b_x16(tpre + j0, a);     // gelu_new'(A + bd), stored by epilogue 1
           ptx::tmem_ld_32x32b_x16(tdz + j0, dz);
           ptx::tmem_ld_wait();
           float da[16];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            float bb[4];
-            sbias4(branch, j0 + q4 * 4, bb);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float gz, dg;
-              gelu_new_both(__uint_as_float(a[q4 * 4 + e]) + bb[e], gz, dg);
-              da[q4 * 4 + e] = dzscale * __uint_as_float(dz[q4 * 4 + e]) * dg;
-            }
-          }
+          for (int e = 0; e < 16; ++e) da[e] = dzscale * __uint_as_float(dz[e]) * __uint_as_float(a[e]);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             uint32_t o[4];

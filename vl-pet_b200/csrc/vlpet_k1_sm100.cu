@@ -15,6 +15,8 @@
 // Two smem rings fed by TMA: an x-ring (x1/x2 64-column chunks, used as MMA operands in phase A and as the residual
 // inputs + output staging in phase B) and a w-ring (weight chunks, always L2 hits).  Weights are padded to R rows /
 // columns by TMA out-of-bounds zero fill, so any r, rg <= R that is a multiple of 8 runs on the same instantiation.
+#include <mutex>
+
 #include "sm100_ptx.cuh"
 #include "vlpet_common.cuh"
 
@@ -38,8 +40,45 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 row-major tensor [rows, cols] with a row pitch of `pitch_elems` elements; box = [box_rows x box_cols],
 // 128-byte swizzle (box_cols * 2 bytes must be <= 128), out-of-bounds elements read as zero / are not written.
+// Descriptor cache: encoding a tensor map costs ~1 us on the host and a backward call needs 19 of them; the same
+// (pointer, shape) tuples recur every step (weights always, activations whenever the allocator reuses addresses).
+struct MapKey {
+  const void* base;
+  uint64_t rows, cols, pitch;
+  uint32_t box_rows, box_cols, weight;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && pitch == o.pitch && box_rows == o.box_rows &&
+           box_cols == o.box_cols && weight == o.weight;
+  }
+};
+struct MapSlot { MapKey key; CUtensorMap map; bool valid; };
+static MapSlot g_map_cache[256];
+static std::mutex g_map_mutex;
+
+static int encode_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                           uint32_t box_rows, uint32_t box_cols, bool weight);
+
 int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows,
                   uint32_t box_cols, bool weight) {
+  const MapKey k{base, rows, cols, pitch_elems, box_rows, box_cols, weight ? 1u : 0u};
+  uint64_t h = reinterpret_cast<uint64_t>(base) * 0x9E3779B97F4A7C15ull ^ (rows * 1315423911ull) ^ (cols << 20) ^ (box_rows << 8) ^ box_cols;
+  h ^= h >> 29;
+  MapSlot& slot = g_map_cache[h & 255];
+  {
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    if (slot.valid && slot.key == k) {
+      *m = slot.map;
+      return 0;
+    }
+  }
+  VLPET_TRY(encode_map_bf16(m, base, rows, cols, pitch_elems, box_rows, box_cols, weight));
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  slot.key = k; slot.map = *m; slot.valid = true;
+  return 0;
+}
+
+static int encode_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                           uint32_t box_rows, uint32_t box_cols, bool weight) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(VLPET_E_NODEVICE, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
