@@ -259,9 +259,9 @@ def run_ours(a):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    n0 = V.launch_count()
+    n0 = trainer.launch_counter()
     ms = timed(step_resident, a.steps)
-    launches = V.launch_count() - n0
+    launches = trainer.launch_counter() - n0
     samples = sum(global_sizes[TASKS[i % nb]] for i in range(a.steps))
     value = samples / (ms * 1e-3)
 

@@ -183,6 +183,16 @@ VLPET_API int vlpet_k3_bwd(const VlpetK3Desc* desc, const void* feats, const voi
                  const void* dout, const VlpetK3Params* w, const float* save, void* dfeats /* may be NULL */,
                  const VlpetK3Grads* g, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- CLIP-grid downsample feeding K3 --------------------------------------------------------------------
+ * Replaces Downsample.downsample_inputs (src/modeling_bart.py:566-583: permute -> [B, F, g, g] -> AdaptiveMaxPool2d((o, o))
+ * -> permute back) for the pre-extracted grid features of the VL-PET scripts (--n_boxes 36 --downsample: 7x7 -> 6x6),
+ * fused with the cast to the compute dtype: in [nimg, g*g, F] (fp32 or bf16) -> out [nimg, o*o, F] (fp32 or bf16).
+ * Max-pooling commutes with the (monotonic) bf16 rounding, so the result equals pooling in fp32 and casting after.
+ * Window of output cell i along one axis: [floor(i*g/o), ceil((i+1)*g/o)) -- PyTorch's adaptive pooling rule.
+ * F must be a multiple of 8.  Features are inputs: there is no backward.                                    */
+VLPET_API int vlpet_grid_maxpool(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t nimg, int32_t g,
+                       int32_t o, int32_t F, void* stream);
+
 /* ---- token-contracted weight-gradient GEMM (building block of the fused backward) -----------------------
  * out_p[c, n] += scale_p * sum_tok A_p[tok, c] * B_p[tok, n]   (transposed_p: out_p[n, c] instead), up to 4 pairs per
  * launch, bf16 operands, fp32 accumulate on the tensor cores (tcgen05), fp32 reductions into out.  These are the dW

@@ -483,3 +483,16 @@ def test_abi_errors_are_loud(V):
     V.gated_pet(x, x, [torch.zeros(8, 64, device="cuda")], [torch.zeros(8, device="cuda")],
                 torch.zeros(64, 8, device="cuda"), torch.zeros(64, device="cuda"), [], V.PetSiteConfig(gate="none"))
     assert V.launch_count() > n0
+
+
+@pytest.mark.parametrize("dt_in,dt_out", [(torch.float32, torch.bfloat16), (torch.float32, torch.float32),
+                                          (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("g,o", [(7, 6), (8, 8), (7, 3)])
+def test_grid_maxpool_matches_adaptive_max_pool(V, g, o, dt_in, dt_out):
+    """vlpet_grid_maxpool == the reference Downsample (permute -> AdaptiveMaxPool2d -> permute) + cast, bit for bit."""
+    B, Fd = 5, 264
+    x = torch.randn(B, g * g, Fd, device="cuda", generator=torch.Generator(device="cuda").manual_seed(g * 10 + o)).to(dt_in)
+    ours = V.grid_maxpool(x, o, dt_out)
+    ref = torch.nn.functional.adaptive_max_pool2d(x.float().permute(0, 2, 1).reshape(B, Fd, g, g), (o, o))
+    ref = ref.reshape(B, Fd, -1).permute(0, 2, 1).to(dt_out)
+    assert torch.equal(ours, ref)

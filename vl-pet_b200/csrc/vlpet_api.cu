@@ -200,6 +200,55 @@ int vlpet_k3_bwd(const VlpetK3Desc* D, const void* feats, const void* pos, const
 // ---- flat-bucket helpers -----------------------------------------------------------------------------------
 namespace vlpet {
 namespace flat {
+// one thread = 8 consecutive channels of one output cell; windows per PyTorch's adaptive rule
+template <typename TI, typename TO>
+__global__ void grid_maxpool_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t nimg, int g, int o, int F) {
+  const int64_t nvec = (int64_t)F / 8;
+  const int64_t total = nimg * o * o * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i % nvec;
+    int64_t t = i / nvec;
+    const int ox = (int)(t % o); t /= o;
+    const int oy = (int)(t % o);
+    const int64_t img = t / o;
+    const int y0 = (oy * g) / o, y1 = ((oy + 1) * g + o - 1) / o;
+    const int x0 = (ox * g) / o, x1 = ((ox + 1) * g + o - 1) / o;
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        const TI* src = in + ((img * g * g + (int64_t)y * g + x) * F + v * 8);
+        if constexpr (sizeof(TI) == 4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
+          m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
+        } else {
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+          const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            m[2 * e] = fmaxf(m[2 * e], __uint_as_float(w[e] << 16));
+            m[2 * e + 1] = fmaxf(m[2 * e + 1], __uint_as_float(w[e] & 0xffff0000u));
+          }
+        }
+      }
+    TO* dst = out + (((img * o + oy) * o + ox) * (int64_t)F + v * 8);
+    if constexpr (sizeof(TO) == 4) {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(m[0], m[1], m[2], m[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(m[4], m[5], m[6], m[7]);
+    } else {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(m[2 * e], m[2 * e + 1]);
+        w[e] = *reinterpret_cast<uint32_t*>(&t2);
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
 __global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
@@ -290,6 +339,29 @@ inline int flat_blocks(int64_t n, int per_thread) {
 using namespace vlpet::flat;
 
 extern "C" {
+int vlpet_grid_maxpool(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t nimg, int32_t g, int32_t o,
+                       int32_t F, void* stream) {
+  if (!in || !out || nimg <= 0 || g <= 0 || o <= 0 || o > g || F <= 0) return fail(VLPET_E_BADARG, "grid_maxpool: bad arguments");
+  if (F % 8 != 0) return fail(VLPET_E_UNSUPPORTED, "grid_maxpool: F must be a multiple of 8");
+  if (!aligned16(in) || !aligned16(out)) return fail(VLPET_E_ALIGN, "grid_maxpool: buffers must be 16-byte aligned");
+  if ((in_dtype != VLPET_F32 && in_dtype != VLPET_BF16) || (out_dtype != VLPET_F32 && out_dtype != VLPET_BF16))
+    return fail(VLPET_E_BADARG, "grid_maxpool: bad dtype");
+  const int64_t total = nimg * o * o * (F / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in_dtype == VLPET_F32 && out_dtype == VLPET_BF16)
+    grid_maxpool_kernel<float, __nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out), nimg, g, o, F);
+  else if (in_dtype == VLPET_F32)
+    grid_maxpool_kernel<float, float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(out), nimg, g, o, F);
+  else if (out_dtype == VLPET_BF16)
+    grid_maxpool_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), nimg, g, o, F);
+  else
+    grid_maxpool_kernel<__nv_bfloat16, float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<float*>(out), nimg, g, o, F);
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+
 int vlpet_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   if (!src || !dst || n < 0) return fail(VLPET_E_BADARG, "cast: bad arguments");
   if (n == 0) return 0;

@@ -387,6 +387,24 @@ def visual_projection(feats, pos, img_order_ids, obj_order_ids, Wf, bf, ln_f_w, 
                            Wp, bp, ln_p_w, ln_p_b, E_img, E_obj.detach())
 
 
+def grid_maxpool(feats: torch.Tensor, out_size: int, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """[B, g*g, F] CLIP grid features -> [B, o*o, F] by adaptive max-pool (src/modeling_bart.py:556-613 Downsample),
+    fused with the cast to ``out_dtype`` (include/vlpet.h vlpet_grid_maxpool).  Inputs are data: no autograd."""
+    _require_cuda(feats)
+    if feats.dim() != 3 or feats.dtype not in _DT:
+        raise ValueError("vlpet.grid_maxpool: feats must be [B, g*g, F] fp32/bf16")
+    B, G, Fd = feats.shape
+    g = int(round(G ** 0.5))
+    if g * g != G:
+        raise ValueError(f"vlpet.grid_maxpool: {G} grid cells is not a square")
+    out_dtype = out_dtype or feats.dtype
+    fc = feats.detach().contiguous()
+    out = torch.empty(B, out_size * out_size, Fd, dtype=out_dtype, device=feats.device)
+    L.check(L.lib.vlpet_grid_maxpool(_p(fc), _DT[fc.dtype], _p(out), _DT[out_dtype], B, g, out_size, Fd, _stream()),
+            "vlpet_grid_maxpool")
+    return out
+
+
 def fwd_is_fused(M: int, d: int, r: int, rg: int, dtype=torch.bfloat16, gate: str = "large") -> bool:
     desc = L.K1Desc(M=M, L=0, d=d, r=r, rg=rg, gate=L.GATE_IDS[gate], add_gate=0, dtype=_DT[dtype], impl=L.IMPL_AUTO,
                     s=1.0, alpha=1.0, kappa=1.0, p_drop=0.0, seed=0)

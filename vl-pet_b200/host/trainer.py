@@ -157,6 +157,9 @@ class PetTrainer:
         for b in model.buffers():
             if b.is_floating_point():
                 b.data = b.data.to(compute_dtype)
+        for m in model.modules():                                 # visual features: pool + cast in one kernel
+            if type(m).__name__ == "Downsample" and self.device.type == "cuda" and compute_dtype in (torch.bfloat16, torch.float32):
+                m.out_dtype = compute_dtype
         self.bucket = PetBucket(named, self.device, torch.bfloat16 if compute_dtype == torch.bfloat16 else None,
                                 torch.float64 if compute_dtype == torch.float64 else torch.float32)
         self._norm_sq = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -204,6 +207,10 @@ class PetTrainer:
 
     def set_step(self, n: int):
         self.step_idx = int(n)
+
+    def launch_counter(self) -> int:
+        """libvlpet.so kernels launched so far on behalf of this process (vlpet_launch_count)."""
+        return L.launch_count()
 
     # -- the three phases of a step, separable so callers can capture / overlap them
     def forward_backward(self, batch: Dict) -> torch.Tensor:
@@ -267,6 +274,12 @@ class GraphedPetTrainer(PetTrainer):
         self._opt = None
         self._stream = torch.cuda.Stream(device=dev)
         self._loss_out = torch.zeros((), dtype=torch.float32, device=dev)
+        self._replayed_launches = 0
+
+    def launch_counter(self) -> int:
+        """Kernels of libvlpet.so executed so far: those launched directly (vlpet_launch_count, which also counts the
+        launches recorded while capturing) plus, for every graph replay, the number recorded in that graph."""
+        return L.launch_count() + self._replayed_launches
 
     def set_step(self, n: int):
         self.step_idx = int(n)
@@ -288,9 +301,11 @@ class GraphedPetTrainer(PetTrainer):
         torch.cuda.current_stream().wait_stream(self._stream)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
         with torch.cuda.graph(g, pool=self._pool, stream=self._stream):
             self._seed.add_(1000003)
             loss = self.forward_backward(static)
+        g.vlpet_launches = L.launch_count() - n0     # libvlpet.so kernels recorded in this graph = launched per replay
         return g, static, loss
 
     def _optimizer_ops(self):
@@ -324,8 +339,10 @@ class GraphedPetTrainer(PetTrainer):
     def _capture_opt(self):
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
         with torch.cuda.graph(g, pool=self._pool, stream=self._stream):
             self._optimizer_ops()
+        g.vlpet_launches = L.launch_count() - n0
         return g
 
     def train_step(self, batch) -> torch.Tensor:
@@ -341,6 +358,7 @@ class GraphedPetTrainer(PetTrainer):
                 static[k].copy_(v, non_blocking=True)
         self._release(key)                    # the staging set is free again once the copies into the static inputs ran
         g.replay()
+        self._replayed_launches += g.vlpet_launches
         # `loss` lives in the pool the graphs share: later replays (the optimizer graph's temporaries) may reuse its
         # storage, so the value is copied out to an ordinary tensor right behind the replay
         self._loss_out.copy_(loss)
@@ -349,5 +367,6 @@ class GraphedPetTrainer(PetTrainer):
             # first use: capture consumes the current gradients once eagerly inside the capture warm-up path
             self._opt = self._capture_opt()
         self._opt.replay()
+        self._replayed_launches += self._opt.vlpet_launches
         self.step_idx += 1
         return self._loss_out

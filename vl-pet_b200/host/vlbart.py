@@ -188,9 +188,14 @@ class Downsample(nn.Module):
     def __init__(self, output_size: Tuple[int, int]):
         super().__init__()
         self.output_size = output_size
+        self.out_dtype = None        # set by the trainer: pool and cast to the compute dtype in one CUDA kernel
 
     def _pool(self, x):
         B, L, dim = x.shape
+        if x.is_cuda and not x.requires_grad and dim % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16) and \
+                self.output_size[0] == self.output_size[1]:
+            from .. import functional as F_
+            return F_.grid_maxpool(x, self.output_size[0], self.out_dtype or x.dtype)
         s = int(L ** 0.5)
         x = F.adaptive_max_pool2d(x.permute(0, 2, 1).reshape(B, dim, s, s), self.output_size)
         return x.reshape(B, dim, -1).permute(0, 2, 1)
