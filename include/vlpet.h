@@ -183,6 +183,16 @@ VLPET_API int vlpet_k3_bwd(const VlpetK3Desc* desc, const void* feats, const voi
                  const void* dout, const VlpetK3Params* w, const float* save, void* dfeats /* may be NULL */,
                  const VlpetK3Grads* g, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- LayerNorm behind the encoder PET sites ---------------------------------------------
+ * The nn.LayerNorm the reference applies to the K1 output (my_transformers/modeling_bart.py:1260-1261, 1376-1377), for the
+ * training configuration: bf16 activations x / y / dy / dx [M, d], fp32 affine parameters (trainable under
+ * --unfreeze_encoder_layer_norms) and fp32 row statistics mean / rstd [M] saved by the forward.  dw / db are
+ * accumulated into (may be NULL for a frozen LayerNorm).  Requires d % 256 == 0, 256 <= d <= 1024.        */
+VLPET_API int vlpet_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int64_t M,
+                        int32_t d, float eps, int32_t dtype, void* stream);
+VLPET_API int vlpet_layernorm_bwd(const void* x, const void* dy, const float* w, const float* mean, const float* rstd, void* dx,
+                        float* dw, float* db, int64_t M, int32_t d, int32_t dtype, void* stream);
+
 /* ---- CLIP-grid downsample feeding K3 --------------------------------------------------------------------
  * Replaces Downsample.downsample_inputs (src/modeling_bart.py:566-583: permute -> [B, F, g, g] -> AdaptiveMaxPool2d((o, o))
  * -> permute back) for the pre-extracted grid features of the VL-PET scripts (--n_boxes 36 --downsample: 7x7 -> 6x6),

@@ -496,3 +496,31 @@ def test_grid_maxpool_matches_adaptive_max_pool(V, g, o, dt_in, dt_out):
     ref = torch.nn.functional.adaptive_max_pool2d(x.float().permute(0, 2, 1).reshape(B, Fd, g, g), (o, o))
     ref = ref.reshape(B, Fd, -1).permute(0, 2, 1).to(dt_out)
     assert torch.equal(ours, ref)
+
+
+@pytest.mark.parametrize("M,d", [(1, 768), (37, 768), (5000, 768), (300, 256), (129, 1024)])
+def test_layernorm_kernels_match_fp64(V, M, d):
+    """vlpet_layernorm_fwd / _bwd (bf16 activations, fp32 affine parameters) against nn.LayerNorm semantics in fp64 on
+    the same bf16 inputs: y / dx pass bf16_check at 1e-3, dgamma / dbeta (fp32) within 1e-5 relative."""
+    rng = np.random.default_rng(M + d)
+    x = rng.standard_normal((M, d)) * 1.5 + 0.3
+    dy = rng.standard_normal((M, d))
+    w, b = 1 + 0.1 * rng.standard_normal(d), 0.1 * rng.standard_normal(d)
+    tx = dev(x, torch.bfloat16).requires_grad_()
+    tw, tb = dev(w, torch.float32).requires_grad_(), dev(b, torch.float32).requires_grad_()
+    y = V.layer_norm(tx, tw, tb, 1e-5)
+    y.backward(dev(dy, torch.bfloat16))
+    torch.cuda.synchronize()
+    xr, dyr = bf16_round(x), bf16_round(dy)
+    wr, br = dev(w, torch.float32).double().cpu().numpy(), dev(b, torch.float32).double().cpu().numpy()
+    mu = xr.mean(1, keepdims=True)
+    var = ((xr - mu) ** 2).mean(1, keepdims=True)
+    rs = 1.0 / np.sqrt(var + 1e-5)
+    xh = (xr - mu) * rs
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    bf16_check(f(y), xh * wr + br, TOL_BF16)
+    g = dyr * wr
+    dx = rs * (g - g.mean(1, keepdims=True) - xh * (g * xh).mean(1, keepdims=True))
+    bf16_check(f(tx.grad), dx, TOL_BF16)
+    assert rel(f(tw.grad), (dyr * xh).sum(0)) < 1e-5
+    assert rel(f(tb.grad), dyr.sum(0)) < 1e-5

@@ -100,6 +100,22 @@ int vlpet_k1_bwd(const VlpetK1Desc* D, const void* x1, const void* x2, const voi
   return generic_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+// ---- LayerNorm behind the PET sites --------------------------------------------------------------------------
+int vlpet_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int64_t M, int32_t d,
+                        float eps, int32_t dtype, void* stream) {
+  if (!x || !w || !b || !y || !mean || !rstd || M <= 0) return fail(VLPET_E_BADARG, "layernorm_fwd: bad arguments");
+  if (!layernorm_supported(d, dtype)) return fail(VLPET_E_UNSUPPORTED, "layernorm_fwd: needs bf16, d %% 256 == 0, d <= 1024 (d=%d)", d);
+  if (!aligned16(x) || !aligned16(y) || !aligned16(w) || !aligned16(b)) return fail(VLPET_E_ALIGN, "layernorm_fwd: misaligned");
+  return layernorm_fwd(x, w, b, y, mean, rstd, M, d, eps, static_cast<cudaStream_t>(stream));
+}
+int vlpet_layernorm_bwd(const void* x, const void* dy, const float* w, const float* mean, const float* rstd, void* dx, float* dw,
+                        float* db, int64_t M, int32_t d, int32_t dtype, void* stream) {
+  if (!x || !dy || !w || !mean || !rstd || !dx || M <= 0) return fail(VLPET_E_BADARG, "layernorm_bwd: bad arguments");
+  if (!layernorm_supported(d, dtype)) return fail(VLPET_E_UNSUPPORTED, "layernorm_bwd: needs bf16, d %% 256 == 0, d <= 1024 (d=%d)", d);
+  if (!aligned16(x) || !aligned16(dy) || !aligned16(dx) || !aligned16(w)) return fail(VLPET_E_ALIGN, "layernorm_bwd: misaligned");
+  return layernorm_bwd(x, dy, w, mean, rstd, dx, dw, db, M, d, static_cast<cudaStream_t>(stream));
+}
+
 // developer hook (not part of include/vlpet.h): phase timestamps of the fused K1 forward, see tools/trace_k1.py
 __attribute__((visibility("default"))) int vlpet_debug_set_k1_trace(void* dev_buf) {
   return vlpet::set_k1_trace(static_cast<unsigned long long*>(dev_buf));

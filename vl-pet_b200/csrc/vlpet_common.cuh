@@ -159,6 +159,12 @@ int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void
                 const int* nb_valid, float* const* out, float* const* bias, const float* scale, const int* transposed,
                 int64_t Mtok, int d, int nout, int sm_count, cudaStream_t st);
 int device_sm_count();
+// LayerNorm behind the PET sites, vlpet_layernorm.cu
+bool layernorm_supported(int d, int dtype);
+int layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int64_t M, int d,
+                  float eps, cudaStream_t st);
+int layernorm_bwd(const void* x, const void* dy, const float* w, const float* mean, const float* rstd, void* dx, float* dw,
+                  float* db, int64_t M, int d, cudaStream_t st);
 int set_k1_trace(unsigned long long* dev_buf);   // developer hook, tools/trace_k1.py
 int set_k1_bwd_trace(unsigned long long* dev_buf);
 // dense projection GEMM (tcgen05), vlpet_gemm_sm100.cu: C fp32 = A bf16 * W^T bf16 + bias

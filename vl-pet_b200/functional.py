@@ -387,6 +387,55 @@ def visual_projection(feats, pos, img_order_ids, obj_order_ids, Wf, bf, ln_f_w, 
                            Wp, bp, ln_p_w, ln_p_b, E_img, E_obj.detach())
 
 
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm on bf16 activations with fp32 affine parameters (include/vlpet.h vlpet_layernorm_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps: float):
+        _require_cuda(x, weight, bias)
+        d = x.shape[-1]
+        xc = x.contiguous()
+        M = xc.numel() // d
+        w32 = weight.detach() if weight.dtype == torch.float32 else weight.detach().float()
+        b32 = bias.detach() if bias.dtype == torch.float32 else bias.detach().float()
+        y = torch.empty_like(xc)
+        stats = torch.empty(2, M, dtype=torch.float32, device=x.device)
+        L.check(_call("ln_fwd", 2 * xc.numel() * xc.element_size(), L.lib.vlpet_layernorm_fwd, _p(xc), _p(w32.contiguous()),
+                      _p(b32.contiguous()), _p(y), _p(stats[0]), _p(stats[1]), M, d, float(eps), _DT[xc.dtype], _stream()),
+                "vlpet_layernorm_fwd")
+        ctx.save_for_backward(xc, w32, stats)
+        ctx.meta = (weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, w32, stats = ctx.saved_tensors
+        d = xc.shape[-1]
+        M = xc.numel() // d
+        dy = dy.contiguous()
+        if dy.dtype != xc.dtype:
+            dy = dy.to(xc.dtype)
+        dx = torch.empty_like(xc)
+        need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        gbuf = torch.zeros(2, d, dtype=torch.float32, device=xc.device) if (need_w or need_b) else None
+        L.check(_call("ln_bwd", 3 * xc.numel() * xc.element_size(), L.lib.vlpet_layernorm_bwd, _p(xc), _p(dy), _p(w32.contiguous()),
+                      _p(stats[0]), _p(stats[1]), _p(dx), _p(gbuf[0]) if need_w else C.c_void_p(0),
+                      _p(gbuf[1]) if need_b else C.c_void_p(0), M, d, _DT[xc.dtype], _stream()), "vlpet_layernorm_bwd")
+        dw = gbuf[0].to(ctx.meta[0]) if need_w else None
+        db = gbuf[1].to(ctx.meta[1]) if need_b else None
+        return dx, dw, db, None
+
+
+def layer_norm(x, weight, bias, eps: float = 1e-5):
+    """LayerNorm over the last dimension through the CUDA kernels (bf16 activations, d % 256 == 0, d <= 1024)."""
+    return LayerNormFn.apply(x, weight, bias, eps)
+
+
+def layer_norm_supported(x: torch.Tensor) -> bool:
+    d = x.shape[-1]
+    return x.is_cuda and x.dtype == torch.bfloat16 and d % 256 == 0 and 256 <= d <= 1024
+
+
 def grid_maxpool(feats: torch.Tensor, out_size: int, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """[B, g*g, F] CLIP grid features -> [B, o*o, F] by adaptive max-pool (src/modeling_bart.py:556-613 Downsample),
     fused with the cast to ``out_dtype`` (include/vlpet.h vlpet_grid_maxpool).  Inputs are data: no autograd."""

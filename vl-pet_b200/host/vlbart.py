@@ -20,13 +20,17 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import encoder as E
+from .. import functional as F_
 from ..adapters import AdapterController
 from ..visual import VisualEmbedding
 from .config import VLPetConfig
 
 
 def _ln(ln: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
-    """LayerNorm whose (trainable, fp32-master) affine parameters may be wider than the activation dtype."""
+    """LayerNorm whose (trainable, fp32-master) affine parameters may be wider than the activation dtype.  On the GPU in
+    bf16 it runs the one-launch row kernels of libvlpet.so; anywhere else stock F.layer_norm."""
+    if x.is_cuda and x.dtype == torch.bfloat16 and F_.layer_norm_supported(x):
+        return F_.layer_norm(x, ln.weight, ln.bias, ln.eps)
     w, b = ln.weight, ln.bias
     if w.dtype != x.dtype:
         w, b = w.to(x.dtype), b.to(x.dtype)
