@@ -134,3 +134,29 @@ def test_host_model_with_cuda_pet_matches_reference_vlbart(H, gate):
         for n in names:
             assert rel(params[n].grad.double().cpu().numpy(), z[f"{task}/grad/{n}"]) < 2e-4, (task, n)
     assert V.launch_count() - n0 >= 2 * (2 * 2 * 2 + 2 + 1), "PET sites did not run the CUDA kernels"
+
+
+@pytest.mark.gpu
+def test_trainer_bucket_gradients_match_reference_vlbart(H):
+    """Same comparison through the PET-only trainer: gradients accumulated by the kernels STRAIGHT into the flat
+    all-reduce bucket (functional.set_direct_grad_accumulation) must equal the reference VLBart gradients."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import vlpet_b200.functional as F_
+    z = _load("large")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model = H.VLBart(_cfg(H, "large")).eval()
+    _load_state(model, z, torch.float32)
+    tr = H.PetTrainer(model, model.config, "cuda", compute_dtype=torch.float32)
+    try:
+        assert F_._direct_grads
+        for task in ("vqa", "nlvr"):
+            loss = tr.forward_backward(_batch(z, task, torch.float32))
+            assert abs(loss.item() - float(z[f"{task}/loss"])) < 2e-5 * abs(float(z[f"{task}/loss"]))
+            flat = tr.bucket.flat_grad.double().cpu().numpy()
+            for n, p, o in zip(tr.bucket.names, tr.bucket.params, tr.bucket.offsets):
+                got = flat[o:o + p.numel()]
+                assert rel(got, z[f"{task}/grad/{n}"].reshape(-1)) < 2e-4, (task, n)
+    finally:
+        F_.set_direct_grad_accumulation(False)

@@ -17,6 +17,40 @@ _seed_dev = None   # optional device int64 scalar added to every dropout seed (C
 _prof = None   # when profiling: list of (kernel name, algorithmic bytes, start event, end event)
 
 
+_direct_grads = False
+
+
+def set_direct_grad_accumulation(flag: bool):
+    """When on, the backward kernels accumulate the fp32 weight gradients STRAIGHT into ``param.grad`` (the C ABI's
+    `+=` contract: with PetBucket those are views of the flat all-reduce payload) and autograd receives ``None`` for
+    the parameters -- no temporary gradient buffer, no per-parameter AccumulateGrad kernels.  Requires every parameter
+    of the call to own a pre-allocated contiguous fp32 ``.grad`` (heads adjacent); otherwise the call falls back to
+    returning gradients.  Off by default (hooks / torch.autograd.grad need the returned tensors)."""
+    global _direct_grads
+    _direct_grads = bool(flag)
+
+
+def _direct_targets(params, groups):
+    """groups: list of index lists into params that must form ONE contiguous fp32 buffer each (e.g. the heads of a
+    multi-head down projection).  -> list of data pointers (one per group) or None."""
+    if not _direct_grads:
+        return None
+    ptrs = []
+    for idxs in groups:
+        g0 = params[idxs[0]].grad
+        if g0 is None or g0.dtype != torch.float32 or not g0.is_contiguous() or (g0.data_ptr() & 15):
+            return None
+        off = g0.data_ptr()
+        for i in idxs:
+            gi = params[i].grad
+            if gi is None or gi.dtype != torch.float32 or not gi.is_contiguous() or gi.data_ptr() != off or \
+                    not params[i].requires_grad:
+                return None
+            off += gi.numel() * 4
+        ptrs.append(g0.data_ptr())
+    return ptrs
+
+
 def set_device_seed(t: Optional[torch.Tensor]):
     """Register a device int64 scalar that the K1 kernels add to their dropout seed at run time (VlpetK1Desc.seed_dev).
     A CUDA graph that captured the calls then draws a fresh mask on every replay once the caller bumps the scalar
@@ -176,6 +210,7 @@ class GatedPETFn(torch.autograd.Function):
                       C.byref(w), _p(out), _p(ws), ws.numel(), _stream()), "vlpet_k1_fwd")
         ctx.desc, ctx.nheads, ctx.cfg = desc, nheads, cfg
         ctx.param_meta = [(tuple(t.shape), t.dtype) for t in params]
+        ctx.param_refs = params
         ctx.save_for_backward(x1c, x2c, Wd, bd, Wu, bu, *gp)
         return out
 
@@ -200,15 +235,23 @@ class GatedPETFn(torch.autograd.Function):
         offs = [0]
         for n in sizes:
             offs.append(offs[-1] + (n + 3) // 4 * 4)      # keep every grad 16-byte aligned
-        gbuf = torch.zeros(offs[-1], dtype=torch.float32, device=x1.device)
-        gv = [gbuf[offs[i]:offs[i] + sizes[i]] for i in range(len(sizes))]
-        g = L.K1Grads(dWd=_p(gv[0]), dbd=_p(gv[1]), dWu=_p(gv[2]), dbu=_p(gv[3]))
+        nh = nheads
+        groups = [list(range(nh)), list(range(nh, 2 * nh))] + [[i] for i in range(2 * nh, len(ctx.param_refs))]
+        direct = _direct_targets(ctx.param_refs, groups)
+        if direct is not None:
+            vp = [C.c_void_p(a) for a in direct]
+            gv = None
+        else:
+            gbuf = torch.zeros(offs[-1], dtype=torch.float32, device=x1.device)
+            gv = [gbuf[offs[i]:offs[i] + sizes[i]] for i in range(len(sizes))]
+            vp = [_p(t) for t in gv]
+        g = L.K1Grads(dWd=vp[0], dbd=vp[1], dWu=vp[2], dbu=vp[3])
         if cfg.gate == "large":
-            g.dGd, g.dgbd, g.dGu, g.dgbu = _p(gv[4]), _p(gv[5]), _p(gv[6]), _p(gv[7])
+            g.dGd, g.dgbd, g.dGu, g.dgbu = vp[4], vp[5], vp[6], vp[7]
         elif cfg.gate in ("middle_x", "small"):
-            g.dgw, g.dgb = _p(gv[4]), _p(gv[5])
+            g.dgw, g.dgb = vp[4], vp[5]
         elif cfg.gate == "middle_y":
-            g.dgz = _p(gv[4])
+            g.dgz = vp[4]
         w = L.K1Params(Wd=_p(Wd), bd=_p(bd), Wu=_p(Wu), bu=_p(bu))
         if cfg.gate == "large":
             w.Gd, w.gbd, w.Gu, w.gbu = _p(gp[0]), _p(gp[1]), _p(gp[2]), _p(gp[3])
@@ -221,6 +264,8 @@ class GatedPETFn(torch.autograd.Function):
         ws = _workspace(nws, x1.device)
         L.check(_call("k1_bwd", 5 * x1.numel() * x1.element_size(), L.lib.vlpet_k1_bwd, C.byref(desc), _p(x1), _p(x2),
                       _p(dout), C.byref(w), _p(dx1), _p(dx2), C.byref(g), _p(ws), ws.numel(), _stream()), "vlpet_k1_bwd")
+        if gv is None:       # gradients were accumulated into param.grad by the kernels
+            return (None, None, None, None, dx1, dx2) + (None,) * len(ctx.param_refs)
         # scatter the flat fp32 grads back onto the parameter list (heads are row slices of dWd / dbd)
         meta = ctx.param_meta
         grads: List[Optional[torch.Tensor]] = []
@@ -273,6 +318,7 @@ class VpaFn(torch.autograd.Function):
                       C.byref(desc), _p(kvc), _p(yc), C.byref(w), _p(out), _p(ws), ws.numel(), _stream()), "vlpet_k2_fwd")
         ctx.desc, ctx.has_y = desc, y is not None
         ctx.param_meta = [(tuple(t.shape), t.dtype) for t in (Wd, bd, Wu, bu)]
+        ctx.param_refs = (Wd, bd, Wu, bu)
         ctx.save_for_backward(kvc, Wdc, bdc, Wuc, buc)
         return out
 
@@ -288,14 +334,21 @@ class VpaFn(torch.autograd.Function):
         offs = [0]
         for n in sizes:
             offs.append(offs[-1] + (n + 3) // 4 * 4)
-        gbuf = torch.zeros(offs[-1], dtype=torch.float32, device=kv.device)
-        gv = [gbuf[offs[i]:offs[i] + sizes[i]] for i in range(4)]
-        g = L.K2Grads(dWd=_p(gv[0]), dbd=_p(gv[1]), dWu=_p(gv[2]), dbu=_p(gv[3]))
+        direct = _direct_targets(ctx.param_refs, [[0], [1], [2], [3]])
+        if direct is not None:
+            gv = None
+            g = L.K2Grads(*[C.c_void_p(a) for a in direct])
+        else:
+            gbuf = torch.zeros(offs[-1], dtype=torch.float32, device=kv.device)
+            gv = [gbuf[offs[i]:offs[i] + sizes[i]] for i in range(4)]
+            g = L.K2Grads(dWd=_p(gv[0]), dbd=_p(gv[1]), dWu=_p(gv[2]), dbu=_p(gv[3]))
         w = L.K2Params(Wd=_p(Wd), bd=_p(bd), Wu=_p(Wu), bu=_p(bu))
         dkv = torch.empty_like(kv) if ctx.needs_input_grad[2] else None
         ws = _workspace(L.lib.vlpet_k2_bwd_workspace_bytes(C.byref(desc)), kv.device)
         L.check(_call("k2_bwd", 3 * kv.numel() * kv.element_size(), L.lib.vlpet_k2_bwd, C.byref(desc), _p(kv), _p(dout),
                       C.byref(w), _p(dkv), C.byref(g), _p(ws), ws.numel(), _stream()), "vlpet_k2_bwd")
+        if gv is None:
+            return (None, None, dkv, dout if ctx.has_y else None, None, None, None, None)
         outg = []
         for gt, (shape, dtype) in zip(gv, ctx.param_meta):
             gt = gt.reshape(shape)
@@ -405,6 +458,7 @@ class LayerNormFn(torch.autograd.Function):
                 "vlpet_layernorm_fwd")
         ctx.save_for_backward(xc, w32, stats)
         ctx.meta = (weight.dtype, bias.dtype)
+        ctx.param_refs = (weight, bias)
         return y
 
     @staticmethod
@@ -417,6 +471,12 @@ class LayerNormFn(torch.autograd.Function):
             dy = dy.to(xc.dtype)
         dx = torch.empty_like(xc)
         need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        direct = _direct_targets(ctx.param_refs, [[0], [1]]) if (need_w and need_b) else None
+        if direct is not None:
+            L.check(_call("ln_bwd", 3 * xc.numel() * xc.element_size(), L.lib.vlpet_layernorm_bwd, _p(xc), _p(dy), _p(w32.contiguous()),
+                          _p(stats[0]), _p(stats[1]), _p(dx), C.c_void_p(direct[0]), C.c_void_p(direct[1]), M, d, _DT[xc.dtype],
+                          _stream()), "vlpet_layernorm_bwd")
+            return dx, None, None, None
         gbuf = torch.zeros(2, d, dtype=torch.float32, device=xc.device) if (need_w or need_b) else None
         L.check(_call("ln_bwd", 3 * xc.numel() * xc.element_size(), L.lib.vlpet_layernorm_bwd, _p(xc), _p(dy), _p(w32.contiguous()),
                       _p(stats[0]), _p(stats[1]), _p(dx), _p(gbuf[0]) if need_w else C.c_void_p(0),

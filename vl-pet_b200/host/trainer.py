@@ -162,6 +162,9 @@ class PetTrainer:
                 m.out_dtype = compute_dtype
         self.bucket = PetBucket(named, self.device, torch.bfloat16 if compute_dtype == torch.bfloat16 else None,
                                 torch.float64 if compute_dtype == torch.float64 else torch.float32)
+        if self.device.type == "cuda" and compute_dtype != torch.float64:
+            from .. import functional as F_
+            F_.set_direct_grad_accumulation(True)                 # weight gradients land in the bucket, no detours
         self._norm_sq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._scale = torch.ones(1, dtype=torch.float32, device=self.device)
         if self.world > 1:                                        # identical start on every rank
