@@ -193,6 +193,16 @@ VLPET_API int vlpet_layernorm_fwd(const void* x, const float* w, const float* b,
 VLPET_API int vlpet_layernorm_bwd(const void* x, const void* dy, const float* w, const float* mean, const float* rstd, void* dx,
                         float* dw, float* db, int64_t M, int32_t d, int32_t dtype, void* stream);
 
+/* ---- FFN activation of the frozen blocks around the PET sites ---------------------------
+ * y = dropout_p(gelu(x)) in one pass and its backward dx = dy * mask/(1-p) * gelu'(x) in one pass, replacing the
+ * reference's `activation_fn(fc1(h))` + `F.dropout(.., p=activation_dropout)` pair (my_transformers/modeling_bart.py:
+ * 1264-1266) and the two autograd kernels behind it.  gelu is the exact erf form (ACT2FN["gelu"]); the dropout mask is the
+ * counter-based stream of K1 (never stored: the backward regenerates it from seed + *seed_dev).  bf16, n % 8 == 0.     */
+VLPET_API int vlpet_gelu_dropout_fwd(const void* x, void* y, int64_t n, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                           void* stream);
+VLPET_API int vlpet_gelu_dropout_bwd(const void* x, const void* dy, void* dx, int64_t n, float p_drop, uint64_t seed,
+                           const uint64_t* seed_dev, void* stream);
+
 /* ---- CLIP-grid downsample feeding K3 --------------------------------------------------------------------
  * Replaces Downsample.downsample_inputs (src/modeling_bart.py:566-583: permute -> [B, F, g, g] -> AdaptiveMaxPool2d((o, o))
  * -> permute back) for the pre-extracted grid features of the VL-PET scripts (--n_boxes 36 --downsample: 7x7 -> 6x6),

@@ -524,3 +524,32 @@ def test_layernorm_kernels_match_fp64(V, M, d):
     bf16_check(f(tx.grad), dx, TOL_BF16)
     assert rel(f(tw.grad), (dyr * xh).sum(0)) < 1e-5
     assert rel(f(tb.grad), dyr.sum(0)) < 1e-5
+
+
+def test_gelu_dropout_kernels(V):
+    """Fused FFN activation: p = 0 equals F.gelu (exact erf form) forward and backward within bf16 rounding; p > 0 keeps
+    1-p of the elements scaled by 1/(1-p), and the backward regenerates the forward's mask."""
+    import vlpet_b200.functional as F_
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (2.0 * torch.randn(333, 3072, device="cuda", generator=g)).to(torch.bfloat16).requires_grad_()
+    dy = torch.randn(333, 3072, device="cuda", generator=g).to(torch.bfloat16)
+    y = F_.gelu_dropout(x, 0.1, training=False)
+    y.backward(dy)
+    xr = x.detach().double().requires_grad_()
+    yr = torch.nn.functional.gelu(xr)
+    yr.backward(dy.double())
+    f = lambda t: t.detach().double().cpu().numpy()  # noqa: E731
+    bf16_check(f(y), f(yr), TOL_BF16)
+    bf16_check(f(x.grad), f(xr.grad), TOL_BF16)
+    x.grad = None
+    F_._seed_counter[0] += 1
+    y2 = F_.GeluDropoutFn.apply(x, 0.25, 4242)
+    y2.backward(dy)
+    base = torch.nn.functional.gelu(x.detach().float())
+    sig = base.abs() > 0.05
+    dropped = (y2 == 0) & sig
+    assert abs(dropped.sum().item() / sig.sum().item() - 0.25) < 0.01
+    kept = sig & ~dropped
+    assert abs((y2.float()[kept] / base[kept]).median().item() - 1 / 0.75) < 0.02
+    sigb = sig & (dy.float().abs() > 0.05) & (xr.grad.float().abs() > 1e-2)
+    assert torch.equal((x.grad == 0)[sigb], dropped[sigb])          # same mask forward and backward

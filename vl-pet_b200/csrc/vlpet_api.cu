@@ -216,6 +216,50 @@ int vlpet_k3_bwd(const VlpetK3Desc* D, const void* feats, const void* pos, const
 // ---- flat-bucket helpers -----------------------------------------------------------------------------------
 namespace vlpet {
 namespace flat {
+// y = dropout(gelu_erf(x)) / dx = dy * mask/(1-p) * gelu_erf'(x); 8 bf16 per thread, mask from drop_hash4
+template <bool BWD>
+__global__ void gelu_dropout_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                    __nv_bfloat16* __restrict__ out, int64_t nvec, uint64_t seed, const uint64_t* seed_dev,
+                                    uint32_t thr16, float inv_keep) {
+  const uint64_t s = seed + ((thr16 && seed_dev) ? *seed_dev : 0ull);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 q = *reinterpret_cast<const uint4*>(x + i * 8);
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    uint32_t g[4] = {0, 0, 0, 0};
+    if (BWD) {
+      const uint4 qd = *reinterpret_cast<const uint4*>(dy + i * 8);
+      g[0] = qd.x; g[1] = qd.y; g[2] = qd.z; g[3] = qd.w;
+    }
+    uint64_t h[2] = {0, 0};
+    if (thr16) { h[0] = drop_hash4(s, (uint64_t)i * 2); h[1] = drop_hash4(s, (uint64_t)i * 2 + 1); }
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float r[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float v = k ? __uint_as_float(u[e] & 0xffff0000u) : __uint_as_float(u[e] << 16);
+        float m = 1.0f;
+        if (thr16) {
+          const uint32_t bits = (uint32_t)(h[e >> 1] >> (16 * ((e & 1) * 2 + k))) & 0xffffu;
+          m = bits >= thr16 ? inv_keep : 0.0f;
+        }
+        const float cdf = 0.5f * (1.0f + erff(v * 0.7071067811865476f));
+        if (BWD) {
+          const float d = k ? __uint_as_float(g[e] & 0xffff0000u) : __uint_as_float(g[e] << 16);
+          const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
+          r[k] = d * m * (cdf + v * pdf);
+        } else {
+          r[k] = m * v * cdf;
+        }
+      }
+      __nv_bfloat162 t = __floats2bfloat162_rn(r[0], r[1]);
+      o[e] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // one thread = 8 consecutive channels of one output cell; windows per PyTorch's adaptive rule
 template <typename TI, typename TO>
 __global__ void grid_maxpool_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t nimg, int g, int o, int F) {
@@ -355,6 +399,34 @@ inline int flat_blocks(int64_t n, int per_thread) {
 using namespace vlpet::flat;
 
 extern "C" {
+static int gelu_dropout_launch(bool bwd, const void* x, const void* dy, void* out, int64_t n, float p_drop, uint64_t seed,
+                               const uint64_t* seed_dev, void* stream) {
+  if (!x || !out || (bwd && !dy) || n <= 0 || !(p_drop >= 0.f && p_drop < 1.f)) return fail(VLPET_E_BADARG, "gelu_dropout: bad arguments");
+  if (n % 8 != 0) return fail(VLPET_E_UNSUPPORTED, "gelu_dropout: n must be a multiple of 8");
+  if (!aligned16(x) || !aligned16(out) || (bwd && !aligned16(dy))) return fail(VLPET_E_ALIGN, "gelu_dropout: misaligned");
+  const uint32_t thr16 = p_drop > 0.f ? drop_thr16(p_drop) : 0u;
+  const float inv_keep = thr16 ? 1.0f / (1.0f - (float)thr16 / 65536.0f) : 1.0f;
+  const int64_t nvec = n / 8;
+  int64_t blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bwd)
+    gelu_dropout_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy),
+                                                               static_cast<__nv_bfloat16*>(out), nvec, seed, seed_dev, thr16, inv_keep);
+  else
+    gelu_dropout_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), nullptr,
+                                                                static_cast<__nv_bfloat16*>(out), nvec, seed, seed_dev, thr16, inv_keep);
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+int vlpet_gelu_dropout_fwd(const void* x, void* y, int64_t n, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+  return gelu_dropout_launch(false, x, nullptr, y, n, p_drop, seed, seed_dev, stream);
+}
+int vlpet_gelu_dropout_bwd(const void* x, const void* dy, void* dx, int64_t n, float p_drop, uint64_t seed,
+                           const uint64_t* seed_dev, void* stream) {
+  return gelu_dropout_launch(true, x, dy, dx, n, p_drop, seed, seed_dev, stream);
+}
+
 int vlpet_grid_maxpool(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t nimg, int32_t g, int32_t o,
                        int32_t F, void* stream) {
   if (!in || !out || nimg <= 0 || g <= 0 || o <= 0 || o > g || F <= 0) return fail(VLPET_E_BADARG, "grid_maxpool: bad arguments");

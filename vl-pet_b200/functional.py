@@ -496,6 +496,42 @@ def layer_norm_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dtype == torch.bfloat16 and d % 256 == 0 and 256 <= d <= 1024
 
 
+class GeluDropoutFn(torch.autograd.Function):
+    """dropout_p(gelu(x)) in one pass each way (include/vlpet.h vlpet_gelu_dropout_fwd / _bwd); bf16, exact erf GELU."""
+
+    @staticmethod
+    def forward(ctx, x, p: float, seed: int):
+        _require_cuda(x)
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        sd = _seed_dev.data_ptr() if (seed and _seed_dev is not None) else None
+        L.check(_call("gelu_drop_fwd", 2 * xc.numel() * 2, L.lib.vlpet_gelu_dropout_fwd, _p(xc), _p(y), xc.numel(), float(p if seed else 0.0),
+                      seed, C.c_void_p(sd) if sd else C.c_void_p(0), _stream()), "vlpet_gelu_dropout_fwd")
+        ctx.save_for_backward(xc)
+        ctx.args = (float(p if seed else 0.0), seed, sd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        p, seed, sd = ctx.args
+        dy = dy.contiguous()
+        dx = torch.empty_like(xc)
+        L.check(_call("gelu_drop_bwd", 3 * xc.numel() * 2, L.lib.vlpet_gelu_dropout_bwd, _p(xc), _p(dy), _p(dx), xc.numel(), p, seed,
+                      C.c_void_p(sd) if sd else C.c_void_p(0), _stream()), "vlpet_gelu_dropout_bwd")
+        return dx, None, None
+
+
+def gelu_dropout(x: torch.Tensor, p: float, training: bool) -> torch.Tensor:
+    """dropout(gelu(x), p) of the frozen FFN, one kernel forward and one backward (bf16 CUDA tensors, numel % 8 == 0)."""
+    seed = next_dropout_seed() if (training and p > 0.0) else 0
+    return GeluDropoutFn.apply(x, p, seed)
+
+
+def gelu_dropout_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.bfloat16 and x.numel() % 8 == 0
+
+
 def grid_maxpool(feats: torch.Tensor, out_size: int, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """[B, g*g, F] CLIP grid features -> [B, o*o, F] by adaptive max-pool (src/modeling_bart.py:556-613 Downsample),
     fused with the cast to ``out_dtype`` (include/vlpet.h vlpet_grid_maxpool).  Inputs are data: no autograd."""

@@ -113,6 +113,14 @@ def _sdpa_policy(q: torch.Tensor):
     return contextlib.nullcontext()
 
 
+def _ffn_act(layer, h: torch.Tensor) -> torch.Tensor:
+    """activation_fn + activation dropout of the frozen FFN (my_transformers/modeling_bart.py:1264-1266): one fused CUDA
+    kernel each way for bf16 gelu, stock PyTorch otherwise."""
+    if layer.activation_fn is F.gelu and F_.gelu_dropout_supported(h):
+        return F_.gelu_dropout(h, layer.activation_dropout, layer.training)
+    return F.dropout(layer.activation_fn(h), p=layer.activation_dropout, training=layer.training)
+
+
 def _act(name: str):
     if name == "gelu":
         return F.gelu
@@ -169,9 +177,7 @@ class BartEncoderLayer(nn.Module):
         x2 = self.self_attn(hidden_states, attn_mask=attn_mask)
         hidden_states = _ln(self.self_attn_layer_norm, self._pet("attn", x1, x2))
         x1 = hidden_states
-        h = self.activation_fn(self.fc1(hidden_states))
-        h = F.dropout(h, p=self.activation_dropout, training=self.training)
-        x2 = self.fc2(h)
+        x2 = self.fc2(_ffn_act(self, self.fc1(hidden_states)))
         return _ln(self.final_layer_norm, self._pet("ff", x1, x2))
 
 
@@ -200,9 +206,7 @@ class BartDecoderLayer(nn.Module):
         hidden_states = _ln(self.self_attn_layer_norm, hidden_states + drop(h))
         h = self.encoder_attn(hidden_states, key_value_states=encoder_hidden_states, attn_mask=cross_mask, task=task)
         hidden_states = _ln(self.encoder_attn_layer_norm, hidden_states + drop(h))
-        h = self.activation_fn(self.fc1(hidden_states))
-        h = F.dropout(h, p=self.activation_dropout, training=self.training)
-        h = self.fc2(h)
+        h = self.fc2(_ffn_act(self, self.fc1(hidden_states)))
         return _ln(self.final_layer_norm, hidden_states + drop(h))
 
 
