@@ -382,7 +382,7 @@ class VLBart(nn.Module):
         dec_in = shift_tokens_right(labels, cfg.pad_token_id, cfg.decoder_start_token_id)
         h = self.model(input_ids, vis_inputs, dec_in, attention_mask, vis_attention_mask, task=task)
         w, b, width = self._lm_operands(h.dtype)
-        logits = F.linear(h, w) + b
+        logits = F.linear(h, w, b.reshape(-1))          # bias folded into the GEMM epilogue: no extra pass over the logits
         lg = logits.view(-1, width)
         if lg.dtype in (torch.bfloat16, torch.float16):
             lg = lg.float()
