@@ -198,6 +198,15 @@ def k1_micro(V, F_, peak):
         tot_ms += ms
         tot_b += by
         res[k] = {"us": round(1e3 * ms, 1), "algorithmic_GBps": round(by / ms / 1e6, 1), "frac": round(by / ms / 1e6 / peak, 3)}
+    try:   # measured DRAM traffic of the same launches, from the committed ncu captures (profiles/r1_ncu_traffic.json)
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        res["k1_fwd"]["traffic_MB"] = round(t["k1_fwd"]["read_MB"] + t["k1_fwd"]["write_MB"], 1)
+        res["k1_bwd"]["traffic_MB"] = round(sum(t[k]["read_MB"] + t[k]["write_MB"] for k in
+                                                 ("k1_bwd_activation_gradients", "k1_bwd_weight_gradients")), 1)
+        res["k1_fwd"]["algorithmic_MB"] = round(s["k1_fwd"]["bytes"] / s["k1_fwd"]["launches"] / 1e6, 1)
+        res["k1_bwd"]["algorithmic_MB"] = round(s["k1_bwd"]["bytes"] / s["k1_bwd"]["launches"] / 1e6, 1)
+    except Exception:
+        pass
     res["k1_fwd+bwd"] = {"us": round(1e3 * tot_ms, 1), "algorithmic_GBps": round(tot_b / tot_ms / 1e6, 1),
                          "frac": round(tot_b / tot_ms / 1e6 / peak, 3)}
     return res
