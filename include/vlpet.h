@@ -213,6 +213,36 @@ VLPET_API int vlpet_gelu_dropout_bwd(const void* x, const void* dy, void* dx, in
 VLPET_API int vlpet_grid_maxpool(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t nimg, int32_t g,
                        int32_t o, int32_t F, void* stream);
 
+/* ---- K3-LR: the PET-shaped visual projector (flag --use_lowrank_visual_projector) -----------------------
+ * Replaces LowRankVisualEmbedding.forward (src/modeling_bart.py:263-334):
+ *     e   = Up(gelu_new(Down feats))                      Down = row-concatenated multi-head Linear(F, r/h)
+ *     e   = e * G   |   e + e * G                         G = sigmoid(GUp(gelu_new(GDown feats)))   (gated / residual flags)
+ *     out = LN(e) + LN([pos,area] Wp^T + bp) + E_img[img_ids] + E_obj[V-1-obj_ids]
+ * Shape-generic CUDA-core implementation (no shipped VL-PET script enables the flag).  `save` as for K3.       */
+typedef struct VlpetK3LRDesc {
+  int64_t M;
+  int32_t N, F, d, r, rg, V, n_img;
+  int32_t gated;    /* use_visual_projector_gating_large_x_lowrank                */
+  int32_t residual; /* use_visual_projector_residual_connection: e + e*G          */
+  int32_t dtype, impl;
+  float eps;
+} VlpetK3LRDesc;
+typedef struct VlpetK3LRParams {
+  const void *Wd, *bd, *Wu, *bu, *Gd, *gbd, *Gu, *gbu; /* [r,F],[r],[d,r],[d],[rg,F],[rg],[d,rg],[d] */
+  const void *ln_f_w, *ln_f_b, *Wp, *bp, *ln_p_w, *ln_p_b, *E_img, *E_obj;
+} VlpetK3LRParams;
+typedef struct VlpetK3LRGrads {
+  float *dWd, *dbd, *dWu, *dbu, *dGd, *dgbd, *dGu, *dgbu, *dln_f_w, *dln_f_b, *dWp, *dbp, *dln_p_w, *dln_p_b, *dE_img;
+} VlpetK3LRGrads;
+VLPET_API size_t vlpet_k3lr_fwd_workspace_bytes(const VlpetK3LRDesc* desc);
+VLPET_API size_t vlpet_k3lr_bwd_workspace_bytes(const VlpetK3LRDesc* desc);
+VLPET_API int vlpet_k3lr_fwd(const VlpetK3LRDesc* desc, const void* feats, const void* pos, const int64_t* img_ids,
+                   const int64_t* obj_ids, const VlpetK3LRParams* w, void* out, float* save /* M*d floats */,
+                   void* workspace, size_t workspace_bytes, void* stream);
+VLPET_API int vlpet_k3lr_bwd(const VlpetK3LRDesc* desc, const void* feats, const void* pos, const int64_t* img_ids,
+                   const void* dout, const VlpetK3LRParams* w, const float* save, const VlpetK3LRGrads* g, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* ---- token-contracted weight-gradient GEMM (building block of the fused backward) -----------------------
  * out_p[c, n] += scale_p * sum_tok A_p[tok, c] * B_p[tok, n]   (transposed_p: out_p[n, c] instead), up to 4 pairs per
  * launch, bf16 operands, fp32 accumulate on the tensor cores (tcgen05), fp32 reductions into out.  These are the dW

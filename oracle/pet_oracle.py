@@ -311,3 +311,82 @@ def visproj_bwd(dout, p, c, rms: bool = False):
     np.add.at(E, c["img_ids"].reshape(-1), dout.reshape(-1, d))
     gr["E_img"] = E
     return df @ p["Wf"], gr
+
+
+# --------------------------------------------------------------------------------------------------------
+# K3-LR: the PET-shaped visual projector (flag-gated: --use_lowrank_visual_projector)
+# --------------------------------------------------------------------------------------------------------
+def lowrank_visproj_fwd(feats, pos, p, img_order_ids=None, obj_order_ids=None, gated: bool = True,
+                        residual: bool = False, eps: float = 1e-5):
+    """LowRankVisualEmbedding.forward (src/modeling_bart.py:263-334):
+
+        e   = Up(gelu_new(cat_h Down_h(feats)))                                         (275-281)
+        e   = e (+ e) * sigmoid(GUp(gelu_new(GDown(feats))))   with the gate flag        (283-293)
+        out = LN(e) + LN([pos, area] Wp^T + bp) + E_img[img_ids] + E_obj[V-1-obj_ids]   (296-327)
+
+    p: Wd [r,F] (row-concatenated heads), bd, Wu [d,r], bu, (Gd [rg,F], gbd, Gu [d,rg], gbu), ln_f_w, ln_f_b
+    (visual_projector_layer_norm), Wp, bp, ln_p_w, ln_p_b, E_img, E_obj."""
+    B, N, F = feats.shape
+    f2 = feats.reshape(-1, F)
+    a = f2 @ p["Wd"].T + p["bd"]
+    z = gelu_new(a)
+    u = z @ p["Wu"].T + p["bu"]
+    c = dict(f2=f2, a=a, z=z, u=u)
+    if gated:
+        pp = f2 @ p["Gd"].T + p["gbd"]
+        q = gelu_new(pp)
+        G = sigmoid(q @ p["Gu"].T + p["gbu"])
+        e = u + u * G if residual else u * G
+        c.update(p=pp, q=q, G=G)
+    else:
+        e = u
+    e = e.reshape(B, N, -1)
+    area = ((pos[:, :, 3] - pos[:, :, 2]) * (pos[:, :, 1] - pos[:, :, 0]))[:, :, None]
+    pos5 = np.concatenate([pos, area], axis=2)
+    apos = pos5 @ p["Wp"].T + p["bp"]
+    fe, cf = layer_norm_fwd(e, p["ln_f_w"], p["ln_f_b"], eps)
+    ae, ca = layer_norm_fwd(apos, p["ln_p_w"], p["ln_p_b"], eps)
+    if img_order_ids is None:
+        img_order_ids = np.zeros((1, N), dtype=np.int64)
+    if obj_order_ids is None:
+        obj_order_ids = np.arange(N, dtype=np.int64)[None]
+    V = p["E_obj"].shape[0]
+    out = fe + ae + p["E_img"][img_order_ids] + p["E_obj"][V - obj_order_ids - 1]
+    c.update(pos5=pos5, cf=cf, ca=ca, img_ids=np.broadcast_to(img_order_ids, (B, N)), gated=gated, residual=residual)
+    return out, c
+
+
+def lowrank_visproj_bwd(dout, p, c):
+    """Grads of every trainable parameter of the low-rank visual projector.  Returns (dfeats, grads)."""
+    gr = {}
+    d = dout.shape[-1]
+    de, gr["ln_f_w"], gr["ln_f_b"] = layer_norm_bwd(dout, p["ln_f_w"], c["cf"])
+    da_pos, gr["ln_p_w"], gr["ln_p_b"] = layer_norm_bwd(dout, p["ln_p_w"], c["ca"])
+    de = de.reshape(-1, d)
+    da_pos = da_pos.reshape(-1, d)
+    gr["Wp"] = da_pos.T @ c["pos5"].reshape(da_pos.shape[0], -1)
+    gr["bp"] = da_pos.sum(0)
+    E = np.zeros_like(p["E_img"])
+    np.add.at(E, c["img_ids"].reshape(-1), dout.reshape(-1, d))
+    gr["E_img"] = E
+    f2 = c["f2"]
+    dfeats = 0.0
+    if c["gated"]:
+        G, u = c["G"], c["u"]
+        du = de * (1.0 + G) if c["residual"] else de * G
+        dt = de * u * G * (1.0 - G)
+        gr["Gu"] = dt.T @ c["q"]
+        gr["gbu"] = dt.sum(0)
+        dp = (dt @ p["Gu"]) * gelu_new_grad(c["p"])
+        gr["Gd"] = dp.T @ f2
+        gr["gbd"] = dp.sum(0)
+        dfeats = dp @ p["Gd"]
+    else:
+        du = de
+    gr["Wu"] = du.T @ c["z"]
+    gr["bu"] = du.sum(0)
+    da = (du @ p["Wu"]) * gelu_new_grad(c["a"])
+    gr["Wd"] = da.T @ f2
+    gr["bd"] = da.sum(0)
+    dfeats = dfeats + da @ p["Wd"]
+    return dfeats.reshape(dout.shape[0], dout.shape[1], -1), gr

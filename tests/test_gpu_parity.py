@@ -553,3 +553,54 @@ def test_gelu_dropout_kernels(V):
     assert abs((y2.float()[kept] / base[kept]).median().item() - 1 / 0.75) < 0.02
     sigb = sig & (dy.float().abs() > 0.05) & (xr.grad.float().abs() > 1e-2)
     assert torch.equal((x.grad == 0)[sigb], dropped[sigb])          # same mask forward and backward
+
+
+@pytest.mark.parametrize("path", golden_files("k3lr_"), ids=os.path.basename)
+def test_k3_lowrank_projector_matches_reference_golden(V, path):
+    """SURVEY §8 row a7 through the module mirror: vlpet_b200.LowRankVisualEmbedding (reference parameter names) in fp32
+    against golden vectors of the reference's LowRankVisualEmbedding: output and every parameter gradient at 1e-5."""
+    g = load(path)
+    import types
+    B, N, Fd = g["feats"].shape
+    d = g["out"].shape[-1]
+    heads, gated = int(g["meta_heads"]), bool(int(g["meta_gated"]))
+    cfg = types.SimpleNamespace(d_model=d, feat_dim=Fd, pos_dim=4, n_images=2, visual_projector_multihead_num_head=heads,
+                                visual_projector_down_dim=g["Wd"].shape[0], use_visual_projector_gating_large_x_lowrank=gated,
+                                visual_projector_gating_down_dim=g["Gd"].shape[0] if gated else 0,
+                                use_visual_projector_residual_connection=bool(int(g["meta_residual"])))
+    emb = torch.nn.Embedding(g["E_obj"].shape[0], d)
+    ve = V.LowRankVisualEmbedding(cfg, emb).cuda()
+    assert [n for n, _ in ve.named_parameters()] == list(g["meta_param_names"])
+    hr = g["Wd"].shape[0] // heads
+    t32 = torch.float32
+    with torch.no_grad():
+        for h in range(heads):
+            ve.visual_projector_multihead_down[h].weight.copy_(dev(g["Wd"][h * hr:(h + 1) * hr], t32))
+            ve.visual_projector_multihead_down[h].bias.copy_(dev(g["bd"][h * hr:(h + 1) * hr], t32))
+        ve.visual_projector_multihead_up.weight.copy_(dev(g["Wu"], t32)); ve.visual_projector_multihead_up.bias.copy_(dev(g["bu"], t32))
+        if gated:
+            ve.visual_projector_gating_large_x_down.weight.copy_(dev(g["Gd"], t32)); ve.visual_projector_gating_large_x_down.bias.copy_(dev(g["gbd"], t32))
+            ve.visual_projector_gating_large_x_up.weight.copy_(dev(g["Gu"], t32)); ve.visual_projector_gating_large_x_up.bias.copy_(dev(g["gbu"], t32))
+        ve.visual_projector_layer_norm.weight.copy_(dev(g["ln_f_w"], t32)); ve.visual_projector_layer_norm.bias.copy_(dev(g["ln_f_b"], t32))
+        pe = ve.absolute_vis_pos_embedding
+        pe[0].weight.copy_(dev(g["Wp"], t32)); pe[0].bias.copy_(dev(g["bp"], t32))
+        pe[1].weight.copy_(dev(g["ln_p_w"], t32)); pe[1].bias.copy_(dev(g["ln_p_b"], t32))
+        ve.img_order_embedding.weight.copy_(dev(g["E_img"], t32)); ve.obj_order_embedding.weight.copy_(dev(g["E_obj"], t32))
+    img = torch.tensor(g["img_ids"], device="cuda") if "img_ids" in g else None
+    obj = torch.tensor(g["obj_ids"], device="cuda") if "obj_ids" in g else None
+    out = ve(dev(g["feats"], t32), dev(g["pos"], t32), img, obj)
+    out.backward(dev(g["dout"], t32))
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    assert rel(f(out), g["out"]) < TOL_F32
+    got = {"Wd": np.concatenate([f(h.weight.grad) for h in ve.visual_projector_multihead_down]),
+           "bd": np.concatenate([f(h.bias.grad) for h in ve.visual_projector_multihead_down]),
+           "Wu": f(ve.visual_projector_multihead_up.weight.grad), "bu": f(ve.visual_projector_multihead_up.bias.grad),
+           "ln_f_w": f(ve.visual_projector_layer_norm.weight.grad), "ln_f_b": f(ve.visual_projector_layer_norm.bias.grad),
+           "Wp": f(pe[0].weight.grad), "bp": f(pe[0].bias.grad), "ln_p_w": f(pe[1].weight.grad), "ln_p_b": f(pe[1].bias.grad),
+           "E_img": f(ve.img_order_embedding.weight.grad)}
+    if gated:
+        got.update(Gd=f(ve.visual_projector_gating_large_x_down.weight.grad), gbd=f(ve.visual_projector_gating_large_x_down.bias.grad),
+                   Gu=f(ve.visual_projector_gating_large_x_up.weight.grad), gbu=f(ve.visual_projector_gating_large_x_up.bias.grad))
+    for k, v in got.items():
+        assert rel(v, g["d" + k]) < TOL_F32, k
+    assert ve.obj_order_embedding.weight.grad is None        # aliases the frozen token table

@@ -88,3 +88,21 @@ def test_multihead_down_is_one_linear():
     W, b = O.stack_heads(Ws, bs)
     ref = np.concatenate([x @ w.T + bb for w, bb in zip(Ws, bs)], axis=-1)
     assert np.allclose(x @ W.T + b, ref, atol=1e-14)
+
+
+LR_KEYS = ["Wd", "bd", "Wu", "bu", "ln_f_w", "ln_f_b", "Wp", "bp", "ln_p_w", "ln_p_b", "E_img", "E_obj"]
+
+
+@pytest.mark.parametrize("path", golden_files("k3lr_"), ids=os.path.basename)
+def test_lowrank_visual_projector_matches_reference(path):
+    """LowRankVisualEmbedding (src/modeling_bart.py:195-334)."""
+    g = load(path)
+    gated, residual = bool(int(g["meta_gated"])), bool(int(g["meta_residual"]))
+    p = {k: g[k] for k in LR_KEYS + (["Gd", "gbd", "Gu", "gbu"] if gated else [])}
+    out, c = O.lowrank_visproj_fwd(g["feats"], g["pos"], p, g.get("img_ids"), g.get("obj_ids"), gated=gated, residual=residual)
+    assert rel(out, g["out"]) < TOL
+    dfeats, gr = O.lowrank_visproj_bwd(g["dout"], p, c)
+    assert rel(dfeats, g["dfeats"]) < TOL
+    assert set(gr) == set(p) - {"E_obj"}
+    for k, v in gr.items():
+        assert rel(v, g["d" + k]) < TOL, k

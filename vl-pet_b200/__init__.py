@@ -9,10 +9,10 @@ from ._lib import LIB_PATH, VlpetError, launch_count
 from .functional import PetSiteConfig, gated_pet, vpa, visual_projection, fwd_is_fused, grid_maxpool, layer_norm
 from .adapters import AdapterConfig, Activations, Adapter, AdapterController
 from .encoder import encoder_pet, gate_kind, patch_layer, patch_reference_model, site_config, site_params
-from .visual import VisualEmbedding, T5LayerNorm, adopt_reference_visual_embedding
+from .visual import VisualEmbedding, LowRankVisualEmbedding, T5LayerNorm, adopt_reference_visual_embedding
 from . import host
 
 __all__ = ["LIB_PATH", "VlpetError", "launch_count", "PetSiteConfig", "gated_pet", "vpa", "visual_projection",
            "fwd_is_fused", "grid_maxpool", "layer_norm", "AdapterConfig", "Activations", "Adapter", "AdapterController", "encoder_pet", "gate_kind",
-           "patch_layer", "patch_reference_model", "site_config", "site_params", "VisualEmbedding", "T5LayerNorm",
+           "patch_layer", "patch_reference_model", "site_config", "site_params", "VisualEmbedding", "LowRankVisualEmbedding", "T5LayerNorm",
            "adopt_reference_visual_embedding"]

@@ -67,6 +67,26 @@ class K3Grads(C.Structure):
     _fields_ = [(n, _fp) for n in ("dWf", "dbf", "dln_f_w", "dln_f_b", "dWp", "dbp", "dln_p_w", "dln_p_b", "dE_img")]
 
 
+class K3LRDesc(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("F", C.c_int32), ("d", C.c_int32), ("r", C.c_int32), ("rg", C.c_int32),
+                ("V", C.c_int32), ("n_img", C.c_int32), ("gated", C.c_int32), ("residual", C.c_int32), ("dtype", C.c_int32),
+                ("impl", C.c_int32), ("eps", C.c_float)]
+
+
+K3LR_PARAM_NAMES = ("Wd", "bd", "Wu", "bu", "Gd", "gbd", "Gu", "gbu", "ln_f_w", "ln_f_b", "Wp", "bp", "ln_p_w", "ln_p_b",
+                    "E_img", "E_obj")
+K3LR_GRAD_NAMES = ("dWd", "dbd", "dWu", "dbu", "dGd", "dgbd", "dGu", "dgbu", "dln_f_w", "dln_f_b", "dWp", "dbp", "dln_p_w",
+                   "dln_p_b", "dE_img")
+
+
+class K3LRParams(C.Structure):
+    _fields_ = [(n, _vp) for n in K3LR_PARAM_NAMES]
+
+
+class K3LRGrads(C.Structure):
+    _fields_ = [(n, _fp) for n in K3LR_GRAD_NAMES]
+
+
 # every symbol include/vlpet.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vlpet_k1_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(K1Desc)]),
@@ -89,6 +109,11 @@ SYMBOLS = {
                                _vp]),
     "vlpet_k3_bwd": (C.c_int, [C.POINTER(K3Desc), _vp, _vp, _vp, _vp, C.POINTER(K3Params), _vp, _vp,
                                C.POINTER(K3Grads), _vp, C.c_size_t, _vp]),
+    "vlpet_k3lr_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(K3LRDesc)]),
+    "vlpet_k3lr_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(K3LRDesc)]),
+    "vlpet_k3lr_fwd": (C.c_int, [C.POINTER(K3LRDesc), _vp, _vp, _vp, _vp, C.POINTER(K3LRParams), _vp, _vp, _vp, C.c_size_t, _vp]),
+    "vlpet_k3lr_bwd": (C.c_int, [C.POINTER(K3LRDesc), _vp, _vp, _vp, _vp, C.POINTER(K3LRParams), _vp, C.POINTER(K3LRGrads), _vp,
+                                 C.c_size_t, _vp]),
     "vlpet_wgrad_bf16": (C.c_int, [C.POINTER(WgradPair), C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp]),
     "vlpet_layernorm_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_int32, _vp]),
     "vlpet_layernorm_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp]),

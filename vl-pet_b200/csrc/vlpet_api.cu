@@ -100,6 +100,33 @@ int vlpet_k1_bwd(const VlpetK1Desc* D, const void* x1, const void* x2, const voi
   return generic_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+// ---- K3-LR ---------------------------------------------------------------------------------------------------
+static int check_k3lr(const VlpetK3LRDesc* D, const VlpetK3LRParams* w) {
+  if (!D || !w) return fail(VLPET_E_BADARG, "k3lr: null desc/params");
+  if (D->M <= 0 || D->d <= 0 || D->F <= 0 || D->N <= 0 || D->V <= 0 || D->n_img <= 0 || D->r <= 0 || (D->gated && D->rg <= 0))
+    return fail(VLPET_E_BADARG, "k3lr: sizes must be positive");
+  if (D->dtype != VLPET_F32 && D->dtype != VLPET_BF16) return fail(VLPET_E_BADARG, "k3lr: bad dtype %d", D->dtype);
+  if (!w->Wd || !w->bd || !w->Wu || !w->bu || !w->ln_f_w || !w->ln_f_b || !w->Wp || !w->bp || !w->ln_p_w || !w->ln_p_b ||
+      !w->E_img || !w->E_obj || (D->gated && (!w->Gd || !w->gbd || !w->Gu || !w->gbu)))
+    return fail(VLPET_E_BADARG, "k3lr: weights missing");
+  if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k3lr: only the generic CUDA path exists");
+  return 0;
+}
+size_t vlpet_k3lr_fwd_workspace_bytes(const VlpetK3LRDesc* D) { return D ? generic_k3lr_fwd_ws(*D) : 0; }
+size_t vlpet_k3lr_bwd_workspace_bytes(const VlpetK3LRDesc* D) { return D ? generic_k3lr_bwd_ws(*D) : 0; }
+int vlpet_k3lr_fwd(const VlpetK3LRDesc* D, const void* feats, const void* pos, const int64_t* img_ids, const int64_t* obj_ids,
+                   const VlpetK3LRParams* w, void* out, float* save, void* ws, size_t ws_bytes, void* stream) {
+  VLPET_TRY(check_k3lr(D, w));
+  if (!feats || !pos || !out || !save) return fail(VLPET_E_BADARG, "k3lr_fwd: null pointer");
+  return generic_k3lr_fwd(*D, feats, pos, img_ids, obj_ids, *w, out, save, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int vlpet_k3lr_bwd(const VlpetK3LRDesc* D, const void* feats, const void* pos, const int64_t* img_ids, const void* dout,
+                   const VlpetK3LRParams* w, const float* save, const VlpetK3LRGrads* g, void* ws, size_t ws_bytes, void* stream) {
+  VLPET_TRY(check_k3lr(D, w));
+  if (!feats || !pos || !dout || !save || !g) return fail(VLPET_E_BADARG, "k3lr_bwd: null pointer");
+  return generic_k3lr_bwd(*D, feats, pos, img_ids, dout, *w, save, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
 // ---- LayerNorm behind the PET sites --------------------------------------------------------------------------
 int vlpet_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int64_t M, int32_t d,
                         float eps, int32_t dtype, void* stream) {

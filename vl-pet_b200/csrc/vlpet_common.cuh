@@ -131,6 +131,12 @@ int generic_k3_fwd(const VlpetK3Desc&, const void* feats, const void* pos, const
 int generic_k3_bwd(const VlpetK3Desc&, const void* feats, const void* pos, const int64_t* img_ids, const void* dout,
                    const VlpetK3Params&, const float* save, void* dfeats, const VlpetK3Grads&, void* ws,
                    size_t ws_bytes, cudaStream_t);
+size_t generic_k3lr_fwd_ws(const VlpetK3LRDesc&);
+size_t generic_k3lr_bwd_ws(const VlpetK3LRDesc&);
+int generic_k3lr_fwd(const VlpetK3LRDesc&, const void* feats, const void* pos, const int64_t* img_ids, const int64_t* obj_ids,
+                     const VlpetK3LRParams&, void* out, float* save, void* ws, size_t ws_bytes, cudaStream_t);
+int generic_k3lr_bwd(const VlpetK3LRDesc&, const void* feats, const void* pos, const int64_t* img_ids, const void* dout,
+                     const VlpetK3LRParams&, const float* save, const VlpetK3LRGrads&, void* ws, size_t ws_bytes, cudaStream_t);
 size_t generic_k3_fwd_ws(const VlpetK3Desc&);
 size_t generic_k3_bwd_ws(const VlpetK3Desc&);
 

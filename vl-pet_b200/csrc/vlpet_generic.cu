@@ -808,4 +808,149 @@ int generic_k3_bwd(const VlpetK3Desc& D, const void* feats, const void* pos, con
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// K3-LR: PET-shaped visual projector (src/modeling_bart.py:263-334)
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+// E <- U * G  |  U + U * G   with G = sigmoid(T)      (forward; E may alias U)
+__global__ void lr_gate_fwd_kernel(const float* U, const float* T, float* E, int64_t n, int residual) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float g = sigmoid_f(T[i]), u = U[i];
+    E[i] = residual ? u + u * g : u * g;
+  }
+}
+// U <- dU = dE * (G | 1 + G),  T <- dT = dE * U * G (1 - G)      (backward, in place)
+__global__ void lr_gate_bwd_kernel(const float* dE, float* U, float* T, int64_t n, int residual) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float g = sigmoid_f(T[i]), u = U[i], de = dE[i];
+    U[i] = residual ? de * (1.0f + g) : de * g;
+    T[i] = de * u * g * (1.0f - g);
+  }
+}
+VlpetK3Params lr_row_params(const VlpetK3LRParams& w) {
+  VlpetK3Params k;
+  memset(&k, 0, sizeof(k));
+  k.ln_f_w = w.ln_f_w; k.ln_f_b = w.ln_f_b; k.Wp = w.Wp; k.bp = w.bp; k.ln_p_w = w.ln_p_w; k.ln_p_b = w.ln_p_b;
+  k.E_img = w.E_img; k.E_obj = w.E_obj;
+  return k;
+}
+}  // namespace
+
+size_t generic_k3lr_fwd_ws(const VlpetK3LRDesc& D) {
+  Arena a(nullptr, 0);
+  a.take<float>(D.M * D.r);
+  if (D.gated) { a.take<float>(D.M * D.rg); a.take<float>(D.M * D.d); }
+  return a.off;
+}
+size_t generic_k3lr_bwd_ws(const VlpetK3LRDesc& D) {
+  Arena a(nullptr, 0);
+  a.take<float>(D.M * D.r); a.take<float>(D.M * D.r); a.take<float>(D.M * D.d); a.take<float>(D.M * D.r);   // Apre Z U DZ
+  if (D.gated) { a.take<float>(D.M * D.rg); a.take<float>(D.M * D.rg); a.take<float>(D.M * D.d); a.take<float>(D.M * D.rg); }
+  for (int i = 0; i < 4; ++i) a.take<float>(D.M * D.d);   // dE dApos XF XA
+  a.take<float>(D.M * 5);
+  return a.off;
+}
+
+int generic_k3lr_fwd(const VlpetK3LRDesc& D, const void* feats, const void* pos, const int64_t* img_ids,
+                     const int64_t* obj_ids, const VlpetK3LRParams& w, void* out, float* save, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  const int bf = D.dtype == VLPET_BF16;
+  const int64_t M = D.M;
+  Arena a(ws, ws_bytes);
+  float* Z = a.take<float>(M * D.r);
+  float *Q = nullptr, *T = nullptr;
+  if (D.gated) { Q = a.take<float>(M * D.rg); T = a.take<float>(M * D.d); }
+  if (!a.ok()) return fail(VLPET_E_WORKSPACE, "k3lr_fwd: workspace %zu < %zu bytes", ws_bytes, a.off);
+  GemmArgs g = linear_nt(feats, bf, w.Wd, w.bd, bf, Z, 0, M, D.r, D.F);
+  g.act = 1;
+  VLPET_TRY(launch_gemm(g, st));
+  VLPET_TRY(launch_gemm(linear_nt(Z, 0, w.Wu, w.bu, bf, save, 0, M, D.d, D.r), st));
+  if (D.gated) {
+    g = linear_nt(feats, bf, w.Gd, w.gbd, bf, Q, 0, M, D.rg, D.F);
+    g.act = 1;
+    VLPET_TRY(launch_gemm(g, st));
+    VLPET_TRY(launch_gemm(linear_nt(Q, 0, w.Gu, w.gbu, bf, T, 0, M, D.d, D.rg), st));
+    lr_gate_fwd_kernel<<<ew_blocks(M * D.d), 256, 0, st>>>(save, T, save, M * D.d, D.residual);
+    VLPET_LAUNCH_OK();
+  }
+  visproj_row_kernel<<<warp_rows_blocks(M), 256, 0, st>>>(save, pos, bf, img_ids, obj_ids, lr_row_params(w), M, D.N, D.d, D.V, 0,
+                                                         D.eps, out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                         nullptr);
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+
+int generic_k3lr_bwd(const VlpetK3LRDesc& D, const void* feats, const void* pos, const int64_t* img_ids, const void* dout,
+                     const VlpetK3LRParams& w, const float* save, const VlpetK3LRGrads& G, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  const int bf = D.dtype == VLPET_BF16;
+  const int64_t M = D.M;
+  const int d = D.d, r = D.r, rg = D.rg;
+  Arena a(ws, ws_bytes);
+  float* Apre = a.take<float>(M * r);
+  float* Z = a.take<float>(M * r);
+  float* U = a.take<float>(M * d);
+  float* DZ = a.take<float>(M * r);
+  float *Ppre = nullptr, *Q = nullptr, *T = nullptr, *DQ = nullptr;
+  if (D.gated) { Ppre = a.take<float>(M * rg); Q = a.take<float>(M * rg); T = a.take<float>(M * d); DQ = a.take<float>(M * rg); }
+  float* dE = a.take<float>(M * d);
+  float* dA = a.take<float>(M * d);
+  float* XF = a.take<float>(M * d);
+  float* XA = a.take<float>(M * d);
+  float* P5 = a.take<float>(M * 5);
+  if (!a.ok()) return fail(VLPET_E_WORKSPACE, "k3lr_bwd: workspace %zu < %zu bytes", ws_bytes, a.off);
+  // LayerNorm / position / order-embedding part: identical to K3 with `save` = e
+  visproj_row_kernel<<<warp_rows_blocks(M), 256, 0, st>>>(save, pos, bf, img_ids, nullptr, lr_row_params(w), M, D.N, d, D.V, 0,
+                                                         D.eps, nullptr, dout, dE, dA, XF, XA, P5, nullptr);
+  VLPET_LAUNCH_OK();
+  VLPET_TRY(launch_colsum(dout, bf, XF, 0, nullptr, 0, M, d, 1.f, G.dln_f_w, st));
+  VLPET_TRY(launch_colsum(dout, bf, XA, 0, nullptr, 0, M, d, 1.f, G.dln_p_w, st));
+  VLPET_TRY(launch_colsum(dout, bf, nullptr, 0, nullptr, 0, M, d, 1.f, G.dln_f_b, st));
+  VLPET_TRY(launch_colsum(dout, bf, nullptr, 0, nullptr, 0, M, d, 1.f, G.dln_p_b, st));
+  VLPET_TRY(launch_wgrad(dA, 0, d, P5, 0, 5, M, G.dWp, 1.f, st));
+  VLPET_TRY(launch_colsum(dA, 0, nullptr, 0, nullptr, 0, M, d, 1.f, G.dbp, st));
+  if (G.dE_img) {
+    for (int i = 0; i < D.n_img; ++i) {
+      if (img_ids == nullptr && i > 0) break;
+      VLPET_TRY(launch_colsum(dout, bf, nullptr, 0, img_ids, i, M, d, 1.f, G.dE_img + (size_t)i * d, st));
+    }
+  }
+  // recompute the projector
+  GemmArgs g = linear_nt(feats, bf, w.Wd, w.bd, bf, Z, 0, M, r, D.F);
+  g.act = 1;
+  g.pre = Apre;
+  VLPET_TRY(launch_gemm(g, st));
+  VLPET_TRY(launch_gemm(linear_nt(Z, 0, w.Wu, w.bu, bf, U, 0, M, d, r), st));
+  const float* dU = dE;
+  if (D.gated) {
+    g = linear_nt(feats, bf, w.Gd, w.gbd, bf, Q, 0, M, rg, D.F);
+    g.act = 1;
+    g.pre = Ppre;
+    VLPET_TRY(launch_gemm(g, st));
+    VLPET_TRY(launch_gemm(linear_nt(Q, 0, w.Gu, w.gbu, bf, T, 0, M, d, rg), st));
+    lr_gate_bwd_kernel<<<ew_blocks(M * d), 256, 0, st>>>(dE, U, T, M * d, D.residual);
+    VLPET_LAUNCH_OK();
+    dU = U;
+    VLPET_TRY(launch_wgrad(T, 0, d, Q, 0, rg, M, G.dGu, 1.f, st));
+    VLPET_TRY(launch_colsum(T, 0, nullptr, 0, nullptr, 0, M, d, 1.f, G.dgbu, st));
+    VLPET_TRY(launch_gemm(linear_nn(T, 0, w.Gu, bf, DQ, 0, M, d, rg), st));
+    mul_gelu_grad_kernel<<<ew_blocks(M * rg), 256, 0, st>>>(DQ, Ppre, M * rg);
+    VLPET_LAUNCH_OK();
+    VLPET_TRY(launch_wgrad(DQ, 0, rg, feats, bf, D.F, M, G.dGd, 1.f, st));
+    VLPET_TRY(launch_colsum(DQ, 0, nullptr, 0, nullptr, 0, M, rg, 1.f, G.dgbd, st));
+  }
+  VLPET_TRY(launch_wgrad(dU, 0, d, Z, 0, r, M, G.dWu, 1.f, st));
+  VLPET_TRY(launch_colsum(dU, 0, nullptr, 0, nullptr, 0, M, d, 1.f, G.dbu, st));
+  VLPET_TRY(launch_gemm(linear_nn(dU, 0, w.Wu, bf, DZ, 0, M, d, r), st));
+  mul_gelu_grad_kernel<<<ew_blocks(M * r), 256, 0, st>>>(DZ, Apre, M * r);
+  VLPET_LAUNCH_OK();
+  VLPET_TRY(launch_wgrad(DZ, 0, r, feats, bf, D.F, M, G.dWd, 1.f, st));
+  VLPET_TRY(launch_colsum(DZ, 0, nullptr, 0, nullptr, 0, M, r, 1.f, G.dbd, st));
+  return 0;
+}
+
 }  // namespace vlpet

@@ -440,6 +440,75 @@ def visual_projection(feats, pos, img_order_ids, obj_order_ids, Wf, bf, ln_f_w, 
                            Wp, bp, ln_p_w, ln_p_b, E_img, E_obj.detach())
 
 
+class LowRankVisProjFn(torch.autograd.Function):
+    """LowRankVisualEmbedding.forward (src/modeling_bart.py:263-334) -- include/vlpet.h K3-LR.  Parameter order:
+    Wd (row-concatenated heads), bd, Wu, bu, Gd, gbd, Gu, gbu (None x4 when not gated), ln_f_w, ln_f_b, Wp, bp, ln_p_w,
+    ln_p_b, E_img, E_obj."""
+
+    @staticmethod
+    def forward(ctx, gated: bool, residual: bool, eps: float, feats, pos, img_ids, obj_ids, *params):
+        _require_cuda(feats, pos)
+        if feats.dim() != 3 or feats.dtype not in _DT or len(params) != 16:
+            raise ValueError("vlpet.lowrank_visual_projection: feats must be [B, N, F] fp32/bf16 with 16 parameter slots")
+        B, N, Fd = feats.shape
+        dt = feats.dtype
+        fc, pc = feats.contiguous(), pos.to(dt).contiguous()
+        ids = lambda t: None if t is None else t.to(torch.int64).expand(B, N).contiguous()  # noqa: E731
+        img, obj = ids(img_ids), ids(obj_ids)
+        ws_ = [_as(t, dt) for t in params]
+        d, r = ws_[2].shape[0], ws_[0].shape[0]
+        rg = ws_[4].shape[0] if gated else 0
+        desc = L.K3LRDesc(M=B * N, N=N, F=Fd, d=d, r=r, rg=rg, V=params[15].shape[0], n_img=params[14].shape[0],
+                          gated=int(gated), residual=int(residual), dtype=_DT[dt], impl=L.IMPL_AUTO, eps=eps)
+        w = L.K3LRParams(*[_p(t) for t in ws_])
+        out = torch.empty(B, N, d, dtype=dt, device=feats.device)
+        save = torch.empty(B * N * d, dtype=torch.float32, device=feats.device)
+        ws = _workspace(L.lib.vlpet_k3lr_fwd_workspace_bytes(C.byref(desc)), feats.device)
+        L.check(L.lib.vlpet_k3lr_fwd(C.byref(desc), _p(fc), _p(pc), _p(img), _p(obj), C.byref(w), _p(out), _p(save), _p(ws),
+                                     ws.numel(), _stream()), "vlpet_k3lr_fwd")
+        ctx.desc = desc
+        ctx.present = [t is not None for t in ws_]
+        ctx.param_meta = [None if t is None else (tuple(t.shape), t.dtype) for t in params]
+        ctx.save_for_backward(fc, pc, img, save, *[t for t in ws_ if t is not None])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        fc, pc, img, save, *rest = ctx.saved_tensors
+        it = iter(rest)
+        ws_ = [next(it) if p else None for p in ctx.present]
+        desc = ctx.desc
+        dout = dout.contiguous()
+        if dout.dtype != fc.dtype:
+            dout = dout.to(fc.dtype)
+        sizes = [0 if m is None else int(torch.Size(m[0]).numel()) for m in ctx.param_meta[:15]]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 3) // 4 * 4)
+        gbuf = torch.zeros(max(offs[-1], 4), dtype=torch.float32, device=fc.device)
+        gv = [gbuf[offs[i]:offs[i] + sizes[i]] if sizes[i] else None for i in range(15)]
+        g = L.K3LRGrads(*[_p(t) for t in gv])
+        w = L.K3LRParams(*[_p(t) for t in ws_])
+        ws = _workspace(L.lib.vlpet_k3lr_bwd_workspace_bytes(C.byref(desc)), fc.device)
+        L.check(L.lib.vlpet_k3lr_bwd(C.byref(desc), _p(fc), _p(pc), _p(img), _p(dout), C.byref(w), _p(save), C.byref(g), _p(ws),
+                                     ws.numel(), _stream()), "vlpet_k3lr_bwd")
+        outg = []
+        for gt, meta in zip(gv, ctx.param_meta[:15]):
+            if meta is None:
+                outg.append(None)
+            else:
+                gt = gt.reshape(meta[0])
+                outg.append(gt if meta[1] == torch.float32 else gt.to(meta[1]))
+        return (None, None, None, None, None, None, None, *outg, None)
+
+
+def lowrank_visual_projection(feats, pos, img_order_ids, obj_order_ids, params, gated: bool, residual: bool, eps: float = 1e-5):
+    """params: the 16 tensors of LowRankVisProjFn (gate slots None when not gated).  Features are inputs: no dfeats."""
+    params = list(params)
+    params[15] = params[15].detach()
+    return LowRankVisProjFn.apply(bool(gated), bool(residual), float(eps), feats, pos, img_order_ids, obj_order_ids, *params)
+
+
 class LayerNormFn(torch.autograd.Function):
     """nn.LayerNorm on bf16 activations with fp32 affine parameters (include/vlpet.h vlpet_layernorm_fwd / _bwd)."""
 

@@ -76,3 +76,51 @@ def adopt_reference_visual_embedding(module: nn.Module) -> nn.Module:
         raise NotImplementedError("vlpet: unexpected VisualEmbedding layout")
     module.forward = types.MethodType(_forward, module)
     return module
+
+
+class LowRankVisualEmbedding(nn.Module):
+    """Mirror of the reference's PET-shaped visual projector (src/modeling_bart.py:195-334, --use_lowrank_visual_projector):
+    same constructor ``(config, obj_order_embedding)``, same parameter names (``visual_projector_multihead_down.{h}``,
+    ``visual_projector_multihead_up``, ``visual_projector_gating_large_x_{down,up}``, ``visual_projector_layer_norm``,
+    ``absolute_vis_pos_embedding.0/.1``, ``img_order_embedding``), forward through include/vlpet.h K3-LR."""
+
+    def __init__(self, config, obj_order_embedding: nn.Embedding):
+        super().__init__()
+        _check_flags(config)
+        self.config = config
+        d, F = config.d_model, config.feat_dim
+        h = config.visual_projector_multihead_num_head
+        r = config.visual_projector_down_dim
+        self.embed_dim = d
+        self.visual_projector_multihead_dim = int(r / h)
+        self.visual_projector_multihead_down = nn.ModuleList([nn.Linear(F, self.visual_projector_multihead_dim) for _ in range(h)])
+        self.visual_projector_multihead_up = nn.Linear(r, d)
+        self.gated = bool(getattr(config, "use_visual_projector_gating_large_x_lowrank", False))
+        if self.gated:
+            rg = config.visual_projector_gating_down_dim
+            self.visual_projector_gating_large_x_down = nn.Linear(F, rg)
+            self.visual_projector_gating_large_x_up = nn.Linear(rg, d)
+        self.visual_projector_layer_norm = nn.LayerNorm(d)
+        self.absolute_vis_pos_embedding = nn.Sequential(nn.Linear(config.pos_dim + 1, d), nn.LayerNorm(d))
+        self.obj_order_embedding = obj_order_embedding
+        self.img_order_embedding = nn.Embedding(config.n_images, d)
+        self.default_obj_order_ids = getattr(config, "default_obj_order_ids", None)
+
+    def forward(self, feats, pos, img_order_ids=None, obj_order_ids=None):
+        B, N, _ = feats.size()
+        assert pos.size() == (B, N, 4)
+        down = self.visual_projector_multihead_down
+        # the multi-head down projection is ONE Linear whose weight is the row-concatenation of the heads (SURVEY F4);
+        # the differentiable cat hands autograd the per-head gradient slices
+        Wd = down[0].weight if len(down) == 1 else torch.cat([h.weight for h in down], dim=0)
+        bd = down[0].bias if len(down) == 1 else torch.cat([h.bias for h in down], dim=0)
+        gate = (self.visual_projector_gating_large_x_down.weight, self.visual_projector_gating_large_x_down.bias,
+                self.visual_projector_gating_large_x_up.weight, self.visual_projector_gating_large_x_up.bias) \
+            if self.gated else (None, None, None, None)
+        ln, pe = self.visual_projector_layer_norm, self.absolute_vis_pos_embedding
+        params = (Wd, bd, self.visual_projector_multihead_up.weight, self.visual_projector_multihead_up.bias, *gate,
+                  ln.weight, ln.bias, pe[0].weight, pe[0].bias, pe[1].weight, pe[1].bias, self.img_order_embedding.weight,
+                  self.obj_order_embedding.weight)
+        return F_.lowrank_visual_projection(feats, pos, img_order_ids, obj_order_ids, params, self.gated,
+                                            bool(getattr(self.config, "use_visual_projector_residual_connection", False)),
+                                            eps=ln.eps)
