@@ -37,5 +37,20 @@ def run(M):
         for c in range(12):
             a, b, cc, dd = rel[3 + 4 * c], rel[4 + 4 * c], rel[5 + 4 * c], rel[6 + 4 * c]
             print(f"    chunk {c:2d}: UT ready {a:7d}  tmem read {b - a:5d}  wait x {cc - b:6d}  math {dd - cc:6d}  -> {dd}")
+    if M >= 128 * 148 * 2:
+        import numpy as np
+        t0 = t[:, 0][t[:, 0] > 0].min()
+        ends = t[:, 52:64].astype(np.int64)
+        print("  per work item (ns since the earliest CTA start): min / median / max end over CTAs, median duration")
+        prev = (t[:, 0] - t0).astype(np.int64)
+        for k in range(12):
+            col = ends[:, k]
+            ok = col > 0
+            if not ok.any():
+                break
+            e = col[ok] - t0
+            dur = e - prev[ok]
+            print(f"    item {k}: ctas {ok.sum():3d}  end {e.min():7d} / {int(np.median(e)):7d} / {e.max():7d}   duration median {int(np.median(dur)):6d} max {dur.max():6d}")
+            prev = np.where(ok, col - t0, prev)
 for M in (128 * 16, 128 * 148, 96000):
     run(M)

@@ -19,6 +19,8 @@
 //   epi 4                   dx2 = k dh G + DX2, dx1 = dout + DX1                      -> smem -> TMA store
 // Warp roles: 0 TMA producer (activations), 3 TMA producer (weights), 1 MMA issuer (TMEM owner), 2 TMA-store issuer, 4..11 epilogue (warp%4 = TMEM
 // lane quarter; (warp-4)/4 = "half": adapter branch / gate branch in epi 1/3, left / right 32 columns in epi 2/4).
+#include <type_traits>
+
 #include "sm100_ptx.cuh"
 #include "vlpet_common.cuh"
 
@@ -52,7 +54,12 @@ struct BCfg {
   static constexpr int OFF_ZQ1 = OFF_Q0 + XCH_BYTES;                     // columns 64..95: z/da in bytes 0..63 of each row, q in 64..127
   static constexpr int OFF_DP0 = OFF_ZQ1 + (KB == 2 ? XCH_BYTES : 0);
   static constexpr int OFF_DP1 = OFF_DP0 + XCH_BYTES;
-  static constexpr int OFF_BAR = OFF_DP1 + (KB == 2 ? XCH_BYTES : 0);
+  // fp32 tables alpha*bu[d] | 0.5*gbu[d] for epilogues 2 / 4, 16 columns (64 B) per entry.  With KB == 2 the dp block of
+  // columns 64..95 only occupies one 64-byte half of each 128-byte row (which half depends on the row's swizzle phase);
+  // entry gi lives in the OTHER half of row gi of that block -- shared memory is full otherwise.  KB == 1: own block.
+  static constexpr int OFF_TAB = OFF_DP1;
+  static constexpr int OFF_BAR = OFF_DP1 + XCH_BYTES;
+  static constexpr int MAX_D = 1024;                                             // 2 * d / 16 table entries <= 128 rows
   static constexpr int SMEM_BYTES = OFF_BAR + 1024 + 2 * R * 4 + 256 + 1024;   // barriers | fp32 bd, gbd | slack + alignment
   static_assert(R <= 96 && R % 16 == 0, "fused backward covers ranks up to 96");
   static_assert(WSLOT % 1024 == 0 && WA_BYTES % 1024 == 0, "swizzle atoms must stay 1024-byte aligned");
@@ -60,7 +67,7 @@ struct BCfg {
 
 // Optional phase-timestamp trace (tools/trace_k1.py --bwd): thread 128 of every CTA stamps %globaltimer at the phase
 // boundaries of its first tile into [cta][128] slots.
-__device__ unsigned long long* g_trace_b = nullptr;
+static unsigned long long* g_trace_b = nullptr;   // host copy; travels to the kernel as BParams::trace
 __device__ __forceinline__ unsigned long long gtimer_b() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -68,7 +75,7 @@ __device__ __forceinline__ unsigned long long gtimer_b() {
 }
 #define VLPET_TRACE_B(slot)                                                                                               \
   do {                                                                                                                    \
-    if (g_trace_b && threadIdx.x == 128 && tile == blockIdx.x && (slot) < 128) g_trace_b[blockIdx.x * 128 + (slot)] = gtimer_b(); \
+    if (p.trace && threadIdx.x == 128 && tile == blockIdx.x && (slot) < 128) p.trace[blockIdx.x * 128 + (slot)] = gtimer_b(); \
   } while (0)
 
 struct BParams {
@@ -84,6 +91,7 @@ struct BParams {
   const uint64_t* seed_dev;
   uint32_t thr16;
   float inv_keep;
+  unsigned long long* trace;            // developer hook (tools/trace_k1_bwd.py), normally null
 };
 
 enum { B_XFULL = 0, B_XEMPTY = B_XFULL + SX, B_WFULL = B_XEMPTY + SX, B_WEMPTY = B_WFULL + SW, B_APFULL = B_WEMPTY + SW,
@@ -96,13 +104,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-__device__ __forceinline__ void gelu_new_both(float v, float& g, float& dg) {
+using namespace ptx;   // f2 helpers (packed fp32 pairs)
+// gelu_new(v) and gelu_new'(v) for a pair: 0.5 v (1 + th), th = tanh(c (v + 0.044715 v^3))
+__device__ __forceinline__ void gelu_new_both2(f2 v, f2& g, f2& dg) {
   const float c = 0.7978845608028654f, ck = 0.7978845608028654f * 0.044715f;
-  const float v2 = v * v;
-  const float th = ptx::tanh_approx(v * fmaf(ck, v2, c));
-  const float hv = 0.5f * v;
-  g = fmaf(hv, th, hv);
-  dg = fmaf(hv * (1.0f - th * th), fmaf(3.0f * ck, v2, c), 0.5f + 0.5f * th);
+  const f2 c2 = mk2(c, c), ck2 = mk2(ck, ck), ck3 = mk2(3.0f * ck, 3.0f * ck), half = mk2(0.5f, 0.5f), one = mk2(1.0f, 1.0f);
+  const f2 v2 = mul2(v, v);
+  const f2 th = tanh2(mul2(v, fma2(ck2, v2, c2)));
+  const f2 hv = mul2(half, v);
+  g = fma2(hv, th, hv);
+  const f2 omt = fma2(mul2(th, mk2(-1.0f, -1.0f)), th, one);          // 1 - th^2
+  dg = fma2(mul2(hv, omt), fma2(ck3, v2, c2), fma2(half, th, half));
 }
 __device__ __forceinline__ void lds128(uint32_t addr, uint32_t (&v)[4]) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
@@ -450,11 +462,20 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       const float v = (j < rr && (GATED || br == 0)) ? __bfloat162float(src[j]) : 0.f;
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_base + 4u * (uint32_t)i), "f"(v) : "memory");
     }
+    // alpha*bu and 0.5*gbu, 16 columns per 64-byte entry (layout: BCfg::OFF_TAB)
+    auto tab_addr = [&](int gi) -> uint32_t { return smem_base + C::OFF_TAB + (uint32_t)gi * 128u + ((gi & 4) ? 0u : 64u); };
+    const int ngrp = p.d / 16;
+    if (GATED) {
+      for (int i = threadIdx.x - 128; i < 2 * p.d; i += EPI_THREADS) {
+        const int col = i < p.d ? i : i - p.d;
+        const float v = i < p.d ? p.alpha * __bfloat162float(p.bu[col]) : 0.5f * __bfloat162float(p.gbu[col]);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tab_addr(i >> 4) + 4u * (uint32_t)(i & 15)), "f"(v) : "memory");
+      }
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // epilogue warps only
-    auto sbias4 = [&](int br, int j, float (&o)[4]) {
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
-                   : "r"(sb_base + 4u * (uint32_t)(br * R + j)));
-    };
+    const f2 half2 = mk2(0.5f, 0.5f), kappa2 = mk2(p.kappa, p.kappa), alpha2 = mk2(p.alpha, p.alpha);
+    const f2 s2 = mk2(p.s, p.s), sa2 = mk2(p.s * p.alpha, p.s * p.alpha);
+    const float s_keep = p.s * p.inv_keep;
     // smem address of the 16-byte group holding columns [k, k+8) of this thread's row in z/da (which=0), q (1), dp (2)
     auto small_addr = [&](int which, int k) -> uint32_t {
       if (k < 64) {
@@ -483,22 +504,19 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           const int j0 = jbeg + jj;
           uint32_t v[16], dgv[16];
           ptx::tmem_ld_32x32b_x16(tsrc + j0, v);
+          f2 bias[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) lds_f2x2(sb_base + 4u * (uint32_t)(branch * R + j0 + e * 4), bias[2 * e], bias[2 * e + 1]);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
-            float b0[4], b1[4];
-            sbias4(branch, j0 + g * 8, b0);
-            sbias4(branch, j0 + g * 8 + 4, b1);
-            const float bb[8] = {b0[0], b0[1], b0[2], b0[3], b1[0], b1[1], b1[2], b1[3]};
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float z0, z1, d0, d1;
-              gelu_new_both(__uint_as_float(v[g * 8 + e * 2]) + bb[e * 2], z0, d0);
-              gelu_new_both(__uint_as_float(v[g * 8 + e * 2 + 1]) + bb[e * 2 + 1], z1, d1);
-              o[e] = pack_bf16(z0, z1);
-              dgv[g * 8 + e * 2] = __float_as_uint(d0);
-              dgv[g * 8 + e * 2 + 1] = __float_as_uint(d1);
+              f2 z2, d2;
+              gelu_new_both2(add2(mk2u(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]), bias[g * 4 + e]), z2, d2);
+              o[e] = pack2(z2);
+              un2u(d2, dgv[g * 8 + e * 2], dgv[g * 8 + e * 2 + 1]);
             }
             const int k = j0 + g * 8;
             sts128(small_addr(branch, k), o);
@@ -536,55 +554,55 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         const uint32_t dorow = x2row + XCH_BYTES;
         const int col0 = c * CH + cg * 16;
         const int64_t idx0 = grow * p.d + col0;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint64_t hsh[2] = {0, 0};
-          if (p.thr16) {
-            hsh[0] = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
-            hsh[1] = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
-          }
+        const uint32_t tabu = tab_addr(c * 4 + cg), thgb = tab_addr(ngrp + c * 4 + cg);
+        auto group2 = [&](auto drop_tag, int g) {
+          constexpr bool DROP = decltype(drop_tag)::value;
           const uint32_t off = (((uint32_t)(cg * 2 + g)) ^ swz) << 4;
           uint32_t xv[4], dv[4], ou[4], ot[4];
           lds128(x2row + off, xv);
           lds128(dorow + off, dv);
-          const uint4 bu4 = __ldg(reinterpret_cast<const uint4*>(p.bu + col0 + g * 8));
-          const uint4 gb4 = __ldg(reinterpret_cast<const uint4*>(p.gbu + col0 + g * 8));
-          const uint32_t buw[4] = {bu4.x, bu4.y, bu4.z, bu4.w}, gbw[4] = {gb4.x, gb4.y, gb4.z, gb4.w};
+          f2 abu[4], hgb[4];
+          lds_f2x2(tabu + g * 32, abu[0], abu[1]);
+          lds_f2x2(tabu + g * 32 + 16, abu[2], abu[3]);
+          lds_f2x2(thgb + g * 32, hgb[0], hgb[1]);
+          lds_f2x2(thgb + g * 32 + 16, hgb[2], hgb[3]);
+          f2 sc[4] = {s2, s2, s2, s2}, sca[4] = {sa2, sa2, sa2, sa2};   // s * mask and alpha * s * mask
+          if (DROP) {
+            const uint64_t h0 = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
+            const uint64_t h1 = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t two = (uint32_t)((e >> 1 ? h1 : h0) >> (32 * (e & 1)));
+              sc[e] = mk2(((two & 0xffffu) >= p.thr16) ? s_keep : 0.f, ((two >> 16) >= p.thr16) ? s_keep : 0.f);
+              sca[e] = mul2(sc[e], alpha2);
+            }
+          }
+          const f2 q2 = mk2(0.25f, 0.25f), nq2 = mk2(-0.25f, -0.25f);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float du2[2], dt2[2];
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              const int j = g * 8 + e * 2 + h2;
-              const float x2f = h2 ? bf_hi(xv[e]) : bf_lo(xv[e]);
-              const float dof = h2 ? bf_hi(dv[e]) : bf_lo(dv[e]);
-              const float buf = h2 ? bf_hi(buw[e]) : bf_lo(buw[e]);
-              const float gbf = h2 ? bf_hi(gbw[e]) : bf_lo(gbw[e]);
-              float sc = p.s;
-              if (p.thr16) {
-                const uint32_t two = (uint32_t)(hsh[e >> 1] >> (32 * (e & 1)));
-                const uint32_t bits = h2 ? (two >> 16) : (two & 0xffffu);
-                sc = (bits >= p.thr16) ? p.s * p.inv_keep : 0.f;
-              }
-              const float dh = sc * dof;
-              const float th = ptx::tanh_approx(0.5f * (__uint_as_float(t[j]) + gbf));
-              const float G = fmaf(0.5f, th, 0.5f);
-              const float gg = 0.25f * (1.0f - th * th);  // G (1 - G)
-              if (mulgate) {
-                const float y1 = fmaf(p.kappa, x2f, p.alpha * (__uint_as_float(u[j]) + buf));
-                du2[h2] = p.alpha * dh * G;
-                dt2[h2] = dh * y1 * gg;
-              } else {
-                du2[h2] = p.alpha * dh;
-                dt2[h2] = dh * gg;
-              }
+            const int j = g * 8 + e * 2;
+            const f2 dof = bf2_to_f2(dv[e]);
+            const f2 dh = mul2(sc[e], dof);                                       // dh = s m dout
+            const f2 th = tanh2(fma2(half2, mk2u(t[j], t[j + 1]), hgb[e]));      // G = 0.5 + 0.5 th
+            const f2 gg = fma2(nq2, mul2(th, th), q2);                            // G (1 - G) = 0.25 (1 - th^2)
+            f2 du, dt;
+            if (mulgate) {
+              f2 y1 = fma2(kappa2, bf2_to_f2(xv[e]), abu[e]);                     // kappa x2 + alpha bu
+              y1 = fma2(alpha2, mk2u(u[j], u[j + 1]), y1);                        // + alpha U
+              du = mul2(mul2(sca[e], dof), fma2(half2, th, half2));               // alpha dh G
+              dt = mul2(mul2(dh, y1), gg);
+            } else {
+              du = mul2(sca[e], dof);
+              dt = mul2(dh, gg);
             }
-            ou[e] = pack_bf16(du2[0], du2[1]);
-            ot[e] = pack_bf16(dt2[0], dt2[1]);
+            ou[e] = pack2(du);
+            ot[e] = pack2(dt);
           }
           sts128(x2row + off, ou);
           sts128(dorow + off, ot);
-        }
+        };
+        if (p.thr16) { group2(std::true_type{}, 0); group2(std::true_type{}, 1); }
+        else { group2(std::false_type{}, 0); group2(std::false_type{}, 1); }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(bar(B_DUDT + (p2i % SX)));
         VLPET_TRACE_B(5 + 3 * c);
@@ -607,14 +625,16 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           ptx::tmem_ld_32x32b_x16(tpre + j0, a);     // gelu_new'(A + bd), stored by epilogue 1
           ptx::tmem_ld_32x32b_x16(tdz + j0, dz);
           ptx::tmem_ld_wait();
-          float da[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) da[e] = dzscale * __uint_as_float(dz[e]) * __uint_as_float(a[e]);
+          const f2 dzs2 = mk2(dzscale, dzscale);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             uint32_t o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = pack_bf16(da[g * 8 + e * 2], da[g * 8 + e * 2 + 1]);
+            for (int e = 0; e < 4; ++e) {
+              const int j = g * 8 + e * 2;
+              const f2 da = mul2(mk2u(dz[j], dz[j + 1]), mk2u(a[j], a[j + 1]));
+              o[e] = pack2(GATED ? da : mul2(dzs2, da));
+            }
             const int k = j0 + g * 8;
             sts128(small_addr(branch ? 2 : 0, k), o);
             if (row_ok && k < rr) *reinterpret_cast<uint4*>(srow + k) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -645,49 +665,50 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         const uint32_t o2row = dorow + XCH_BYTES;
         const int col0 = c * CH + cg * 16;
         const int64_t idx0 = grow * p.d + col0;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint64_t hsh[2] = {0, 0};
-          if (p.thr16) {
-            hsh[0] = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
-            hsh[1] = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
-          }
+        const uint32_t thgb = tab_addr(ngrp + c * 4 + cg);
+        auto group4 = [&](auto drop_tag, int g) {
+          constexpr bool DROP = decltype(drop_tag)::value;
           const uint32_t off = (((uint32_t)(cg * 2 + g)) ^ swz) << 4;
           uint32_t dv[4] = {0, 0, 0, 0}, o1[4], o2[4];
           if (GATED) lds128(dorow + off, dv);
-          uint32_t gbw[4] = {0, 0, 0, 0};
+          f2 hgb[4] = {0, 0, 0, 0};
           if (GATED && mulgate) {
-            const uint4 gb4 = __ldg(reinterpret_cast<const uint4*>(p.gbu + col0 + g * 8));
-            gbw[0] = gb4.x; gbw[1] = gb4.y; gbw[2] = gb4.z; gbw[3] = gb4.w;
+            lds_f2x2(thgb + g * 32, hgb[0], hgb[1]);
+            lds_f2x2(thgb + g * 32 + 16, hgb[2], hgb[3]);
+          }
+          f2 sc[4] = {s2, s2, s2, s2};
+          if (DROP) {
+            const uint64_t h0 = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
+            const uint64_t h1 = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t two = (uint32_t)((e >> 1 ? h1 : h0) >> (32 * (e & 1)));
+              sc[e] = mk2(((two & 0xffffu) >= p.thr16) ? s_keep : 0.f, ((two >> 16) >= p.thr16) ? s_keep : 0.f);
+            }
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float r1[2], r2[2];
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              const int j = g * 8 + e * 2 + h2;
-              const float dof = h2 ? bf_hi(dv[e]) : bf_lo(dv[e]);
-              float sc = p.s;
-              if (p.thr16) {
-                const uint32_t two = (uint32_t)(hsh[e >> 1] >> (32 * (e & 1)));
-                const uint32_t bits = h2 ? (two >> 16) : (two & 0xffffu);
-                sc = (bits >= p.thr16) ? p.s * p.inv_keep : 0.f;
+            const int j = g * 8 + e * 2;
+            const f2 g2p = mk2u(g2[j], g2[j + 1]);
+            if (GATED) {
+              const f2 dof = bf2_to_f2(dv[e]);
+              f2 dy1 = mul2(sc[e], dof);                                             // dh = s m dout
+              if (mulgate) {
+                const f2 th = tanh2(fma2(half2, mk2u(t[j], t[j + 1]), hgb[e]));
+                dy1 = mul2(dy1, fma2(half2, th, half2));                             // dh G
               }
-              float dy1 = sc * dof;
-              if (GATED && mulgate) {
-                const float gbf = h2 ? bf_hi(gbw[e]) : bf_lo(gbw[e]);
-                const float th = ptx::tanh_approx(0.5f * (__uint_as_float(t[j]) + gbf));
-                dy1 *= fmaf(0.5f, th, 0.5f);
-              }
-              r2[h2] = GATED ? fmaf(p.kappa, dy1, __uint_as_float(g2[j])) : __uint_as_float(g2[j]);
-              r1[h2] = GATED ? dof + __uint_as_float(g1[j]) : 0.f;
+              o2[e] = pack2(fma2(kappa2, dy1, g2p));                                 // dx2 = kappa dy1 + da Wd
+              o1[e] = pack2(add2(dof, mk2u(g1[j], g1[j + 1])));                      // dx1 = dout + dp Gd
+            } else {
+              o2[e] = pack2(g2p);
+              o1[e] = 0u;
             }
-            o1[e] = pack_bf16(r1[0], r1[1]);
-            o2[e] = pack_bf16(r2[0], r2[1]);
           }
           if (GATED) sts128(dorow + off, o1);
           sts128(o2row + off, o2);
-        }
+        };
+        if (p.thr16) { group4(std::true_type{}, 0); group4(std::true_type{}, 1); }
+        else { group4(std::false_type{}, 0); group4(std::false_type{}, 1); }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(bar(B_OUTRDY + (ai % SX)));
         VLPET_TRACE_B(45 + 3 * c);
@@ -800,6 +821,7 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   p.dbd = G.dbd; p.dgbd = gated ? G.dgbd : nullptr;
   p.seed = D.seed;
   p.seed_dev = D.seed_dev;
+  p.trace = g_trace_b;
   p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
   p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
   int rc = 0;
@@ -860,13 +882,13 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
 }  // namespace
 
 int set_k1_bwd_trace(unsigned long long* dev_buf) {
-  VLPET_CUDA_OK(cudaMemcpyToSymbol(g_trace_b, &dev_buf, sizeof(dev_buf)));
+  g_trace_b = dev_buf;
   return 0;
 }
 
 bool fused_k1_bwd_supported(const VlpetK1Desc& D) {
   if (D.dtype != VLPET_BF16 || D.gate != VLPET_GATE_LARGE) return false;
-  if (D.d % 128 != 0 || D.d < 128) return false;
+  if (D.d % 128 != 0 || D.d < 128 || D.d > 1024) return false;   // d <= 1024: the fp32 bias tables (BCfg::OFF_TAB)
   if (D.r % 8 != 0 || D.rg % 8 != 0 || D.r < 8 || D.rg < 8 || pick_R2(D.r, D.rg) == 0) return false;
   if (D.M <= 0 || D.M > (int64_t)0x7fffff00) return false;
   return device_sm_count() > 0 && wgrad_sm100_supported(D.d, D.r) && wgrad_sm100_supported(D.d, D.rg);

@@ -16,6 +16,7 @@
 // inputs + output staging in phase B) and a w-ring (weight chunks, always L2 hits).  Weights are padded to R rows /
 // columns by TMA out-of-bounds zero fill, so any r, rg <= R that is a multiple of 8 runs on the same instantiation.
 #include <mutex>
+#include <type_traits>
 
 #include "sm100_ptx.cuh"
 #include "vlpet_common.cuh"
@@ -99,32 +100,40 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int CH = 64;  // chunk width in elements: 64 bf16 = one 128-byte swizzle row
-constexpr int SX = 3;   // x-ring stages
 constexpr int SW = 2;   // w-ring stages
 constexpr int XCH_BYTES = TILE_M * CH * 2;  // 16 KB: one [128 x 64] bf16 chunk
 constexpr int NUM_THREADS = 640;   // 4 role warps + 16 epilogue warps
 constexpr int EPI_THREADS = 512;
 constexpr int TMEM_COLS = 512;
 constexpr int TM_A = 0, TM_P = 128, TM_UT = 256;  // TMEM column offsets
+constexpr int SMEM_LIMIT = 232448;                // 227 KB opt-in maximum per CTA
 
 template <int R>
 struct Cfg {
-  static constexpr int KB = (R + 63) / 64;             // 64-wide K blocks of z / q
+  static constexpr int SX = 4;                         // x-ring stages
+  static constexpr int KB = (R + 63) / 64;             // 64-wide K blocks of the phase-B weight chunks
   static constexpr int WA_BYTES = R * CH * 2;          // one [R x 64] weight chunk (phase A)
   static constexpr int WB_BYTES = KB * CH * CH * 2;    // one [64 x (KB*64)] weight chunk (phase B)
   static constexpr int WSLOT = (2 * WA_BYTES > 2 * WB_BYTES) ? 2 * WA_BYTES : 2 * WB_BYTES;
-  static constexpr int ZQ_BYTES = KB * XCH_BYTES;      // z (or q): KB blocks of [128 x 64]
   static constexpr int OFF_X = 0;
   static constexpr int OFF_W = OFF_X + SX * 2 * XCH_BYTES;
-  static constexpr int OFF_Z = OFF_W + SW * WSLOT;
-  static constexpr int OFF_Q = OFF_Z + ZQ_BYTES;
-  static constexpr int OFF_BAR = OFF_Q + ZQ_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // barriers + slack for the manual 1024-B alignment
+  static constexpr int OFF_BD = OFF_W + SW * WSLOT;    // fp32 bd[128], gbd[128] (zero padded)
+  static constexpr int OFF_BAR = OFF_BD + 2 * 128 * 4;
+  static constexpr int OFF_BU = OFF_BAR + 256;         // fp32 alpha*bu[d], 0.5*gbu[d]
+  static constexpr int smem_bytes(int d) { return OFF_BU + 2 * d * 4 + 1024; }  // + slack for the manual 1024-B alignment
+  // z = gelu_new(A + bd) and q = gelu_new(P + gbd) never touch shared memory: epilogue 1 packs them to bf16 and stores
+  // them back into TMEM over the accumulator columns it has just read, and phase B feeds them to tcgen05.mma as the
+  // A operand straight from TMEM.  Each epilogue warp owns HALF = R/2 accumulator columns and writes its HALF/2 packed
+  // columns at the start of its own range, so K step ks (16 values = 8 columns) of z / q starts at this column:
+  static constexpr int HALF = R / 2;
+  __host__ __device__ static constexpr uint32_t zq_col(int ks) {
+    return (16 * ks < HALF) ? (uint32_t)(8 * ks) : (uint32_t)(HALF + (16 * ks - HALF) / 2);
+  }
 };
 
 // Optional phase-timestamp trace (tools/trace_k1.py): when non-null, thread 128 (epilogue warp 4, lane 0) of every CTA
 // appends %globaltimer values at the phase boundaries of its tiles: [cta][64] slots.
-__device__ unsigned long long* g_trace = nullptr;
+static unsigned long long* g_trace = nullptr;   // host copy; travels to the kernel as Params::trace (constant bank: free when off)
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -132,27 +141,30 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #define VLPET_TRACE(slot)                                                                      \
   do {                                                                                         \
-    if (g_trace && threadIdx.x == 128 && w == blockIdx.x && (slot) < 64) g_trace[blockIdx.x * 64 + (slot)] = gtimer(); \
+    if (p.trace && threadIdx.x == 128 && w == blockIdx.x && (slot) < 64) p.trace[blockIdx.x * 64 + (slot)] = gtimer(); \
   } while (0)
 
 struct Params {
   int64_t M;
   int d, r, rg;
   int add_gate;
-  int nsplit;         // > 1 (small M): every tile is handled by nsplit CTAs, each redoing phase A and owning nkc/nsplit
-                      // of the phase-B column chunks -- trades redundant L2 reads for a shorter critical path
-  int gated;          // 0: no gate (h = y1; the K2 value-parallel-adapter form), 1: large gate
+  int64_t full_tiles; // tiles [0, full_tiles) are one work item each; every later tile is split over nsplit work items
+  int nsplit;         // split tiles (the last, partial wave of a large M, or all tiles of a small M): nsplit CTAs each redo
+                      // phase A and own nkc/nsplit of the phase-B column chunks -- trades redundant L2 reads for a
+                      // shorter critical path
   float s, alpha, kappa;
   const __nv_bfloat16 *bd, *bu, *gbd, *gbu;
   uint64_t seed;      // dropout stream (vlpet_common.cuh: drop_hash4)
   const uint64_t* seed_dev;  // optional device scalar added to seed (CUDA-graph replays)
   uint32_t thr16;     // 0 = no dropout
   float inv_keep;
+  unsigned long long* trace;  // developer hook (tools/trace_k1.py), normally null
 };
 
 // barrier slots (8 bytes each) inside the barrier block
-enum { B_XFULL = 0, B_XEMPTY = B_XFULL + SX, B_WFULL = B_XEMPTY + SX, B_WEMPTY = B_WFULL + SW, B_APFULL = B_WEMPTY + SW,
-       B_ZQFULL, B_UTFULL, B_UTEMPTY = B_UTFULL + 2, B_OUTRDY = B_UTEMPTY + 2, B_COUNT = B_OUTRDY + SX };
+constexpr int SXM = 4;  // barrier slots are laid out for the deepest x-ring
+enum { B_XFULL = 0, B_XEMPTY = B_XFULL + SXM, B_WFULL = B_XEMPTY + SXM, B_WEMPTY = B_WFULL + SW, B_APFULL = B_WEMPTY + SW,
+       B_ZQFULL, B_UTFULL, B_UTEMPTY = B_UTFULL + 2, B_OUTRDY = B_UTEMPTY + 2, B_COUNT = B_OUTRDY + SXM };
 
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
@@ -160,23 +172,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-__device__ __forceinline__ float gelu_new_fast(float v) {
-  const float c = 0.7978845608028654f, ck = 0.7978845608028654f * 0.044715f;
-  float t = ptx::tanh_approx(v * fmaf(ck, v * v, c));
-  float hv = 0.5f * v;
-  return fmaf(hv, t, hv);
+using namespace ptx;   // f2 helpers (packed fp32 pairs)
+// gelu_new(v) = 0.5 v (1 + tanh(c (v + 0.044715 v^3)))
+__device__ __forceinline__ f2 gelu_new2(f2 v) {
+  const f2 ck = mk2(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
+  const f2 c = mk2(0.7978845608028654f, 0.7978845608028654f), half = mk2(0.5f, 0.5f);
+  const f2 t = tanh2(mul2(v, fma2(ck, mul2(v, v), c)));
+  const f2 hv = mul2(half, v);
+  return fma2(hv, t, hv);
 }
-__device__ __forceinline__ float sigmoid_fast(float v) { return fmaf(0.5f, ptx::tanh_approx(0.5f * v), 0.5f); }
-
-template <int R>
+template <int R, bool GATED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_wd,
                     const __grid_constant__ CUtensorMap tm_gd, const __grid_constant__ CUtensorMap tm_wu,
                     const __grid_constant__ CUtensorMap tm_gu, const Params p) {
   using C = Cfg<R>;
+  constexpr int SX = C::SX;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));   // generic-space view of the aligned base
   const uint32_t bar_base = smem_base + C::OFF_BAR;
   auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
   const uint32_t tmem_slot = bar_base + 8u * B_COUNT;  // 4 bytes: TMEM base address written by tcgen05.alloc
@@ -185,11 +200,17 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   const int lane = threadIdx.x % 32;
   const int nkc = p.d / CH;  // chunks along d (phase A: K chunks; phase B: N chunks)
   const int64_t num_tiles = (p.M + TILE_M - 1) / TILE_M;
-  const int64_t num_items = num_tiles * p.nsplit;
-  const int cps = nkc / p.nsplit;   // phase-B chunks per work item (nsplit divides nkc)
-#define WORK_ITEM()                                  \
-  const int64_t tile = w / p.nsplit;                 \
-  const int cb = (int)(w % p.nsplit) * cps, ce = cb + cps; \
+  const int64_t num_items = p.full_tiles + (num_tiles - p.full_tiles) * p.nsplit;
+  const int cps = nkc / p.nsplit;   // phase-B chunks per split work item (nsplit divides nkc)
+#define WORK_ITEM()                                                    \
+  int64_t tile = w;                                                    \
+  int cb = 0, ce = nkc;                                                \
+  if (w >= p.full_tiles) {                                             \
+    const int64_t t_ = w - p.full_tiles;                               \
+    tile = p.full_tiles + t_ / p.nsplit;                               \
+    cb = (int)(t_ % p.nsplit) * cps;                                   \
+    ce = cb + cps;                                                     \
+  }                                                                    \
   (void)tile; (void)cb; (void)ce
 
   if (threadIdx.x == 0) {
@@ -205,6 +226,22 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     ptx::prefetch_tmap(&tm_wd); ptx::prefetch_tmap(&tm_gd); ptx::prefetch_tmap(&tm_wu); ptx::prefetch_tmap(&tm_gu);
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  {  // biases -> fp32 in shared memory, pre-multiplied so that the epilogues fold them into FMAs they issue anyway:
+     // bd / gbd (zero padded to 128), alpha*bu, 0.5*gbu
+    float* sbd = reinterpret_cast<float*>(smem_gen + C::OFF_BD);
+    float* sbu = reinterpret_cast<float*>(smem_gen + C::OFF_BU);
+    for (int i = threadIdx.x; i < 256; i += NUM_THREADS) {
+      const int j = i & 127;
+      float v = 0.f;
+      if (i < 128) { if (j < p.r) v = __bfloat162float(p.bd[j]); }
+      else if (GATED) { if (j < p.rg) v = __bfloat162float(p.gbd[j]); }
+      sbd[i] = v;
+    }
+    for (int i = threadIdx.x; i < p.d; i += NUM_THREADS) {
+      sbu[i] = p.alpha * __bfloat162float(p.bu[i]);
+      sbu[p.d + i] = GATED ? 0.5f * __bfloat162float(p.gbu[i]) : 0.f;
+    }
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -243,15 +280,15 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             ptx::mbar_wait(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1);
             const uint32_t wdst = smem_base + C::OFF_W + sw * C::WSLOT;
             if (ph == 0) {
-              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (p.gated ? 2 : 1) * C::WA_BYTES);
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (GATED ? 2 : 1) * C::WA_BYTES);
               ptx::tma_load_2d(wdst, &tm_wd, c * CH, 0, bar(B_WFULL + sw));
-              if (p.gated) ptx::tma_load_2d(wdst + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
+              if (GATED) ptx::tma_load_2d(wdst + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
             } else {
-              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (p.gated ? 2 : 1) * C::WB_BYTES);
+              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (GATED ? 2 : 1) * C::WB_BYTES);
 #pragma unroll
               for (int kb = 0; kb < C::KB; ++kb) {
                 ptx::tma_load_2d(wdst + kb * (CH * CH * 2), &tm_wu, kb * CH, c * CH, bar(B_WFULL + sw));
-                if (p.gated)
+                if (GATED)
                   ptx::tma_load_2d(wdst + C::WB_BYTES + kb * (CH * CH * 2), &tm_gu, kb * CH, c * CH, bar(B_WFULL + sw));
               }
             }
@@ -265,7 +302,6 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       constexpr uint32_t IDESC_A = ptx::umma_idesc_bf16_m128(R);
       constexpr uint32_t IDESC_B = ptx::umma_idesc_bf16_m128(CH);
       uint32_t xi = 0, wi = 0, ui = 0, ti = 0;
-      const uint32_t z_base = smem_base + C::OFF_Z, q_base = smem_base + C::OFF_Q;
       for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x, ++ti) {
         WORK_ITEM();
         // ---- phase A: A += x2_c Wd_c^T ; P += x1_c Gd_c^T
@@ -281,7 +317,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
             ptx::umma_bf16_ss(tmem_base + TM_A, ptx::umma_desc_kmajor_sw128(x2s + ks * 32),
                               ptx::umma_desc_kmajor_sw128(wds + ks * 32), IDESC_A, acc);
-            if (p.gated)
+            if (GATED)
               ptx::umma_bf16_ss(tmem_base + TM_P, ptx::umma_desc_kmajor_sw128(x1s + ks * 32),
                                 ptx::umma_desc_kmajor_sw128(gds + ks * 32), IDESC_A, acc);
           }
@@ -301,11 +337,11 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           const uint32_t tU = tmem_base + TM_UT + ub * 128, tT = tU + 64;
 #pragma unroll
           for (int ks = 0; ks < R / 16; ++ks) {
-            const uint32_t kb = ks / 4, kin = ks % 4;
-            ptx::umma_bf16_ss(tU, ptx::umma_desc_kmajor_sw128(z_base + kb * XCH_BYTES + kin * 32),
+            const int kb = ks / 4, kin = ks % 4;
+            ptx::umma_bf16_ts(tU, tmem_base + TM_A + C::zq_col(ks),
                               ptx::umma_desc_kmajor_sw128(wus + kb * (CH * CH * 2) + kin * 32), IDESC_B, ks > 0);
-            if (p.gated)
-              ptx::umma_bf16_ss(tT, ptx::umma_desc_kmajor_sw128(q_base + kb * XCH_BYTES + kin * 32),
+            if (GATED)
+              ptx::umma_bf16_ts(tT, tmem_base + TM_P + C::zq_col(ks),
                                 ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_B, ks > 0);
           }
           ptx::umma_commit(bar(B_WEMPTY + sw));
@@ -335,55 +371,48 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   } else if (warp >= 4) {
     // ===================================== epilogue warps =====================================
     // 16 warps: warp%4 = TMEM lane quarter (hardware rule), cg = (warp-4)/4 = column group.  Four warps per scheduler
-    // keep the issue slots busy while tcgen05.ld / ld.shared / MUFU latencies are in flight (the 8-warp version spent
-    // 1.4 us of pure math per chunk at ~45 % issue utilisation, tools/trace_k1.py).
+    // keep the issue slots busy while tcgen05.ld / ld.shared / MUFU latencies are in flight.  All arithmetic is on
+    // packed fp32 pairs (FFMA2), biases come pre-scaled from shared memory: ~8 issue slots per output element.
     const int quarter = warp % 4;            // TMEM lanes [32*quarter, 32*quarter+32)
     const int cg = (warp - 4) / 4;           // epilogue 1: branch = cg/2 (z | q), half of its columns = cg%2; epilogue 2: 16 of 64 columns
     const int row = quarter * 32 + lane;     // row inside the 128-token tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t swz = (uint32_t)(row & 7);
     const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
+    const f2 kappa2 = mk2(p.kappa, p.kappa), alpha2 = mk2(p.alpha, p.alpha), half2 = mk2(0.5f, 0.5f);
+    const f2 s2 = mk2(p.s, p.s), sh2 = mk2(0.5f * p.s, 0.5f * p.s);
+    const float s_keep = p.s * p.inv_keep;
     uint32_t xi = 0, ui = 0, oi = 0, ti = 0;
     for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x, ++ti) {
         WORK_ITEM();
-      // ---- epilogue 1: z = gelu_new(A + bd) (cg 0,1) / q = gelu_new(P + gbd) (cg 2,3) -> swizzled K-major smem
+      // ---- epilogue 1: z = gelu_new(A + bd) (cg 0,1) / q = gelu_new(P + gbd) (cg 2,3) -> packed bf16, back into TMEM
       VLPET_TRACE(0);
       ptx::mbar_wait(bar(B_APFULL), ti & 1);
       VLPET_TRACE(1);
       ptx::tc_fence_after();
       const int branch = cg >> 1;
-      if (p.gated || branch == 0) {
+      if (GATED || branch == 0) {
         const uint32_t tsrc = lane_addr + (branch ? TM_P : TM_A);
-        const uint32_t dst = smem_base + (branch ? C::OFF_Q : C::OFF_Z) + (uint32_t)row * 128u;
-        const __nv_bfloat16* bias = branch ? p.gbd : p.bd;
-        const int rr = branch ? p.rg : p.r;
-        constexpr int HALF = R / 2;            // columns per warp (R % 32 == 0 -> a multiple of 16)
+        const uint32_t sbias = smem_base + C::OFF_BD + (uint32_t)branch * 512u;
+        constexpr int HALF = C::HALF;          // columns per warp (R % 32 == 0 -> a multiple of 16)
         const int jbeg = (cg & 1) * HALF;
 #pragma unroll
         for (int jj = 0; jj < HALF; jj += 16) {
           const int j0 = jbeg + jj;
           uint32_t v[16];
           ptx::tmem_ld_32x32b_x16(tsrc + j0, v);
+          f2 bias[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) lds_f2x2(sbias + (uint32_t)(j0 + e * 4) * 4u, bias[2 * e], bias[2 * e + 1]);
           ptx::tmem_ld_wait();
+          uint32_t o[8];
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {  // 8 columns -> one 16-byte swizzled store
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = j0 + g * 8 + e * 2;
-              float b0 = (j < rr) ? __bfloat162float(bias[j]) : 0.f;
-              float b1 = (j + 1 < rr) ? __bfloat162float(bias[j + 1]) : 0.f;
-              o[e] = pack_bf16(gelu_new_fast(__uint_as_float(v[g * 8 + e * 2]) + b0),
-                               gelu_new_fast(__uint_as_float(v[g * 8 + e * 2 + 1]) + b1));
-            }
-            const int k = j0 + g * 8;                       // first column of this 16-byte group
-            const uint32_t kb = (uint32_t)k / 64, c16 = ((uint32_t)k % 64) / 8;
-            const uint32_t addr = dst + kb * XCH_BYTES + ((c16 ^ swz) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-          }
+          for (int e = 0; e < 8; ++e)
+            o[e] = pack2(gelu_new2(add2(mk2u(v[e * 2], v[e * 2 + 1]), bias[e])));
+          ptx::tmem_st_32x32b_x8(tsrc + jbeg + jj / 2, o);   // packed bf16 over columns this warp has already read
         }
+        ptx::tmem_st_wait();
       }
-      ptx::fence_proxy_async_smem();  // z/q were written by the generic proxy and are read by tcgen05.mma
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(B_ZQFULL));
       VLPET_TRACE(2);
@@ -391,13 +420,14 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       // ---- epilogue 2, per 64-column chunk: this warp owns columns [cg*16, cg*16+16) of the chunk
       for (int c = cb; c < ce; ++c, ++xi, ++ui, ++oi) {
         const uint32_t sx = xi % SX, ub = ui & 1, so = oi % SX;
+        const int col0 = c * CH + cg * 16;  // first of this thread's 16 output columns
         ptx::mbar_wait(bar(B_UTFULL + ub), (ui >> 1) & 1);
         VLPET_TRACE(3 + 4 * (c - cb));
         ptx::tc_fence_after();
         uint32_t u[16], t[16];
         const uint32_t tU = lane_addr + TM_UT + ub * 128 + cg * 16;
         ptx::tmem_ld_32x32b_x16(tU, u);
-        if (p.gated) ptx::tmem_ld_32x32b_x16(tU + 64, t);
+        if (GATED) ptx::tmem_ld_32x32b_x16(tU + 64, t);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_UTEMPTY + ub));  // accumulators are in registers: the MMA warp may overwrite them
@@ -406,48 +436,63 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         VLPET_TRACE(5 + 4 * (c - cb));
         const uint32_t x1row = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t x2row = x1row + XCH_BYTES;
-        const int col0 = c * CH + cg * 16;  // first of this thread's 16 output columns
+        const uint32_t sabu = smem_base + C::OFF_BU + (uint32_t)col0 * 4u;   // alpha*bu for this thread's columns
+        const uint32_t shgb = sabu + (uint32_t)p.d * 4u;                      // 0.5*gbu
         const int64_t idx0 = ((int64_t)tile * TILE_M + row) * p.d + col0;  // flat element index (dropout stream)
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint64_t hsh[2] = {0, 0};
-          if (p.thr16) {
-            hsh[0] = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
-            hsh[1] = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
-          }
+        auto group = [&](auto drop_tag, int g) {
+          constexpr bool DROP = decltype(drop_tag)::value;
           const uint32_t off = (((uint32_t)(cg * 2 + g)) ^ swz) << 4;
           uint32_t a[4], b[4], o[4];
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(x1row + off));
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(x2row + off));
-          const uint4 bu4 = __ldg(reinterpret_cast<const uint4*>(p.bu + col0 + g * 8));
-          const uint4 gb4 = p.gated ? __ldg(reinterpret_cast<const uint4*>(p.gbu + col0 + g * 8)) : make_uint4(0, 0, 0, 0);
-          const uint32_t buw[4] = {bu4.x, bu4.y, bu4.z, bu4.w}, gbw[4] = {gb4.x, gb4.y, gb4.z, gb4.w};
+          f2 abu[4], hgb[4];
+          lds_f2x2(sabu + g * 32, abu[0], abu[1]);
+          lds_f2x2(sabu + g * 32 + 16, abu[2], abu[3]);
+          if (GATED) {
+            lds_f2x2(shgb + g * 32, hgb[0], hgb[1]);
+            lds_f2x2(shgb + g * 32 + 16, hgb[2], hgb[3]);
+          }
+          f2 sc[4] = {s2, s2, s2, s2}, sh[4] = {sh2, sh2, sh2, sh2};   // s * dropout mask (and half of it), per element
+          if (DROP) {
+            const uint64_t h0 = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
+            const uint64_t h1 = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t two = (uint32_t)((e >> 1 ? h1 : h0) >> (32 * (e & 1)));  // 16 bits for column j, 16 for j+1
+              sc[e] = mk2(((two & 0xffffu) >= p.thr16) ? s_keep : 0.f, ((two >> 16) >= p.thr16) ? s_keep : 0.f);
+              sh[e] = mul2(sc[e], half2);
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = g * 8 + e * 2;
-            float y0 = fmaf(p.kappa, bf_lo(b[e]), p.alpha * (__uint_as_float(u[j]) + bf_lo(buw[e])));
-            float y1 = fmaf(p.kappa, bf_hi(b[e]), p.alpha * (__uint_as_float(u[j + 1]) + bf_hi(buw[e])));
-            float h0 = y0, h1 = y1;
-            if (p.gated) {
-              float g0 = sigmoid_fast(__uint_as_float(t[j]) + bf_lo(gbw[e]));
-              float g1 = sigmoid_fast(__uint_as_float(t[j + 1]) + bf_hi(gbw[e]));
-              h0 = p.add_gate ? y0 + g0 : y0 * g0;
-              h1 = p.add_gate ? y1 + g1 : y1 * g1;
+            const f2 x1p = bf2_to_f2(a[e]);
+            f2 y = fma2(kappa2, bf2_to_f2(b[e]), abu[e]);          // kappa*x2 + alpha*bu
+            y = fma2(alpha2, mk2u(u[j], u[j + 1]), y);             // + alpha*U
+            f2 res;
+            if (GATED) {
+              // G = sigmoid(T + gbu) = 0.5 + 0.5*tanh(0.5*(T + gbu))
+              const f2 th = tanh2(fma2(half2, mk2u(t[j], t[j + 1]), hgb[e]));
+              if (!p.add_gate) {        // out = x1 + sc*y*G = (x1 + hs) + hs*th,  hs = 0.5*sc*y
+                const f2 hs = mul2(sh[e], y);
+                res = fma2(hs, th, add2(x1p, hs));
+              } else {                  // out = x1 + sc*(y + G) = (x1 + sc*y + 0.5*sc) + 0.5*sc*th
+                res = fma2(sh[e], th, add2(fma2(sc[e], y, x1p), sh[e]));
+              }
+            } else {
+              res = fma2(sc[e], y, x1p);
             }
-            float s0 = p.s, s1 = p.s;
-            if (p.thr16) {
-              const uint32_t two = (uint32_t)(hsh[e >> 1] >> (32 * (e & 1)));  // 16 bits for column j, 16 for j+1
-              s0 = ((two & 0xffffu) >= p.thr16) ? p.s * p.inv_keep : 0.f;
-              s1 = ((two >> 16) >= p.thr16) ? p.s * p.inv_keep : 0.f;
-            }
-            o[e] = pack_bf16(fmaf(s0, h0, bf_lo(a[e])), fmaf(s1, h1, bf_hi(a[e])));
+            o[e] = pack2(res);
           }
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(x1row + off), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-        }
+        };
+        if (p.thr16) { group(std::true_type{}, 0); group(std::true_type{}, 1); }
+        else { group(std::false_type{}, 0); group(std::false_type{}, 1); }
         ptx::fence_proxy_async_smem();  // out chunk (in the x1 slot) is read by the TMA store
         ptx::mbar_arrive(bar(B_OUTRDY + so));
         VLPET_TRACE(6 + 4 * (c - cb));
       }
+      if (p.trace && threadIdx.x == 128 && ti < 12) p.trace[blockIdx.x * 64 + 52 + ti] = gtimer();   // end of work item ti
     }
   }
 
@@ -487,27 +532,43 @@ const DevInfo& dev_info() {
   return di;
 }
 
-template <int R>
+template <int R, bool GATED>
 int launch(const VlpetK1Desc& D, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
   using C = Cfg<R>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLPET_CUDA_OK(cudaFuncSetAttribute(k1_fwd_sm100_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+  const int smem = C::smem_bytes(D.d);
+  static int attr_set = 0;
+  if (attr_set < smem) {
+    VLPET_CUDA_OK(cudaFuncSetAttribute(k1_fwd_sm100_kernel<R, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = smem;
   }
   const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
-  const int64_t items = tiles * p.nsplit;
+  const int64_t items = p.full_tiles + (tiles - p.full_tiles) * p.nsplit;
   int grid = (int)(items < dev_info().sms ? items : dev_info().sms);
-  k1_fwd_sm100_kernel<R><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
-                                                                  maps[6], p);
+  k1_fwd_sm100_kernel<R, GATED><<<grid, NUM_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+                                                                 maps[6], p);
   VLPET_LAUNCH_OK();
   return 0;
+}
+
+template <int R>
+int launch_r(const VlpetK1Desc& D, const CUtensorMap* maps, const Params& p, bool gated, cudaStream_t st) {
+  return gated ? launch<R, true>(D, maps, p, st) : launch<R, false>(D, maps, p, st);
+}
+
+int smem_need(int R, int d) {
+  switch (R) {
+    case 32: return Cfg<32>::smem_bytes(d);
+    case 64: return Cfg<64>::smem_bytes(d);
+    case 96: return Cfg<96>::smem_bytes(d);
+    case 128: return Cfg<128>::smem_bytes(d);
+  }
+  return 1 << 30;
 }
 
 }  // namespace
 
 int set_k1_trace(unsigned long long* dev_buf) {
-  VLPET_CUDA_OK(cudaMemcpyToSymbol(g_trace, &dev_buf, sizeof(dev_buf)));
+  g_trace = dev_buf;
   return 0;
 }
 
@@ -517,6 +578,7 @@ bool fused_k1_fwd_supported(const VlpetK1Desc& D) {
   const bool gated = D.gate == VLPET_GATE_LARGE;
   if (D.r % 8 != 0 || (gated && D.rg % 8 != 0) || pick_R(D) == 0) return false;
   if (D.M <= 0 || D.M > (int64_t)0x7fffff00) return false;
+  if (smem_need(pick_R(D), D.d) > SMEM_LIMIT) return false;   // the fp32 bias tables (8 bytes per column of d) must fit
   const DevInfo& di = dev_info();
   return di.ok && di.major == 10;
 }
@@ -526,8 +588,7 @@ size_t fused_k1_fwd_ws(const VlpetK1Desc&) { return 0; }
 int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const VlpetK1Params& w, void* out, void*, size_t,
                  cudaStream_t st) {
   const bool gated = D.gate == VLPET_GATE_LARGE;
-  if (!aligned16(w.Wd) || !aligned16(w.Wu) || !aligned16(w.bu) ||
-      (gated && (!aligned16(w.Gd) || !aligned16(w.Gu) || !aligned16(w.gbu))))
+  if (!aligned16(w.Wd) || !aligned16(w.Wu) || (gated && (!aligned16(w.Gd) || !aligned16(w.Gu))))
     return fail(VLPET_E_ALIGN, "k1_fwd(fused): weights must be 16-byte aligned");
   const int R = pick_R(D);
   CUtensorMap maps[7];
@@ -539,26 +600,32 @@ int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const Vlp
   VLPET_TRY(make_map(&maps[5], w.Wu, (uint64_t)D.d, (uint64_t)D.r, CH, true));
   VLPET_TRY(make_map(&maps[6], gated ? w.Gu : w.Wu, (uint64_t)D.d, (uint64_t)(gated ? D.rg : D.r), CH, true));
   Params p;
-  p.M = D.M; p.d = D.d; p.r = D.r; p.rg = gated ? D.rg : D.r; p.add_gate = D.add_gate; p.gated = gated ? 1 : 0;
+  p.M = D.M; p.d = D.d; p.r = D.r; p.rg = gated ? D.rg : D.r; p.add_gate = D.add_gate;
   p.s = D.s; p.alpha = D.alpha; p.kappa = D.kappa;
   p.bd = static_cast<const __nv_bfloat16*>(w.bd); p.bu = static_cast<const __nv_bfloat16*>(w.bu);
   p.gbd = static_cast<const __nv_bfloat16*>(gated ? w.gbd : w.bd); p.gbu = static_cast<const __nv_bfloat16*>(gated ? w.gbu : w.bu);
   p.seed = D.seed;
   p.seed_dev = D.seed_dev;
-  {  // small M: split every tile's phase-B columns over several CTAs (largest divisor of nkc that still fits one wave)
-    const int nkc = D.d / CH;
+  p.trace = g_trace;
+  {  // Whole waves of tiles run one tile per CTA.  The tiles of the last, partial wave (all tiles when M is small) are
+     // split over several CTAs each (largest divisor of nkc that still fits the wave): the tail costs one phase A plus
+     // nkc/nsplit chunks instead of a full tile time.
+    const int nkc = D.d / CH, sms = dev_info().sms;
     const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
+    const int64_t rem = tiles % sms;
+    p.full_tiles = tiles - rem;
     p.nsplit = 1;
     for (int ns = 2; ns <= nkc; ++ns)
-      if (nkc % ns == 0 && tiles * ns <= dev_info().sms) p.nsplit = ns;
+      if (nkc % ns == 0 && rem * ns <= sms) p.nsplit = ns;
+    if (p.nsplit == 1) p.full_tiles = tiles;
   }
   p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
   p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
   switch (R) {
-    case 32: return launch<32>(D, maps, p, st);
-    case 64: return launch<64>(D, maps, p, st);
-    case 96: return launch<96>(D, maps, p, st);
-    case 128: return launch<128>(D, maps, p, st);
+    case 32: return launch_r<32>(D, maps, p, gated, st);
+    case 64: return launch_r<64>(D, maps, p, gated, st);
+    case 96: return launch_r<96>(D, maps, p, gated, st);
+    case 128: return launch_r<128>(D, maps, p, gated, st);
   }
   return fail(VLPET_E_UNSUPPORTED, "k1_fwd(fused): unsupported rank");
 }
