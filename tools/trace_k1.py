@@ -13,7 +13,7 @@ def run(M):
     x1 = torch.randn(M, d, device="cuda", generator=g).to(bf); x2 = torch.randn(M, d, device="cuda", generator=g).to(bf)
     W = [(torch.randn(*s, device="cuda", generator=g) * 0.05).to(bf) for s in ((r, d), (r,), (d, r), (d,), (r, d), (r,), (d, r), (d,))]
     cfg = V.PetSiteConfig(gate="large")
-    buf = torch.zeros(148 * 64, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(148 * 256, dtype=torch.int64, device="cuda")
     L.lib.vlpet_debug_set_k1_trace.argtypes = [C.c_void_p]
     for _ in range(3):
         with torch.no_grad():
@@ -27,7 +27,7 @@ def run(M):
     e.record()
     torch.cuda.synchronize()
     L.lib.vlpet_debug_set_k1_trace(C.c_void_p(0))
-    t = buf.view(148, 64).cpu().numpy()
+    t = buf.view(148, 256).cpu().numpy()
     print(f"M={M}: kernel {s.elapsed_time(e)*1e3:.1f} us (first tile of CTA 0 and CTA 5, ns relative to tile start)")
     for cta in (0, 5):
         row = t[cta]
@@ -38,6 +38,13 @@ def run(M):
             a, b, cc, dd = rel[3 + 4 * c], rel[4 + 4 * c], rel[5 + 4 * c], rel[6 + 4 * c]
             print(f"    chunk {c:2d}: UT ready {a:7d}  tmem read {b - a:5d}  wait x {cc - b:6d}  math {dd - cc:6d}  -> {dd}")
     if M >= 128 * 148 * 2:
+        r0 = t[0]
+        z = r0[0]
+        print("  cta 0 MMA thread: standalone phase A steps issued at", [int(v - z) for v in r0[100:112]])
+        print("  cta 0 MMA thread, item 0: chunk_b issued at", [int(v - z) for v in r0[64:88:2]])
+        print("  cta 0 MMA thread, item 0: step_a (next item) issued at", [int(v - z) for v in r0[65:88:2]])
+        print("  cta 0 x manager: OUTRDY seen at", [int(v - z) for v in r0[128:152:2]])
+        print("  cta 0 x manager: store read done at", [int(v - z) for v in r0[129:152:2]])
         import numpy as np
         t0 = t[:, 0][t[:, 0] > 0].min()
         ends = t[:, 52:64].astype(np.int64)

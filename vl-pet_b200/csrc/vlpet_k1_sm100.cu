@@ -6,15 +6,20 @@
 //
 // Design.  Persistent CTAs, one per SM, each walks 128-token tiles.  Per tile:
 //   phase A  (contraction over d):   A[128,R] = x2 Wd^T,  P[128,R] = x1 Gd^T        tcgen05.mma, fp32 accum in TMEM
-//   epilogue 1:                      z = gelu_new(A + bd), q = gelu_new(P + gbd)    TMEM -> regs -> bf16 -> swizzled smem
-//   phase B  (per 64-column chunk):  U = z Wu_n^T, T = q Gu_n^T                     tcgen05.mma, double-buffered TMEM
+//   epilogue 1:                      z = gelu_new(A + bd), q = gelu_new(P + gbd)    TMEM -> regs -> packed bf16 -> TMEM
+//   phase B  (per 64-column chunk):  U = z Wu_n^T, T = q Gu_n^T                     tcgen05.mma, A operand from TMEM
 //   epilogue 2:                      out_n = x1_n + s*(kappa*x2_n + alpha*(U+bu)) (*|+) sigmoid(T+gbu)   -> smem -> TMA store
-// Warp roles: warp 0 = TMA producer (activations), warp 3 = TMA producer (weights), warp 1 = MMA issuer (+ TMEM owner),
-// warp 2 = TMA-store issuer,
-// warps 4..11 = epilogue (two warpgroups; warp%4 selects the TMEM lane quarter).
-// Two smem rings fed by TMA: an x-ring (x1/x2 64-column chunks, used as MMA operands in phase A and as the residual
-// inputs + output staging in phase B) and a w-ring (weight chunks, always L2 hits).  Weights are padded to R rows /
-// columns by TMA out-of-bounds zero fill, so any r, rg <= R that is a multiple of 8 runs on the same instantiation.
+// Software pipeline across tiles: phase A of tile i+1 (the HBM stream) is interleaved step by step with phase B of tile i
+// (L2 re-reads + stores), so that HBM, the tensor pipe and the epilogue warps are busy at the same time instead of all
+// CTAs alternating in lockstep between an HBM-bound and an epilogue-bound half (tools/trace_k1.py showed exactly that).
+// Warp roles: warp 0 = TMA producer of the phase-A operands (x chunks + Wd/Gd chunks), warp 3 = TMA producer of the
+// phase-B weights (Wu/Gu chunks), warp 1 = MMA issuer (+ TMEM owner; issues phase-A steps and phase-B chunks in
+// whatever order their inputs become ready), warp 2 = phase-B x manager (TMA load of the
+// residual chunks, TMA store of the finished out chunk from the same slot), warps 4..19 = epilogue (warp%4 = TMEM lane
+// quarter).  Shared memory: XA ring (2 x 32 KB), XB ring (2 x 32 KB), WA ring (3 x [R x 64]), WB ring (3 x [64 x 128]),
+// fp32 bias tables.  Weights are padded to R rows / columns by TMA out-of-bounds zero fill, so any r, rg <= R that is a
+// multiple of 8 runs on the same instantiation.  The kernel is shared-memory-bandwidth bound (TMA writes + UMMA operand
+// reads + epilogue LDS/STS all go through the 128 B/clk port); keeping z/q in TMEM removed a quarter of that traffic.
 #include <mutex>
 #include <type_traits>
 
@@ -40,7 +45,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 row-major tensor [rows, cols] with a row pitch of `pitch_elems` elements; box = [box_rows x box_cols],
-// 128-byte swizzle (box_cols * 2 bytes must be <= 128), out-of-bounds elements read as zero / are not written.
+// 128-byte swizzle (64-byte swizzle when the box is 32 columns wide), out-of-bounds elements read as zero / are not written.
 // Descriptor cache: encoding a tensor map costs ~1 us on the host and a backward call needs 19 of them; the same
 // (pointer, shape) tuples recur every step (weights always, activations whenever the allocator reuses addresses).
 struct MapKey {
@@ -87,7 +92,7 @@ static int encode_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    weight ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VLPET_E_BADARG, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box=%ux%u",
@@ -100,48 +105,57 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int CH = 64;  // chunk width in elements: 64 bf16 = one 128-byte swizzle row
-constexpr int SW = 2;   // w-ring stages
+constexpr int NXA = 2;  // XA ring stages (phase-A operands of the NEXT tile: the HBM stream)
+constexpr int NXB = 2;  // XB ring stages (phase-B residual inputs of the current tile + out staging)
 constexpr int XCH_BYTES = TILE_M * CH * 2;  // 16 KB: one [128 x 64] bf16 chunk
 constexpr int NUM_THREADS = 640;   // 4 role warps + 16 epilogue warps
 constexpr int EPI_THREADS = 512;
 constexpr int TMEM_COLS = 512;
-constexpr int TM_A = 0, TM_P = 128, TM_UT = 256;  // TMEM column offsets
+// TMEM columns: fp32 accumulators A, P | packed bf16 z, q (2 values per column) | U, T of one 64-column chunk
+constexpr int TM_A = 0, TM_P = 128, TM_Z = 256, TM_Q = 320, TM_UT = 384;
 constexpr int SMEM_LIMIT = 232448;                // 227 KB opt-in maximum per CTA
 
 template <int R>
 struct Cfg {
-  static constexpr int SX = 4;                         // x-ring stages
-  static constexpr int KB = (R + 63) / 64;             // 64-wide K blocks of the phase-B weight chunks
+  // Weight rings hold 4 slots = two full steps (a step consumes one chunk of each of the two branches): with 3 slots the
+  // second matrix of every step was requested only after the previous step's MMAs had retired -- one exposed L2 latency
+  // (~1 us) per step (tools/trace_k1.py).
+  static constexpr int NWA = (R == 128) ? 2 : 3;       // WA ring slots (one [R x 64] chunk of Wd or Gd each); phase A is not
+                                                       // the critical path, the MMA warp never blocks on it (ready_a)
+  static constexpr int NWB = (R == 128) ? 2 : 4;       // WB ring slots (one [64 x R] chunk of Wu or Gu each)
+  static constexpr int KBF = R / 64;                   // full 64-wide K blocks of a phase-B weight chunk (128-byte swizzle)
+  static constexpr int REM = R % 64;                   // 0 or 32: a last 32-wide K block (64-byte swizzle, half the bytes)
   static constexpr int WA_BYTES = R * CH * 2;          // one [R x 64] weight chunk (phase A)
-  static constexpr int WB_BYTES = KB * CH * CH * 2;    // one [64 x (KB*64)] weight chunk (phase B)
-  static constexpr int WSLOT = (2 * WA_BYTES > 2 * WB_BYTES) ? 2 * WA_BYTES : 2 * WB_BYTES;
-  static constexpr int OFF_X = 0;
-  static constexpr int OFF_W = OFF_X + SX * 2 * XCH_BYTES;
-  static constexpr int OFF_BD = OFF_W + SW * WSLOT;    // fp32 bd[128], gbd[128] (zero padded)
+  static constexpr int WB_BYTES = KBF * CH * CH * 2 + (REM ? CH * 32 * 2 : 0);   // one [64 x R] weight chunk (phase B)
+  static constexpr int OFF_XA = 0;
+  static constexpr int OFF_XB = OFF_XA + NXA * 2 * XCH_BYTES;
+  static constexpr int OFF_WA = OFF_XB + NXB * 2 * XCH_BYTES;
+  static constexpr int OFF_WB = OFF_WA + NWA * WA_BYTES;
+  static constexpr int OFF_BD = OFF_WB + NWB * WB_BYTES;   // fp32 bd[128], gbd[128] (zero padded)
   static constexpr int OFF_BAR = OFF_BD + 2 * 128 * 4;
   static constexpr int OFF_BU = OFF_BAR + 256;         // fp32 alpha*bu[d], 0.5*gbu[d]
   static constexpr int smem_bytes(int d) { return OFF_BU + 2 * d * 4 + 1024; }  // + slack for the manual 1024-B alignment
-  // z = gelu_new(A + bd) and q = gelu_new(P + gbd) never touch shared memory: epilogue 1 packs them to bf16 and stores
-  // them back into TMEM over the accumulator columns it has just read, and phase B feeds them to tcgen05.mma as the
-  // A operand straight from TMEM.  Each epilogue warp owns HALF = R/2 accumulator columns and writes its HALF/2 packed
-  // columns at the start of its own range, so K step ks (16 values = 8 columns) of z / q starts at this column:
-  static constexpr int HALF = R / 2;
-  __host__ __device__ static constexpr uint32_t zq_col(int ks) {
-    return (16 * ks < HALF) ? (uint32_t)(8 * ks) : (uint32_t)(HALF + (16 * ks - HALF) / 2);
-  }
+  static constexpr int HALF = R / 2;                   // accumulator columns per epilogue-1 warp
+  static_assert(REM == 0 || REM == 32, "rank buckets are multiples of 32");
+  static_assert(WA_BYTES % 1024 == 0 && WB_BYTES % 1024 == 0, "swizzle atoms must stay 1024-byte aligned");
 };
 
 // Optional phase-timestamp trace (tools/trace_k1.py): when non-null, thread 128 (epilogue warp 4, lane 0) of every CTA
-// appends %globaltimer values at the phase boundaries of its tiles: [cta][64] slots.
+// stamps %globaltimer at the phase boundaries of its first work item and at the end of every work item; the MMA thread and
+// the phase-B x manager stamp their issue times of the first item: [cta][256] slots.
 static unsigned long long* g_trace = nullptr;   // host copy; travels to the kernel as Params::trace (constant bank: free when off)
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#define VLPET_TR(slot)                                                             \
+  do {                                                                             \
+    if (p.trace) p.trace[blockIdx.x * 256 + (slot)] = gtimer();                    \
+  } while (0)
 #define VLPET_TRACE(slot)                                                                      \
   do {                                                                                         \
-    if (p.trace && threadIdx.x == 128 && w == blockIdx.x && (slot) < 64) p.trace[blockIdx.x * 64 + (slot)] = gtimer(); \
+    if (p.trace && threadIdx.x == 128 && ti == 0 && (slot) < 52) p.trace[blockIdx.x * 256 + (slot)] = gtimer(); \
   } while (0)
 
 struct Params {
@@ -162,9 +176,9 @@ struct Params {
 };
 
 // barrier slots (8 bytes each) inside the barrier block
-constexpr int SXM = 4;  // barrier slots are laid out for the deepest x-ring
-enum { B_XFULL = 0, B_XEMPTY = B_XFULL + SXM, B_WFULL = B_XEMPTY + SXM, B_WEMPTY = B_WFULL + SW, B_APFULL = B_WEMPTY + SW,
-       B_ZQFULL, B_UTFULL, B_UTEMPTY = B_UTFULL + 2, B_OUTRDY = B_UTEMPTY + 2, B_COUNT = B_OUTRDY + SXM };
+enum { B_XAFULL = 0, B_XAEMPTY = B_XAFULL + NXA, B_XBFULL = B_XAEMPTY + NXA, B_OUTRDY = B_XBFULL + NXB,
+       B_WAFULL = B_OUTRDY + NXB, B_WAEMPTY = B_WAFULL + 4, B_WBFULL = B_WAEMPTY + 4, B_WBEMPTY = B_WBFULL + 4,
+       B_APFULL = B_WBEMPTY + 4, B_ZQFULL, B_UTFULL, B_UTEMPTY, B_COUNT };
 
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
@@ -181,14 +195,37 @@ __device__ __forceinline__ f2 gelu_new2(f2 v) {
   const f2 hv = mul2(half, v);
   return fma2(hv, t, hv);
 }
+// The work items of one CTA, in order: w = blockIdx.x, + gridDim.x, ...  (tile, [cb, ce) = its phase-B chunks)
+struct ItemCursor {
+  int64_t w, num_items, full_tiles, tile;
+  int nsplit, cps, nkc, stride, cb, ce;
+  __device__ __forceinline__ void init(const Params& p, int nkc_, int64_t num_items_) {
+    w = blockIdx.x; num_items = num_items_; full_tiles = p.full_tiles; nsplit = p.nsplit; nkc = nkc_;
+    cps = nkc_ / p.nsplit; stride = gridDim.x;
+    decode();
+  }
+  __device__ __forceinline__ bool valid() const { return w < num_items; }
+  __device__ __forceinline__ void decode() {
+    tile = w; cb = 0; ce = nkc;
+    if (w >= full_tiles) {
+      const int64_t t = w - full_tiles;
+      tile = full_tiles + t / nsplit;
+      cb = (int)(t % nsplit) * cps;
+      ce = cb + cps;
+    }
+  }
+  __device__ __forceinline__ void next() { w += stride; decode(); }
+};
+
 template <int R, bool GATED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_wd,
                     const __grid_constant__ CUtensorMap tm_gd, const __grid_constant__ CUtensorMap tm_wu,
-                    const __grid_constant__ CUtensorMap tm_gu, const Params p) {
+                    const __grid_constant__ CUtensorMap tm_gu, const __grid_constant__ CUtensorMap tm_wu_t,
+                    const __grid_constant__ CUtensorMap tm_gu_t, const Params p) {
   using C = Cfg<R>;
-  constexpr int SX = C::SX;
+  constexpr int NWA = C::NWA, NWB = C::NWB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));   // generic-space view of the aligned base
@@ -201,35 +238,29 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   const int nkc = p.d / CH;  // chunks along d (phase A: K chunks; phase B: N chunks)
   const int64_t num_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int64_t num_items = p.full_tiles + (num_tiles - p.full_tiles) * p.nsplit;
-  const int cps = nkc / p.nsplit;   // phase-B chunks per split work item (nsplit divides nkc)
-#define WORK_ITEM()                                                    \
-  int64_t tile = w;                                                    \
-  int cb = 0, ce = nkc;                                                \
-  if (w >= p.full_tiles) {                                             \
-    const int64_t t_ = w - p.full_tiles;                               \
-    tile = p.full_tiles + t_ / p.nsplit;                               \
-    cb = (int)(t_ % p.nsplit) * cps;                                   \
-    ce = cb + cps;                                                     \
-  }                                                                    \
-  (void)tile; (void)cb; (void)ce
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SX; ++i) { ptx::mbar_init(bar(B_XFULL + i), 1); ptx::mbar_init(bar(B_XEMPTY + i), 1); ptx::mbar_init(bar(B_OUTRDY + i), EPI_THREADS); }
-    for (int i = 0; i < SW; ++i) { ptx::mbar_init(bar(B_WFULL + i), 1); ptx::mbar_init(bar(B_WEMPTY + i), 1); }
+    for (int i = 0; i < NXA; ++i) { ptx::mbar_init(bar(B_XAFULL + i), 1); ptx::mbar_init(bar(B_XAEMPTY + i), 1); }
+    for (int i = 0; i < NXB; ++i) { ptx::mbar_init(bar(B_XBFULL + i), 1); ptx::mbar_init(bar(B_OUTRDY + i), EPI_THREADS); }
+    for (int i = 0; i < NWA; ++i) { ptx::mbar_init(bar(B_WAFULL + i), 1); ptx::mbar_init(bar(B_WAEMPTY + i), 1); }
+    for (int i = 0; i < NWB; ++i) { ptx::mbar_init(bar(B_WBFULL + i), 1); ptx::mbar_init(bar(B_WBEMPTY + i), 1); }
     ptx::mbar_init(bar(B_APFULL), 1);
     ptx::mbar_init(bar(B_ZQFULL), EPI_THREADS);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(B_UTFULL + i), 1); ptx::mbar_init(bar(B_UTEMPTY + i), EPI_THREADS); }
+    ptx::mbar_init(bar(B_UTFULL), 1);
+    ptx::mbar_init(bar(B_UTEMPTY), EPI_THREADS);
     ptx::fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_out); }
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); }
+  if (warp == 2 && lane == 0) { ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_out); }
   if (warp == 3 && lane == 0) {
-    ptx::prefetch_tmap(&tm_wd); ptx::prefetch_tmap(&tm_gd); ptx::prefetch_tmap(&tm_wu); ptx::prefetch_tmap(&tm_gu);
+    ptx::prefetch_tmap(&tm_wu); ptx::prefetch_tmap(&tm_gu);
+    if (C::REM) { ptx::prefetch_tmap(&tm_wu_t); ptx::prefetch_tmap(&tm_gu_t); }
   }
+  if (warp == 0 && lane == 1) { ptx::prefetch_tmap(&tm_wd); ptx::prefetch_tmap(&tm_gd); }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
   {  // biases -> fp32 in shared memory, pre-multiplied so that the epilogues fold them into FMAs they issue anyway:
      // bd / gbd (zero padded to 128), alpha*bu, 0.5*gbu
     float* sbd = reinterpret_cast<float*>(smem_gen + C::OFF_BD);
-    float* sbu = reinterpret_cast<float*>(smem_gen + C::OFF_BU);
     for (int i = threadIdx.x; i < 256; i += NUM_THREADS) {
       const int j = i & 127;
       float v = 0.f;
@@ -237,6 +268,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       else if (GATED) { if (j < p.rg) v = __bfloat162float(p.gbd[j]); }
       sbd[i] = v;
     }
+    float* sbu = reinterpret_cast<float*>(smem_gen + C::OFF_BU);
     for (int i = threadIdx.x; i < p.d; i += NUM_THREADS) {
       sbu[i] = p.alpha * __bfloat162float(p.bu[i]);
       sbu[p.d + i] = GATED ? 0.5f * __bfloat162float(p.gbu[i]) : 0.f;
@@ -249,124 +281,203 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ===================================== TMA producer: activations =====================================
-    if (lane == 0) {
-      uint32_t xi = 0;
-      for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x) {
-        WORK_ITEM();
-        const int row0 = (int)(tile * TILE_M);
-        for (int ph = 0; ph < 2; ++ph) {
-          for (int c = (ph ? cb : 0); c < (ph ? ce : nkc); ++c, ++xi) {
-            const uint32_t sx = xi % SX;
-            ptx::mbar_wait(bar(B_XEMPTY + sx), ((xi / SX) & 1) ^ 1);
-            const uint32_t xdst = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
-            ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), 2 * XCH_BYTES);
-            ptx::tma_load_2d(xdst, &tm_x1, c * CH, row0, bar(B_XFULL + sx));
-            ptx::tma_load_2d(xdst + XCH_BYTES, &tm_x2, c * CH, row0, bar(B_XFULL + sx));
+    // ===================================== TMA producer: phase-A x chunks (HBM stream) =====================================
+    // (all role warps run converged with one elected lane issuing, see the MMA warp)
+    {
+      ItemCursor it; it.init(p, nkc, num_items);
+      uint32_t n = 0, na = 0;
+      for (; it.valid(); it.next()) {
+        const int row0 = (int)(it.tile * TILE_M);
+        for (int k = 0; k < nkc; ++k, ++n) {
+          const uint32_t sl = n % NXA;
+          ptx::mbar_wait(bar(B_XAEMPTY + sl), ((n / NXA) & 1) ^ 1);
+          const uint32_t dst = smem_base + C::OFF_XA + sl * (2 * XCH_BYTES);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar(B_XAFULL + sl), (GATED ? 2 : 1) * XCH_BYTES);
+            // first touch of data that phase B reads again one tile later: ask L2 to keep it
+            if (GATED) ptx::tma_load_2d_hint(dst, &tm_x1, k * CH, row0, bar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
+            ptx::tma_load_2d_hint(dst + XCH_BYTES, &tm_x2, k * CH, row0, bar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
+          }
+          __syncwarp();
+          // the weight chunks the same MMA step consumes: Wd_k, Gd_k (always L2 hits)
+#pragma unroll
+          for (int m = 0; m < (GATED ? 2 : 1); ++m, ++na) {
+            const uint32_t sw = na % NWA;
+            ptx::mbar_wait(bar(B_WAEMPTY + sw), ((na / NWA) & 1) ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(bar(B_WAFULL + sw), C::WA_BYTES);
+              ptx::tma_load_2d_hint(smem_base + C::OFF_WA + sw * C::WA_BYTES, m ? &tm_gd : &tm_wd, k * CH, 0, bar(B_WAFULL + sw),
+                                    ptx::L2_EVICT_LAST);
+            }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 3) {
-    // ===================================== TMA producer: weights (always L2 hits) =====================================
-    // its own thread, so that the weight ring runs ahead independently of the activation ring's (later) releases
-    if (lane == 0) {
-      uint32_t wi = 0;
-      for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x) {
-        WORK_ITEM();
-        for (int ph = 0; ph < 2; ++ph) {
-          for (int c = (ph ? cb : 0); c < (ph ? ce : nkc); ++c, ++wi) {
-            const uint32_t sw = wi % SW;
-            ptx::mbar_wait(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1);
-            const uint32_t wdst = smem_base + C::OFF_W + sw * C::WSLOT;
-            if (ph == 0) {
-              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (GATED ? 2 : 1) * C::WA_BYTES);
-              ptx::tma_load_2d(wdst, &tm_wd, c * CH, 0, bar(B_WFULL + sw));
-              if (GATED) ptx::tma_load_2d(wdst + C::WA_BYTES, &tm_gd, c * CH, 0, bar(B_WFULL + sw));
-            } else {
-              ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (GATED ? 2 : 1) * C::WB_BYTES);
+    // ===================================== TMA producer: phase-B weights Wu_c, Gu_c (always L2 hits) ====================
+    {
+      uint32_t nb = 0;
+      ItemCursor it; it.init(p, nkc, num_items);
+      for (; it.valid(); it.next()) {
+        for (int c = it.cb; c < it.ce; ++c) {
 #pragma unroll
-              for (int kb = 0; kb < C::KB; ++kb) {
-                ptx::tma_load_2d(wdst + kb * (CH * CH * 2), &tm_wu, kb * CH, c * CH, bar(B_WFULL + sw));
-                if (GATED)
-                  ptx::tma_load_2d(wdst + C::WB_BYTES + kb * (CH * CH * 2), &tm_gu, kb * CH, c * CH, bar(B_WFULL + sw));
-              }
+          for (int m = 0; m < (GATED ? 2 : 1); ++m, ++nb) {
+            const uint32_t sl = nb % NWB;
+            ptx::mbar_wait(bar(B_WBEMPTY + sl), ((nb / NWB) & 1) ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(bar(B_WBFULL + sl), C::WB_BYTES);
+#pragma unroll
+              for (int kb = 0; kb < C::KBF; ++kb)
+                ptx::tma_load_2d_hint(smem_base + C::OFF_WB + sl * C::WB_BYTES + kb * (CH * CH * 2), m ? &tm_gu : &tm_wu, kb * CH,
+                                      c * CH, bar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
+              if (C::REM)
+                ptx::tma_load_2d_hint(smem_base + C::OFF_WB + sl * C::WB_BYTES + C::KBF * (CH * CH * 2), m ? &tm_gu_t : &tm_wu_t,
+                                      C::KBF * CH, c * CH, bar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
             }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    // The whole warp runs this loop converged and one elected lane issues: operands of tcgen05.mma / tcgen05.commit live in
+    // uniform registers, and a divergent single-lane loop made ptxas wrap EVERY issue in an elect / broadcast / branch
+    // sequence (~15 instructions, >100 ns per MMA measured with tools/trace_k1.py -- the whole kernel was issue-bound).
+    {
       constexpr uint32_t IDESC_A = ptx::umma_idesc_bf16_m128(R);
       constexpr uint32_t IDESC_B = ptx::umma_idesc_bf16_m128(CH);
-      uint32_t xi = 0, wi = 0, ui = 0, ti = 0;
-      for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x, ++ti) {
-        WORK_ITEM();
-        // ---- phase A: A += x2_c Wd_c^T ; P += x1_c Gd_c^T
-        for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
-          const uint32_t sx = xi % SX, sw = wi % SW;
-          ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
-          ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
-          ptx::tc_fence_after();
-          const uint32_t x1s = smem_base + C::OFF_X + sx * (2 * XCH_BYTES), x2s = x1s + XCH_BYTES;
-          const uint32_t wds = smem_base + C::OFF_W + sw * C::WSLOT, gds = wds + C::WA_BYTES;
+      uint32_t nxa = 0, na = 0, nb = 0, ui = 0, ti = 0;
+      // Phase A of the next item and phase B of this item are issued in whatever order their inputs become ready
+      // (non-blocking barrier tests): the HBM stream is not paced by the epilogue and vice versa.
+      auto ready_a = [&]() -> bool {
+        bool r = ptx::mbar_test(bar(B_XAFULL + nxa % NXA), (nxa / NXA) & 1) && ptx::mbar_test(bar(B_WAFULL + na % NWA), (na / NWA) & 1);
+        if (GATED) r = r && ptx::mbar_test(bar(B_WAFULL + (na + 1) % NWA), ((na + 1) / NWA) & 1);
+        return __all_sync(0xffffffffu, r);
+      };
+      auto ready_b = [&]() -> bool {
+        bool r = ptx::mbar_test(bar(B_UTEMPTY), (ui & 1) ^ 1) && ptx::mbar_test(bar(B_WBFULL + nb % NWB), (nb / NWB) & 1);
+        if (GATED) r = r && ptx::mbar_test(bar(B_WBFULL + (nb + 1) % NWB), ((nb + 1) / NWB) & 1);
+        return __all_sync(0xffffffffu, r);
+      };
+      // one phase-A step: A += x2_k Wd_k^T ; P += x1_k Gd_k^T
+      auto step_a = [&](int k) {
+        const uint32_t sx = nxa % NXA;
+        ptx::mbar_wait(bar(B_XAFULL + sx), (nxa / NXA) & 1);
+        const uint32_t x1s = smem_base + C::OFF_XA + sx * (2 * XCH_BYTES), x2s = x1s + XCH_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < CH / 16; ++ks) {
-            const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
-            ptx::umma_bf16_ss(tmem_base + TM_A, ptx::umma_desc_kmajor_sw128(x2s + ks * 32),
-                              ptx::umma_desc_kmajor_sw128(wds + ks * 32), IDESC_A, acc);
-            if (GATED)
-              ptx::umma_bf16_ss(tmem_base + TM_P, ptx::umma_desc_kmajor_sw128(x1s + ks * 32),
-                                ptx::umma_desc_kmajor_sw128(gds + ks * 32), IDESC_A, acc);
+        for (int m = 0; m < (GATED ? 2 : 1); ++m, ++na) {
+          const uint32_t sl = na % NWA;
+          ptx::mbar_wait(bar(B_WAFULL + sl), (na / NWA) & 1);
+          ptx::tc_fence_after();
+          const uint32_t ws = smem_base + C::OFF_WA + sl * C::WA_BYTES;
+          const uint64_t adesc = ptx::umma_desc_kmajor_sw128(m ? x1s : x2s), bdesc = ptx::umma_desc_kmajor_sw128(ws);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < CH / 16; ++ks)   // +32 bytes per K step = +2 in the descriptor's 16-byte address units
+              ptx::umma_bf16_ss(tmem_base + (m ? TM_P : TM_A), adesc + 2 * ks, bdesc + 2 * ks, IDESC_A, (k > 0 || ks > 0) ? 1u : 0u);
+            ptx::umma_commit(bar(B_WAEMPTY + sl));
+            if (m == (GATED ? 1 : 0)) ptx::umma_commit(bar(B_XAEMPTY + sx));
           }
-          ptx::umma_commit(bar(B_XEMPTY + sx));
-          ptx::umma_commit(bar(B_WEMPTY + sw));
+          __syncwarp();
         }
-        ptx::umma_commit(bar(B_APFULL));
-        // ---- phase B: U_n = z Wu_n^T ; T_n = q Gu_n^T
+        ++nxa;
+      };
+      // one phase-B chunk: U = z Wu_c^T ; T = q Gu_c^T  (z, q: A operand from TMEM)
+      auto chunk_b = [&]() {
+        ptx::mbar_wait(bar(B_UTEMPTY), (ui & 1) ^ 1);
+#pragma unroll
+        for (int m = 0; m < (GATED ? 2 : 1); ++m, ++nb) {
+          const uint32_t sl = nb % NWB;
+          ptx::mbar_wait(bar(B_WBFULL + sl), (nb / NWB) & 1);
+          ptx::tc_fence_after();
+          const uint32_t ws = smem_base + C::OFF_WB + sl * C::WB_BYTES;
+          const uint64_t d128 = ptx::umma_desc_kmajor_sw128(ws), d64 = ptx::umma_desc_kmajor_sw64(ws + C::KBF * (CH * CH * 2));
+          const uint32_t ta = tmem_base + (m ? TM_Q : TM_Z), td = tmem_base + TM_UT + (m ? CH : 0);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < R / 16; ++ks) {
+              const int kb = ks / 4, kin = ks % 4;
+              const uint64_t bdesc = (kb < C::KBF) ? d128 + (uint64_t)(kb * (CH * CH * 2 / 16) + 2 * kin) : d64 + (uint64_t)(2 * kin);
+              ptx::umma_bf16_ts(td, ta + 8 * ks, bdesc, IDESC_B, ks > 0);
+            }
+            ptx::umma_commit(bar(B_WBEMPTY + sl));
+            if (m == (GATED ? 1 : 0)) ptx::umma_commit(bar(B_UTFULL));
+          }
+          __syncwarp();
+        }
+        ++ui;
+      };
+      ItemCursor it; it.init(p, nkc, num_items);
+      if (it.valid()) {
+        for (int k = 0; k < nkc; ++k) { step_a(k); if (lane == 0 && k < 12) VLPET_TR(100 + k); }
+        if (ptx::elect_one()) ptx::umma_commit(bar(B_APFULL));
+        __syncwarp();
+      }
+      for (; it.valid(); it.next(), ++ti) {
+        const int nB = it.ce - it.cb;
+        const int nA = (it.w + it.stride < num_items) ? nkc : 0;
+        // z/q of this item are in TMEM, and A/P have been drained: phase B of this item and phase A of the next may run
         ptx::mbar_wait(bar(B_ZQFULL), ti & 1);
         ptx::tc_fence_after();
-        for (int c = cb; c < ce; ++c, ++xi, ++wi, ++ui) {
-          const uint32_t sw = wi % SW, ub = ui & 1;
-          ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
-          ptx::mbar_wait(bar(B_UTEMPTY + ub), ((ui >> 1) & 1) ^ 1);
-          ptx::tc_fence_after();
-          const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT, gus = wus + C::WB_BYTES;
-          const uint32_t tU = tmem_base + TM_UT + ub * 128, tT = tU + 64;
-#pragma unroll
-          for (int ks = 0; ks < R / 16; ++ks) {
-            const int kb = ks / 4, kin = ks % 4;
-            ptx::umma_bf16_ts(tU, tmem_base + TM_A + C::zq_col(ks),
-                              ptx::umma_desc_kmajor_sw128(wus + kb * (CH * CH * 2) + kin * 32), IDESC_B, ks > 0);
-            if (GATED)
-              ptx::umma_bf16_ts(tT, tmem_base + TM_P + C::zq_col(ks),
-                                ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_B, ks > 0);
+        int kb = 0, ka = 0;
+        uint32_t spins = 0;
+        while (kb < nB || ka < nA) {
+          bool did = false;
+          if (kb < nB && ready_b()) { chunk_b(); if (lane == 0 && ti == 0 && kb < 12) VLPET_TR(64 + 2 * kb); ++kb; did = true; }
+          if (ka < nA && ready_a()) {
+            step_a(ka);
+            if (lane == 0 && ti == 0 && ka < 12) VLPET_TR(65 + 2 * ka);
+            if (++ka == nA) {
+              if (ptx::elect_one()) ptx::umma_commit(bar(B_APFULL));
+              __syncwarp();
+            }
+            did = true;
           }
-          ptx::umma_commit(bar(B_WEMPTY + sw));
-          ptx::umma_commit(bar(B_UTFULL + ub));
+          if (did) spins = 0;
+          else if (++spins > (1u << 24)) __trap();
         }
       }
     }
   } else if (warp == 2) {
-    // ===================================== TMA store issuer =====================================
-    if (lane == 0) {
-      uint32_t xi = 0, oi = 0;
-      for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x) {
-        WORK_ITEM();
-        const int row0 = (int)(tile * TILE_M);
-        xi += nkc;  // phase A steps of the x-ring are consumed by the MMA warp
-        for (int c = cb; c < ce; ++c, ++xi, ++oi) {
-          const uint32_t sx = xi % SX, so = oi % SX;
-          ptx::mbar_wait(bar(B_OUTRDY + so), (oi / SX) & 1);
-          ptx::tma_store_2d(&tm_out, smem_base + C::OFF_X + sx * (2 * XCH_BYTES), c * CH, row0);
+    // ===================================== phase-B x manager: TMA load of x1_c / x2_c, TMA store of out_c ==============
+    // The residual chunks of ALL work items form one stream of entries; entry e lives in XB slot e % NXB.  This thread
+    // frees a slot itself (its store has read it), so it can refill it right away: no empty barrier.
+    {
+      const bool leader = ptx::elect_one();   // the bulk-group waits below belong to the thread that issued the stores
+      ItemCursor ld; ld.init(p, nkc, num_items);
+      ItemCursor st = ld;
+      int lc = ld.valid() ? ld.cb : 0, sc = lc;
+      uint32_t e_st = 0;
+      auto load = [&](uint32_t sl) {
+        const uint32_t dst = smem_base + C::OFF_XB + sl * (2 * XCH_BYTES);
+        const int row0 = (int)(ld.tile * TILE_M);
+        if (leader) {
+          ptx::mbar_arrive_expect_tx(bar(B_XBFULL + sl), 2 * XCH_BYTES);
+          ptx::tma_load_2d_hint(dst, &tm_x1, lc * CH, row0, bar(B_XBFULL + sl), ptx::L2_EVICT_FIRST);   // last use
+          ptx::tma_load_2d_hint(dst + XCH_BYTES, &tm_x2, lc * CH, row0, bar(B_XBFULL + sl), ptx::L2_EVICT_FIRST);
+        }
+        __syncwarp();
+        if (++lc == ld.ce) { ld.next(); lc = ld.cb; }
+      };
+      for (uint32_t i = 0; i < NXB && ld.valid(); ++i) load(i);
+      for (; st.valid(); ++e_st) {
+        const uint32_t sl = e_st % NXB;
+        ptx::mbar_wait(bar(B_OUTRDY + sl), (e_st / NXB) & 1);
+        if (lane == 0 && e_st < 12) VLPET_TR(128 + 2 * e_st);
+        if (leader) {
+          ptx::tma_store_2d_hint(&tm_out, smem_base + C::OFF_XB + sl * (2 * XCH_BYTES), sc * CH, (int)(st.tile * TILE_M),
+                                 ptx::L2_EVICT_FIRST);   // never re-read by this kernel
           ptx::tma_store_commit();
           ptx::tma_store_wait_read0();
-          ptx::mbar_arrive(bar(B_XEMPTY + sx));
         }
+        __syncwarp();
+        if (lane == 0 && e_st < 12) VLPET_TR(129 + 2 * e_st);
+        if (++sc == st.ce) { st.next(); sc = st.cb; }
+        if (ld.valid()) load(sl);
       }
-      ptx::tma_store_wait_all0();
+      if (leader) ptx::tma_store_wait_all0();
     }
   } else if (warp >= 4) {
     // ===================================== epilogue warps =====================================
@@ -382,10 +493,12 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     const f2 kappa2 = mk2(p.kappa, p.kappa), alpha2 = mk2(p.alpha, p.alpha), half2 = mk2(0.5f, 0.5f);
     const f2 s2 = mk2(p.s, p.s), sh2 = mk2(0.5f * p.s, 0.5f * p.s);
     const float s_keep = p.s * p.inv_keep;
-    uint32_t xi = 0, ui = 0, oi = 0, ti = 0;
-    for (int64_t w = blockIdx.x; w < num_items; w += gridDim.x, ++ti) {
-        WORK_ITEM();
-      // ---- epilogue 1: z = gelu_new(A + bd) (cg 0,1) / q = gelu_new(P + gbd) (cg 2,3) -> packed bf16, back into TMEM
+    uint32_t e = 0, ui = 0, ti = 0;
+    ItemCursor it; it.init(p, nkc, num_items);
+    for (; it.valid(); it.next(), ++ti) {
+      const int64_t tile = it.tile;
+      const int cb = it.cb, ce = it.ce;
+      // ---- epilogue 1: z = gelu_new(A + bd) (cg 0,1) / q = gelu_new(P + gbd) (cg 2,3) -> packed bf16 into TMEM
       VLPET_TRACE(0);
       ptx::mbar_wait(bar(B_APFULL), ti & 1);
       VLPET_TRACE(1);
@@ -393,6 +506,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       const int branch = cg >> 1;
       if (GATED || branch == 0) {
         const uint32_t tsrc = lane_addr + (branch ? TM_P : TM_A);
+        const uint32_t tdst = lane_addr + (branch ? TM_Q : TM_Z);
         const uint32_t sbias = smem_base + C::OFF_BD + (uint32_t)branch * 512u;
         constexpr int HALF = C::HALF;          // columns per warp (R % 32 == 0 -> a multiple of 16)
         const int jbeg = (cg & 1) * HALF;
@@ -403,38 +517,37 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           ptx::tmem_ld_32x32b_x16(tsrc + j0, v);
           f2 bias[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) lds_f2x2(sbias + (uint32_t)(j0 + e * 4) * 4u, bias[2 * e], bias[2 * e + 1]);
+          for (int q = 0; q < 4; ++q) lds_f2x2(sbias + (uint32_t)(j0 + q * 4) * 4u, bias[2 * q], bias[2 * q + 1]);
           ptx::tmem_ld_wait();
           uint32_t o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            o[e] = pack2(gelu_new2(add2(mk2u(v[e * 2], v[e * 2 + 1]), bias[e])));
-          ptx::tmem_st_32x32b_x8(tsrc + jbeg + jj / 2, o);   // packed bf16 over columns this warp has already read
+          for (int q = 0; q < 8; ++q)
+            o[q] = pack2(gelu_new2(add2(mk2u(v[q * 2], v[q * 2 + 1]), bias[q])));
+          ptx::tmem_st_32x32b_x8(tdst + j0 / 2, o);
         }
         ptx::tmem_st_wait();
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(bar(B_ZQFULL));
+      ptx::mbar_arrive(bar(B_ZQFULL));   // z/q are in place AND this thread is done reading A/P
       VLPET_TRACE(2);
-      xi += nkc;
       // ---- epilogue 2, per 64-column chunk: this warp owns columns [cg*16, cg*16+16) of the chunk
-      for (int c = cb; c < ce; ++c, ++xi, ++ui, ++oi) {
-        const uint32_t sx = xi % SX, ub = ui & 1, so = oi % SX;
+      for (int c = cb; c < ce; ++c, ++ui, ++e) {
+        const uint32_t sl = e % NXB;
         const int col0 = c * CH + cg * 16;  // first of this thread's 16 output columns
-        ptx::mbar_wait(bar(B_UTFULL + ub), (ui >> 1) & 1);
+        ptx::mbar_wait(bar(B_UTFULL), ui & 1);
         VLPET_TRACE(3 + 4 * (c - cb));
         ptx::tc_fence_after();
         uint32_t u[16], t[16];
-        const uint32_t tU = lane_addr + TM_UT + ub * 128 + cg * 16;
+        const uint32_t tU = lane_addr + TM_UT + cg * 16;
         ptx::tmem_ld_32x32b_x16(tU, u);
-        if (GATED) ptx::tmem_ld_32x32b_x16(tU + 64, t);
+        if (GATED) ptx::tmem_ld_32x32b_x16(tU + CH, t);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(bar(B_UTEMPTY + ub));  // accumulators are in registers: the MMA warp may overwrite them
+        ptx::mbar_arrive(bar(B_UTEMPTY));  // accumulators are in registers: the MMA warp may overwrite them
         VLPET_TRACE(4 + 4 * (c - cb));
-        ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+        ptx::mbar_wait(bar(B_XBFULL + sl), (e / NXB) & 1);
         VLPET_TRACE(5 + 4 * (c - cb));
-        const uint32_t x1row = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
+        const uint32_t x1row = smem_base + C::OFF_XB + sl * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t x2row = x1row + XCH_BYTES;
         const uint32_t sabu = smem_base + C::OFF_BU + (uint32_t)col0 * 4u;   // alpha*bu for this thread's columns
         const uint32_t shgb = sabu + (uint32_t)p.d * 4u;                      // 0.5*gbu
@@ -489,10 +602,10 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         if (p.thr16) { group(std::true_type{}, 0); group(std::true_type{}, 1); }
         else { group(std::false_type{}, 0); group(std::false_type{}, 1); }
         ptx::fence_proxy_async_smem();  // out chunk (in the x1 slot) is read by the TMA store
-        ptx::mbar_arrive(bar(B_OUTRDY + so));
+        ptx::mbar_arrive(bar(B_OUTRDY + sl));
         VLPET_TRACE(6 + 4 * (c - cb));
       }
-      if (p.trace && threadIdx.x == 128 && ti < 12) p.trace[blockIdx.x * 64 + 52 + ti] = gtimer();   // end of work item ti
+      if (p.trace && threadIdx.x == 128 && ti < 12) p.trace[blockIdx.x * 256 + 52 + ti] = gtimer();   // end of work item ti
     }
   }
 
@@ -545,7 +658,7 @@ int launch(const VlpetK1Desc& D, const CUtensorMap* maps, const Params& p, cudaS
   const int64_t items = p.full_tiles + (tiles - p.full_tiles) * p.nsplit;
   int grid = (int)(items < dev_info().sms ? items : dev_info().sms);
   k1_fwd_sm100_kernel<R, GATED><<<grid, NUM_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
-                                                                 maps[6], p);
+                                                                 maps[6], maps[7], maps[8], p);
   VLPET_LAUNCH_OK();
   return 0;
 }
@@ -588,10 +701,11 @@ size_t fused_k1_fwd_ws(const VlpetK1Desc&) { return 0; }
 int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const VlpetK1Params& w, void* out, void*, size_t,
                  cudaStream_t st) {
   const bool gated = D.gate == VLPET_GATE_LARGE;
-  if (!aligned16(w.Wd) || !aligned16(w.Wu) || (gated && (!aligned16(w.Gd) || !aligned16(w.Gu))))
+  if (!aligned16(w.Wd) || !aligned16(w.Wu) || !aligned16(w.bu) ||
+      (gated && (!aligned16(w.Gd) || !aligned16(w.Gu) || !aligned16(w.gbu))))
     return fail(VLPET_E_ALIGN, "k1_fwd(fused): weights must be 16-byte aligned");
   const int R = pick_R(D);
-  CUtensorMap maps[7];
+  CUtensorMap maps[9];
   VLPET_TRY(make_map(&maps[0], x1, (uint64_t)D.M, (uint64_t)D.d, TILE_M, false));
   VLPET_TRY(make_map(&maps[1], x2, (uint64_t)D.M, (uint64_t)D.d, TILE_M, false));
   VLPET_TRY(make_map(&maps[2], out, (uint64_t)D.M, (uint64_t)D.d, TILE_M, false));
@@ -599,6 +713,10 @@ int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const Vlp
   VLPET_TRY(make_map(&maps[4], gated ? w.Gd : w.Wd, (uint64_t)(gated ? D.rg : D.r), (uint64_t)D.d, (uint32_t)R, true));
   VLPET_TRY(make_map(&maps[5], w.Wu, (uint64_t)D.d, (uint64_t)D.r, CH, true));
   VLPET_TRY(make_map(&maps[6], gated ? w.Gu : w.Wu, (uint64_t)D.d, (uint64_t)(gated ? D.rg : D.r), CH, true));
+  // 32-column boxes (64-byte swizzle) for the last, half-wide K block of the phase-B weight chunks (R % 64 == 32)
+  VLPET_TRY(make_map_bf16(&maps[7], w.Wu, (uint64_t)D.d, (uint64_t)D.r, (uint64_t)D.r, CH, 32, true));
+  VLPET_TRY(make_map_bf16(&maps[8], gated ? w.Gu : w.Wu, (uint64_t)D.d, (uint64_t)(gated ? D.rg : D.r),
+                          (uint64_t)(gated ? D.rg : D.r), CH, 32, true));
   Params p;
   p.M = D.M; p.d = D.d; p.r = D.r; p.rg = gated ? D.rg : D.r; p.add_gate = D.add_gate;
   p.s = D.s; p.alpha = D.alpha; p.kappa = D.kappa;
