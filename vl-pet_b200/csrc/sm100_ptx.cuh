@@ -53,6 +53,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 24)) __trap();
   }
 }
+// Same, and the timed-out waiter first records who it is in host-mapped memory (vlpet_common.cuh: trap_buffer_dev), which
+// survives the fault: {code (source line), blockIdx.x, threadIdx.x, parity}.  vlpet_debug_last_trap() reads it back.
+__device__ __forceinline__ void mbar_wait_dbg(uint32_t bar, uint32_t parity, uint32_t* dbg, uint32_t code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) {
+      if (dbg) {
+        dbg[1] = blockIdx.x; dbg[2] = threadIdx.x; dbg[3] = parity; dbg[4] = bar;
+        dbg[0] = code;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
 
 // ---- proxy / tcgen05 fences -------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -266,6 +281,49 @@ __device__ __forceinline__ uint32_t pack2(f2 v) {   // fp32 pair -> packed bf16 
 }
 __device__ __forceinline__ void lds_f2x2(uint32_t addr, f2& a, f2& b) {
   asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+
+// ---- warp-converged issue ------------------------------------------------------------------------------------------
+// The "_e" forms are executed by ALL lanes of a converged warp; elect.sync inside picks the one lane that issues.  Operands
+// of tcgen05.mma / tcgen05.commit / cp.async.bulk.tensor live in uniform registers: when a divergent single-lane loop issues
+// them, ptxas wraps every instruction in an elect / R2UR.BROADCAST / branch sequence (~15 instructions, > 100 ns per MMA).
+__device__ __forceinline__ void umma_bf16_ss_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_e(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_e(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_e(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
 }
 
 }  // namespace ptx

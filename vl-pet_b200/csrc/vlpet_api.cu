@@ -1,5 +1,7 @@
 // C-ABI entry points of libvlpet.so (declared in include/vlpet.h): argument validation, dispatch between the
 // fused sm_100a kernels and the generic CUDA-core kernels, and the flat-bucket helpers (cast / AdamW / sumsq).
+#include <cstring>
+
 #include "vlpet_common.cuh"
 
 namespace vlpet {
@@ -8,6 +10,23 @@ char* tls_error_buffer() {
   static thread_local char buf[512] = {0};
   return buf;
 }
+
+static uint32_t *g_trap_host = nullptr, *g_trap_dev = nullptr;
+uint32_t* trap_buffer_dev() {
+  static bool once = []() {
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return false; }
+    memset(h, 0, 64);
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaGetLastError(); return false; }
+    g_trap_host = static_cast<uint32_t*>(h);
+    g_trap_dev = static_cast<uint32_t*>(d);
+    return true;
+  }();
+  (void)once;
+  return g_trap_dev;
+}
+const uint32_t* trap_buffer_host() { return g_trap_host; }
 
 int device_sm_count() {
   static int sms = []() {
@@ -143,6 +162,13 @@ int vlpet_layernorm_bwd(const void* x, const void* dy, const float* w, const flo
   return layernorm_bwd(x, dy, w, mean, rstd, dx, dw, db, M, d, static_cast<cudaStream_t>(stream));
 }
 
+// developer hook: who timed out?  {source line, block, thread, parity, barrier address} of the last barrier-wait trap
+__attribute__((visibility("default"))) int vlpet_debug_last_trap(uint32_t* out5) {
+  const uint32_t* h = vlpet::trap_buffer_host();
+  if (!h || !out5) return 1;
+  for (int i = 0; i < 5; ++i) out5[i] = h[i];
+  return 0;
+}
 // developer hook (not part of include/vlpet.h): phase timestamps of the fused K1 forward, see tools/trace_k1.py
 __attribute__((visibility("default"))) int vlpet_debug_set_k1_trace(void* dev_buf) {
   return vlpet::set_k1_trace(static_cast<unsigned long long*>(dev_buf));

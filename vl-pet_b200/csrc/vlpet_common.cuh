@@ -22,6 +22,10 @@ inline int fail(int code, const char* fmt, ...) {
   return code;
 }
 extern std::atomic<uint64_t> g_launches;
+// 16 x uint32 of host-mapped pinned memory (device view / host view; nullptr if the allocation failed): a kernel whose
+// barrier wait times out writes its identity there before it traps, see ptx::mbar_wait_dbg
+uint32_t* trap_buffer_dev();
+const uint32_t* trap_buffer_host();
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 #define VLPET_CUDA_OK(expr)                                                                           \

@@ -54,7 +54,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int m0 = (int)(tile / ntn) * BM, n0 = (int)(tile % ntn) * BN;
@@ -69,7 +69,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       constexpr uint32_t IDESC = ptx::umma_idesc_bf16_m128(BN);
       uint32_t it = 0, ti = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {

@@ -92,6 +92,7 @@ struct BParams {
   uint32_t thr16;
   float inv_keep;
   unsigned long long* trace;            // developer hook (tools/trace_k1_bwd.py), normally null
+  uint32_t* dbg;                        // host-mapped trap record (ptx::mbar_wait_dbg)
 };
 
 enum { B_XFULL = 0, B_XEMPTY = B_XFULL + SX, B_WFULL = B_XEMPTY + SX, B_WEMPTY = B_WFULL + SW, B_APFULL = B_WEMPTY + SW,
@@ -224,7 +225,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         for (int ph = 0; ph < 3; ++ph) {
           for (int c = 0; c < nkc; ++c, ++xi) {
             const uint32_t sx = xi % SX;
-            ptx::mbar_wait(bar(B_XEMPTY + sx), ((xi / SX) & 1) ^ 1);
+            ptx::mbar_wait_dbg(bar(B_XEMPTY + sx), ((xi / SX) & 1) ^ 1, p.dbg, __LINE__);
             const uint32_t xdst = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
             if (ph == 0) {
               ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), (GATED ? 2 : 1) * XCH_BYTES);
@@ -256,7 +257,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         for (int ph = 0; ph < 3; ++ph) {
           for (int c = 0; c < nkc; ++c, ++wi) {
             const uint32_t sw = wi % SW;
-            ptx::mbar_wait(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1);
+            ptx::mbar_wait_dbg(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1, p.dbg, __LINE__);
             const uint32_t wdst = smem_base + C::OFF_W + sw * C::WSLOT;
             if (ph == 0) {
               ptx::mbar_arrive_expect_tx(bar(B_WFULL + sw), (GATED ? 2 : 1) * C::WA_BYTES);
@@ -297,15 +298,15 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         if (ai > 0) {
           for (uint32_t b = 0; b < 2; ++b) {
             const uint32_t nb = (ai + 1 - b) >> 1;
-            if (nb > 0) ptx::mbar_wait(bar(B_ACCEMPTY + b), (nb - 1) & 1);
+            if (nb > 0) ptx::mbar_wait_dbg(bar(B_ACCEMPTY + b), (nb - 1) & 1, p.dbg, __LINE__);
           }
           ptx::tc_fence_after();
         }
         // ---- phase 1
         for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
           const uint32_t sx = xi % SX, sw = wi % SW;
-          ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
-          ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
+          ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
+          ptx::mbar_wait_dbg(bar(B_WFULL + sw), (wi / SW) & 1, p.dbg, __LINE__);
           ptx::tc_fence_after();
           const uint32_t x1s = smem_base + C::OFF_X + sx * (2 * XCH_BYTES), x2s = x1s + XCH_BYTES;
           const uint32_t wds = smem_base + C::OFF_W + sw * C::WSLOT, gds = wds + C::WA_BYTES;
@@ -326,8 +327,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         if (!GATED) {
           for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
             const uint32_t sx = xi % SX, sw = wi % SW;
-            ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
-            ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
+            ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
+            ptx::mbar_wait_dbg(bar(B_WFULL + sw), (wi / SW) & 1, p.dbg, __LINE__);
             ptx::tc_fence_after();
             const uint32_t dos = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
             const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT;
@@ -341,12 +342,12 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           ptx::umma_commit(bar(B_DZFULL));
         }
         if (GATED) {
-        ptx::mbar_wait(bar(B_ZQFULL), ti & 1);
+        ptx::mbar_wait_dbg(bar(B_ZQFULL), ti & 1, p.dbg, __LINE__);
         ptx::tc_fence_after();
         const uint32_t xi2 = xi, wi2 = wi, p2i0 = p2i;
         auto issue_dzdq = [&](int cc) {
           const uint32_t sx = (xi2 + cc) % SX, sw = (wi2 + cc) % SW, k = (p2i0 + cc) % SX;
-          ptx::mbar_wait(bar(B_DUDT + k), ((p2i0 + cc) / SX) & 1);
+          ptx::mbar_wait_dbg(bar(B_DUDT + k), ((p2i0 + cc) / SX) & 1, p.dbg, __LINE__);
           ptx::tc_fence_after();
           const uint32_t dus = smem_base + C::OFF_X + sx * (2 * XCH_BYTES), dts = dus + XCH_BYTES;
           const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT, gus = wus + C::WB_BYTES;
@@ -363,8 +364,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         };
         for (int c = 0; c < nkc; ++c, ++xi, ++wi, ++ui, ++p2i) {
           const uint32_t sw = wi % SW;
-          ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
-          ptx::mbar_wait(bar(B_UTEMPTY), (ui & 1) ^ 1);
+          ptx::mbar_wait_dbg(bar(B_WFULL + sw), (wi / SW) & 1, p.dbg, __LINE__);
+          ptx::mbar_wait_dbg(bar(B_UTEMPTY), (ui & 1) ^ 1, p.dbg, __LINE__);
           ptx::tc_fence_after();
           const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT, gus = wus + C::WB_BYTES;
 #pragma unroll
@@ -382,12 +383,12 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         ptx::umma_commit(bar(B_DZFULL));
         }
         // ---- phase 3
-        ptx::mbar_wait(bar(B_DAPFULL), ti & 1);
+        ptx::mbar_wait_dbg(bar(B_DAPFULL), ti & 1, p.dbg, __LINE__);
         ptx::tc_fence_after();
         for (int c = 0; c < nkc; ++c, ++xi, ++wi, ++ai) {
           const uint32_t sw = wi % SW, b = ai & 1;
-          ptx::mbar_wait(bar(B_WFULL + sw), (wi / SW) & 1);
-          ptx::mbar_wait(bar(B_ACCEMPTY + b), ((ai >> 1) & 1) ^ 1);
+          ptx::mbar_wait_dbg(bar(B_WFULL + sw), (wi / SW) & 1, p.dbg, __LINE__);
+          ptx::mbar_wait_dbg(bar(B_ACCEMPTY + b), ((ai >> 1) & 1) ^ 1, p.dbg, __LINE__);
           ptx::tc_fence_after();
           const uint32_t gus = smem_base + C::OFF_W + sw * C::WSLOT, wds = gus + C::WB_BYTES, gds = wds + C::WA_BYTES;
           const uint32_t tacc = tmem_base + TM_ACC + b * ACC_STRIDE;
@@ -418,18 +419,18 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         if (!GATED) xi += nkc;  // ungated: phase-2 stages are released by the MMA warp as well
         for (int c = 0; GATED && c < nkc; ++c, ++xi, ++p2i) {
           const uint32_t sx = xi % SX, k = p2i % SX;
-          ptx::mbar_wait(bar(B_DUDT + k), (p2i / SX) & 1);
+          ptx::mbar_wait_dbg(bar(B_DUDT + k), (p2i / SX) & 1, p.dbg, __LINE__);
           const uint32_t src = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
           ptx::tma_store_2d(&tm_du, src, c * CH, row0);
           ptx::tma_store_2d(&tm_dt, src + XCH_BYTES, c * CH, row0);
           ptx::tma_store_commit();
-          ptx::mbar_wait(bar(B_DZQDONE + k), (p2i / SX) & 1);   // dz/dq MMAs finished reading du_c / dt_c
+          ptx::mbar_wait_dbg(bar(B_DZQDONE + k), (p2i / SX) & 1, p.dbg, __LINE__);   // dz/dq MMAs finished reading du_c / dt_c
           ptx::tma_store_wait_read0();
           ptx::mbar_arrive(bar(B_XEMPTY + sx));
         }
         for (int c = 0; c < nkc; ++c, ++xi, ++p3i) {
           const uint32_t sx = xi % SX, k = p3i % SX;
-          ptx::mbar_wait(bar(B_OUTRDY + k), (p3i / SX) & 1);
+          ptx::mbar_wait_dbg(bar(B_OUTRDY + k), (p3i / SX) & 1, p.dbg, __LINE__);
           const uint32_t src = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
           if (GATED) ptx::tma_store_2d(&tm_dx1, src, c * CH, row0);
           ptx::tma_store_2d(&tm_dx2, src + XCH_BYTES, c * CH, row0);
@@ -474,7 +475,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     }
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // epilogue warps only
     const f2 half2 = mk2(0.5f, 0.5f), kappa2 = mk2(p.kappa, p.kappa), alpha2 = mk2(p.alpha, p.alpha);
-    const f2 s2 = mk2(p.s, p.s), sa2 = mk2(p.s * p.alpha, p.s * p.alpha);
+    const f2 s2 = mk2(p.s, p.s);
     const float s_keep = p.s * p.inv_keep;
     // smem address of the 16-byte group holding columns [k, k+8) of this thread's row in z/da (which=0), q (1), dp (2)
     auto small_addr = [&](int which, int k) -> uint32_t {
@@ -492,7 +493,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       const bool row_ok = grow < p.M;
       // ---- epilogue 1 (APFULL also implies that every MMA of the previous tile, which read z/q/da/dp, has completed)
       VLPET_TRACE_B(0);
-      ptx::mbar_wait(bar(B_APFULL), ti & 1);
+      ptx::mbar_wait_dbg(bar(B_APFULL), ti & 1, p.dbg, __LINE__);
       VLPET_TRACE_B(1);
       ptx::tc_fence_after();
       if (GATED || branch == 0) {
@@ -539,7 +540,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       if (!GATED) xi += nkc;
       for (int c = 0; GATED && c < nkc; ++c, ++xi, ++ui, ++p2i) {
         const uint32_t sx = xi % SX;
-        ptx::mbar_wait(bar(B_UTFULL), ui & 1);
+        ptx::mbar_wait_dbg(bar(B_UTFULL), ui & 1, p.dbg, __LINE__);
         VLPET_TRACE_B(3 + 3 * c);
         ptx::tc_fence_after();
         uint32_t u[16], t[16];
@@ -548,7 +549,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_UTEMPTY));
-        ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+        ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
         VLPET_TRACE_B(4 + 3 * c);
         const uint32_t x2row = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t dorow = x2row + XCH_BYTES;
@@ -566,33 +567,31 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           lds_f2x2(tabu + g * 32 + 16, abu[2], abu[3]);
           lds_f2x2(thgb + g * 32, hgb[0], hgb[1]);
           lds_f2x2(thgb + g * 32 + 16, hgb[2], hgb[3]);
-          f2 sc[4] = {s2, s2, s2, s2}, sca[4] = {sa2, sa2, sa2, sa2};   // s * mask and alpha * s * mask
+          uint64_t h0 = 0, h1 = 0;
           if (DROP) {
-            const uint64_t h0 = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
-            const uint64_t h1 = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t two = (uint32_t)((e >> 1 ? h1 : h0) >> (32 * (e & 1)));
-              sc[e] = mk2(((two & 0xffffu) >= p.thr16) ? s_keep : 0.f, ((two >> 16) >= p.thr16) ? s_keep : 0.f);
-              sca[e] = mul2(sc[e], alpha2);
-            }
+            h0 = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
+            h1 = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
           }
           const f2 q2 = mk2(0.25f, 0.25f), nq2 = mk2(-0.25f, -0.25f);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = g * 8 + e * 2;
-            const f2 dof = bf2_to_f2(dv[e]);
-            const f2 dh = mul2(sc[e], dof);                                       // dh = s m dout
+            f2 sce = s2;                                                          // s * dropout mask of this pair
+            if (DROP) {
+              const uint32_t two = (uint32_t)((e >> 1 ? h1 : h0) >> (32 * (e & 1)));
+              sce = mk2(((two & 0xffffu) >= p.thr16) ? s_keep : 0.f, ((two >> 16) >= p.thr16) ? s_keep : 0.f);
+            }
+            const f2 dh = mul2(sce, bf2_to_f2(dv[e]));                            // dh = s m dout
             const f2 th = tanh2(fma2(half2, mk2u(t[j], t[j + 1]), hgb[e]));      // G = 0.5 + 0.5 th
             const f2 gg = fma2(nq2, mul2(th, th), q2);                            // G (1 - G) = 0.25 (1 - th^2)
             f2 du, dt;
             if (mulgate) {
               f2 y1 = fma2(kappa2, bf2_to_f2(xv[e]), abu[e]);                     // kappa x2 + alpha bu
               y1 = fma2(alpha2, mk2u(u[j], u[j + 1]), y1);                        // + alpha U
-              du = mul2(mul2(sca[e], dof), fma2(half2, th, half2));               // alpha dh G
+              du = mul2(mul2(alpha2, dh), fma2(half2, th, half2));                // alpha dh G
               dt = mul2(mul2(dh, y1), gg);
             } else {
-              du = mul2(sca[e], dof);
+              du = mul2(alpha2, dh);
               dt = mul2(dh, gg);
             }
             ou[e] = pack2(du);
@@ -609,7 +608,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       }
       // ---- epilogue 3: da = dz * gelu_new'(A + bd) (branch 0), dp = dq * gelu_new'(P + gbd) (branch 1)
       VLPET_TRACE_B(40);
-      ptx::mbar_wait(bar(B_DZFULL), ti & 1);
+      ptx::mbar_wait_dbg(bar(B_DZFULL), ti & 1, p.dbg, __LINE__);
       VLPET_TRACE_B(41);
       ptx::tc_fence_after();
       if (GATED || branch == 0) {
@@ -648,7 +647,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       // ---- epilogue 4, per 64-column chunk: dx1, dx2
       for (int c = 0; c < nkc; ++c, ++xi, ++ai) {
         const uint32_t sx = xi % SX, b = ai & 1;
-        ptx::mbar_wait(bar(B_ACCFULL + b), (ai >> 1) & 1);
+        ptx::mbar_wait_dbg(bar(B_ACCFULL + b), (ai >> 1) & 1, p.dbg, __LINE__);
         VLPET_TRACE_B(43 + 3 * c);
         ptx::tc_fence_after();
         const uint32_t tacc = lane_addr + TM_ACC + b * ACC_STRIDE + cg * 16;
@@ -659,7 +658,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_ACCEMPTY + b));
-        ptx::mbar_wait(bar(B_XFULL + sx), (xi / SX) & 1);
+        ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
         VLPET_TRACE_B(44 + 3 * c);
         const uint32_t dorow = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t o2row = dorow + XCH_BYTES;
@@ -676,15 +675,10 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             lds_f2x2(thgb + g * 32, hgb[0], hgb[1]);
             lds_f2x2(thgb + g * 32 + 16, hgb[2], hgb[3]);
           }
-          f2 sc[4] = {s2, s2, s2, s2};
+          uint64_t h0 = 0, h1 = 0;
           if (DROP) {
-            const uint64_t h0 = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
-            const uint64_t h1 = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t two = (uint32_t)((e >> 1 ? h1 : h0) >> (32 * (e & 1)));
-              sc[e] = mk2(((two & 0xffffu) >= p.thr16) ? s_keep : 0.f, ((two >> 16) >= p.thr16) ? s_keep : 0.f);
-            }
+            h0 = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
+            h1 = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -692,7 +686,12 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             const f2 g2p = mk2u(g2[j], g2[j + 1]);
             if (GATED) {
               const f2 dof = bf2_to_f2(dv[e]);
-              f2 dy1 = mul2(sc[e], dof);                                             // dh = s m dout
+              f2 sce = s2;
+              if (DROP) {
+                const uint32_t two = (uint32_t)((e >> 1 ? h1 : h0) >> (32 * (e & 1)));
+                sce = mk2(((two & 0xffffu) >= p.thr16) ? s_keep : 0.f, ((two >> 16) >= p.thr16) ? s_keep : 0.f);
+              }
+              f2 dy1 = mul2(sce, dof);                                               // dh = s m dout
               if (mulgate) {
                 const f2 th = tanh2(fma2(half2, mk2u(t[j], t[j + 1]), hgb[e]));
                 dy1 = mul2(dy1, fma2(half2, th, half2));                             // dh G
@@ -822,6 +821,7 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   p.seed = D.seed;
   p.seed_dev = D.seed_dev;
   p.trace = g_trace_b;
+  p.dbg = trap_buffer_dev();
   p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
   p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
   int rc = 0;

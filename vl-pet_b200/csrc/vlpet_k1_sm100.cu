@@ -173,6 +173,7 @@ struct Params {
   uint32_t thr16;     // 0 = no dropout
   float inv_keep;
   unsigned long long* trace;  // developer hook (tools/trace_k1.py), normally null
+  uint32_t* dbg;              // host-mapped trap record (ptx::mbar_wait_dbg)
 };
 
 // barrier slots (8 bytes each) inside the barrier block
@@ -282,41 +283,35 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
 
   if (warp == 0) {
     // ===================================== TMA producer: phase-A x chunks (HBM stream) =====================================
-    // (all role warps run converged with one elected lane issuing, see the MMA warp)
-    {
+    // (every role loop is run by ONE elected thread, see the MMA warp)
+    if (ptx::elect_one()) {
       ItemCursor it; it.init(p, nkc, num_items);
       uint32_t n = 0, na = 0;
       for (; it.valid(); it.next()) {
         const int row0 = (int)(it.tile * TILE_M);
         for (int k = 0; k < nkc; ++k, ++n) {
           const uint32_t sl = n % NXA;
-          ptx::mbar_wait(bar(B_XAEMPTY + sl), ((n / NXA) & 1) ^ 1);
+          ptx::mbar_wait_dbg(bar(B_XAEMPTY + sl), ((n / NXA) & 1) ^ 1, p.dbg, __LINE__);
           const uint32_t dst = smem_base + C::OFF_XA + sl * (2 * XCH_BYTES);
-          if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(bar(B_XAFULL + sl), (GATED ? 2 : 1) * XCH_BYTES);
-            // first touch of data that phase B reads again one tile later: ask L2 to keep it
-            if (GATED) ptx::tma_load_2d_hint(dst, &tm_x1, k * CH, row0, bar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
-            ptx::tma_load_2d_hint(dst + XCH_BYTES, &tm_x2, k * CH, row0, bar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
-          }
-          __syncwarp();
+          ptx::mbar_arrive_expect_tx(bar(B_XAFULL + sl), (GATED ? 2 : 1) * XCH_BYTES);
+          // first touch of data that phase B reads again one tile later: ask L2 to keep it
+          if (GATED) ptx::tma_load_2d_hint(dst, &tm_x1, k * CH, row0, bar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
+          ptx::tma_load_2d_hint(dst + XCH_BYTES, &tm_x2, k * CH, row0, bar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
           // the weight chunks the same MMA step consumes: Wd_k, Gd_k (always L2 hits)
 #pragma unroll
           for (int m = 0; m < (GATED ? 2 : 1); ++m, ++na) {
             const uint32_t sw = na % NWA;
-            ptx::mbar_wait(bar(B_WAEMPTY + sw), ((na / NWA) & 1) ^ 1);
-            if (ptx::elect_one()) {
-              ptx::mbar_arrive_expect_tx(bar(B_WAFULL + sw), C::WA_BYTES);
-              ptx::tma_load_2d_hint(smem_base + C::OFF_WA + sw * C::WA_BYTES, m ? &tm_gd : &tm_wd, k * CH, 0, bar(B_WAFULL + sw),
-                                    ptx::L2_EVICT_LAST);
-            }
-            __syncwarp();
+            ptx::mbar_wait_dbg(bar(B_WAEMPTY + sw), ((na / NWA) & 1) ^ 1, p.dbg, __LINE__);
+            ptx::mbar_arrive_expect_tx(bar(B_WAFULL + sw), C::WA_BYTES);
+            ptx::tma_load_2d_hint(smem_base + C::OFF_WA + sw * C::WA_BYTES, m ? &tm_gd : &tm_wd, k * CH, 0, bar(B_WAFULL + sw),
+                                  ptx::L2_EVICT_LAST);
           }
         }
       }
     }
   } else if (warp == 3) {
     // ===================================== TMA producer: phase-B weights Wu_c, Gu_c (always L2 hits) ====================
-    {
+    if (ptx::elect_one()) {
       uint32_t nb = 0;
       ItemCursor it; it.init(p, nkc, num_items);
       for (; it.valid(); it.next()) {
@@ -324,28 +319,26 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
 #pragma unroll
           for (int m = 0; m < (GATED ? 2 : 1); ++m, ++nb) {
             const uint32_t sl = nb % NWB;
-            ptx::mbar_wait(bar(B_WBEMPTY + sl), ((nb / NWB) & 1) ^ 1);
-            if (ptx::elect_one()) {
-              ptx::mbar_arrive_expect_tx(bar(B_WBFULL + sl), C::WB_BYTES);
+            ptx::mbar_wait_dbg(bar(B_WBEMPTY + sl), ((nb / NWB) & 1) ^ 1, p.dbg, __LINE__);
+            ptx::mbar_arrive_expect_tx(bar(B_WBFULL + sl), C::WB_BYTES);
 #pragma unroll
-              for (int kb = 0; kb < C::KBF; ++kb)
-                ptx::tma_load_2d_hint(smem_base + C::OFF_WB + sl * C::WB_BYTES + kb * (CH * CH * 2), m ? &tm_gu : &tm_wu, kb * CH,
-                                      c * CH, bar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
-              if (C::REM)
-                ptx::tma_load_2d_hint(smem_base + C::OFF_WB + sl * C::WB_BYTES + C::KBF * (CH * CH * 2), m ? &tm_gu_t : &tm_wu_t,
-                                      C::KBF * CH, c * CH, bar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
-            }
-            __syncwarp();
+            for (int kb = 0; kb < C::KBF; ++kb)
+              ptx::tma_load_2d_hint(smem_base + C::OFF_WB + sl * C::WB_BYTES + kb * (CH * CH * 2), m ? &tm_gu : &tm_wu, kb * CH,
+                                    c * CH, bar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
+            if (C::REM)
+              ptx::tma_load_2d_hint(smem_base + C::OFF_WB + sl * C::WB_BYTES + C::KBF * (CH * CH * 2), m ? &tm_gu_t : &tm_wu_t,
+                                    C::KBF * CH, c * CH, bar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    // The whole warp runs this loop converged and one elected lane issues: operands of tcgen05.mma / tcgen05.commit live in
-    // uniform registers, and a divergent single-lane loop made ptxas wrap EVERY issue in an elect / broadcast / branch
-    // sequence (~15 instructions, >100 ns per MMA measured with tools/trace_k1.py -- the whole kernel was issue-bound).
-    {
+    // ONE thread chosen by elect.sync runs the whole loop (the CUTLASS idiom).  Operands of tcgen05.mma / tcgen05.commit /
+    // cp.async.bulk.tensor live in uniform registers: under `if (lane == 0)` ptxas wrapped EVERY issue in an elect /
+    // R2UR.BROADCAST / branch sequence (~15 instructions, > 100 ns per MMA measured with tools/trace_k1.py -- the whole
+    // kernel was issue-bound); under an elect predicate it keeps the descriptors in uniform registers.
+    if (ptx::elect_one()) {
       constexpr uint32_t IDESC_A = ptx::umma_idesc_bf16_m128(R);
       constexpr uint32_t IDESC_B = ptx::umma_idesc_bf16_m128(CH);
       uint32_t nxa = 0, na = 0, nb = 0, ui = 0, ti = 0;
@@ -354,85 +347,75 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       auto ready_a = [&]() -> bool {
         bool r = ptx::mbar_test(bar(B_XAFULL + nxa % NXA), (nxa / NXA) & 1) && ptx::mbar_test(bar(B_WAFULL + na % NWA), (na / NWA) & 1);
         if (GATED) r = r && ptx::mbar_test(bar(B_WAFULL + (na + 1) % NWA), ((na + 1) / NWA) & 1);
-        return __all_sync(0xffffffffu, r);
+        return r;
       };
       auto ready_b = [&]() -> bool {
         bool r = ptx::mbar_test(bar(B_UTEMPTY), (ui & 1) ^ 1) && ptx::mbar_test(bar(B_WBFULL + nb % NWB), (nb / NWB) & 1);
         if (GATED) r = r && ptx::mbar_test(bar(B_WBFULL + (nb + 1) % NWB), ((nb + 1) / NWB) & 1);
-        return __all_sync(0xffffffffu, r);
+        return r;
       };
       // one phase-A step: A += x2_k Wd_k^T ; P += x1_k Gd_k^T
       auto step_a = [&](int k) {
         const uint32_t sx = nxa % NXA;
-        ptx::mbar_wait(bar(B_XAFULL + sx), (nxa / NXA) & 1);
+        ptx::mbar_wait_dbg(bar(B_XAFULL + sx), (nxa / NXA) & 1, p.dbg, __LINE__);
         const uint32_t x1s = smem_base + C::OFF_XA + sx * (2 * XCH_BYTES), x2s = x1s + XCH_BYTES;
 #pragma unroll
         for (int m = 0; m < (GATED ? 2 : 1); ++m, ++na) {
           const uint32_t sl = na % NWA;
-          ptx::mbar_wait(bar(B_WAFULL + sl), (na / NWA) & 1);
+          ptx::mbar_wait_dbg(bar(B_WAFULL + sl), (na / NWA) & 1, p.dbg, __LINE__);
           ptx::tc_fence_after();
           const uint32_t ws = smem_base + C::OFF_WA + sl * C::WA_BYTES;
           const uint64_t adesc = ptx::umma_desc_kmajor_sw128(m ? x1s : x2s), bdesc = ptx::umma_desc_kmajor_sw128(ws);
-          if (ptx::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < CH / 16; ++ks)   // +32 bytes per K step = +2 in the descriptor's 16-byte address units
-              ptx::umma_bf16_ss(tmem_base + (m ? TM_P : TM_A), adesc + 2 * ks, bdesc + 2 * ks, IDESC_A, (k > 0 || ks > 0) ? 1u : 0u);
-            ptx::umma_commit(bar(B_WAEMPTY + sl));
-            if (m == (GATED ? 1 : 0)) ptx::umma_commit(bar(B_XAEMPTY + sx));
-          }
-          __syncwarp();
+          for (int ks = 0; ks < CH / 16; ++ks)   // +32 bytes per K step = +2 in the descriptor's 16-byte address units
+            ptx::umma_bf16_ss(tmem_base + (m ? TM_P : TM_A), adesc + 2 * ks, bdesc + 2 * ks, IDESC_A, (k > 0 || ks > 0) ? 1u : 0u);
+          ptx::umma_commit(bar(B_WAEMPTY + sl));
+          if (m == (GATED ? 1 : 0)) ptx::umma_commit(bar(B_XAEMPTY + sx));
         }
         ++nxa;
       };
       // one phase-B chunk: U = z Wu_c^T ; T = q Gu_c^T  (z, q: A operand from TMEM)
       auto chunk_b = [&]() {
-        ptx::mbar_wait(bar(B_UTEMPTY), (ui & 1) ^ 1);
+        ptx::mbar_wait_dbg(bar(B_UTEMPTY), (ui & 1) ^ 1, p.dbg, __LINE__);
 #pragma unroll
         for (int m = 0; m < (GATED ? 2 : 1); ++m, ++nb) {
           const uint32_t sl = nb % NWB;
-          ptx::mbar_wait(bar(B_WBFULL + sl), (nb / NWB) & 1);
+          ptx::mbar_wait_dbg(bar(B_WBFULL + sl), (nb / NWB) & 1, p.dbg, __LINE__);
           ptx::tc_fence_after();
           const uint32_t ws = smem_base + C::OFF_WB + sl * C::WB_BYTES;
           const uint64_t d128 = ptx::umma_desc_kmajor_sw128(ws), d64 = ptx::umma_desc_kmajor_sw64(ws + C::KBF * (CH * CH * 2));
           const uint32_t ta = tmem_base + (m ? TM_Q : TM_Z), td = tmem_base + TM_UT + (m ? CH : 0);
-          if (ptx::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < R / 16; ++ks) {
-              const int kb = ks / 4, kin = ks % 4;
-              const uint64_t bdesc = (kb < C::KBF) ? d128 + (uint64_t)(kb * (CH * CH * 2 / 16) + 2 * kin) : d64 + (uint64_t)(2 * kin);
-              ptx::umma_bf16_ts(td, ta + 8 * ks, bdesc, IDESC_B, ks > 0);
-            }
-            ptx::umma_commit(bar(B_WBEMPTY + sl));
-            if (m == (GATED ? 1 : 0)) ptx::umma_commit(bar(B_UTFULL));
+          for (int ks = 0; ks < R / 16; ++ks) {
+            const int kb = ks / 4, kin = ks % 4;
+            const uint64_t bdesc = (kb < C::KBF) ? d128 + (uint64_t)(kb * (CH * CH * 2 / 16) + 2 * kin) : d64 + (uint64_t)(2 * kin);
+            ptx::umma_bf16_ts(td, ta + 8 * ks, bdesc, IDESC_B, ks > 0);
           }
-          __syncwarp();
+          ptx::umma_commit(bar(B_WBEMPTY + sl));
+          if (m == (GATED ? 1 : 0)) ptx::umma_commit(bar(B_UTFULL));
         }
         ++ui;
       };
       ItemCursor it; it.init(p, nkc, num_items);
       if (it.valid()) {
-        for (int k = 0; k < nkc; ++k) { step_a(k); if (lane == 0 && k < 12) VLPET_TR(100 + k); }
-        if (ptx::elect_one()) ptx::umma_commit(bar(B_APFULL));
-        __syncwarp();
+        for (int k = 0; k < nkc; ++k) { step_a(k); if (k < 12) VLPET_TR(100 + k); }
+        ptx::umma_commit(bar(B_APFULL));
       }
       for (; it.valid(); it.next(), ++ti) {
         const int nB = it.ce - it.cb;
         const int nA = (it.w + it.stride < num_items) ? nkc : 0;
         // z/q of this item are in TMEM, and A/P have been drained: phase B of this item and phase A of the next may run
-        ptx::mbar_wait(bar(B_ZQFULL), ti & 1);
+        ptx::mbar_wait_dbg(bar(B_ZQFULL), ti & 1, p.dbg, __LINE__);
         ptx::tc_fence_after();
         int kb = 0, ka = 0;
         uint32_t spins = 0;
         while (kb < nB || ka < nA) {
           bool did = false;
-          if (kb < nB && ready_b()) { chunk_b(); if (lane == 0 && ti == 0 && kb < 12) VLPET_TR(64 + 2 * kb); ++kb; did = true; }
+          if (kb < nB && ready_b()) { chunk_b(); if (ti == 0 && kb < 12) VLPET_TR(64 + 2 * kb); ++kb; did = true; }
           if (ka < nA && ready_a()) {
             step_a(ka);
-            if (lane == 0 && ti == 0 && ka < 12) VLPET_TR(65 + 2 * ka);
-            if (++ka == nA) {
-              if (ptx::elect_one()) ptx::umma_commit(bar(B_APFULL));
-              __syncwarp();
-            }
+            if (ti == 0 && ka < 12) VLPET_TR(65 + 2 * ka);
+            if (++ka == nA) ptx::umma_commit(bar(B_APFULL));
             did = true;
           }
           if (did) spins = 0;
@@ -444,8 +427,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     // ===================================== phase-B x manager: TMA load of x1_c / x2_c, TMA store of out_c ==============
     // The residual chunks of ALL work items form one stream of entries; entry e lives in XB slot e % NXB.  This thread
     // frees a slot itself (its store has read it), so it can refill it right away: no empty barrier.
-    {
-      const bool leader = ptx::elect_one();   // the bulk-group waits below belong to the thread that issued the stores
+    if (ptx::elect_one()) {
       ItemCursor ld; ld.init(p, nkc, num_items);
       ItemCursor st = ld;
       int lc = ld.valid() ? ld.cb : 0, sc = lc;
@@ -453,31 +435,25 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       auto load = [&](uint32_t sl) {
         const uint32_t dst = smem_base + C::OFF_XB + sl * (2 * XCH_BYTES);
         const int row0 = (int)(ld.tile * TILE_M);
-        if (leader) {
-          ptx::mbar_arrive_expect_tx(bar(B_XBFULL + sl), 2 * XCH_BYTES);
-          ptx::tma_load_2d_hint(dst, &tm_x1, lc * CH, row0, bar(B_XBFULL + sl), ptx::L2_EVICT_FIRST);   // last use
-          ptx::tma_load_2d_hint(dst + XCH_BYTES, &tm_x2, lc * CH, row0, bar(B_XBFULL + sl), ptx::L2_EVICT_FIRST);
-        }
-        __syncwarp();
+        ptx::mbar_arrive_expect_tx(bar(B_XBFULL + sl), 2 * XCH_BYTES);
+        ptx::tma_load_2d_hint(dst, &tm_x1, lc * CH, row0, bar(B_XBFULL + sl), ptx::L2_EVICT_FIRST);   // last use
+        ptx::tma_load_2d_hint(dst + XCH_BYTES, &tm_x2, lc * CH, row0, bar(B_XBFULL + sl), ptx::L2_EVICT_FIRST);
         if (++lc == ld.ce) { ld.next(); lc = ld.cb; }
       };
       for (uint32_t i = 0; i < NXB && ld.valid(); ++i) load(i);
       for (; st.valid(); ++e_st) {
         const uint32_t sl = e_st % NXB;
-        ptx::mbar_wait(bar(B_OUTRDY + sl), (e_st / NXB) & 1);
-        if (lane == 0 && e_st < 12) VLPET_TR(128 + 2 * e_st);
-        if (leader) {
-          ptx::tma_store_2d_hint(&tm_out, smem_base + C::OFF_XB + sl * (2 * XCH_BYTES), sc * CH, (int)(st.tile * TILE_M),
-                                 ptx::L2_EVICT_FIRST);   // never re-read by this kernel
-          ptx::tma_store_commit();
-          ptx::tma_store_wait_read0();
-        }
-        __syncwarp();
-        if (lane == 0 && e_st < 12) VLPET_TR(129 + 2 * e_st);
+        ptx::mbar_wait_dbg(bar(B_OUTRDY + sl), (e_st / NXB) & 1, p.dbg, __LINE__);
+        if (e_st < 12) VLPET_TR(128 + 2 * e_st);
+        ptx::tma_store_2d_hint(&tm_out, smem_base + C::OFF_XB + sl * (2 * XCH_BYTES), sc * CH, (int)(st.tile * TILE_M),
+                               ptx::L2_EVICT_FIRST);   // never re-read by this kernel
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_read0();
+        if (e_st < 12) VLPET_TR(129 + 2 * e_st);
         if (++sc == st.ce) { st.next(); sc = st.cb; }
         if (ld.valid()) load(sl);
       }
-      if (leader) ptx::tma_store_wait_all0();
+      ptx::tma_store_wait_all0();
     }
   } else if (warp >= 4) {
     // ===================================== epilogue warps =====================================
@@ -500,7 +476,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       const int cb = it.cb, ce = it.ce;
       // ---- epilogue 1: z = gelu_new(A + bd) (cg 0,1) / q = gelu_new(P + gbd) (cg 2,3) -> packed bf16 into TMEM
       VLPET_TRACE(0);
-      ptx::mbar_wait(bar(B_APFULL), ti & 1);
+      ptx::mbar_wait_dbg(bar(B_APFULL), ti & 1, p.dbg, __LINE__);
       VLPET_TRACE(1);
       ptx::tc_fence_after();
       const int branch = cg >> 1;
@@ -534,7 +510,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       for (int c = cb; c < ce; ++c, ++ui, ++e) {
         const uint32_t sl = e % NXB;
         const int col0 = c * CH + cg * 16;  // first of this thread's 16 output columns
-        ptx::mbar_wait(bar(B_UTFULL), ui & 1);
+        ptx::mbar_wait_dbg(bar(B_UTFULL), ui & 1, p.dbg, __LINE__);
         VLPET_TRACE(3 + 4 * (c - cb));
         ptx::tc_fence_after();
         uint32_t u[16], t[16];
@@ -545,7 +521,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_UTEMPTY));  // accumulators are in registers: the MMA warp may overwrite them
         VLPET_TRACE(4 + 4 * (c - cb));
-        ptx::mbar_wait(bar(B_XBFULL + sl), (e / NXB) & 1);
+        ptx::mbar_wait_dbg(bar(B_XBFULL + sl), (e / NXB) & 1, p.dbg, __LINE__);
         VLPET_TRACE(5 + 4 * (c - cb));
         const uint32_t x1row = smem_base + C::OFF_XB + sl * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t x2row = x1row + XCH_BYTES;
@@ -725,6 +701,7 @@ int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const Vlp
   p.seed = D.seed;
   p.seed_dev = D.seed_dev;
   p.trace = g_trace;
+  p.dbg = trap_buffer_dev();
   {  // Whole waves of tiles run one tile per CTA.  The tiles of the last, partial wave (all tiles when M is small) are
      // split over several CTAs each (largest divisor of nkc that still fits the wave): the tail costs one phase A plus
      // nkc/nsplit chunks instead of a full tile time.

@@ -44,6 +44,7 @@ struct WgradArgs {
   int64_t Mtok;
   int d, nout, NB;      // NB = MMA N (multiple of 16, >= nout + (bias ? 1 : 0))
   int ncolgroups;       // ceil(d / (SPC*SLAB))
+  uint32_t* dbg;        // host-mapped trap record (ptx::mbar_wait_dbg)
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -75,11 +76,11 @@ wgrad_sm100_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       for (int64_t i = 0; i < my_steps; ++i) {
         const uint32_t s = (uint32_t)(i % NST);
         const int tok0 = (int)((blockIdx.y + i * gridDim.y) * KT);
-        ptx::mbar_wait(bar(NST + s), (uint32_t)((i / NST) & 1) ^ 1);
+        ptx::mbar_wait_dbg(bar(NST + s), (uint32_t)((i / NST) & 1) ^ 1, p.dbg, __LINE__);
         const uint32_t dst = smem_base + s * STAGE;
         ptx::mbar_arrive_expect_tx(bar(s), (uint32_t)(nslab * 2 * BOX_BYTES + B_STAGE));
         for (int sl = 0; sl < nslab; ++sl) {
@@ -91,11 +92,11 @@ wgrad_sm100_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t idesc = ptx::umma_idesc_bf16_m128_major((uint32_t)p.NB, 1u, 1u);
       for (int64_t i = 0; i < my_steps; ++i) {
         const uint32_t s = (uint32_t)(i % NST);
-        ptx::mbar_wait(bar(s), (uint32_t)((i / NST) & 1));
+        ptx::mbar_wait_dbg(bar(s), (uint32_t)((i / NST) & 1), p.dbg, __LINE__);
         ptx::tc_fence_after();
         const uint32_t a0 = smem_base + s * STAGE, b0 = a0 + A_STAGE;
         for (int sl = 0; sl < nslab; ++sl) {
@@ -119,7 +120,7 @@ wgrad_sm100_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) {
     const int quarter = warp % 4;
     const int ew = warp - 2;                 // 0..3
     const int row = quarter * 32 + lane;
-    ptx::mbar_wait(bar(2 * NST), 0);
+    ptx::mbar_wait_dbg(bar(2 * NST), 0, p.dbg, __LINE__);
     ptx::tc_fence_after();
     float* out = p.out[pair];
     float* bias = p.bias[pair];
@@ -211,6 +212,7 @@ int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void
   a.Mtok = Mtok; a.d = d; a.nout = nout;
   a.NB = (nbmax + 15) / 16 * 16;
   a.ncolgroups = (d / SLAB + SPC - 1) / SPC;
+  a.dbg = trap_buffer_dev();
   static bool attr_set = false;
   if (!attr_set) {
     VLPET_CUDA_OK(cudaFuncSetAttribute(wgrad_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
