@@ -167,6 +167,45 @@ def test_k1_fused_forward_matches_oracle(V, M, d, r, rg, add_gate, s):
     assert rel(out, gen) < 2 * TOL_BF16      # every row: fused vs generic CUDA path
 
 
+@pytest.mark.parametrize("M,d,r,rg,add_gate,p_drop", [
+    (129, 768, 96, 96, False, 0.0),            # one full pair-tile: the second CTA of the pair owns a 1-row tile
+    (128 * 3, 768, 96, 96, False, 0.0),        # odd number of tiles: the last pair's second CTA works on nothing
+    (5000, 768, 48, 96, True, 0.0),            # padded rank, add-gate
+    (4111, 512, 32, 32, False, 0.1),           # R = 32 (a single 64-byte-swizzled block), dropout stream
+    (148 * 128 * 4 + 1000, 768, 96, 96, False, 0.1),   # several pair-tiles per pair + split tail (the auto-selected regime)
+])
+def test_k1_forward_cta_pairs_match_single_ctas(V, M, d, r, rg, add_gate, p_drop):
+    """The cta_group::2 variant of the fused forward (one UMMA across a CTA pair, each CTA staging half of every weight
+    chunk) must reproduce the single-CTA kernel bit for bit: same products, same accumulation order per element."""
+    import ctypes as C
+    from vlpet_b200 import _lib as L
+    L.lib.vlpet_debug_set_k1_pairs.argtypes = [C.c_int]
+    rng = np.random.default_rng(M + r)
+    x1, x2, _, p = random_large_case(rng, M, d, r, rg)
+    bf = torch.bfloat16
+    args = (dev(x1, bf), dev(x2, bf), [dev(p["Wd"], bf)], [dev(p["bd"], bf)], dev(p["Wu"], bf), dev(p["bu"], bf),
+            [dev(p[k], bf) for k in ("Gd", "gbd", "Gu", "gbu")])
+    scfg = V.PetSiteConfig(gate="large", add_gate=add_gate, s=0.7, p_drop=p_drop, impl="fused")
+    outs = []
+    try:
+        for mode in (0, 1):
+            L.lib.vlpet_debug_set_k1_pairs(mode)
+            torch.manual_seed(1234)
+            import vlpet_b200.functional as F_
+            F_._seed_counter[0] = 77          # same dropout stream for both runs
+            with torch.no_grad():
+                outs.append(V.gated_pet(*args, scfg, training=p_drop > 0))
+        torch.cuda.synchronize()
+    finally:
+        L.lib.vlpet_debug_set_k1_pairs(-1)
+    assert torch.equal(outs[0], outs[1])
+    ref, _ = O.gated_pet_fwd(bf16_round(x1[:200]), bf16_round(x2[:200]),
+                             {k: bf16_round(v).reshape(np.shape(v)) for k, v in p.items()},
+                             O.PetConfig(gate="large", add_gate=add_gate, s=0.7))
+    if p_drop == 0.0:
+        bf16_check(outs[1][:200].to(torch.float64).cpu().numpy(), ref, TOL_BF16)
+
+
 @pytest.mark.parametrize("M,d,r,rg,add_gate,s,alpha,kappa", [
     (1, 768, 96, 96, False, 1.0, 1.0, 1.0),
     (129, 768, 96, 96, False, 1.0, 1.0, 1.0),

@@ -177,6 +177,7 @@ int layernorm_bwd(const void* x, const void* dy, const float* w, const float* me
                   float* db, int64_t M, int d, cudaStream_t st);
 int set_k1_trace(unsigned long long* dev_buf);   // developer hook, tools/trace_k1.py
 int set_k1_bwd_trace(unsigned long long* dev_buf);
+int set_k1_pairs(int mode);                       // developer hook: -1 auto, 0 single CTAs, 1 CTA pairs (cta_group::2)
 // dense projection GEMM (tcgen05), vlpet_gemm_sm100.cu: C fp32 = A bf16 * W^T bf16 + bias
 bool gemm_sm100_supported(int64_t M, int N, int K, int64_t ldc);
 int gemm_sm100(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, float* C, int64_t ldc, int64_t M,

@@ -20,6 +20,8 @@
 // fp32 bias tables.  Weights are padded to R rows / columns by TMA out-of-bounds zero fill, so any r, rg <= R that is a
 // multiple of 8 runs on the same instantiation.  The kernel is shared-memory-bandwidth bound (TMA writes + UMMA operand
 // reads + epilogue LDS/STS all go through the 128 B/clk port); keeping z/q in TMEM removed a quarter of that traffic.
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <type_traits>
 
@@ -105,8 +107,6 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int CH = 64;  // chunk width in elements: 64 bf16 = one 128-byte swizzle row
-constexpr int NXA = 2;  // XA ring stages (phase-A operands of the NEXT tile: the HBM stream)
-constexpr int NXB = 2;  // XB ring stages (phase-B residual inputs of the current tile + out staging)
 constexpr int XCH_BYTES = TILE_M * CH * 2;  // 16 KB: one [128 x 64] bf16 chunk
 constexpr int NUM_THREADS = 640;   // 4 role warps + 16 epilogue warps
 constexpr int EPI_THREADS = 512;
@@ -115,8 +115,14 @@ constexpr int TMEM_COLS = 512;
 constexpr int TM_A = 0, TM_P = 128, TM_Z = 256, TM_Q = 320, TM_UT = 384;
 constexpr int SMEM_LIMIT = 232448;                // 227 KB opt-in maximum per CTA
 
-template <int R>
+template <int R, int NCTA = 1>
 struct Cfg {
+  // NCTA = 2: CTA pairs (cta_group::2).  One UMMA spans the two 128-token tiles of a pair (M = 256) and every CTA stages
+  // only HALF of each weight chunk (its N/2 rows of the B operand): half the weight bytes through the shared-memory port
+  // -- the kernel's bottleneck -- and room for a third XB stage.
+  static constexpr int NXA = 2;                        // XA ring stages (phase-A operands of the NEXT tile: the HBM stream)
+  static constexpr int NXB = (NCTA == 2) ? 3 : 2;      // XB ring stages (phase-B residual inputs + out staging); a third
+                                                       // XA stage instead measured slower (132 vs 128 us)
   // Weight rings hold 4 slots = two full steps (a step consumes one chunk of each of the two branches): with 3 slots the
   // second matrix of every step was requested only after the previous step's MMAs had retired -- one exposed L2 latency
   // (~1 us) per step (tools/trace_k1.py).
@@ -125,15 +131,18 @@ struct Cfg {
   static constexpr int NWB = (R == 128) ? 2 : 4;       // WB ring slots (one [64 x R] chunk of Wu or Gu each)
   static constexpr int KBF = R / 64;                   // full 64-wide K blocks of a phase-B weight chunk (128-byte swizzle)
   static constexpr int REM = R % 64;                   // 0 or 32: a last 32-wide K block (64-byte swizzle, half the bytes)
-  static constexpr int WA_BYTES = R * CH * 2;          // one [R x 64] weight chunk (phase A)
-  static constexpr int WB_BYTES = KBF * CH * CH * 2 + (REM ? CH * 32 * 2 : 0);   // one [64 x R] weight chunk (phase B)
+  static constexpr int WA_ROWS = R / NCTA;             // rows of a [R x 64] phase-A weight chunk staged by this CTA
+  static constexpr int WB_ROWS = CH / NCTA;            // rows of a [64 x R] phase-B weight chunk staged by this CTA
+  static constexpr int WA_BYTES = WA_ROWS * CH * 2;
+  static constexpr int WB_BLK = WB_ROWS * CH * 2;      // one 64-wide K block of the staged rows
+  static constexpr int WB_BYTES = KBF * WB_BLK + (REM ? WB_ROWS * 32 * 2 : 0);
   static constexpr int OFF_XA = 0;
   static constexpr int OFF_XB = OFF_XA + NXA * 2 * XCH_BYTES;
   static constexpr int OFF_WA = OFF_XB + NXB * 2 * XCH_BYTES;
   static constexpr int OFF_WB = OFF_WA + NWA * WA_BYTES;
   static constexpr int OFF_BD = OFF_WB + NWB * WB_BYTES;   // fp32 bd[128], gbd[128] (zero padded)
   static constexpr int OFF_BAR = OFF_BD + 2 * 128 * 4;
-  static constexpr int OFF_BU = OFF_BAR + 256;         // fp32 alpha*bu[d], 0.5*gbu[d]
+  static constexpr int OFF_BU = OFF_BAR + 512;         // fp32 alpha*bu[d], 0.5*gbu[d] (the barrier block is 512 bytes)
   static constexpr int smem_bytes(int d) { return OFF_BU + 2 * d * 4 + 1024; }  // + slack for the manual 1024-B alignment
   static constexpr int HALF = R / 2;                   // accumulator columns per epilogue-1 warp
   static_assert(REM == 0 || REM == 32, "rank buckets are multiples of 32");
@@ -162,7 +171,8 @@ struct Params {
   int64_t M;
   int d, r, rg;
   int add_gate;
-  int64_t full_tiles; // tiles [0, full_tiles) are one work item each; every later tile is split over nsplit work items
+  int64_t num_units;  // work units: 128-token tiles (NCTA = 1) or pairs of adjacent tiles (NCTA = 2)
+  int64_t full_tiles; // units [0, full_tiles) are one work item each; every later unit is split over nsplit work items
   int nsplit;         // split tiles (the last, partial wave of a large M, or all tiles of a small M): nsplit CTAs each redo
                       // phase A and own nkc/nsplit of the phase-B column chunks -- trades redundant L2 reads for a
                       // shorter critical path
@@ -177,9 +187,10 @@ struct Params {
 };
 
 // barrier slots (8 bytes each) inside the barrier block
-enum { B_XAFULL = 0, B_XAEMPTY = B_XAFULL + NXA, B_XBFULL = B_XAEMPTY + NXA, B_OUTRDY = B_XBFULL + NXB,
-       B_WAFULL = B_OUTRDY + NXB, B_WAEMPTY = B_WAFULL + 4, B_WBFULL = B_WAEMPTY + 4, B_WBEMPTY = B_WBFULL + 4,
+enum { B_XAFULL = 0, B_XAEMPTY = B_XAFULL + 3, B_XBFULL = B_XAEMPTY + 3, B_OUTRDY = B_XBFULL + 3,
+       B_WAFULL = B_OUTRDY + 3, B_WAEMPTY = B_WAFULL + 4, B_WBFULL = B_WAEMPTY + 4, B_WBEMPTY = B_WBFULL + 4,
        B_APFULL = B_WBEMPTY + 4, B_ZQFULL, B_UTFULL, B_UTEMPTY, B_COUNT };
+static_assert(8 * B_COUNT + 8 <= 512, "barriers + the TMEM address slot must fit the 512-byte barrier block");
 
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
@@ -200,9 +211,9 @@ __device__ __forceinline__ f2 gelu_new2(f2 v) {
 struct ItemCursor {
   int64_t w, num_items, full_tiles, tile;
   int nsplit, cps, nkc, stride, cb, ce;
-  __device__ __forceinline__ void init(const Params& p, int nkc_, int64_t num_items_) {
-    w = blockIdx.x; num_items = num_items_; full_tiles = p.full_tiles; nsplit = p.nsplit; nkc = nkc_;
-    cps = nkc_ / p.nsplit; stride = gridDim.x;
+  __device__ __forceinline__ void init(const Params& p, int nkc_, int64_t num_items_, int ncta = 1) {
+    w = blockIdx.x / ncta; num_items = num_items_; full_tiles = p.full_tiles; nsplit = p.nsplit; nkc = nkc_;
+    cps = nkc_ / p.nsplit; stride = gridDim.x / ncta;
     decode();
   }
   __device__ __forceinline__ bool valid() const { return w < num_items; }
@@ -218,15 +229,16 @@ struct ItemCursor {
   __device__ __forceinline__ void next() { w += stride; decode(); }
 };
 
-template <int R, bool GATED>
+template <int R, bool GATED, int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_wd,
                     const __grid_constant__ CUtensorMap tm_gd, const __grid_constant__ CUtensorMap tm_wu,
                     const __grid_constant__ CUtensorMap tm_gu, const __grid_constant__ CUtensorMap tm_wu_t,
                     const __grid_constant__ CUtensorMap tm_gu_t, const Params p) {
-  using C = Cfg<R>;
-  constexpr int NWA = C::NWA, NWB = C::NWB;
+  using C = Cfg<R, NCTA>;
+  constexpr int NWA = C::NWA, NWB = C::NWB, NXA = C::NXA, NXB = C::NXB;
+  const uint32_t rank = (NCTA == 2) ? ptx::cluster_ctarank() : 0u;   // position in the CTA pair; rank 0 issues the MMAs
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));   // generic-space view of the aligned base
@@ -237,8 +249,9 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   const int nkc = p.d / CH;  // chunks along d (phase A: K chunks; phase B: N chunks)
-  const int64_t num_tiles = (p.M + TILE_M - 1) / TILE_M;
-  const int64_t num_items = p.full_tiles + (num_tiles - p.full_tiles) * p.nsplit;
+  const int64_t num_items = p.full_tiles + (p.num_units - p.full_tiles) * p.nsplit;
+  // barrier `i` of the pair leader as a shared::cluster address (the leader's MMA thread waits on ITS barriers only)
+  auto lbar = [&](int i) { return (NCTA == 2) ? ptx::mapa(bar(i), 0u) : bar(i); };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NXA; ++i) { ptx::mbar_init(bar(B_XAFULL + i), 1); ptx::mbar_init(bar(B_XAEMPTY + i), 1); }
@@ -246,9 +259,9 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     for (int i = 0; i < NWA; ++i) { ptx::mbar_init(bar(B_WAFULL + i), 1); ptx::mbar_init(bar(B_WAEMPTY + i), 1); }
     for (int i = 0; i < NWB; ++i) { ptx::mbar_init(bar(B_WBFULL + i), 1); ptx::mbar_init(bar(B_WBEMPTY + i), 1); }
     ptx::mbar_init(bar(B_APFULL), 1);
-    ptx::mbar_init(bar(B_ZQFULL), EPI_THREADS);
+    ptx::mbar_init(bar(B_ZQFULL), EPI_THREADS * NCTA);    // the epilogue threads of BOTH CTAs arrive at the leader's copy
     ptx::mbar_init(bar(B_UTFULL), 1);
-    ptx::mbar_init(bar(B_UTEMPTY), EPI_THREADS);
+    ptx::mbar_init(bar(B_UTEMPTY), EPI_THREADS * NCTA);
     ptx::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); }
@@ -258,7 +271,9 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     if (C::REM) { ptx::prefetch_tmap(&tm_wu_t); ptx::prefetch_tmap(&tm_gu_t); }
   }
   if (warp == 0 && lane == 1) { ptx::prefetch_tmap(&tm_wd); ptx::prefetch_tmap(&tm_gd); }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if (NCTA == 2) ptx::tmem_alloc_cg2(tmem_slot, TMEM_COLS); else ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   {  // biases -> fp32 in shared memory, pre-multiplied so that the epilogues fold them into FMAs they issue anyway:
      // bd / gbd (zero padded to 128), alpha*bu, 0.5*gbu
     float* sbd = reinterpret_cast<float*>(smem_gen + C::OFF_BD);
@@ -277,6 +292,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) ptx::cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / TMA signal
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -285,26 +301,36 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     // ===================================== TMA producer: phase-A x chunks (HBM stream) =====================================
     // (every role loop is run by ONE elected thread, see the MMA warp)
     if (ptx::elect_one()) {
-      ItemCursor it; it.init(p, nkc, num_items);
+      ItemCursor it; it.init(p, nkc, num_items, NCTA);
       uint32_t n = 0, na = 0;
       for (; it.valid(); it.next()) {
-        const int row0 = (int)(it.tile * TILE_M);
+        const int row0 = (int)((it.tile * NCTA + rank) * TILE_M);
         for (int k = 0; k < nkc; ++k, ++n) {
           const uint32_t sl = n % NXA;
           ptx::mbar_wait_dbg(bar(B_XAEMPTY + sl), ((n / NXA) & 1) ^ 1, p.dbg, __LINE__);
           const uint32_t dst = smem_base + C::OFF_XA + sl * (2 * XCH_BYTES);
-          ptx::mbar_arrive_expect_tx(bar(B_XAFULL + sl), (GATED ? 2 : 1) * XCH_BYTES);
+          // (pairs: the leader expects the bytes of both CTAs; every load signals the LEADER's barrier)
+          if (rank == 0) ptx::mbar_arrive_expect_tx(bar(B_XAFULL + sl), NCTA * (GATED ? 2 : 1) * XCH_BYTES);
           // first touch of data that phase B reads again one tile later: ask L2 to keep it
-          if (GATED) ptx::tma_load_2d_hint(dst, &tm_x1, k * CH, row0, bar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
-          ptx::tma_load_2d_hint(dst + XCH_BYTES, &tm_x2, k * CH, row0, bar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
+          if (NCTA == 2) {
+            if (GATED) ptx::tma_load_2d_hint_cg2(dst, &tm_x1, k * CH, row0, lbar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
+            ptx::tma_load_2d_hint_cg2(dst + XCH_BYTES, &tm_x2, k * CH, row0, lbar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
+          } else {
+            if (GATED) ptx::tma_load_2d_hint(dst, &tm_x1, k * CH, row0, bar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
+            ptx::tma_load_2d_hint(dst + XCH_BYTES, &tm_x2, k * CH, row0, bar(B_XAFULL + sl), ptx::L2_EVICT_LAST);
+          }
           // the weight chunks the same MMA step consumes: Wd_k, Gd_k (always L2 hits)
 #pragma unroll
           for (int m = 0; m < (GATED ? 2 : 1); ++m, ++na) {
             const uint32_t sw = na % NWA;
             ptx::mbar_wait_dbg(bar(B_WAEMPTY + sw), ((na / NWA) & 1) ^ 1, p.dbg, __LINE__);
-            ptx::mbar_arrive_expect_tx(bar(B_WAFULL + sw), C::WA_BYTES);
-            ptx::tma_load_2d_hint(smem_base + C::OFF_WA + sw * C::WA_BYTES, m ? &tm_gd : &tm_wd, k * CH, 0, bar(B_WAFULL + sw),
-                                  ptx::L2_EVICT_LAST);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(bar(B_WAFULL + sw), NCTA * C::WA_BYTES);
+            if (NCTA == 2)   // this CTA's half of the rows
+              ptx::tma_load_2d_hint_cg2(smem_base + C::OFF_WA + sw * C::WA_BYTES, m ? &tm_gd : &tm_wd, k * CH, (int)rank * C::WA_ROWS,
+                                        lbar(B_WAFULL + sw), ptx::L2_EVICT_LAST);
+            else
+              ptx::tma_load_2d_hint(smem_base + C::OFF_WA + sw * C::WA_BYTES, m ? &tm_gd : &tm_wd, k * CH, 0, bar(B_WAFULL + sw),
+                                    ptx::L2_EVICT_LAST);
           }
         }
       }
@@ -313,21 +339,25 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     // ===================================== TMA producer: phase-B weights Wu_c, Gu_c (always L2 hits) ====================
     if (ptx::elect_one()) {
       uint32_t nb = 0;
-      ItemCursor it; it.init(p, nkc, num_items);
+      ItemCursor it; it.init(p, nkc, num_items, NCTA);
       for (; it.valid(); it.next()) {
         for (int c = it.cb; c < it.ce; ++c) {
+          const int wrow = c * CH + (int)rank * C::WB_ROWS;   // first row of Wu / Gu this CTA stages
 #pragma unroll
           for (int m = 0; m < (GATED ? 2 : 1); ++m, ++nb) {
             const uint32_t sl = nb % NWB;
             ptx::mbar_wait_dbg(bar(B_WBEMPTY + sl), ((nb / NWB) & 1) ^ 1, p.dbg, __LINE__);
-            ptx::mbar_arrive_expect_tx(bar(B_WBFULL + sl), C::WB_BYTES);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(bar(B_WBFULL + sl), NCTA * C::WB_BYTES);
+            const uint32_t wdst = smem_base + C::OFF_WB + sl * C::WB_BYTES;
 #pragma unroll
-            for (int kb = 0; kb < C::KBF; ++kb)
-              ptx::tma_load_2d_hint(smem_base + C::OFF_WB + sl * C::WB_BYTES + kb * (CH * CH * 2), m ? &tm_gu : &tm_wu, kb * CH,
-                                    c * CH, bar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
-            if (C::REM)
-              ptx::tma_load_2d_hint(smem_base + C::OFF_WB + sl * C::WB_BYTES + C::KBF * (CH * CH * 2), m ? &tm_gu_t : &tm_wu_t,
-                                    C::KBF * CH, c * CH, bar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
+            for (int kb = 0; kb < C::KBF; ++kb) {
+              if (NCTA == 2) ptx::tma_load_2d_hint_cg2(wdst + kb * C::WB_BLK, m ? &tm_gu : &tm_wu, kb * CH, wrow, lbar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
+              else ptx::tma_load_2d_hint(wdst + kb * C::WB_BLK, m ? &tm_gu : &tm_wu, kb * CH, wrow, bar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
+            }
+            if (C::REM) {
+              if (NCTA == 2) ptx::tma_load_2d_hint_cg2(wdst + C::KBF * C::WB_BLK, m ? &tm_gu_t : &tm_wu_t, C::KBF * CH, wrow, lbar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
+              else ptx::tma_load_2d_hint(wdst + C::KBF * C::WB_BLK, m ? &tm_gu_t : &tm_wu_t, C::KBF * CH, wrow, bar(B_WBFULL + sl), ptx::L2_EVICT_LAST);
+            }
           }
         }
       }
@@ -338,9 +368,18 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     // cp.async.bulk.tensor live in uniform registers: under `if (lane == 0)` ptxas wrapped EVERY issue in an elect /
     // R2UR.BROADCAST / branch sequence (~15 instructions, > 100 ns per MMA measured with tools/trace_k1.py -- the whole
     // kernel was issue-bound); under an elect predicate it keeps the descriptors in uniform registers.
-    if (ptx::elect_one()) {
-      constexpr uint32_t IDESC_A = ptx::umma_idesc_bf16_m128(R);
-      constexpr uint32_t IDESC_B = ptx::umma_idesc_bf16_m128(CH);
+    if (rank == 0 && ptx::elect_one()) {   // pairs: the leader CTA issues for both SMs
+      constexpr uint32_t IDESC_A = ptx::umma_idesc_bf16(128 * NCTA, R);
+      constexpr uint32_t IDESC_B = ptx::umma_idesc_bf16(128 * NCTA, CH);
+      auto mma_ss = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if (NCTA == 2) ptx::umma_bf16_ss_cg2(d, a, b, idesc, acc); else ptx::umma_bf16_ss(d, a, b, idesc, acc);
+      };
+      auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if (NCTA == 2) ptx::umma_bf16_ts_cg2(d, a, b, idesc, acc); else ptx::umma_bf16_ts(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint32_t b) {   // pairs: arrives on the barrier at this offset in BOTH CTAs
+        if (NCTA == 2) ptx::umma_commit_cg2(b); else ptx::umma_commit(b);
+      };
       uint32_t nxa = 0, na = 0, nb = 0, ui = 0, ti = 0;
       // Phase A of the next item and phase B of this item are issued in whatever order their inputs become ready
       // (non-blocking barrier tests): the HBM stream is not paced by the epilogue and vice versa.
@@ -368,9 +407,9 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           const uint64_t adesc = ptx::umma_desc_kmajor_sw128(m ? x1s : x2s), bdesc = ptx::umma_desc_kmajor_sw128(ws);
 #pragma unroll
           for (int ks = 0; ks < CH / 16; ++ks)   // +32 bytes per K step = +2 in the descriptor's 16-byte address units
-            ptx::umma_bf16_ss(tmem_base + (m ? TM_P : TM_A), adesc + 2 * ks, bdesc + 2 * ks, IDESC_A, (k > 0 || ks > 0) ? 1u : 0u);
-          ptx::umma_commit(bar(B_WAEMPTY + sl));
-          if (m == (GATED ? 1 : 0)) ptx::umma_commit(bar(B_XAEMPTY + sx));
+            mma_ss(tmem_base + (m ? TM_P : TM_A), adesc + 2 * ks, bdesc + 2 * ks, IDESC_A, (k > 0 || ks > 0) ? 1u : 0u);
+          commit(bar(B_WAEMPTY + sl));
+          if (m == (GATED ? 1 : 0)) commit(bar(B_XAEMPTY + sx));
         }
         ++nxa;
       };
@@ -383,23 +422,23 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           ptx::mbar_wait_dbg(bar(B_WBFULL + sl), (nb / NWB) & 1, p.dbg, __LINE__);
           ptx::tc_fence_after();
           const uint32_t ws = smem_base + C::OFF_WB + sl * C::WB_BYTES;
-          const uint64_t d128 = ptx::umma_desc_kmajor_sw128(ws), d64 = ptx::umma_desc_kmajor_sw64(ws + C::KBF * (CH * CH * 2));
+          const uint64_t d128 = ptx::umma_desc_kmajor_sw128(ws), d64 = ptx::umma_desc_kmajor_sw64(ws + C::KBF * C::WB_BLK);
           const uint32_t ta = tmem_base + (m ? TM_Q : TM_Z), td = tmem_base + TM_UT + (m ? CH : 0);
 #pragma unroll
           for (int ks = 0; ks < R / 16; ++ks) {
             const int kb = ks / 4, kin = ks % 4;
-            const uint64_t bdesc = (kb < C::KBF) ? d128 + (uint64_t)(kb * (CH * CH * 2 / 16) + 2 * kin) : d64 + (uint64_t)(2 * kin);
-            ptx::umma_bf16_ts(td, ta + 8 * ks, bdesc, IDESC_B, ks > 0);
+            const uint64_t bdesc = (kb < C::KBF) ? d128 + (uint64_t)(kb * (C::WB_BLK / 16) + 2 * kin) : d64 + (uint64_t)(2 * kin);
+            mma_ts(td, ta + 8 * ks, bdesc, IDESC_B, ks > 0);
           }
-          ptx::umma_commit(bar(B_WBEMPTY + sl));
-          if (m == (GATED ? 1 : 0)) ptx::umma_commit(bar(B_UTFULL));
+          commit(bar(B_WBEMPTY + sl));
+          if (m == (GATED ? 1 : 0)) commit(bar(B_UTFULL));
         }
         ++ui;
       };
-      ItemCursor it; it.init(p, nkc, num_items);
+      ItemCursor it; it.init(p, nkc, num_items, NCTA);
       if (it.valid()) {
         for (int k = 0; k < nkc; ++k) { step_a(k); if (k < 12) VLPET_TR(100 + k); }
-        ptx::umma_commit(bar(B_APFULL));
+        commit(bar(B_APFULL));
       }
       for (; it.valid(); it.next(), ++ti) {
         const int nB = it.ce - it.cb;
@@ -415,7 +454,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           if (ka < nA && ready_a()) {
             step_a(ka);
             if (ti == 0 && ka < 12) VLPET_TR(65 + 2 * ka);
-            if (++ka == nA) ptx::umma_commit(bar(B_APFULL));
+            if (++ka == nA) commit(bar(B_APFULL));
             did = true;
           }
           if (did) spins = 0;
@@ -428,13 +467,13 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     // The residual chunks of ALL work items form one stream of entries; entry e lives in XB slot e % NXB.  This thread
     // frees a slot itself (its store has read it), so it can refill it right away: no empty barrier.
     if (ptx::elect_one()) {
-      ItemCursor ld; ld.init(p, nkc, num_items);
+      ItemCursor ld; ld.init(p, nkc, num_items, NCTA);
       ItemCursor st = ld;
       int lc = ld.valid() ? ld.cb : 0, sc = lc;
       uint32_t e_st = 0;
       auto load = [&](uint32_t sl) {
         const uint32_t dst = smem_base + C::OFF_XB + sl * (2 * XCH_BYTES);
-        const int row0 = (int)(ld.tile * TILE_M);
+        const int row0 = (int)((ld.tile * NCTA + rank) * TILE_M);
         ptx::mbar_arrive_expect_tx(bar(B_XBFULL + sl), 2 * XCH_BYTES);
         ptx::tma_load_2d_hint(dst, &tm_x1, lc * CH, row0, bar(B_XBFULL + sl), ptx::L2_EVICT_FIRST);   // last use
         ptx::tma_load_2d_hint(dst + XCH_BYTES, &tm_x2, lc * CH, row0, bar(B_XBFULL + sl), ptx::L2_EVICT_FIRST);
@@ -445,7 +484,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         const uint32_t sl = e_st % NXB;
         ptx::mbar_wait_dbg(bar(B_OUTRDY + sl), (e_st / NXB) & 1, p.dbg, __LINE__);
         if (e_st < 12) VLPET_TR(128 + 2 * e_st);
-        ptx::tma_store_2d_hint(&tm_out, smem_base + C::OFF_XB + sl * (2 * XCH_BYTES), sc * CH, (int)(st.tile * TILE_M),
+        ptx::tma_store_2d_hint(&tm_out, smem_base + C::OFF_XB + sl * (2 * XCH_BYTES), sc * CH, (int)((st.tile * NCTA + rank) * TILE_M),
                                ptx::L2_EVICT_FIRST);   // never re-read by this kernel
         ptx::tma_store_commit();
         ptx::tma_store_wait_read0();
@@ -470,9 +509,10 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     const f2 s2 = mk2(p.s, p.s), sh2 = mk2(0.5f * p.s, 0.5f * p.s);
     const float s_keep = p.s * p.inv_keep;
     uint32_t e = 0, ui = 0, ti = 0;
-    ItemCursor it; it.init(p, nkc, num_items);
+    const uint32_t zqfull = lbar(B_ZQFULL), utempty = lbar(B_UTEMPTY);
+    ItemCursor it; it.init(p, nkc, num_items, NCTA);
     for (; it.valid(); it.next(), ++ti) {
-      const int64_t tile = it.tile;
+      const int64_t tile = it.tile * NCTA + rank;
       const int cb = it.cb, ce = it.ce;
       // ---- epilogue 1: z = gelu_new(A + bd) (cg 0,1) / q = gelu_new(P + gbd) (cg 2,3) -> packed bf16 into TMEM
       VLPET_TRACE(0);
@@ -504,7 +544,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         ptx::tmem_st_wait();
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(bar(B_ZQFULL));   // z/q are in place AND this thread is done reading A/P
+      if (NCTA == 2 && rank != 0) ptx::mbar_arrive_cluster(zqfull); else ptx::mbar_arrive(bar(B_ZQFULL));   // z/q in place AND A/P drained
       VLPET_TRACE(2);
       // ---- epilogue 2, per 64-column chunk: this warp owns columns [cg*16, cg*16+16) of the chunk
       for (int c = cb; c < ce; ++c, ++ui, ++e) {
@@ -519,7 +559,7 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         if (GATED) ptx::tmem_ld_32x32b_x16(tU + CH, t);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(bar(B_UTEMPTY));  // accumulators are in registers: the MMA warp may overwrite them
+        if (NCTA == 2 && rank != 0) ptx::mbar_arrive_cluster(utempty); else ptx::mbar_arrive(bar(B_UTEMPTY));  // accumulators are in registers
         VLPET_TRACE(4 + 4 * (c - cb));
         ptx::mbar_wait_dbg(bar(B_XBFULL + sl), (e / NXB) & 1, p.dbg, __LINE__);
         VLPET_TRACE(5 + 4 * (c - cb));
@@ -587,9 +627,10 @@ k1_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) ptx::cluster_sync_all();   // no CTA of a pair exits (or frees TMEM) while its peer can still signal it
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (NCTA == 2) ptx::tmem_dealloc_cg2(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -621,27 +662,62 @@ const DevInfo& dev_info() {
   return di;
 }
 
-template <int R, bool GATED>
-int launch(const VlpetK1Desc& D, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
-  using C = Cfg<R>;
+template <int R, bool GATED, int NCTA>
+int launch(const VlpetK1Desc& D, const CUtensorMap* maps, Params p, cudaStream_t st) {
+  using C = Cfg<R, NCTA>;
   const int smem = C::smem_bytes(D.d);
+  auto kern = k1_fwd_sm100_kernel<R, GATED, NCTA>;
   static int attr_set = 0;
   if (attr_set < smem) {
-    VLPET_CUDA_OK(cudaFuncSetAttribute(k1_fwd_sm100_kernel<R, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VLPET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = smem;
   }
-  const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
-  const int64_t items = p.full_tiles + (tiles - p.full_tiles) * p.nsplit;
-  int grid = (int)(items < dev_info().sms ? items : dev_info().sms);
-  k1_fwd_sm100_kernel<R, GATED><<<grid, NUM_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
-                                                                 maps[6], maps[7], maps[8], p);
-  VLPET_LAUNCH_OK();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  int slots = dev_info().sms;      // concurrently resident work units: CTAs, or CTA pairs
+  if (NCTA == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int max_pairs = -1;     // a GPC with an odd number of SMs strands one SM: ask the driver how many pairs fit at once
+    if (max_pairs < 0) {
+      cfg.gridDim = dim3((unsigned)(dev_info().sms / 2 * 2));
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = 0; }
+      max_pairs = n;
+    }
+    if (max_pairs < 1) return fail(VLPET_E_UNSUPPORTED, "k1_fwd(fused): no room for a CTA pair");
+    slots = max_pairs;
+  }
+  {  // Whole waves run one unit (tile / tile pair) per slot.  The units of the last, partial wave (all of them when M is
+     // small) are split over several slots each (largest divisor of nkc that still fits the wave): the tail costs one
+     // phase A plus nkc/nsplit chunks instead of a full tile time.
+    const int nkc = D.d / CH;
+    const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
+    p.num_units = (tiles + NCTA - 1) / NCTA;
+    const int64_t rem = p.num_units % slots;
+    p.full_tiles = p.num_units - rem;
+    p.nsplit = 1;
+    for (int ns = 2; ns <= nkc; ++ns)
+      if (nkc % ns == 0 && rem * ns <= slots) p.nsplit = ns;
+    if (p.nsplit == 1) p.full_tiles = p.num_units;
+  }
+  const int64_t items = p.full_tiles + (p.num_units - p.full_tiles) * p.nsplit;
+  cfg.gridDim = dim3((unsigned)(NCTA * (items < slots ? items : slots)));
+  VLPET_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], maps[8], p));
+  count_launch();
   return 0;
 }
 
 template <int R>
-int launch_r(const VlpetK1Desc& D, const CUtensorMap* maps, const Params& p, bool gated, cudaStream_t st) {
-  return gated ? launch<R, true>(D, maps, p, st) : launch<R, false>(D, maps, p, st);
+int launch_r(const VlpetK1Desc& D, const CUtensorMap* maps, const Params& p, bool gated, int ncta, cudaStream_t st) {
+  if (ncta == 2) return gated ? launch<R, true, 2>(D, maps, p, st) : launch<R, false, 2>(D, maps, p, st);
+  return gated ? launch<R, true, 1>(D, maps, p, st) : launch<R, false, 1>(D, maps, p, st);
 }
 
 int smem_need(int R, int d) {
@@ -654,10 +730,25 @@ int smem_need(int R, int d) {
   return 1 << 30;
 }
 
+// CTA pairs pay off when there are several tiles per SM (weights are the largest share of the shared-memory traffic:
+// 128 vs 132 us at M = 96 000); with less than two waves the single-CTA kernel's finer tail split wins.
+// g_pairs_mode: -1 auto, 0 never, 1 whenever there are at least two tiles (vlpet_debug_set_k1_pairs / VLPET_K1_PAIRS).
+int g_pairs_mode = []() { const char* e = getenv("VLPET_K1_PAIRS"); return e ? atoi(e) : -1; }();
+bool use_pairs(const VlpetK1Desc& D, int R) {
+  if (R == 128 || g_pairs_mode == 0) return false;
+  const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
+  if (g_pairs_mode == 1) return tiles >= 2;
+  return tiles >= 2 * (int64_t)dev_info().sms;
+}
+
 }  // namespace
 
 int set_k1_trace(unsigned long long* dev_buf) {
   g_trace = dev_buf;
+  return 0;
+}
+int set_k1_pairs(int mode) {
+  g_pairs_mode = mode;
   return 0;
 }
 
@@ -681,18 +772,20 @@ int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const Vlp
       (gated && (!aligned16(w.Gd) || !aligned16(w.Gu) || !aligned16(w.gbu))))
     return fail(VLPET_E_ALIGN, "k1_fwd(fused): weights must be 16-byte aligned");
   const int R = pick_R(D);
+  const int ncta = use_pairs(D, R) ? 2 : 1;
+  const uint32_t wa_rows = (uint32_t)(R / ncta), wb_rows = (uint32_t)(CH / ncta);   // rows of a weight chunk one CTA stages
   CUtensorMap maps[9];
   VLPET_TRY(make_map(&maps[0], x1, (uint64_t)D.M, (uint64_t)D.d, TILE_M, false));
   VLPET_TRY(make_map(&maps[1], x2, (uint64_t)D.M, (uint64_t)D.d, TILE_M, false));
   VLPET_TRY(make_map(&maps[2], out, (uint64_t)D.M, (uint64_t)D.d, TILE_M, false));
-  VLPET_TRY(make_map(&maps[3], w.Wd, (uint64_t)D.r, (uint64_t)D.d, (uint32_t)R, true));
-  VLPET_TRY(make_map(&maps[4], gated ? w.Gd : w.Wd, (uint64_t)(gated ? D.rg : D.r), (uint64_t)D.d, (uint32_t)R, true));
-  VLPET_TRY(make_map(&maps[5], w.Wu, (uint64_t)D.d, (uint64_t)D.r, CH, true));
-  VLPET_TRY(make_map(&maps[6], gated ? w.Gu : w.Wu, (uint64_t)D.d, (uint64_t)(gated ? D.rg : D.r), CH, true));
+  VLPET_TRY(make_map(&maps[3], w.Wd, (uint64_t)D.r, (uint64_t)D.d, wa_rows, true));
+  VLPET_TRY(make_map(&maps[4], gated ? w.Gd : w.Wd, (uint64_t)(gated ? D.rg : D.r), (uint64_t)D.d, wa_rows, true));
+  VLPET_TRY(make_map(&maps[5], w.Wu, (uint64_t)D.d, (uint64_t)D.r, wb_rows, true));
+  VLPET_TRY(make_map(&maps[6], gated ? w.Gu : w.Wu, (uint64_t)D.d, (uint64_t)(gated ? D.rg : D.r), wb_rows, true));
   // 32-column boxes (64-byte swizzle) for the last, half-wide K block of the phase-B weight chunks (R % 64 == 32)
-  VLPET_TRY(make_map_bf16(&maps[7], w.Wu, (uint64_t)D.d, (uint64_t)D.r, (uint64_t)D.r, CH, 32, true));
+  VLPET_TRY(make_map_bf16(&maps[7], w.Wu, (uint64_t)D.d, (uint64_t)D.r, (uint64_t)D.r, wb_rows, 32, true));
   VLPET_TRY(make_map_bf16(&maps[8], gated ? w.Gu : w.Wu, (uint64_t)D.d, (uint64_t)(gated ? D.rg : D.r),
-                          (uint64_t)(gated ? D.rg : D.r), CH, 32, true));
+                          (uint64_t)(gated ? D.rg : D.r), wb_rows, 32, true));
   Params p;
   p.M = D.M; p.d = D.d; p.r = D.r; p.rg = gated ? D.rg : D.r; p.add_gate = D.add_gate;
   p.s = D.s; p.alpha = D.alpha; p.kappa = D.kappa;
@@ -702,25 +795,13 @@ int fused_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const Vlp
   p.seed_dev = D.seed_dev;
   p.trace = g_trace;
   p.dbg = trap_buffer_dev();
-  {  // Whole waves of tiles run one tile per CTA.  The tiles of the last, partial wave (all tiles when M is small) are
-     // split over several CTAs each (largest divisor of nkc that still fits the wave): the tail costs one phase A plus
-     // nkc/nsplit chunks instead of a full tile time.
-    const int nkc = D.d / CH, sms = dev_info().sms;
-    const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
-    const int64_t rem = tiles % sms;
-    p.full_tiles = tiles - rem;
-    p.nsplit = 1;
-    for (int ns = 2; ns <= nkc; ++ns)
-      if (nkc % ns == 0 && rem * ns <= sms) p.nsplit = ns;
-    if (p.nsplit == 1) p.full_tiles = tiles;
-  }
   p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
   p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
   switch (R) {
-    case 32: return launch_r<32>(D, maps, p, gated, st);
-    case 64: return launch_r<64>(D, maps, p, gated, st);
-    case 96: return launch_r<96>(D, maps, p, gated, st);
-    case 128: return launch_r<128>(D, maps, p, gated, st);
+    case 32: return launch_r<32>(D, maps, p, gated, ncta, st);
+    case 64: return launch_r<64>(D, maps, p, gated, ncta, st);
+    case 96: return launch_r<96>(D, maps, p, gated, ncta, st);
+    case 128: return launch_r<128>(D, maps, p, gated, 1, st);
   }
   return fail(VLPET_E_UNSUPPORTED, "k1_fwd(fused): unsupported rank");
 }
