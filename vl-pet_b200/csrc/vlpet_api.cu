@@ -2,6 +2,7 @@
 // fused sm_100a kernels and the generic CUDA-core kernels, and the flat-bucket helpers (cast / AdamW / sumsq).
 #include <cstring>
 
+#include "sm100_ptx.cuh"
 #include "vlpet_common.cuh"
 
 namespace vlpet {
@@ -162,6 +163,20 @@ int vlpet_layernorm_bwd(const void* x, const void* dy, const float* w, const flo
   return layernorm_bwd(x, dy, w, mean, rstd, dx, dw, db, M, d, static_cast<cudaStream_t>(stream));
 }
 
+// developer hook: a kernel that waits on a barrier nobody completes -- proves that the trap record reaches the host
+namespace vlpet {
+__global__ void selftest_trap_kernel(uint32_t* dbg) {
+  __shared__ uint64_t mbar;
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(&mbar);
+  if (threadIdx.x == 0) { ptx::mbar_init(b, 1); ptx::fence_barrier_init(); }
+  __syncthreads();
+  if (threadIdx.x == 0) ptx::mbar_wait_dbg(b, 0, dbg, 4242);
+}
+}  // namespace vlpet
+__attribute__((visibility("default"))) int vlpet_debug_selftest_trap(void) {
+  vlpet::selftest_trap_kernel<<<1, 32>>>(vlpet::trap_buffer_dev());
+  return (int)cudaDeviceSynchronize();
+}
 // developer hook: who timed out?  {source line, block, thread, parity, barrier address} of the last barrier-wait trap
 __attribute__((visibility("default"))) int vlpet_debug_last_trap(uint32_t* out5) {
   const uint32_t* h = vlpet::trap_buffer_host();
@@ -271,12 +286,23 @@ int vlpet_k3_bwd(const VlpetK3Desc* D, const void* feats, const void* pos, const
 // ---- flat-bucket helpers -----------------------------------------------------------------------------------
 namespace vlpet {
 namespace flat {
-// y = dropout(gelu_erf(x)) / dx = dy * mask/(1-p) * gelu_erf'(x); 8 bf16 per thread, mask from drop_hash4
+// y = dropout(gelu_erf(x)) / dx = dy * mask/(1-p) * gelu_erf'(x); 8 bf16 per thread, mask from drop_hash4.
+// The kernel was bound by erff() (~30 instructions per element: 2.3 TB/s); now Phi(v) comes from the Abramowitz-Stegun
+// 7.1.26 rational form (|error| < 1.5e-7, far inside bf16), evaluated on packed fp32 pairs, and shares its exponential
+// with the pdf of the backward:  E = exp(-v^2/2), t = 1/(1 + p|v|/sqrt2), h = E * t*(a1+t*(a2+...))/2,
+// Phi(v) = 1/2 + copysign(1/2 - h, v), phi(v) = E/sqrt(2 pi).
 template <bool BWD>
-__global__ void gelu_dropout_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+__global__ void __launch_bounds__(256) gelu_dropout_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                     __nv_bfloat16* __restrict__ out, int64_t nvec, uint64_t seed, const uint64_t* seed_dev,
                                     uint32_t thr16, float inv_keep) {
+  using namespace ptx;
   const uint64_t s = seed + ((thr16 && seed_dev) ? *seed_dev : 0ull);
+  const f2 kp = mk2(0.3275911f * 0.7071067811865476f, 0.3275911f * 0.7071067811865476f), one = mk2(1.f, 1.f);
+  const f2 a1 = mk2(0.5f * 0.254829592f, 0.5f * 0.254829592f), a2 = mk2(0.5f * -0.284496736f, 0.5f * -0.284496736f),
+           a3 = mk2(0.5f * 1.421413741f, 0.5f * 1.421413741f), a4 = mk2(0.5f * -1.453152027f, 0.5f * -1.453152027f),
+           a5 = mk2(0.5f * 1.061405429f, 0.5f * 1.061405429f);
+  const f2 ce = mk2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f), half = mk2(0.5f, 0.5f), mone = mk2(-1.f, -1.f);
+  const f2 cpdf = mk2(0.3989422804014327f, 0.3989422804014327f);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 q = *reinterpret_cast<const uint4*>(x + i * 8);
     const uint32_t u[4] = {q.x, q.y, q.z, q.w};
@@ -290,26 +316,38 @@ __global__ void gelu_dropout_kernel(const __nv_bfloat16* __restrict__ x, const _
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float r[2];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const float v = k ? __uint_as_float(u[e] & 0xffff0000u) : __uint_as_float(u[e] << 16);
-        float m = 1.0f;
-        if (thr16) {
-          const uint32_t bits = (uint32_t)(h[e >> 1] >> (16 * ((e & 1) * 2 + k))) & 0xffffu;
-          m = bits >= thr16 ? inv_keep : 0.0f;
-        }
-        const float cdf = 0.5f * (1.0f + erff(v * 0.7071067811865476f));
-        if (BWD) {
-          const float d = k ? __uint_as_float(g[e] & 0xffff0000u) : __uint_as_float(g[e] << 16);
-          const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
-          r[k] = d * m * (cdf + v * pdf);
-        } else {
-          r[k] = m * v * cdf;
-        }
+      const uint32_t vlo = u[e] << 16, vhi = u[e] & 0xffff0000u;
+      const f2 v = mk2u(vlo, vhi), av = mk2u(vlo & 0x7fffffffu, vhi & 0x7fffffffu);
+      float t0, t1, e0, e1;
+      un2(fma2(kp, av, one), t0, t1);
+      un2(mul2(mul2(v, v), ce), e0, e1);
+      float r0, r1, x0, x1;                               // MUFU.RCP / MUFU.EX2: 1-2 ulp, far inside the bf16 result
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x0) : "f"(e0));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x1) : "f"(e1));
+      const f2 t = mk2(r0, r1), E = mk2(x0, x1);
+      f2 poly = fma2(a5, t, a4);
+      poly = fma2(poly, t, a3);
+      poly = fma2(poly, t, a2);
+      poly = fma2(poly, t, a1);
+      const f2 hh = mul2(mul2(poly, t), E);               // (1 - erf(|v|/sqrt2)) / 2
+      uint32_t c0, c1;
+      un2u(fma2(hh, mone, half), c0, c1);                 // 1/2 - h  >= 0
+      const f2 cdf = add2(half, mk2u(c0 | (vlo & 0x80000000u), c1 | (vhi & 0x80000000u)));
+      f2 m = one;
+      if (thr16) {
+        const uint32_t two = (uint32_t)(h[e >> 1] >> (32 * (e & 1)));
+        m = mk2(((two & 0xffffu) >= thr16) ? inv_keep : 0.f, ((two >> 16) >= thr16) ? inv_keep : 0.f);
       }
-      __nv_bfloat162 t = __floats2bfloat162_rn(r[0], r[1]);
-      o[e] = *reinterpret_cast<uint32_t*>(&t);
+      f2 r;
+      if (BWD) {
+        const f2 d = bf2_to_f2(g[e]);
+        r = mul2(mul2(d, m), fma2(mul2(v, cpdf), E, cdf));   // dy * mask * (Phi + v phi)
+      } else {
+        r = mul2(mul2(m, v), cdf);
+      }
+      o[e] = pack2(r);
     }
     *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
