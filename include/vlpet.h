@@ -203,6 +203,19 @@ VLPET_API int vlpet_gelu_dropout_fwd(const void* x, void* y, int64_t n, float p_
 VLPET_API int vlpet_gelu_dropout_bwd(const void* x, const void* dy, void* dx, int64_t n, float p_drop, uint64_t seed,
                            const uint64_t* seed_dev, void* stream);
 
+/* ---- token cross-entropy of the LM head (frozen decoder output) -------------------------
+ * loss[i] = logsumexp_j(logits[i, j]) - logits[i, labels[i]] in fp32 straight from the bf16 logits (0, and a zero gradient
+ * row, where labels[i] == ignore_index), replacing `lm_logits.float()` + `CrossEntropyLoss(ignore_index=-100,
+ * reduction='none')` of the reference (src/modeling_bart.py:1585-1586): for a caption batch the logits are [10 000 x 50 465],
+ * and the fp32 copy + softmax forward/backward moved ~10 GB per step.  Forward: one pass, online max/sum per row, also
+ * writes lse[i] for the backward.  Backward: dlogits[i, j] = dloss[i] * (exp(logits[i, j] - lse[i]) - [j == labels[i]]) as
+ * bf16 (may alias `logits`: every element is read once before it is written by the same thread).
+ * logits / dlogits: [rows, ncols] bf16 with row pitch `ld` elements; ncols % 8 == 0, ld % 8 == 0, 16-byte aligned.   */
+VLPET_API int vlpet_ce_fwd(const void* logits, int64_t ld, const int64_t* labels, float* loss, float* lse, int64_t rows,
+                 int32_t ncols, int64_t ignore_index, void* stream);
+VLPET_API int vlpet_ce_bwd(const void* logits, int64_t ld, const int64_t* labels, const float* lse, const float* dloss,
+                 void* dlogits, int64_t rows, int32_t ncols, int64_t ignore_index, void* stream);
+
 /* ---- CLIP-grid downsample feeding K3 --------------------------------------------------------------------
  * Replaces Downsample.downsample_inputs (src/modeling_bart.py:566-583: permute -> [B, F, g, g] -> AdaptiveMaxPool2d((o, o))
  * -> permute back) for the pre-extracted grid features of the VL-PET scripts (--n_boxes 36 --downsample: 7x7 -> 6x6),

@@ -594,6 +594,31 @@ def test_gelu_dropout_kernels(V):
     assert torch.equal((x.grad == 0)[sigb], dropped[sigb])          # same mask forward and backward
 
 
+@pytest.mark.parametrize("rows,ncols,ld", [(1, 8, 8), (333, 50496, 50496), (77, 1000, 1024), (2000, 512, 512)])
+def test_cross_entropy_bf16_matches_torch(V, rows, ncols, ld):
+    """LM-head loss straight from bf16 logits == CrossEntropyLoss(ignore_index=-100, reduction='none') on the fp32 copy
+    (src/modeling_bart.py:1585-1586), forward (fp32 accumulation: 1e-5) and backward (bf16 result: TOL_BF16)."""
+    import vlpet_b200.functional as F_
+    g = torch.Generator(device="cuda").manual_seed(rows + ncols)
+    buf = (3.0 * torch.randn(rows, ld, device="cuda", generator=g)).to(torch.bfloat16)
+    logits = buf[:, :ncols].requires_grad_()
+    labels = torch.randint(0, ncols, (rows,), device="cuda", generator=g)
+    labels[::7] = -100
+    if rows == 1:
+        labels[0] = 3
+    dl = torch.rand(rows, device="cuda", generator=g) + 0.5
+    assert F_.cross_entropy_supported(logits)
+    loss = F_.cross_entropy_bf16(logits, labels, -100)
+    (gl,) = torch.autograd.grad(loss, logits, dl)
+    ref_in = logits.detach().double().requires_grad_()
+    ref = torch.nn.functional.cross_entropy(ref_in, labels, ignore_index=-100, reduction="none")
+    (gr,) = torch.autograd.grad(ref, ref_in, dl.double())
+    f = lambda t: t.detach().double().cpu().numpy()  # noqa: E731
+    assert np.max(np.abs(f(loss) - f(ref))) <= 1e-5 * max(1.0, float(np.max(np.abs(f(ref)))))
+    assert torch.all(loss[labels == -100] == 0) and torch.all(gl[labels == -100] == 0)
+    bf16_check(f(gl), f(gr), TOL_BF16)
+
+
 @pytest.mark.parametrize("path", golden_files("k3lr_"), ids=os.path.basename)
 def test_k3_lowrank_projector_matches_reference_golden(V, path):
     """SURVEY §8 row a7 through the module mirror: vlpet_b200.LowRankVisualEmbedding (reference parameter names) in fp32

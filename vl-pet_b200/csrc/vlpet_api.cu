@@ -353,6 +353,76 @@ __global__ void __launch_bounds__(256) gelu_dropout_kernel(const __nv_bfloat16* 
   }
 }
 
+// Token cross-entropy over bf16 logits: one CTA per row, 8 logits per thread and iteration, online (max, sum) per
+// thread, block reduction through shared memory.  exp2 with the max folded in: sum_j 2^((x_j - m) log2e).
+constexpr int CE_THREADS = 256;
+__device__ __forceinline__ void ce_merge(float& m, float& s, float m2, float s2) {
+  const float mm = fmaxf(m, m2);
+  s = s * exp2f((m - mm) * 1.4426950408889634f) + s2 * exp2f((m2 - mm) * 1.4426950408889634f);
+  m = mm;
+}
+__global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld,
+                                                            const int64_t* __restrict__ labels, float* __restrict__ loss,
+                                                            float* __restrict__ lse, int ncols, int64_t ignore_index) {
+  const int64_t row = blockIdx.x;
+  const __nv_bfloat16* x = logits + row * ld;
+  float m = -3.0e38f, s = 0.f;
+  for (int i = threadIdx.x; i < ncols / 8; i += CE_THREADS) {
+    const uint4 q = *reinterpret_cast<const uint4*>(x + i * 8);
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(u[e] << 16); v[2 * e + 1] = __uint_as_float(u[e] & 0xffff0000u); }
+    float lm = v[0];
+#pragma unroll
+    for (int e = 1; e < 8; ++e) lm = fmaxf(lm, v[e]);
+    const float mm = fmaxf(m, lm);
+    float acc = s * exp2f((m - mm) * 1.4426950408889634f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += exp2f((v[e] - mm) * 1.4426950408889634f);
+    m = mm; s = acc;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ce_merge(m, s, __shfl_xor_sync(0xffffffffu, m, o), __shfl_xor_sync(0xffffffffu, s, o));
+  __shared__ float sm[CE_THREADS / 32], ss[CE_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; ss[threadIdx.x >> 5] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < CE_THREADS / 32; ++w) ce_merge(m, s, sm[w], ss[w]);
+    const float l = m + logf(s);
+    const int64_t lab = labels[row];
+    lse[row] = l;
+    loss[row] = (lab == ignore_index) ? 0.f : l - __bfloat162float(x[lab]);
+  }
+}
+__global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld,
+                                                            const int64_t* __restrict__ labels, const float* __restrict__ lse,
+                                                            const float* __restrict__ dloss, __nv_bfloat16* __restrict__ dlogits,
+                                                            int ncols, int64_t ignore_index) {
+  const int64_t row = blockIdx.x;
+  const __nv_bfloat16* x = logits + row * ld;
+  __nv_bfloat16* dx = dlogits + row * ld;
+  const int64_t lab = labels[row];
+  const float g = (lab == ignore_index) ? 0.f : dloss[row];
+  const float l2 = lse[row] * 1.4426950408889634f;
+  for (int i = threadIdx.x; i < ncols / 8; i += CE_THREADS) {
+    const uint4 q = *reinterpret_cast<const uint4*>(x + i * 8);
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = i * 8 + 2 * e;
+      float p0 = exp2f(fmaf(__uint_as_float(u[e] << 16), 1.4426950408889634f, -l2));
+      float p1 = exp2f(fmaf(__uint_as_float(u[e] & 0xffff0000u), 1.4426950408889634f, -l2));
+      if (j == lab) p0 -= 1.f;
+      if (j + 1 == lab) p1 -= 1.f;
+      __nv_bfloat162 t = __floats2bfloat162_rn(g * p0, g * p1);
+      o[e] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(dx + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // one thread = 8 consecutive channels of one output cell; windows per PyTorch's adaptive rule
 template <typename TI, typename TO>
 __global__ void grid_maxpool_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t nimg, int g, int o, int F) {
@@ -518,6 +588,32 @@ int vlpet_gelu_dropout_fwd(const void* x, void* y, int64_t n, float p_drop, uint
 int vlpet_gelu_dropout_bwd(const void* x, const void* dy, void* dx, int64_t n, float p_drop, uint64_t seed,
                            const uint64_t* seed_dev, void* stream) {
   return gelu_dropout_launch(true, x, dy, dx, n, p_drop, seed, seed_dev, stream);
+}
+
+static int check_ce(const void* logits, int64_t ld, const void* labels, int64_t rows, int32_t ncols) {
+  if (!logits || !labels || rows <= 0 || ncols <= 0 || ld < ncols) return fail(VLPET_E_BADARG, "ce: bad arguments");
+  if (ncols % 8 != 0 || ld % 8 != 0) return fail(VLPET_E_UNSUPPORTED, "ce: ncols and ld must be multiples of 8 (ncols=%d)", ncols);
+  if (!aligned16(logits)) return fail(VLPET_E_ALIGN, "ce: logits must be 16-byte aligned");
+  if (rows > 0x7fffffff) return fail(VLPET_E_UNSUPPORTED, "ce: too many rows");
+  return 0;
+}
+int vlpet_ce_fwd(const void* logits, int64_t ld, const int64_t* labels, float* loss, float* lse, int64_t rows, int32_t ncols,
+                 int64_t ignore_index, void* stream) {
+  VLPET_TRY(check_ce(logits, ld, labels, rows, ncols));
+  if (!loss || !lse) return fail(VLPET_E_BADARG, "ce_fwd: null output");
+  flat::ce_fwd_kernel<<<(unsigned)rows, flat::CE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(logits), ld, labels, loss, lse, ncols, ignore_index);
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+int vlpet_ce_bwd(const void* logits, int64_t ld, const int64_t* labels, const float* lse, const float* dloss, void* dlogits,
+                 int64_t rows, int32_t ncols, int64_t ignore_index, void* stream) {
+  VLPET_TRY(check_ce(logits, ld, labels, rows, ncols));
+  if (!lse || !dloss || !dlogits || !aligned16(dlogits)) return fail(VLPET_E_BADARG, "ce_bwd: bad arguments");
+  flat::ce_bwd_kernel<<<(unsigned)rows, flat::CE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(logits), ld, labels, lse, dloss, static_cast<__nv_bfloat16*>(dlogits), ncols, ignore_index);
+  VLPET_LAUNCH_OK();
+  return 0;
 }
 
 int vlpet_grid_maxpool(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t nimg, int32_t g, int32_t o,

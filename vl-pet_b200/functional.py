@@ -601,6 +601,47 @@ def gelu_dropout_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dtype == torch.bfloat16 and x.numel() % 8 == 0
 
 
+class CrossEntropyBf16Fn(torch.autograd.Function):
+    """Per-token cross-entropy (reduction='none') straight from bf16 logits (include/vlpet.h vlpet_ce_fwd / _bwd):
+    no fp32 copy of the [tokens, vocab] logits, one pass forward, one pass backward."""
+
+    @staticmethod
+    def forward(ctx, logits2d, labels, ignore_index: int):
+        _require_cuda(logits2d, labels)
+        rows, ncols = logits2d.shape
+        ld = logits2d.stride(0)
+        lab = labels.reshape(-1).contiguous()
+        loss = torch.empty(rows, dtype=torch.float32, device=logits2d.device)
+        lse = torch.empty(rows, dtype=torch.float32, device=logits2d.device)
+        L.check(_call("ce_fwd", rows * ncols * 2, L.lib.vlpet_ce_fwd, _p(logits2d), ld, _p(lab), _p(loss), _p(lse), rows, ncols,
+                      int(ignore_index), _stream()), "vlpet_ce_fwd")
+        ctx.save_for_backward(logits2d, lab, lse)
+        ctx.ignore_index = int(ignore_index)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits2d, lab, lse = ctx.saved_tensors
+        rows, ncols = logits2d.shape
+        ld = logits2d.stride(0)
+        dl = dloss.contiguous().float()
+        dlogits = torch.empty_strided(logits2d.shape, logits2d.stride(), dtype=logits2d.dtype, device=logits2d.device)
+        L.check(_call("ce_bwd", 2 * rows * ncols * 2, L.lib.vlpet_ce_bwd, _p(logits2d), ld, _p(lab), _p(lse), _p(dl), _p(dlogits),
+                      rows, ncols, ctx.ignore_index, _stream()), "vlpet_ce_bwd")
+        return dlogits, None, None
+
+
+def cross_entropy_supported(logits2d: torch.Tensor) -> bool:
+    return (logits2d.is_cuda and logits2d.dtype == torch.bfloat16 and logits2d.dim() == 2 and logits2d.stride(1) == 1
+            and logits2d.shape[1] % 8 == 0 and logits2d.stride(0) % 8 == 0 and logits2d.stride(0) >= logits2d.shape[1]
+            and logits2d.data_ptr() % 16 == 0)
+
+
+def cross_entropy_bf16(logits2d: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    """F.cross_entropy(logits.float(), labels, ignore_index, reduction='none') without the fp32 logits."""
+    return CrossEntropyBf16Fn.apply(logits2d, labels, ignore_index)
+
+
 def grid_maxpool(feats: torch.Tensor, out_size: int, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """[B, g*g, F] CLIP grid features -> [B, o*o, F] by adaptive max-pool (src/modeling_bart.py:556-613 Downsample),
     fused with the cast to ``out_dtype`` (include/vlpet.h vlpet_grid_maxpool).  Inputs are data: no autograd."""

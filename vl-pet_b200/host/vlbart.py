@@ -384,9 +384,12 @@ class VLBart(nn.Module):
         w, b, width = self._lm_operands(h.dtype)
         logits = F.linear(h, w, b.reshape(-1))          # bias folded into the GEMM epilogue: no extra pass over the logits
         lg = logits.view(-1, width)
-        if lg.dtype in (torch.bfloat16, torch.float16):
-            lg = lg.float()
-        loss = F.cross_entropy(lg, labels.reshape(-1), ignore_index=-100, reduction="none")
+        if F_.cross_entropy_supported(lg):     # bf16 on the GPU: fused kernel, no fp32 copy of the [tokens, vocab] logits
+            loss = F_.cross_entropy_bf16(lg, labels.reshape(-1), -100)
+        else:
+            if lg.dtype in (torch.bfloat16, torch.float16):
+                lg = lg.float()
+            loss = F.cross_entropy(lg, labels.reshape(-1), ignore_index=-100, reduction="none")
         return loss, logits[..., :cfg.vocab_size]
 
     def train_step(self, batch: dict) -> dict:
