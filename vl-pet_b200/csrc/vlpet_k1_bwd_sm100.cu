@@ -287,7 +287,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {   // NOT elect_one(): with the fast issue path B1 faults sporadically, and gains nothing   // NOT elect_one(): with the fast issue path B1 faults sporadically (open item)
+    if (lane == 0) {   // NOT elect_one(): with the fast issue path B1 faults sporadically, and gains nothing
       constexpr uint32_t IDESC_AP = ptx::umma_idesc_bf16_m128(R);                       // A/P: N = R, K-major x K-major
       constexpr uint32_t IDESC_UT = ptx::umma_idesc_bf16_m128(CH);                      // U/T: N = 64
       constexpr uint32_t IDESC_DZ = ptx::umma_idesc_bf16_m128_major(R, 0u, 1u);         // dz/dq: B MN-major, N = R
