@@ -59,3 +59,32 @@ def test_graph_replays_draw_fresh_dropout_masks():
         assert torch.equal(outs[1], outs[2])          # same device seed -> same mask (forward/backward agreement)
     finally:
         F_.set_device_seed(None)
+
+
+def test_fused_qkv_projection_equals_three_linears():
+    """Frozen self-attention: the one-GEMM q/k/v projection (host.vlbart.BartAttention._fused_qkv) must give the same
+    output and input gradient as the reference's three Linears (my_transformers/modeling_bart.py:143-280)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import vlpet_b200.host as H
+    from vlpet_b200.host.vlbart import BartAttention
+    torch.manual_seed(0)
+    cfg = H.tiny_test_config(d_model=128, adapter_down_dim=32, adapter_gating_down_dim=32,
+                             decoder_enc_attn_value_parallel_adapter_down_dim=32, assume_no_padding=True, dropout=0.0,
+                             attention_dropout=0.0, activation_dropout=0.0)
+    att = BartAttention(cfg, 4, is_decoder=False, value_adapter=False).cuda().to(torch.bfloat16).eval()
+    for p_ in att.parameters():
+        p_.requires_grad_(False)
+    x = torch.randn(5, 37, 128, device="cuda").to(torch.bfloat16)
+    dy = torch.randn(5, 37, 128, device="cuda").to(torch.bfloat16)
+    outs = []
+    for fused in (True, False):
+        xi = x.clone().requires_grad_()
+        if not fused:
+            att._fused_qkv = lambda: None
+        assert (att._fused_qkv() is not None) == fused
+        y = att(xi)
+        y.backward(dy)
+        outs.append((y.float(), xi.grad.float()))
+    for a, b in zip(outs[0], outs[1]):
+        assert (a - b).norm() <= 1e-2 * b.norm()        # two bf16 GEMM schedules: a few ulps apart

@@ -81,6 +81,20 @@ class BartAttention(nn.Module):
         self.q_proj = nn.Linear(d, d)
         self.out_proj = nn.Linear(d, d)
         self.attn_value_parallel_adapter = AdapterController(config.vpa_adapter_config()) if value_adapter else None
+        self._qkv = None      # (key, [3d, d] weight, [3d] bias): fused projection of a FROZEN self-attention, see _fused_qkv
+
+    def _fused_qkv(self):
+        """Self-attention with frozen projections on the GPU: q, k, v come out of ONE GEMM over the row-concatenated
+        weights (a cached copy; the state-dict keeps the reference's three Linears), and the backward is one dgrad GEMM
+        instead of three plus two gradient-accumulation passes over [tokens, d]."""
+        ws = (self.q_proj.weight, self.k_proj.weight, self.v_proj.weight)
+        bs = (self.q_proj.bias, self.k_proj.bias, self.v_proj.bias)
+        if any(t.requires_grad for t in ws + bs) or not ws[0].is_cuda:
+            return None
+        key = tuple((t.data_ptr(), t._version, t.dtype) for t in ws + bs)
+        if self._qkv is None or self._qkv[0] != key:
+            self._qkv = (key, torch.cat([t.detach() for t in ws], 0).contiguous(), torch.cat([t.detach() for t in bs], 0).contiguous())
+        return self._qkv[1], self._qkv[2]
 
     def _heads(self, t: torch.Tensor) -> torch.Tensor:
         B, L, _ = t.shape
@@ -88,15 +102,21 @@ class BartAttention(nn.Module):
 
     def forward(self, hidden_states, key_value_states=None, attn_mask=None, is_causal=False, task=None):
         src = hidden_states if key_value_states is None else key_value_states
-        q = self.q_proj(hidden_states)
-        k = self.k_proj(src)
-        v = self.v_proj(src)
-        if key_value_states is not None and self.attn_value_parallel_adapter is not None:
-            v = self.attn_value_parallel_adapter(key_value_states, task, y=v)          # K2
-        with _sdpa_policy(q):
-            o = F.scaled_dot_product_attention(self._heads(q), self._heads(k), self._heads(v), attn_mask=attn_mask,
-                                               dropout_p=self.dropout if self.training else 0.0, is_causal=is_causal)
+        fused = self._fused_qkv() if key_value_states is None else None
         B, L, _ = hidden_states.shape
+        if fused is not None:
+            qkv = F.linear(hidden_states, fused[0], fused[1]).view(B, L, 3, self.num_heads, self.head_dim)
+            qh, kh, vh = (t.transpose(1, 2) for t in qkv.unbind(2))
+        else:
+            q = self.q_proj(hidden_states)
+            k = self.k_proj(src)
+            v = self.v_proj(src)
+            if key_value_states is not None and self.attn_value_parallel_adapter is not None:
+                v = self.attn_value_parallel_adapter(key_value_states, task, y=v)          # K2
+            qh, kh, vh = self._heads(q), self._heads(k), self._heads(v)
+        with _sdpa_policy(qh):
+            o = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=attn_mask,
+                                               dropout_p=self.dropout if self.training else 0.0, is_causal=is_causal)
         return self.out_proj(o.transpose(1, 2).reshape(B, L, self.embed_dim))
 
 
