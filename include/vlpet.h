@@ -203,6 +203,21 @@ VLPET_API int vlpet_gelu_dropout_fwd(const void* x, void* y, int64_t n, float p_
 VLPET_API int vlpet_gelu_dropout_bwd(const void* x, const void* dy, void* dx, int64_t n, float p_drop, uint64_t seed,
                            const uint64_t* seed_dev, void* stream);
 
+/* ---- short-sequence attention of the frozen blocks -------------------------------------
+ * out = dropout_p(softmax(q k^T / 8 [+ causal mask])) v per (batch, head), head_dim = 64, bf16, Lq, Lk <= 128, no padding
+ * mask -- the bmm / softmax / dropout / bmm sequence of BartAttention.forward (my_transformers/modeling_bart.py:143-280)
+ * at the sequence lengths of the VL-PET workloads, where the library flash kernels are overhead-bound.  One CTA per
+ * (batch, head), the whole score tile in shared memory.  q / k / v: row i of batch b at base + (b*L + i)*rs elements, head h
+ * at +64h inside the row (so the three thirds of a fused [B, L, 3*H*64] projection, or three [B, L, H*64] tensors).
+ * out / dout / dq / dk / dv: [B, L, H*64] contiguous; lse: [B, H, Lq] fp32 (saved for the backward).  The dropout mask is
+ * the counter-based stream of K1 (seed + *seed_dev), regenerated by the backward.                                     */
+VLPET_API int vlpet_attn_fwd(const void* q, const void* k, const void* v, int64_t q_rs, int64_t k_rs, int64_t v_rs, void* out,
+                   float* lse, int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t causal, float p_drop, uint64_t seed,
+                   const uint64_t* seed_dev, void* stream);
+VLPET_API int vlpet_attn_bwd(const void* q, const void* k, const void* v, int64_t q_rs, int64_t k_rs, int64_t v_rs, const void* out,
+                   const void* dout, const float* lse, void* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t Lq,
+                   int32_t Lk, int32_t causal, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream);
+
 /* ---- token cross-entropy of the LM head (frozen decoder output) -------------------------
  * loss[i] = logsumexp_j(logits[i, j]) - logits[i, labels[i]] in fp32 straight from the bf16 logits (0, and a zero gradient
  * row, where labels[i] == ignore_index), replacing `lm_logits.float()` + `CrossEntropyLoss(ignore_index=-100,

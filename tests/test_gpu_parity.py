@@ -668,3 +668,90 @@ def test_k3_lowrank_projector_matches_reference_golden(V, path):
     for k, v in got.items():
         assert rel(v, g["d" + k]) < TOL_F32, k
     assert ve.obj_order_embedding.weight.grad is None        # aliases the frozen token table
+
+
+def _attn_ref(q, k, v, H, causal, mask=None):
+    """fp64 reference of BartAttention's core (my_transformers/modeling_bart.py:143-280): [B, L, H*64] in and out."""
+    B, Lq, _ = q.shape
+    Lk = k.shape[1]
+    qh, kh, vh = (t.double().view(B, -1, H, 64).transpose(1, 2) for t in (q, k, v))
+    s = qh @ kh.transpose(-1, -2) * 0.125
+    if causal:
+        s = s.masked_fill(torch.ones(Lq, Lk, dtype=torch.bool, device=q.device).triu(1), float("-inf"))
+    p = torch.softmax(s, -1)
+    if mask is not None:
+        p = p * mask
+    return (p @ vh).transpose(1, 2).reshape(B, Lq, H * 64)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,causal,fused", [
+    (3, 12, 56, 56, False, True),      # encoder self-attention (36 visual + 20 text tokens), fused q/k/v projection views
+    (2, 12, 92, 92, False, False),     # NLVR: two images
+    (4, 12, 40, 40, True, True),       # decoder self-attention, causal
+    (3, 12, 5, 56, False, False),      # cross-attention
+    (2, 4, 1, 1, True, False),
+    (2, 3, 128, 77, False, False),
+])
+def test_short_attention_matches_reference(V, B, H, Lq, Lk, causal, fused):
+    import vlpet_b200.functional as F_
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Lq + Lk)
+    bf = torch.bfloat16
+    d = H * 64
+    if fused:
+        qkv = torch.randn(B, Lq, 3, d, device="cuda", generator=g).to(bf).requires_grad_()
+        q, k, v = qkv.unbind(2)
+    else:
+        q = torch.randn(B, Lq, d, device="cuda", generator=g).to(bf).requires_grad_()
+        k = torch.randn(B, Lk, d, device="cuda", generator=g).to(bf).requires_grad_()
+        v = torch.randn(B, Lk, d, device="cuda", generator=g).to(bf).requires_grad_()
+    dout = torch.randn(B, Lq, d, device="cuda", generator=g).to(bf)
+    assert F_.short_attention_supported(q, k, v, H)
+    out = F_.short_attention(q, k, v, H, causal, 0.0, False)
+    leaves = (qkv,) if fused else (q, k, v)
+    grads = torch.autograd.grad(out, leaves, dout)
+    if fused:
+        rl = qkv.detach().double().requires_grad_()
+        rq, rk, rv = rl.unbind(2)
+        rleaves = (rl,)
+    else:
+        rq, rk, rv = (t.detach().double().requires_grad_() for t in (q, k, v))
+        rleaves = (rq, rk, rv)
+    ref = _attn_ref(rq, rk, rv, H, causal)
+    rgrads = torch.autograd.grad(ref, rleaves, dout.double())
+    f = lambda t: t.detach().double().cpu().numpy()  # noqa: E731
+    bf16_check(f(out), f(ref), 4 * TOL_BF16)          # P is rounded to bf16 before the P V product (as torch's bf16 bmm does)
+    for a, b in zip(grads, rgrads):                   # bf16 P / dS operands: library flash kernels land in the same place
+        a, b = f(a), f(b)                             # (absolute floor: with one key the true dq, dk are exactly zero)
+        assert np.linalg.norm(a - b) <= 2e-2 * np.linalg.norm(b) + 1e-5 * np.sqrt(a.size)
+
+
+def test_short_attention_dropout_mask_is_consistent(V):
+    """p > 0: the forward's mask is recovered exactly by feeding v = identity; out and all three gradients then match the
+    reference evaluated with THAT mask (the backward regenerates it from the seed), and ~p of the probabilities are dropped."""
+    import vlpet_b200.functional as F_
+    B, H, L, p = 2, 12, 48, 0.25
+    g = torch.Generator(device="cuda").manual_seed(5)
+    bf = torch.bfloat16
+    q = torch.randn(B, L, H * 64, device="cuda", generator=g).to(bf).requires_grad_()
+    k = torch.randn(B, L, H * 64, device="cuda", generator=g).to(bf).requires_grad_()
+    v = torch.randn(B, L, H * 64, device="cuda", generator=g).to(bf).requires_grad_()
+    dout = torch.randn(B, L, H * 64, device="cuda", generator=g).to(bf)
+    eye = torch.zeros(B, L, H, 64, device="cuda", dtype=bf)
+    for j in range(L):
+        eye[:, j, :, j] = 1.0
+    seed = 4242
+    with torch.no_grad():
+        pd = F_.ShortAttentionFn.apply(q, k, eye.view(B, L, H * 64), H, False, p, seed).view(B, L, H, 64)[..., :L]   # [B, i, H, j]
+    pd = pd.permute(0, 2, 1, 3).double()                      # [B, H, i, j]
+    mask = (pd > 0).double() / (1 - p)
+    frac = 1.0 - float((pd > 0).double().mean())
+    assert abs(frac - p) < 0.02
+    out = F_.ShortAttentionFn.apply(q, k, v, H, False, p, seed)
+    grads = torch.autograd.grad(out, (q, k, v), dout)
+    rq, rk, rv = (t.detach().double().requires_grad_() for t in (q, k, v))
+    ref = _attn_ref(rq, rk, rv, H, False, mask=mask)
+    rgrads = torch.autograd.grad(ref, (rq, rk, rv), dout.double())
+    f = lambda t: t.detach().double().cpu().numpy()  # noqa: E731
+    assert rel(f(out), f(ref)) < 1e-2
+    for a, b in zip(grads, rgrads):
+        assert rel(f(a), f(b)) < 2e-2

@@ -590,6 +590,19 @@ int vlpet_gelu_dropout_bwd(const void* x, const void* dy, void* dx, int64_t n, f
   return gelu_dropout_launch(true, x, dy, dx, n, p_drop, seed, seed_dev, stream);
 }
 
+int vlpet_attn_fwd(const void* q, const void* k, const void* v, int64_t q_rs, int64_t k_rs, int64_t v_rs, void* out, float* lse,
+                   int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t causal, float p_drop, uint64_t seed,
+                   const uint64_t* seed_dev, void* stream) {
+  return attn_run(false, q, k, v, q_rs, k_rs, v_rs, out, lse, nullptr, nullptr, nullptr, nullptr, nullptr, B, H, Lq, Lk, causal,
+                  p_drop, seed, seed_dev, static_cast<cudaStream_t>(stream));
+}
+int vlpet_attn_bwd(const void* q, const void* k, const void* v, int64_t q_rs, int64_t k_rs, int64_t v_rs, const void* out,
+                   const void* dout, const float* lse, void* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
+                   int32_t causal, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+  return attn_run(true, q, k, v, q_rs, k_rs, v_rs, nullptr, const_cast<float*>(lse), out, dout, dq, dk, dv, B, H, Lq, Lk, causal,
+                  p_drop, seed, seed_dev, static_cast<cudaStream_t>(stream));
+}
+
 static int check_ce(const void* logits, int64_t ld, const void* labels, int64_t rows, int32_t ncols) {
   if (!logits || !labels || rows <= 0 || ncols <= 0 || ld < ncols) return fail(VLPET_E_BADARG, "ce: bad arguments");
   if (ncols % 8 != 0 || ld % 8 != 0) return fail(VLPET_E_UNSUPPORTED, "ce: ncols and ld must be multiples of 8 (ncols=%d)", ncols);

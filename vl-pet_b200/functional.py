@@ -601,6 +601,57 @@ def gelu_dropout_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dtype == torch.bfloat16 and x.numel() % 8 == 0
 
 
+class ShortAttentionFn(torch.autograd.Function):
+    """softmax(q k^T / 8 [causal]) (dropout) v for head_dim 64 and L <= 128 (include/vlpet.h vlpet_attn_fwd / _bwd).
+    q, k, v: [B, L, H*64] bf16 with unit inner stride and batch stride L * row stride (views of a fused projection ok)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, H: int, causal: bool, p: float, seed: int):
+        _require_cuda(q, k, v)
+        B, Lq, _ = q.shape
+        Lk = k.shape[1]
+        out = torch.empty(B, Lq, H * 64, dtype=q.dtype, device=q.device)
+        lse = torch.empty(B, H, Lq, dtype=torch.float32, device=q.device)
+        sd = _seed_dev.data_ptr() if (seed and _seed_dev is not None) else None
+        pd = float(p if seed else 0.0)
+        nb = 2 * (q.numel() + k.numel() + v.numel() + out.numel())
+        L.check(_call("attn_fwd", nb, L.lib.vlpet_attn_fwd, _p(q), _p(k), _p(v), q.stride(1), k.stride(1), v.stride(1), _p(out), _p(lse),
+                      B, H, Lq, Lk, int(causal), pd, seed, C.c_void_p(sd) if sd else C.c_void_p(0), _stream()), "vlpet_attn_fwd")
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.args = (H, int(causal), pd, seed, sd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        H, causal, pd, seed, sd = ctx.args
+        B, Lq, _ = q.shape
+        Lk = k.shape[1]
+        dout = dout.contiguous()
+        dq = torch.empty(B, Lq, H * 64, dtype=q.dtype, device=q.device)
+        dk = torch.empty(B, Lk, H * 64, dtype=q.dtype, device=q.device)
+        dv = torch.empty(B, Lk, H * 64, dtype=q.dtype, device=q.device)
+        nb = 2 * (2 * q.numel() + 2 * k.numel() + 2 * v.numel() + 2 * out.numel())
+        L.check(_call("attn_bwd", nb, L.lib.vlpet_attn_bwd, _p(q), _p(k), _p(v), q.stride(1), k.stride(1), v.stride(1), _p(out),
+                      _p(dout), _p(lse), _p(dq), _p(dk), _p(dv), B, H, Lq, Lk, causal, pd, seed,
+                      C.c_void_p(sd) if sd else C.c_void_p(0), _stream()), "vlpet_attn_bwd")
+        return dq, dk, dv, None, None, None, None
+
+
+def short_attention_supported(q, k, v, H: int) -> bool:
+    def ok(t):
+        return (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 3 and t.shape[2] == H * 64 and t.stride(2) == 1
+                and t.stride(1) % 8 == 0 and t.stride(0) == t.shape[1] * t.stride(1) and t.data_ptr() % 16 == 0)
+    return ok(q) and ok(k) and ok(v) and q.shape[1] <= 128 and k.shape[1] <= 128 and k.shape[1] == v.shape[1] \
+        and q.shape[0] == k.shape[0]
+
+
+def short_attention(q, k, v, H: int, causal: bool, p: float, training: bool) -> torch.Tensor:
+    """[B, Lq, H*64] x [B, Lk, H*64]^2 -> [B, Lq, H*64]: attention of the frozen BART blocks in one launch each way."""
+    seed = next_dropout_seed() if (training and p > 0.0) else 0
+    return ShortAttentionFn.apply(q, k, v, H, causal, p, seed)
+
+
 class CrossEntropyBf16Fn(torch.autograd.Function):
     """Per-token cross-entropy (reduction='none') straight from bf16 logits (include/vlpet.h vlpet_ce_fwd / _bwd):
     no fp32 copy of the [tokens, vocab] logits, one pass forward, one pass backward."""

@@ -33,6 +33,11 @@ except Exception:                                                    # older tor
     _SDPA_ORDER = None
 
 
+SHORT_ATTENTION = False    # vlpet_attn_fwd/_bwd (one CTA per head, wmma tiles through shared memory) is parity-green but measured
+                           # SLOWER than torch's memory-efficient SDPA at these lengths (146 vs 59 us forward, 295 vs 119 us
+                           # backward per call, bs = 300): off until the register-resident version exists
+
+
 def _ln(ln: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
     """LayerNorm whose (trainable, fp32-master) affine parameters may be wider than the activation dtype.  On the GPU in
     bf16 it runs the one-launch row kernels of libvlpet.so; anywhere else stock F.layer_norm."""
@@ -105,15 +110,19 @@ class BartAttention(nn.Module):
         fused = self._fused_qkv() if key_value_states is None else None
         B, L, _ = hidden_states.shape
         if fused is not None:
-            qkv = F.linear(hidden_states, fused[0], fused[1]).view(B, L, 3, self.num_heads, self.head_dim)
-            qh, kh, vh = (t.transpose(1, 2) for t in qkv.unbind(2))
+            q, k, v = F.linear(hidden_states, fused[0], fused[1]).view(B, L, 3, self.embed_dim).unbind(2)
         else:
             q = self.q_proj(hidden_states)
             k = self.k_proj(src)
             v = self.v_proj(src)
             if key_value_states is not None and self.attn_value_parallel_adapter is not None:
                 v = self.attn_value_parallel_adapter(key_value_states, task, y=v)          # K2
-            qh, kh, vh = self._heads(q), self._heads(k), self._heads(v)
+        if attn_mask is None and self.head_dim == 64 and SHORT_ATTENTION and F_.short_attention_supported(q, k, v, self.num_heads):
+            # one CTA per (batch, head), whole score tile in shared memory (include/vlpet.h vlpet_attn_fwd); output is
+            # already [B, L, d]: no head transposes either way
+            o = F_.short_attention(q, k, v, self.num_heads, is_causal, self.dropout, self.training)
+            return self.out_proj(o)
+        qh, kh, vh = self._heads(q), self._heads(k), self._heads(v)
         with _sdpa_policy(qh):
             o = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=attn_mask,
                                                dropout_p=self.dropout if self.training else 0.0, is_causal=is_causal)
