@@ -382,7 +382,8 @@ def test_k2_matches_reference_golden(V, path, dtype, tol):
 
 
 @pytest.mark.parametrize("M,d,r,sf", [(1, 768, 96, 1.0), (200, 768, 96, 1.0), (1300, 768, 96, 0.7), (333, 768, 48, 1.0),
-                                      (640, 256, 32, 2.0), (148 * 128 + 500, 768, 96, 1.0)])
+                                      (640, 256, 32, 2.0), (148 * 128 + 500, 768, 96, 1.0),
+                                      (148 * 128 * 2 + 300, 768, 96, 0.7)])   # two waves: the ungated CTA-pair forward
 def test_k2_fused_matches_oracle(V, M, d, r, sf):
     """Decoder value parallel adapter through the fused tcgen05 kernels (ungated form of K1: x1 = y, x2 = kv, kappa = 0,
     alpha = sf).  Same bars as the gated backward: bf16_check at 1e-3 for out / dkv against the fp64 oracle with bf16
