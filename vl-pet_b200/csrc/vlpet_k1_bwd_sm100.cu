@@ -17,8 +17,10 @@
 //   phase 3  (64-col chunks) T_c again (only G is needed; recompute beats keeping [128 x 768] gates),
 //                           DX2_c = da Wd[:,c], DX1_c = dp Gd[:,c]                    tcgen05 (B MN-major from Wd_c/Gd_c tiles)
 //   epi 4                   dx2 = k dh G + DX2, dx1 = dout + DX1                      -> smem -> TMA store
-// Warp roles: 0 TMA producer (activations), 3 TMA producer (weights), 1 MMA issuer (TMEM owner), 2 TMA-store issuer, 4..11 epilogue (warp%4 = TMEM
-// lane quarter; (warp-4)/4 = "half": adapter branch / gate branch in epi 1/3, left / right 32 columns in epi 2/4).
+// Warp roles: 0 TMA producer (activations), 3 TMA producer (weights), 1 MMA issuer (TMEM owner), 2 TMA-store issuer,
+// 4..19 epilogue (warp%4 = TMEM lane quarter; cg = (warp-4)/4: adapter | gate branch and column half in epi 1/3, 16 of the
+// chunk's 64 columns in epi 2/4).  Epilogue arithmetic is on packed fp32 pairs (FFMA2); the pre-scaled fp32 bias tables
+// live in the unused 64-byte halves of the swizzled dp block (BCfg::OFF_TAB).
 #include <type_traits>
 
 #include "sm100_ptx.cuh"
