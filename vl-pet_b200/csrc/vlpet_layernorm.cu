@@ -22,12 +22,25 @@ __global__ void __launch_bounds__(256) ln_fwd_bf16_kernel(const __nv_bfloat16* _
   const int lane = threadIdx.x % 32;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x / 32);
+  // Rows are latency-bound (load -> two warp reductions -> store): the next row's loads are issued before this row's
+  // reductions, so every warp keeps a row in flight while it computes.
+  uint4 cur[VPL];
+  if (warp0 < M) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) cur[i] = *reinterpret_cast<const uint4*>(x + warp0 * D + (i * 32 + lane) * 8);
+  }
   for (int64_t row = warp0; row < M; row += nwarps) {
+    uint4 nxt[VPL];
+    const int64_t nrow = row + nwarps;
+    if (nrow < M) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) nxt[i] = *reinterpret_cast<const uint4*>(x + nrow * D + (i * 32 + lane) * 8);
+    }
     float v[VPL * 8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const uint4 q = *reinterpret_cast<const uint4*>(x + row * D + (i * 32 + lane) * 8);
+      const uint4 q = cur[i];
       const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -57,6 +70,8 @@ __global__ void __launch_bounds__(256) ln_fwd_bf16_kernel(const __nv_bfloat16* _
       }
       *reinterpret_cast<uint4*>(y + row * D + c) = make_uint4(o[0], o[1], o[2], o[3]);
     }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) cur[i] = nxt[i];
   }
 }
 
@@ -147,7 +162,7 @@ bool layernorm_supported(int d, int dtype) { return dtype == VLPET_BF16 && d % 2
 int layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int64_t M, int d,
                   float eps, cudaStream_t st) {
   int64_t blocks = (M + 7) / 8;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 3) blocks = 148 * 3;   // all resident (3 blocks of 256 threads per SM): every warp pipelines its rows
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
   switch (d / 256) {
