@@ -646,6 +646,12 @@ def short_attention_supported(q, k, v, H: int) -> bool:
         and q.shape[0] == k.shape[0]
 
 
+def short_attention_profitable(q, k) -> bool:
+    """L <= 64 runs the register-resident kernels (1.7-2.4x faster than torch SDPA forward + backward on B200 at the
+    workload's shapes, tools/attn_probe.py); 65..128 runs the shared-memory (wmma) kernels, which are slower than SDPA."""
+    return q.shape[1] <= 64 and k.shape[1] <= 64
+
+
 def short_attention(q, k, v, H: int, causal: bool, p: float, training: bool) -> torch.Tensor:
     """[B, Lq, H*64] x [B, Lk, H*64]^2 -> [B, Lq, H*64]: attention of the frozen BART blocks in one launch each way."""
     seed = next_dropout_seed() if (training and p > 0.0) else 0

@@ -33,9 +33,9 @@ except Exception:                                                    # older tor
     _SDPA_ORDER = None
 
 
-SHORT_ATTENTION = False    # vlpet_attn_fwd/_bwd (one CTA per head, wmma tiles through shared memory) is parity-green but measured
-                           # SLOWER than torch's memory-efficient SDPA at these lengths (146 vs 59 us forward, 295 vs 119 us
-                           # backward per call, bs = 300): off until the register-resident version exists
+SHORT_ATTENTION = True     # frozen attention through vlpet_attn_fwd/_bwd when both sequence lengths are <= 64 (register-resident
+                           # kernels: 187 vs 314 us forward + backward per encoder call at bs = 300); longer sequences (NLVR: 92)
+                           # and masked attention stay on torch SDPA
 
 
 def _ln(ln: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
@@ -117,7 +117,8 @@ class BartAttention(nn.Module):
             v = self.v_proj(src)
             if key_value_states is not None and self.attn_value_parallel_adapter is not None:
                 v = self.attn_value_parallel_adapter(key_value_states, task, y=v)          # K2
-        if attn_mask is None and self.head_dim == 64 and SHORT_ATTENTION and F_.short_attention_supported(q, k, v, self.num_heads):
+        if attn_mask is None and self.head_dim == 64 and SHORT_ATTENTION and F_.short_attention_supported(q, k, v, self.num_heads) \
+                and F_.short_attention_profitable(q, k):
             # one CTA per (batch, head), whole score tile in shared memory (include/vlpet.h vlpet_attn_fwd); output is
             # already [B, L, d]: no head transposes either way
             o = F_.short_attention(q, k, v, self.num_heads, is_causal, self.dropout, self.training)
