@@ -257,9 +257,15 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {     // lowbias32
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
-// 2 x 16 random bits for key columns (c, c+1), c even, of row `rowid`
-__device__ __forceinline__ uint32_t attn_bits(uint32_t seed_lo, uint32_t seed_hi, uint32_t rowid, uint32_t c) {
-  return mix32(seed_lo ^ mix32(rowid * 0x9E3779B1u + seed_hi) ^ ((c >> 1) * 0x85EBCA6Bu));
+// per-row key of the dropout stream, and 2 x 16 random bits for key columns (c, c+1), c even, of that row
+__device__ __forceinline__ uint32_t attn_rowkey(uint32_t seed_lo, uint32_t seed_hi, uint32_t rowid) {
+  return seed_lo ^ mix32(rowid * 0x9E3779B1u + seed_hi);
+}
+__device__ __forceinline__ uint32_t attn_bits(uint32_t rowkey, uint32_t c) { return mix32(rowkey ^ ((c >> 1) * 0x85EBCA6Bu)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -383,7 +389,7 @@ __global__ void __launch_bounds__(128) attn2_fwd_kernel(const AttnArgs a) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float mm = (e < 2) ? m0 : m1;
-      const float pv = (s[n][e] > -1.0e38f) ? exp2f(s[n][e] - mm) : 0.f;
+      const float pv = (s[n][e] > -1.0e38f) ? ex2_approx(s[n][e] - mm) : 0.f;
       s[n][e] = pv;
       if (e < 2) sum0 += pv; else sum1 += pv;
     }
@@ -395,13 +401,14 @@ __global__ void __launch_bounds__(128) attn2_fwd_kernel(const AttnArgs a) {
     if (row1 < a.Lq) a.lse[bh * a.Lq + row1] = (m1 + log2f(sum1)) * 0.6931471805599453f;
   }
   const float k0 = inv0 * a.inv_keep, k1 = inv1 * a.inv_keep;   // inv_keep == 1 without dropout
-  const uint32_t slo = (uint32_t)seed, shi = (uint32_t)(seed >> 32);
+  const uint32_t rk0 = attn_rowkey((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(bh * a.Lq + row0));
+  const uint32_t rk1 = attn_rowkey((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(bh * a.Lq + row1));
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     float f0 = k0, f1 = k0, f2 = k1, f3 = k1;
     if (a.thr16) {
       const uint32_t c = (uint32_t)(n * 8 + 2 * t);
-      const uint32_t r0b = attn_bits(slo, shi, (uint32_t)(bh * a.Lq + row0), c), r1b = attn_bits(slo, shi, (uint32_t)(bh * a.Lq + row1), c);
+      const uint32_t r0b = attn_bits(rk0, c), r1b = attn_bits(rk1, c);
       if ((r0b & 0xffffu) < a.thr16) f0 = 0.f;
       if ((r0b >> 16) < a.thr16) f1 = 0.f;
       if ((r1b & 0xffffu) < a.thr16) f2 = 0.f;
@@ -450,7 +457,8 @@ __global__ void __launch_bounds__(128) attn2_bwd_kernel(const AttnArgs a) {
     gemm_nt(dp, da, uV, lane);                         // dP = dO V^T
     const float l0 = (row0 < a.Lq) ? a.lse[bh * a.Lq + row0] * 1.4426950408889634f : 0.f;
     const float l1 = (row1 < a.Lq) ? a.lse[bh * a.Lq + row1] * 1.4426950408889634f : 0.f;
-    const uint32_t slo = (uint32_t)seed, shi = (uint32_t)(seed >> 32);
+    const uint32_t rk0 = attn_rowkey((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(bh * a.Lq + row0));
+    const uint32_t rk1 = attn_rowkey((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(bh * a.Lq + row1));
     float d0 = 0.f, d1 = 0.f;
     float pd[8][4];
 #pragma unroll
@@ -458,7 +466,7 @@ __global__ void __launch_bounds__(128) attn2_bwd_kernel(const AttnArgs a) {
       float f[4] = {a.inv_keep, a.inv_keep, a.inv_keep, a.inv_keep};
       if (a.thr16) {
         const uint32_t c = (uint32_t)(n * 8 + 2 * t);
-        const uint32_t r0b = attn_bits(slo, shi, (uint32_t)(bh * a.Lq + row0), c), r1b = attn_bits(slo, shi, (uint32_t)(bh * a.Lq + row1), c);
+        const uint32_t r0b = attn_bits(rk0, c), r1b = attn_bits(rk1, c);
         if ((r0b & 0xffffu) < a.thr16) f[0] = 0.f;
         if ((r0b >> 16) < a.thr16) f[1] = 0.f;
         if ((r1b & 0xffffu) < a.thr16) f[2] = 0.f;
@@ -468,7 +476,7 @@ __global__ void __launch_bounds__(128) attn2_bwd_kernel(const AttnArgs a) {
       for (int e = 0; e < 4; ++e) {
         const int col = n * 8 + 2 * t + (e & 1), row = (e < 2) ? row0 : row1;
         const bool ok = row < a.Lq && col < a.Lk && (!a.causal || col <= row);
-        const float pv = ok ? exp2f(s[n][e] * sl2 - ((e < 2) ? l0 : l1)) : 0.f;
+        const float pv = ok ? ex2_approx(s[n][e] * sl2 - ((e < 2) ? l0 : l1)) : 0.f;
         s[n][e] = pv;                                  // P
         pd[n][e] = pv * f[e];                          // P dropped (scaled)
         dp[n][e] *= f[e];                              // dP through the dropout
