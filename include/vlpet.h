@@ -209,14 +209,16 @@ VLPET_API int vlpet_gelu_dropout_bwd(const void* x, const void* dy, void* dx, in
  * at the sequence lengths of the VL-PET workloads, where the library flash kernels are overhead-bound.  One CTA per
  * (batch, head), the whole score tile in shared memory.  q / k / v: row i of batch b at base + (b*L + i)*rs elements, head h
  * at +64h inside the row (so the three thirds of a fused [B, L, 3*H*64] projection, or three [B, L, H*64] tensors).
- * out / dout / dq / dk / dv: [B, L, H*64] contiguous; lse: [B, H, Lq] fp32 (saved for the backward).  The dropout mask is
- * the counter-based stream of K1 (seed + *seed_dev), regenerated by the backward.                                     */
+ * out / dout: [B, L, H*64] contiguous; dq / dk / dv: rows with strides dq_rs / dk_rs / dv_rs elements (H*64 for separate
+ * tensors, 3*H*64 for the thirds of one fused [B, L, 3*H*64] gradient buffer); lse: [B, H, Lq] fp32 (saved for the backward).
+ * The dropout mask is a counter-based stream (seed + *seed_dev), regenerated by the backward.                          */
 VLPET_API int vlpet_attn_fwd(const void* q, const void* k, const void* v, int64_t q_rs, int64_t k_rs, int64_t v_rs, void* out,
                    float* lse, int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t causal, float p_drop, uint64_t seed,
                    const uint64_t* seed_dev, void* stream);
 VLPET_API int vlpet_attn_bwd(const void* q, const void* k, const void* v, int64_t q_rs, int64_t k_rs, int64_t v_rs, const void* out,
-                   const void* dout, const float* lse, void* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t Lq,
-                   int32_t Lk, int32_t causal, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream);
+                   const void* dout, const float* lse, void* dq, void* dk, void* dv, int64_t dq_rs, int64_t dk_rs, int64_t dv_rs,
+                   int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t causal, float p_drop, uint64_t seed,
+                   const uint64_t* seed_dev, void* stream);
 
 /* ---- token cross-entropy of the LM head (frozen decoder output) -------------------------
  * loss[i] = logsumexp_j(logits[i, j]) - logits[i, labels[i]] in fp32 straight from the bf16 logits (0, and a zero gradient

@@ -707,7 +707,12 @@ def test_short_attention_matches_reference(V, B, H, Lq, Lk, causal, fused):
         v = torch.randn(B, Lk, d, device="cuda", generator=g).to(bf).requires_grad_()
     dout = torch.randn(B, Lq, d, device="cuda", generator=g).to(bf)
     assert F_.short_attention_supported(q, k, v, H)
-    out = F_.short_attention(q, k, v, H, causal, 0.0, False)
+    if fused:      # the path of the host model: attention straight on the fused projection, one fused gradient buffer back
+        out = F_.short_self_attention(qkv, H, causal, 0.0, False)
+        out2 = F_.short_attention(q, k, v, H, causal, 0.0, False)
+        assert torch.equal(out, out2)
+    else:
+        out = F_.short_attention(q, k, v, H, causal, 0.0, False)
     leaves = (qkv,) if fused else (q, k, v)
     grads = torch.autograd.grad(out, leaves, dout)
     if fused:

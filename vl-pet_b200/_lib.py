@@ -121,8 +121,8 @@ SYMBOLS = {
     "vlpet_gelu_dropout_bwd": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_float, C.c_uint64, _vp, _vp]),
     "vlpet_attn_fwd": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_float, C.c_uint64, _vp, _vp]),
-    "vlpet_attn_bwd": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32,
-                                 C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _vp, _vp]),
+    "vlpet_attn_bwd": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64,
+                                 C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _vp, _vp]),
     "vlpet_ce_fwd": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int64, _vp]),
     "vlpet_ce_bwd": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int64, _vp]),
     "vlpet_grid_maxpool": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp]),

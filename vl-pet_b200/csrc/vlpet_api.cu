@@ -593,14 +593,15 @@ int vlpet_gelu_dropout_bwd(const void* x, const void* dy, void* dx, int64_t n, f
 int vlpet_attn_fwd(const void* q, const void* k, const void* v, int64_t q_rs, int64_t k_rs, int64_t v_rs, void* out, float* lse,
                    int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t causal, float p_drop, uint64_t seed,
                    const uint64_t* seed_dev, void* stream) {
-  return attn_run(false, q, k, v, q_rs, k_rs, v_rs, out, lse, nullptr, nullptr, nullptr, nullptr, nullptr, B, H, Lq, Lk, causal,
-                  p_drop, seed, seed_dev, static_cast<cudaStream_t>(stream));
+  return attn_run(false, q, k, v, q_rs, k_rs, v_rs, out, lse, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, B, H, Lq, Lk,
+                  causal, p_drop, seed, seed_dev, static_cast<cudaStream_t>(stream));
 }
 int vlpet_attn_bwd(const void* q, const void* k, const void* v, int64_t q_rs, int64_t k_rs, int64_t v_rs, const void* out,
-                   const void* dout, const float* lse, void* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
-                   int32_t causal, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream) {
-  return attn_run(true, q, k, v, q_rs, k_rs, v_rs, nullptr, const_cast<float*>(lse), out, dout, dq, dk, dv, B, H, Lq, Lk, causal,
-                  p_drop, seed, seed_dev, static_cast<cudaStream_t>(stream));
+                   const void* dout, const float* lse, void* dq, void* dk, void* dv, int64_t dq_rs, int64_t dk_rs, int64_t dv_rs,
+                   int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t causal, float p_drop, uint64_t seed,
+                   const uint64_t* seed_dev, void* stream) {
+  return attn_run(true, q, k, v, q_rs, k_rs, v_rs, nullptr, const_cast<float*>(lse), out, dout, dq, dk, dv, dq_rs, dk_rs, dv_rs, B, H,
+                  Lq, Lk, causal, p_drop, seed, seed_dev, static_cast<cudaStream_t>(stream));
 }
 
 static int check_ce(const void* logits, int64_t ld, const void* labels, int64_t rows, int32_t ncols) {

@@ -40,7 +40,8 @@ struct AttnArgs {
   __nv_bfloat16* out;                // [B, Lq, H*64]
   float* lse;                        // [B, H, Lq]
   const __nv_bfloat16 *o, *dout;     // backward: forward output and its gradient, [B, Lq, H*64]
-  __nv_bfloat16 *dq, *dk, *dv;       // [B, L, H*64]
+  __nv_bfloat16 *dq, *dk, *dv;       // rows of head-interleaved gradients, row strides below
+  int64_t dq_rs, dk_rs, dv_rs;       // elements; H*64 for separate [B, L, H*64] tensors, 3*H*64 for the thirds of a fused buffer
   int B, H, Lq, Lk, causal;
   float scale;
   uint64_t seed;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(AttnCfg<LP>::THREADS) attn_bwd_kernel(const At
   __syncthreads();
   tile_gemm<true, false, NW>(sS, C::SP, sX, C::PP, sdO, QP, LP, HD, LP);              // dV = Pd^T dO
   __syncthreads();
-  store_tile<C::THREADS>(a.dv + (int64_t)b * a.Lk * orow + h * HD, orow, sS, C::SP, a.Lk, 1.0f);
+  store_tile<C::THREADS>(a.dv + (int64_t)b * a.Lk * a.dv_rs + h * HD, a.dv_rs, sS, C::SP, a.Lk, 1.0f);
   __syncthreads();
   tile_gemm<false, true, NW>(sS, C::SP, sdO, QP, sV, QP, LP, LP, HD);                 // dP = dO V^T
   __syncthreads();
@@ -238,11 +239,11 @@ __global__ void __launch_bounds__(AttnCfg<LP>::THREADS) attn_bwd_kernel(const At
   __syncthreads();
   tile_gemm<false, false, NW>(sS, C::SP, sX, C::PP, sK, QP, LP, HD, LP);              // dQ = dS K
   __syncthreads();
-  store_tile<C::THREADS>(a.dq + (int64_t)b * a.Lq * orow + h * HD, orow, sS, C::SP, a.Lq, a.scale);
+  store_tile<C::THREADS>(a.dq + (int64_t)b * a.Lq * a.dq_rs + h * HD, a.dq_rs, sS, C::SP, a.Lq, a.scale);
   __syncthreads();
   tile_gemm<true, false, NW>(sS, C::SP, sX, C::PP, sQ, QP, LP, HD, LP);               // dK = dS^T Q
   __syncthreads();
-  store_tile<C::THREADS>(a.dk + (int64_t)b * a.Lk * orow + h * HD, orow, sS, C::SP, a.Lk, a.scale);
+  store_tile<C::THREADS>(a.dk + (int64_t)b * a.Lk * a.dk_rs + h * HD, a.dk_rs, sS, C::SP, a.Lk, a.scale);
 }
 
 // =====================================================================================================================
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(128) attn2_bwd_kernel(const AttnArgs a) {
 #pragma unroll
     for (int n = 0; n < 8; ++n) { dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f; }
     gemm_nn(dq, sa, uK, lane);                         // dQ = dS K
-    store_frag_rows(a.dq + (int64_t)b * a.Lq * orow + h * HD, orow, dq, row0, a.Lq, t, a.scale);
+    store_frag_rows(a.dq + (int64_t)b * a.Lq * a.dq_rs + h * HD, a.dq_rs, dq, row0, a.Lq, t, a.scale);
   }
   __syncthreads();
   // dV = Pd^T dO and dK = dS^T Q: warp w owns key rows 16w..16w+15, contraction over all 64 queries
@@ -519,8 +520,8 @@ __global__ void __launch_bounds__(128) attn2_bwd_kernel(const AttnArgs a) {
     for (int n = 0; n < 8; ++n) { dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f; dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f; }
     gemm_nn(dv, pa, udO, lane);                        // dV[key][dim] = sum_q Pd[q][key] dO[q][dim]
     gemm_nn(dk, sa, uQ, lane);                         // dK[key][dim] = sum_q dS[q][key] Q[q][dim]
-    store_frag_rows(a.dv + (int64_t)b * a.Lk * orow + h * HD, orow, dv, warp * 16 + g, a.Lk, t, 1.0f);
-    store_frag_rows(a.dk + (int64_t)b * a.Lk * orow + h * HD, orow, dk, warp * 16 + g, a.Lk, t, a.scale);
+    store_frag_rows(a.dv + (int64_t)b * a.Lk * a.dv_rs + h * HD, a.dv_rs, dv, warp * 16 + g, a.Lk, t, 1.0f);
+    store_frag_rows(a.dk + (int64_t)b * a.Lk * a.dk_rs + h * HD, a.dk_rs, dk, warp * 16 + g, a.Lk, t, a.scale);
   }
 }
 
@@ -569,14 +570,15 @@ int check_attn(const AttnArgs& a) {
 }  // namespace
 
 int attn_run(bool bwd, const void* q, const void* k, const void* v, int64_t q_rs, int64_t k_rs, int64_t v_rs, void* out, float* lse,
-             const void* o, const void* dout, void* dq, void* dk, void* dv, int B, int H, int Lq, int Lk, int causal, float p_drop,
-             uint64_t seed, const uint64_t* seed_dev, cudaStream_t st) {
+             const void* o, const void* dout, void* dq, void* dk, void* dv, int64_t dq_rs, int64_t dk_rs, int64_t dv_rs, int B, int H,
+             int Lq, int Lk, int causal, float p_drop, uint64_t seed, const uint64_t* seed_dev, cudaStream_t st) {
   AttnArgs a;
   a.q = static_cast<const __nv_bfloat16*>(q); a.k = static_cast<const __nv_bfloat16*>(k); a.v = static_cast<const __nv_bfloat16*>(v);
   a.q_rs = q_rs; a.k_rs = k_rs; a.v_rs = v_rs;
   a.out = static_cast<__nv_bfloat16*>(out); a.lse = lse;
   a.o = static_cast<const __nv_bfloat16*>(o); a.dout = static_cast<const __nv_bfloat16*>(dout);
   a.dq = static_cast<__nv_bfloat16*>(dq); a.dk = static_cast<__nv_bfloat16*>(dk); a.dv = static_cast<__nv_bfloat16*>(dv);
+  a.dq_rs = dq_rs; a.dk_rs = dk_rs; a.dv_rs = dv_rs;
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.causal = causal;
   a.scale = 0.125f;   // 1 / sqrt(64)
   a.seed = seed; a.seed_dev = seed_dev;
@@ -584,7 +586,8 @@ int attn_run(bool bwd, const void* q, const void* k, const void* v, int64_t q_rs
   a.inv_keep = a.thr16 ? 1.0f / (1.0f - (float)a.thr16 / 65536.0f) : 1.0f;
   VLPET_TRY(check_attn(a));
   if (!lse) return fail(VLPET_E_BADARG, "attn: lse missing");
-  if (bwd && (!o || !dout || !dq || !dk || !dv || !aligned16(o) || !aligned16(dout) || !aligned16(dq) || !aligned16(dk) || !aligned16(dv)))
+  if (bwd && (!o || !dout || !dq || !dk || !dv || !aligned16(o) || !aligned16(dout) || !aligned16(dq) || !aligned16(dk) || !aligned16(dv) ||
+              dq_rs < (int64_t)H * HD || dk_rs < (int64_t)H * HD || dv_rs < (int64_t)H * HD || (dq_rs | dk_rs | dv_rs) % 8 != 0))
     return fail(VLPET_E_BADARG, "attn_bwd: bad arguments");
   if (!bwd && (!out || !aligned16(out))) return fail(VLPET_E_BADARG, "attn_fwd: bad output");
   const int L = Lq > Lk ? Lq : Lk;

@@ -177,8 +177,8 @@ int layernorm_bwd(const void* x, const void* dy, const float* w, const float* me
                   float* db, int64_t M, int d, cudaStream_t st);
 // short-sequence attention, vlpet_attention.cu
 int attn_run(bool bwd, const void* q, const void* k, const void* v, int64_t q_rs, int64_t k_rs, int64_t v_rs, void* out, float* lse,
-             const void* o, const void* dout, void* dq, void* dk, void* dv, int B, int H, int Lq, int Lk, int causal, float p_drop,
-             uint64_t seed, const uint64_t* seed_dev, cudaStream_t st);
+             const void* o, const void* dout, void* dq, void* dk, void* dv, int64_t dq_rs, int64_t dk_rs, int64_t dv_rs, int B, int H,
+             int Lq, int Lk, int causal, float p_drop, uint64_t seed, const uint64_t* seed_dev, cudaStream_t st);
 int set_k1_trace(unsigned long long* dev_buf);   // developer hook, tools/trace_k1.py
 int set_k1_bwd_trace(unsigned long long* dev_buf);
 int set_k1_pairs(int mode);                       // developer hook: -1 auto, 0 single CTAs, 1 CTA pairs (cta_group::2)

@@ -633,9 +633,50 @@ class ShortAttentionFn(torch.autograd.Function):
         dv = torch.empty(B, Lk, H * 64, dtype=q.dtype, device=q.device)
         nb = 2 * (2 * q.numel() + 2 * k.numel() + 2 * v.numel() + 2 * out.numel())
         L.check(_call("attn_bwd", nb, L.lib.vlpet_attn_bwd, _p(q), _p(k), _p(v), q.stride(1), k.stride(1), v.stride(1), _p(out),
-                      _p(dout), _p(lse), _p(dq), _p(dk), _p(dv), B, H, Lq, Lk, causal, pd, seed,
+                      _p(dout), _p(lse), _p(dq), _p(dk), _p(dv), H * 64, H * 64, H * 64, B, H, Lq, Lk, causal, pd, seed,
                       C.c_void_p(sd) if sd else C.c_void_p(0), _stream()), "vlpet_attn_bwd")
         return dq, dk, dv, None, None, None, None
+
+
+class ShortSelfAttentionFn(torch.autograd.Function):
+    """Self-attention straight on the output of the one-GEMM q/k/v projection: qkv [B, L, 3, H*64] contiguous.  The
+    backward writes dq / dk / dv into the thirds of ONE [B, L, 3, H*64] gradient (no concatenation pass)."""
+
+    @staticmethod
+    def forward(ctx, qkv, H: int, causal: bool, p: float, seed: int):
+        _require_cuda(qkv)
+        B, Lq, _, d = qkv.shape
+        q, k, v = qkv.unbind(2)
+        out = torch.empty(B, Lq, d, dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty(B, H, Lq, dtype=torch.float32, device=qkv.device)
+        sd = _seed_dev.data_ptr() if (seed and _seed_dev is not None) else None
+        pd = float(p if seed else 0.0)
+        L.check(_call("attn_fwd", 2 * (qkv.numel() + out.numel()), L.lib.vlpet_attn_fwd, _p(q), _p(k), _p(v), 3 * d, 3 * d, 3 * d,
+                      _p(out), _p(lse), B, H, Lq, Lq, int(causal), pd, seed, C.c_void_p(sd) if sd else C.c_void_p(0), _stream()),
+                "vlpet_attn_fwd")
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.args = (H, int(causal), pd, seed, sd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        H, causal, pd, seed, sd = ctx.args
+        B, Lq, _, d = qkv.shape
+        q, k, v = qkv.unbind(2)
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        dq, dk, dv = dqkv.unbind(2)
+        L.check(_call("attn_bwd", 2 * (2 * qkv.numel() + 2 * out.numel()), L.lib.vlpet_attn_bwd, _p(q), _p(k), _p(v), 3 * d, 3 * d,
+                      3 * d, _p(out), _p(dout), _p(lse), _p(dq), _p(dk), _p(dv), 3 * d, 3 * d, 3 * d, B, H, Lq, Lq, causal, pd, seed,
+                      C.c_void_p(sd) if sd else C.c_void_p(0), _stream()), "vlpet_attn_bwd")
+        return dqkv, None, None, None, None
+
+
+def short_self_attention(qkv, H: int, causal: bool, p: float, training: bool) -> torch.Tensor:
+    """qkv [B, L, 3, H*64] (fused projection) -> [B, L, H*64]."""
+    seed = next_dropout_seed() if (training and p > 0.0) else 0
+    return ShortSelfAttentionFn.apply(qkv, H, causal, p, seed)
 
 
 def short_attention_supported(q, k, v, H: int) -> bool:

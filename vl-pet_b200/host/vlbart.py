@@ -110,7 +110,11 @@ class BartAttention(nn.Module):
         fused = self._fused_qkv() if key_value_states is None else None
         B, L, _ = hidden_states.shape
         if fused is not None:
-            q, k, v = F.linear(hidden_states, fused[0], fused[1]).view(B, L, 3, self.embed_dim).unbind(2)
+            qkv = F.linear(hidden_states, fused[0], fused[1]).view(B, L, 3, self.embed_dim)
+            if attn_mask is None and self.head_dim == 64 and SHORT_ATTENTION and L <= 64 and qkv.dtype == torch.bfloat16:
+                # fused projection -> attention -> out_proj: the backward writes dq | dk | dv into one buffer
+                return self.out_proj(F_.short_self_attention(qkv, self.num_heads, is_causal, self.dropout, self.training))
+            q, k, v = qkv.unbind(2)
         else:
             q = self.q_proj(hidden_states)
             k = self.k_proj(src)
