@@ -144,9 +144,9 @@ class VlpetError(RuntimeError):
 
 
 def _load():
-    path = os.environ.get("VLPET_LIB") or _build.LIB
-    if not os.path.exists(path):
-        path = _build.build()
+    # Always go through build(): it is a digest comparison when the library is current, and it rebuilds a stale one
+    # (the ctypes layouts below must match the loaded code).  VLPET_LIB loads a developer variant as is.
+    path = os.environ.get("VLPET_LIB") or _build.build()
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

@@ -21,6 +21,7 @@
 // 4..19 epilogue (warp%4 = TMEM lane quarter; cg = (warp-4)/4: adapter | gate branch and column half in epi 1/3, 16 of the
 // chunk's 64 columns in epi 2/4).  Epilogue arithmetic is on packed fp32 pairs (FFMA2); the pre-scaled fp32 bias tables
 // live in the unused 64-byte halves of the swizzled dp block (BCfg::OFF_TAB).
+#include <cstdlib>
 #include <type_traits>
 
 #include "sm100_ptx.cuh"
@@ -31,6 +32,12 @@ int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols
                   uint32_t box_cols, bool weight);
 namespace {
 
+// -DVLPET_B1_FAST: role loops under elect.sync (the fast issue path under investigation: profiles/r2_sanitizer_*)
+#ifdef VLPET_B1_FAST
+#define VLPET_B1_ISSUER ptx::elect_one()
+#else
+#define VLPET_B1_ISSUER (lane == 0)
+#endif
 constexpr int TILE_M = 128;
 constexpr int CH = 64;
 constexpr int SX = 2;
@@ -220,7 +227,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
 
   if (warp == 0) {
     // ===================================== TMA producer: activations =====================================
-    if (lane == 0) {
+    if (VLPET_B1_ISSUER) {
       uint32_t xi = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = (int)(tile * TILE_M);
@@ -253,7 +260,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     }
   } else if (warp == 3) {
     // ===================================== TMA producer: weights (always L2 hits) =====================================
-    if (lane == 0) {
+    if (VLPET_B1_ISSUER) {
       uint32_t wi = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int ph = 0; ph < 3; ++ph) {
@@ -289,7 +296,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {   // NOT elect_one(): with the fast issue path B1 faults sporadically, and gains nothing
+    if (VLPET_B1_ISSUER) {   // NOT elect_one() by default: with the fast issue path B1 faults sporadically
       constexpr uint32_t IDESC_AP = ptx::umma_idesc_bf16_m128(R);                       // A/P: N = R, K-major x K-major
       constexpr uint32_t IDESC_UT = ptx::umma_idesc_bf16_m128(CH);                      // U/T: N = 64
       constexpr uint32_t IDESC_DZ = ptx::umma_idesc_bf16_m128_major(R, 0u, 1u);         // dz/dq: B MN-major, N = R
@@ -413,7 +420,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     }
   } else if (warp == 2) {
     // ===================================== TMA store issuer =====================================
-    if (lane == 0) {
+    if (VLPET_B1_ISSUER) {
       uint32_t xi = 0, p2i = 0, p3i = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = (int)(tile * TILE_M);
@@ -659,8 +666,13 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         if (GATED) ptx::tmem_ld_32x32b_x16(tacc + 2 * CH, g1);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(bar(B_ACCEMPTY + b));
+        // The XFULL wait comes BEFORE the ACCEMPTY arrive: the MMA warp waits XFULL itself for the phase-1 entries of the
+        // next tile, and a parity wait is only meaningful once the previous phase of that barrier has completed.  With the
+        // arrive first, the MMA warp could reach the next tile while this chunk's dout load was still in flight, see
+        // "previous-previous phase complete" as "complete", consume a stale slot and release it a second time
+        // (profiles/r2_b1_fault_rootcause.md: the sporadic launch failure of round 1).
         ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
+        ptx::mbar_arrive(bar(B_ACCEMPTY + b));
         VLPET_TRACE_B(44 + 3 * c);
         const uint32_t dorow = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t o2row = dorow + XCH_BYTES;
@@ -826,8 +838,12 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   p.dbg = trap_buffer_dev();
   p.thr16 = D.p_drop > 0.f ? drop_thr16(D.p_drop) : 0u;
   p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
+  // developer hook (tools/run_sanitizers.sh): VLPET_DEBUG_BWD_PARTS bit 0 = run the tile kernel, bit 1 = column sums,
+  // bit 2 = weight-gradient GEMM (default: all)
+  static const int parts = []() { const char* e = getenv("VLPET_DEBUG_BWD_PARTS"); return e ? atoi(e) : 7; }();
   int rc = 0;
-  if (gated) {
+  if (!(parts & 1)) {
+  } else if (gated) {
     switch (R) {
       case 32: rc = launch<32, true>(D, m, p, sms, st); break;
       case 64: rc = launch<64, true>(D, m, p, sms, st); break;
@@ -843,8 +859,11 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
     }
   }
   if (rc) return rc;
-  VLPET_TRY(launch_colsum_scratch(s.das, s.pz, D.r, D.M, G.dbd, st));
-  if (gated) VLPET_TRY(launch_colsum_scratch(s.dps, s.pq, rg, D.M, G.dgbd, st));
+  if (parts & 2) {
+    VLPET_TRY(launch_colsum_scratch(s.das, s.pz, D.r, D.M, G.dbd, st));
+    if (gated) VLPET_TRY(launch_colsum_scratch(s.dps, s.pq, rg, D.M, G.dgbd, st));
+  }
+  if (!(parts & 4)) return 0;
   // ---- weight gradients: dWu = du^T z (+dbu), dGu = dt^T q (+dgbu), dWd = (x2^T da)^T, dGd = (x1^T dp)^T
   //      (ungated: du = alpha*dout, so A = dout with scale alpha)
   const void* A[4]; const void* B[4]; int64_t lda[4], ldb[4]; int nbv[4], tr[4]; float* out[4]; float* bias[4]; float sc[4];
