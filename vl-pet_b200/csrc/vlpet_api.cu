@@ -190,6 +190,7 @@ __attribute__((visibility("default"))) int vlpet_debug_set_k1_trace(void* dev_bu
 }
 // developer hook: force (1) / forbid (0) / auto-select (-1) the CTA-pair (cta_group::2) variant of the fused K1 forward
 __attribute__((visibility("default"))) int vlpet_debug_set_k1_pairs(int mode) { return vlpet::set_k1_pairs(mode); }
+__attribute__((visibility("default"))) int vlpet_debug_set_k1_bwd_parts(int parts) { return vlpet::set_k1_bwd_parts(parts); }
 __attribute__((visibility("default"))) int vlpet_debug_set_k1_bwd_trace(void* dev_buf) {
   return vlpet::set_k1_bwd_trace(static_cast<unsigned long long*>(dev_buf));
 }

@@ -181,6 +181,7 @@ int attn_run(bool bwd, const void* q, const void* k, const void* v, int64_t q_rs
              int Lq, int Lk, int causal, float p_drop, uint64_t seed, const uint64_t* seed_dev, cudaStream_t st);
 int set_k1_trace(unsigned long long* dev_buf);   // developer hook, tools/trace_k1.py
 int set_k1_bwd_trace(unsigned long long* dev_buf);
+int set_k1_bwd_parts(int parts);                 // developer hook: bit 0 tile kernel, bit 1 column sums, bit 2 weight-gradient GEMM
 int set_k1_pairs(int mode);                       // developer hook: -1 auto, 0 single CTAs, 1 CTA pairs (cta_group::2)
 // dense projection GEMM (tcgen05), vlpet_gemm_sm100.cu: C fp32 = A bf16 * W^T bf16 + bias
 bool gemm_sm100_supported(int64_t M, int N, int K, int64_t ldc);

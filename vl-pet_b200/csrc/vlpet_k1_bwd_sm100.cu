@@ -1,27 +1,34 @@
 // K1 backward, fused, sm_100a ("B1"): activation gradients of the granularity-controlled PET module, large gate, in ONE
 // launch; the four token-contracted weight-gradient GEMMs run right after it in vlpet_wgrad_sm100.cu ("B2") from the
-// small intermediates this kernel leaves behind.  Math: SURVEY Appendix A / oracle gated_pet_bwd
+// intermediates this kernel leaves behind.  Math: SURVEY Appendix A / oracle gated_pet_bwd
 // (my_transformers/modeling_bart.py:1145-1155, 1195-1209, 1256-1260 differentiated).
 //
 // Persistent CTAs, one per SM, each walks 128-token tiles.  Per tile (nothing is saved by the forward: everything is
 // recomputed from x1 / x2):
-//   phase 1  (K = d)        A = x2 Wd^T, P = x1 Gd^T                                  tcgen05, fp32 accum in TMEM (kept)
-//   epi 1                   z = gelu_new(A+bd), q = gelu_new(P+gbd)                  -> swizzled smem (bf16) + scratch
-//   phase 2  (64-col chunks) U_c = z Wu_c^T, T_c = q Gu_c^T                           tcgen05
+//   phase 1  (K = d)        A = x2 Wd^T, P = x1 Gd^T                                  tcgen05 SS, fp32 accum in TMEM
+//   epi 1                   z = gelu_new(A+bd), q = gelu_new(P+gbd)  -> packed bf16 IN PLACE over A / P in TMEM (the A operand
+//                           of every later MMA that contracts over r: tcgen05.mma TS form) + scratch for B2;
+//                           gelu_new'(.) -> 16-bit fixed point next to it (8 + 8 columns per 16 pre-activations)
+//   phase 2  (64-col chunks) U_c = z Wu_c^T, T_c = q Gu_c^T                           tcgen05 TS
 //   epi 2                   y1 = k x2 + a(U+bu), G = sig(T+gbu), dh = s m dout,
 //                           du = a dh G, dt = dh y1 G(1-G)   (add-gate: du = a dh, dt = dh G(1-G))
 //                                                                                     -> in place over x2_c / dout_c in smem
-//            MMA            dz += du_c Wu_c, dq += dt_c Gu_c   (B operands MN-major from the SAME smem tiles of Wu_c/Gu_c)
+//            MMA            dz += du_c Wu_c, dq += dt_c Gu_c   (SS; B operands MN-major from the SAME smem tiles of Wu_c/Gu_c)
 //            store          du_c, dt_c -> scratch (TMA store) for the weight-gradient GEMMs
-//   epi 3                   da = dz gelu_new'(A+bd), dp = dq gelu_new'(P+gbd)        -> smem (over z) + scratch; dbd, dgbd
+//   epi 3                   da = dz gelu_new'(A+bd), dp = dq gelu_new'(P+gbd)        -> packed bf16 over the gelu' slots in TMEM
+//                                                                                        + scratch
 //   phase 3  (64-col chunks) T_c again (only G is needed; recompute beats keeping [128 x 768] gates),
-//                           DX2_c = da Wd[:,c], DX1_c = dp Gd[:,c]                    tcgen05 (B MN-major from Wd_c/Gd_c tiles)
+//                           DX2_c = da Wd[:,c], DX1_c = dp Gd[:,c]                    tcgen05 TS (B MN-major from Wd_c/Gd_c tiles)
 //   epi 4                   dx2 = k dh G + DX2, dx1 = dout + DX1                      -> smem -> TMA store
+// Round-2 changes against the first version: z / q / da / dp never touch shared memory (80 KB and ~1.5 MB
+// of shared-memory port traffic per tile freed: the kernel is port-bound), which pays for 3-stage activation and weight
+// rings; role loops run under elect.sync (uniform-register issue path); and the barrier-phase hazard behind the sporadic
+// launch failure of round 1 is closed (see epilogue 4).
 // Warp roles: 0 TMA producer (activations), 3 TMA producer (weights), 1 MMA issuer (TMEM owner), 2 TMA-store issuer,
 // 4..19 epilogue (warp%4 = TMEM lane quarter; cg = (warp-4)/4: adapter | gate branch and column half in epi 1/3, 16 of the
-// chunk's 64 columns in epi 2/4).  Epilogue arithmetic is on packed fp32 pairs (FFMA2); the pre-scaled fp32 bias tables
-// live in the unused 64-byte halves of the swizzled dp block (BCfg::OFF_TAB).
+// chunk's 64 columns in epi 2/4).  Epilogue arithmetic is on packed fp32 pairs (FFMA2).
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "sm100_ptx.cuh"
@@ -32,21 +39,14 @@ int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols
                   uint32_t box_cols, bool weight);
 namespace {
 
-// -DVLPET_B1_FAST: role loops under elect.sync (the fast issue path under investigation: profiles/r2_sanitizer_*)
-#ifdef VLPET_B1_FAST
-#define VLPET_B1_ISSUER ptx::elect_one()
-#else
-#define VLPET_B1_ISSUER (lane == 0)
-#endif
 constexpr int TILE_M = 128;
 constexpr int CH = 64;
-constexpr int SX = 2;
-constexpr int SW = 2;
+constexpr int SX = 3;              // activation ring stages (2 x [128 x 64] bf16 each)
+constexpr int SW = 3;              // weight ring stages
 constexpr int XCH_BYTES = TILE_M * CH * 2;  // 16 KB
 constexpr int NUM_THREADS = 640;   // 4 role warps + 16 epilogue warps
 constexpr int EPI_THREADS = 512;
-constexpr int TM_A = 0, TM_P = 96, TM_DZ = 192, TM_DQ = 288, TM_UT = 384;  // phase 1-2 TMEM columns
-constexpr int TM_ACC = 128, ACC_STRIDE = 192;                              // phase 3: {T, DX2, DX1} x 2 buffers
+constexpr int SMEM_LIMIT = 232448;
 
 template <int R>
 struct BCfg {
@@ -58,25 +58,23 @@ struct BCfg {
   static constexpr int WSLOT = W3 > W12 ? W3 : W12;
   static constexpr int OFF_X = 0;
   static constexpr int OFF_W = OFF_X + SX * 2 * XCH_BYTES;
-  static constexpr int OFF_Z0 = OFF_W + SW * WSLOT;                      // z (later da), columns 0..63
-  static constexpr int OFF_Q0 = OFF_Z0 + XCH_BYTES;                      // q, columns 0..63
-  static constexpr int OFF_ZQ1 = OFF_Q0 + XCH_BYTES;                     // columns 64..95: z/da in bytes 0..63 of each row, q in 64..127
-  static constexpr int OFF_DP0 = OFF_ZQ1 + (KB == 2 ? XCH_BYTES : 0);
-  static constexpr int OFF_DP1 = OFF_DP0 + XCH_BYTES;
-  // fp32 tables alpha*bu[d] | 0.5*gbu[d] for epilogues 2 / 4, 16 columns (64 B) per entry.  With KB == 2 the dp block of
-  // columns 64..95 only occupies one 64-byte half of each 128-byte row (which half depends on the row's swizzle phase);
-  // entry gi lives in the OTHER half of row gi of that block -- shared memory is full otherwise.  KB == 1: own block.
-  static constexpr int OFF_TAB = OFF_DP1;
-  static constexpr int OFF_BAR = OFF_DP1 + XCH_BYTES;
-  static constexpr int MAX_D = 1024;                                             // 2 * d / 16 table entries <= 128 rows
-  static constexpr int SMEM_BYTES = OFF_BAR + 1024 + 2 * R * 4 + 256 + 1024;   // barriers | fp32 bd, gbd | slack + alignment
-  static_assert(R <= 96 && R % 16 == 0, "fused backward covers ranks up to 96");
+  static constexpr int OFF_BD = OFF_W + SW * WSLOT;          // fp32 bd[R] | gbd[R]
+  static constexpr int OFF_BAR = OFF_BD + 2 * R * 4;
+  static constexpr int OFF_TAB = OFF_BAR + 512;              // fp32 alpha*bu[d] | 0.5*gbu[d]
+  static constexpr int smem_bytes(int d) { return OFF_TAB + 2 * d * 4 + 1024; }   // + slack for the manual 1024-B alignment
+  // TMEM columns.  Phases 1-2: A | P (in place after epilogue 1: per 16 columns, 8 of packed z/q then 8 of gelu' fixed point,
+  // later packed da/dp) | dz | dq | U_c T_c.  Phase 3 reuses dz.. for {T_c, DX2_c, DX1_c}.
+  static constexpr int TM_A = 0, TM_P = R, TM_DZ = 2 * R, TM_DQ = 3 * R, TM_UT = 4 * R;
+  static constexpr int TM_T = 2 * R, TM_DX2 = 2 * R + CH, TM_DX1 = 2 * R + 2 * CH;
+  static_assert(R <= 96 && R % 32 == 0, "fused backward covers rank buckets 32 / 64 / 96");
+  static_assert(TM_UT + 2 * CH <= 512 && TM_DX1 + CH <= 512, "TMEM budget");
   static_assert(WSLOT % 1024 == 0 && WA_BYTES % 1024 == 0, "swizzle atoms must stay 1024-byte aligned");
 };
 
 // Optional phase-timestamp trace (tools/trace_k1.py --bwd): thread 128 of every CTA stamps %globaltimer at the phase
 // boundaries of its first tile into [cta][128] slots.
 static unsigned long long* g_trace_b = nullptr;   // host copy; travels to the kernel as BParams::trace
+static int g_bwd_parts = []() { const char* e = getenv("VLPET_DEBUG_BWD_PARTS"); return e ? atoi(e) : 7; }();
 __device__ __forceinline__ unsigned long long gtimer_b() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -84,7 +82,7 @@ __device__ __forceinline__ unsigned long long gtimer_b() {
 }
 #define VLPET_TRACE_B(slot)                                                                                               \
   do {                                                                                                                    \
-    if (p.trace && threadIdx.x == 128 && tile == blockIdx.x && (slot) < 128) p.trace[blockIdx.x * 128 + (slot)] = gtimer_b(); \
+    if (p.trace && threadIdx.x == 128 && ti == 0 && (slot) < 128) p.trace[blockIdx.x * 128 + (slot)] = gtimer_b();       \
   } while (0)
 
 struct BParams {
@@ -95,7 +93,6 @@ struct BParams {
   const __nv_bfloat16 *bd, *bu, *gbd, *gbu;
   __nv_bfloat16 *zs, *qs, *das, *dps;   // scratch [M, pz] / [M, pq]
   int pz, pq;                           // scratch row pitches (elements)
-  float *dbd, *dgbd;                    // fp32 bias gradients (accumulated into) or nullptr
   uint64_t seed;
   const uint64_t* seed_dev;
   uint32_t thr16;
@@ -106,14 +103,9 @@ struct BParams {
 
 enum { B_XFULL = 0, B_XEMPTY = B_XFULL + SX, B_WFULL = B_XEMPTY + SX, B_WEMPTY = B_WFULL + SW, B_APFULL = B_WEMPTY + SW,
        B_ZQFULL, B_UTFULL, B_UTEMPTY, B_DUDT, B_DZQDONE = B_DUDT + SX, B_DZFULL = B_DZQDONE + SX, B_DAPFULL,
-       B_ACCFULL, B_ACCEMPTY = B_ACCFULL + 2, B_OUTRDY = B_ACCEMPTY + 2, B_COUNT = B_OUTRDY + SX };
+       B_ACCFULL, B_ACCEMPTY, B_OUTRDY, B_COUNT = B_OUTRDY + SX };
+static_assert(8 * B_COUNT + 8 <= 512, "barriers + the TMEM address slot must fit the 512-byte barrier block");
 
-__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
 using namespace ptx;   // f2 helpers (packed fp32 pairs)
 // gelu_new(v) and gelu_new'(v) for a pair: 0.5 v (1 + th), th = tanh(c (v + 0.044715 v^3))
 __device__ __forceinline__ void gelu_new_both2(f2 v, f2& g, f2& dg) {
@@ -126,46 +118,28 @@ __device__ __forceinline__ void gelu_new_both2(f2 v, f2& g, f2& dg) {
   const f2 omt = fma2(mul2(th, mk2(-1.0f, -1.0f)), th, one);          // 1 - th^2
   dg = fma2(mul2(hv, omt), fma2(ck3, v2, c2), fma2(half, th, half));
 }
+// gelu_new' lies in [-0.13, 1.13]; it waits in TMEM between epilogues 1 and 3 as 16-bit fixed point, two per column:
+// u = round(40000 g + 10000), taken from the mantissa of (2^23 + u).  Step 2.5e-5 absolute -- a bf16 pair would cost
+// 2^-9 relative on every da / dp, on top of their own rounding.
+__device__ __forceinline__ uint32_t enc_fix2(f2 g) {
+  const f2 t = fma2(g, mk2(40000.0f, 40000.0f), mk2(8398608.0f, 8398608.0f));
+  uint32_t lo, hi;
+  un2u(t, lo, hi);
+  return __byte_perm(lo, hi, 0x5410);
+}
+__device__ __forceinline__ f2 dec_fix2(uint32_t v) {
+  const f2 f = mk2u(__byte_perm(v, 0x4B000000u, 0x7610), __byte_perm(v, 0x4B000000u, 0x7632));
+  return fma2(add2(f, mk2(-8388608.0f, -8388608.0f)), mk2(2.5e-5f, 2.5e-5f), mk2(-0.25f, -0.25f));
+}
 __device__ __forceinline__ void lds128(uint32_t addr, uint32_t (&v)[4]) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
 }
 __device__ __forceinline__ void sts128(uint32_t addr, const uint32_t (&v)[4]) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
-// Column sums over the 32 lanes of a warp: lane l enters with its row's 32 values, leaves with sum_rows column l in v[0].
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = hi ? v[i] : v[i + off];
-      const float keep = hi ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
 
 // GATED = false is the ungated form used for the decoder value parallel adapter (K2): out = x1 + alpha*(Up(gelu_new(Down x2)))
 // -> dx2 = (alpha * (dout Wu) * gelu_new'(A)) Wd, no gate branch, no U/T recompute, no du/dt scratch (du = alpha*dout).
-// Same over 16 columns: every lane enters with its row's 16 values; lanes l and l^16 end up with sum_rows column (l & 15).
-__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
-#pragma unroll
-  for (int off = 8; off >= 1; off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = hi ? v[i] : v[i + off];
-      const float keep = hi ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-
 template <int R, bool GATED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
@@ -177,6 +151,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   using C = BCfg<R>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + C::OFF_BAR;
   auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
   const uint32_t tmem_slot = bar_base + 8u * B_COUNT;
@@ -200,7 +175,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     ptx::mbar_init(bar(B_UTEMPTY), EPI_THREADS);
     ptx::mbar_init(bar(B_DZFULL), 1);
     ptx::mbar_init(bar(B_DAPFULL), EPI_THREADS);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(B_ACCFULL + i), 1); ptx::mbar_init(bar(B_ACCEMPTY + i), EPI_THREADS); }
+    ptx::mbar_init(bar(B_ACCFULL), 1);
+    ptx::mbar_init(bar(B_ACCEMPTY), EPI_THREADS);
     ptx::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_dout); }
@@ -211,23 +187,33 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     ptx::prefetch_tmap(&tm_dx1); ptx::prefetch_tmap(&tm_dx2); ptx::prefetch_tmap(&tm_du); ptx::prefetch_tmap(&tm_dt);
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  {  // biases -> fp32 in shared memory, pre-multiplied so that the epilogues fold them into FMAs they issue anyway
+    float* sbd = reinterpret_cast<float*>(smem_gen + C::OFF_BD);
+    for (int i = threadIdx.x; i < 2 * R; i += NUM_THREADS) {
+      const int br = i / R, j = i % R;
+      const int rr = br ? p.rg : p.r;
+      const __nv_bfloat16* src = br ? p.gbd : p.bd;
+      sbd[i] = (j < rr && (GATED || br == 0)) ? __bfloat162float(src[j]) : 0.f;
+    }
+    float* stab = reinterpret_cast<float*>(smem_gen + C::OFF_TAB);
+    if (GATED) {
+      for (int i = threadIdx.x; i < p.d; i += NUM_THREADS) {
+        stab[i] = p.alpha * __bfloat162float(p.bu[i]);
+        stab[p.d + i] = 0.5f * __bfloat162float(p.gbu[i]);
+      }
+    }
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // K-major A-operand descriptor start of the k-th 16-element K step of z/da (which=0), q (1), dp (2)
-  auto small_a = [&](int which, int ks) -> uint32_t {
-    const uint32_t b0 = smem_base + (which == 0 ? C::OFF_Z0 : (which == 1 ? C::OFF_Q0 : C::OFF_DP0));
-    if (ks < 4) return b0 + (uint32_t)ks * 32u;
-    const uint32_t b1 = smem_base + (which == 2 ? C::OFF_DP1 : C::OFF_ZQ1) + (which == 1 ? 64u : 0u);
-    return b1 + (uint32_t)(ks - 4) * 32u;
-  };
-
   if (warp == 0) {
     // ===================================== TMA producer: activations =====================================
-    if (VLPET_B1_ISSUER) {
+    // x1 / x2 are read again by the weight-gradient GEMM right after this kernel, dout again in phase 3: default L2 policy,
+    // except the last read of dout.
+    if (ptx::elect_one()) {
       uint32_t xi = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = (int)(tile * TILE_M);
@@ -250,7 +236,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
               }
             } else if (GATED) {
               ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), XCH_BYTES);
-              ptx::tma_load_2d(xdst, &tm_dout, c * CH, row0, bar(B_XFULL + sx));
+              ptx::tma_load_2d_hint(xdst, &tm_dout, c * CH, row0, bar(B_XFULL + sx), ptx::L2_EVICT_FIRST);
             } else {
               ptx::mbar_arrive(bar(B_XFULL + sx));   // the stage is only the staging buffer of dx2_c
             }
@@ -260,7 +246,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     }
   } else if (warp == 3) {
     // ===================================== TMA producer: weights (always L2 hits) =====================================
-    if (VLPET_B1_ISSUER) {
+    if (ptx::elect_one()) {
       uint32_t wi = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int ph = 0; ph < 3; ++ph) {
@@ -296,21 +282,17 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (VLPET_B1_ISSUER) {   // NOT elect_one() by default: with the fast issue path B1 faults sporadically
+    if (ptx::elect_one()) {
       constexpr uint32_t IDESC_AP = ptx::umma_idesc_bf16_m128(R);                       // A/P: N = R, K-major x K-major
       constexpr uint32_t IDESC_UT = ptx::umma_idesc_bf16_m128(CH);                      // U/T: N = 64
       constexpr uint32_t IDESC_DZ = ptx::umma_idesc_bf16_m128_major(R, 0u, 1u);         // dz/dq: B MN-major, N = R
       constexpr uint32_t IDESC_DX = ptx::umma_idesc_bf16_m128_major(CH, 0u, 1u);        // DX: B MN-major, N = 64
       uint32_t xi = 0, wi = 0, ui = 0, p2i = 0, ai = 0, ti = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
-        // the phase-3 accumulators of the previous tile overlap P / DZ / DQ / UT: wait until the epilogue drained them
-        if (ai > 0) {
-          for (uint32_t b = 0; b < 2; ++b) {
-            const uint32_t nb = (ai + 1 - b) >> 1;
-            if (nb > 0) ptx::mbar_wait_dbg(bar(B_ACCEMPTY + b), (nb - 1) & 1, p.dbg, __LINE__);
-          }
-          ptx::tc_fence_after();
-        }
+        // Ordering, not a TMEM hazard: the phase-3 XFULL phases of the previous tile were observed by the EPILOGUE only, and
+        // it arrives on ACCEMPTY after having seen them.  A parity wait on XFULL below is meaningful only once the previous
+        // phase of that barrier has completed (see epilogue 4).
+        if (ai > 0) ptx::mbar_wait_dbg(bar(B_ACCEMPTY), (ai - 1) & 1, p.dbg, __LINE__);
         // ---- phase 1
         for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
           const uint32_t sx = xi % SX, sw = wi % SW;
@@ -322,10 +304,10 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
 #pragma unroll
           for (int ks = 0; ks < CH / 16; ++ks) {
             const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
-            ptx::umma_bf16_ss(tmem_base + TM_A, ptx::umma_desc_kmajor_sw128(x2s + ks * 32),
+            ptx::umma_bf16_ss(tmem_base + C::TM_A, ptx::umma_desc_kmajor_sw128(x2s + ks * 32),
                               ptx::umma_desc_kmajor_sw128(wds + ks * 32), IDESC_AP, acc);
             if (GATED)
-              ptx::umma_bf16_ss(tmem_base + TM_P, ptx::umma_desc_kmajor_sw128(x1s + ks * 32),
+              ptx::umma_bf16_ss(tmem_base + C::TM_P, ptx::umma_desc_kmajor_sw128(x1s + ks * 32),
                                 ptx::umma_desc_kmajor_sw128(gds + ks * 32), IDESC_AP, acc);
           }
           ptx::umma_commit(bar(B_XEMPTY + sx));
@@ -334,6 +316,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         ptx::umma_commit(bar(B_APFULL));
         // ---- phase 2
         if (!GATED) {
+          // dz += dout_c Wu_c straight from the ring.  The accumulator columns are free: epilogue 3 of the previous tile
+          // (their last reader) precedes every phase-3 accumulator hand-over this thread has already waited for.
           for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
             const uint32_t sx = xi % SX, sw = wi % SW;
             ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
@@ -343,84 +327,82 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT;
 #pragma unroll
             for (int ks = 0; ks < CH / 16; ++ks)
-              ptx::umma_bf16_ss(tmem_base + TM_DZ, ptx::umma_desc_kmajor_sw128(dos + ks * 32),
+              ptx::umma_bf16_ss(tmem_base + C::TM_DZ, ptx::umma_desc_kmajor_sw128(dos + ks * 32),
                                 ptx::umma_desc_mnmajor_sw128(wus + ks * 2048, CH * CH * 2), IDESC_DZ, (c > 0 || ks > 0) ? 1u : 0u);
             ptx::umma_commit(bar(B_XEMPTY + sx));
             ptx::umma_commit(bar(B_WEMPTY + sw));
           }
           ptx::umma_commit(bar(B_DZFULL));
-        }
-        if (GATED) {
-        ptx::mbar_wait_dbg(bar(B_ZQFULL), ti & 1, p.dbg, __LINE__);
-        ptx::tc_fence_after();
-        const uint32_t xi2 = xi, wi2 = wi, p2i0 = p2i;
-        auto issue_dzdq = [&](int cc) {
-          const uint32_t sx = (xi2 + cc) % SX, sw = (wi2 + cc) % SW, k = (p2i0 + cc) % SX;
-          ptx::mbar_wait_dbg(bar(B_DUDT + k), ((p2i0 + cc) / SX) & 1, p.dbg, __LINE__);
+        } else {
+          ptx::mbar_wait_dbg(bar(B_ZQFULL), ti & 1, p.dbg, __LINE__);
           ptx::tc_fence_after();
-          const uint32_t dus = smem_base + C::OFF_X + sx * (2 * XCH_BYTES), dts = dus + XCH_BYTES;
-          const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT, gus = wus + C::WB_BYTES;
+          const uint32_t xi2 = xi, wi2 = wi, p2i0 = p2i;
+          auto issue_dzdq = [&](int cc) {
+            const uint32_t sx = (xi2 + cc) % SX, sw = (wi2 + cc) % SW, k = (p2i0 + cc) % SX;
+            ptx::mbar_wait_dbg(bar(B_DUDT + k), ((p2i0 + cc) / SX) & 1, p.dbg, __LINE__);
+            ptx::tc_fence_after();
+            const uint32_t dus = smem_base + C::OFF_X + sx * (2 * XCH_BYTES), dts = dus + XCH_BYTES;
+            const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT, gus = wus + C::WB_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < CH / 16; ++ks) {
-            const uint32_t acc = (cc > 0 || ks > 0) ? 1u : 0u;
-            ptx::umma_bf16_ss(tmem_base + TM_DZ, ptx::umma_desc_kmajor_sw128(dus + ks * 32),
-                              ptx::umma_desc_mnmajor_sw128(wus + ks * 2048, CH * CH * 2), IDESC_DZ, acc);
-            ptx::umma_bf16_ss(tmem_base + TM_DQ, ptx::umma_desc_kmajor_sw128(dts + ks * 32),
-                              ptx::umma_desc_mnmajor_sw128(gus + ks * 2048, CH * CH * 2), IDESC_DZ, acc);
-          }
-          ptx::umma_commit(bar(B_DZQDONE + k));
-          ptx::umma_commit(bar(B_WEMPTY + sw));
-        };
-        for (int c = 0; c < nkc; ++c, ++xi, ++wi, ++ui, ++p2i) {
-          const uint32_t sw = wi % SW;
-          ptx::mbar_wait_dbg(bar(B_WFULL + sw), (wi / SW) & 1, p.dbg, __LINE__);
-          ptx::mbar_wait_dbg(bar(B_UTEMPTY), (ui & 1) ^ 1, p.dbg, __LINE__);
-          ptx::tc_fence_after();
-          const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT, gus = wus + C::WB_BYTES;
+            for (int ks = 0; ks < CH / 16; ++ks) {
+              const uint32_t acc = (cc > 0 || ks > 0) ? 1u : 0u;
+              ptx::umma_bf16_ss(tmem_base + C::TM_DZ, ptx::umma_desc_kmajor_sw128(dus + ks * 32),
+                                ptx::umma_desc_mnmajor_sw128(wus + ks * 2048, CH * CH * 2), IDESC_DZ, acc);
+              ptx::umma_bf16_ss(tmem_base + C::TM_DQ, ptx::umma_desc_kmajor_sw128(dts + ks * 32),
+                                ptx::umma_desc_mnmajor_sw128(gus + ks * 2048, CH * CH * 2), IDESC_DZ, acc);
+            }
+            ptx::umma_commit(bar(B_DZQDONE + k));
+            ptx::umma_commit(bar(B_WEMPTY + sw));
+          };
+          for (int c = 0; c < nkc; ++c, ++xi, ++wi, ++ui, ++p2i) {
+            const uint32_t sw = wi % SW;
+            ptx::mbar_wait_dbg(bar(B_WFULL + sw), (wi / SW) & 1, p.dbg, __LINE__);
+            ptx::mbar_wait_dbg(bar(B_UTEMPTY), (ui & 1) ^ 1, p.dbg, __LINE__);
+            ptx::tc_fence_after();
+            const uint32_t wus = smem_base + C::OFF_W + sw * C::WSLOT, gus = wus + C::WB_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < R / 16; ++ks) {
-            const uint32_t kb = ks / 4, kin = ks % 4;
-            ptx::umma_bf16_ss(tmem_base + TM_UT, ptx::umma_desc_kmajor_sw128(small_a(0, ks)),
-                              ptx::umma_desc_kmajor_sw128(wus + kb * (CH * CH * 2) + kin * 32), IDESC_UT, ks > 0);
-            ptx::umma_bf16_ss(tmem_base + TM_UT + CH, ptx::umma_desc_kmajor_sw128(small_a(1, ks)),
-                              ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_UT, ks > 0);
+            for (int ks = 0; ks < R / 16; ++ks) {   // z / q: A operand from TMEM, 8 packed columns per K step at stride 16
+              const uint32_t kb = ks / 4, kin = ks % 4;
+              ptx::umma_bf16_ts(tmem_base + C::TM_UT, tmem_base + C::TM_A + 16 * ks,
+                                ptx::umma_desc_kmajor_sw128(wus + kb * (CH * CH * 2) + kin * 32), IDESC_UT, ks > 0);
+              ptx::umma_bf16_ts(tmem_base + C::TM_UT + CH, tmem_base + C::TM_P + 16 * ks,
+                                ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_UT, ks > 0);
+            }
+            ptx::umma_commit(bar(B_UTFULL));
+            if (c > 0) issue_dzdq(c - 1);
           }
-          ptx::umma_commit(bar(B_UTFULL));
-          if (c > 0) issue_dzdq(c - 1);
-        }
-        issue_dzdq(nkc - 1);
-        ptx::umma_commit(bar(B_DZFULL));
+          issue_dzdq(nkc - 1);
+          ptx::umma_commit(bar(B_DZFULL));
         }
         // ---- phase 3
         ptx::mbar_wait_dbg(bar(B_DAPFULL), ti & 1, p.dbg, __LINE__);
         ptx::tc_fence_after();
         for (int c = 0; c < nkc; ++c, ++xi, ++wi, ++ai) {
-          const uint32_t sw = wi % SW, b = ai & 1;
+          const uint32_t sw = wi % SW;
           ptx::mbar_wait_dbg(bar(B_WFULL + sw), (wi / SW) & 1, p.dbg, __LINE__);
-          ptx::mbar_wait_dbg(bar(B_ACCEMPTY + b), ((ai >> 1) & 1) ^ 1, p.dbg, __LINE__);
+          ptx::mbar_wait_dbg(bar(B_ACCEMPTY), (ai & 1) ^ 1, p.dbg, __LINE__);
           ptx::tc_fence_after();
           const uint32_t gus = smem_base + C::OFF_W + sw * C::WSLOT, wds = gus + C::WB_BYTES, gds = wds + C::WA_BYTES;
-          const uint32_t tacc = tmem_base + TM_ACC + b * ACC_STRIDE;
 #pragma unroll
           for (int ks = 0; ks < R / 16; ++ks) {
             const uint32_t kb = ks / 4, kin = ks % 4;
             if (GATED && mulgate)
-              ptx::umma_bf16_ss(tacc, ptx::umma_desc_kmajor_sw128(small_a(1, ks)),
+              ptx::umma_bf16_ts(tmem_base + C::TM_T, tmem_base + C::TM_P + 16 * ks,
                                 ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_UT, ks > 0);
-            ptx::umma_bf16_ss(tacc + CH, ptx::umma_desc_kmajor_sw128(small_a(0, ks)),
+            ptx::umma_bf16_ts(tmem_base + C::TM_DX2, tmem_base + C::TM_A + 16 * ks + 8,
                               ptx::umma_desc_mnmajor_sw128(wds + ks * 2048, C::WA_BYTES), IDESC_DX, ks > 0);
             if (GATED)
-              ptx::umma_bf16_ss(tacc + 2 * CH, ptx::umma_desc_kmajor_sw128(small_a(2, ks)),
+              ptx::umma_bf16_ts(tmem_base + C::TM_DX1, tmem_base + C::TM_P + 16 * ks + 8,
                                 ptx::umma_desc_mnmajor_sw128(gds + ks * 2048, C::WA_BYTES), IDESC_DX, ks > 0);
           }
           ptx::umma_commit(bar(B_WEMPTY + sw));
-          ptx::umma_commit(bar(B_ACCFULL + b));
+          ptx::umma_commit(bar(B_ACCFULL));
         }
       }
     }
   } else if (warp == 2) {
     // ===================================== TMA store issuer =====================================
-    if (VLPET_B1_ISSUER) {
+    if (ptx::elect_one()) {
       uint32_t xi = 0, p2i = 0, p3i = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = (int)(tile * TILE_M);
@@ -463,76 +445,46 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
     constexpr int HALF = R / 2;                // columns per warp in epilogues 1 / 3 (a multiple of 16)
     const int jbeg = (cg & 1) * HALF;
-    // fp32 copies of the down-projection biases in shared memory (broadcast reads instead of scalar global loads)
-    const uint32_t sb_base = bar_base + 1024;   // [2][R] floats behind the barrier block
-    for (int i = threadIdx.x - 128; i < 2 * R; i += EPI_THREADS) {
-      const int br = i / R, j = i % R;
-      const int rr = br ? p.rg : p.r;
-      const __nv_bfloat16* src = br ? p.gbd : p.bd;
-      const float v = (j < rr && (GATED || br == 0)) ? __bfloat162float(src[j]) : 0.f;
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_base + 4u * (uint32_t)i), "f"(v) : "memory");
-    }
-    // alpha*bu and 0.5*gbu, 16 columns per 64-byte entry (layout: BCfg::OFF_TAB)
-    auto tab_addr = [&](int gi) -> uint32_t { return smem_base + C::OFF_TAB + (uint32_t)gi * 128u + ((gi & 4) ? 0u : 64u); };
-    const int ngrp = p.d / 16;
-    if (GATED) {
-      for (int i = threadIdx.x - 128; i < 2 * p.d; i += EPI_THREADS) {
-        const int col = i < p.d ? i : i - p.d;
-        const float v = i < p.d ? p.alpha * __bfloat162float(p.bu[col]) : 0.5f * __bfloat162float(p.gbu[col]);
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tab_addr(i >> 4) + 4u * (uint32_t)(i & 15)), "f"(v) : "memory");
-      }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // epilogue warps only
+    const uint32_t sb_base = smem_base + C::OFF_BD;     // fp32 [2][R]
+    const uint32_t tab_base = smem_base + C::OFF_TAB;   // fp32 alpha*bu[d] | 0.5*gbu[d]
     const f2 half2 = mk2(0.5f, 0.5f), kappa2 = mk2(p.kappa, p.kappa), alpha2 = mk2(p.alpha, p.alpha);
     const f2 s2 = mk2(p.s, p.s);
     const float s_keep = p.s * p.inv_keep;
-    // smem address of the 16-byte group holding columns [k, k+8) of this thread's row in z/da (which=0), q (1), dp (2)
-    auto small_addr = [&](int which, int k) -> uint32_t {
-      if (k < 64) {
-        const uint32_t b0 = smem_base + (which == 0 ? C::OFF_Z0 : (which == 1 ? C::OFF_Q0 : C::OFF_DP0));
-        return b0 + (uint32_t)row * 128u + ((((uint32_t)k >> 3) ^ swz) << 4);
-      }
-      const uint32_t b1 = smem_base + (which == 2 ? C::OFF_DP1 : C::OFF_ZQ1);
-      const uint32_t c16 = (((uint32_t)k - 64u) >> 3) + (which == 1 ? 4u : 0u);
-      return b1 + (uint32_t)row * 128u + ((c16 ^ swz) << 4);
-    };
-    uint32_t xi = 0, ui = 0, p2i = 0, ai = 0, ti = 0;
+    uint32_t xi = 0, ui = 0, p2i = 0, p3i = 0, ai = 0, ti = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
       const int64_t grow = tile * TILE_M + row;
       const bool row_ok = grow < p.M;
-      // ---- epilogue 1 (APFULL also implies that every MMA of the previous tile, which read z/q/da/dp, has completed)
+      // ---- epilogue 1 (APFULL also implies that every MMA of the previous tile, which read q / da / dp, has completed)
       VLPET_TRACE_B(0);
       ptx::mbar_wait_dbg(bar(B_APFULL), ti & 1, p.dbg, __LINE__);
       VLPET_TRACE_B(1);
       ptx::tc_fence_after();
       if (GATED || branch == 0) {
-        const uint32_t tsrc = lane_addr + (branch ? TM_P : TM_A);
+        const uint32_t tsrc = lane_addr + (branch ? C::TM_P : C::TM_A);
         const int rr = branch ? p.rg : p.r;
         __nv_bfloat16* srow = (branch ? p.qs + grow * p.pq : p.zs + grow * p.pz);
 #pragma unroll
         for (int jj = 0; jj < HALF; jj += 16) {
           const int j0 = jbeg + jj;
-          uint32_t v[16], dgv[16];
+          uint32_t v[16], o[16];
           ptx::tmem_ld_32x32b_x16(tsrc + j0, v);
           f2 bias[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) lds_f2x2(sb_base + 4u * (uint32_t)(branch * R + j0 + e * 4), bias[2 * e], bias[2 * e + 1]);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              f2 z2, d2;
-              gelu_new_both2(add2(mk2u(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]), bias[g * 4 + e]), z2, d2);
-              o[e] = pack2(z2);
-              un2u(d2, dgv[g * 8 + e * 2], dgv[g * 8 + e * 2 + 1]);
-            }
-            const int k = j0 + g * 8;
-            sts128(small_addr(branch, k), o);
-            if (row_ok && k < rr) *reinterpret_cast<uint4*>(srow + k) = make_uint4(o[0], o[1], o[2], o[3]);
+          for (int e = 0; e < 8; ++e) {
+            f2 z2, d2;
+            gelu_new_both2(add2(mk2u(v[e * 2], v[e * 2 + 1]), bias[e]), z2, d2);
+            o[e] = pack2(z2);
+            o[8 + e] = enc_fix2(d2);
           }
-          ptx::tmem_st_32x32b_x16(tsrc + j0, dgv);   // gelu_new'(pre-activation) replaces the pre-activation in TMEM: epilogue 3 only multiplies
+          // in place: columns j0 .. j0+7 <- packed z (K step j0/16 of the TS-form A operand), j0+8 .. j0+15 <- gelu'
+          ptx::tmem_st_32x32b_x16(tsrc + j0, o);
+          if (row_ok) {
+            if (j0 < rr) *reinterpret_cast<uint4*>(srow + j0) = make_uint4(o[0], o[1], o[2], o[3]);
+            if (j0 + 8 < rr) *reinterpret_cast<uint4*>(srow + j0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
         }
         ptx::tmem_st_wait();
         if (row_ok && (cg & 1) == 1) {  // ones column (bias-gradient trick of the weight-gradient GEMM) + zero pad up to the pitch
@@ -540,7 +492,6 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           *reinterpret_cast<uint4*>(srow + rr) = one;
         }
       }
-      ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(B_ZQFULL));
       VLPET_TRACE_B(2);
@@ -553,8 +504,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         VLPET_TRACE_B(3 + 3 * c);
         ptx::tc_fence_after();
         uint32_t u[16], t[16];
-        ptx::tmem_ld_32x32b_x16(lane_addr + TM_UT + cg * 16, u);
-        ptx::tmem_ld_32x32b_x16(lane_addr + TM_UT + CH + cg * 16, t);
+        ptx::tmem_ld_32x32b_x16(lane_addr + C::TM_UT + cg * 16, u);
+        ptx::tmem_ld_32x32b_x16(lane_addr + C::TM_UT + CH + cg * 16, t);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_UTEMPTY));
@@ -564,7 +515,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         const uint32_t dorow = x2row + XCH_BYTES;
         const int col0 = c * CH + cg * 16;
         const int64_t idx0 = grow * p.d + col0;
-        const uint32_t tabu = tab_addr(c * 4 + cg), thgb = tab_addr(ngrp + c * 4 + cg);
+        const uint32_t tabu = tab_base + 4u * (uint32_t)col0, thgb = tabu + 4u * (uint32_t)p.d;
         auto group2 = [&](auto drop_tag, int g) {
           constexpr bool DROP = decltype(drop_tag)::value;
           const uint32_t off = (((uint32_t)(cg * 2 + g)) ^ swz) << 4;
@@ -621,64 +572,57 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       VLPET_TRACE_B(41);
       ptx::tc_fence_after();
       if (GATED || branch == 0) {
-        const float dzscale = GATED ? 1.0f : p.alpha;   // ungated: du = alpha*dout was fed unscaled
-        const uint32_t tpre = lane_addr + (branch ? TM_P : TM_A);
-        const uint32_t tdz = lane_addr + (branch ? TM_DQ : TM_DZ);
+        const f2 dzs2 = GATED ? mk2(1.0f, 1.0f) : alpha2;   // ungated: du = alpha*dout was fed unscaled
+        const uint32_t tpre = lane_addr + (branch ? C::TM_P : C::TM_A);
+        const uint32_t tdz = lane_addr + (branch ? C::TM_DQ : C::TM_DZ);
         const int rr = branch ? p.rg : p.r;
         __nv_bfloat16* srow = (branch ? p.dps + grow * p.pq : p.das + grow * p.pz);
 #pragma unroll
         for (int jj = 0; jj < HALF; jj += 16) {
           const int j0 = jbeg + jj;
-          uint32_t a[16], dz[16];
-          ptx::tmem_ld_32x32b_x16(tpre + j0, a);     // gelu_new'(A + bd), stored by epilogue 1
+          uint32_t gq[8], dz[16], o[8];
+          ptx::tmem_ld_32x32b_x8(tpre + j0 + 8, gq);   // gelu_new'(pre-activation), stored by epilogue 1
           ptx::tmem_ld_32x32b_x16(tdz + j0, dz);
           ptx::tmem_ld_wait();
-          const f2 dzs2 = mk2(dzscale, dzscale);
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = g * 8 + e * 2;
-              const f2 da = mul2(mk2u(dz[j], dz[j + 1]), mk2u(a[j], a[j + 1]));
-              o[e] = pack2(GATED ? da : mul2(dzs2, da));
-            }
-            const int k = j0 + g * 8;
-            sts128(small_addr(branch ? 2 : 0, k), o);
-            if (row_ok && k < rr) *reinterpret_cast<uint4*>(srow + k) = make_uint4(o[0], o[1], o[2], o[3]);
+          for (int e = 0; e < 8; ++e)
+            o[e] = pack2(mul2(mul2(mk2u(dz[2 * e], dz[2 * e + 1]), dec_fix2(gq[e])), dzs2));
+          ptx::tmem_st_32x32b_x8(tpre + j0 + 8, o);     // packed da / dp: K step j0/16 of the phase-3 A operands
+          if (row_ok) {
+            if (j0 < rr) *reinterpret_cast<uint4*>(srow + j0) = make_uint4(o[0], o[1], o[2], o[3]);
+            if (j0 + 8 < rr) *reinterpret_cast<uint4*>(srow + j0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
           }
         }
+        ptx::tmem_st_wait();
       }
-      ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(B_DAPFULL));
       VLPET_TRACE_B(42);
       // ---- epilogue 4, per 64-column chunk: dx1, dx2
-      for (int c = 0; c < nkc; ++c, ++xi, ++ai) {
-        const uint32_t sx = xi % SX, b = ai & 1;
-        ptx::mbar_wait_dbg(bar(B_ACCFULL + b), (ai >> 1) & 1, p.dbg, __LINE__);
+      for (int c = 0; c < nkc; ++c, ++xi, ++ai, ++p3i) {
+        const uint32_t sx = xi % SX;
+        ptx::mbar_wait_dbg(bar(B_ACCFULL), ai & 1, p.dbg, __LINE__);
         VLPET_TRACE_B(43 + 3 * c);
         ptx::tc_fence_after();
-        const uint32_t tacc = lane_addr + TM_ACC + b * ACC_STRIDE + cg * 16;
         uint32_t t[16], g2[16], g1[16];
-        if (GATED && mulgate) ptx::tmem_ld_32x32b_x16(tacc, t);
-        ptx::tmem_ld_32x32b_x16(tacc + CH, g2);
-        if (GATED) ptx::tmem_ld_32x32b_x16(tacc + 2 * CH, g1);
+        if (GATED && mulgate) ptx::tmem_ld_32x32b_x16(lane_addr + C::TM_T + cg * 16, t);
+        ptx::tmem_ld_32x32b_x16(lane_addr + C::TM_DX2 + cg * 16, g2);
+        if (GATED) ptx::tmem_ld_32x32b_x16(lane_addr + C::TM_DX1 + cg * 16, g1);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-        // The XFULL wait comes BEFORE the ACCEMPTY arrive: the MMA warp waits XFULL itself for the phase-1 entries of the
+        // The XFULL wait comes BEFORE the ACCEMPTY arrive.  The MMA warp waits XFULL itself for the phase-1 entries of the
         // next tile, and a parity wait is only meaningful once the previous phase of that barrier has completed.  With the
-        // arrive first, the MMA warp could reach the next tile while this chunk's dout load was still in flight, see
-        // "previous-previous phase complete" as "complete", consume a stale slot and release it a second time
-        // (profiles/r2_b1_fault_rootcause.md: the sporadic launch failure of round 1).
+        // arrive first (round 1), the MMA warp could reach the next tile while this chunk's dout load was still in flight,
+        // take "the phase before the previous one is complete" for "complete", consume a stale slot and release it a second
+        // time: the sporadic launch failure of round 1 (profiles/r2_b1_fault_rootcause.md).
         ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
-        ptx::mbar_arrive(bar(B_ACCEMPTY + b));
+        ptx::mbar_arrive(bar(B_ACCEMPTY));
         VLPET_TRACE_B(44 + 3 * c);
         const uint32_t dorow = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t o2row = dorow + XCH_BYTES;
         const int col0 = c * CH + cg * 16;
         const int64_t idx0 = grow * p.d + col0;
-        const uint32_t thgb = tab_addr(ngrp + c * 4 + cg);
+        const uint32_t thgb = tab_base + 4u * (uint32_t)(p.d + col0);
         auto group4 = [&](auto drop_tag, int g) {
           constexpr bool DROP = decltype(drop_tag)::value;
           const uint32_t off = (((uint32_t)(cg * 2 + g)) ^ swz) << 4;
@@ -723,7 +667,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         if (p.thr16) { group4(std::true_type{}, 0); group4(std::true_type{}, 1); }
         else { group4(std::false_type{}, 0); group4(std::false_type{}, 1); }
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(bar(B_OUTRDY + (ai % SX)));
+        ptx::mbar_arrive(bar(B_OUTRDY + (p3i % SX)));
         VLPET_TRACE_B(45 + 3 * c);
       }
     }
@@ -737,25 +681,60 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   }
 }
 
-// dbd / dgbd = column sums of the da / dp scratch ([M, pitch] bf16, first ncols columns).  Kept out of the tile kernel: a
-// warp-shuffle transpose-reduce there cost ~5 us per tile on its critical path (tools/trace_k1_bwd.py).
-__global__ void __launch_bounds__(128) colsum_scratch_kernel(const __nv_bfloat16* __restrict__ A, int pitch, int ncols,
-                                                             int64_t M, int rows_per_block, float* __restrict__ out) {
-  const int c = threadIdx.x;
-  if (c >= ncols) return;
-  const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
-  int64_t m1 = m0 + rows_per_block;
-  if (m1 > M) m1 = M;
-  float acc = 0.f;
-  for (int64_t m = m0; m < m1; ++m) acc += __bfloat162float(A[m * pitch + c]);
-  atomicAdd(out + c, acc);
+// dbd / dgbd = column sums of the da / dp scratch ([M, pitch] bf16, first ncols columns), both in ONE launch.  Kept out of
+// the tile kernel: a warp-shuffle transpose-reduce there cost ~5 us per tile on its critical path (tools/trace_k1_bwd.py).
+// The scratch is read as a flat stream of 16-byte groups: a thread keeps its group-of-8-columns (pitch/8 groups per row
+// divide the thread stride), so every load is a coalesced uint4 and the reduction over rows happens in registers.
+struct ColsumArgs {
+  const __nv_bfloat16* A[2];
+  float* out[2];
+  int pitch[2], ncols[2];
+  int64_t M;
+};
+constexpr int CS_THREADS = 256;
+__global__ void __launch_bounds__(CS_THREADS) colsum_scratch_kernel(const ColsumArgs a) {
+  const int w = blockIdx.y;
+  const __nv_bfloat16* A = a.A[w];
+  float* out = a.out[w];
+  if (!A || !out) return;
+  const int gpr = a.pitch[w] / 8;                   // 16-byte groups per row
+  const int rows_per_pass = CS_THREADS / gpr;       // rows one pass of the block covers
+  const int t = threadIdx.x;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  __shared__ float red[256];                        // [column] partial sums (pitch <= 256)
+  for (int i = t; i < 256; i += CS_THREADS) red[i] = 0.f;
+  __syncthreads();
+  if (t < rows_per_pass * gpr) {
+    const int g = t % gpr, r0 = t / gpr;
+    const uint4* base = reinterpret_cast<const uint4*>(A);
+    for (int64_t row = (int64_t)blockIdx.x * rows_per_pass + r0; row < a.M; row += (int64_t)gridDim.x * rows_per_pass) {
+      const uint4 v = __ldg(base + row * gpr + g);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[2 * e] += __uint_as_float(u[e] << 16);
+        acc[2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (g * 8 + e < a.ncols[w]) atomicAdd(&red[g * 8 + e], acc[e]);
+  }
+  __syncthreads();
+  for (int c = t; c < a.ncols[w]; c += CS_THREADS) atomicAdd(out + c, red[c]);
 }
-int launch_colsum_scratch(const __nv_bfloat16* A, int pitch, int ncols, int64_t M, float* out, cudaStream_t st) {
-  if (!out) return 0;
-  int64_t rpb = (M + 295) / 296;
-  if (rpb < 32) rpb = 32;
-  const int64_t blocks = (M + rpb - 1) / rpb;
-  colsum_scratch_kernel<<<(unsigned)blocks, 128, 0, st>>>(A, pitch, ncols, M, (int)rpb, out);
+int launch_colsum_scratch(const __nv_bfloat16* A0, int pitch0, int ncols0, float* out0, const __nv_bfloat16* A1, int pitch1,
+                          int ncols1, float* out1, int64_t M, int sms, cudaStream_t st) {
+  if (!out0 && !out1) return 0;
+  ColsumArgs a;
+  a.A[0] = out0 ? A0 : nullptr; a.out[0] = out0; a.pitch[0] = pitch0; a.ncols[0] = ncols0;
+  a.A[1] = out1 ? A1 : nullptr; a.out[1] = out1; a.pitch[1] = pitch1 > 0 ? pitch1 : 8; a.ncols[1] = ncols1;
+  a.M = M;
+  const int rpp = CS_THREADS / (pitch0 / 8);
+  int64_t bx = (M + (int64_t)rpp * 8 - 1) / ((int64_t)rpp * 8);   // >= 8 passes per block
+  if (bx > 2 * sms) bx = 2 * sms;
+  if (bx < 1) bx = 1;
+  colsum_scratch_kernel<<<dim3((unsigned)bx, 2), CS_THREADS, 0, st>>>(a);
   VLPET_LAUNCH_OK();
   return 0;
 }
@@ -786,15 +765,18 @@ Scratch carve(int64_t M, int d, int r, int rg, bool gated, void* ws) {
 template <int R, bool GATED>
 int launch(const VlpetK1Desc& D, const CUtensorMap* m, const BParams& p, int sms, cudaStream_t st) {
   using C = BCfg<R>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLPET_CUDA_OK(cudaFuncSetAttribute(k1_bwd_sm100_kernel<R, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+  const int smem = C::smem_bytes(D.d);
+  auto kern = k1_bwd_sm100_kernel<R, GATED>;
+  static int attr_set[64] = {0};   // per device: cudaFuncSetAttribute applies to the current device's copy of the kernel
+  int dev = 0;
+  VLPET_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || attr_set[dev] < smem) {
+    VLPET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) attr_set[dev] = smem;
   }
   const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  k1_bwd_sm100_kernel<R, GATED><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9],
-                                                                  m[10], p);
+  kern<<<grid, NUM_THREADS, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], p);
   VLPET_LAUNCH_OK();
   return 0;
 }
@@ -831,7 +813,6 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   p.bd = static_cast<const __nv_bfloat16*>(w.bd); p.bu = static_cast<const __nv_bfloat16*>(w.bu);
   p.gbd = static_cast<const __nv_bfloat16*>(gated ? w.gbd : w.bd); p.gbu = static_cast<const __nv_bfloat16*>(gated ? w.gbu : w.bu);
   p.zs = s.zs; p.qs = s.qs; p.das = s.das; p.dps = s.dps; p.pz = s.pz; p.pq = s.pq;
-  p.dbd = G.dbd; p.dgbd = gated ? G.dgbd : nullptr;
   p.seed = D.seed;
   p.seed_dev = D.seed_dev;
   p.trace = g_trace_b;
@@ -840,7 +821,7 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   p.inv_keep = p.thr16 ? 1.0f / (1.0f - (float)p.thr16 / 65536.0f) : 1.0f;
   // developer hook (tools/run_sanitizers.sh): VLPET_DEBUG_BWD_PARTS bit 0 = run the tile kernel, bit 1 = column sums,
   // bit 2 = weight-gradient GEMM (default: all)
-  static const int parts = []() { const char* e = getenv("VLPET_DEBUG_BWD_PARTS"); return e ? atoi(e) : 7; }();
+  const int parts = g_bwd_parts;
   int rc = 0;
   if (!(parts & 1)) {
   } else if (gated) {
@@ -860,8 +841,7 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   }
   if (rc) return rc;
   if (parts & 2) {
-    VLPET_TRY(launch_colsum_scratch(s.das, s.pz, D.r, D.M, G.dbd, st));
-    if (gated) VLPET_TRY(launch_colsum_scratch(s.dps, s.pq, rg, D.M, G.dgbd, st));
+    VLPET_TRY(launch_colsum_scratch(s.das, s.pz, D.r, G.dbd, s.dps, gated ? s.pq : 0, rg, gated ? G.dgbd : nullptr, D.M, sms, st));
   }
   if (!(parts & 4)) return 0;
   // ---- weight gradients: dWu = du^T z (+dbu), dGu = dt^T q (+dgbu), dWd = (x2^T da)^T, dGd = (x1^T dp)^T
@@ -902,6 +882,10 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
 
 }  // namespace
 
+int set_k1_bwd_parts(int parts) {
+  g_bwd_parts = parts;
+  return 0;
+}
 int set_k1_bwd_trace(unsigned long long* dev_buf) {
   g_trace_b = dev_buf;
   return 0;
@@ -909,7 +893,7 @@ int set_k1_bwd_trace(unsigned long long* dev_buf) {
 
 bool fused_k1_bwd_supported(const VlpetK1Desc& D) {
   if (D.dtype != VLPET_BF16 || D.gate != VLPET_GATE_LARGE) return false;
-  if (D.d % 128 != 0 || D.d < 128 || D.d > 1024) return false;   // d <= 1024: the fp32 bias tables (BCfg::OFF_TAB)
+  if (D.d % 128 != 0 || D.d < 128 || BCfg<96>::smem_bytes(D.d) > SMEM_LIMIT) return false;   // the fp32 bias tables must fit
   if (D.r % 8 != 0 || D.rg % 8 != 0 || D.r < 8 || D.rg < 8 || pick_R2(D.r, D.rg) == 0) return false;
   if (D.M <= 0 || D.M > (int64_t)0x7fffff00) return false;
   return device_sm_count() > 0 && wgrad_sm100_supported(D.d, D.r) && wgrad_sm100_supported(D.d, D.rg);
