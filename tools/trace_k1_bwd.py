@@ -27,11 +27,14 @@ def run(M):
     row = t[0]; rel = row - row[0]
     print(f"M={M}: CTA 0 first tile, ns from tile start: A/P ready {rel[1]}, epi1 done {rel[2]}")
     for c in range(12):
+        if rel[3 + 3 * c] < 0: break
         a, b, cc = rel[3 + 3 * c], rel[4 + 3 * c], rel[5 + 3 * c]
         print(f"   p2 chunk {c:2d}: UT ready {a:7d}  ld+wait x {b - a:5d}  math {cc - b:6d} -> {cc}")
     print(f"   dz ready {rel[41]} (waited {rel[41]-rel[40]}), epi3 done {rel[42]}")
     for c in range(12):
+        if rel[43 + 3 * c] < 0: break
         a, b, cc = rel[43 + 3 * c], rel[44 + 3 * c], rel[45 + 3 * c]
         print(f"   p3 chunk {c:2d}: ACC ready {a:7d}  ld+wait x {b - a:5d}  math {cc - b:6d} -> {cc}")
-for M in (128 * 100, 96000):
+import sys as _s
+for M in ([int(x) for x in _s.argv[1:]] or (128 * 100, 96000)):
     run(M)

@@ -311,6 +311,33 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   // epilogue threads microseconds per arrive (measured), and the TMEM hand-over is ordered by the tcgen05 fences anyway
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// cluster-scope hand-over through an mbarrier: the arriving thread publishes (release) what its CTA wrote before a CTA-level
+// barrier, the waiting threads acquire it
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_dbg(uint32_t bar, uint32_t parity, uint32_t* dbg, uint32_t code) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 24)) {
+      if (dbg) {
+        dbg[1] = blockIdx.x; dbg[2] = threadIdx.x; dbg[3] = parity; dbg[4] = bar;
+        dbg[0] = code;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");

@@ -24,6 +24,10 @@
 // of shared-memory port traffic per tile freed: the kernel is port-bound), which pays for 3-stage activation and weight
 // rings; role loops run under elect.sync (uniform-register issue path); and the barrier-phase hazard behind the sporadic
 // launch failure of round 1 is closed (see epilogue 4).
+// Tile split (small M, the strong-scaling case: fewer tiles than SMs): a thread-block cluster of nsplit CTAs shares a tile.
+// Every CTA runs phase 1 and epilogue 1 in full (redundant, L2 hits), but only nkc/nsplit of the column chunks of phases 2
+// and 3; the partial dz / dq sums meet in an L2-resident exchange buffer between phase 2 and epilogue 3 (plain stores, one
+// cluster-scope mbarrier round, summed in rank order: deterministic).  One tile then costs phase 1 + 1/nsplit of the rest.
 // Warp roles: 0 TMA producer (activations), 3 TMA producer (weights), 1 MMA issuer (TMEM owner), 2 TMA-store issuer,
 // 4..19 epilogue (warp%4 = TMEM lane quarter; cg = (warp-4)/4: adapter | gate branch and column half in epi 1/3, 16 of the
 // chunk's 64 columns in epi 2/4).  Epilogue arithmetic is on packed fp32 pairs (FFMA2).
@@ -97,13 +101,15 @@ struct BParams {
   const uint64_t* seed_dev;
   uint32_t thr16;
   float inv_keep;
+  int nsplit;                           // > 1: a cluster of nsplit CTAs shares every tile (small M), see "tile split" below
+  float* xchg;                          // [tiles][nsplit][2R][128] fp32: partial dz | dq of the CTAs of a cluster
   unsigned long long* trace;            // developer hook (tools/trace_k1_bwd.py), normally null
   uint32_t* dbg;                        // host-mapped trap record (ptx::mbar_wait_dbg)
 };
 
 enum { B_XFULL = 0, B_XEMPTY = B_XFULL + SX, B_WFULL = B_XEMPTY + SX, B_WEMPTY = B_WFULL + SW, B_APFULL = B_WEMPTY + SW,
        B_ZQFULL, B_UTFULL, B_UTEMPTY, B_DUDT, B_DZQDONE = B_DUDT + SX, B_DZFULL = B_DZQDONE + SX, B_DAPFULL,
-       B_ACCFULL, B_ACCEMPTY, B_OUTRDY, B_COUNT = B_OUTRDY + SX };
+       B_ACCFULL, B_ACCEMPTY, B_XCHG, B_OUTRDY, B_COUNT = B_OUTRDY + SX };
 static_assert(8 * B_COUNT + 8 <= 512, "barriers + the TMEM address slot must fit the 512-byte barrier block");
 
 using namespace ptx;   // f2 helpers (packed fp32 pairs)
@@ -161,6 +167,10 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   const int nkc = p.d / CH;
   const int64_t num_tiles = (p.M + TILE_M - 1) / TILE_M;
   const bool mulgate = p.add_gate == 0;
+  const uint32_t crank = p.nsplit > 1 ? ptx::cluster_ctarank() : 0u;
+  const int cps = nkc / p.nsplit;                       // chunks of phases 2 / 3 this CTA owns: [cb, ce)
+  const int cb = (int)crank * cps, ce = cb + cps;
+  const int64_t tile0 = blockIdx.x / p.nsplit, tstride = gridDim.x / p.nsplit;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SX; ++i) {
@@ -177,6 +187,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     ptx::mbar_init(bar(B_DAPFULL), EPI_THREADS);
     ptx::mbar_init(bar(B_ACCFULL), 1);
     ptx::mbar_init(bar(B_ACCEMPTY), EPI_THREADS);
+    ptx::mbar_init(bar(B_XCHG), (uint32_t)p.nsplit);
     ptx::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_dout); }
@@ -205,6 +216,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.nsplit > 1) ptx::cluster_sync_all();   // the peers' exchange barriers are initialised before any remote arrive
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -215,10 +227,10 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     // except the last read of dout.
     if (ptx::elect_one()) {
       uint32_t xi = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int64_t tile = tile0; tile < num_tiles; tile += tstride) {
         const int row0 = (int)(tile * TILE_M);
         for (int ph = 0; ph < 3; ++ph) {
-          for (int c = 0; c < nkc; ++c, ++xi) {
+          for (int c = ph ? cb : 0; c < (ph ? ce : nkc); ++c, ++xi) {
             const uint32_t sx = xi % SX;
             ptx::mbar_wait_dbg(bar(B_XEMPTY + sx), ((xi / SX) & 1) ^ 1, p.dbg, __LINE__);
             const uint32_t xdst = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
@@ -248,9 +260,9 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     // ===================================== TMA producer: weights (always L2 hits) =====================================
     if (ptx::elect_one()) {
       uint32_t wi = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int64_t tile = tile0; tile < num_tiles; tile += tstride) {
         for (int ph = 0; ph < 3; ++ph) {
-          for (int c = 0; c < nkc; ++c, ++wi) {
+          for (int c = ph ? cb : 0; c < (ph ? ce : nkc); ++c, ++wi) {
             const uint32_t sw = wi % SW;
             ptx::mbar_wait_dbg(bar(B_WEMPTY + sw), ((wi / SW) & 1) ^ 1, p.dbg, __LINE__);
             const uint32_t wdst = smem_base + C::OFF_W + sw * C::WSLOT;
@@ -288,7 +300,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       constexpr uint32_t IDESC_DZ = ptx::umma_idesc_bf16_m128_major(R, 0u, 1u);         // dz/dq: B MN-major, N = R
       constexpr uint32_t IDESC_DX = ptx::umma_idesc_bf16_m128_major(CH, 0u, 1u);        // DX: B MN-major, N = 64
       uint32_t xi = 0, wi = 0, ui = 0, p2i = 0, ai = 0, ti = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      for (int64_t tile = tile0; tile < num_tiles; tile += tstride, ++ti) {
         // Ordering, not a TMEM hazard: the phase-3 XFULL phases of the previous tile were observed by the EPILOGUE only, and
         // it arrives on ACCEMPTY after having seen them.  A parity wait on XFULL below is meaningful only once the previous
         // phase of that barrier has completed (see epilogue 4).
@@ -318,7 +330,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         if (!GATED) {
           // dz += dout_c Wu_c straight from the ring.  The accumulator columns are free: epilogue 3 of the previous tile
           // (their last reader) precedes every phase-3 accumulator hand-over this thread has already waited for.
-          for (int c = 0; c < nkc; ++c, ++xi, ++wi) {
+          for (int c = cb; c < ce; ++c, ++xi, ++wi) {
             const uint32_t sx = xi % SX, sw = wi % SW;
             ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
             ptx::mbar_wait_dbg(bar(B_WFULL + sw), (wi / SW) & 1, p.dbg, __LINE__);
@@ -328,7 +340,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
 #pragma unroll
             for (int ks = 0; ks < CH / 16; ++ks)
               ptx::umma_bf16_ss(tmem_base + C::TM_DZ, ptx::umma_desc_kmajor_sw128(dos + ks * 32),
-                                ptx::umma_desc_mnmajor_sw128(wus + ks * 2048, CH * CH * 2), IDESC_DZ, (c > 0 || ks > 0) ? 1u : 0u);
+                                ptx::umma_desc_mnmajor_sw128(wus + ks * 2048, CH * CH * 2), IDESC_DZ, (c > cb || ks > 0) ? 1u : 0u);
             ptx::umma_commit(bar(B_XEMPTY + sx));
             ptx::umma_commit(bar(B_WEMPTY + sw));
           }
@@ -354,7 +366,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             ptx::umma_commit(bar(B_DZQDONE + k));
             ptx::umma_commit(bar(B_WEMPTY + sw));
           };
-          for (int c = 0; c < nkc; ++c, ++xi, ++wi, ++ui, ++p2i) {
+          for (int c = cb; c < ce; ++c, ++xi, ++wi, ++ui, ++p2i) {
             const uint32_t sw = wi % SW;
             ptx::mbar_wait_dbg(bar(B_WFULL + sw), (wi / SW) & 1, p.dbg, __LINE__);
             ptx::mbar_wait_dbg(bar(B_UTEMPTY), (ui & 1) ^ 1, p.dbg, __LINE__);
@@ -369,15 +381,15 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
                                 ptx::umma_desc_kmajor_sw128(gus + kb * (CH * CH * 2) + kin * 32), IDESC_UT, ks > 0);
             }
             ptx::umma_commit(bar(B_UTFULL));
-            if (c > 0) issue_dzdq(c - 1);
+            if (c > cb) issue_dzdq(c - 1 - cb);
           }
-          issue_dzdq(nkc - 1);
+          issue_dzdq(cps - 1);
           ptx::umma_commit(bar(B_DZFULL));
         }
         // ---- phase 3
         ptx::mbar_wait_dbg(bar(B_DAPFULL), ti & 1, p.dbg, __LINE__);
         ptx::tc_fence_after();
-        for (int c = 0; c < nkc; ++c, ++xi, ++wi, ++ai) {
+        for (int c = cb; c < ce; ++c, ++xi, ++wi, ++ai) {
           const uint32_t sw = wi % SW;
           ptx::mbar_wait_dbg(bar(B_WFULL + sw), (wi / SW) & 1, p.dbg, __LINE__);
           ptx::mbar_wait_dbg(bar(B_ACCEMPTY), (ai & 1) ^ 1, p.dbg, __LINE__);
@@ -404,11 +416,11 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     // ===================================== TMA store issuer =====================================
     if (ptx::elect_one()) {
       uint32_t xi = 0, p2i = 0, p3i = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int64_t tile = tile0; tile < num_tiles; tile += tstride) {
         const int row0 = (int)(tile * TILE_M);
         xi += nkc;  // phase-1 stages are released by the MMA warp
-        if (!GATED) xi += nkc;  // ungated: phase-2 stages are released by the MMA warp as well
-        for (int c = 0; GATED && c < nkc; ++c, ++xi, ++p2i) {
+        if (!GATED) xi += cps;  // ungated: phase-2 stages are released by the MMA warp as well
+        for (int c = cb; GATED && c < ce; ++c, ++xi, ++p2i) {
           const uint32_t sx = xi % SX, k = p2i % SX;
           ptx::mbar_wait_dbg(bar(B_DUDT + k), (p2i / SX) & 1, p.dbg, __LINE__);
           const uint32_t src = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
@@ -419,7 +431,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           ptx::tma_store_wait_read0();
           ptx::mbar_arrive(bar(B_XEMPTY + sx));
         }
-        for (int c = 0; c < nkc; ++c, ++xi, ++p3i) {
+        for (int c = cb; c < ce; ++c, ++xi, ++p3i) {
           const uint32_t sx = xi % SX, k = p3i % SX;
           ptx::mbar_wait_dbg(bar(B_OUTRDY + k), (p3i / SX) & 1, p.dbg, __LINE__);
           const uint32_t src = smem_base + C::OFF_X + sx * (2 * XCH_BYTES);
@@ -451,7 +463,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     const f2 s2 = mk2(p.s, p.s);
     const float s_keep = p.s * p.inv_keep;
     uint32_t xi = 0, ui = 0, p2i = 0, p3i = 0, ai = 0, ti = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+    for (int64_t tile = tile0; tile < num_tiles; tile += tstride, ++ti) {
       const int64_t grow = tile * TILE_M + row;
       const bool row_ok = grow < p.M;
       // ---- epilogue 1 (APFULL also implies that every MMA of the previous tile, which read q / da / dp, has completed)
@@ -481,13 +493,13 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           }
           // in place: columns j0 .. j0+7 <- packed z (K step j0/16 of the TS-form A operand), j0+8 .. j0+15 <- gelu'
           ptx::tmem_st_32x32b_x16(tsrc + j0, o);
-          if (row_ok) {
+          if (row_ok && crank == 0) {
             if (j0 < rr) *reinterpret_cast<uint4*>(srow + j0) = make_uint4(o[0], o[1], o[2], o[3]);
             if (j0 + 8 < rr) *reinterpret_cast<uint4*>(srow + j0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
           }
         }
         ptx::tmem_st_wait();
-        if (row_ok && (cg & 1) == 1) {  // ones column (bias-gradient trick of the weight-gradient GEMM) + zero pad up to the pitch
+        if (row_ok && crank == 0 && (cg & 1) == 1) {  // ones column (bias-gradient trick of the weight-gradient GEMM) + zero pad up to the pitch
           const uint4 one = make_uint4(0x00003F80u, 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(srow + rr) = one;
         }
@@ -497,11 +509,11 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       VLPET_TRACE_B(2);
       xi += nkc;
       // ---- epilogue 2, per 64-column chunk: du, dt
-      if (!GATED) xi += nkc;
-      for (int c = 0; GATED && c < nkc; ++c, ++xi, ++ui, ++p2i) {
+      if (!GATED) xi += cps;
+      for (int c = cb; GATED && c < ce; ++c, ++xi, ++ui, ++p2i) {
         const uint32_t sx = xi % SX;
         ptx::mbar_wait_dbg(bar(B_UTFULL), ui & 1, p.dbg, __LINE__);
-        VLPET_TRACE_B(3 + 3 * c);
+        VLPET_TRACE_B(3 + 3 * (c - cb));
         ptx::tc_fence_after();
         uint32_t u[16], t[16];
         ptx::tmem_ld_32x32b_x16(lane_addr + C::TM_UT + cg * 16, u);
@@ -510,7 +522,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_UTEMPTY));
         ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
-        VLPET_TRACE_B(4 + 3 * c);
+        VLPET_TRACE_B(4 + 3 * (c - cb));
         const uint32_t x2row = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t dorow = x2row + XCH_BYTES;
         const int col0 = c * CH + cg * 16;
@@ -564,13 +576,37 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         else { group2(std::false_type{}, 0); group2(std::false_type{}, 1); }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(bar(B_DUDT + (p2i % SX)));
-        VLPET_TRACE_B(5 + 3 * c);
+        VLPET_TRACE_B(5 + 3 * (c - cb));
       }
       // ---- epilogue 3: da = dz * gelu_new'(A + bd) (branch 0), dp = dq * gelu_new'(P + gbd) (branch 1)
       VLPET_TRACE_B(40);
       ptx::mbar_wait_dbg(bar(B_DZFULL), ti & 1, p.dbg, __LINE__);
       VLPET_TRACE_B(41);
       ptx::tc_fence_after();
+      if (p.nsplit > 1) {
+        // ---- tile split: publish this CTA's partial dz | dq, meet the other CTAs of the cluster
+        if (GATED || branch == 0) {
+          const uint32_t tdz = lane_addr + (branch ? C::TM_DQ : C::TM_DZ);
+          // [tile][rank][column][row]: the 32 lanes of a warp (32 rows) write one 128-byte line per column -- a row-major
+          // slot made every warp instruction touch 32 lines (~40 us per exchange in the L1 wavefront queue)
+          float* mine = p.xchg + (((size_t)tile * p.nsplit + crank) * (2 * R) + branch * R + jbeg) * TILE_M + row;
+#pragma unroll
+          for (int jj = 0; jj < HALF; jj += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld_32x32b_x16(tdz + jbeg + jj, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) __stcg(mine + (size_t)(jj + e) * TILE_M, __uint_as_float(v[e]));
+          }
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // epilogue warps only
+        if (threadIdx.x == 128) {
+          for (uint32_t pr = 0; pr < (uint32_t)p.nsplit; ++pr) ptx::mbar_arrive_cluster_release(ptx::mapa(bar(B_XCHG), pr));
+        }
+        ptx::mbar_wait_cluster_dbg(bar(B_XCHG), ti & 1, p.dbg, __LINE__);
+        __threadfence();
+      }
       if (GATED || branch == 0) {
         const f2 dzs2 = GATED ? mk2(1.0f, 1.0f) : alpha2;   // ungated: du = alpha*dout was fed unscaled
         const uint32_t tpre = lane_addr + (branch ? C::TM_P : C::TM_A);
@@ -584,11 +620,28 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           ptx::tmem_ld_32x32b_x8(tpre + j0 + 8, gq);   // gelu_new'(pre-activation), stored by epilogue 1
           ptx::tmem_ld_32x32b_x16(tdz + j0, dz);
           ptx::tmem_ld_wait();
+          if (p.nsplit > 1) {   // sum of the partials in rank order (every CTA of the cluster gets the same bits)
+            float acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+            for (uint32_t pr = 0; pr < (uint32_t)p.nsplit; ++pr) {
+              if (pr == crank) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(dz[e]);
+              } else {
+                const float* peer = p.xchg + (((size_t)tile * p.nsplit + pr) * (2 * R) + branch * R + j0) * TILE_M + row;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[e] += __ldcg(peer + (size_t)e * TILE_M);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) dz[e] = __float_as_uint(acc[e]);
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e)
             o[e] = pack2(mul2(mul2(mk2u(dz[2 * e], dz[2 * e + 1]), dec_fix2(gq[e])), dzs2));
           ptx::tmem_st_32x32b_x8(tpre + j0 + 8, o);     // packed da / dp: K step j0/16 of the phase-3 A operands
-          if (row_ok) {
+          if (row_ok && crank == 0) {
             if (j0 < rr) *reinterpret_cast<uint4*>(srow + j0) = make_uint4(o[0], o[1], o[2], o[3]);
             if (j0 + 8 < rr) *reinterpret_cast<uint4*>(srow + j0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
           }
@@ -599,10 +652,10 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       ptx::mbar_arrive(bar(B_DAPFULL));
       VLPET_TRACE_B(42);
       // ---- epilogue 4, per 64-column chunk: dx1, dx2
-      for (int c = 0; c < nkc; ++c, ++xi, ++ai, ++p3i) {
+      for (int c = cb; c < ce; ++c, ++xi, ++ai, ++p3i) {
         const uint32_t sx = xi % SX;
         ptx::mbar_wait_dbg(bar(B_ACCFULL), ai & 1, p.dbg, __LINE__);
-        VLPET_TRACE_B(43 + 3 * c);
+        VLPET_TRACE_B(43 + 3 * (c - cb));
         ptx::tc_fence_after();
         uint32_t t[16], g2[16], g1[16];
         if (GATED && mulgate) ptx::tmem_ld_32x32b_x16(lane_addr + C::TM_T + cg * 16, t);
@@ -617,7 +670,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         // time: the sporadic launch failure of round 1 (profiles/r2_b1_fault_rootcause.md).
         ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
         ptx::mbar_arrive(bar(B_ACCEMPTY));
-        VLPET_TRACE_B(44 + 3 * c);
+        VLPET_TRACE_B(44 + 3 * (c - cb));
         const uint32_t dorow = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t o2row = dorow + XCH_BYTES;
         const int col0 = c * CH + cg * 16;
@@ -668,13 +721,14 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         else { group4(std::false_type{}, 0); group4(std::false_type{}, 1); }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(bar(B_OUTRDY + (p3i % SX)));
-        VLPET_TRACE_B(45 + 3 * c);
+        VLPET_TRACE_B(45 + 3 * (c - cb));
       }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.nsplit > 1) ptx::cluster_sync_all();   // no CTA exits while a peer can still arrive on its exchange barrier
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -739,9 +793,60 @@ int launch_colsum_scratch(const __nv_bfloat16* A0, int pitch0, int ncols0, float
   return 0;
 }
 
+// ---- tile split: how many CTAs share a tile -----------------------------------------------------------------------
+// The largest divisor of nkc (<= 8, the portable cluster size) for which every tile still gets its own cluster in ONE wave.
+// Cluster capacity is asked from the driver once per device and cluster size (GPCs strand SMs for some sizes).
+template <int R, bool GATED>
+int max_clusters(int ns, int d) {
+  static int cache[64][9];
+  static bool init = false;
+  if (!init) { memset(cache, 0, sizeof(cache)); init = true; }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cache[dev][ns] != 0) return cache[dev][ns] > 0 ? cache[dev][ns] : 0;
+  auto kern = k1_bwd_sm100_kernel<R, GATED>;
+  const int smem = BCfg<R>::smem_bytes(d > 1024 ? d : 1024);
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)ns; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)(ns * 16)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  } else {
+    cudaGetLastError();
+  }
+  cache[dev][ns] = n > 0 ? n : -1;
+  return n;
+}
+int g_bwd_split = []() { const char* e = getenv("VLPET_K1_BWD_SPLIT"); return e ? atoi(e) : -1; }();   // -1 auto, 1 never
+template <int R, bool GATED>
+int pick_split(int64_t tiles, int d, int sms) {
+  if (g_bwd_split == 1 || tiles * 2 > sms) return 1;
+  const int nkc = d / CH;
+  for (int ns = 4; ns >= 2; --ns) {   // 6 measured no faster than 4 (43 us at M = 2128): the exchange grows with the cluster
+    if (nkc % ns != 0 || (g_bwd_split > 1 && ns != g_bwd_split)) continue;
+    if (tiles <= max_clusters<R, GATED>(ns, d)) return ns;
+  }
+  return 1;
+}
+int pick_R2(int r, int rg);
+int pick_split_rt(bool gated, int R, int64_t tiles, int d, int sms) {
+  switch (R) {
+    case 32: return gated ? pick_split<32, true>(tiles, d, sms) : pick_split<32, false>(tiles, d, sms);
+    case 64: return gated ? pick_split<64, true>(tiles, d, sms) : pick_split<64, false>(tiles, d, sms);
+    case 96: return gated ? pick_split<96, true>(tiles, d, sms) : pick_split<96, false>(tiles, d, sms);
+  }
+  return 1;
+}
+
 struct Scratch {
   __nv_bfloat16 *zs, *qs, *das, *dps, *dus, *dts;
-  int pz, pq;
+  float* xchg;
+  int pz, pq, nsplit;
   size_t bytes;
 };
 Scratch carve(int64_t M, int d, int r, int rg, bool gated, void* ws) {
@@ -758,6 +863,10 @@ Scratch carve(int64_t M, int d, int r, int rg, bool gated, void* ws) {
     s.dus = a.take<__nv_bfloat16>((size_t)M * d);
     s.dts = a.take<__nv_bfloat16>((size_t)M * d);
   }
+  const int64_t tiles = (M + TILE_M - 1) / TILE_M;
+  const int R = pick_R2(r, rg);
+  s.nsplit = R ? pick_split_rt(gated, R, tiles, d, device_sm_count()) : 1;
+  s.xchg = s.nsplit > 1 ? a.take<float>((size_t)tiles * s.nsplit * TILE_M * 2 * R) : nullptr;
   s.bytes = a.off;
   return s;
 }
@@ -775,6 +884,18 @@ int launch(const VlpetK1Desc& D, const CUtensorMap* m, const BParams& p, int sms
     if (dev >= 0 && dev < 64) attr_set[dev] = smem;
   }
   const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
+  if (p.nsplit > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.nsplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)(tiles * p.nsplit)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    VLPET_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], p));
+    count_launch();
+    return 0;
+  }
   const int grid = (int)(tiles < sms ? tiles : sms);
   kern<<<grid, NUM_THREADS, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], p);
   VLPET_LAUNCH_OK();
@@ -813,6 +934,7 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   p.bd = static_cast<const __nv_bfloat16*>(w.bd); p.bu = static_cast<const __nv_bfloat16*>(w.bu);
   p.gbd = static_cast<const __nv_bfloat16*>(gated ? w.gbd : w.bd); p.gbu = static_cast<const __nv_bfloat16*>(gated ? w.gbu : w.bu);
   p.zs = s.zs; p.qs = s.qs; p.das = s.das; p.dps = s.dps; p.pz = s.pz; p.pq = s.pq;
+  p.nsplit = s.nsplit; p.xchg = s.xchg;
   p.seed = D.seed;
   p.seed_dev = D.seed_dev;
   p.trace = g_trace_b;

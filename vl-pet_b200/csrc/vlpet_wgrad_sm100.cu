@@ -10,8 +10,8 @@
 // Why a separate kernel (DESIGN.md "K1-bwd"): the four dW accumulators are 4 x [768 x 96] fp32 = 1.18 MB, far more
 // than one SM can keep on chip (TMEM is 256 KB), and they contract over ALL tokens -- so a token-tile-major kernel
 // would have to flush 1.18 MB of partials per 128-token tile (885 MB of L2 reductions at M = 96 000).  Here the
-// accumulators are STATIONARY instead: a CTA owns (pair, 384 output rows) in TMEM (3 x [128 x N] fp32) for the whole
-// launch, streams 64-token slices of A and B through a 3-stage TMA ring, and flushes once at the end.
+// accumulators are STATIONARY instead: a CTA owns (pair, 128 output rows) in TMEM ([128 x N] fp32) for the whole
+// launch, streams 64-token slices of A and B through a 6-stage TMA ring, and flushes once at the end.
 //
 // Both operands are consumed MN-major straight from the row-major global layout ([tok][c] / [tok][n], contraction
 // index = row), i.e. no transposed copies exist anywhere.
@@ -23,12 +23,15 @@ namespace {
 
 constexpr int KT = 64;                    // tokens per ring stage
 constexpr int SLAB = 128;                 // output rows (d columns) per accumulator = MMA M
-constexpr int SPC = 3;                    // slabs per CTA
+constexpr int SPC = 1;                    // slabs per CTA: one -- the final flush (fp32 reductions into the gradient buffers) is
+                                          // the per-launch floor and scales with the rows a CTA owns (3 slabs: 31 us at any M)
 constexpr int BOX_BYTES = KT * 64 * 2;    // one [64 tok x 64 cols] bf16 box = 8 KB
 constexpr int A_STAGE = SPC * 2 * BOX_BYTES;   // 48 KB
 constexpr int B_STAGE = 2 * BOX_BYTES;         // 16 KB
 constexpr int STAGE = A_STAGE + B_STAGE;       // 64 KB
-constexpr int NST = 3;
+constexpr int NST = 6;
+constexpr int NACC = 4;                   // accumulators per slab, used round-robin by the steps and summed at the flush: the
+                                          // fp32 accumulation chain of one TMEM accumulator stays 4x shorter (rounding)
 constexpr int SMEM_BYTES = NST * STAGE + 256 + 1024;
 constexpr int THREADS = 192;
 
@@ -68,7 +71,7 @@ wgrad_sm100_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) {
     ptx::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&maps.a[pair]); ptx::prefetch_tmap(&maps.b[pair]); }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 128 * SPC * NACC);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -102,9 +105,9 @@ wgrad_sm100_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) {
         for (int sl = 0; sl < nslab; ++sl) {
 #pragma unroll
           for (int ks = 0; ks < KT / 16; ++ks) {
-            ptx::umma_bf16_ss(tmem_base + (uint32_t)(sl * 128),
+            ptx::umma_bf16_ss(tmem_base + (uint32_t)((sl * NACC + (int)(i % NACC)) * 128),
                               ptx::umma_desc_mnmajor_sw128(a0 + (sl * 2) * BOX_BYTES + ks * 2048, BOX_BYTES),
-                              ptx::umma_desc_mnmajor_sw128(b0 + ks * 2048, BOX_BYTES), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+                              ptx::umma_desc_mnmajor_sw128(b0 + ks * 2048, BOX_BYTES), idesc, (i >= NACC || ks > 0) ? 1u : 0u);
           }
         }
         ptx::umma_commit(bar(NST + s));
@@ -130,11 +133,19 @@ wgrad_sm100_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) {
     constexpr int STG = 132;                 // row pitch (floats) of the non-transposed staging: 16-byte aligned, conflict-light
     for (int sl = 0; sl < nslab; ++sl) {
       const int c0 = (slab0 + sl) * SLAB;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sl * 128);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sl * NACC * 128);
+      const int nacc = my_steps < NACC ? (int)my_steps : NACC;   // accumulators that were written at all
       for (int n0 = 0; n0 < p.NB; n0 += 16) {
         uint32_t v[16];
         ptx::tmem_ld_32x32b_x16(taddr + n0, v);
         ptx::tmem_ld_wait();
+        for (int a = 1; a < nacc; ++a) {
+          uint32_t w[16];
+          ptx::tmem_ld_32x32b_x16(taddr + a * 128 + n0, w);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
+        }
         if (transposed) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) stage[(n0 + e) * SLAB + row] = sc * __uint_as_float(v[e]);
@@ -178,7 +189,7 @@ wgrad_sm100_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) {
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc(tmem_base, 128 * SPC * NACC);
   }
 }
 
@@ -218,15 +229,10 @@ int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void
     VLPET_CUDA_OK(cudaFuncSetAttribute(wgrad_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  // Token groups: every group ends with a flush of its partial sums (red.global.add of d x nout floats per pair, ~1.1 us
-  // of L2 reductions per group measured), every step of a group costs ~1.2 us when the operands are L2 resident:
-  // gy ~ sqrt(1.1 * nsteps) balances the two for small M; large M takes every SM.
+  // Token groups: one CTA per (pair, slab, token group); every group ends with a flush of its [128 x nout] partial sums.
   const int gx = npairs * a.ncolgroups;
   const int64_t nsteps = (Mtok + KT - 1) / KT;
   int gy = sm_count / gx;
-  int gopt = 1;
-  while ((int64_t)gopt * gopt < nsteps + nsteps / 10) ++gopt;
-  if (gy > gopt) gy = gopt;
   if (gy > nsteps) gy = (int)nsteps;
   if (gy < 1) gy = 1;
   wgrad_sm100_kernel<<<dim3(gx, gy), THREADS, SMEM_BYTES, st>>>(maps, a);
