@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--batch-size", type=int, default=300)
     ap.add_argument("--rank-r", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-eager", action="store_true", help="skip the reference-eager-on-B200 leg")
+    ap.add_argument("--ref-batch-size", type=int, default=None,
+                    help="--impl reference: per-step --batch-size of the CPU run (default: the workload's if it fits ~150 s)")
     ap.add_argument("--no-micro", action="store_true", help="skip the K1 micro-benchmark at the north-star shape")
     ap.add_argument("--graphs", type=int, default=1, help="replay each task step as a CUDA graph (0 = eager)")
     return ap.parse_args()
@@ -108,60 +111,158 @@ def peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU legs: the reference's stock-PyTorch eager path (oracle/eager_ref.py port; /root/reference does not travel)
-def cpu_reference_run(steps, warmup, bs, r, threads=None):
-    """Times `steps` optimizer steps of the eager fp32 CPU port on a bounded sample (per-task batch sizes derived
-    from --batch-size CPU_SAMPLE_BS).  Returns (samples_per_s, ms_per_step, cores, sample description)."""
-    import vlpet_b200.host as H
-    from oracle.eager_ref import use_eager_pet
+# CPU legs.  The reference itself (baseline/ref_arm.py: the unmodified sources staged under baseline/_ref/src, driven
+# through its own VLBartMultiTask.train_step) when it is staged; otherwise the op-by-op port under oracle/ (kind "port").
+def _quiet():
+    import logging
+    import warnings
+    warnings.filterwarnings("ignore")
+    logging.getLogger("transformers").setLevel(logging.ERROR)
+    try:
+        import transformers
+        transformers.logging.set_verbosity_error()
+    except Exception:
+        pass
+
+
+def _host_info():
+    model = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"cpu": model, "os_cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads(), "torch": torch.__version__}
+
+
+def cpu_reference_run(steps, warmup, bs, r, sample_bs=None, budget_s=150.0, threads=None):
+    """Times `steps` optimizer steps (fwd + bwd + clip + AdamW, dropout 0.1, fp32 eager, all host cores) of the reference on
+    the task cycle.  The per-step batch is the workload's (--batch-size bs) when it fits `budget_s`, else the largest
+    bounded sample that does (measured from one probe step).  -> dict(value, ms_per_step, cores, kind, sample, ...)."""
     cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    cfg = H.bart_base_vlpet_large(r=r, rg=r, dec_r=r)
-    model = use_eager_pet(H.VLBart(cfg)).train()
-    names = set(H.trainable_names(model, cfg))
-    params = []
-    for n, p in model.named_parameters():
-        p.requires_grad_(n in names)
-        if n in names:
-            params.append(p)
-    no_decay = ("bias", "LayerNorm.weight")
-    named = [(n, p) for n, p in model.named_parameters() if n in names]
-    opt = torch.optim.AdamW([{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
-                             {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}],
-                            lr=1e-3, eps=1e-6)
-    cycle = H.multitask_cycle(CPU_SAMPLE_BS, TASKS, seed=0)
-    n_samples, t_total = 0, 0.0
-    for i in range(warmup + steps):
-        b = cycle[i % len(cycle)]
+    _quiet()
+    from baseline import ref_arm as RA
+    if RA.available():
+        kind = "reference"
+        model, _ = RA.build_model("bart", r=r)
+        model.train()
+        params, opt = RA.prepare_training(model, lr=1e-3)
+        make_cycle = lambda b: RA.reference_batches(b, TASKS)                      # noqa: E731
+        run = lambda cyc, k, w: RA.train_steps(model, params, opt, cyc, k, w, "cpu")  # noqa: E731
+    else:
+        kind = "port"
+        import vlpet_b200.host as H
+        from oracle.eager_ref import use_eager_pet
+        torch.manual_seed(0)
+        cfg = H.bart_base_vlpet_large(r=r, rg=r, dec_r=r)
+        model = use_eager_pet(H.VLBart(cfg)).train()
+        names = set(H.trainable_names(model, cfg))
+        for n, p in model.named_parameters():
+            p.requires_grad_(n in names)
+        named = [(n, p) for n, p in model.named_parameters() if n in names]
+        params = [p for _, p in named]
+        no_decay = ("bias", "LayerNorm.weight")
+        opt = torch.optim.AdamW([{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+                                 {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}],
+                                lr=1e-3, eps=1e-6)
+        make_cycle = lambda b: (H.multitask_cycle(b, TASKS, seed=0), H.task_batch_sizes(b))  # noqa: E731
+
+        def run(cyc, k, w):
+            n, t = 0, 0.0
+            for i in range(w + k):
+                b = cyc[i % len(cyc)]
+                t0 = time.perf_counter()
+                opt.zero_grad(set_to_none=True)
+                loss = model.train_step(b)["loss"]
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(params, 5.0)
+                opt.step()
+                if i >= w:
+                    n += b["input_ids"].shape[0]
+                    t += time.perf_counter() - t0
+            return n, t, float(loss.detach())
+    if sample_bs is None:
+        probe, _ = make_cycle(CPU_SAMPLE_BS)
+        n, t, _ = run(probe, 1, 1)
+        rate = n / t                                  # samples/s at the probe size (a lower bound for larger batches)
+        per_bs = sum(make_cycle(60)[1].values()) / 4 / 60.0   # mean task batch per unit of --batch-size
+        fit = int(budget_s * rate / ((steps + warmup) * per_bs))
+        sample_bs = max(CPU_SAMPLE_BS, min(bs, fit))
+    cycle, sizes = make_cycle(sample_bs)
+    n, t, loss = run(cycle, steps, warmup)
+    sample = (f"{steps} optimizer steps (fwd+bwd+clip+AdamW, dropout 0.1, fp32 eager, {cores} threads) over the task cycle at "
+              f"per-step batch sizes {sizes} (--batch-size {sample_bs}" + ("" if sample_bs == bs else f" instead of {bs}") +
+              f"); {warmup} warm-up steps")
+    return {"value": n / t, "ms_per_step": 1e3 * t / steps, "cores": cores, "kind": kind, "sample": sample,
+            "same_config": sample_bs == bs, "sample_batch_size": sample_bs, "last_loss": loss, "host": _host_info()}
+
+
+def cpu_isolated_pet(iters=3, B=8, L=320, d=768, r=96):
+    """Kernel-level CPU baseline: the reference's encoder PET op sequence (oracle/eager_ref.py
+    isolated_pet_step: my_transformers/modeling_bart.py:1149-1155, 1196-1209, 1260) forward + backward, fp32, all cores."""
+    from oracle.eager_ref import isolated_pet_step
+    g = torch.Generator().manual_seed(0)
+    x1 = torch.randn(B, L, d, generator=g).requires_grad_()
+    x2 = (0.5 * torch.randn(B, L, d, generator=g)).requires_grad_()
+    dout = torch.randn(B, L, d, generator=g)
+    P = {k: (torch.randn(*sh, generator=g) * 0.05).requires_grad_() for k, sh in
+         (("Wd", (r, d)), ("bd", (r,)), ("Wu", (d, r)), ("bu", (d,)), ("Gd", (r, d)), ("gbd", (r,)), ("Gu", (d, r)), ("gbu", (d,)))}
+    isolated_pet_step(x1, x2, dout, P)
+    ts = []
+    for _ in range(iters):
         t0 = time.perf_counter()
-        opt.zero_grad(set_to_none=True)
-        loss = model.train_step(b)["loss"]
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(params, 5.0)
-        opt.step()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            n_samples += b["input_ids"].shape[0]
-            t_total += dt
-    sizes = H.task_batch_sizes(CPU_SAMPLE_BS)
-    sample = (f"{steps} optimizer steps (fwd+bwd+clip+AdamW, dropout 0.1, fp32 eager) over the task cycle at per-step "
-              f"sample sizes {sizes} (= --batch-size {CPU_SAMPLE_BS} instead of {bs}); {warmup} warm-up steps")
-    return n_samples / t_total, 1e3 * t_total / steps, cores, sample
+        isolated_pet_step(x1, x2, dout, P)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    t = ts[len(ts) // 2]
+    M = B * L
+    return {"tokens_per_s": round(M / t, 1), "algorithmic_GBps_fp32": round(8 * d * 4 * M / t / 1e9, 3),
+            "shape": {"M": M, "d": d, "r": r}, "bytes_per_token": 8 * d * 4, "threads": torch.get_num_threads()}
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, ms, cores, sample = cpu_reference_run(a.steps, max(1, min(a.warmup, 2)), a.batch_size, a.rank_r)
+    res = cpu_reference_run(a.steps, max(1, min(a.warmup, 2)), a.batch_size, a.rank_r, sample_bs=a.ref_batch_size)
+    v = res["value"]
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 2), "higher_is_better": True,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(res["ms_per_step"], 2), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a.batch_size, a.rank_r), "l2": "CPU run"},
-            "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": workload_name(a.batch_size, a.rank_r), "l2": "CPU run", "same_config": res["same_config"],
+                       "host": res["host"]},
+            "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
+                             "sample": res["sample"]},
             "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def reference_eager_b200(a, dev, host_cycle, global_sizes):
+    """The like-for-like GPU comparison: the reference's own model and train_step, stock PyTorch
+    eager on the same B200, fp32 (what the shipped scripts run) and bf16 autocast, fed the same pinned host batches."""
+    _quiet()
+    from baseline import ref_arm as RA
+    if not RA.available():
+        return {"unavailable": "reference sources not staged under baseline/_ref/src"}
+    out = {"workload": workload_name(a.batch_size, a.rank_r), "what": "reference VLBartMultiTask.train_step + backward + clip + AdamW, "
+           "eager, host batches -> .to(device) inside train_step (its own API)"}
+    samples = sum(global_sizes[t] for t in TASKS)
+    for name, ac in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        try:
+            model, _ = RA.build_model("bart", r=a.rank_r)
+            model = model.to(dev).train()
+            params, opt = RA.prepare_training(model, lr=1e-3)
+            n, t, loss = RA.train_steps(model, params, opt, host_cycle, 2 * len(TASKS), len(TASKS), dev, autocast_dtype=ac)
+            out[name] = {"value": round(n / t, 1), "unit": UNIT, "ms_per_step": round(1e3 * t / (2 * len(TASKS)), 2),
+                         "last_loss": round(loss, 4)}
+            del model, params, opt
+            torch.cuda.empty_cache()
+        except Exception as ex:   # noqa: BLE001
+            out[name] = {"unavailable": repr(ex)[:200]}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -198,8 +299,9 @@ def k1_micro(V, F_, peak):
         tot_ms += ms
         tot_b += by
         res[k] = {"us": round(1e3 * ms, 1), "algorithmic_GBps": round(by / ms / 1e6, 1), "frac": round(by / ms / 1e6 / peak, 3)}
-    try:   # measured DRAM traffic of the same launches, from the committed ncu captures (profiles/r1_ncu_traffic.json)
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+    try:   # DRAM traffic of the same launches: NOT measured by this run -- read from the committed ncu capture
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        res["traffic_source"] = "committed ncu capture (profiles/ncu_traffic.json: " + t.get("capture", "?") + "), not this run"
         res["k1_fwd"]["traffic_MB"] = round(t["k1_fwd"]["read_MB"] + t["k1_fwd"]["write_MB"], 1)
         res["k1_bwd"]["traffic_MB"] = round(sum(t[k]["read_MB"] + t[k]["write_MB"] for k in
                                                  ("k1_bwd_activation_gradients", "k1_bwd_weight_gradients")), 1)
@@ -321,10 +423,14 @@ def run_ours(a):
     micro = None
     if not a.no_micro and world == 1:
         micro = k1_micro(V, F_, peak)
+    ref_gpu = None
+    if world == 1 and not a.no_ref_eager:
+        ref_gpu = reference_eager_b200(a, dev, host_cycle, global_sizes)
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
-        v, _, cores, sample = cpu_reference_run(4, 1, a.batch_size, a.rank_r)
-        cpu = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        res = cpu_reference_run(4, 1, a.batch_size, a.rank_r, sample_bs=CPU_SAMPLE_BS)
+        cpu = {"value": round(res["value"], 3), "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"],
+               "host": res["host"], "isolated_pet": cpu_isolated_pet()}
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -335,7 +441,8 @@ def run_ours(a):
                        "cuda_graphs": bool(a.graphs)},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / a.steps, 3), "last_loss": losses[-1] if losses else None},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "k1_micro": micro}
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "k1_micro": micro,
+            "reference_eager_b200": ref_gpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

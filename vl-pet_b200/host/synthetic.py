@@ -45,13 +45,13 @@ def make_task_batch(task: str, B: int, feat_dim: int = 2048, grid: int = 49, see
 
 
 def multitask_cycle(batch_size: int, tasks: List[str], feat_dim: int = 2048, seed: int = 0, pin: bool = False,
-                    rank: int = 0, world: int = 1) -> List[Dict]:
+                    rank: int = 0, world: int = 1, vocab_hi: int = 50000) -> List[Dict]:
     """One round-robin cycle over ``tasks`` at the reference ratios; with world > 1 each batch is this rank's
     contiguous shard of the GLOBAL task batch (strong scaling: the global batch is fixed)."""
     sizes = task_batch_sizes(batch_size)
     out = []
     for t in tasks:
-        gb = make_task_batch(t, sizes[t], feat_dim=feat_dim, seed=seed)
+        gb = make_task_batch(t, sizes[t], feat_dim=feat_dim, seed=seed, vocab_hi=vocab_hi)
         b = shard_batch(gb, rank, world)
         if pin:
             b = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
