@@ -39,8 +39,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-size", type=int, default=300)
-    ap.add_argument("--rank-r", type=int, default=96)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configs[] index + 1: 2 BART-base large r=96 bs=300 (the metric's config, default); "
+                         "3 T5-base large r=96 bs=300; 4 BART-base small r=4 bs=512; 5 BART-base large, video-text, bs=128")
+    ap.add_argument("--batch-size", type=int, default=None)
+    ap.add_argument("--rank-r", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-eager", action="store_true", help="skip the reference-eager-on-B200 leg")
     ap.add_argument("--ref-batch-size", type=int, default=None,
@@ -50,8 +53,28 @@ def parse():
     return ap.parse_args()
 
 
-def workload_name(bs, r):
-    return f"BART-base + VL-PET-large r={r}, image-text multitask synthetic (vqa/gqa/nlvr/caption at {bs}:{int(bs*100/60)}:{int(bs*20/60)}:{int(bs*50/60)}), bs={bs}, bf16"
+def workload_name(bs, r, config=2):
+    ratios = f"(vqa/gqa/nlvr/caption at {bs}:{int(bs*100/60)}:{int(bs*20/60)}:{int(bs*50/60)})"
+    if config == 3:
+        return f"T5-base + VL-PET-large r={r} (gate scale 0.3), image-text multitask synthetic {ratios}, bs={bs}, bf16"
+    if config == 4:
+        return f"BART-base + VL-PET-small r={r}, image-text multitask synthetic {ratios}, bs={bs}, bf16"
+    if config == 5:
+        return (f"BART-base + VL-PET-large r={r}, video-text multitask synthetic (tvqa/how2qa/tvc/yc2c, 64 CLIP-ViT frame features "
+                f"of width 512 + 256 text tokens = 320 encoder tokens, {bs} samples per task), bs={bs}, bf16")
+    return f"BART-base + VL-PET-large r={r}, image-text multitask synthetic {ratios}, bs={bs}, bf16"
+
+
+def resolve_config(a):
+    """Fill --batch-size / --rank-r from the BASELINE config and return (tasks, feat_dim, grid, vocab_hi)."""
+    defaults = {2: (300, 96), 3: (300, 96), 4: (512, 4), 5: (128, 96)}[a.config]
+    if a.batch_size is None:
+        a.batch_size = defaults[0]
+    if a.rank_r is None:
+        a.rank_r = defaults[1]
+    if a.config == 5:
+        return ["tvqa", "how2qa", "tvc", "yc2c"], 512, 64, 50000
+    return TASKS, 2048, 49, (32000 if a.config == 3 else 50000)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -137,7 +160,7 @@ def _host_info():
     return {"cpu": model, "os_cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads(), "torch": torch.__version__}
 
 
-def cpu_reference_run(steps, warmup, bs, r, sample_bs=None, budget_s=150.0, threads=None):
+def cpu_reference_run(steps, warmup, bs, r, sample_bs=None, budget_s=175.0, threads=None):
     """Times `steps` optimizer steps (fwd + bwd + clip + AdamW, dropout 0.1, fp32 eager, all host cores) of the reference on
     the task cycle.  The per-step batch is the workload's (--batch-size bs) when it fits `budget_s`, else the largest
     bounded sample that does (measured from one probe step).  -> dict(value, ms_per_step, cores, kind, sample, ...)."""
@@ -227,6 +250,9 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    resolve_config(a)
+    if a.config != 2:
+        raise SystemExit("bench.py --impl reference: the reference arm runs the metric's config (2)")
     res = cpu_reference_run(a.steps, max(1, min(a.warmup, 2)), a.batch_size, a.rank_r, sample_bs=a.ref_batch_size)
     v = res["value"]
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": a.gpus,
@@ -331,15 +357,27 @@ def run_ours(a):
     import vlpet_b200.host as H
 
     torch.manual_seed(0)
-    cfg = H.bart_base_vlpet_large(r=a.rank_r, rg=a.rank_r, dec_r=a.rank_r, assume_no_padding=True)
-    model = H.VLBart(cfg).train()
+    tasks, feat_dim, grid, vocab_hi = resolve_config(a)
+    if a.config == 3:
+        cfg = H.t5_base_vlpet_large(r=a.rank_r, rg=a.rank_r, dec_r=a.rank_r, assume_no_padding=True)
+        model = H.VLT5(cfg).train()
+    elif a.config == 4:
+        cfg = H.bart_base_vlpet_small(r=a.rank_r, dec_r=a.rank_r, assume_no_padding=True)
+        model = H.VLBart(cfg).train()
+    elif a.config == 5:
+        cfg = H.bart_base_vlpet_large_video(r=a.rank_r, rg=a.rank_r, dec_r=a.rank_r, assume_no_padding=True)
+        model = H.VLBart(cfg).train()
+    else:
+        cfg = H.bart_base_vlpet_large(r=a.rank_r, rg=a.rank_r, dec_r=a.rank_r, assume_no_padding=True)
+        model = H.VLBart(cfg).train()
     total_steps = 20 * 1000
     Trainer = H.GraphedPetTrainer if a.graphs else H.PetTrainer
-    trainer = Trainer(model, cfg, dev, lr=1e-3, total_steps=total_steps)
+    trainer = Trainer(model, cfg, dev, lr=3e-4 if a.config == 3 else 1e-3, total_steps=total_steps)
     trainer.set_step(total_steps // 10)           # past warm-up: a non-zero learning rate
-    host_cycle = H.multitask_cycle(a.batch_size, TASKS, seed=0, pin=True, rank=rank, world=world)
+    host_cycle = H.multitask_cycle(a.batch_size, tasks, feat_dim=feat_dim, seed=0, pin=True, rank=rank, world=world,
+                                   vocab_hi=vocab_hi, grid=grid)
     dev_cycle = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()} for b in host_cycle]
-    global_sizes = H.task_batch_sizes(a.batch_size)
+    global_sizes = H.task_batch_sizes(a.batch_size, tasks)
     nb = len(dev_cycle)
 
     def sync_all():
@@ -373,7 +411,7 @@ def run_ours(a):
     n0 = trainer.launch_counter()
     ms = timed(step_resident, a.steps)
     launches = trainer.launch_counter() - n0
-    samples = sum(global_sizes[TASKS[i % nb]] for i in range(a.steps))
+    samples = sum(global_sizes[tasks[i % nb]] for i in range(a.steps))
     value = samples / (ms * 1e-3)
 
     # ---- end-to-end leg: host (pinned) batch -> device every step, loss read back every step
@@ -421,20 +459,21 @@ def run_ours(a):
             dist.destroy_process_group()
         return
     micro = None
-    if not a.no_micro and world == 1:
+    if not a.no_micro and world == 1 and a.config == 2:
         micro = k1_micro(V, F_, peak)
     ref_gpu = None
-    if world == 1 and not a.no_ref_eager:
+    if world == 1 and not a.no_ref_eager and a.config == 2:
         ref_gpu = reference_eager_b200(a, dev, host_cycle, global_sizes)
     cpu = None
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and a.config == 2:
         res = cpu_reference_run(4, 1, a.batch_size, a.rank_r, sample_bs=CPU_SAMPLE_BS)
         cpu = {"value": round(res["value"], 3), "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"],
                "host": res["host"], "isolated_pet": cpu_isolated_pet()}
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(a.batch_size, a.rank_r), "global_batch_per_task": global_sizes,
+            "config": {"workload": workload_name(a.batch_size, a.rank_r, a.config), "baseline_config": a.config,
+                       "global_batch_per_task": global_sizes,
                        "parallelism": f"dp{world} (batch sharded by sample, 1 all-reduce of {trainer.bucket.n_trainable} PET grads/step)",
                        "l2": "per-step working set (weights + activations) exceeds the 126 MB L2; no explicit flush",
                        "trainable_params": trainer.bucket.n_trainable, "optimizer": "fused AdamW on the flat PET bucket",

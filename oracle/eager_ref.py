@@ -66,6 +66,34 @@ def eager_encoder_pet(layer, site: str, x1, x2):
     return x1 + h
 
 
+def eager_encoder_pet_t5(layer, site: str, x1, x2):
+    """One encoder PET site as T5LayerSelfAttention.forward / T5LayerFF.forward run it inline
+    (my_transformers/modeling_t5.py:777-824, 359-409): optional adapter / x2 scales, no add-gate, no LayerNorm behind."""
+    cfg = layer.config
+    g = lambda n, d=False: getattr(cfg, n, d)  # noqa: E731
+    down = getattr(layer, f"{site}_adapter_multihead_down")
+    up = getattr(layer, f"{site}_adapter_multihead_up")
+    stem = f"encoder_{site}_adapter_gating"
+    u = up(gelu_new(torch.cat([down[i](x2) for i in range(len(down))], dim=-1)))
+    if g("use_encoder_adapter_scaling"):
+        u = u * g("encoder_adapter_scaling_factor", 1.0)
+    y = x2 * g("encoder_x2_scaling_factor", 1.0) if g("use_encoder_x2_scaling") else x2
+    y = y + u
+    if g("use_encoder_adapter_gating_large_x_lowrank"):
+        gate = torch.sigmoid(getattr(layer, stem + "_large_x_up")(gelu_new(getattr(layer, stem + "_large_x_down")(x1))))
+        y = y * gate
+    elif g("use_encoder_adapter_gating_small_xy_cat"):
+        gate = torch.sigmoid(getattr(layer, stem + "_small_xy_cat")(torch.cat([x1, y], dim=2)))
+        y = y * torch.mean(gate, dim=1).unsqueeze(-1)
+    elif g("use_encoder_adapter_gating_middle_xy_add"):
+        y = y * torch.sigmoid(getattr(layer, stem + "_middle_xy_add")(x1 + y))
+    elif g("use_encoder_adapter_gating_middle_ia3_add"):
+        y = y + y * getattr(layer, stem + "_middle_ia3_add")
+    if g("use_encoder_gating_scaling"):
+        y = y * g("encoder_gating_scaling_factor", 1.0)
+    return x1 + F.dropout(y, p=layer.dropout, training=layer.training)
+
+
 def eager_adapter_controller_forward(self, inputs, task, y=None):
     adapter = self.adapters[task]
     z = self.pre_layer_norm(inputs) if self.add_layer_norm_before_adapter else inputs
@@ -104,6 +132,9 @@ def use_eager_pet(model):
         cls = type(m).__name__
         if cls == "BartEncoderLayer" and hasattr(m, "attn_adapter_multihead_down"):
             m._pet = types.MethodType(lambda self, site, x1, x2: eager_encoder_pet(self, site, x1, x2), m)
+            n += 1
+        elif cls in ("T5LayerSelfAttention", "T5LayerFF") and hasattr(m, "_vlpet_site_cfg"):
+            m._pet = types.MethodType(lambda self, site, x1, x2: eager_encoder_pet_t5(self, site, x1, x2), m)
             n += 1
         elif cls == "AdapterController":
             m.forward = types.MethodType(eager_adapter_controller_forward, m)

@@ -256,6 +256,44 @@ def test_k1_fused_backward_matches_oracle(V, M, d, r, rg, add_gate, s, alpha, ka
             assert np.max(np.abs(v - g_r[k].reshape(np.shape(v)))) < 2e-3 * np.max(np.abs(g_r[k])), k
 
 
+@pytest.mark.parametrize("M", [129, 16000])
+def test_k1_bf16_error_is_no_worse_than_the_reference_run_in_bf16(V, M):
+    """Pins the bf16 bar instead of arguing it (round-1 verdict): on identical bf16 inputs / bf16-representable weights,
+    the error of the fused kernels against the exact fp64 evaluation must not exceed the error of the REFERENCE op
+    sequence (oracle/eager_ref.isolated_pet_step: per-head Linears + cat, un-fused gelu_new, sigmoid -- what
+    my_transformers/modeling_bart.py:1149-1155, 1196-1209, 1260 issue) run by stock PyTorch in bf16 autocast with fp32
+    master weights (the only bf16 mode a reference user has: `torch.autocast`, multitask.py:229-234).  Checked for out,
+    dx1, dx2 and all 8 parameter gradients at d = 768, r = 96."""
+    from oracle.eager_ref import isolated_pet_step
+    d, r = 768, 96
+    rng = np.random.default_rng(M)
+    x1, x2, dout, p = random_large_case(rng, M, d, r, r)
+    cfg = O.PetConfig(gate="large")
+    out, dx1, dx2, gr = run_k1(V, x1, x2, dout, p, cfg, 4, torch.bfloat16, "auto", (1, M, d))
+    x1r, x2r, dor = bf16_round(x1), bf16_round(x2), bf16_round(dout)
+    pr = {k: bf16_round(v).reshape(np.shape(v)) for k, v in p.items()}
+    ref_out, cx = O.gated_pet_fwd(x1r, x2r, pr, cfg)
+    x_dx1, x_dx2, g_x = O.gated_pet_bwd(dor, pr, cfg, cx)
+    # the reference sequence in bf16 autocast on the same device
+    bf = torch.bfloat16
+    t1, t2 = dev(x1, bf).requires_grad_(), dev(x2, bf).requires_grad_()
+    P = {k: dev(pr[k], torch.float32).requires_grad_() for k in ("Wd", "bd", "Wu", "bu", "Gd", "gbd", "Gu", "gbu")}
+    with torch.autocast("cuda", dtype=bf):
+        o_ref = isolated_pet_step(t1, t2, dev(dout, bf), P, nheads=4)
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    cols = {"out": (out, f(o_ref).reshape(M, d), ref_out), "dx1": (dx1, f(t1.grad).reshape(M, d), x_dx1),
+            "dx2": (dx2, f(t2.grad).reshape(M, d), x_dx2)}
+    for k in P:
+        cols["d" + k] = (gr[k], f(P[k].grad).reshape(np.shape(gr[k])), g_x[k].reshape(np.shape(gr[k])))
+    worse = []
+    for name, (ours, theirs, exact) in cols.items():
+        e_o, e_r = rel(ours, exact), rel(theirs, exact)
+        print(f"{name:5s}: ours {e_o:.2e}   reference-bf16 {e_r:.2e}")
+        if e_o > 1.05 * e_r + 1e-6:
+            worse.append((name, e_o, e_r))
+    assert not worse, worse
+
+
 def test_k1_fused_backward_accumulates_and_matches_generic(V):
     """Weight gradients are ACCUMULATED into the caller's buffers (C-ABI contract); fused vs generic CUDA path."""
     M, d, r = 900, 768, 96

@@ -160,3 +160,77 @@ def test_trainer_bucket_gradients_match_reference_vlbart(H):
                 assert rel(got, z[f"{task}/grad/{n}"].reshape(-1)) < 2e-4, (task, n)
     finally:
         F_.set_direct_grad_accumulation(False)
+
+
+# ------------------------------------------------------------------------------------------ T5 (BASELINE config 3)
+def _load_t5():
+    return np.load(os.path.join(GOLDEN, "vlt5_tiny_large.npz"), allow_pickle=False)
+
+
+def _t5_cfg(H, **kw):
+    return H.tiny_t5_test_config(dropout_rate=0.0, dropout=0.0, **kw)
+
+
+def test_t5_state_dict_names_and_trainable_set_match_reference(H):
+    z = _load_t5()
+    model = H.VLT5(_t5_cfg(H))
+    _load_state(model, z, torch.float32)
+    assert sorted(H.trainable_names(model, model.config)) == sorted(str(n) for n in z["meta_trainable"])
+
+
+def test_host_model_matches_reference_vlt5_cpu(H):
+    """The reference's own VLT5 (tests/golden/make_golden_vlt5.py: T5-VL-PET-large flags, gate scale 0.3) against
+    host.VLT5 with the eager T5 PET restatement on the sites: loss and every trainable gradient.  The model is fp64, but the
+    reference's T5Attention takes its softmax in float32 (`F.softmax(scores.float())`, my_transformers/modeling_t5.py:655)
+    and T5LayerNorm its variance (235-252), so the golden itself carries ~1e-8 of fp32 noise: bars 1e-7 / 2e-6."""
+    from oracle.eager_ref import use_eager_pet
+    z = _load_t5()
+    model = use_eager_pet(H.VLT5(_t5_cfg(H)).double().eval())
+    _load_state(model, z, torch.float64)
+    names = [str(n) for n in z["meta_trainable"]]
+    params = dict(model.named_parameters())
+    for task in ("vqa", "nlvr"):
+        model.zero_grad()
+        loss = model.train_step(_batch(z, task, torch.float64))["loss"]
+        loss.backward()
+        assert abs(loss.item() - float(z[f"{task}/loss"])) < 1e-7, (loss.item(), float(z[f"{task}/loss"]))
+        for n in names:
+            assert rel(params[n].grad.numpy(), z[f"{task}/grad/{n}"]) < 2e-6, (task, n)
+
+
+def test_t5_base_trainable_count_is_the_reference_checksum(H):
+    """T5-base + VL-PET-large at r = rg = dec_r = 96 (BASELINE config 3): 10 499 712 trainable parameters, the count obtained
+    by instantiating the reference VLT5."""
+    cfg = H.t5_base_vlpet_large()
+    with torch.device("meta"):
+        model = H.VLT5(cfg)
+    names = set(H.trainable_names(model, cfg))
+    assert sum(p.numel() for k, p in model.named_parameters() if k in names) == 10499712
+
+
+@pytest.mark.gpu
+def test_host_t5_with_cuda_pet_matches_reference_vlt5(H):
+    """T5 PET sites (K1 with s = 0.3, no LayerNorm behind), the T5 value parallel adapter (K2) and the RMS-norm visual
+    projection (K3) through the CUDA kernels inside host.VLT5, against the reference VLT5 golden (fp32)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import vlpet_b200 as V
+    z = _load_t5()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model = H.VLT5(_t5_cfg(H)).eval()
+    _load_state(model, z, torch.float32)
+    model.cuda()
+    names = [str(n) for n in z["meta_trainable"]]
+    params = dict(model.named_parameters())
+    for n in names:
+        params[n].requires_grad_(True)
+    n0 = V.launch_count()
+    for task in ("vqa", "nlvr"):
+        model.zero_grad()
+        loss = model.train_step(_batch(z, task, torch.float32))["loss"]
+        loss.backward()
+        assert abs(loss.item() - float(z[f"{task}/loss"])) < 5e-5 * abs(float(z[f"{task}/loss"]))
+        for n in names:
+            assert rel(params[n].grad.double().cpu().numpy(), z[f"{task}/grad/{n}"]) < 5e-4, (task, n)
+    assert V.launch_count() - n0 >= 2 * (2 * 2 * 2 + 2 + 1), "PET sites did not run the CUDA kernels"

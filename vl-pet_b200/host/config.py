@@ -61,6 +61,16 @@ class VLPetConfig:
     decoder_enc_attn_value_parallel_adapter_down_dim: int = 96
     use_single_adapter: bool = True
     freeze_vis_emb: bool = False
+    # ---- T5-base (t5-base config.json; vocab 32 100 + 100 <vis_extra_id> tokens, tokenization.py:58-60); used when arch == "t5"
+    arch: str = "bart"
+    d_kv: int = 64
+    d_ff: int = 3072
+    num_layers: int = 12
+    num_decoder_layers: int = 12
+    num_heads: int = 12
+    relative_attention_num_buckets: int = 32
+    layer_norm_epsilon: float = 1e-6
+    dropout_rate: float = 0.1
     # ---- host-side execution policy (ours)
     assume_no_padding: bool = False   # synthetic batches carry no pad tokens: skip building attention masks
     pet_impl: str = "auto"            # forward kernel selection passed to the C ABI
@@ -87,6 +97,38 @@ def bart_base_vlpet_large(r: int = 96, heads: int = 4, rg: int = 96, dec_r: int 
     """BASELINE config 2: BART-base + VL-PET-large (script arguments `96 4 96 96`)."""
     return VLPetConfig(adapter_down_dim=r, encoder_adapter_multihead_num_head=heads, adapter_gating_down_dim=rg,
                        decoder_enc_attn_value_parallel_adapter_down_dim=dec_r).clone(**kw)
+
+
+def t5_base_vlpet_large(r: int = 96, heads: int = 4, rg: int = 96, dec_r: int = 96, s: float = 0.3, **kw) -> VLPetConfig:
+    """BASELINE config 3: T5-base + VL-PET-large at r = rg = 96 (scripts/image-text/T5-VL-PET-large.sh:41-58 with the
+    ranks BASELINE.json names; the script's own `192 4 192 96` is a legal value of the same flags), gate scale 0.3."""
+    return VLPetConfig(arch="t5", vocab_size=32200, pad_token_id=0, decoder_start_token_id=0, eos_token_id=1,
+                       adapter_down_dim=r, encoder_adapter_multihead_num_head=heads, adapter_gating_down_dim=rg,
+                       decoder_enc_attn_value_parallel_adapter_down_dim=dec_r, use_encoder_gating_scaling=True,
+                       encoder_gating_scaling_factor=s).clone(**kw)
+
+
+def bart_base_vlpet_small(r: int = 4, heads: int = 4, dec_r: int = 4, **kw) -> VLPetConfig:
+    """BASELINE config 4: BART-base + VL-PET-small (scripts/image-text/VL-PET-small.sh flag set) at rank 4."""
+    return VLPetConfig(adapter_down_dim=r, encoder_adapter_multihead_num_head=heads, use_encoder_adapter_gating_large_x_lowrank=False,
+                       use_encoder_adapter_gating_small_xy_cat=True, decoder_enc_attn_value_parallel_adapter_down_dim=dec_r).clone(**kw)
+
+
+def bart_base_vlpet_large_video(r: int = 96, heads: int = 4, rg: int = 96, dec_r: int = 96, **kw) -> VLPetConfig:
+    """BASELINE config 5: BART-base + VL-PET-large on the video-text multitask (scripts/video-text/VL-PET-large.sh:
+    --feat_dim 512 --n_boxes 64 --downsample (an 8x8 -> 8x8 no-op), tasks tvqa / how2qa / tvc / yc2c)."""
+    return VLPetConfig(adapter_down_dim=r, encoder_adapter_multihead_num_head=heads, adapter_gating_down_dim=rg,
+                       decoder_enc_attn_value_parallel_adapter_down_dim=dec_r, feat_dim=512, n_boxes=64,
+                       tasks=["tvqa", "how2qa", "tvc", "yc2c"]).clone(**kw)
+
+
+def tiny_t5_test_config(**kw) -> VLPetConfig:
+    """2+2-layer d=64 T5 used by the parity test against the reference's VLT5 (tests/golden/vlt5_tiny_large.npz)."""
+    return VLPetConfig(arch="t5", vocab_size=300, pad_token_id=0, decoder_start_token_id=0, eos_token_id=1, d_model=64, d_kv=16,
+                       d_ff=128, num_layers=2, num_decoder_layers=2, num_heads=4, feat_dim=128, adapter_down_dim=16,
+                       encoder_adapter_multihead_num_head=4, adapter_gating_down_dim=16,
+                       decoder_enc_attn_value_parallel_adapter_down_dim=16, use_encoder_gating_scaling=True,
+                       encoder_gating_scaling_factor=0.3).clone(**kw)
 
 
 def tiny_test_config(**kw) -> VLPetConfig:

@@ -11,11 +11,17 @@ import torch
 
 # task -> (text length, answer/target length, images per sample); text 20 tokens (--max_text_length 20), caption
 # prompts are short and its targets up to 40 tokens (multitask.py:682-695)
-TASK_SHAPES = {"vqa": (20, 5, 1), "gqa": (20, 5, 1), "nlvr": (20, 3, 2), "caption": (4, 40, 1)}
-_TASK_INDEX = {"vqa": 0, "gqa": 1, "nlvr": 2, "caption": 3}
+TASK_SHAPES = {"vqa": (20, 5, 1), "gqa": (20, 5, 1), "nlvr": (20, 3, 2), "caption": (4, 40, 1),
+               # video-text multitask (multitask_video.py:738-743: 64 CLIP-ViT frame features of width 512, text up to 600
+               # tokens -- fixed at 256 here so that text + frames = 320 tokens, targets <= 20; equal batch per task)
+               "tvqa": (256, 20, 1), "how2qa": (256, 20, 1), "tvc": (256, 20, 1), "yc2c": (256, 20, 1)}
+_TASK_INDEX = {"vqa": 0, "gqa": 1, "nlvr": 2, "caption": 3, "tvqa": 4, "how2qa": 5, "tvc": 6, "yc2c": 7}
+VIDEO_TASKS = ["tvqa", "how2qa", "tvc", "yc2c"]
 
 
-def task_batch_sizes(batch_size: int) -> Dict[str, int]:
+def task_batch_sizes(batch_size: int, tasks=None) -> Dict[str, int]:
+    if tasks is not None and all(t in VIDEO_TASKS for t in tasks):
+        return {t: batch_size for t in tasks}               # multitask_video.py:740-743: no ratio scaling
     return {"vqa": batch_size, "gqa": int(batch_size * 100 / 60), "nlvr": int(batch_size * 20 / 60),
             "caption": int(batch_size * 50 / 60)}
 
@@ -37,7 +43,7 @@ def make_task_batch(task: str, B: int, feat_dim: int = 2048, grid: int = 49, see
         feats = torch.randn(B, grid, feat_dim, generator=g)
         boxes = torch.zeros(B, grid, 4)
     batch = {"task": task, "input_ids": ids, "vis_feats": feats, "boxes": boxes, "target_ids": tgt}
-    if task in ("vqa", "gqa"):
+    if task in ("vqa", "gqa", "tvqa", "how2qa"):
         batch["scores"] = torch.ones(B)
     if pin:
         batch = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
@@ -45,13 +51,13 @@ def make_task_batch(task: str, B: int, feat_dim: int = 2048, grid: int = 49, see
 
 
 def multitask_cycle(batch_size: int, tasks: List[str], feat_dim: int = 2048, seed: int = 0, pin: bool = False,
-                    rank: int = 0, world: int = 1, vocab_hi: int = 50000) -> List[Dict]:
+                    rank: int = 0, world: int = 1, vocab_hi: int = 50000, grid: int = 49) -> List[Dict]:
     """One round-robin cycle over ``tasks`` at the reference ratios; with world > 1 each batch is this rank's
     contiguous shard of the GLOBAL task batch (strong scaling: the global batch is fixed)."""
-    sizes = task_batch_sizes(batch_size)
+    sizes = task_batch_sizes(batch_size, tasks)
     out = []
     for t in tasks:
-        gb = make_task_batch(t, sizes[t], feat_dim=feat_dim, seed=seed, vocab_hi=vocab_hi)
+        gb = make_task_batch(t, sizes[t], feat_dim=feat_dim, seed=seed, vocab_hi=vocab_hi, grid=grid)
         b = shard_batch(gb, rank, world)
         if pin:
             b = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}

@@ -454,7 +454,7 @@ class VLBart(nn.Module):
         T = labels.shape[1]
         mask = (labels != -100).float()
         loss = loss.view(B, T) * mask
-        if task == "caption":                                    # caption_model.py: sum / count over the whole batch
+        if task in ("caption", "tvc", "yc2c"):                   # caption_model.py: sum / count over the whole batch
             loss = loss.sum() / mask.sum().clamp(min=1)
         else:
             loss = loss.sum(dim=1) / mask.sum(dim=1).clamp(min=1)
