@@ -119,7 +119,9 @@ VLPET_API int vlpet_k1_fwd(const VlpetK1Desc* desc, const void* x1, const void* 
 VLPET_API int vlpet_k1_bwd(const VlpetK1Desc* desc, const void* x1, const void* x2, const void* dout,
                  const VlpetK1Params* w, void* dx1, void* dx2, const VlpetK1Grads* g, void* workspace,
                  size_t workspace_bytes, void* stream);
-/* 1 if vlpet_k1_fwd / _bwd would run the fused tcgen05 kernel for this desc under VLPET_IMPL_AUTO */
+/* Which path vlpet_k1_fwd / _bwd take for this desc under VLPET_IMPL_AUTO: 1 = the fused tcgen05 kernels (large gate, ungated
+ * form), 2 = the row-wise gate kernels (middleX / middleY / small gates -- composed with the tcgen05 adapter kernel at tensor-core
+ * ranks -- and ranks <= 16 in one launch; csrc/vlpet_rows.cu), 0 = the generic CUDA-core path (fp32, odd shapes) */
 VLPET_API int vlpet_k1_fwd_is_fused(const VlpetK1Desc* desc);
 VLPET_API int vlpet_k1_bwd_is_fused(const VlpetK1Desc* desc);
 

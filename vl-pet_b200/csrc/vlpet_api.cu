@@ -58,6 +58,8 @@ int check_k1(const VlpetK1Desc* D, const VlpetK1Params* w) {
 }
 bool use_fused_fwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && fused_k1_fwd_supported(D); }
 bool use_fused_bwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && fused_k1_bwd_supported(D); }
+bool use_rows_fwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && !use_fused_fwd(D) && rows_k1_supported(D, false); }
+bool use_rows_bwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && !use_fused_bwd(D) && rows_k1_supported(D, true); }
 }  // namespace
 }  // namespace vlpet
 
@@ -81,16 +83,16 @@ int vlpet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
 }
 
 // ---- K1 ----------------------------------------------------------------------------------------------------
-int vlpet_k1_fwd_is_fused(const VlpetK1Desc* D) { return D && use_fused_fwd(*D) ? 1 : 0; }
-int vlpet_k1_bwd_is_fused(const VlpetK1Desc* D) { return D && use_fused_bwd(*D) ? 1 : 0; }
+int vlpet_k1_fwd_is_fused(const VlpetK1Desc* D) { return !D ? 0 : (use_fused_fwd(*D) ? 1 : (use_rows_fwd(*D) ? 2 : 0)); }
+int vlpet_k1_bwd_is_fused(const VlpetK1Desc* D) { return !D ? 0 : (use_fused_bwd(*D) ? 1 : (use_rows_bwd(*D) ? 2 : 0)); }
 
 size_t vlpet_k1_fwd_workspace_bytes(const VlpetK1Desc* D) {
   if (!D) return 0;
-  return use_fused_fwd(*D) ? fused_k1_fwd_ws(*D) : generic_k1_fwd_ws(*D);
+  return use_fused_fwd(*D) ? fused_k1_fwd_ws(*D) : (use_rows_fwd(*D) ? rows_k1_fwd_ws(*D) : generic_k1_fwd_ws(*D));
 }
 size_t vlpet_k1_bwd_workspace_bytes(const VlpetK1Desc* D) {
   if (!D) return 0;
-  return use_fused_bwd(*D) ? fused_k1_bwd_ws(*D) : generic_k1_bwd_ws(*D);
+  return use_fused_bwd(*D) ? fused_k1_bwd_ws(*D) : (use_rows_bwd(*D) ? rows_k1_bwd_ws(*D) : generic_k1_bwd_ws(*D));
 }
 
 int vlpet_k1_fwd(const VlpetK1Desc* D, const void* x1, const void* x2, const VlpetK1Params* w, void* out, void* ws,
@@ -100,6 +102,7 @@ int vlpet_k1_fwd(const VlpetK1Desc* D, const void* x1, const void* x2, const Vlp
   if (!aligned16(x1) || !aligned16(x2) || !aligned16(out)) return fail(VLPET_E_ALIGN, "k1_fwd: activations must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_fused_fwd(*D)) return fused_k1_fwd(*D, x1, x2, *w, out, ws, ws_bytes, st);
+  if (use_rows_fwd(*D)) return rows_k1_fwd(*D, x1, x2, *w, out, ws, ws_bytes, st);
   if (D->impl == VLPET_IMPL_FUSED)
     return fail(VLPET_E_UNSUPPORTED, "k1_fwd: fused kernel does not cover d=%d r=%d rg=%d gate=%d dtype=%d", D->d, D->r,
                 D->rg, D->gate, D->dtype);
@@ -114,6 +117,8 @@ int vlpet_k1_bwd(const VlpetK1Desc* D, const void* x1, const void* x2, const voi
     return fail(VLPET_E_ALIGN, "k1_bwd: activations must be 16-byte aligned");
   if (use_fused_bwd(*D))
     return fused_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  if (use_rows_bwd(*D))
+    return rows_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
   if (D->impl == VLPET_IMPL_FUSED)
     return fail(VLPET_E_UNSUPPORTED, "k1_bwd: fused kernel does not cover d=%d r=%d rg=%d gate=%d dtype=%d", D->d, D->r,
                 D->rg, D->gate, D->dtype);

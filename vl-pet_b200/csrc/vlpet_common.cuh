@@ -163,6 +163,21 @@ int fused_k2_fwd(const VlpetK2Desc&, const void* kv, const void* y, const VlpetK
 int fused_k2_bwd(const VlpetK2Desc&, const void* kv, const void* dout, const VlpetK2Params&, void* dkv, const VlpetK2Grads&,
                  void* ws, size_t ws_bytes, cudaStream_t);
 
+// same with the x2 scale of the K1 form: dkv = kappa * dout + adapter-path gradient (the row-wise gate path, vlpet_rows.cu)
+int fused_k2_bwd_kappa(const VlpetK2Desc&, float kappa, const void* kv, const void* dout, const VlpetK2Params&, void* dkv,
+                       const VlpetK2Grads&, void* ws, size_t ws_bytes, cudaStream_t);
+// column sums of a [M, pitch] bf16 matrix (first ncols columns) accumulated into out[ncols] (vlpet_k1_bwd_sm100.cu)
+int colsum_bf16(const void* A, int pitch, int ncols, float* out, int64_t M, int sms, cudaStream_t st);
+
+// ---- row-wise K1 (middleX / middleY / small gates, ungated form, ranks <= 16), vlpet_rows.cu -----------------------
+bool rows_k1_supported(const VlpetK1Desc&, bool bwd);
+size_t rows_k1_fwd_ws(const VlpetK1Desc&);
+size_t rows_k1_bwd_ws(const VlpetK1Desc&);
+int rows_k1_fwd(const VlpetK1Desc&, const void* x1, const void* x2, const VlpetK1Params&, void* out, void* ws, size_t ws_bytes,
+                cudaStream_t);
+int rows_k1_bwd(const VlpetK1Desc&, const void* x1, const void* x2, const void* dout, const VlpetK1Params&, void* dx1, void* dx2,
+                const VlpetK1Grads&, void* ws, size_t ws_bytes, cudaStream_t);
+
 // ---- token-contracted weight-gradient GEMM (tcgen05), vlpet_wgrad_sm100.cu -----------------------------------
 bool wgrad_sm100_supported(int d, int nout);
 int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void* const* B, const int64_t* ldb,

@@ -249,6 +249,9 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             } else if (GATED) {
               ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), XCH_BYTES);
               ptx::tma_load_2d_hint(xdst, &tm_dout, c * CH, row0, bar(B_XFULL + sx), ptx::L2_EVICT_FIRST);
+            } else if (p.kappa != 0.f) {             // ungated with an x2 scale: dx2 = kappa dout + da Wd needs dout_c again
+              ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), XCH_BYTES);
+              ptx::tma_load_2d_hint(xdst, &tm_dout, c * CH, row0, bar(B_XFULL + sx), ptx::L2_EVICT_FIRST);
             } else {
               ptx::mbar_arrive(bar(B_XFULL + sx));   // the stage is only the staging buffer of dx2_c
             }
@@ -680,7 +683,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           constexpr bool DROP = decltype(drop_tag)::value;
           const uint32_t off = (((uint32_t)(cg * 2 + g)) ^ swz) << 4;
           uint32_t dv[4] = {0, 0, 0, 0}, o1[4], o2[4];
-          if (GATED) lds128(dorow + off, dv);
+          const bool ungated_kappa = !GATED && p.kappa != 0.f;
+          if (GATED || ungated_kappa) lds128(dorow + off, dv);
           f2 hgb[4] = {0, 0, 0, 0};
           if (GATED && mulgate) {
             lds_f2x2(thgb + g * 32, hgb[0], hgb[1]);
@@ -710,7 +714,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
               o2[e] = pack2(fma2(kappa2, dy1, g2p));                                 // dx2 = kappa dy1 + da Wd
               o1[e] = pack2(add2(dof, mk2u(g1[j], g1[j + 1])));                      // dx1 = dout + dp Gd
             } else {
-              o2[e] = pack2(g2p);
+              o2[e] = pack2(ungated_kappa ? fma2(kappa2, bf2_to_f2(dv[e]), g2p) : g2p);
               o1[e] = 0u;
             }
           }
@@ -1004,6 +1008,9 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
 
 }  // namespace
 
+int colsum_bf16(const void* A, int pitch, int ncols, float* out, int64_t M, int sms, cudaStream_t st) {
+  return launch_colsum_scratch(static_cast<const __nv_bfloat16*>(A), pitch, ncols, out, nullptr, 0, 0, nullptr, M, sms, st);
+}
 int set_k1_bwd_parts(int parts) {
   g_bwd_parts = parts;
   return 0;
@@ -1053,6 +1060,21 @@ int fused_k2_fwd(const VlpetK2Desc& D, const void* kv, const void* y, const Vlpe
   memset(&P, 0, sizeof(P));
   P.Wd = w.Wd; P.bd = w.bd; P.Wu = w.Wu; P.bu = w.bu;
   return fused_k1_fwd(k2_as_k1(D), y, kv, P, out, nullptr, 0, st);
+}
+
+int fused_k2_bwd_kappa(const VlpetK2Desc& D, float kappa, const void* kv, const void* dout, const VlpetK2Params& w, void* dkv,
+                       const VlpetK2Grads& g, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!aligned16(w.Wd) || !aligned16(w.Wu) || !aligned16(w.bu))
+    return fail(VLPET_E_ALIGN, "k2_bwd(fused): weights must be 16-byte aligned");
+  VlpetK1Params P;
+  memset(&P, 0, sizeof(P));
+  P.Wd = w.Wd; P.bd = w.bd; P.Wu = w.Wu; P.bu = w.bu;
+  VlpetK1Grads G;
+  memset(&G, 0, sizeof(G));
+  G.dWd = g.dWd; G.dbd = g.dbd; G.dWu = g.dWu; G.dbu = g.dbu;
+  VlpetK1Desc K = k2_as_k1(D);
+  K.kappa = kappa;
+  return run_bwd(false, K, nullptr, kv, dout, P, nullptr, dkv, G, ws, ws_bytes, st);
 }
 
 int fused_k2_bwd(const VlpetK2Desc& D, const void* kv, const void* dout, const VlpetK2Params& w, void* dkv,
