@@ -38,6 +38,7 @@ struct RowsArgs {
   const __nv_bfloat16 *Wd, *bd, *Wu, *bu, *gw, *gb, *gz;
   float *gmean, *dgsum;                                // [B] per-sample gate mean / dG sum (small gate)
   float *dgw, *dgb, *dgz;                              // fp32 gate gradients, accumulated into
+  float* dbd;                                          // INLINE backward: fp32 down-projection bias gradient, accumulated into
 };
 
 __device__ __forceinline__ float bf2f(uint32_t v, int hi) { return __uint_as_float(hi ? (v & 0xffff0000u) : (v << 16)); }
@@ -226,6 +227,9 @@ __global__ void __launch_bounds__(RW_THREADS) rows_bwd_kernel(const RowsArgs p) 
   float acc_g[2 * NE], acc_b = 0.f;     // gate-parameter gradients of the rows this warp handles
 #pragma unroll
   for (int e = 0; e < 2 * NE; ++e) acc_g[e] = 0.f;
+  float acc_da[RW_MAXR];                // dbd = sum over rows of da, kept in fp32 (the bf16 da scratch only feeds the GEMM)
+#pragma unroll
+  for (int j = 0; j < RW_MAXR; ++j) acc_da[j] = 0.f;
   const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
   const int64_t nw = (int64_t)gridDim.x * (RW_THREADS / 32);
   for (int64_t row = (int64_t)blockIdx.x * (RW_THREADS / 32) + warp; row < p.M; row += nw) {
@@ -302,6 +306,7 @@ __global__ void __launch_bounds__(RW_THREADS) rows_bwd_kernel(const RowsArgs p) 
         for (int e = 0; e < 8; ++e) dz = fmaf(du[ch * 8 + e], w[e], dz);
       }
       const float da = warp_sum(dz) * gelu_new_grad_f(S.a[j]);
+      acc_da[j] += da;
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         float w[8];
@@ -316,6 +321,11 @@ __global__ void __launch_bounds__(RW_THREADS) rows_bwd_kernel(const RowsArgs p) 
     }
     store_row<NCH>(p.dx2 + row * p.d, lane, dx2);
     store_row<NCH>(p.du + row * p.d, lane, du);
+  }
+  if (!p.has_y1 && p.dbd && lane == 0 && !(GATE == VLPET_GATE_SMALL && p.pass == 0)) {
+#pragma unroll
+    for (int j = 0; j < RW_MAXR; ++j)
+      if (j < p.r) atomicAdd(p.dbd + j, acc_da[j]);
   }
   // ---- gate-parameter gradients: lanes own distinct columns; reduce over the CTA's warps in shared memory, then one
   //      atomicAdd per column and CTA
@@ -508,7 +518,7 @@ int rows_k1_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const void
   a.x1 = static_cast<const __nv_bfloat16*>(x1); a.x2 = static_cast<const __nv_bfloat16*>(x2);
   a.dout = static_cast<const __nv_bfloat16*>(dout);
   a.dx1 = static_cast<__nv_bfloat16*>(dx1); a.dx2 = static_cast<__nv_bfloat16*>(dx2);
-  a.dgw = G.dgw; a.dgb = G.dgb; a.dgz = G.dgz;
+  a.dgw = G.dgw; a.dgb = G.dgb; a.dgz = G.dgz; a.dbd = G.dbd;
   VlpetK1Params P;
   memset(&P, 0, sizeof(P));
   P.Wd = w.Wd; P.bd = w.bd; P.Wu = w.Wu; P.bu = w.bu;
@@ -561,7 +571,6 @@ int rows_k1_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const void
     A[k] = x2; lda[k] = D.d; Bm[k] = W.das; ldb[k] = W.pz; nbv[k] = r8; tr[k] = 1; out[k] = oWd; bias[k] = nullptr; sc[k] = 1.f; ++k;
   }
   if (k) VLPET_TRY(wgrad_sm100(k, A, lda, Bm, ldb, nbv, out, bias, sc, tr, D.M, D.d, r8, sms, st));
-  if (G.dbd) VLPET_TRY(colsum_bf16(W.das, W.pz, D.r, G.dbd, D.M, sms, st));
   if (r8 != D.r && (G.dWu || G.dWd)) {
     const int n = D.d * D.r;
     unpad_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(W.pWu, W.pWd, G.dWu, G.dWd, D.d, D.r, r8);
