@@ -150,7 +150,7 @@ def test_trainer_bucket_gradients_match_reference_vlbart(H):
     _load_state(model, z, torch.float32)
     tr = H.PetTrainer(model, model.config, "cuda", compute_dtype=torch.float32)
     try:
-        assert F_._direct_grads
+        assert tr._direct and not F_._direct_grads      # direct accumulation is scoped to the trainer's own steps
         for task in ("vqa", "nlvr"):
             loss = tr.forward_backward(_batch(z, task, torch.float32))
             assert abs(loss.item() - float(z[f"{task}/loss"])) < 2e-5 * abs(float(z[f"{task}/loss"]))

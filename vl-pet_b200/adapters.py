@@ -167,6 +167,11 @@ class AdapterController(nn.Module):
         if adapter.track_z:
             with torch.no_grad():
                 adapter.z = gelu_new(torch.nn.functional.linear(z, adapter.down_sampler.weight, adapter.down_sampler.bias))
+        if z.is_cuda and (torch.is_autocast_enabled() or (residual is not None and residual.dtype != z.dtype)):
+            # torch.autocast: `inputs` comes out of a LayerNorm in fp32, y = v_proj(inputs) in the autocast dtype
+            ct = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else residual.dtype
+            z = z.to(ct)
+            residual = residual.to(ct) if residual is not None else None
         if self.add_layer_norm_after_adapter:   # LayerNorm sits between the scaled adapter output and the residual
             out = F_.vpa(z, None, adapter.down_sampler.weight, adapter.down_sampler.bias, adapter.up_sampler.weight,
                          adapter.up_sampler.bias, sf)

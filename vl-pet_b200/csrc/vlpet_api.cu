@@ -29,14 +29,18 @@ uint32_t* trap_buffer_dev() {
 }
 const uint32_t* trap_buffer_host() { return g_trap_host; }
 
-int device_sm_count() {
-  static int sms = []() {
-    int dev = 0;
-    cudaDeviceProp p;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
-    return p.major == 10 ? p.multiProcessorCount : -1;
-  }();
-  return sms;
+int device_sm_count() {   // SM count of the CURRENT device (cached per ordinal); -1 if it is not a compute-capability-10 part
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < 64 && cache[dev] != 0) return cache[dev];
+  int sms = 0, major = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return 0;
+  const int v = major == 10 ? sms : -1;
+  if (dev >= 0 && dev < 64) cache[dev] = v;
+  return v;
 }
 
 namespace {

@@ -49,6 +49,18 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     if (_r != 0) return _r; \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device's copy of a kernel: remember per device
+// ordinal what was set (one process may drive several GPUs).  `slot` is one zero-initialised int[64] per kernel.
+inline int ensure_dyn_smem(const void* kern, int (&slot)[64], int bytes) {
+  int dev = 0;
+  VLPET_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || slot[dev] < bytes) {
+    VLPET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (dev >= 0 && dev < 64) slot[dev] = bytes;
+  }
+  return 0;
+}
+
 inline size_t esize(int dtype) { return dtype == VLPET_BF16 ? 2 : 4; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -153,11 +153,8 @@ int gemm_sm100(const void* A, int64_t lda, const void* W, int64_t ldw, const voi
   VLPET_TRY(make_map_bf16(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN, BK, true));
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = static_cast<const __nv_bfloat16*>(bias);
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLPET_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  static int attr_set[64] = {0};
+  VLPET_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(gemm_sm100_kernel), attr_set, SMEM_BYTES));
   const int64_t ntiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int sms = device_sm_count();
   const int grid = (int)(ntiles < sms ? ntiles : sms);

@@ -649,17 +649,9 @@ int pick_R(const VlpetK1Desc& D) {
 }
 
 struct DevInfo { int ok, sms, major; };
-const DevInfo& dev_info() {
-  static DevInfo di = []() {
-    DevInfo d{0, 0, 0};
-    int dev = 0;
-    cudaDeviceProp p;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
-      d.ok = 1; d.sms = p.multiProcessorCount; d.major = p.major;
-    }
-    return d;
-  }();
-  return di;
+DevInfo dev_info() {   // of the CURRENT device
+  const int sms = device_sm_count();
+  return DevInfo{sms != 0 ? 1 : 0, sms > 0 ? sms : 0, sms > 0 ? 10 : 0};
 }
 
 template <int R, bool GATED, int NCTA>
@@ -667,11 +659,8 @@ int launch(const VlpetK1Desc& D, const CUtensorMap* maps, Params p, cudaStream_t
   using C = Cfg<R, NCTA>;
   const int smem = C::smem_bytes(D.d);
   auto kern = k1_fwd_sm100_kernel<R, GATED, NCTA>;
-  static int attr_set = 0;
-  if (attr_set < smem) {
-    VLPET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = smem;
-  }
+  static int attr_set[64] = {0};
+  VLPET_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kern), attr_set, smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
@@ -684,7 +673,12 @@ int launch(const VlpetK1Desc& D, const CUtensorMap* maps, Params p, cudaStream_t
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    static int max_pairs = -1;     // a GPC with an odd number of SMs strands one SM: ask the driver how many pairs fit at once
+    static int max_pairs_dev[64];  // a GPC with an odd number of SMs strands one SM: ask the driver how many pairs fit at once
+    static bool mp_init = false;
+    if (!mp_init) { for (int i = 0; i < 64; ++i) max_pairs_dev[i] = -1; mp_init = true; }
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    int& max_pairs = max_pairs_dev[(dev_ >= 0 && dev_ < 64) ? dev_ : 0];
     if (max_pairs < 0) {
       cfg.gridDim = dim3((unsigned)(dev_info().sms / 2 * 2));
       int n = 0;

@@ -224,11 +224,8 @@ int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void
   a.NB = (nbmax + 15) / 16 * 16;
   a.ncolgroups = (d / SLAB + SPC - 1) / SPC;
   a.dbg = trap_buffer_dev();
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLPET_CUDA_OK(cudaFuncSetAttribute(wgrad_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  static int attr_set[64] = {0};
+  VLPET_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(wgrad_sm100_kernel), attr_set, SMEM_BYTES));
   // Token groups: one CTA per (pair, slab, token group); every group ends with a flush of its [128 x nout] partial sums.
   const int gx = npairs * a.ncolgroups;
   const int64_t nsteps = (Mtok + KT - 1) / KT;

@@ -92,6 +92,12 @@ def encoder_pet(layer: nn.Module, site: str, x1: torch.Tensor, x2: torch.Tensor)
     The BART LayerNorm that follows stays with the caller."""
     cfg = layer._vlpet_site_cfg
     down_ws, down_bs, up_w, up_b, gp = site_params(layer, site, cfg.gate)
+    if x1.is_cuda and (torch.is_autocast_enabled() or x1.dtype != x2.dtype):
+        # torch.autocast (the reference's only reduced-precision mode, multitask.py:229-234): the residual stream stays fp32,
+        # the sub-layer output arrives in the autocast dtype.  The kernel runs in that dtype; the sum goes back to the stream's.
+        ct = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x2.dtype
+        out = F_.gated_pet(x1.to(ct), x2.to(ct), down_ws, down_bs, up_w, up_b, gp, cfg, training=layer.training)
+        return out.to(x1.dtype)
     return F_.gated_pet(x1, x2, down_ws, down_bs, up_w, up_b, gp, cfg, training=layer.training)
 
 

@@ -122,9 +122,9 @@ def _p(t: Optional[torch.Tensor]):
 def _as(t: Optional[torch.Tensor], dtype) -> Optional[torch.Tensor]:
     if t is None:
         return None
-    sh = getattr(t, "_vlpet_shadow", None)  # bf16 shadow kept fresh by PetBucket
-    if sh is not None and sh.dtype == dtype:
-        return sh
+    sh = getattr(t, "_vlpet_shadow", None)  # bf16 shadow kept fresh by PetBucket (refresh_shadow / the fused AdamW kernel)
+    if sh is not None and sh.dtype == dtype and getattr(t, "_vlpet_shadow_version", None) == t._version:
+        return sh      # an in-place write through torch since the last refresh (load_state_dict, copy_) bumps _version: cast instead
     t = t.detach()
     return (t if t.dtype == dtype else t.to(dtype)).contiguous()
 

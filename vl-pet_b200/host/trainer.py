@@ -101,11 +101,24 @@ class PetBucket:
         self.refresh_shadow()
 
     def refresh_shadow(self):
+        """Re-cast the bf16 shadow from the fp32 masters and record the parameters' version counters: the kernels read the
+        shadow only while a parameter has not been written through torch since (functional._as).  Call it after
+        load_state_dict() / manual in-place edits; the fused AdamW keeps the shadow fresh by itself (raw-pointer writes do
+        not bump versions)."""
         if self.shadow is None:
             return
         L.check(L.lib.vlpet_cast_f32_to_bf16(C.c_void_p(self.flat_param.data_ptr()), C.c_void_p(self.shadow.data_ptr()),
                                              self.numel, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                 "vlpet_cast_f32_to_bf16")
+        for p in self.params:
+            p._vlpet_shadow_version = p._version
+
+    def release(self):
+        """Detach the shadows from the parameters (the attribute would otherwise outlive the trainer)."""
+        for p in self.params:
+            for a in ("_vlpet_shadow", "_vlpet_shadow_version"):
+                if hasattr(p, a):
+                    delattr(p, a)
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -162,9 +175,8 @@ class PetTrainer:
                 m.out_dtype = compute_dtype
         self.bucket = PetBucket(named, self.device, torch.bfloat16 if compute_dtype == torch.bfloat16 else None,
                                 torch.float64 if compute_dtype == torch.float64 else torch.float32)
-        if self.device.type == "cuda" and compute_dtype != torch.float64:
-            from .. import functional as F_
-            F_.set_direct_grad_accumulation(True)                 # weight gradients land in the bucket, no detours
+        self._direct = self.device.type == "cuda" and compute_dtype != torch.float64   # see forward_backward
+        self.opt_steps = 0                                        # optimizer updates taken (AdamW bias correction), NOT the LR step
         self._norm_sq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._scale = torch.ones(1, dtype=torch.float32, device=self.device)
         if self.world > 1:                                        # identical start on every rank
@@ -218,6 +230,16 @@ class PetTrainer:
     # -- the three phases of a step, separable so callers can capture / overlap them
     def forward_backward(self, batch: Dict) -> torch.Tensor:
         self.bucket.zero_grad()
+        if self._direct:                       # scoped: weight gradients land in the bucket only inside this trainer's steps
+            from .. import functional as F_
+            prev = F_._direct_grads
+            F_.set_direct_grad_accumulation(True)
+            try:
+                loss = self.model.train_step(batch)["loss"]
+                loss.backward()
+            finally:
+                F_.set_direct_grad_accumulation(prev)
+            return loss.detach()
         loss = self.model.train_step(batch)["loss"]
         loss.backward()
         return loss.detach()
@@ -229,6 +251,9 @@ class PetTrainer:
 
     def optimizer_step(self):
         b = self.bucket
+        if b.flat_param.dtype != torch.float32:
+            raise RuntimeError("PetTrainer.optimizer_step: the fused AdamW kernels take fp32 master buffers; a float64 trainer "
+                               "(CPU parity runs) must use forward_backward() + its own optimizer")
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         # global-norm clip factor on the device (no host sync): scale = min(1, clip / (||g||/world + 1e-6)) / world
         self._norm_sq.zero_()
@@ -240,10 +265,11 @@ class PetTrainer:
         self._scale.div_(w)
         lr = linear_warmup_lr(self.step_idx, self.total_steps, self.warmup_ratio, self.lr)
         self.step_idx += 1
+        self.opt_steps += 1                    # transformers' AdamW keeps its own state['step'], independent of the scheduler
         L.check(L.lib.vlpet_adamw_step(C.c_void_p(b.flat_param.data_ptr()), C.c_void_p(b.flat_grad.data_ptr()),
                                        C.c_void_p(b.exp_avg.data_ptr()), C.c_void_p(b.exp_avg_sq.data_ptr()),
                                        C.c_void_p(b.wd_mask.data_ptr()), b.numel, lr, self.betas[0], self.betas[1],
-                                       self.eps, self.wd, self.step_idx, C.c_void_p(self._scale.data_ptr()),
+                                       self.eps, self.wd, self.opt_steps, C.c_void_p(self._scale.data_ptr()),
                                        C.c_void_p(b.shadow.data_ptr()) if b.shadow is not None else C.c_void_p(0), st),
                 "vlpet_adamw_step")
 
@@ -270,11 +296,14 @@ class GraphedPetTrainer(PetTrainer):
         self._F = F_
         self._seed = torch.zeros(1, dtype=torch.int64, device=dev)
         F_.set_device_seed(self._seed)
-        self._t = torch.full((1,), float(self.step_idx), dtype=torch.float32, device=dev)   # optimizer steps taken so far
+        self._t = torch.full((1,), float(self.step_idx), dtype=torch.float32, device=dev)   # LR-scheduler step
+        self._k = torch.zeros(1, dtype=torch.float64, device=dev)                           # optimizer updates taken (bias correction)
         self._hyper = torch.zeros(2, dtype=torch.float32, device=dev)
         self._pool = torch.cuda.graph_pool_handle()
         self._fb = {}
         self._opt = None
+        self._whole = {}                 # batch signature -> ONE graph: forward + backward + gradient all-reduce + optimizer
+        self.single_graph = True         # falls back to the three host-issued phases if NCCL refuses stream capture
         self._stream = torch.cuda.Stream(device=dev)
         self._loss_out = torch.zeros((), dtype=torch.float32, device=dev)
         self._replayed_launches = 0
@@ -327,10 +356,11 @@ class GraphedPetTrainer(PetTrainer):
         down = (float(self.total_steps) - s_) / max(1.0, float(self.total_steps) - warm)
         lr = self.lr * torch.where(s_ < warm, up, down).clamp(min=0.0)
         self._t.add_(1.0)
-        bc1 = 1.0 - torch.pow(torch.full_like(self._t, self.betas[0]), self._t)
-        bc2 = 1.0 - torch.pow(torch.full_like(self._t, self.betas[1]), self._t)
+        self._k.add_(1.0)
+        bc1 = 1.0 - torch.pow(torch.full_like(self._k, self.betas[0]), self._k)      # float64: 1 - 0.999^k loses digits in fp32
+        bc2 = 1.0 - torch.pow(torch.full_like(self._k, self.betas[1]), self._k)
         self._hyper[0:1].copy_(lr)
-        self._hyper[1:2].copy_(lr * bc2.sqrt() / bc1)
+        self._hyper[1:2].copy_(lr * (bc2.sqrt() / bc1).float())
         L.check(L.lib.vlpet_adamw_step_dev(C.c_void_p(b.flat_param.data_ptr()), C.c_void_p(b.flat_grad.data_ptr()),
                                            C.c_void_p(b.exp_avg.data_ptr()), C.c_void_p(b.exp_avg_sq.data_ptr()),
                                            C.c_void_p(b.wd_mask.data_ptr()), b.numel, C.c_void_p(self._hyper.data_ptr()),
@@ -338,6 +368,34 @@ class GraphedPetTrainer(PetTrainer):
                                            C.c_void_p(self._scale.data_ptr()),
                                            C.c_void_p(b.shadow.data_ptr()) if b.shadow is not None else C.c_void_p(0), st),
                 "vlpet_adamw_step_dev")
+
+    def _capture_whole(self, batch: Dict):
+        """forward + backward, the NCCL all-reduce of the flat gradient bucket and the fused optimizer in ONE CUDA graph:
+        a step is a single replay, and the collective starts the moment the last gradient kernel retires instead of after a
+        host round trip (round 1: graph replay -> eager all_reduce -> graph replay)."""
+        static = {k: (torch.empty(v.shape, dtype=v.dtype, device=self.device) if torch.is_tensor(v) else v)
+                  for k, v in batch.items()}
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                static[k].copy_(v)
+        torch.cuda.synchronize()
+        self._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._stream):
+            for _ in range(2):                     # eager warm-up on the side stream (lazy initialisation, workspaces, NCCL)
+                self.forward_backward(static)
+                self.exchange()
+        torch.cuda.current_stream().wait_stream(self._stream)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
+        with torch.cuda.graph(g, pool=self._pool, stream=self._stream, capture_error_mode="thread_local"):
+            self._seed.add_(1000003)
+            loss = self.forward_backward(static)
+            self.exchange()
+            self._optimizer_ops()
+            self._loss_out.copy_(loss)
+        g.vlpet_launches = L.launch_count() - n0
+        return g, static
 
     def _capture_opt(self):
         torch.cuda.synchronize()
@@ -351,6 +409,26 @@ class GraphedPetTrainer(PetTrainer):
     def train_step(self, batch) -> torch.Tensor:
         batch, key = self._consume(batch)
         sig = self._signature(batch)
+        if self.single_graph:
+            ent = self._whole.get(sig)
+            if ent is None:
+                try:
+                    ent = self._whole[sig] = self._capture_whole(batch)
+                except Exception as ex:   # noqa: BLE001  (e.g. a NCCL build that refuses capture): keep the 3-phase step
+                    import warnings
+                    warnings.warn(f"vlpet: single-graph step capture failed ({ex!r}); using the three-phase step")
+                    self.single_graph = False
+                    torch.cuda.synchronize()
+            if ent is not None:
+                g, static = ent
+                for k, v in batch.items():
+                    if torch.is_tensor(v) and v.data_ptr() != static[k].data_ptr():
+                        static[k].copy_(v, non_blocking=True)
+                self._release(key)
+                g.replay()
+                self._replayed_launches += g.vlpet_launches
+                self.step_idx += 1
+                return self._loss_out
         ent = self._fb.get(sig)
         if ent is None:
             ent = self._fb[sig] = self._capture_fb(batch)

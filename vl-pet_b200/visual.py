@@ -63,6 +63,8 @@ def _forward(self, feats, pos, img_order_ids=None, obj_order_ids=None):
     lin_p, ln_p = self.absolute_vis_pos_embedding[0], self.absolute_vis_pos_embedding[1]
     rms = not hasattr(ln_f, "bias") or getattr(ln_f, "bias", None) is None
     eps = getattr(ln_f, "variance_epsilon", None) if rms else ln_f.eps
+    if feats.is_cuda and torch.is_autocast_enabled():      # torch.autocast: the projection GEMM runs in the autocast dtype
+        feats = feats.to(torch.get_autocast_dtype("cuda"))
     return F_.visual_projection(feats, pos, img_order_ids, obj_order_ids, lin_f.weight, lin_f.bias, ln_f.weight,
                                 None if rms else ln_f.bias, lin_p.weight, lin_p.bias, ln_p.weight,
                                 None if rms else ln_p.bias, self.img_order_embedding.weight,
