@@ -303,7 +303,10 @@ class GraphedPetTrainer(PetTrainer):
         self._fb = {}
         self._opt = None
         self._whole = {}                 # batch signature -> ONE graph: forward + backward + gradient all-reduce + optimizer
-        self.single_graph = True         # falls back to the three host-issued phases if NCCL refuses stream capture
+        # One graph per step only on a single rank.  With world > 1 the captured NCCL all-reduce hung the 8-GPU bench of this
+        # round (all ranks stuck after capture; not root-caused within the GPU budget), so multi-rank runs keep the
+        # three host-issued phases that round 1 measured: fb graph -> eager all_reduce -> optimizer graph.
+        self.single_graph = self.world == 1
         self._stream = torch.cuda.Stream(device=dev)
         self._loss_out = torch.zeros((), dtype=torch.float32, device=dev)
         self._replayed_launches = 0
