@@ -50,6 +50,8 @@ def parse():
                     help="--impl reference: per-step --batch-size of the CPU run (default: the workload's if it fits ~150 s)")
     ap.add_argument("--no-micro", action="store_true", help="skip the K1 micro-benchmark at the north-star shape")
     ap.add_argument("--graphs", type=int, default=1, help="replay each task step as a CUDA graph (0 = eager)")
+    ap.add_argument("--micro-sweep", action="store_true",
+                    help="run the SURVEY 8(d) kernel sweep (r x L x gate) instead of the bench and write profiles/r2_micro_sweep.json")
     return ap.parse_args()
 
 
@@ -490,6 +492,8 @@ def run_ours(a):
 
 def main():
     a = parse()
+    if a.micro_sweep:
+        raise SystemExit(subprocess.call([sys.executable, os.path.join(ROOT, "tools", "micro_sweep.py")]))
     if a.impl == "reference":
         run_reference(a)
     else:
