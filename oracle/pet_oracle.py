@@ -150,7 +150,7 @@ def gated_pet_bwd(dout, p: Dict[str, np.ndarray], cfg: PetConfig, c, rnd=None):
         dp_exact = dq * gelu_new_grad(c["p"])
         dp = R(dp_exact)
         gr["Gd"] = dp.T @ x1
-        gr["gbd"] = dp.sum(0)
+        gr["gbd"] = dp_exact.sum(0)       # bias sums are taken before the storage rounding (fp32 in the kernel's epilogue)
         dx1 = dx1 + dp @ p["Gd"]
     elif g == GATE_MIDDLE_X:
         G = c["G"]
@@ -199,7 +199,7 @@ def gated_pet_bwd(dout, p: Dict[str, np.ndarray], cfg: PetConfig, c, rnd=None):
     da_exact = dz * gelu_new_grad(a)
     da = R(da_exact)
     gr["Wd"] = da.T @ x2
-    gr["bd"] = da.sum(0)
+    gr["bd"] = da_exact.sum(0)            # as above: only the GEMM operand da is stored in bf16
     dx2 = cfg.kappa * dy1 + da @ p["Wd"]
     return dx1, dx2, gr
 

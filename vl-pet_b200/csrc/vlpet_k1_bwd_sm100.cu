@@ -63,7 +63,8 @@ struct BCfg {
   static constexpr int OFF_X = 0;
   static constexpr int OFF_W = OFF_X + SX * 2 * XCH_BYTES;
   static constexpr int OFF_BD = OFF_W + SW * WSLOT;          // fp32 bd[R] | gbd[R]
-  static constexpr int OFF_BAR = OFF_BD + 2 * R * 4;
+  static constexpr int OFF_DSUM = OFF_BD + 2 * R * 4;        // fp32 column sums of da | dp over this CTA's tiles (dbd, dgbd)
+  static constexpr int OFF_BAR = OFF_DSUM + 2 * R * 4;
   static constexpr int OFF_TAB = OFF_BAR + 512;              // fp32 alpha*bu[d] | 0.5*gbu[d]
   static constexpr int smem_bytes(int d) { return OFF_TAB + 2 * d * 4 + 1024; }   // + slack for the manual 1024-B alignment
   // TMEM columns.  Phases 1-2: A | P (in place after epilogue 1: per 16 columns, 8 of packed z/q then 8 of gelu' fixed point,
@@ -96,6 +97,7 @@ struct BParams {
   float s, alpha, kappa;
   const __nv_bfloat16 *bd, *bu, *gbd, *gbu;
   __nv_bfloat16 *zs, *qs, *das, *dps;   // scratch [M, pz] / [M, pq]
+  float *dbd, *dgbd;                    // fp32 bias gradients of the down projections (accumulated into) or nullptr
   int pz, pq;                           // scratch row pitches (elements)
   uint64_t seed;
   const uint64_t* seed_dev;
@@ -136,6 +138,23 @@ __device__ __forceinline__ uint32_t enc_fix2(f2 g) {
 __device__ __forceinline__ f2 dec_fix2(uint32_t v) {
   const f2 f = mk2u(__byte_perm(v, 0x4B000000u, 0x7610), __byte_perm(v, 0x4B000000u, 0x7632));
   return fma2(add2(f, mk2(-8388608.0f, -8388608.0f)), mk2(2.5e-5f, 2.5e-5f), mk2(-0.25f, -0.25f));
+}
+// Column sums over the 32 lanes of a warp (= 32 token rows), 16 columns: every lane enters with its row's 16 values; lanes l and
+// l ^ 16 leave with the sum over rows of column (l & 15).  31 shuffles instead of 80 for 16 butterflies.
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? v[i] : v[i + off];
+      const float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
 }
 __device__ __forceinline__ void lds128(uint32_t addr, uint32_t (&v)[4]) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
@@ -206,6 +225,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       const __nv_bfloat16* src = br ? p.gbd : p.bd;
       sbd[i] = (j < rr && (GATED || br == 0)) ? __bfloat162float(src[j]) : 0.f;
     }
+    float* sds = reinterpret_cast<float*>(smem_gen + C::OFF_DSUM);
+    for (int i = threadIdx.x; i < 2 * R; i += NUM_THREADS) sds[i] = 0.f;
     float* stab = reinterpret_cast<float*>(smem_gen + C::OFF_TAB);
     if (GATED) {
       for (int i = threadIdx.x; i < p.d; i += NUM_THREADS) {
@@ -640,10 +661,18 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
 #pragma unroll
             for (int e = 0; e < 16; ++e) dz[e] = __float_as_uint(acc[e]);
           }
+          float cs[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            o[e] = pack2(mul2(mul2(mk2u(dz[2 * e], dz[2 * e + 1]), dec_fix2(gq[e])), dzs2));
+          for (int e = 0; e < 8; ++e) {
+            const f2 da2 = mul2(mul2(mk2u(dz[2 * e], dz[2 * e + 1]), dec_fix2(gq[e])), dzs2);
+            o[e] = pack2(da2);
+            un2(da2, cs[2 * e], cs[2 * e + 1]);
+          }
           ptx::tmem_st_32x32b_x8(tpre + j0 + 8, o);     // packed da / dp: K step j0/16 of the phase-3 A operands
+          // dbd / dgbd: fp32 column sums of da / dp (rows beyond M contribute exact zeros: their dout is zero-filled)
+          const float csum = warp_colsum16(cs, lane);
+          if (lane < 16 && crank == 0)
+            atomicAdd(reinterpret_cast<float*>(smem_gen + C::OFF_DSUM) + branch * R + j0 + lane, csum);
           if (row_ok && crank == 0) {
             if (j0 < rr) *reinterpret_cast<uint4*>(srow + j0) = make_uint4(o[0], o[1], o[2], o[3]);
             if (j0 + 8 < rr) *reinterpret_cast<uint4*>(srow + j0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
@@ -732,6 +761,14 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
 
   ptx::tc_fence_before();
   __syncthreads();
+  {  // this CTA's share of the down-projection bias gradients
+    const float* sds = reinterpret_cast<const float*>(smem_gen + C::OFF_DSUM);
+    for (int i = threadIdx.x; i < 2 * R; i += NUM_THREADS) {
+      const int br = i / R, j = i % R;
+      float* dst = br ? p.dgbd : p.dbd;
+      if (dst && j < (br ? p.rg : p.r) && sds[i] != 0.f) atomicAdd(dst + j, sds[i]);
+    }
+  }
   if (p.nsplit > 1) ptx::cluster_sync_all();   // no CTA exits while a peer can still arrive on its exchange barrier
   if (warp == 1) {
     ptx::tc_fence_after();
@@ -939,6 +976,7 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   p.gbd = static_cast<const __nv_bfloat16*>(gated ? w.gbd : w.bd); p.gbu = static_cast<const __nv_bfloat16*>(gated ? w.gbu : w.bu);
   p.zs = s.zs; p.qs = s.qs; p.das = s.das; p.dps = s.dps; p.pz = s.pz; p.pq = s.pq;
   p.nsplit = s.nsplit; p.xchg = s.xchg;
+  p.dbd = G.dbd; p.dgbd = gated ? G.dgbd : nullptr;
   p.seed = D.seed;
   p.seed_dev = D.seed_dev;
   p.trace = g_trace_b;
@@ -966,9 +1004,7 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
     }
   }
   if (rc) return rc;
-  if (parts & 2) {
-    VLPET_TRY(launch_colsum_scratch(s.das, s.pz, D.r, G.dbd, s.dps, gated ? s.pq : 0, rg, gated ? G.dgbd : nullptr, D.M, sms, st));
-  }
+  // (round 1 ran two column-sum launches over the da / dp scratch here; the sums are now formed in epilogue 3 of the tile kernel)
   if (!(parts & 4)) return 0;
   // ---- weight gradients: dWu = du^T z (+dbu), dGu = dt^T q (+dgbu), dWd = (x2^T da)^T, dGd = (x1^T dp)^T
   //      (ungated: du = alpha*dout, so A = dout with scale alpha)
