@@ -103,6 +103,7 @@ struct BParams {
   const uint64_t* seed_dev;
   uint32_t thr16;
   float inv_keep;
+  int64_t tile_begin, tile_end;         // tiles [tile_begin, tile_end) belong to this launch
   int nsplit;                           // > 1: a cluster of nsplit CTAs shares every tile (small M), see "tile split" below
   float* xchg;                          // [tiles][nsplit][2R][128] fp32: partial dz | dq of the CTAs of a cluster
   unsigned long long* trace;            // developer hook (tools/trace_k1_bwd.py), normally null
@@ -184,12 +185,12 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   const int nkc = p.d / CH;
-  const int64_t num_tiles = (p.M + TILE_M - 1) / TILE_M;
+  const int64_t num_tiles = p.tile_end;
   const bool mulgate = p.add_gate == 0;
   const uint32_t crank = p.nsplit > 1 ? ptx::cluster_ctarank() : 0u;
   const int cps = nkc / p.nsplit;                       // chunks of phases 2 / 3 this CTA owns: [cb, ce)
   const int cb = (int)crank * cps, ce = cb + cps;
-  const int64_t tile0 = blockIdx.x / p.nsplit, tstride = gridDim.x / p.nsplit;
+  const int64_t tile0 = p.tile_begin + blockIdx.x / p.nsplit, tstride = gridDim.x / p.nsplit;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SX; ++i) {
@@ -613,7 +614,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           const uint32_t tdz = lane_addr + (branch ? C::TM_DQ : C::TM_DZ);
           // [tile][rank][column][row]: the 32 lanes of a warp (32 rows) write one 128-byte line per column -- a row-major
           // slot made every warp instruction touch 32 lines (~40 us per exchange in the L1 wavefront queue)
-          float* mine = p.xchg + (((size_t)tile * p.nsplit + crank) * (2 * R) + branch * R + jbeg) * TILE_M + row;
+          float* mine = p.xchg + (((size_t)(tile - p.tile_begin) * p.nsplit + crank) * (2 * R) + branch * R + jbeg) * TILE_M + row;
 #pragma unroll
           for (int jj = 0; jj < HALF; jj += 16) {
             uint32_t v[16];
@@ -653,7 +654,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
 #pragma unroll
                 for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(dz[e]);
               } else {
-                const float* peer = p.xchg + (((size_t)tile * p.nsplit + pr) * (2 * R) + branch * R + j0) * TILE_M + row;
+                const float* peer = p.xchg + (((size_t)(tile - p.tile_begin) * p.nsplit + pr) * (2 * R) + branch * R + j0) * TILE_M + row;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) acc[e] += __ldcg(peer + (size_t)e * TILE_M);
               }
@@ -888,6 +889,8 @@ struct Scratch {
   __nv_bfloat16 *zs, *qs, *das, *dps, *dus, *dts;
   float* xchg;
   int pz, pq, nsplit;
+  int64_t main_tiles, split_tiles;   // launch plan: tiles [0, main_tiles) one CTA each (persistent), then split_tiles tiles with
+                                     // nsplit CTAs each (small M: everything; large M: the last, partial wave)
   size_t bytes;
 };
 Scratch carve(int64_t M, int d, int r, int rg, bool gated, void* ws) {
@@ -906,8 +909,21 @@ Scratch carve(int64_t M, int d, int r, int rg, bool gated, void* ws) {
   }
   const int64_t tiles = (M + TILE_M - 1) / TILE_M;
   const int R = pick_R2(r, rg);
-  s.nsplit = R ? pick_split_rt(gated, R, tiles, d, device_sm_count()) : 1;
-  s.xchg = s.nsplit > 1 ? a.take<float>((size_t)tiles * s.nsplit * TILE_M * 2 * R) : nullptr;
+  const int sms = device_sm_count();
+  s.main_tiles = tiles; s.split_tiles = 0; s.nsplit = 1;
+  if (R && sms > 0) {
+    if (tiles * 2 <= sms) {                       // small M: every tile is shared by a cluster
+      s.nsplit = pick_split_rt(gated, R, tiles, d, sms);
+      if (s.nsplit > 1) { s.main_tiles = 0; s.split_tiles = tiles; }
+    } else if (tiles > sms && tiles % sms != 0 && (tiles % sms) * 2 <= sms) {
+      // large M: the last wave is partial (750 tiles on 148 SMs: 10 tiles would cost a sixth full round) -> its tiles
+      // go to a second launch, split over clusters
+      const int64_t rem = tiles % sms;
+      const int ns = pick_split_rt(gated, R, rem, d, sms);
+      if (ns > 1) { s.nsplit = ns; s.main_tiles = tiles - rem; s.split_tiles = rem; }
+    }
+  }
+  s.xchg = s.nsplit > 1 ? a.take<float>((size_t)s.split_tiles * s.nsplit * TILE_M * 2 * R) : nullptr;
   s.bytes = a.off;
   return s;
 }
@@ -924,7 +940,8 @@ int launch(const VlpetK1Desc& D, const CUtensorMap* m, const BParams& p, int sms
     VLPET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (dev >= 0 && dev < 64) attr_set[dev] = smem;
   }
-  const int64_t tiles = (D.M + TILE_M - 1) / TILE_M;
+  const int64_t tiles = p.tile_end - p.tile_begin;
+  if (tiles <= 0) return 0;
   if (p.nsplit > 1) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -987,21 +1004,27 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   // bit 2 = weight-gradient GEMM (default: all)
   const int parts = g_bwd_parts;
   int rc = 0;
-  if (!(parts & 1)) {
-  } else if (gated) {
-    switch (R) {
-      case 32: rc = launch<32, true>(D, m, p, sms, st); break;
-      case 64: rc = launch<64, true>(D, m, p, sms, st); break;
-      case 96: rc = launch<96, true>(D, m, p, sms, st); break;
-      default: return fail(VLPET_E_UNSUPPORTED, "bwd(fused): unsupported rank");
+  auto launch_range = [&](int64_t t0, int64_t t1, int ns) -> int {
+    BParams q = p;
+    q.tile_begin = t0; q.tile_end = t1; q.nsplit = ns;
+    if (gated) {
+      switch (R) {
+        case 32: return launch<32, true>(D, m, q, sms, st);
+        case 64: return launch<64, true>(D, m, q, sms, st);
+        case 96: return launch<96, true>(D, m, q, sms, st);
+      }
+    } else {
+      switch (R) {
+        case 32: return launch<32, false>(D, m, q, sms, st);
+        case 64: return launch<64, false>(D, m, q, sms, st);
+        case 96: return launch<96, false>(D, m, q, sms, st);
+      }
     }
-  } else {
-    switch (R) {
-      case 32: rc = launch<32, false>(D, m, p, sms, st); break;
-      case 64: rc = launch<64, false>(D, m, p, sms, st); break;
-      case 96: rc = launch<96, false>(D, m, p, sms, st); break;
-      default: return fail(VLPET_E_UNSUPPORTED, "bwd(fused): unsupported rank");
-    }
+    return fail(VLPET_E_UNSUPPORTED, "bwd(fused): unsupported rank");
+  };
+  if (parts & 1) {
+    rc = launch_range(0, s.main_tiles, 1);
+    if (!rc) rc = launch_range(s.main_tiles, s.main_tiles + s.split_tiles, s.nsplit);
   }
   if (rc) return rc;
   // (round 1 ran two column-sum launches over the da / dp scratch here; the sums are now formed in epilogue 3 of the tile kernel)
