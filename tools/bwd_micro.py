@@ -12,6 +12,7 @@ ap.add_argument("--r", type=int, default=96)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--flush", type=int, default=1)
 ap.add_argument("--gate", default="large")
+ap.add_argument("--p-drop", type=float, default=0.0, help="dropout probability of the PET output (training: 0.1)")
 a = ap.parse_args()
 d, r, bf = 768, a.r, torch.bfloat16
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -28,7 +29,7 @@ for M in a.M:
          mk(r, d, std=0.05), mk(r, std=0.02), mk(d, r, std=0.05), mk(d, std=0.02)]
     G = [torch.zeros(w.shape, dtype=torch.float32, device="cuda") for w in W]
     desc = L.K1Desc(M=M, L=0, d=d, r=r, rg=r, gate=L.GATE_IDS[a.gate], add_gate=0, dtype=L.BF16, impl=L.IMPL_AUTO, s=1.0, alpha=1.0,
-                    kappa=1.0, p_drop=0.0, seed=0, seed_dev=None)
+                    kappa=1.0, p_drop=a.p_drop, seed=1234, seed_dev=None)
     w = L.K1Params(Wd=p_(W[0]), bd=p_(W[1]), Wu=p_(W[2]), bu=p_(W[3]), Gd=p_(W[4]), gbd=p_(W[5]), Gu=p_(W[6]), gbu=p_(W[7]))
     gr = L.K1Grads(dWd=p_(G[0]), dbd=p_(G[1]), dWu=p_(G[2]), dbu=p_(G[3]), dGd=p_(G[4]), dgbd=p_(G[5]), dGu=p_(G[6]), dgbu=p_(G[7]))
     dx1, dx2 = torch.empty_like(x1), torch.empty_like(x2)

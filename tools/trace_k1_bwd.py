@@ -2,6 +2,9 @@
 import ctypes as C, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _variant
+_variant.use_trace_lib()   # the stamps exist only in the -DVLPET_TRACE build
 import vlpet_b200 as V
 import vlpet_b200.functional as F_
 from vlpet_b200 import _lib as L

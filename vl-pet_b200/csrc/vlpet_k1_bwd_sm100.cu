@@ -67,6 +67,8 @@ struct BCfg {
   static constexpr int OFF_BAR = OFF_DSUM + 2 * R * 4;
   static constexpr int OFF_TAB = OFF_BAR + 512;              // fp32 alpha*bu[d] | 0.5*gbu[d]
   static constexpr int smem_bytes(int d) { return OFF_TAB + 2 * d * 4 + 1024; }   // + slack for the manual 1024-B alignment
+  // optional: the dropout bits of a tile row, u16 [d / 64][512 epilogue threads], filled while phase 1 streams (see "dropout bits")
+  static constexpr int mask_bytes(int d) { return (d / CH) * EPI_THREADS * 2; }
   // TMEM columns.  Phases 1-2: A | P (in place after epilogue 1: per 16 columns, 8 of packed z/q then 8 of gelu' fixed point,
   // later packed da/dp) | dz | dq | U_c T_c.  Phase 3 reuses dz.. for {T_c, DX2_c, DX1_c}.
   static constexpr int TM_A = 0, TM_P = R, TM_DZ = 2 * R, TM_DQ = 3 * R, TM_UT = 4 * R;
@@ -85,10 +87,14 @@ __device__ __forceinline__ unsigned long long gtimer_b() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef VLPET_TRACE   // developer builds only (tools/_variant.py): the stamps cost the issue-bound epilogues ~30 instructions per chunk
 #define VLPET_TRACE_B(slot)                                                                                               \
   do {                                                                                                                    \
     if (p.trace && threadIdx.x == 128 && ti == 0 && (slot) < 128) p.trace[blockIdx.x * 128 + (slot)] = gtimer_b();       \
   } while (0)
+#else
+#define VLPET_TRACE_B(slot) do { } while (0)
+#endif
 
 struct BParams {
   int64_t M;
@@ -103,6 +109,7 @@ struct BParams {
   const uint64_t* seed_dev;
   uint32_t thr16;
   float inv_keep;
+  int premask;                          // the shared-memory table of dropout bits exists (it fits for d <= 768)
   int64_t tile_begin, tile_end;         // tiles [tile_begin, tile_end) belong to this launch
   int nsplit;                           // > 1: a cluster of nsplit CTAs shares every tile (small M), see "tile split" below
   float* xchg;                          // [tiles][nsplit][2R][128] fp32: partial dz | dq of the CTAs of a cluster
@@ -166,7 +173,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint32_t (&v)[4]) {
 
 // GATED = false is the ungated form used for the decoder value parallel adapter (K2): out = x1 + alpha*(Up(gelu_new(Down x2)))
 // -> dx2 = (alpha * (dout Wu) * gelu_new'(A)) Wd, no gate branch, no U/T recompute, no du/dt scratch (du = alpha*dout).
-template <int R, bool GATED>
+// MUL = the gate multiplies (default) / false = the add-gate ablation flag (a compile-time switch: as a run-time one it
+// cost ~40 of the ~530 instructions epilogue 2 issues per thread and chunk, and the epilogues are issue-bound).
+// SPLIT = the tile-split form (a cluster shares a tile): a compile-time switch as well -- as a run-time one the exchange
+// code sat in epilogue 3 as ~100 predicated-off instructions per 16 columns.
+template <int R, bool GATED, bool MUL, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                     const __grid_constant__ CUtensorMap tm_dout, const __grid_constant__ CUtensorMap tm_dx1,
@@ -186,11 +197,12 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   const int lane = threadIdx.x % 32;
   const int nkc = p.d / CH;
   const int64_t num_tiles = p.tile_end;
-  const bool mulgate = p.add_gate == 0;
-  const uint32_t crank = p.nsplit > 1 ? ptx::cluster_ctarank() : 0u;
-  const int cps = nkc / p.nsplit;                       // chunks of phases 2 / 3 this CTA owns: [cb, ce)
+  constexpr bool mulgate = MUL;
+  const int nsplit = SPLIT ? p.nsplit : 1;
+  const uint32_t crank = SPLIT ? ptx::cluster_ctarank() : 0u;
+  const int cps = nkc / nsplit;                       // chunks of phases 2 / 3 this CTA owns: [cb, ce)
   const int cb = (int)crank * cps, ce = cb + cps;
-  const int64_t tile0 = p.tile_begin + blockIdx.x / p.nsplit, tstride = gridDim.x / p.nsplit;
+  const int64_t tile0 = p.tile_begin + blockIdx.x / nsplit, tstride = gridDim.x / nsplit;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SX; ++i) {
@@ -207,7 +219,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     ptx::mbar_init(bar(B_DAPFULL), EPI_THREADS);
     ptx::mbar_init(bar(B_ACCFULL), 1);
     ptx::mbar_init(bar(B_ACCEMPTY), EPI_THREADS);
-    ptx::mbar_init(bar(B_XCHG), (uint32_t)p.nsplit);
+    ptx::mbar_init(bar(B_XCHG), (uint32_t)nsplit);
     ptx::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_dout); }
@@ -238,7 +250,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (p.nsplit > 1) ptx::cluster_sync_all();   // the peers' exchange barriers are initialised before any remote arrive
+  if (SPLIT) ptx::cluster_sync_all();   // the peers' exchange barriers are initialised before any remote arrive
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -485,12 +497,46 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     const uint32_t sb_base = smem_base + C::OFF_BD;     // fp32 [2][R]
     const uint32_t tab_base = smem_base + C::OFF_TAB;   // fp32 alpha*bu[d] | 0.5*gbu[d]
     const f2 half2 = mk2(0.5f, 0.5f), kappa2 = mk2(p.kappa, p.kappa), alpha2 = mk2(p.alpha, p.alpha);
+    const f2 halpha2 = mk2(0.5f * p.alpha, 0.5f * p.alpha);
     const f2 s2 = mk2(p.s, p.s);
     const float s_keep = p.s * p.inv_keep;
-    uint32_t xi = 0, ui = 0, p2i = 0, p3i = 0, ai = 0, ti = 0;
+    uint32_t ui = 0, ai = 0, ti = 0;
+    // dbd / dgbd: this warp's running fp32 column sums of da / dp over all tiles of the CTA (lane l < 16 <-> column
+    // jbeg + 16 k + l), reduced over the four lane quarters once, after the tile loop.  (A shared-memory float atomicAdd per
+    // tile is a CAS spin loop under 4-way contention: it cost epilogue 3 ~5 us per tile.)
+    float dsum_acc[HALF / 16];
+#pragma unroll
+    for (int k = 0; k < HALF / 16; ++k) dsum_acc[k] = 0.f;
+    // Ring positions are advanced incrementally: with 3-stage rings, index % 3 and index / 3 in every chunk cost the
+    // (issue-bound) epilogues a multiply-high sequence each.  xs / xph = stage and parity of the activation-ring entry
+    // this role looks at next; k2 / k3 = stage of the DUDT / OUTRDY barrier rings.
+    uint32_t xs = 0, xph = 0, k2 = 0, k3 = 0;
+    auto x_adv = [&]() { if (++xs == SX) { xs = 0; xph ^= 1u; } };
+    auto x_skip = [&](uint32_t n) { const uint32_t t = xs + n; xph ^= (t / SX) & 1u; xs = t % SX; };
+    // dropout mode of epilogues 2 / 4: 0 none, 1 hash in the loop, 2 bits from the shared-memory table
+    const int drop_mode = (GATED && p.thr16) ? (p.premask ? 2 : 1) : 0;
+    const uint32_t mask_base = tab_base + 8u * (uint32_t)p.d + 2u * (uint32_t)(threadIdx.x - 128);   // u16 [chunk][thread]
     for (int64_t tile = tile0; tile < num_tiles; tile += tstride, ++ti) {
       const int64_t grow = tile * TILE_M + row;
       const bool row_ok = grow < p.M;
+      // ---- dropout bits: the 16 keep bits of (this row, this thread's 16 columns) for every chunk this CTA owns, formed
+      //      here -- while phase 1 streams x1 / x2 and the epilogue warps have nothing to do -- instead of hashing inside
+      //      epilogues 2 and 4, which are issue-bound (the hashes were 136 of ~530 instructions per chunk there).
+      //      Bit 4h + k = element k of hash h, the order the in-loop hashing uses.  Written and read by the same thread.
+      if (drop_mode == 2) {
+        for (int c = cb; c < ce; ++c) {
+          const uint64_t i4 = (uint64_t)(grow * p.d + c * CH + cg * 16) >> 2;
+          uint32_t bits = 0;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const uint64_t hv = drop_hash4(seed_eff, i4 + h);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              bits |= (((uint32_t)(hv >> (16 * k)) & 0xffffu) >= p.thr16) ? (1u << (4 * h + k)) : 0u;
+          }
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(mask_base + (uint32_t)(c - cb) * (EPI_THREADS * 2)), "h"((uint16_t)bits) : "memory");
+        }
+      }
       // ---- epilogue 1 (APFULL also implies that every MMA of the previous tile, which read q / da / dp, has completed)
       VLPET_TRACE_B(0);
       ptx::mbar_wait_dbg(bar(B_APFULL), ti & 1, p.dbg, __LINE__);
@@ -532,11 +578,10 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(B_ZQFULL));
       VLPET_TRACE_B(2);
-      xi += nkc;
+      x_skip((uint32_t)nkc + (GATED ? 0u : (uint32_t)cps));
       // ---- epilogue 2, per 64-column chunk: du, dt
-      if (!GATED) xi += cps;
-      for (int c = cb; GATED && c < ce; ++c, ++xi, ++ui, ++p2i) {
-        const uint32_t sx = xi % SX;
+      for (int c = cb; GATED && c < ce; ++c, ++ui) {
+        const uint32_t sx = xs;
         ptx::mbar_wait_dbg(bar(B_UTFULL), ui & 1, p.dbg, __LINE__);
         VLPET_TRACE_B(3 + 3 * (c - cb));
         ptx::tc_fence_after();
@@ -546,15 +591,21 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(B_UTEMPTY));
-        ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
+        ptx::mbar_wait_dbg(bar(B_XFULL + sx), xph, p.dbg, __LINE__);
         VLPET_TRACE_B(4 + 3 * (c - cb));
         const uint32_t x2row = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
         const uint32_t dorow = x2row + XCH_BYTES;
         const int col0 = c * CH + cg * 16;
         const int64_t idx0 = grow * p.d + col0;
         const uint32_t tabu = tab_base + 4u * (uint32_t)col0, thgb = tabu + 4u * (uint32_t)p.d;
+        uint32_t mbits = 0;
+        if (drop_mode == 2) {
+          uint16_t mb;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(mb) : "r"(mask_base + (uint32_t)(c - cb) * (EPI_THREADS * 2)));
+          mbits = mb;
+        }
         auto group2 = [&](auto drop_tag, int g) {
-          constexpr bool DROP = decltype(drop_tag)::value;
+          constexpr int DROP = decltype(drop_tag)::value;
           const uint32_t off = (((uint32_t)(cg * 2 + g)) ^ swz) << 4;
           uint32_t xv[4], dv[4], ou[4], ot[4];
           lds128(x2row + off, xv);
@@ -565,7 +616,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           lds_f2x2(thgb + g * 32, hgb[0], hgb[1]);
           lds_f2x2(thgb + g * 32 + 16, hgb[2], hgb[3]);
           uint64_t h0 = 0, h1 = 0;
-          if (DROP) {
+          if (DROP == 1) {
             h0 = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
             h1 = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
           }
@@ -574,9 +625,11 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           for (int e = 0; e < 4; ++e) {
             const int j = g * 8 + e * 2;
             f2 sce = s2;                                                          // s * dropout mask of this pair
-            if (DROP) {
+            if (DROP == 1) {
               const uint32_t two = (uint32_t)((e >> 1 ? h1 : h0) >> (32 * (e & 1)));
               sce = mk2(((two & 0xffffu) >= p.thr16) ? s_keep : 0.f, ((two >> 16) >= p.thr16) ? s_keep : 0.f);
+            } else if (DROP == 2) {
+              sce = mk2((mbits & (1u << j)) ? s_keep : 0.f, (mbits & (2u << j)) ? s_keep : 0.f);
             }
             const f2 dh = mul2(sce, bf2_to_f2(dv[e]));                            // dh = s m dout
             const f2 th = tanh2(fma2(half2, mk2u(t[j], t[j + 1]), hgb[e]));      // G = 0.5 + 0.5 th
@@ -585,7 +638,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             if (mulgate) {
               f2 y1 = fma2(kappa2, bf2_to_f2(xv[e]), abu[e]);                     // kappa x2 + alpha bu
               y1 = fma2(alpha2, mk2u(u[j], u[j + 1]), y1);                        // + alpha U
-              du = mul2(mul2(alpha2, dh), fma2(half2, th, half2));                // alpha dh G
+              const f2 h5 = mul2(halpha2, dh);
+              du = fma2(h5, th, h5);                                              // alpha dh G = (0.5 alpha dh)(1 + th)
               dt = mul2(mul2(dh, y1), gg);
             } else {
               du = mul2(alpha2, dh);
@@ -597,10 +651,14 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           sts128(x2row + off, ou);
           sts128(dorow + off, ot);
         };
-        if (p.thr16) { group2(std::true_type{}, 0); group2(std::true_type{}, 1); }
-        else { group2(std::false_type{}, 0); group2(std::false_type{}, 1); }
+        using Tag0 = std::integral_constant<int, 0>; using Tag1 = std::integral_constant<int, 1>; using Tag2 = std::integral_constant<int, 2>;
+        if (drop_mode == 2) { group2(Tag2{}, 0); group2(Tag2{}, 1); }
+        else if (drop_mode == 1) { group2(Tag1{}, 0); group2(Tag1{}, 1); }
+        else { group2(Tag0{}, 0); group2(Tag0{}, 1); }
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(bar(B_DUDT + (p2i % SX)));
+        ptx::mbar_arrive(bar(B_DUDT + k2));
+        if (++k2 == SX) k2 = 0;
+        x_adv();
         VLPET_TRACE_B(5 + 3 * (c - cb));
       }
       // ---- epilogue 3: da = dz * gelu_new'(A + bd) (branch 0), dp = dq * gelu_new'(P + gbd) (branch 1)
@@ -608,7 +666,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       ptx::mbar_wait_dbg(bar(B_DZFULL), ti & 1, p.dbg, __LINE__);
       VLPET_TRACE_B(41);
       ptx::tc_fence_after();
-      if (p.nsplit > 1) {
+      if (SPLIT) {
         // ---- tile split: publish this CTA's partial dz | dq, meet the other CTAs of the cluster
         if (GATED || branch == 0) {
           const uint32_t tdz = lane_addr + (branch ? C::TM_DQ : C::TM_DZ);
@@ -645,19 +703,22 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           ptx::tmem_ld_32x32b_x8(tpre + j0 + 8, gq);   // gelu_new'(pre-activation), stored by epilogue 1
           ptx::tmem_ld_32x32b_x16(tdz + j0, dz);
           ptx::tmem_ld_wait();
-          if (p.nsplit > 1) {   // sum of the partials in rank order (every CTA of the cluster gets the same bits)
+          if (SPLIT) {   // sum of the partials in rank order (every CTA of the cluster gets the same bits)
+            // two peers' partials are requested per round (two L2 round trips per 16 columns instead of one per peer; four
+            // at once spilled); the CTA's own slot is read back like the others, so the code is the same for every rank and
+            // the sum is formed in rank order ((p0 + p1) + p2) + p3 on every CTA
             float acc[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-            for (uint32_t pr = 0; pr < (uint32_t)p.nsplit; ++pr) {
-              if (pr == crank) {
+            for (uint32_t pr = 0; pr < 4; pr += 2) {
+              float pv[2][16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(dz[e]);
-              } else {
-                const float* peer = p.xchg + (((size_t)(tile - p.tile_begin) * p.nsplit + pr) * (2 * R) + branch * R + j0) * TILE_M + row;
+              for (uint32_t q = 0; q < 2; ++q) {
+                const float* peer = p.xchg + (((size_t)(tile - p.tile_begin) * p.nsplit + pr + q) * (2 * R) + branch * R + j0) * TILE_M + row;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) acc[e] += __ldcg(peer + (size_t)e * TILE_M);
+                for (int e = 0; e < 16; ++e) pv[q][e] = (pr + q) < (uint32_t)p.nsplit ? __ldcg(peer + (size_t)e * TILE_M) : 0.f;
               }
+#pragma unroll
+              for (int e = 0; e < 16; ++e) acc[e] = pr == 0 ? pv[0][e] + pv[1][e] : (acc[e] + pv[0][e]) + pv[1][e];
             }
 #pragma unroll
             for (int e = 0; e < 16; ++e) dz[e] = __float_as_uint(acc[e]);
@@ -671,9 +732,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           }
           ptx::tmem_st_32x32b_x8(tpre + j0 + 8, o);     // packed da / dp: K step j0/16 of the phase-3 A operands
           // dbd / dgbd: fp32 column sums of da / dp (rows beyond M contribute exact zeros: their dout is zero-filled)
-          const float csum = warp_colsum16(cs, lane);
-          if (lane < 16 && crank == 0)
-            atomicAdd(reinterpret_cast<float*>(smem_gen + C::OFF_DSUM) + branch * R + j0 + lane, csum);
+          dsum_acc[jj / 16] += warp_colsum16(cs, lane);
           if (row_ok && crank == 0) {
             if (j0 < rr) *reinterpret_cast<uint4*>(srow + j0) = make_uint4(o[0], o[1], o[2], o[3]);
             if (j0 + 8 < rr) *reinterpret_cast<uint4*>(srow + j0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
@@ -685,8 +744,8 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
       ptx::mbar_arrive(bar(B_DAPFULL));
       VLPET_TRACE_B(42);
       // ---- epilogue 4, per 64-column chunk: dx1, dx2
-      for (int c = cb; c < ce; ++c, ++xi, ++ai, ++p3i) {
-        const uint32_t sx = xi % SX;
+      for (int c = cb; c < ce; ++c, ++ai) {
+        const uint32_t sx = xs;
         ptx::mbar_wait_dbg(bar(B_ACCFULL), ai & 1, p.dbg, __LINE__);
         VLPET_TRACE_B(43 + 3 * (c - cb));
         ptx::tc_fence_after();
@@ -701,7 +760,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         // arrive first (round 1), the MMA warp could reach the next tile while this chunk's dout load was still in flight,
         // take "the phase before the previous one is complete" for "complete", consume a stale slot and release it a second
         // time: the sporadic launch failure of round 1 (profiles/r2_b1_fault_rootcause.md).
-        ptx::mbar_wait_dbg(bar(B_XFULL + sx), (xi / SX) & 1, p.dbg, __LINE__);
+        ptx::mbar_wait_dbg(bar(B_XFULL + sx), xph, p.dbg, __LINE__);
         ptx::mbar_arrive(bar(B_ACCEMPTY));
         VLPET_TRACE_B(44 + 3 * (c - cb));
         const uint32_t dorow = smem_base + C::OFF_X + sx * (2 * XCH_BYTES) + (uint32_t)row * 128u;
@@ -709,8 +768,14 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
         const int col0 = c * CH + cg * 16;
         const int64_t idx0 = grow * p.d + col0;
         const uint32_t thgb = tab_base + 4u * (uint32_t)(p.d + col0);
+        uint32_t mbits = 0;
+        if (drop_mode == 2) {
+          uint16_t mb;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(mb) : "r"(mask_base + (uint32_t)(c - cb) * (EPI_THREADS * 2)));
+          mbits = mb;
+        }
         auto group4 = [&](auto drop_tag, int g) {
-          constexpr bool DROP = decltype(drop_tag)::value;
+          constexpr int DROP = decltype(drop_tag)::value;
           const uint32_t off = (((uint32_t)(cg * 2 + g)) ^ swz) << 4;
           uint32_t dv[4] = {0, 0, 0, 0}, o1[4], o2[4];
           const bool ungated_kappa = !GATED && p.kappa != 0.f;
@@ -721,7 +786,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             lds_f2x2(thgb + g * 32 + 16, hgb[2], hgb[3]);
           }
           uint64_t h0 = 0, h1 = 0;
-          if (DROP) {
+          if (DROP == 1) {
             h0 = drop_hash4(seed_eff, (uint64_t)(idx0 + g * 8) >> 2);
             h1 = drop_hash4(seed_eff, ((uint64_t)(idx0 + g * 8) >> 2) + 1);
           }
@@ -732,9 +797,11 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             if (GATED) {
               const f2 dof = bf2_to_f2(dv[e]);
               f2 sce = s2;
-              if (DROP) {
+              if (DROP == 1) {
                 const uint32_t two = (uint32_t)((e >> 1 ? h1 : h0) >> (32 * (e & 1)));
                 sce = mk2(((two & 0xffffu) >= p.thr16) ? s_keep : 0.f, ((two >> 16) >= p.thr16) ? s_keep : 0.f);
+              } else if (DROP == 2) {
+                sce = mk2((mbits & (1u << j)) ? s_keep : 0.f, (mbits & (2u << j)) ? s_keep : 0.f);
               }
               f2 dy1 = mul2(sce, dof);                                               // dh = s m dout
               if (mulgate) {
@@ -751,12 +818,26 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
           if (GATED) sts128(dorow + off, o1);
           sts128(o2row + off, o2);
         };
-        if (p.thr16) { group4(std::true_type{}, 0); group4(std::true_type{}, 1); }
-        else { group4(std::false_type{}, 0); group4(std::false_type{}, 1); }
+        using Tag0 = std::integral_constant<int, 0>; using Tag1 = std::integral_constant<int, 1>; using Tag2 = std::integral_constant<int, 2>;
+        if (drop_mode == 2) { group4(Tag2{}, 0); group4(Tag2{}, 1); }
+        else if (drop_mode == 1) { group4(Tag1{}, 0); group4(Tag1{}, 1); }
+        else { group4(Tag0{}, 0); group4(Tag0{}, 1); }
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(bar(B_OUTRDY + (p3i % SX)));
+        ptx::mbar_arrive(bar(B_OUTRDY + k3));
+        if (++k3 == SX) k3 = 0;
+        x_adv();
         VLPET_TRACE_B(45 + 3 * (c - cb));
       }
+    }
+    // The four lane quarters take turns adding their sums into the [2R] block (within a quarter every column has exactly one
+    // owner lane): four named barriers among the epilogue warps, once per launch, no atomics.
+    for (int qq = 0; qq < 4; ++qq) {
+      if (quarter == qq && (GATED || branch == 0) && lane < 16) {
+        float* s1 = reinterpret_cast<float*>(smem_gen + C::OFF_DSUM) + branch * R + jbeg + lane;
+#pragma unroll
+        for (int k = 0; k < HALF / 16; ++k) s1[16 * k] += dsum_acc[k];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
     }
   }
 
@@ -767,10 +848,10 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     for (int i = threadIdx.x; i < 2 * R; i += NUM_THREADS) {
       const int br = i / R, j = i % R;
       float* dst = br ? p.dgbd : p.dbd;
-      if (dst && j < (br ? p.rg : p.r) && sds[i] != 0.f) atomicAdd(dst + j, sds[i]);
+      if (dst && crank == 0 && j < (br ? p.rg : p.r) && sds[i] != 0.f) atomicAdd(dst + j, sds[i]);
     }
   }
-  if (p.nsplit > 1) ptx::cluster_sync_all();   // no CTA exits while a peer can still arrive on its exchange barrier
+  if (SPLIT) ptx::cluster_sync_all();   // no CTA exits while a peer can still arrive on its exchange barrier
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -835,19 +916,30 @@ int launch_colsum_scratch(const __nv_bfloat16* A0, int pitch0, int ncols0, float
   return 0;
 }
 
+// Dynamic shared memory of a launch: the layout of BCfg plus, when it still fits the 227 KB limit (d <= 768 at R = 96),
+// the table of dropout bits (BParams::premask).
+template <int R>
+int bwd_smem(int d, bool gated, int* premask) {
+  int smem = BCfg<R>::smem_bytes(d);
+  const bool fits = gated && smem + BCfg<R>::mask_bytes(d) <= SMEM_LIMIT;
+  if (fits) smem += BCfg<R>::mask_bytes(d);
+  if (premask) *premask = fits ? 1 : 0;
+  return smem;
+}
+
 // ---- tile split: how many CTAs share a tile -----------------------------------------------------------------------
 // The largest divisor of nkc (<= 8, the portable cluster size) for which every tile still gets its own cluster in ONE wave.
 // Cluster capacity is asked from the driver once per device and cluster size (GPCs strand SMs for some sizes).
 template <int R, bool GATED>
 int max_clusters(int ns, int d) {
-  static int cache[64][9];
+  static int cache[64][9];   // shared memory is 213-225 KB for every supported d: one CTA per SM either way
   static bool init = false;
   if (!init) { memset(cache, 0, sizeof(cache)); init = true; }
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
   if (cache[dev][ns] != 0) return cache[dev][ns] > 0 ? cache[dev][ns] : 0;
-  auto kern = k1_bwd_sm100_kernel<R, GATED>;
-  const int smem = BCfg<R>::smem_bytes(d > 1024 ? d : 1024);
+  auto kern = k1_bwd_sm100_kernel<R, GATED, true, true>;      // (the add-gate instantiation has the same footprint)
+  const int smem = bwd_smem<R>(d, GATED, nullptr);
   int n = 0;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess) {
     cudaLaunchConfig_t cfg;
@@ -928,16 +1020,18 @@ Scratch carve(int64_t M, int d, int r, int rg, bool gated, void* ws) {
   return s;
 }
 
-template <int R, bool GATED>
-int launch(const VlpetK1Desc& D, const CUtensorMap* m, const BParams& p, int sms, cudaStream_t st) {
-  using C = BCfg<R>;
-  const int smem = C::smem_bytes(D.d);
-  auto kern = k1_bwd_sm100_kernel<R, GATED>;
+template <int R, bool GATED, bool MUL>
+int launch(const VlpetK1Desc& D, const CUtensorMap* m, const BParams& p0, int sms, cudaStream_t st) {
+  BParams p = p0;
+  const int smem = bwd_smem<R>(D.d, GATED, &p.premask);
+  auto kern = k1_bwd_sm100_kernel<R, GATED, MUL, false>;
+  auto kern_split = k1_bwd_sm100_kernel<R, GATED, MUL, true>;
   static int attr_set[64] = {0};   // per device: cudaFuncSetAttribute applies to the current device's copy of the kernel
   int dev = 0;
   VLPET_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || attr_set[dev] < smem) {
     VLPET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VLPET_CUDA_OK(cudaFuncSetAttribute(kern_split, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (dev >= 0 && dev < 64) attr_set[dev] = smem;
   }
   const int64_t tiles = p.tile_end - p.tile_begin;
@@ -950,7 +1044,7 @@ int launch(const VlpetK1Desc& D, const CUtensorMap* m, const BParams& p, int sms
     attr[0].val.clusterDim.x = (unsigned)p.nsplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3((unsigned)(tiles * p.nsplit)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
-    VLPET_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], p));
+    VLPET_CUDA_OK(cudaLaunchKernelEx(&cfg, kern_split, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], p));
     count_launch();
     return 0;
   }
@@ -1007,17 +1101,23 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   auto launch_range = [&](int64_t t0, int64_t t1, int ns) -> int {
     BParams q = p;
     q.tile_begin = t0; q.tile_end = t1; q.nsplit = ns;
-    if (gated) {
+    if (gated && D.add_gate == 0) {
       switch (R) {
-        case 32: return launch<32, true>(D, m, q, sms, st);
-        case 64: return launch<64, true>(D, m, q, sms, st);
-        case 96: return launch<96, true>(D, m, q, sms, st);
+        case 32: return launch<32, true, true>(D, m, q, sms, st);
+        case 64: return launch<64, true, true>(D, m, q, sms, st);
+        case 96: return launch<96, true, true>(D, m, q, sms, st);
+      }
+    } else if (gated) {
+      switch (R) {
+        case 32: return launch<32, true, false>(D, m, q, sms, st);
+        case 64: return launch<64, true, false>(D, m, q, sms, st);
+        case 96: return launch<96, true, false>(D, m, q, sms, st);
       }
     } else {
       switch (R) {
-        case 32: return launch<32, false>(D, m, q, sms, st);
-        case 64: return launch<64, false>(D, m, q, sms, st);
-        case 96: return launch<96, false>(D, m, q, sms, st);
+        case 32: return launch<32, false, true>(D, m, q, sms, st);
+        case 64: return launch<64, false, true>(D, m, q, sms, st);
+        case 96: return launch<96, false, true>(D, m, q, sms, st);
       }
     }
     return fail(VLPET_E_UNSUPPORTED, "bwd(fused): unsupported rank");

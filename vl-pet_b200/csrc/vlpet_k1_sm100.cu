@@ -158,6 +158,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef VLPET_TRACE   // developer builds only (tools/_variant.py)
 #define VLPET_TR(slot)                                                             \
   do {                                                                             \
     if (p.trace) p.trace[blockIdx.x * 256 + (slot)] = gtimer();                    \
@@ -166,6 +167,10 @@ __device__ __forceinline__ unsigned long long gtimer() {
   do {                                                                                         \
     if (p.trace && threadIdx.x == 128 && ti == 0 && (slot) < 52) p.trace[blockIdx.x * 256 + (slot)] = gtimer(); \
   } while (0)
+#else
+#define VLPET_TR(slot) do { } while (0)
+#define VLPET_TRACE(slot) do { } while (0)
+#endif
 
 struct Params {
   int64_t M;

@@ -198,7 +198,9 @@ __global__ void __launch_bounds__(RW_THREADS) rows_fwd_kernel(const RowsArgs p) 
     }
     float o[NE];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
+    for (int ch = 0; ch < NCH; ++ch) {
+      float m[8];
+      drop_scale8(seed_eff, p.thr16, p.inv_keep, row * p.d + ch * 256 + lane * 8, m);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int i = ch * 8 + e;
@@ -206,9 +208,9 @@ __global__ void __launch_bounds__(RW_THREADS) rows_fwd_kernel(const RowsArgs p) 
         if (GATE == VLPET_GATE_MIDDLE_Y) h = p.add_gate ? S.y1[i] + 1.f + gwr[i] : S.y1[i] * (1.f + gwr[i]);
         else if (GATE == VLPET_GATE_NONE) h = S.y1[i];
         else h = p.add_gate ? S.y1[i] + S.g : S.y1[i] * S.g;
-        const float m = drop_scale(seed_eff, p.thr16, p.inv_keep, row * p.d + ch * 256 + lane * 8 + e);
-        o[i] = S.x1[i] + p.s * m * h;
+        o[i] = S.x1[i] + p.s * m[e] * h;
       }
+    }
     store_row<NCH>(p.out + row * p.d, lane, o);
   }
 }
@@ -240,14 +242,16 @@ __global__ void __launch_bounds__(RW_THREADS) rows_bwd_kernel(const RowsArgs p) 
     load_row<NCH>(p.dout + row * p.d, lane, dx1);           // dx1 starts as dout
     float dgs = 0.f;                                        // sum_c dG contribution of this row
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
+    for (int ch = 0; ch < NCH; ++ch) {
+      float m[8];
+      drop_scale8(seed_eff, p.thr16, p.inv_keep, row * p.d + ch * 256 + lane * 8, m);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int i = ch * 8 + e;
-        const float m = drop_scale(seed_eff, p.thr16, p.inv_keep, row * p.d + ch * 256 + lane * 8 + e);
-        dh[i] = p.s * m * dx1[i];
+        dh[i] = p.s * m[e] * dx1[i];
         dgs += p.add_gate ? dh[i] : dh[i] * S.y1[i];
       }
+    }
     if (GATE == VLPET_GATE_SMALL && p.pass == 0) {          // first pass: dG of the sample = sum over its tokens and columns
       dgs = warp_sum(dgs);
       if (lane == 0) atomicAdd(p.dgsum + row / p.L, dgs);
