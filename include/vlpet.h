@@ -121,7 +121,9 @@ VLPET_API int vlpet_k1_bwd(const VlpetK1Desc* desc, const void* x1, const void* 
                  size_t workspace_bytes, void* stream);
 /* Which path vlpet_k1_fwd / _bwd take for this desc under VLPET_IMPL_AUTO: 1 = the fused tcgen05 kernels (large gate, ungated
  * form), 2 = the row-wise gate kernels (middleX / middleY / small gates -- composed with the tcgen05 adapter kernel at tensor-core
- * ranks -- and ranks <= 16 in one launch; csrc/vlpet_rows.cu), 0 = the generic CUDA-core path (fp32, odd shapes) */
+ * ranks -- and ranks <= 16 in one launch; csrc/vlpet_rows.cu), 3 = large gate with 96 < max(r, rg) <= 192 (the rank of the
+ * reference's T5 scripts) composed from the ungated tcgen05 kernels per rank half + one element-wise gate kernel
+ * (csrc/vlpet_wide.cu), 0 = the generic CUDA-core path (fp32, odd shapes) */
 VLPET_API int vlpet_k1_fwd_is_fused(const VlpetK1Desc* desc);
 VLPET_API int vlpet_k1_bwd_is_fused(const VlpetK1Desc* desc);
 

@@ -294,11 +294,70 @@ def test_k1_bf16_error_is_no_worse_than_the_reference_run_in_bf16(V, M):
     assert not worse, worse
 
 
+@pytest.mark.parametrize("M,r,rg,add_gate,s,p_heads", [
+    (700, 192, 192, False, 0.3, 4),     # what the reference's T5 scripts ship (README.md:253): 4 heads x 48, gate dim 192, scale 0.3
+    (16000, 192, 192, False, 1.0, 4),   # the same ranks at a step-sized M, pinned against the reference run in bf16
+    (129, 192, 192, True, 1.0, 4),      # add-gate ablation flag
+    (3000, 136, 96, False, 1.0, 1),     # only the adapter branch is wide, second half = 40 ranks
+    (257, 96, 160, False, 0.7, 4),      # only the gate branch is wide
+])
+def test_k1_wide_rank_matches_oracle_and_reference_bf16(V, M, r, rg, add_gate, s, p_heads):
+    """Ranks above one TMEM bucket (96 < max(r, rg) <= 192; csrc/vlpet_wide.cu): the module composed from the ungated
+    tcgen05 kernels per rank half + one element-wise gate kernel, through the C ABI (`is_fused` == 3), against the fp64
+    oracle on the bf16-rounded inputs.  y1 and T cross HBM in bf16 between the launches -- what the reference does under
+    torch.autocast, where every nn.Linear returns bf16 -- so next to the absolute bars the error is pinned against the
+    reference op sequence run in bf16 on the same inputs (oracle/eager_ref.isolated_pet_step)."""
+    import ctypes as C
+    import vlpet_b200._lib as L_
+    from oracle.eager_ref import isolated_pet_step
+    d = 768
+    desc = L_.K1Desc(M=M, L=0, d=d, r=r, rg=rg, gate=L_.GATE_IDS["large"], add_gate=int(add_gate), dtype=L_.BF16, impl=L_.IMPL_AUTO,
+                     s=s, alpha=1.0, kappa=1.0, p_drop=0.0, seed=0)
+    assert L_.lib.vlpet_k1_fwd_is_fused(C.byref(desc)) == (3 if max(r, rg) > 128 else 1)
+    assert L_.lib.vlpet_k1_bwd_is_fused(C.byref(desc)) == 3
+    rng = np.random.default_rng(1000 + M)
+    x1, x2, dout, p = random_large_case(rng, M, d, r, rg)
+    cfg = O.PetConfig(gate="large", add_gate=add_gate, s=s)
+    out, dx1, dx2, gr = run_k1(V, x1, x2, dout, p, cfg, p_heads, torch.bfloat16, "auto", (1, M, d))
+    o_out, o_dx1, o_dx2, o_gr = oracle_bf16(x1, x2, dout, p, cfg)
+    errs = {"out": rel(out, o_out), "dx1": rel(dx1, o_dx1), "dx2": rel(dx2, o_dx2)}
+    errs.update({"d" + k: rel(v, o_gr[k].reshape(np.shape(v))) for k, v in gr.items()})
+    print("errors vs the exact oracle:", {k: float("%.2e" % e) for k, e in errs.items()})
+    for k in ("out", "dx1", "dx2"):
+        assert errs[k] < 4e-3, (k, errs[k])      # bf16-typed results (1.6e-3 is their own storage rounding) behind bf16-stored y1 / T
+    for k, e in errs.items():
+        if k not in ("out", "dx1", "dx2"):
+            assert e < 6e-3, (k, e)              # the bar of the fused backward against exact intermediates (DESIGN.md section 2)
+    if add_gate or s != 1.0:
+        return                           # isolated_pet_step is the plain form (mul gate, s = 1)
+    bf = torch.bfloat16
+    pr = {k: bf16_round(v).reshape(np.shape(v)) for k, v in p.items()}
+    t1, t2 = dev(x1, bf).requires_grad_(), dev(x2, bf).requires_grad_()
+    P = {k: dev(pr[k], torch.float32).requires_grad_() for k in ("Wd", "bd", "Wu", "bu", "Gd", "gbd", "Gu", "gbu")}
+    with torch.autocast("cuda", dtype=bf):
+        o_ref = isolated_pet_step(t1, t2, dev(dout, bf), P, nheads=p_heads)
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    cols = {"out": (out, f(o_ref).reshape(M, d), o_out), "dx1": (dx1, f(t1.grad).reshape(M, d), o_dx1),
+            "dx2": (dx2, f(t2.grad).reshape(M, d), o_dx2)}
+    for k in P:
+        cols["d" + k] = (gr[k], f(P[k].grad).reshape(np.shape(gr[k])), o_gr[k].reshape(np.shape(gr[k])))
+    worse = []
+    for name, (ours, theirs, exact) in cols.items():
+        e_o, e_r = rel(ours, exact), rel(theirs, exact)
+        print(f"{name:5s}: ours {e_o:.2e}   reference-bf16 {e_r:.2e}")
+        if e_o > 1.5 * e_r + 1e-6:
+            worse.append((name, e_o, e_r))
+    assert not worse, worse
+
+
 @pytest.mark.parametrize("gate,r,B,L,add_gate,s", [
     ("middle_x", 96, 7, 92, False, 1.0), ("middle_y", 96, 7, 92, False, 1.0), ("small", 96, 7, 92, False, 1.0),
     ("middle_x", 96, 3, 56, True, 0.3), ("middle_y", 96, 3, 56, True, 0.3), ("small", 96, 3, 56, True, 0.3),
     ("small", 4, 9, 56, False, 1.0), ("middle_x", 4, 5, 56, False, 1.0), ("middle_y", 4, 5, 56, False, 0.3), ("none", 4, 5, 56, False, 1.0),
     ("small", 16, 4, 40, False, 1.0), ("small", 8, 300, 56, False, 1.0),
+    # r = 192: what the reference's T5 middleX / middleY / small scripts ship (README.md:300-334); the adapter runs as two
+    # rank halves of the ungated tcgen05 kernels (csrc/vlpet_wide.cu)
+    ("middle_x", 192, 5, 56, False, 0.3), ("middle_y", 192, 5, 56, False, 0.3), ("small", 192, 6, 92, False, 0.3),
 ])
 def test_k1_rowwise_gates_match_oracle(V, gate, r, B, L, add_gate, s):
     """The row-wise path (csrc/vlpet_rows.cu): middleX / middleY / small gates at d = 768 -- r = 96 composed with the
@@ -329,8 +388,9 @@ def test_k1_rowwise_gates_match_oracle(V, gate, r, B, L, add_gate, s):
     for k, v in gr.items():
         errs["d" + k] = rel(v, np.asarray(g_x[k]).reshape(np.shape(v)))
     print({k: float("%.2e" % e) for k, e in errs.items()})
+    bar = 4e-3 if r > 96 else 3e-3                       # r > 96: dx2 is accumulated over two rank halves, one more bf16 rounding
     for k in ("out", "dx1", "dx2"):
-        assert errs[k] < 3e-3, (k, errs[k])              # bf16-typed results: 1.6e-3 of that is the storage rounding itself
+        assert errs[k] < bar, (k, errs[k])               # bf16-typed results: 1.6e-3 of that is the storage rounding itself
     for k, e in errs.items():
         if k not in ("out", "dx1", "dx2"):
             assert e < 6e-3, (k, e)                       # fp32 gradients of contractions over bf16-stored operands

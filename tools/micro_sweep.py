@@ -56,8 +56,6 @@ for L_seq in a.lens:
         gw1, gw2, gb, gz = mk(d, std=0.05), mk(2 * d, std=0.05), mk(1, std=0.02), mk(d, std=0.05)
         f32 = lambda t: torch.zeros(t.shape, dtype=torch.float32, device="cuda")  # noqa: E731
         for gate in a.gates:
-            if r > 128 and gate != "large":     # no shipped script combines r = 192 with a middle / small gate (T5 ships r = 192 large)
-                continue
             desc = L.K1Desc(M=M, L=L_seq, d=d, r=r, rg=r if gate == "large" else 0, gate=L.GATE_IDS[gate], add_gate=0, dtype=L.BF16,
                             impl=L.IMPL_AUTO, s=1.0, alpha=1.0, kappa=1.0, p_drop=0.0, seed=0, seed_dev=None)
             w = L.K1Params(Wd=p_(Wd), bd=p_(bd), Wu=p_(Wu), bu=p_(bu))
@@ -97,7 +95,8 @@ for L_seq in a.lens:
             print(json.dumps(rec), flush=True)
             del wsf, wsb
 doc = {"what": "K1 micro sweep (SURVEY 8d): C-ABI calls replayed from CUDA graphs, L2 flushed between replays, median",
-       "d": d, "dtype": "bf16", "hbm_peak_GBps": peak, "paths": {"1": "fused tcgen05", "2": "row-wise (+ tcgen05 adapter kernel at r >= 24)",
+       "d": d, "dtype": "bf16", "hbm_peak_GBps": peak, "paths": {"1": "fused tcgen05", "2": "row-wise (+ tcgen05 adapter kernel at r >= 24, two rank halves at r > 96)",
+                                                               "3": "large gate at 96 < r <= 192: ungated tcgen05 kernels per rank half + element-wise gate kernel",
                                                                "0": "generic CUDA-core path"},
        "results": results}
 with open(a.out, "w") as fh:

@@ -64,6 +64,8 @@ bool use_fused_fwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC &
 bool use_fused_bwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && fused_k1_bwd_supported(D); }
 bool use_rows_fwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && !use_fused_fwd(D) && rows_k1_supported(D, false); }
 bool use_rows_bwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && !use_fused_bwd(D) && rows_k1_supported(D, true); }
+bool use_wide_fwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && !use_fused_fwd(D) && !use_rows_fwd(D) && wide_k1_supported(D, false); }
+bool use_wide_bwd(const VlpetK1Desc& D) { return D.impl != VLPET_IMPL_GENERIC && !use_fused_bwd(D) && !use_rows_bwd(D) && wide_k1_supported(D, true); }
 }  // namespace
 }  // namespace vlpet
 
@@ -87,16 +89,22 @@ int vlpet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
 }
 
 // ---- K1 ----------------------------------------------------------------------------------------------------
-int vlpet_k1_fwd_is_fused(const VlpetK1Desc* D) { return !D ? 0 : (use_fused_fwd(*D) ? 1 : (use_rows_fwd(*D) ? 2 : 0)); }
-int vlpet_k1_bwd_is_fused(const VlpetK1Desc* D) { return !D ? 0 : (use_fused_bwd(*D) ? 1 : (use_rows_bwd(*D) ? 2 : 0)); }
+int vlpet_k1_fwd_is_fused(const VlpetK1Desc* D) {
+  return !D ? 0 : (use_fused_fwd(*D) ? 1 : (use_rows_fwd(*D) ? 2 : (use_wide_fwd(*D) ? 3 : 0)));
+}
+int vlpet_k1_bwd_is_fused(const VlpetK1Desc* D) {
+  return !D ? 0 : (use_fused_bwd(*D) ? 1 : (use_rows_bwd(*D) ? 2 : (use_wide_bwd(*D) ? 3 : 0)));
+}
 
 size_t vlpet_k1_fwd_workspace_bytes(const VlpetK1Desc* D) {
   if (!D) return 0;
-  return use_fused_fwd(*D) ? fused_k1_fwd_ws(*D) : (use_rows_fwd(*D) ? rows_k1_fwd_ws(*D) : generic_k1_fwd_ws(*D));
+  return use_fused_fwd(*D) ? fused_k1_fwd_ws(*D)
+                           : (use_rows_fwd(*D) ? rows_k1_fwd_ws(*D) : (use_wide_fwd(*D) ? wide_k1_fwd_ws(*D) : generic_k1_fwd_ws(*D)));
 }
 size_t vlpet_k1_bwd_workspace_bytes(const VlpetK1Desc* D) {
   if (!D) return 0;
-  return use_fused_bwd(*D) ? fused_k1_bwd_ws(*D) : (use_rows_bwd(*D) ? rows_k1_bwd_ws(*D) : generic_k1_bwd_ws(*D));
+  return use_fused_bwd(*D) ? fused_k1_bwd_ws(*D)
+                           : (use_rows_bwd(*D) ? rows_k1_bwd_ws(*D) : (use_wide_bwd(*D) ? wide_k1_bwd_ws(*D) : generic_k1_bwd_ws(*D)));
 }
 
 int vlpet_k1_fwd(const VlpetK1Desc* D, const void* x1, const void* x2, const VlpetK1Params* w, void* out, void* ws,
@@ -107,6 +115,7 @@ int vlpet_k1_fwd(const VlpetK1Desc* D, const void* x1, const void* x2, const Vlp
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_fused_fwd(*D)) return fused_k1_fwd(*D, x1, x2, *w, out, ws, ws_bytes, st);
   if (use_rows_fwd(*D)) return rows_k1_fwd(*D, x1, x2, *w, out, ws, ws_bytes, st);
+  if (use_wide_fwd(*D)) return wide_k1_fwd(*D, x1, x2, *w, out, ws, ws_bytes, st);
   if (D->impl == VLPET_IMPL_FUSED)
     return fail(VLPET_E_UNSUPPORTED, "k1_fwd: fused kernel does not cover d=%d r=%d rg=%d gate=%d dtype=%d", D->d, D->r,
                 D->rg, D->gate, D->dtype);
@@ -123,6 +132,8 @@ int vlpet_k1_bwd(const VlpetK1Desc* D, const void* x1, const void* x2, const voi
     return fused_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
   if (use_rows_bwd(*D))
     return rows_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  if (use_wide_bwd(*D))
+    return wide_k1_bwd(*D, x1, x2, dout, *w, dx1, dx2, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
   if (D->impl == VLPET_IMPL_FUSED)
     return fail(VLPET_E_UNSUPPORTED, "k1_bwd: fused kernel does not cover d=%d r=%d rg=%d gate=%d dtype=%d", D->d, D->r,
                 D->rg, D->gate, D->dtype);

@@ -203,6 +203,16 @@ int fused_k2_bwd(const VlpetK2Desc&, const void* kv, const void* dout, const Vlp
 // same with the x2 scale of the K1 form: dkv = kappa * dout + adapter-path gradient (the row-wise gate path, vlpet_rows.cu)
 int fused_k2_bwd_kappa(const VlpetK2Desc&, float kappa, const void* kv, const void* dout, const VlpetK2Params&, void* dkv,
                        const VlpetK2Grads&, void* ws, size_t ws_bytes, cudaStream_t);
+// The ungated backward as a building block of composed paths (vlpet_wide.cu: ranks above one TMEM bucket as two rank
+// halves): kap_src = the [M, d] tensor the kappa term of dkv is read from (nullptr: dout itself; dkv for "accumulate into
+// the previous half's result", in place), ldo_wu = row pitch in floats of the dWu buffer (0: r; a column slice of a wider
+// [d, r_total] gradient otherwise).
+struct BwdExtras {
+  const void* kap_src;
+  int64_t ldo_wu;
+};
+int fused_k2_bwd_ex(const VlpetK2Desc&, float kappa, const void* kv, const void* dout, const VlpetK2Params&, void* dkv,
+                    const VlpetK2Grads&, const BwdExtras&, void* ws, size_t ws_bytes, cudaStream_t);
 // column sums of a [M, pitch] bf16 matrix (first ncols columns) accumulated into out[ncols] (vlpet_k1_bwd_sm100.cu)
 int colsum_bf16(const void* A, int pitch, int ncols, float* out, int64_t M, int sms, cudaStream_t st);
 
@@ -215,11 +225,27 @@ int rows_k1_fwd(const VlpetK1Desc&, const void* x1, const void* x2, const VlpetK
 int rows_k1_bwd(const VlpetK1Desc&, const void* x1, const void* x2, const void* dout, const VlpetK1Params&, void* dx1, void* dx2,
                 const VlpetK1Grads&, void* ws, size_t ws_bytes, cudaStream_t);
 
+// ---- K1, large gate, 96 < max(r, rg) <= 192: composed from the ungated fused kernels per rank half, vlpet_wide.cu -------
+bool wide_k1_supported(const VlpetK1Desc&, bool bwd);
+size_t wide_k1_fwd_ws(const VlpetK1Desc&);
+size_t wide_k1_bwd_ws(const VlpetK1Desc&);
+int wide_k1_fwd(const VlpetK1Desc&, const void* x1, const void* x2, const VlpetK1Params&, void* out, void* ws, size_t ws_bytes,
+                cudaStream_t);
+int wide_k1_bwd(const VlpetK1Desc&, const void* x1, const void* x2, const void* dout, const VlpetK1Params&, void* dx1, void* dx2,
+                const VlpetK1Grads&, void* ws, size_t ws_bytes, cudaStream_t);
+
+// the adapter branch alone at 96 < r <= 192 (y1 = kappa x2 + alpha (Up(gelu_new(Down x2)) + bu)) for the row-wise gates
+bool wide_adapter_supported(const VlpetK1Desc&, bool bwd);
+size_t wide_adapter_ws(const VlpetK1Desc&, bool bwd);
+int wide_adapter_fwd(const VlpetK1Desc&, const void* x2, const VlpetK1Params&, void* y1, void* ws, size_t ws_bytes, cudaStream_t);
+int wide_adapter_bwd(const VlpetK1Desc&, const void* x2, const void* dy1, const VlpetK1Params&, void* dx2, const VlpetK1Grads&,
+                     void* ws_fwd, void* ws, size_t ws_bytes, cudaStream_t);
+
 // ---- token-contracted weight-gradient GEMM (tcgen05), vlpet_wgrad_sm100.cu -----------------------------------
 bool wgrad_sm100_supported(int d, int nout);
 int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void* const* B, const int64_t* ldb,
                 const int* nb_valid, float* const* out, float* const* bias, const float* scale, const int* transposed,
-                int64_t Mtok, int d, int nout, int sm_count, cudaStream_t st);
+                int64_t Mtok, int d, int nout, int sm_count, cudaStream_t st, const int64_t* ldo = nullptr);
 int device_sm_count();
 // LayerNorm behind the PET sites, vlpet_layernorm.cu
 bool layernorm_supported(int d, int dtype);

@@ -184,7 +184,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
                     const __grid_constant__ CUtensorMap tm_dx2, const __grid_constant__ CUtensorMap tm_du,
                     const __grid_constant__ CUtensorMap tm_dt, const __grid_constant__ CUtensorMap tm_wd,
                     const __grid_constant__ CUtensorMap tm_gd, const __grid_constant__ CUtensorMap tm_wu,
-                    const __grid_constant__ CUtensorMap tm_gu, const BParams p) {
+                    const __grid_constant__ CUtensorMap tm_gu, const __grid_constant__ CUtensorMap tm_kap, const BParams p) {
   using C = BCfg<R>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -222,7 +222,7 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
     ptx::mbar_init(bar(B_XCHG), (uint32_t)nsplit);
     ptx::fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_dout); }
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_dout); ptx::prefetch_tmap(&tm_kap); }
   if (warp == 3 && lane == 0) {
     ptx::prefetch_tmap(&tm_wd); ptx::prefetch_tmap(&tm_gd); ptx::prefetch_tmap(&tm_wu); ptx::prefetch_tmap(&tm_gu);
   }
@@ -283,9 +283,9 @@ k1_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_cons
             } else if (GATED) {
               ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), XCH_BYTES);
               ptx::tma_load_2d_hint(xdst, &tm_dout, c * CH, row0, bar(B_XFULL + sx), ptx::L2_EVICT_FIRST);
-            } else if (p.kappa != 0.f) {             // ungated with an x2 scale: dx2 = kappa dout + da Wd needs dout_c again
-              ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), XCH_BYTES);
-              ptx::tma_load_2d_hint(xdst, &tm_dout, c * CH, row0, bar(B_XFULL + sx), ptx::L2_EVICT_FIRST);
+            } else if (p.kappa != 0.f) {             // ungated with an x2 scale: dx2 = kappa K + da Wd; K = dout again, or
+              ptx::mbar_arrive_expect_tx(bar(B_XFULL + sx), XCH_BYTES);   // another [M, d] tensor (BwdExtras::kap_src)
+              ptx::tma_load_2d_hint(xdst, &tm_kap, c * CH, row0, bar(B_XFULL + sx), ptx::L2_EVICT_FIRST);
             } else {
               ptx::mbar_arrive(bar(B_XFULL + sx));   // the stage is only the staging buffer of dx2_c
             }
@@ -1044,12 +1044,12 @@ int launch(const VlpetK1Desc& D, const CUtensorMap* m, const BParams& p0, int sm
     attr[0].val.clusterDim.x = (unsigned)p.nsplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3((unsigned)(tiles * p.nsplit)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
-    VLPET_CUDA_OK(cudaLaunchKernelEx(&cfg, kern_split, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], p));
+    VLPET_CUDA_OK(cudaLaunchKernelEx(&cfg, kern_split, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], p));
     count_launch();
     return 0;
   }
   const int grid = (int)(tiles < sms ? tiles : sms);
-  kern<<<grid, NUM_THREADS, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], p);
+  kern<<<grid, NUM_THREADS, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], p);
   VLPET_LAUNCH_OK();
   return 0;
 }
@@ -1061,13 +1061,14 @@ int pick_R2(int r, int rg) {
 
 // shared driver of the gated (K1, large gate) and ungated (K2) backward
 int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, const void* dout, const VlpetK1Params& w,
-            void* dx1, void* dx2, const VlpetK1Grads& G, void* ws, size_t ws_bytes, cudaStream_t st) {
+            void* dx1, void* dx2, const VlpetK1Grads& G, void* ws, size_t ws_bytes, cudaStream_t st,
+            const BwdExtras* ex = nullptr) {
   const int rg = gated ? D.rg : D.r;
   Scratch s = carve(D.M, D.d, D.r, rg, gated, ws);
   if (!ws || ws_bytes < s.bytes) return fail(VLPET_E_WORKSPACE, "bwd(fused): workspace %zu < %zu bytes", ws_bytes, s.bytes);
   const int R = pick_R2(D.r, rg);
   const int sms = device_sm_count();
-  CUtensorMap m[11];
+  CUtensorMap m[12];
   const uint64_t M = (uint64_t)D.M, d = (uint64_t)D.d;
   VLPET_TRY(make_map_bf16(&m[0], gated ? x1 : x2, M, d, d, TILE_M, CH, false));
   VLPET_TRY(make_map_bf16(&m[1], x2, M, d, d, TILE_M, CH, false));
@@ -1080,6 +1081,7 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   VLPET_TRY(make_map_bf16(&m[8], gated ? w.Gd : w.Wd, (uint64_t)rg, d, d, (uint32_t)R, CH, true));
   VLPET_TRY(make_map_bf16(&m[9], w.Wu, d, (uint64_t)D.r, (uint64_t)D.r, CH, CH, true));
   VLPET_TRY(make_map_bf16(&m[10], gated ? w.Gu : w.Wu, d, (uint64_t)rg, (uint64_t)rg, CH, CH, true));
+  VLPET_TRY(make_map_bf16(&m[11], (ex && ex->kap_src) ? ex->kap_src : dout, M, d, d, TILE_M, CH, false));
   BParams p;
   p.M = D.M; p.d = D.d; p.r = D.r; p.rg = rg; p.add_gate = D.add_gate;
   p.s = D.s; p.alpha = D.alpha; p.kappa = D.kappa;
@@ -1131,7 +1133,7 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
   if (!(parts & 4)) return 0;
   // ---- weight gradients: dWu = du^T z (+dbu), dGu = dt^T q (+dgbu), dWd = (x2^T da)^T, dGd = (x1^T dp)^T
   //      (ungated: du = alpha*dout, so A = dout with scale alpha)
-  const void* A[4]; const void* B[4]; int64_t lda[4], ldb[4]; int nbv[4], tr[4]; float* out[4]; float* bias[4]; float sc[4];
+  const void* A[4]; const void* B[4]; int64_t lda[4], ldb[4], ldo[4]; int nbv[4], tr[4]; float* out[4]; float* bias[4]; float sc[4];
   auto run = [&](const int* which, int n, int nout) -> int {
     int k = 0;
     for (int i = 0; i < n; ++i) {
@@ -1147,10 +1149,11 @@ int run_bwd(bool gated, const VlpetK1Desc& D, const void* x1, const void* x2, co
       nbv[k] = (q < 2) ? nout + 1 : nout;
       tr[k] = q >= 2;
       out[k] = o; bias[k] = b; sc[k] = (q == 0 && !gated) ? D.alpha : 1.0f;
+      ldo[k] = (q == 0 && ex && ex->ldo_wu > 0) ? ex->ldo_wu : 0;
       ++k;
     }
     if (k == 0) return 0;
-    return wgrad_sm100(k, A, lda, B, ldb, nbv, out, bias, sc, tr, D.M, D.d, nout, sms, st);
+    return wgrad_sm100(k, A, lda, B, ldb, nbv, out, bias, sc, tr, D.M, D.d, nout, sms, st, ldo);
   };
   if (!gated) {
     const int ad[2] = {0, 2};
@@ -1234,6 +1237,22 @@ int fused_k2_bwd_kappa(const VlpetK2Desc& D, float kappa, const void* kv, const 
   VlpetK1Desc K = k2_as_k1(D);
   K.kappa = kappa;
   return run_bwd(false, K, nullptr, kv, dout, P, nullptr, dkv, G, ws, ws_bytes, st);
+}
+
+int fused_k2_bwd_ex(const VlpetK2Desc& D, float kappa, const void* kv, const void* dout, const VlpetK2Params& w, void* dkv,
+                    const VlpetK2Grads& g, const BwdExtras& ex, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!aligned16(w.Wd) || !aligned16(w.Wu) || !aligned16(w.bu))
+    return fail(VLPET_E_ALIGN, "k2_bwd(fused): weights must be 16-byte aligned");
+  if (ex.kap_src && !aligned16(ex.kap_src)) return fail(VLPET_E_ALIGN, "k2_bwd(fused): kap_src must be 16-byte aligned");
+  VlpetK1Params P;
+  memset(&P, 0, sizeof(P));
+  P.Wd = w.Wd; P.bd = w.bd; P.Wu = w.Wu; P.bu = w.bu;
+  VlpetK1Grads G;
+  memset(&G, 0, sizeof(G));
+  G.dWd = g.dWd; G.dbd = g.dbd; G.dWu = g.dWu; G.dbu = g.dbu;
+  VlpetK1Desc K = k2_as_k1(D);
+  K.kappa = kappa;
+  return run_bwd(false, K, nullptr, kv, dout, P, nullptr, dkv, G, ws, ws_bytes, st, &ex);
 }
 
 int fused_k2_bwd(const VlpetK2Desc& D, const void* kv, const void* dout, const VlpetK2Params& w, void* dkv,

@@ -417,9 +417,11 @@ struct RowsWs {
   __nv_bfloat16 *y1, *dy1, *du, *zs, *das;
   float *gmean, *dgsum, *pWu, *pWd;
   void* sub;          // workspace of the composed tcgen05 backward
-  size_t sub_bytes, bytes;
+  void* wfwd;         // r > 96: workspace of the two-half adapter forward (vlpet_wide.cu)
+  size_t sub_bytes, wfwd_bytes, bytes;
   int pz, r8;
 };
+bool wide_mode(const VlpetK1Desc& D) { return D.r > 96; }   // the adapter runs as two rank halves (vlpet_wide.cu)
 RowsWs carve_rows(const VlpetK1Desc& D, bool bwd, void* ws) {
   RowsWs w;
   memset(&w, 0, sizeof(w));
@@ -430,6 +432,10 @@ RowsWs carve_rows(const VlpetK1Desc& D, bool bwd, void* ws) {
   w.pz = w.r8 + 8;
   if (B) { w.gmean = a.take<float>((size_t)B); if (bwd) w.dgsum = a.take<float>((size_t)B); }
   if (!inl) w.y1 = a.take<__nv_bfloat16>((size_t)D.M * D.d);
+  if (!inl && wide_mode(D)) {
+    w.wfwd_bytes = wide_adapter_ws(D, false);
+    w.wfwd = a.take<char>(w.wfwd_bytes);
+  }
   if (bwd) {
     if (inl) {
       w.du = a.take<__nv_bfloat16>((size_t)D.M * D.d);
@@ -441,7 +447,7 @@ RowsWs carve_rows(const VlpetK1Desc& D, bool bwd, void* ws) {
       VlpetK2Desc K2;
       memset(&K2, 0, sizeof(K2));
       K2.M = D.M; K2.d = D.d; K2.r = D.r; K2.dtype = D.dtype;
-      w.sub_bytes = fused_k2_bwd_ws(K2);
+      w.sub_bytes = wide_mode(D) ? wide_adapter_ws(D, true) : fused_k2_bwd_ws(K2);
       w.sub = a.take<char>(w.sub_bytes);
     }
   }
@@ -474,6 +480,7 @@ bool rows_k1_supported(const VlpetK1Desc& D, bool bwd) {
   if (device_sm_count() <= 0) return false;
   if (inline_mode(D)) return !bwd || wgrad_sm100_supported(D.d, r8_of(D.r));
   if (D.gate == VLPET_GATE_NONE) return false;      // the ungated form at tensor-core ranks IS the fused kernel (K2 form)
+  if (wide_mode(D)) return wide_adapter_supported(D, bwd);
   VlpetK1Desc A = adapter_desc(D);
   if (!fused_k1_fwd_supported(A)) return false;
   if (bwd) {
@@ -499,7 +506,8 @@ int rows_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const Vlpe
     VlpetK1Params P;
     memset(&P, 0, sizeof(P));
     P.Wd = w.Wd; P.bd = w.bd; P.Wu = w.Wu; P.bu = w.bu;
-    VLPET_TRY(fused_k1_fwd(adapter_desc(D), x2, x2, P, W.y1, nullptr, 0, st));
+    if (wide_mode(D)) VLPET_TRY(wide_adapter_fwd(D, x2, P, W.y1, W.wfwd, W.wfwd_bytes, st));
+    else VLPET_TRY(fused_k1_fwd(adapter_desc(D), x2, x2, P, W.y1, nullptr, 0, st));
     a.has_y1 = 1; a.y1in = W.y1;
   }
   if (D.gate == VLPET_GATE_SMALL) {
@@ -527,7 +535,8 @@ int rows_k1_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const void
   memset(&P, 0, sizeof(P));
   P.Wd = w.Wd; P.bd = w.bd; P.Wu = w.Wu; P.bu = w.bu;
   if (!inl) {
-    VLPET_TRY(fused_k1_fwd(adapter_desc(D), x2, x2, P, W.y1, nullptr, 0, st));     // y1 again: nothing is saved by the forward
+    if (wide_mode(D)) VLPET_TRY(wide_adapter_fwd(D, x2, P, W.y1, W.wfwd, W.wfwd_bytes, st));
+    else VLPET_TRY(fused_k1_fwd(adapter_desc(D), x2, x2, P, W.y1, nullptr, 0, st));     // y1 again: nothing is saved by the forward
     a.has_y1 = 1; a.y1in = W.y1; a.dy1 = W.dy1;
   } else {
     a.du = W.du; a.zs = W.zs; a.das = W.das; a.pz = W.pz; a.r8 = W.r8;
@@ -547,6 +556,12 @@ int rows_k1_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const void
   VLPET_TRY(launch_rows_d(true, a, sms, st));
   if (!inl) {
     // adapter backward through the ungated tcgen05 kernels with dout := dy1: dx2 = kappa dy1 + (alpha (dy1 Wu) gelu') Wd
+    if (wide_mode(D)) {
+      VlpetK1Grads Ga;
+      memset(&Ga, 0, sizeof(Ga));
+      Ga.dWd = G.dWd; Ga.dbd = G.dbd; Ga.dWu = G.dWu; Ga.dbu = G.dbu;
+      return wide_adapter_bwd(D, x2, W.dy1, P, dx2, Ga, W.wfwd, W.sub, W.sub_bytes, st);
+    }
     VlpetK2Desc K2;
     memset(&K2, 0, sizeof(K2));
     K2.M = D.M; K2.d = D.d; K2.r = D.r; K2.dtype = D.dtype; K2.sf = D.alpha;

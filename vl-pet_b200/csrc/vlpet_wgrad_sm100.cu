@@ -40,7 +40,8 @@ struct alignas(64) WgradMaps {
   CUtensorMap b[4];
 };
 struct WgradArgs {
-  float* out[4];        // [d, nout] (transposed == 0) or [nout, d] (transposed == 1), fp32, accumulated into
+  float* out[4];        // [d, nout] (transposed == 0, row pitch ldo floats) or [nout, d] (transposed == 1), fp32, accumulated into
+  int64_t ldo[4];       // row pitch of a non-transposed output (a column slice of a wider matrix: rank halves, vlpet_wide.cu)
   float* bias[4];       // [d] or nullptr: receives column `nout` of D (the ones-column trick)
   float scale[4];
   int transposed[4];
@@ -126,6 +127,7 @@ wgrad_sm100_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) {
     ptx::mbar_wait_dbg(bar(2 * NST), 0, p.dbg, __LINE__);
     ptx::tc_fence_after();
     float* out = p.out[pair];
+    const int64_t ldo = p.ldo[pair];
     float* bias = p.bias[pair];
     const float sc = p.scale[pair];
     const int transposed = p.transposed[pair];
@@ -175,11 +177,11 @@ wgrad_sm100_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) {
         for (int r = ew; r < SLAB; r += 4)
           for (int j = lane; j < nv; j += 32) {
             const float4 q = *reinterpret_cast<const float4*>(stage + r * STG + j * 4);
-            ptx::red_add_v4(out + (size_t)(c0 + r) * p.nout + j * 4, q.x, q.y, q.z, q.w);
+            ptx::red_add_v4(out + (size_t)(c0 + r) * ldo + j * 4, q.x, q.y, q.z, q.w);
           }
       } else {
         for (int r = ew; r < SLAB; r += 4)
-          for (int j = lane; j < p.nout; j += 32) atomicAdd(out + (size_t)(c0 + r) * p.nout + j, stage[r * STG + j]);
+          for (int j = lane; j < p.nout; j += 32) atomicAdd(out + (size_t)(c0 + r) * ldo + j, stage[r * STG + j]);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
@@ -206,7 +208,7 @@ bool wgrad_sm100_supported(int d, int nout) {
 // ones column), out / bias fp32 accumulated into.
 int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void* const* B, const int64_t* ldb,
                 const int* nb_valid, float* const* out, float* const* bias, const float* scale, const int* transposed,
-                int64_t Mtok, int d, int nout, int sm_count, cudaStream_t st) {
+                int64_t Mtok, int d, int nout, int sm_count, cudaStream_t st, const int64_t* ldo) {
   if (npairs < 1 || npairs > 4) return fail(VLPET_E_BADARG, "wgrad: 1..4 pairs");
   if (!wgrad_sm100_supported(d, nout)) return fail(VLPET_E_UNSUPPORTED, "wgrad: d=%d nout=%d", d, nout);
   WgradMaps maps;
@@ -217,6 +219,9 @@ int wgrad_sm100(int npairs, const void* const* A, const int64_t* lda, const void
     VLPET_TRY(make_map_bf16(&maps.a[i], A[i], (uint64_t)Mtok, (uint64_t)d, (uint64_t)lda[i], KT, 64, false));
     VLPET_TRY(make_map_bf16(&maps.b[i], B[i], (uint64_t)Mtok, (uint64_t)nb_valid[i], (uint64_t)ldb[i], KT, 64, false));
     a.out[i] = out[i]; a.bias[i] = bias[i]; a.scale[i] = scale[i]; a.transposed[i] = transposed[i];
+    a.ldo[i] = (ldo && ldo[i] > 0) ? ldo[i] : nout;
+    if (!transposed[i] && (a.ldo[i] & 3) != 0 && (nout & 3) == 0)
+      return fail(VLPET_E_ALIGN, "wgrad: output pitch %lld must be a multiple of 4 floats", (long long)a.ldo[i]);
     if (nb_valid[i] > nbmax) nbmax = nb_valid[i];
   }
   for (int i = npairs; i < 4; ++i) { maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; }
