@@ -521,6 +521,40 @@ def test_k2_matches_reference_golden(V, path, dtype, tol):
         assert rel(f(P[k].grad), ref_gr[k]) < tol, k
 
 
+@pytest.mark.parametrize("M,r,sf", [(900, 4, 1.0), (37, 4, 0.7), (4000, 8, 1.0), (513, 16, 2.0), (2000, 6, 1.0)])
+def test_k2_small_rank_rowwise_matches_oracle(V, M, r, sf):
+    """Decoder value parallel adapter at ranks too small for a tensor-core tile (BASELINE config 4: r = 4): the ungated form
+    of the row-wise kernels (csrc/vlpet_rows.cu; `vlpet_k2_is_fused` == 2) against the fp64 oracle on the bf16-rounded inputs
+    (adapters/adapter_controller.py:149-162)."""
+    import ctypes as C
+    import vlpet_b200._lib as L
+    d = 768
+    desc = L.K2Desc(M=M, d=d, r=r, dtype=L.BF16, impl=L.IMPL_AUTO, sf=sf)
+    assert L.lib.vlpet_k2_is_fused(C.byref(desc)) == (2 if r < 8 else 1)     # r = 8, 16 fit the smallest tcgen05 rank bucket
+    rng = np.random.default_rng(M + r)
+    kv, y, dout = rng.standard_normal((M, d)), 0.5 * rng.standard_normal((M, d)), rng.standard_normal((M, d))
+    p = {"Wd": rng.standard_normal((r, d)) * 0.05, "bd": rng.standard_normal(r) * 0.02,
+         "Wu": rng.standard_normal((d, r)) * 0.05, "bu": rng.standard_normal(d) * 0.02}
+    bf = torch.bfloat16
+    tkv, ty = dev(kv, bf).requires_grad_(), dev(y, bf).requires_grad_()
+    P = {k: dev(v, bf).float().requires_grad_() for k, v in p.items()}
+    out = V.vpa(tkv, ty, P["Wd"], P["bd"], P["Wu"], P["bu"], sf)
+    out.backward(dev(dout, bf))
+    torch.cuda.synchronize()
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    kvr, yr, dor = bf16_round(kv), bf16_round(y), bf16_round(dout)
+    pr = {k: bf16_round(v).reshape(np.shape(v)) for k, v in p.items()}
+    ref_out, cache = O.vpa_fwd(kvr, yr, pr, sf)
+    bf16_check(f(out), ref_out, TOL_BF16)
+    cfg = O.PetConfig(gate="none", s=1.0, alpha=sf, kappa=0.0)
+    _, cx = O.gated_pet_fwd(yr, kvr, pr, cfg)
+    _, x_dkv, g_x = O.gated_pet_bwd(dor, pr, cfg, cx)
+    assert rel(f(ty.grad), dor) == 0.0                     # the residual input's gradient is dout itself
+    assert rel(f(tkv.grad), x_dkv) < 3e-3                  # bf16-typed result (1.6e-3 is its own storage rounding)
+    for k in ("Wd", "bd", "Wu", "bu"):
+        assert rel(f(P[k].grad), g_x[k].reshape(np.shape(p[k]))) < 6e-3, k
+
+
 @pytest.mark.parametrize("M,d,r,sf", [(1, 768, 96, 1.0), (200, 768, 96, 1.0), (1300, 768, 96, 0.7), (333, 768, 48, 1.0),
                                       (640, 256, 32, 2.0), (148 * 128 + 500, 768, 96, 1.0),
                                       (148 * 128 * 2 + 300, 768, 96, 0.7)])   # two waves: the ungated CTA-pair forward

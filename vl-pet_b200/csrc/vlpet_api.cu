@@ -246,19 +246,44 @@ static int check_k2(const VlpetK2Desc* D, const VlpetK2Params* w) {
   return 0;
 }
 static bool use_fused_k2(const VlpetK2Desc& D) { return D.impl != VLPET_IMPL_GENERIC && fused_k2_supported(D); }
-size_t vlpet_k2_fwd_workspace_bytes(const VlpetK2Desc* D) { return D ? generic_k2_fwd_ws(*D) : 0; }
+// ranks too small for a tensor-core tile (r <= 16, e.g. BASELINE config 4: r = 4): the ungated form of the row-wise K1
+// kernels (csrc/vlpet_rows.cu, one launch forward): out = y + 1 * (0 * kv + sf * (Up(gelu_new(Down kv)) + bu))
+static VlpetK1Desc k2_rows_desc(const VlpetK2Desc& D) {
+  VlpetK1Desc K;
+  memset(&K, 0, sizeof(K));
+  K.M = D.M; K.L = 1; K.d = D.d; K.r = D.r; K.rg = 0; K.gate = VLPET_GATE_NONE; K.dtype = D.dtype; K.impl = D.impl;
+  K.s = 1.0f; K.alpha = D.sf; K.kappa = 0.0f;
+  return K;
+}
+static bool use_rows_k2(const VlpetK2Desc& D, bool bwd) {
+  return D.impl != VLPET_IMPL_GENERIC && !use_fused_k2(D) && D.r <= 16 && rows_k1_supported(k2_rows_desc(D), bwd);
+}
+static VlpetK1Params k2_as_k1_params(const VlpetK2Params& w) {
+  VlpetK1Params P;
+  memset(&P, 0, sizeof(P));
+  P.Wd = w.Wd; P.bd = w.bd; P.Wu = w.Wu; P.bu = w.bu;
+  return P;
+}
+size_t vlpet_k2_fwd_workspace_bytes(const VlpetK2Desc* D) {
+  if (!D) return 0;
+  const size_t a = generic_k2_fwd_ws(*D), b = use_rows_k2(*D, false) ? rows_k1_fwd_ws(k2_rows_desc(*D)) : 0;
+  return a > b ? a : b;
+}
 size_t vlpet_k2_bwd_workspace_bytes(const VlpetK2Desc* D) {
   if (!D) return 0;
   const size_t a = generic_k2_bwd_ws(*D), b = use_fused_k2(*D) ? fused_k2_bwd_ws(*D) : 0;
-  return a > b ? a : b;   // dkv == NULL falls back to the generic path even when the shape qualifies
+  const size_t c = use_rows_k2(*D, true) ? rows_k1_bwd_ws(k2_rows_desc(*D)) : 0;
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);   // dkv == NULL falls back to the generic path even when the shape qualifies
 }
-int vlpet_k2_is_fused(const VlpetK2Desc* D) { return D && use_fused_k2(*D) ? 1 : 0; }
+int vlpet_k2_is_fused(const VlpetK2Desc* D) { return !D ? 0 : (use_fused_k2(*D) ? 1 : (use_rows_k2(*D, true) ? 2 : 0)); }
 int vlpet_k2_fwd(const VlpetK2Desc* D, const void* kv, const void* y, const VlpetK2Params* w, void* out, void* ws,
                  size_t ws_bytes, void* stream) {
   VLPET_TRY(check_k2(D, w));
   if (!kv || !out) return fail(VLPET_E_BADARG, "k2_fwd: null activation pointer"); /* y may be NULL: no residual */
   if (y && use_fused_k2(*D) && aligned16(kv) && aligned16(y) && aligned16(out))
     return fused_k2_fwd(*D, kv, y, *w, out, static_cast<cudaStream_t>(stream));
+  if (y && use_rows_k2(*D, false) && aligned16(kv) && aligned16(y) && aligned16(out))
+    return rows_k1_fwd(k2_rows_desc(*D), y, kv, k2_as_k1_params(*w), out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
   if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k2_fwd: fused kernel needs bf16, y != NULL, d %% 128 == 0, r %% 8 == 0, r <= 96");
   return generic_k2_fwd(*D, kv, y, *w, out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
@@ -268,6 +293,14 @@ int vlpet_k2_bwd(const VlpetK2Desc* D, const void* kv, const void* dout, const V
   if (!kv || !dout || !g) return fail(VLPET_E_BADARG, "k2_bwd: null pointer");
   if (dkv && use_fused_k2(*D) && aligned16(kv) && aligned16(dout) && aligned16(dkv))
     return fused_k2_bwd(*D, kv, dout, *w, dkv, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  if (dkv && use_rows_k2(*D, true) && aligned16(kv) && aligned16(dout) && aligned16(dkv)) {
+    VlpetK1Grads G;
+    memset(&G, 0, sizeof(G));
+    G.dWd = g->dWd; G.dbd = g->dbd; G.dWu = g->dWu; G.dbu = g->dbu;
+    // x1 (the residual y) is not needed by the ungated backward and its gradient is dout itself: no dx1 output
+    return rows_k1_bwd(k2_rows_desc(*D), kv, kv, dout, k2_as_k1_params(*w), nullptr, dkv, G, ws, ws_bytes,
+                       static_cast<cudaStream_t>(stream));
+  }
   if (D->impl == VLPET_IMPL_FUSED) return fail(VLPET_E_UNSUPPORTED, "k2_bwd: fused kernel needs bf16, dkv != NULL, d %% 128 == 0, r %% 8 == 0, r <= 96");
   return generic_k2_bwd(*D, kv, dout, *w, dkv, *g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }

@@ -21,8 +21,10 @@
 namespace vlpet {
 namespace {
 
-constexpr int RW_THREADS = 256;   // 8 warps = 8 rows in flight per CTA
+constexpr int RW_THREADS = 256;   // 8 warps = 8 rows in flight per CTA, 2 CTAs per SM
+constexpr int RW_WARPS = RW_THREADS / 32;
 constexpr int RW_MAXR = 16;
+constexpr int RW_NS = 2;          // row stages per warp: the row being processed + the next one in flight
 
 struct RowsArgs {
   int64_t M;
@@ -41,301 +43,418 @@ struct RowsArgs {
   float* dbd;                                          // INLINE backward: fp32 down-projection bias gradient, accumulated into
 };
 
-__device__ __forceinline__ float bf2f(uint32_t v, int hi) { return __uint_as_float(hi ? (v & 0xffff0000u) : (v << 16)); }
 __device__ __forceinline__ uint32_t pack_bf(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-template <int NCH>
-__device__ __forceinline__ void load_row(const __nv_bfloat16* row, int lane, float (&v)[NCH * 8]) {
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + ch * 256 + lane * 8));
-    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { v[ch * 8 + 2 * e] = bf2f(u[e], 0); v[ch * 8 + 2 * e + 1] = bf2f(u[e], 1); }
-  }
-}
-template <int NCH>
-__device__ __forceinline__ void store_row(__nv_bfloat16* row, int lane, const float (&v)[NCH * 8]) {
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    uint4 q;
-    q.x = pack_bf(v[ch * 8 + 0], v[ch * 8 + 1]); q.y = pack_bf(v[ch * 8 + 2], v[ch * 8 + 3]);
-    q.z = pack_bf(v[ch * 8 + 4], v[ch * 8 + 5]); q.w = pack_bf(v[ch * 8 + 6], v[ch * 8 + 7]);
-    *reinterpret_cast<uint4*>(row + ch * 256 + lane * 8) = q;
-  }
-}
-// 8 consecutive bf16 of a shared-memory row -> floats
+// 8 consecutive bf16 at a 16-byte aligned shared-memory address -> floats (one LDS.128 + 8 ALU)
 __device__ __forceinline__ void lds8(const __nv_bfloat16* p, float (&w)[8]) {
   const uint4 q = *reinterpret_cast<const uint4*>(p);
   const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-  for (int e = 0; e < 4; ++e) { w[2 * e] = bf2f(u[e], 0); w[2 * e + 1] = bf2f(u[e], 1); }
+  for (int e = 0; e < 4; ++e) { w[2 * e] = __uint_as_float(u[e] << 16); w[2 * e + 1] = __uint_as_float(u[e] & 0xffff0000u); }
+}
+__device__ __forceinline__ void stg8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 q;
+  q.x = pack_bf(v[0], v[1]); q.y = pack_bf(v[2], v[3]); q.z = pack_bf(v[4], v[5]); q.w = pack_bf(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+__device__ __forceinline__ float dot8(const float (&a)[8], const float (&b)[8], float acc) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc = fmaf(a[e], b[e], acc);
+  return acc;
+}
+// all N sums at once: N independent shuffle chains per step instead of N serial 5-step reductions
+template <int N>
+__device__ __forceinline__ void warp_sum_n(float (&v)[N]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// Shared-memory plan of one CTA (dynamic):
+//   [Wd r x d][Wu^T r x d]   bf16, INLINE only (staged once per CTA)
+//   [bu d][gv 2d]            bf16: up-projection bias (INLINE), gate vector(s) (middleX gw | middleY gz | small gw_x, gw_y)
+//   [GW 16]                  fp32: <gate vector of the y1 half, Wu^T_j>  (INLINE backward of middleX / small)
+//   rows: RW_WARPS x RW_NS x NT x d bf16 -- every warp owns RW_NS row stages of NT tensors (x1, x2 | y1 [, dout]); a lane
+//         copies exactly the 16-byte pieces it later reads (cp.async, no cross-lane traffic, no barrier), so the bytes in
+//         flight do not depend on the register budget: 8 warps x 2 CTAs x one 3-4.6 KB row ahead = 48-74 KB per SM.
+//   The block reduction of the gate gradients at the end of the backward reuses the row region.
+struct SmemPlan {
+  __nv_bfloat16 *Wd, *WuT, *bu, *gv;
+  float* GW;
+  __nv_bfloat16* rows;
+};
+__host__ __device__ inline size_t rows_smem_bytes(int d, int r_inline, int nt) {
+  size_t s = (size_t)2 * r_inline * d * 2 + (size_t)3 * d * 2 + RW_MAXR * 4;
+  s = (s + 15) / 16 * 16;
+  return s + (size_t)RW_WARPS * RW_NS * nt * d * 2;
+}
+__device__ __forceinline__ SmemPlan carve_smem(uint8_t* smem, int d, int r_inline) {
+  SmemPlan P;
+  P.Wd = reinterpret_cast<__nv_bfloat16*>(smem);
+  P.WuT = P.Wd + (size_t)r_inline * d;
+  P.bu = P.WuT + (size_t)r_inline * d;
+  P.gv = P.bu + d;
+  P.GW = reinterpret_cast<float*>(P.gv + 2 * d);
+  size_t off = (size_t)2 * r_inline * d * 2 + (size_t)3 * d * 2 + RW_MAXR * 4;
+  off = (off + 15) / 16 * 16;
+  P.rows = reinterpret_cast<__nv_bfloat16*>(smem + off);
+  return P;
 }
 
-// Shared state of one row: forward quantities the backward needs again.
-template <int NCH>
-struct RowState {
-  float x1[NCH * 8], y1[NCH * 8];
-  float a[RW_MAXR], z[RW_MAXR];   // INLINE only
-  float g;                        // middleX: sigmoid of the row's dot; small: the sample's mean gate
-  float sg;                       // small: this token's sigmoid
+// stage the per-CTA constants; RMAX = 0: COMPOSED mode (no adapter weights)
+template <int RMAX, int GATE>
+__device__ __forceinline__ void stage_constants(const RowsArgs& p, const SmemPlan& S, bool bwd) {
+  if constexpr (RMAX > 0) {
+    const int n = p.r * p.d;
+    for (int i = threadIdx.x; i < n; i += RW_THREADS) {
+      S.Wd[i] = p.Wd[i];
+      const int j = i / p.d, c = i % p.d;
+      S.WuT[i] = p.Wu[(size_t)c * p.r + j];      // Wu is [d, r]: transposed into [r, d] rows
+    }
+    for (int i = threadIdx.x; i < p.d; i += RW_THREADS) S.bu[i] = p.bu[i];
+  }
+  if (GATE == VLPET_GATE_MIDDLE_X) for (int i = threadIdx.x; i < p.d; i += RW_THREADS) S.gv[i] = p.gw[i];
+  if (GATE == VLPET_GATE_MIDDLE_Y) for (int i = threadIdx.x; i < p.d; i += RW_THREADS) S.gv[i] = p.gz[i];
+  if (GATE == VLPET_GATE_SMALL) for (int i = threadIdx.x; i < 2 * p.d; i += RW_THREADS) S.gv[i] = p.gw[i];
+  __syncthreads();
+  if (RMAX > 0 && bwd && (GATE == VLPET_GATE_MIDDLE_X || GATE == VLPET_GATE_SMALL)) {
+    // GW_j = sum_c gv_y[c] Wu^T[j][c]: the part of dz_j that is proportional to the row's gate scalar gradient dt
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const __nv_bfloat16* gy = S.gv + (GATE == VLPET_GATE_SMALL ? p.d : 0);
+    for (int j = warp; j < p.r; j += RW_WARPS) {
+      float acc = 0.f;
+      for (int c = lane; c < p.d; c += 32) acc = fmaf(__bfloat162float(gy[c]), __bfloat162float(S.WuT[(size_t)j * p.d + c]), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) S.GW[j] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// issue the asynchronous copy of one row (NT tensors) into a stage; every lane copies its own NCH pieces per tensor
+// (SKIP_X1: the backward of the gates without a per-row scalar -- none, middleY -- never reads x1)
+template <int NCH, int NT, bool SKIP_X1 = false>
+__device__ __forceinline__ void issue_row(const RowsArgs& p, int64_t row, int lane, __nv_bfloat16* stage) {
+  const __nv_bfloat16* src[3] = {p.x1 + row * p.d, (p.has_y1 ? p.y1in : p.x2) + row * p.d, NT > 2 ? p.dout + row * p.d : nullptr};
+#pragma unroll
+  for (int t = SKIP_X1 ? 1 : 0; t < NT; ++t)
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) cp_async16(stage + (size_t)t * p.d + ch * 256 + lane * 8, src[t] + ch * 256 + lane * 8);
+}
+
+// Forward quantities of one row: y1 (kept in registers), the adapter pre-activations a_j / z_j (INLINE), the gate scalars.
+template <int NCH, int RMAX>
+struct RowFwd {
+  float y1[NCH * 8];
+  float a[RMAX > 0 ? RMAX : 1], z[RMAX > 0 ? RMAX : 1];
+  float g, sg;          // middleX: g = sigmoid of the row's dot; small: sg = this token's sigmoid, g = the sample's mean gate
 };
 
-// y1 (INLINE: from x2 and the staged weights; COMPOSED: loaded), then the row's gate scalars.
-template <int NCH, int GATE>
-__device__ __forceinline__ void row_forward(const RowsArgs& p, int64_t row, int lane, const __nv_bfloat16* sWd, const __nv_bfloat16* sWuT,
-                                            const float* gwr, float gbias, RowState<NCH>& S, float (&x2)[NCH * 8]) {
-  constexpr int NE = NCH * 8;
-  load_row<NCH>(p.x1 + row * p.d, lane, S.x1);
-  if (p.has_y1) {
-    load_row<NCH>(p.y1in + row * p.d, lane, S.y1);
-  } else {
-    load_row<NCH>(p.x2 + row * p.d, lane, x2);
+template <int NCH, int GATE, int RMAX>
+__device__ __forceinline__ void row_forward(const RowsArgs& p, const SmemPlan& S, const __nv_bfloat16* sx1, const __nv_bfloat16* sx2,
+                                            int lane, float gbias, RowFwd<NCH, RMAX>& F) {
+  if constexpr (RMAX > 0) {
+    // ---- sweep A: a_j = <x2, Wd_j> + bd_j for all ranks, one batched reduction
+    float acc[RMAX];
 #pragma unroll
-    for (int j = 0; j < RW_MAXR; ++j) {
-      if (j >= p.r) break;
-      float acc = 0.f;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        float w[8];
-        lds8(sWd + (size_t)j * p.d + ch * 256 + lane * 8, w);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc = fmaf(x2[ch * 8 + e], w[e], acc);
-      }
-      acc = warp_sum(acc) + __bfloat162float(p.bd[j]);
-      S.a[j] = acc;
-      S.z[j] = gelu_new_f(acc);
-    }
+    for (int j = 0; j < RMAX; ++j) acc[j] = 0.f;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.bu + ch * 256 + lane * 8));
-      const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+      float x2c[8];
+      lds8(sx2 + ch * 256 + lane * 8, x2c);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { S.y1[ch * 8 + 2 * e] = bf2f(u[e], 0); S.y1[ch * 8 + 2 * e + 1] = bf2f(u[e], 1); }
-    }
-#pragma unroll
-    for (int j = 0; j < RW_MAXR; ++j) {
-      if (j >= p.r) break;
-      const float zj = S.z[j];
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        float w[8];
-        lds8(sWuT + (size_t)j * p.d + ch * 256 + lane * 8, w);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) S.y1[ch * 8 + e] = fmaf(zj, w[e], S.y1[ch * 8 + e]);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < NE; ++e) S.y1[e] = p.kappa * x2[e] + p.alpha * S.y1[e];
-  }
-  S.g = 1.f;
-  S.sg = 0.f;
-  if (GATE == VLPET_GATE_MIDDLE_X) {
-    float t = 0.f;
-#pragma unroll
-    for (int e = 0; e < NE; ++e) t = fmaf(S.x1[e] + S.y1[e], gwr[e], t);
-    S.g = sigmoid_f(warp_sum(t) + gbias);
-  } else if (GATE == VLPET_GATE_SMALL) {
-    float t = 0.f;
-#pragma unroll
-    for (int e = 0; e < NE; ++e) t = fmaf(S.x1[e], gwr[e], fmaf(S.y1[e], gwr[NE + e], t));
-    S.sg = sigmoid_f(warp_sum(t) + gbias);
-    if (p.pass != 0) S.g = p.gmean[row / p.L];
-  }
-}
-
-// per-lane copies of the gate's row vector(s): middleX gw[d], middleY gz[d], small gw[2d] (x1 half, then y1 half)
-template <int NCH, int GATE>
-__device__ __forceinline__ void load_gate_vec(const RowsArgs& p, int lane, float (&gwr)[2 * NCH * 8], float& gbias) {
-  constexpr int NE = NCH * 8;
-  gbias = 0.f;
-#pragma unroll
-  for (int e = 0; e < 2 * NE; ++e) gwr[e] = 0.f;
-  const __nv_bfloat16* v = GATE == VLPET_GATE_MIDDLE_Y ? p.gz : p.gw;
-  if (GATE == VLPET_GATE_NONE) return;
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      gwr[ch * 8 + e] = __bfloat162float(v[ch * 256 + lane * 8 + e]);
-      if (GATE == VLPET_GATE_SMALL) gwr[NE + ch * 8 + e] = __bfloat162float(v[p.d + ch * 256 + lane * 8 + e]);
-    }
-  if (GATE != VLPET_GATE_MIDDLE_Y) gbias = __bfloat162float(p.gb[0]);
-}
-
-__device__ __forceinline__ void stage_weights(const RowsArgs& p, __nv_bfloat16* sWd, __nv_bfloat16* sWuT) {
-  if (p.has_y1) return;
-  const int n = p.r * p.d;
-  for (int i = threadIdx.x; i < n; i += RW_THREADS) {
-    sWd[i] = p.Wd[i];
-    const int j = i / p.d, c = i % p.d;
-    sWuT[i] = p.Wu[(size_t)c * p.r + j];      // Wu is [d, r]: transposed into [r, d] rows
-  }
-  __syncthreads();
-}
-
-template <int NCH, int GATE>
-__global__ void __launch_bounds__(RW_THREADS) rows_fwd_kernel(const RowsArgs p) {
-  constexpr int NE = NCH * 8;
-  extern __shared__ __align__(16) uint8_t smem[];
-  __nv_bfloat16* sWd = reinterpret_cast<__nv_bfloat16*>(smem);
-  __nv_bfloat16* sWuT = sWd + (size_t)p.r * p.d;
-  stage_weights(p, sWd, sWuT);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float gwr[2 * NE], gbias;
-  load_gate_vec<NCH, GATE>(p, lane, gwr, gbias);
-  const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
-  const int64_t nw = (int64_t)gridDim.x * (RW_THREADS / 32);
-  for (int64_t row = (int64_t)blockIdx.x * (RW_THREADS / 32) + warp; row < p.M; row += nw) {
-    RowState<NCH> S;
-    float x2[NE];
-    row_forward<NCH, GATE>(p, row, lane, sWd, sWuT, gwr, gbias, S, x2);
-    if (GATE == VLPET_GATE_SMALL && p.pass == 0) {
-      if (lane == 0) atomicAdd(p.gmean + row / p.L, S.sg / (float)p.L);
-      continue;
-    }
-    float o[NE];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      float m[8];
-      drop_scale8(seed_eff, p.thr16, p.inv_keep, row * p.d + ch * 256 + lane * 8, m);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int i = ch * 8 + e;
-        float h;
-        if (GATE == VLPET_GATE_MIDDLE_Y) h = p.add_gate ? S.y1[i] + 1.f + gwr[i] : S.y1[i] * (1.f + gwr[i]);
-        else if (GATE == VLPET_GATE_NONE) h = S.y1[i];
-        else h = p.add_gate ? S.y1[i] + S.g : S.y1[i] * S.g;
-        o[i] = S.x1[i] + p.s * m[e] * h;
-      }
-    }
-    store_row<NCH>(p.out + row * p.d, lane, o);
-  }
-}
-
-template <int NCH, int GATE>
-__global__ void __launch_bounds__(RW_THREADS) rows_bwd_kernel(const RowsArgs p) {
-  constexpr int NE = NCH * 8;
-  extern __shared__ __align__(16) uint8_t smem[];
-  __nv_bfloat16* sWd = reinterpret_cast<__nv_bfloat16*>(smem);
-  __nv_bfloat16* sWuT = sWd + (size_t)p.r * p.d;
-  float* sred = reinterpret_cast<float*>(smem + (p.has_y1 ? 0 : (size_t)2 * p.r * p.d * 2));   // [2 d + 1] block reduction of gate grads
-  stage_weights(p, sWd, sWuT);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float gwr[2 * NE], gbias;
-  load_gate_vec<NCH, GATE>(p, lane, gwr, gbias);
-  float acc_g[2 * NE], acc_b = 0.f;     // gate-parameter gradients of the rows this warp handles
-#pragma unroll
-  for (int e = 0; e < 2 * NE; ++e) acc_g[e] = 0.f;
-  float acc_da[RW_MAXR];                // dbd = sum over rows of da, kept in fp32 (the bf16 da scratch only feeds the GEMM)
-#pragma unroll
-  for (int j = 0; j < RW_MAXR; ++j) acc_da[j] = 0.f;
-  const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
-  const int64_t nw = (int64_t)gridDim.x * (RW_THREADS / 32);
-  for (int64_t row = (int64_t)blockIdx.x * (RW_THREADS / 32) + warp; row < p.M; row += nw) {
-    RowState<NCH> S;
-    float x2[NE], dh[NE], dy1[NE];
-    row_forward<NCH, GATE>(p, row, lane, sWd, sWuT, gwr, gbias, S, x2);
-    float dx1[NE];
-    load_row<NCH>(p.dout + row * p.d, lane, dx1);           // dx1 starts as dout
-    float dgs = 0.f;                                        // sum_c dG contribution of this row
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      float m[8];
-      drop_scale8(seed_eff, p.thr16, p.inv_keep, row * p.d + ch * 256 + lane * 8, m);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int i = ch * 8 + e;
-        dh[i] = p.s * m[e] * dx1[i];
-        dgs += p.add_gate ? dh[i] : dh[i] * S.y1[i];
-      }
-    }
-    if (GATE == VLPET_GATE_SMALL && p.pass == 0) {          // first pass: dG of the sample = sum over its tokens and columns
-      dgs = warp_sum(dgs);
-      if (lane == 0) atomicAdd(p.dgsum + row / p.L, dgs);
-      continue;
-    }
-    if (GATE == VLPET_GATE_NONE) {
-#pragma unroll
-      for (int i = 0; i < NE; ++i) dy1[i] = dh[i];
-    } else if (GATE == VLPET_GATE_MIDDLE_Y) {
-#pragma unroll
-      for (int i = 0; i < NE; ++i) {
-        dy1[i] = p.add_gate ? dh[i] : dh[i] * (1.f + gwr[i]);
-        acc_g[i] += p.add_gate ? dh[i] : dh[i] * S.y1[i];
-      }
-    } else {
-      // middleX: dt = dG g (1 - g) with dG the row sum; small: dt = dG_sample / L * sg (1 - sg), gate value = the sample mean
-      float dt;
-      if (GATE == VLPET_GATE_MIDDLE_X) dt = warp_sum(dgs) * S.g * (1.f - S.g);
-      else dt = p.dgsum[row / p.L] / (float)p.L * S.sg * (1.f - S.sg);
-      acc_b += dt;
-#pragma unroll
-      for (int i = 0; i < NE; ++i) {
-        const float base = p.add_gate ? dh[i] : dh[i] * S.g;
-        if (GATE == VLPET_GATE_MIDDLE_X) {
-          acc_g[i] += dt * (S.x1[i] + S.y1[i]);
-          dy1[i] = base + dt * gwr[i];
-          dx1[i] += dt * gwr[i];
-        } else {
-          acc_g[i] += dt * S.x1[i];
-          acc_g[NE + i] += dt * S.y1[i];
-          dx1[i] += dt * gwr[i];
-          dy1[i] = base + dt * gwr[NE + i];
+      for (int j = 0; j < RMAX; ++j) {
+        if (j < p.r) {
+          float w[8];
+          lds8(S.Wd + (size_t)j * p.d + ch * 256 + lane * 8, w);
+          acc[j] = dot8(x2c, w, acc[j]);
         }
       }
     }
-    store_row<NCH>(p.dx1 + row * p.d, lane, dx1);
-    if (p.has_y1) {
-      store_row<NCH>(p.dy1 + row * p.d, lane, dy1);          // the ungated tcgen05 backward takes it from here
+    warp_sum_n<RMAX>(acc);
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      F.a[j] = acc[j] + (j < p.r ? __bfloat162float(p.bd[j]) : 0.f);
+      F.z[j] = j < p.r ? gelu_new_f(F.a[j]) : 0.f;
+    }
+  }
+  // ---- sweep B: y1 chunks (INLINE: kappa x2 + alpha (sum_j z_j Wu^T_j + bu); COMPOSED: loaded) and the gate's dot product
+  float t = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    float y[8];
+    if constexpr (RMAX > 0) {
+      float x2c[8];
+      lds8(sx2 + ch * 256 + lane * 8, x2c);
+      lds8(S.bu + ch * 256 + lane * 8, y);
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j) {
+        if (j < p.r) {
+          float w[8];
+          lds8(S.WuT + (size_t)j * p.d + ch * 256 + lane * 8, w);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = fmaf(F.z[j], w[e], y[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = p.kappa * x2c[e] + p.alpha * y[e];
+    } else {
+      lds8(sx2 + ch * 256 + lane * 8, y);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) F.y1[ch * 8 + e] = y[e];
+    if (GATE == VLPET_GATE_MIDDLE_X || GATE == VLPET_GATE_SMALL) {
+      float x1c[8], gx[8];
+      lds8(sx1 + ch * 256 + lane * 8, x1c);
+      lds8(S.gv + ch * 256 + lane * 8, gx);
+      if (GATE == VLPET_GATE_MIDDLE_X) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t = fmaf(x1c[e] + y[e], gx[e], t);
+      } else {
+        float gy[8];
+        lds8(S.gv + p.d + ch * 256 + lane * 8, gy);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t = fmaf(x1c[e], gx[e], fmaf(y[e], gy[e], t));
+      }
+    }
+  }
+  F.g = 1.f;
+  F.sg = 0.f;
+  if (GATE == VLPET_GATE_MIDDLE_X) F.g = sigmoid_f(warp_sum(t) + gbias);
+  if (GATE == VLPET_GATE_SMALL) F.sg = sigmoid_f(warp_sum(t) + gbias);
+}
+
+template <int NCH, int GATE, int RMAX>
+__global__ void __launch_bounds__(RW_THREADS, 2) rows_fwd_kernel(const RowsArgs p) {
+  constexpr int NT = 2;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const SmemPlan S = carve_smem(smem, p.d, RMAX > 0 ? p.r : 0);
+  stage_constants<RMAX, GATE>(p, S, false);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float gbias = (GATE == VLPET_GATE_MIDDLE_X || GATE == VLPET_GATE_SMALL) ? __bfloat162float(p.gb[0]) : 0.f;
+  const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
+  const int64_t nw = (int64_t)gridDim.x * RW_WARPS;
+  __nv_bfloat16* const wrows = S.rows + (size_t)warp * RW_NS * NT * p.d;
+  int64_t row = (int64_t)blockIdx.x * RW_WARPS + warp;
+  if (row < p.M) issue_row<NCH, NT>(p, row, lane, wrows);
+  cp_async_commit();
+  for (int it = 0; row < p.M; ++it, row += nw) {
+    if (row + nw < p.M) issue_row<NCH, NT>(p, row + nw, lane, wrows + (size_t)((it + 1) & 1) * NT * p.d);
+    cp_async_commit();
+    cp_async_wait1();
+    const __nv_bfloat16* sx1 = wrows + (size_t)(it & 1) * NT * p.d;
+    const __nv_bfloat16* sx2 = sx1 + p.d;
+    RowFwd<NCH, RMAX> F;
+    row_forward<NCH, GATE, RMAX>(p, S, sx1, sx2, lane, gbias, F);
+    if (GATE == VLPET_GATE_SMALL) {
+      if (p.pass == 0) {
+        if (lane == 0) atomicAdd(p.gmean + row / p.L, F.sg / (float)p.L);
+        continue;
+      }
+      F.g = p.gmean[row / p.L];
+    }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      float x1c[8], m[8], o[8], gz[8];
+      lds8(sx1 + ch * 256 + lane * 8, x1c);
+      if (GATE == VLPET_GATE_MIDDLE_Y) lds8(S.gv + ch * 256 + lane * 8, gz);
+      drop_scale8(seed_eff, p.thr16, p.inv_keep, row * p.d + ch * 256 + lane * 8, m);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float y = F.y1[ch * 8 + e];
+        float h;
+        if (GATE == VLPET_GATE_MIDDLE_Y) h = p.add_gate ? y + 1.f + gz[e] : y * (1.f + gz[e]);
+        else if (GATE == VLPET_GATE_NONE) h = y;
+        else h = p.add_gate ? y + F.g : y * F.g;
+        o[e] = x1c[e] + p.s * m[e] * h;
+      }
+      stg8(p.out + row * p.d + ch * 256 + lane * 8, o);
+    }
+  }
+}
+
+// Backward.  pass 0 (small gate only): the per-sample reductions both directions need before any output can be formed --
+// the gate mean (sum of the tokens' sigmoids) AND dG (sum over tokens and columns of dh (y1)) -- in ONE sweep over x1, x2, dout.
+template <int NCH, int GATE, int RMAX>
+__global__ void __launch_bounds__(RW_THREADS, 2) rows_bwd_kernel(const RowsArgs p) {
+  constexpr int NT = 3;
+  constexpr int NE = NCH * 8;
+  constexpr bool ROWGATE = GATE == VLPET_GATE_MIDDLE_X || GATE == VLPET_GATE_SMALL;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const SmemPlan S = carve_smem(smem, p.d, RMAX > 0 ? p.r : 0);
+  stage_constants<RMAX, GATE>(p, S, true);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float gbias = ROWGATE ? __bfloat162float(p.gb[0]) : 0.f;
+  const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
+  const int64_t nw = (int64_t)gridDim.x * RW_WARPS;
+  __nv_bfloat16* const wrows = S.rows + (size_t)warp * RW_NS * NT * p.d;
+  // gate-parameter gradients of the rows this warp handles (lanes own distinct columns): middleX / middleY one vector, small two
+  float acc_g[GATE == VLPET_GATE_SMALL ? 2 * NE : (GATE == VLPET_GATE_NONE ? 1 : NE)];
+#pragma unroll
+  for (int e = 0; e < (int)(sizeof(acc_g) / sizeof(float)); ++e) acc_g[e] = 0.f;
+  float acc_b = 0.f;
+  float acc_da[RMAX > 0 ? RMAX : 1];      // dbd = sum over rows of da, kept in fp32 (the bf16 da scratch only feeds the GEMM)
+#pragma unroll
+  for (int j = 0; j < (RMAX > 0 ? RMAX : 1); ++j) acc_da[j] = 0.f;
+
+  int64_t row = (int64_t)blockIdx.x * RW_WARPS + warp;
+  if (row < p.M) issue_row<NCH, NT, !ROWGATE>(p, row, lane, wrows);
+  cp_async_commit();
+  for (int it = 0; row < p.M; ++it, row += nw) {
+    if (row + nw < p.M) issue_row<NCH, NT, !ROWGATE>(p, row + nw, lane, wrows + (size_t)((it + 1) & 1) * NT * p.d);
+    cp_async_commit();
+    cp_async_wait1();
+    const __nv_bfloat16* sx1 = wrows + (size_t)(it & 1) * NT * p.d;
+    const __nv_bfloat16* sx2 = sx1 + p.d;
+    const __nv_bfloat16* sdo = sx2 + p.d;
+    RowFwd<NCH, RMAX> F;
+    row_forward<NCH, GATE, RMAX>(p, S, sx1, sx2, lane, gbias, F);
+    if (GATE == VLPET_GATE_SMALL && p.pass != 0) F.g = p.gmean[row / p.L];
+    // ---- sweep C: dh = s m dout; the row's dG contribution; the dt-independent part of dz_j (INLINE)
+    //      base = dy1 without the gate-scalar term: dh (add gate) | dh g (middleX / small) | dh (1 + gz) (middleY) | dh (none)
+    uint32_t mbits = 0;
+    float dgs = 0.f;
+    float dzb[RMAX > 0 ? RMAX : 1];
+#pragma unroll
+    for (int j = 0; j < (RMAX > 0 ? RMAX : 1); ++j) dzb[j] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      float doc[8], m[8], base[8], gz[8];
+      lds8(sdo + ch * 256 + lane * 8, doc);
+      if (GATE == VLPET_GATE_MIDDLE_Y) lds8(S.gv + ch * 256 + lane * 8, gz);
+      drop_scale8(seed_eff, p.thr16, p.inv_keep, row * p.d + ch * 256 + lane * 8, m);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (m[e] != 0.f) mbits |= 1u << (ch * 8 + e);
+        const float dh = p.s * m[e] * doc[e];
+        dgs += p.add_gate ? dh : dh * F.y1[ch * 8 + e];
+        if (p.add_gate || GATE == VLPET_GATE_NONE) base[e] = dh;
+        else if (GATE == VLPET_GATE_MIDDLE_Y) base[e] = dh * (1.f + gz[e]);
+        else base[e] = dh * F.g;
+      }
+      if constexpr (RMAX > 0) {
+        if (!(GATE == VLPET_GATE_SMALL && p.pass == 0)) {
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) {
+          if (j < p.r) {
+            float w[8];
+            lds8(S.WuT + (size_t)j * p.d + ch * 256 + lane * 8, w);
+            dzb[j] = dot8(base, w, dzb[j]);
+          }
+        }
+        }
+      }
+    }
+    if (GATE == VLPET_GATE_SMALL && p.pass == 0) {
+      dgs = warp_sum(dgs);
+      if (lane == 0) {
+        atomicAdd(p.gmean + row / p.L, F.sg / (float)p.L);
+        atomicAdd(p.dgsum + row / p.L, dgs);
+      }
       continue;
     }
-    // ---- INLINE adapter backward: du = alpha dy1, dz = du Wu, da = dz gelu'(a), dx2 = kappa dy1 + da Wd
-    float du[NE], dx2[NE];
+    // ---- the row's gate-scalar gradient: middleX dt = dG g (1 - g) with dG the row sum; small dt = dG_sample / L * sg (1 - sg)
+    float dt = 0.f;
+    if (GATE == VLPET_GATE_MIDDLE_X) dt = warp_sum(dgs) * F.g * (1.f - F.g);
+    if (GATE == VLPET_GATE_SMALL) dt = p.dgsum[row / p.L] / (float)p.L * F.sg * (1.f - F.sg);
+    acc_b += dt;
+    // ---- INLINE adapter: dz_j = alpha (dzb_j + dt GW_j), da_j = dz_j gelu_new'(a_j); z / da rows for the weight-gradient GEMM
+    float da[RMAX > 0 ? RMAX : 1];
+    if constexpr (RMAX > 0) {
+      warp_sum_n<RMAX>(dzb);
+      __nv_bfloat16* zrow = p.zs + row * p.pz;
+      __nv_bfloat16* darow = p.das + row * p.pz;
 #pragma unroll
-    for (int i = 0; i < NE; ++i) { du[i] = p.alpha * dy1[i]; dx2[i] = p.kappa * dy1[i]; }
-    __nv_bfloat16* zrow = p.zs + row * p.pz;
-    __nv_bfloat16* darow = p.das + row * p.pz;
-#pragma unroll
-    for (int j = 0; j < RW_MAXR; ++j) {
-      if (j >= p.r) break;
-      float dz = 0.f;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        float w[8];
-        lds8(sWuT + (size_t)j * p.d + ch * 256 + lane * 8, w);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) dz = fmaf(du[ch * 8 + e], w[e], dz);
+      for (int j = 0; j < RMAX; ++j) {
+        const float dz = p.alpha * (dzb[j] + (ROWGATE ? dt * S.GW[j < p.r ? j : 0] : 0.f));
+        da[j] = j < p.r ? dz * gelu_new_grad_f(F.a[j]) : 0.f;
+        acc_da[j] += da[j];
       }
-      const float da = warp_sum(dz) * gelu_new_grad_f(S.a[j]);
-      acc_da[j] += da;
+      if (lane < p.pz) {     // columns [0, r): z / da; column r8: the ones column (bias-gradient trick of the GEMM); the rest zero
+        float zv = 0.f, dv = 0.f;
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        float w[8];
-        lds8(sWd + (size_t)j * p.d + ch * 256 + lane * 8, w);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) dx2[ch * 8 + e] = fmaf(da, w[e], dx2[ch * 8 + e]);
+        for (int j = 0; j < RMAX; ++j)
+          if (lane == j) { zv = F.z[j]; dv = da[j]; }
+        if (lane >= p.r) { zv = lane == p.r8 ? 1.f : 0.f; dv = 0.f; }
+        zrow[lane] = __float2bfloat16_rn(zv);
+        darow[lane] = __float2bfloat16_rn(dv);
       }
-      if (lane == 0) { zrow[j] = __float2bfloat16_rn(S.z[j]); darow[j] = __float2bfloat16_rn(da); }
     }
-    if (lane == 0) {      // zero padding up to the GEMM's rank r8, then the ones column (its bias-gradient trick) at index r8
-      for (int j = p.r; j < p.pz; ++j) { zrow[j] = __float2bfloat16_rn(j == p.r8 ? 1.f : 0.f); darow[j] = __float2bfloat16_rn(0.f); }
-    }
-    store_row<NCH>(p.dx2 + row * p.d, lane, dx2);
-    store_row<NCH>(p.du + row * p.d, lane, du);
-  }
-  if (!p.has_y1 && p.dbd && lane == 0 && !(GATE == VLPET_GATE_SMALL && p.pass == 0)) {
+    // ---- sweep D: dy1 = base + dt gv_y, dx1 = dout + dt gv_x, gate-parameter gradients; COMPOSED: dy1 out; INLINE: du, dx2 out
 #pragma unroll
-    for (int j = 0; j < RW_MAXR; ++j)
-      if (j < p.r) atomicAdd(p.dbd + j, acc_da[j]);
+    for (int ch = 0; ch < NCH; ++ch) {
+      float doc[8], x1c[8], gx[8], gy[8], dy1[8], dx1[8];
+      lds8(sdo + ch * 256 + lane * 8, doc);
+      if (GATE != VLPET_GATE_NONE) lds8(S.gv + ch * 256 + lane * 8, gx);
+      if (GATE == VLPET_GATE_SMALL) lds8(S.gv + p.d + ch * 256 + lane * 8, gy);
+      if (ROWGATE) lds8(sx1 + ch * 256 + lane * 8, x1c);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = ch * 8 + e;
+        const float dh = ((mbits >> i) & 1u) ? p.s * p.inv_keep * doc[e] : 0.f;
+        const float y = F.y1[i];
+        float base;
+        if (p.add_gate || GATE == VLPET_GATE_NONE) base = dh;
+        else if (GATE == VLPET_GATE_MIDDLE_Y) base = dh * (1.f + gx[e]);
+        else base = dh * F.g;
+        dx1[e] = doc[e];
+        dy1[e] = base;
+        if (GATE == VLPET_GATE_MIDDLE_Y) acc_g[i] += p.add_gate ? dh : dh * y;
+        if (GATE == VLPET_GATE_MIDDLE_X) {
+          acc_g[i] += dt * (x1c[e] + y);
+          dy1[e] = base + dt * gx[e];
+          dx1[e] = doc[e] + dt * gx[e];
+        }
+        if (GATE == VLPET_GATE_SMALL) {
+          acc_g[i] += dt * x1c[e];
+          acc_g[NE + i] += dt * y;
+          dy1[e] = base + dt * gy[e];
+          dx1[e] = doc[e] + dt * gx[e];
+        }
+      }
+      if (p.dx1) stg8(p.dx1 + row * p.d + ch * 256 + lane * 8, dx1);   // (K2 through the ungated form: dx1 = dout, not written)
+      if constexpr (RMAX == 0) {
+        stg8(p.dy1 + row * p.d + ch * 256 + lane * 8, dy1);      // the ungated tcgen05 backward takes it from here
+      } else {
+        float du[8], dx2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { du[e] = p.alpha * dy1[e]; dx2[e] = p.kappa * dy1[e]; }
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) {
+          if (j < p.r) {
+            float w[8];
+            lds8(S.Wd + (size_t)j * p.d + ch * 256 + lane * 8, w);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dx2[e] = fmaf(da[j], w[e], dx2[e]);
+          }
+        }
+        stg8(p.dx2 + row * p.d + ch * 256 + lane * 8, dx2);
+        stg8(p.du + row * p.d + ch * 256 + lane * 8, du);
+      }
+    }
   }
-  // ---- gate-parameter gradients: lanes own distinct columns; reduce over the CTA's warps in shared memory, then one
-  //      atomicAdd per column and CTA
-  if (GATE == VLPET_GATE_NONE || (GATE == VLPET_GATE_SMALL && p.pass == 0)) return;
+  if (GATE == VLPET_GATE_SMALL && p.pass == 0) return;
+  if constexpr (RMAX > 0) {
+    if (p.dbd && lane == 0) {
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j)
+        if (j < p.r) atomicAdd(p.dbd + j, acc_da[j]);
+    }
+  }
+  // ---- gate-parameter gradients: lanes own distinct columns; reduce over the CTA's warps in shared memory (the row region
+  //      is idle now), then one atomicAdd per column and CTA
+  if (GATE == VLPET_GATE_NONE) return;
   const int nvec = (GATE == VLPET_GATE_SMALL ? 2 : 1) * p.d;
-  __syncthreads();                                           // staged weights no longer needed (sred may overlap nothing, kept simple)
+  float* sred = reinterpret_cast<float*>(S.rows);
+  __syncthreads();
   for (int i = threadIdx.x; i < nvec + 1; i += RW_THREADS) sred[i] = 0.f;
   __syncthreads();
 #pragma unroll
@@ -361,39 +480,41 @@ __global__ void unpad_add_kernel(const float* __restrict__ pWu, const float* __r
   if (dWd) dWd[i] += pWd[i];                       // [r8, d] row-major: the first r rows are the first r*d elements
 }
 
-size_t smem_for(const RowsArgs& a, bool bwd) {
-  size_t s = a.has_y1 ? 0 : (size_t)2 * a.r * a.d * 2;
-  if (bwd) s += (size_t)(2 * a.d + 1) * 4 + 16;
-  return s;
-}
+// rank bucket of the INLINE kernels (compile-time loop bound; the loops skip j >= r): 0 = COMPOSED (y1 is an input)
+int rmax_of(const RowsArgs& a) { return a.has_y1 ? 0 : (a.r <= 4 ? 4 : RW_MAXR); }
 
-template <int NCH>
-int launch_rows(bool bwd, const RowsArgs& a, int sms, cudaStream_t st) {
-  const size_t smem = smem_for(a, bwd);
-  int64_t blocks = (a.M + (RW_THREADS / 32) - 1) / (RW_THREADS / 32);
-  if (blocks > 2 * sms) blocks = 2 * sms;
-#define VLPET_ROWS_CASE(G)                                                                                          \
-  case G: {                                                                                                          \
-    auto kf = rows_fwd_kernel<NCH, G>;                                                                               \
-    auto kb = rows_bwd_kernel<NCH, G>;                                                                               \
-    if (smem > 48 * 1024) {                                                                                          \
-      if (bwd) VLPET_CUDA_OK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-      else VLPET_CUDA_OK(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-    }                                                                                                                \
-    if (bwd) kb<<<(unsigned)blocks, RW_THREADS, smem, st>>>(a);                                                      \
-    else kf<<<(unsigned)blocks, RW_THREADS, smem, st>>>(a);                                                          \
-    break;                                                                                                           \
-  }
-  switch (a.gate) {
-    VLPET_ROWS_CASE(VLPET_GATE_NONE)
-    VLPET_ROWS_CASE(VLPET_GATE_MIDDLE_X)
-    VLPET_ROWS_CASE(VLPET_GATE_MIDDLE_Y)
-    VLPET_ROWS_CASE(VLPET_GATE_SMALL)
-    default: return fail(VLPET_E_UNSUPPORTED, "rows: gate %d", a.gate);
-  }
-#undef VLPET_ROWS_CASE
+template <int NCH, int GATE, int RMAX>
+int launch_rows_k(bool bwd, const RowsArgs& a, int sms, cudaStream_t st) {
+  const size_t smem = rows_smem_bytes(a.d, RMAX > 0 ? a.r : 0, bwd ? 3 : 2);
+  int64_t blocks = (a.M + RW_WARPS - 1) / RW_WARPS;
+  if (blocks > 2 * sms) blocks = 2 * sms;            // two resident CTAs per SM (launch bounds), every warp walks rows
+  auto kf = rows_fwd_kernel<NCH, GATE, RMAX>;
+  auto kb = rows_bwd_kernel<NCH, GATE, RMAX>;
+  static int attr_f[64] = {0}, attr_b[64] = {0};
+  if (bwd) VLPET_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kb), attr_b, (int)smem));
+  else VLPET_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kf), attr_f, (int)smem));
+  if (bwd) kb<<<(unsigned)blocks, RW_THREADS, smem, st>>>(a);
+  else kf<<<(unsigned)blocks, RW_THREADS, smem, st>>>(a);
   VLPET_LAUNCH_OK();
   return 0;
+}
+template <int NCH, int GATE>
+int launch_rows_g(bool bwd, const RowsArgs& a, int sms, cudaStream_t st) {
+  switch (rmax_of(a)) {
+    case 0: return launch_rows_k<NCH, GATE, 0>(bwd, a, sms, st);
+    case 4: return launch_rows_k<NCH, GATE, 4>(bwd, a, sms, st);
+    default: return launch_rows_k<NCH, GATE, RW_MAXR>(bwd, a, sms, st);
+  }
+}
+template <int NCH>
+int launch_rows(bool bwd, const RowsArgs& a, int sms, cudaStream_t st) {
+  switch (a.gate) {
+    case VLPET_GATE_NONE: return launch_rows_g<NCH, VLPET_GATE_NONE>(bwd, a, sms, st);
+    case VLPET_GATE_MIDDLE_X: return launch_rows_g<NCH, VLPET_GATE_MIDDLE_X>(bwd, a, sms, st);
+    case VLPET_GATE_MIDDLE_Y: return launch_rows_g<NCH, VLPET_GATE_MIDDLE_Y>(bwd, a, sms, st);
+    case VLPET_GATE_SMALL: return launch_rows_g<NCH, VLPET_GATE_SMALL>(bwd, a, sms, st);
+  }
+  return fail(VLPET_E_UNSUPPORTED, "rows: gate %d", a.gate);
 }
 int launch_rows_d(bool bwd, const RowsArgs& a, int sms, cudaStream_t st) {
   switch (a.d / 256) {
@@ -546,12 +667,10 @@ int rows_k1_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const void
     VLPET_CUDA_OK(cudaMemsetAsync(W.gmean, 0, nb, st));
     VLPET_CUDA_OK(cudaMemsetAsync(W.dgsum, 0, nb, st));
     a.gmean = W.gmean; a.dgsum = W.dgsum;
-    a.pass = 0;
-    VLPET_TRY(launch_rows_d(false, a, sms, st));       // forward pass 0: the per-sample gate mean
-    a.pass = 1;
     RowsArgs b0 = a;
     b0.pass = 0;
-    VLPET_TRY(launch_rows_d(true, b0, sms, st));       // backward pass 0: dG per sample
+    VLPET_TRY(launch_rows_d(true, b0, sms, st));       // backward pass 0: the per-sample gate mean and dG in one sweep
+    a.pass = 1;
   }
   VLPET_TRY(launch_rows_d(true, a, sms, st));
   if (!inl) {
