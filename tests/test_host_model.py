@@ -83,6 +83,61 @@ def test_host_model_matches_reference_vlbart_cpu(H, gate):
             assert rel(params[n].grad.numpy(), z[f"{task}/grad/{n}"]) < 1e-9, (task, n)
 
 
+def _generate_case(H, dtype, device, eager):
+    z = np.load(os.path.join(GOLDEN, "vlbart_tiny_generate.npz"), allow_pickle=False)
+    model = H.VLBart(_cfg(H, "large"))
+    model = model.double() if dtype == torch.float64 else model
+    if eager:
+        from oracle.eager_ref import use_eager_pet
+        model = use_eager_pet(model)
+    model.eval()
+    _load_state(model, z, dtype)
+    model.to(device)
+    ids = torch.tensor(z["vqa/input_ids"]).to(device)
+    vis = (torch.tensor(z["vqa/vis_feats"]).to(device=device, dtype=dtype), torch.tensor(z["vqa/boxes"]).to(device=device, dtype=dtype))
+    bias = torch.tensor(z["vqa/logit_bias"]).to(device)
+    proc = lambda step, tokens, scores: scores + bias[:, step].to(scores.dtype)  # noqa: E731
+    return z, model, ids, vis, proc
+
+
+def test_generate_matches_reference_cached_decode_cpu(H):
+    """greedy decoding through the KV cache (cross-attention keys / values -- the values through the value
+    parallel adapter -- formed once) against the reference's own cached decode path
+    (tests/golden/make_golden_generate.py: VLBart.forward with past_key_values, src/modeling_bart.py:1522-1602), host logic
+    in fp64 with the eager PET restatement: same tokens, every step's logits to 1e-9; and the cached steps reproduce the
+    model's own full teacher-forced pass."""
+    z, model, ids, vis, proc = _generate_case(H, torch.float64, "cpu", eager=True)
+    tokens, logits = model.generate(ids, vis, task="vqa", max_length=int(z["meta_max_length"]), min_length=int(z["meta_min_length"]),
+                                    logits_processor=proc, return_step_logits=True)
+    assert tokens.tolist() == z["vqa/tokens"].tolist()
+    assert rel(logits.numpy(), z["vqa/step_logits"]) < 1e-9
+    with torch.no_grad():
+        h = model.model(ids, vis, tokens[:, :-1], task="vqa")
+        full = model._logits(h)
+    assert rel(full.numpy(), logits.numpy()) < 1e-9
+    with pytest.raises(NotImplementedError):
+        model.generate(ids, vis, task="vqa", num_beams=5)
+    assert model.test_step({"task": "vqa", "input_ids": ids, "vis_feats": vis[0], "boxes": vis[1]}, max_length=4, min_length=4)["token_ids"].shape == (3, 4)
+
+
+@pytest.mark.gpu
+def test_generate_with_cuda_vpa_matches_reference_cached_decode(H):
+    """The same on the GPU in fp32: the value parallel adapter inside ``cross_kv`` is the K2 CUDA kernel (forward only, once per
+    generation); tokens identical, step logits to 2e-4."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import vlpet_b200 as V
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    z, model, ids, vis, proc = _generate_case(H, torch.float32, "cuda", eager=False)
+    n0 = V.launch_count()
+    tokens, logits = model.generate(ids, vis, task="vqa", max_length=int(z["meta_max_length"]), min_length=int(z["meta_min_length"]),
+                                    logits_processor=proc, return_step_logits=True)
+    assert V.launch_count() - n0 >= 2 + 2 * 2 + 1, "PET sites did not run the CUDA kernels"   # K2 per decoder layer, K1 x 2 per encoder layer, K3
+    assert tokens.cpu().tolist() == z["vqa/tokens"].tolist()
+    assert rel(logits.double().cpu().numpy(), z["vqa/step_logits"]) < 2e-4
+
+
 def test_bart_base_trainable_count_is_the_reference_checksum(H):
     """BART-base + VL-PET-large r=96: 6 052 416 trainable parameters = the 4.16 % of the reference README
     (README.md:360; reproduced by instantiating the reference model)."""

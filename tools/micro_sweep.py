@@ -59,7 +59,8 @@ for L_seq in a.lens:
             desc = L.K1Desc(M=M, L=L_seq, d=d, r=r, rg=r if gate == "large" else 0, gate=L.GATE_IDS[gate], add_gate=0, dtype=L.BF16,
                             impl=L.IMPL_AUTO, s=1.0, alpha=1.0, kappa=1.0, p_drop=0.0, seed=0, seed_dev=None)
             w = L.K1Params(Wd=p_(Wd), bd=p_(bd), Wu=p_(Wu), bu=p_(bu))
-            gr = L.K1Grads(dWd=p_(f32(Wd)), dbd=p_(f32(bd)), dWu=p_(f32(Wu)), dbu=p_(f32(bu)))
+            gkeep = [f32(Wd), f32(bd), f32(Wu), f32(bu)]          # (the tensors must outlive the calls: only pointers travel)
+            gr = L.K1Grads(dWd=p_(gkeep[0]), dbd=p_(gkeep[1]), dWu=p_(gkeep[2]), dbu=p_(gkeep[3]))
             keep = []
             if gate == "large":
                 w.Gd, w.gbd, w.Gu, w.gbu = p_(Gd), p_(gbd), p_(Gu), p_(gbu)

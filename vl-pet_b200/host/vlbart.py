@@ -134,6 +134,31 @@ class BartAttention(nn.Module):
         return self.out_proj(o.transpose(1, 2).reshape(B, L, self.embed_dim))
 
 
+    # ---- KV-cached decode (my_transformers/modeling_bart.py:419-430, 486-508) -------------------------
+    def cross_kv(self, encoder_hidden_states, task=None):
+        """Keys / values of a cross-attention for a whole generation: computed once, the values already through the value
+        parallel adapter (K2, forward only) -- the reference caches exactly this pair in ``past_key_value``."""
+        k = self.k_proj(encoder_hidden_states)
+        v = self.v_proj(encoder_hidden_states)
+        if self.attn_value_parallel_adapter is not None:
+            v = self.attn_value_parallel_adapter(encoder_hidden_states, task, y=v)                  # K2
+        return self._heads(k), self._heads(v)
+
+    def attend_cached(self, hidden_states, kh, vh, attn_mask=None, is_causal=False):
+        """``hidden_states`` [B, T, d] (T new positions) against cached heads kh / vh [B, H, S, hd]."""
+        B, T, _ = hidden_states.shape
+        qh = self._heads(self.q_proj(hidden_states))
+        o = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=attn_mask, is_causal=is_causal and T > 1 and attn_mask is None)
+        return self.out_proj(o.transpose(1, 2).reshape(B, T, self.embed_dim))
+
+    def self_kv(self, hidden_states, past=None):
+        """Self-attention keys / values of the new positions appended to the cache (past = (kh, vh) or None)."""
+        kh, vh = self._heads(self.k_proj(hidden_states)), self._heads(self.v_proj(hidden_states))
+        if past is not None:
+            kh, vh = torch.cat([past[0], kh], dim=2), torch.cat([past[1], vh], dim=2)
+        return kh, vh
+
+
 def _sdpa_policy(q: torch.Tensor):
     """Backend order for the frozen attention (stock PyTorch SDPA, host code).  At the sequence lengths of this workload
     (<= 92 encoder tokens, <= 40 decoder tokens) the memory-efficient kernel beats the cuDNN / flash kernels, whose
@@ -242,6 +267,24 @@ class BartDecoderLayer(nn.Module):
         hidden_states = _ln(self.encoder_attn_layer_norm, hidden_states + drop(h))
         h = self.fc2(_ffn_act(self, self.fc1(hidden_states)))
         return _ln(self.final_layer_norm, hidden_states + drop(h))
+
+    @torch.no_grad()
+    def step(self, hidden_states, cross, self_past=None, cross_mask=None):
+        """Incremental form of ``forward`` (eval mode): T new positions, cached self-attention heads, cross = (kh, vh) from
+        ``encoder_attn.cross_kv``.  Returns (hidden_states, new self-attention cache)."""
+        T = hidden_states.shape[1]
+        kv = self.self_attn.self_kv(hidden_states, self_past)
+        mask = None
+        if self_past is not None and T > 1:                       # new positions see the whole past and a causal triangle
+            S = kv[0].shape[2]
+            mask = torch.ones(T, S, dtype=torch.bool, device=hidden_states.device).tril(diagonal=S - T)
+        h = self.self_attn.attend_cached(hidden_states, kv[0], kv[1], attn_mask=mask, is_causal=self_past is None)
+        hidden_states = _ln(self.self_attn_layer_norm, hidden_states + h)
+        h = self.encoder_attn.attend_cached(hidden_states, cross[0], cross[1], attn_mask=cross_mask)
+        hidden_states = _ln(self.encoder_attn_layer_norm, hidden_states + h)
+        h = self.fc2(self.activation_fn(self.fc1(hidden_states)))
+        return _ln(self.final_layer_norm, hidden_states + h), kv
+
 
 
 class Downsample(nn.Module):
@@ -353,6 +396,26 @@ class BartDecoder(nn.Module):
         return x
 
 
+    @torch.no_grad()
+    def init_cache(self, encoder_hidden_states, encoder_mask=None, task=None):
+        """Per-layer cross-attention heads for a whole generation (the value parallel adapter runs here, once) + empty
+        self-attention caches."""
+        cross = [layer.encoder_attn.cross_kv(encoder_hidden_states, task) for layer in self.layers]
+        return {"cross": cross, "self": [None] * len(self.layers), "len": 0, "mask": encoder_mask}
+
+    @torch.no_grad()
+    def step(self, input_ids, cache):
+        """``input_ids`` [B, T]: the positions after the ``cache['len']`` already decoded ones -> hidden states [B, T, d]."""
+        B, T = input_ids.shape
+        x = self.embed_tokens(input_ids) * self.embed_scale + self.embed_positions(T, past=cache["len"])
+        x = _ln(self.layernorm_embedding, x)
+        cross_mask = _pad_mask(cache["mask"], x.dtype, T)
+        for i, layer in enumerate(self.layers):
+            x, cache["self"][i] = layer.step(x, cache["cross"][i], cache["self"][i], cross_mask)
+        cache["len"] += T
+        return x
+
+
 class VLBartModel(nn.Module):
     def __init__(self, config: VLPetConfig):
         super().__init__()
@@ -425,6 +488,81 @@ class VLBart(nn.Module):
                 lg = lg.float()
             loss = F.cross_entropy(lg, labels.reshape(-1), ignore_index=-100, reduction="none")
         return loss, logits[..., :cfg.vocab_size]
+
+    def _vis_inputs(self, batch: dict, dev):
+        """(feats, boxes[, img_ids, obj_ids]) of a task batch on the device; NLVR pairs are flattened (nlvr_model.py:156-176)."""
+        feats = batch["vis_feats"].to(dev, non_blocking=True)
+        boxes = batch["boxes"].to(dev, non_blocking=True)
+        if batch["task"] != "nlvr":
+            return (feats, boxes)
+        B, V_L = feats.shape[0], feats.shape[2]
+        feats = feats.reshape(B, 2 * V_L, -1)
+        boxes = boxes.reshape(B, 2 * V_L, 4)
+        key = (V_L, str(dev))
+        if key not in self._nlvr_ids:                        # built once: no host->device copy inside a step
+            self._nlvr_ids[key] = (torch.tensor([0] * V_L + [1] * V_L, dtype=torch.long, device=dev).view(1, -1),
+                                   torch.arange(V_L, dtype=torch.long, device=dev).repeat(2).view(1, -1))
+        return (feats, boxes, self._nlvr_ids[key][0].expand(B, -1), self._nlvr_ids[key][1].expand(B, -1))
+
+    def _logits(self, h):
+        w, b, _ = self._lm_operands(h.dtype)
+        return F.linear(h, w, b.reshape(-1))[..., :self.config.vocab_size]
+
+    @torch.no_grad()
+    def generate(self, input_ids, vis_inputs, task=None, max_length: int = 20, min_length: int = 0, num_beams: int = 1,
+                 logits_processor=None, attention_mask=None, vis_attention_mask=None, return_step_logits: bool = False):
+        """Greedy decoding with the KV cache of the reference's decode path (src/modeling_bart.py:1522-1602 with
+        ``past_key_values``; what ``test_step`` -> ``generate(num_beams=1)`` runs for VQA / GQA / NLVR, multitask.py:480, 516):
+        the encoder runs once, every decoder layer's cross-attention keys / values -- the values through the value parallel
+        adapter (K2) -- are formed once, each step feeds ONE new position.  ``logits_processor(step, tokens, scores)`` is the
+        caller's hook (HF's logits processors); ``min_length`` masks EOS as HF's MinLengthLogitsProcessor does.  Beam search
+        (caption: --num_beams 5) is HF search machinery above this path and is not built: ``num_beams > 1`` raises."""
+        if num_beams != 1:
+            raise NotImplementedError("host.VLBart.generate: greedy decoding only (num_beams == 1); beam search is the caller's "
+                                      "search loop over the same cached step")
+        cfg = self.config
+        was_training = self.training
+        self.eval()
+        try:
+            enc, mask = self.model.encoder(input_ids, vis_inputs, attention_mask, vis_attention_mask, task=task)
+            cache = self.model.decoder.init_cache(enc, mask, task=task)
+            B = input_ids.shape[0]
+            tokens = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=input_ids.device)
+            done = torch.zeros(B, dtype=torch.bool, device=input_ids.device)
+            steps = []
+            while tokens.shape[1] < max_length:
+                h = self.model.decoder.step(tokens if cache["len"] == 0 else tokens[:, -1:], cache)
+                scores = self._logits(h[:, -1])
+                if scores.dtype in (torch.bfloat16, torch.float16):
+                    scores = scores.float()
+                if return_step_logits:
+                    steps.append(scores.clone())
+                if logits_processor is not None:
+                    scores = logits_processor(tokens.shape[1] - 1, tokens, scores)     # (step index, tokens so far, scores)
+                if tokens.shape[1] < min_length:
+                    scores[:, cfg.eos_token_id] = -float("inf")
+                nxt = scores.argmax(-1)
+                nxt = torch.where(done, torch.full_like(nxt, cfg.pad_token_id), nxt)
+                done |= nxt == cfg.eos_token_id
+                tokens = torch.cat([tokens, nxt[:, None]], dim=1)
+                if bool(done.all()):
+                    break
+        finally:
+            self.train(was_training)
+        return (tokens, torch.stack(steps, 1)) if return_step_logits else tokens
+
+    @torch.no_grad()
+    def test_step(self, batch: dict, **gen_kwargs) -> dict:
+        """vqa_model.py:235-288 (generative branch): batch -> {'token_ids'} (and 'pred_ans' when a tokenizer was attached as
+        ``self.tokenizer``; tokenizers need files this offline image does not have)."""
+        dev = self.model.shared.weight.device
+        out = self.generate(batch["input_ids"].to(dev, non_blocking=True), self._vis_inputs(batch, dev), task=batch["task"],
+                            **gen_kwargs)
+        result = {"token_ids": out}
+        tok = getattr(self, "tokenizer", None)
+        if tok is not None:
+            result["pred_ans"] = tok.batch_decode(out, skip_special_tokens=True)
+        return result
 
     def train_step(self, batch: dict) -> dict:
         """One task batch -> {'loss': scalar}.  Batch schema = the reference collate (vqa_clip_data.py:365-390):
