@@ -399,6 +399,34 @@ def test_k1_rowwise_gates_match_oracle(V, gate, r, B, L, add_gate, s):
             assert e < 6e-3, (k, e)                       # fp32 gradients of contractions over bf16-stored operands
 
 
+@pytest.mark.parametrize("M,r,rg,add_gate,s", [(3000, 4, 4, False, 1.0), (777, 4, 4, True, 0.3), (5000, 6, 12, False, 1.0),
+                                               (300, 2, 16, False, 0.7)])
+def test_k1_large_gate_small_rank_rowwise_matches_oracle(V, M, r, rg, add_gate, s):
+    """Large gate at ranks too small for a tensor-core tile (r, rg <= 16 and not a multiple of 8 >= 8; r = 4 is in the
+    SURVEY 8(d) sweep): both skinny branches evaluated row-locally by the cp.async-staged SIMT kernels (csrc/vlpet_rows.cu,
+    `is_fused` == 2), forward and backward against the fp64 oracle on the bf16-rounded inputs
+    (my_transformers/modeling_bart.py:1145-1155, 1195-1209, 1256-1260)."""
+    import ctypes as C
+    import vlpet_b200._lib as L_
+    d = 768
+    desc = L_.K1Desc(M=M, L=0, d=d, r=r, rg=rg, gate=L_.GATE_IDS["large"], add_gate=int(add_gate), dtype=L_.BF16, impl=L_.IMPL_AUTO,
+                     s=s, alpha=1.0, kappa=1.0, p_drop=0.0, seed=0)
+    assert L_.lib.vlpet_k1_fwd_is_fused(C.byref(desc)) == 2 and L_.lib.vlpet_k1_bwd_is_fused(C.byref(desc)) == 2
+    rng = np.random.default_rng(M + 31 * r + rg)
+    x1, x2, dout, p = random_large_case(rng, M, d, r, rg)
+    cfg = O.PetConfig(gate="large", add_gate=add_gate, s=s)
+    out, dx1, dx2, gr = run_k1(V, x1, x2, dout, p, cfg, 2 if r % 2 == 0 else 1, torch.bfloat16, "auto", (1, M, d))
+    o_out, o_dx1, o_dx2, o_gr = oracle_bf16(x1, x2, dout, p, cfg)
+    errs = {"out": rel(out, o_out), "dx1": rel(dx1, o_dx1), "dx2": rel(dx2, o_dx2)}
+    errs.update({"d" + k: rel(v, o_gr[k].reshape(np.shape(v))) for k, v in gr.items()})
+    print({k: float("%.2e" % e) for k, e in errs.items()})
+    for k in ("out", "dx1", "dx2"):
+        assert errs[k] < 3e-3, (k, errs[k])              # bf16-typed results: 1.6e-3 of that is the storage rounding itself
+    for k, e in errs.items():
+        if k not in ("out", "dx1", "dx2"):
+            assert e < 6e-3, (k, e)                       # fp32 gradients of contractions over bf16-stored operands
+
+
 def test_k1_fused_backward_accumulates_and_matches_generic(V):
     """Weight gradients are ACCUMULATED into the caller's buffers (C-ABI contract); fused vs generic CUDA path."""
     M, d, r = 900, 768, 96

@@ -472,6 +472,270 @@ __global__ void __launch_bounds__(RW_THREADS, 2) rows_bwd_kernel(const RowsArgs 
   if (GATE != VLPET_GATE_MIDDLE_Y && p.dgb && threadIdx.x == 0) atomicAdd(p.dgb, sred[nvec]);
 }
 
+// ---- large gate at ranks too small for a tensor-core tile (r, rg <= 16; e.g. r = 4 in the SURVEY 8(d) sweep) ---------------
+// G = sigmoid(gelu_new(x1 Gd^T + gbd) Gu^T + gbu) is a second skinny adapter on x1 (my_transformers/modeling_bart.py:1195-1209):
+// the same row-local structure, two branches.  The backward writes du / dT and z / q / da / dp rows for the weight-gradient GEMM.
+struct LargeArgs {
+  RowsArgs a;                                 // adapter branch + common fields (gate / gw / gz unused)
+  int rg, rg8, pq;
+  const __nv_bfloat16 *Gd, *gbd, *Gu, *gbu;
+  __nv_bfloat16 *dt, *qs, *dps;               // [M, d] dT scratch, [M, pq] q | 1 | 0.. and dp rows
+  float* dgbd;
+};
+struct LargePlan { __nv_bfloat16 *Wd, *WuT, *Gd, *GuT, *bu, *gbu, *rows; };
+__host__ __device__ inline size_t large_smem_bytes(int d, int r, int rg, int nt) {
+  size_t s = (size_t)2 * (r + rg) * d * 2 + (size_t)2 * d * 2;
+  s = (s + 15) / 16 * 16;
+  return s + (size_t)RW_WARPS * RW_NS * nt * d * 2;
+}
+__device__ __forceinline__ LargePlan carve_large(uint8_t* smem, int d, int r, int rg) {
+  LargePlan P;
+  P.Wd = reinterpret_cast<__nv_bfloat16*>(smem);
+  P.WuT = P.Wd + (size_t)r * d;
+  P.Gd = P.WuT + (size_t)r * d;
+  P.GuT = P.Gd + (size_t)rg * d;
+  P.bu = P.GuT + (size_t)rg * d;
+  P.gbu = P.bu + d;
+  size_t off = (size_t)2 * (r + rg) * d * 2 + (size_t)2 * d * 2;
+  off = (off + 15) / 16 * 16;
+  P.rows = reinterpret_cast<__nv_bfloat16*>(smem + off);
+  return P;
+}
+__device__ __forceinline__ void stage_large(const LargeArgs& q, const LargePlan& S) {
+  const RowsArgs& p = q.a;
+  for (int i = threadIdx.x; i < p.r * p.d; i += RW_THREADS) {
+    S.Wd[i] = p.Wd[i];
+    S.WuT[i] = p.Wu[(size_t)(i % p.d) * p.r + i / p.d];
+  }
+  for (int i = threadIdx.x; i < q.rg * p.d; i += RW_THREADS) {
+    S.Gd[i] = q.Gd[i];
+    S.GuT[i] = q.Gu[(size_t)(i % p.d) * q.rg + i / p.d];
+  }
+  for (int i = threadIdx.x; i < p.d; i += RW_THREADS) { S.bu[i] = p.bu[i]; S.gbu[i] = q.gbu[i]; }
+  __syncthreads();
+}
+// acc[j] += <row chunk, W_j chunk> over all chunks of a row held in shared memory
+template <int NCH, int RMAX>
+__device__ __forceinline__ void branch_dots(const __nv_bfloat16* srow, const __nv_bfloat16* sW, int r, int d, int lane, float (&acc)[RMAX]) {
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    float xc[8];
+    lds8(srow + ch * 256 + lane * 8, xc);
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      if (j < r) {
+        float w[8];
+        lds8(sW + (size_t)j * d + ch * 256 + lane * 8, w);
+        acc[j] = dot8(xc, w, acc[j]);
+      }
+    }
+  }
+}
+// y = bias_c + sum_j z_j W^T_j,c for one 8-element chunk piece
+template <int RMAX>
+__device__ __forceinline__ void up_piece(const __nv_bfloat16* sWT, const __nv_bfloat16* sbias, const float (&z)[RMAX], int r, int d, int off,
+                                         float (&y)[8]) {
+  lds8(sbias + off, y);
+#pragma unroll
+  for (int j = 0; j < RMAX; ++j) {
+    if (j < r) {
+      float w[8];
+      lds8(sWT + (size_t)j * d + off, w);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = fmaf(z[j], w[e], y[e]);
+    }
+  }
+}
+// forward quantities of a row: y1 and G per element (registers), pre-activations of both branches
+template <int NCH, int RMAX>
+struct LargeFwd { float y1[NCH * 8], G[NCH * 8], a[RMAX], z[RMAX], pa[RMAX], q[RMAX]; };
+template <int NCH, int RMAX>
+__device__ __forceinline__ void large_forward(const LargeArgs& q, const LargePlan& S, const __nv_bfloat16* sx1, const __nv_bfloat16* sx2,
+                                              int lane, LargeFwd<NCH, RMAX>& F) {
+  const RowsArgs& p = q.a;
+  float acc[2 * RMAX];
+#pragma unroll
+  for (int j = 0; j < 2 * RMAX; ++j) acc[j] = 0.f;
+  {
+    float (&aa)[RMAX] = *reinterpret_cast<float (*)[RMAX]>(&acc[0]);
+    float (&pp)[RMAX] = *reinterpret_cast<float (*)[RMAX]>(&acc[RMAX]);
+    branch_dots<NCH, RMAX>(sx2, S.Wd, p.r, p.d, lane, aa);
+    branch_dots<NCH, RMAX>(sx1, S.Gd, q.rg, p.d, lane, pp);
+  }
+  warp_sum_n<2 * RMAX>(acc);
+#pragma unroll
+  for (int j = 0; j < RMAX; ++j) {
+    F.a[j] = acc[j] + (j < p.r ? __bfloat162float(p.bd[j]) : 0.f);
+    F.z[j] = j < p.r ? gelu_new_f(F.a[j]) : 0.f;
+    F.pa[j] = acc[RMAX + j] + (j < q.rg ? __bfloat162float(q.gbd[j]) : 0.f);
+    F.q[j] = j < q.rg ? gelu_new_f(F.pa[j]) : 0.f;
+  }
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int off = ch * 256 + lane * 8;
+    float x2c[8], y[8], t[8];
+    lds8(sx2 + off, x2c);
+    up_piece<RMAX>(S.WuT, S.bu, F.z, p.r, p.d, off, y);
+    up_piece<RMAX>(S.GuT, S.gbu, F.q, q.rg, p.d, off, t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      F.y1[ch * 8 + e] = p.kappa * x2c[e] + p.alpha * y[e];
+      F.G[ch * 8 + e] = sigmoid_f(t[e]);
+    }
+  }
+}
+
+template <int NCH, int RMAX>
+__global__ void __launch_bounds__(RW_THREADS, 2) rows_large_fwd_kernel(const LargeArgs q) {
+  constexpr int NT = 2;
+  const RowsArgs& p = q.a;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const LargePlan S = carve_large(smem, p.d, p.r, q.rg);
+  stage_large(q, S);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
+  const int64_t nw = (int64_t)gridDim.x * RW_WARPS;
+  __nv_bfloat16* const wrows = S.rows + (size_t)warp * RW_NS * NT * p.d;
+  int64_t row = (int64_t)blockIdx.x * RW_WARPS + warp;
+  if (row < p.M) issue_row<NCH, NT>(p, row, lane, wrows);
+  cp_async_commit();
+  for (int it = 0; row < p.M; ++it, row += nw) {
+    if (row + nw < p.M) issue_row<NCH, NT>(p, row + nw, lane, wrows + (size_t)((it + 1) & 1) * NT * p.d);
+    cp_async_commit();
+    cp_async_wait1();
+    const __nv_bfloat16* sx1 = wrows + (size_t)(it & 1) * NT * p.d;
+    LargeFwd<NCH, RMAX> F;
+    large_forward<NCH, RMAX>(q, S, sx1, sx1 + p.d, lane, F);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      float x1c[8], m[8], o[8];
+      lds8(sx1 + ch * 256 + lane * 8, x1c);
+      drop_scale8(seed_eff, p.thr16, p.inv_keep, row * p.d + ch * 256 + lane * 8, m);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float y = F.y1[ch * 8 + e], g = F.G[ch * 8 + e];
+        o[e] = x1c[e] + p.s * m[e] * (p.add_gate ? y + g : y * g);
+      }
+      stg8(p.out + row * p.d + ch * 256 + lane * 8, o);
+    }
+  }
+}
+
+template <int NCH, int RMAX>
+__global__ void __launch_bounds__(RW_THREADS, 2) rows_large_bwd_kernel(const LargeArgs q) {
+  constexpr int NT = 3;
+  const RowsArgs& p = q.a;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const LargePlan S = carve_large(smem, p.d, p.r, q.rg);
+  stage_large(q, S);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t seed_eff = p.seed + ((p.thr16 && p.seed_dev) ? __ldg(p.seed_dev) : 0ull);
+  const int64_t nw = (int64_t)gridDim.x * RW_WARPS;
+  __nv_bfloat16* const wrows = S.rows + (size_t)warp * RW_NS * NT * p.d;
+  float acc_da[RMAX], acc_dp[RMAX];       // dbd / dgbd in fp32
+#pragma unroll
+  for (int j = 0; j < RMAX; ++j) acc_da[j] = acc_dp[j] = 0.f;
+  int64_t row = (int64_t)blockIdx.x * RW_WARPS + warp;
+  if (row < p.M) issue_row<NCH, NT>(p, row, lane, wrows);
+  cp_async_commit();
+  for (int it = 0; row < p.M; ++it, row += nw) {
+    if (row + nw < p.M) issue_row<NCH, NT>(p, row + nw, lane, wrows + (size_t)((it + 1) & 1) * NT * p.d);
+    cp_async_commit();
+    cp_async_wait1();
+    const __nv_bfloat16* sx1 = wrows + (size_t)(it & 1) * NT * p.d;
+    const __nv_bfloat16* sx2 = sx1 + p.d;
+    const __nv_bfloat16* sdo = sx2 + p.d;
+    LargeFwd<NCH, RMAX> F;
+    large_forward<NCH, RMAX>(q, S, sx1, sx2, lane, F);
+    // ---- sweep C: dh = s m dout; dy1 = dh G (add gate: dh), dT = dh y1 G (1 - G) (add gate: dh G (1 - G)); du / dT rows out;
+    //      dz_j = alpha <dy1, Wu^T_j>, dq_j = <dT, Gu^T_j>.  F.y1 / F.G are overwritten by dy1 / dT (sweep D needs only those).
+    float dzq[2 * RMAX];
+#pragma unroll
+    for (int j = 0; j < 2 * RMAX; ++j) dzq[j] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int off = ch * 256 + lane * 8;
+      float doc[8], m[8], dy1[8], dT[8], du[8];
+      lds8(sdo + off, doc);
+      drop_scale8(seed_eff, p.thr16, p.inv_keep, row * p.d + off, m);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dh = p.s * m[e] * doc[e], y = F.y1[ch * 8 + e], g = F.G[ch * 8 + e], gg = g * (1.f - g);
+        dy1[e] = p.add_gate ? dh : dh * g;
+        dT[e] = p.add_gate ? dh * gg : dh * y * gg;
+        du[e] = p.alpha * dy1[e];
+        F.y1[ch * 8 + e] = dy1[e];
+        F.G[ch * 8 + e] = dT[e];
+      }
+      stg8(p.du + row * p.d + off, du);
+      stg8(q.dt + row * p.d + off, dT);
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j) {
+        float w[8];
+        if (j < p.r) { lds8(S.WuT + (size_t)j * p.d + off, w); dzq[j] = dot8(du, w, dzq[j]); }
+        if (j < q.rg) { lds8(S.GuT + (size_t)j * p.d + off, w); dzq[RMAX + j] = dot8(dT, w, dzq[RMAX + j]); }
+      }
+    }
+    warp_sum_n<2 * RMAX>(dzq);
+    float da[RMAX], dp[RMAX];
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      da[j] = j < p.r ? dzq[j] * gelu_new_grad_f(F.a[j]) : 0.f;
+      dp[j] = j < q.rg ? dzq[RMAX + j] * gelu_new_grad_f(F.pa[j]) : 0.f;
+      acc_da[j] += da[j];
+      acc_dp[j] += dp[j];
+    }
+    {   // z | 1 | 0.. and da rows (pitch pz), q | 1 | 0.. and dp rows (pitch pq): the ones column sits at index r8 / rg8
+      float zv = 0.f, dv = 0.f, qv = 0.f, pv = 0.f;
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j)
+        if (lane == j) { zv = F.z[j]; dv = da[j]; qv = F.q[j]; pv = dp[j]; }
+      if (lane < p.pz) {
+        if (lane >= p.r) { zv = lane == p.r8 ? 1.f : 0.f; dv = 0.f; }
+        p.zs[row * p.pz + lane] = __float2bfloat16_rn(zv);
+        p.das[row * p.pz + lane] = __float2bfloat16_rn(dv);
+      }
+      if (lane < q.pq) {
+        if (lane >= q.rg) { qv = lane == q.rg8 ? 1.f : 0.f; pv = 0.f; }
+        q.qs[row * q.pq + lane] = __float2bfloat16_rn(qv);
+        q.dps[row * q.pq + lane] = __float2bfloat16_rn(pv);
+      }
+    }
+    // ---- sweep D: dx2 = kappa dy1 + sum_j da_j Wd_j, dx1 = dout + sum_j dp_j Gd_j
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int off = ch * 256 + lane * 8;
+      float dx1[8], dx2[8];
+      lds8(sdo + off, dx1);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dx2[e] = p.kappa * F.y1[ch * 8 + e];
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j) {
+        float w[8];
+        if (j < p.r) {
+          lds8(S.Wd + (size_t)j * p.d + off, w);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dx2[e] = fmaf(da[j], w[e], dx2[e]);
+        }
+        if (j < q.rg) {
+          lds8(S.Gd + (size_t)j * p.d + off, w);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dx1[e] = fmaf(dp[j], w[e], dx1[e]);
+        }
+      }
+      stg8(p.dx1 + row * p.d + off, dx1);
+      stg8(p.dx2 + row * p.d + off, dx2);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      if (p.dbd && j < p.r) atomicAdd(p.dbd + j, acc_da[j]);
+      if (q.dgbd && j < q.rg) atomicAdd(q.dgbd + j, acc_dp[j]);
+    }
+  }
+}
+
 // add the first r columns / rows of the zero-padded weight-gradient buffers (rank padded to 8 for the GEMM) into the real ones
 __global__ void unpad_add_kernel(const float* __restrict__ pWu, const float* __restrict__ pWd, float* dWu, float* dWd, int d, int r, int r8) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -591,11 +855,123 @@ RowsArgs base_args(const VlpetK1Desc& D, const VlpetK1Params& w) {
   return a;
 }
 
+
+// ---- large gate at small ranks: host side -------------------------------------------------------------------------------------
+struct LargeWs {
+  __nv_bfloat16 *du, *dt, *zs, *das, *qs, *dps;
+  float *pWu, *pWd, *pGu, *pGd;
+  size_t bytes;
+  int r8, rg8, pz, pq;
+};
+LargeWs carve_large_ws(const VlpetK1Desc& D, bool bwd, void* ws) {
+  LargeWs w;
+  memset(&w, 0, sizeof(w));
+  w.r8 = r8_of(D.r); w.rg8 = r8_of(D.rg); w.pz = w.r8 + 8; w.pq = w.rg8 + 8;
+  Arena a(ws, (size_t)-1);
+  if (bwd) {
+    w.du = a.take<__nv_bfloat16>((size_t)D.M * D.d); w.dt = a.take<__nv_bfloat16>((size_t)D.M * D.d);
+    w.zs = a.take<__nv_bfloat16>((size_t)D.M * w.pz); w.das = a.take<__nv_bfloat16>((size_t)D.M * w.pz);
+    w.qs = a.take<__nv_bfloat16>((size_t)D.M * w.pq); w.dps = a.take<__nv_bfloat16>((size_t)D.M * w.pq);
+    if (w.r8 != D.r) { w.pWu = a.take<float>((size_t)D.d * w.r8); w.pWd = a.take<float>((size_t)D.d * w.r8); }
+    if (w.rg8 != D.rg) { w.pGu = a.take<float>((size_t)D.d * w.rg8); w.pGd = a.take<float>((size_t)D.d * w.rg8); }
+  }
+  w.bytes = a.off;
+  return w;
+}
+bool large_rows_supported(const VlpetK1Desc& D, bool bwd) {
+  if (D.dtype != VLPET_BF16 || D.gate != VLPET_GATE_LARGE || D.r > RW_MAXR || D.rg > RW_MAXR || D.r < 1 || D.rg < 1) return false;
+  if (D.d % 256 != 0 || D.d < 256 || D.d > 768 || D.M <= 0 || device_sm_count() <= 0) return false;
+  if (large_smem_bytes(D.d, D.r, D.rg, 3) > 200 * 1024) return false;
+  return !bwd || (wgrad_sm100_supported(D.d, r8_of(D.r)) && wgrad_sm100_supported(D.d, r8_of(D.rg)));
+}
+LargeArgs large_args(const VlpetK1Desc& D, const VlpetK1Params& w) {
+  LargeArgs q;
+  memset(&q, 0, sizeof(q));
+  q.a = base_args(D, w);
+  q.rg = D.rg; q.rg8 = r8_of(D.rg); q.pq = q.rg8 + 8;
+  q.a.r8 = r8_of(D.r); q.a.pz = q.a.r8 + 8;
+  q.Gd = static_cast<const __nv_bfloat16*>(w.Gd); q.gbd = static_cast<const __nv_bfloat16*>(w.gbd);
+  q.Gu = static_cast<const __nv_bfloat16*>(w.Gu); q.gbu = static_cast<const __nv_bfloat16*>(w.gbu);
+  return q;
+}
+template <int NCH, int RMAX>
+int launch_large_k(bool bwd, const LargeArgs& q, int sms, cudaStream_t st) {
+  const size_t smem = large_smem_bytes(q.a.d, q.a.r, q.rg, bwd ? 3 : 2);
+  int64_t blocks = (q.a.M + RW_WARPS - 1) / RW_WARPS;
+  if (blocks > 2 * sms) blocks = 2 * sms;
+  auto kf = rows_large_fwd_kernel<NCH, RMAX>;
+  auto kb = rows_large_bwd_kernel<NCH, RMAX>;
+  static int attr_f[64] = {0}, attr_b[64] = {0};
+  if (bwd) VLPET_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kb), attr_b, (int)smem));
+  else VLPET_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kf), attr_f, (int)smem));
+  if (bwd) kb<<<(unsigned)blocks, RW_THREADS, smem, st>>>(q);
+  else kf<<<(unsigned)blocks, RW_THREADS, smem, st>>>(q);
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+int launch_large(bool bwd, const LargeArgs& q, int sms, cudaStream_t st) {
+  const int rm = (q.a.r > q.rg ? q.a.r : q.rg) <= 4 ? 4 : RW_MAXR;
+  switch (q.a.d / 256) {
+    case 1: return rm == 4 ? launch_large_k<1, 4>(bwd, q, sms, st) : launch_large_k<1, RW_MAXR>(bwd, q, sms, st);
+    case 2: return rm == 4 ? launch_large_k<2, 4>(bwd, q, sms, st) : launch_large_k<2, RW_MAXR>(bwd, q, sms, st);
+    case 3: return rm == 4 ? launch_large_k<3, 4>(bwd, q, sms, st) : launch_large_k<3, RW_MAXR>(bwd, q, sms, st);
+  }
+  return fail(VLPET_E_UNSUPPORTED, "rows(large): d = %d", q.a.d);
+}
+int large_rows_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const VlpetK1Params& w, void* out, cudaStream_t st) {
+  LargeArgs q = large_args(D, w);
+  q.a.x1 = static_cast<const __nv_bfloat16*>(x1); q.a.x2 = static_cast<const __nv_bfloat16*>(x2);
+  q.a.out = static_cast<__nv_bfloat16*>(out);
+  return launch_large(false, q, device_sm_count(), st);
+}
+int large_rows_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const void* dout, const VlpetK1Params& w, void* dx1, void* dx2,
+                   const VlpetK1Grads& G, void* ws, size_t ws_bytes, cudaStream_t st) {
+  LargeWs W = carve_large_ws(D, true, ws);
+  if (!ws || ws_bytes < W.bytes) return fail(VLPET_E_WORKSPACE, "k1_bwd(rows, large): workspace %zu < %zu bytes", ws_bytes, W.bytes);
+  const int sms = device_sm_count();
+  LargeArgs q = large_args(D, w);
+  q.a.x1 = static_cast<const __nv_bfloat16*>(x1); q.a.x2 = static_cast<const __nv_bfloat16*>(x2);
+  q.a.dout = static_cast<const __nv_bfloat16*>(dout);
+  q.a.dx1 = static_cast<__nv_bfloat16*>(dx1); q.a.dx2 = static_cast<__nv_bfloat16*>(dx2);
+  q.a.du = W.du; q.dt = W.dt; q.a.zs = W.zs; q.a.das = W.das; q.qs = W.qs; q.dps = W.dps;
+  q.a.dbd = G.dbd; q.dgbd = G.dgbd;
+  VLPET_TRY(launch_large(true, q, sms, st));
+  // weight gradients: dWu = du^T z (+dbu), dWd = (x2^T da)^T for the adapter branch; dGu = dT^T q (+dgbu), dGd = (x1^T dp)^T for the gate
+  for (int br = 0; br < 2; ++br) {
+    const int r = br ? D.rg : D.r, r8 = br ? W.rg8 : W.r8, pitch = br ? W.pq : W.pz;
+    float* gWu = br ? G.dGu : G.dWu; float* gWd = br ? G.dGd : G.dWd; float* gbu = br ? G.dgbu : G.dbu;
+    float* pWu = br ? W.pGu : W.pWu; float* pWd = br ? W.pGd : W.pWd;
+    float *oWu = gWu, *oWd = gWd;
+    if (r8 != r) {
+      VLPET_CUDA_OK(cudaMemsetAsync(pWu, 0, (size_t)D.d * r8 * sizeof(float), st));
+      VLPET_CUDA_OK(cudaMemsetAsync(pWd, 0, (size_t)D.d * r8 * sizeof(float), st));
+      oWu = gWu ? pWu : nullptr; oWd = gWd ? pWd : nullptr;
+    }
+    const void* A[2]; const void* Bm[2]; int64_t lda[2], ldb[2]; int nbv[2], tr[2]; float* out[2]; float* bias[2]; float sc[2];
+    int k = 0;
+    if (oWu || gbu) {
+      if (!oWu) return fail(VLPET_E_BADARG, "k1_bwd(rows, large): a bias gradient needs its weight gradient buffer");
+      A[k] = br ? W.dt : W.du; lda[k] = D.d; Bm[k] = br ? W.qs : W.zs; ldb[k] = pitch; nbv[k] = r8 + 1; tr[k] = 0; out[k] = oWu; bias[k] = gbu; sc[k] = 1.f; ++k;
+    }
+    if (oWd) {
+      A[k] = br ? x1 : x2; lda[k] = D.d; Bm[k] = br ? W.dps : W.das; ldb[k] = pitch; nbv[k] = r8; tr[k] = 1; out[k] = oWd; bias[k] = nullptr; sc[k] = 1.f; ++k;
+    }
+    if (k) VLPET_TRY(wgrad_sm100(k, A, lda, Bm, ldb, nbv, out, bias, sc, tr, D.M, D.d, r8, sms, st));
+    if (r8 != r && (gWu || gWd)) {
+      const int n = D.d * r;
+      unpad_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(pWu, pWd, gWu, gWd, D.d, r, r8);
+      VLPET_LAUNCH_OK();
+    }
+  }
+  return 0;
+}
+
 }  // namespace
 
 // ---- entry points ------------------------------------------------------------------------------------------------
 bool rows_k1_supported(const VlpetK1Desc& D, bool bwd) {
-  if (D.dtype != VLPET_BF16 || D.gate == VLPET_GATE_LARGE) return false;
+  if (D.gate == VLPET_GATE_LARGE) return large_rows_supported(D, bwd);
+  if (D.dtype != VLPET_BF16) return false;
   if (D.d % 256 != 0 || D.d < 256 || D.d > 768 || D.M <= 0) return false;
   if (D.gate == VLPET_GATE_SMALL && (D.L <= 0 || D.M % D.L != 0)) return false;
   if (device_sm_count() <= 0) return false;
@@ -612,11 +988,16 @@ bool rows_k1_supported(const VlpetK1Desc& D, bool bwd) {
   }
   return true;
 }
-size_t rows_k1_fwd_ws(const VlpetK1Desc& D) { return carve_rows(D, false, nullptr).bytes; }
-size_t rows_k1_bwd_ws(const VlpetK1Desc& D) { return carve_rows(D, true, nullptr).bytes; }
+size_t rows_k1_fwd_ws(const VlpetK1Desc& D) {
+  return D.gate == VLPET_GATE_LARGE ? carve_large_ws(D, false, nullptr).bytes : carve_rows(D, false, nullptr).bytes;
+}
+size_t rows_k1_bwd_ws(const VlpetK1Desc& D) {
+  return D.gate == VLPET_GATE_LARGE ? carve_large_ws(D, true, nullptr).bytes : carve_rows(D, true, nullptr).bytes;
+}
 
 int rows_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const VlpetK1Params& w, void* out, void* ws, size_t ws_bytes,
                 cudaStream_t st) {
+  if (D.gate == VLPET_GATE_LARGE) return large_rows_fwd(D, x1, x2, w, out, st);
   RowsWs W = carve_rows(D, false, ws);
   if (W.bytes && (!ws || ws_bytes < W.bytes)) return fail(VLPET_E_WORKSPACE, "k1_fwd(rows): workspace %zu < %zu bytes", ws_bytes, W.bytes);
   const int sms = device_sm_count();
@@ -643,6 +1024,7 @@ int rows_k1_fwd(const VlpetK1Desc& D, const void* x1, const void* x2, const Vlpe
 
 int rows_k1_bwd(const VlpetK1Desc& D, const void* x1, const void* x2, const void* dout, const VlpetK1Params& w, void* dx1, void* dx2,
                 const VlpetK1Grads& G, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (D.gate == VLPET_GATE_LARGE) return large_rows_bwd(D, x1, x2, dout, w, dx1, dx2, G, ws, ws_bytes, st);
   RowsWs W = carve_rows(D, true, ws);
   if (!ws || ws_bytes < W.bytes) return fail(VLPET_E_WORKSPACE, "k1_bwd(rows): workspace %zu < %zu bytes", ws_bytes, W.bytes);
   const int sms = device_sm_count();
