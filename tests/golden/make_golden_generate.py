@@ -7,7 +7,9 @@ vqa_model.py:235-288).  Test infrastructure; run in the build container:
 
     python tests/golden/make_golden_generate.py
 
-Writes ``vlbart_tiny_generate.npz``: state_dict, batch, the greedy token ids and the last-position logits of every step.
+Writes ``vlbart_tiny_generate.npz`` and ``vlt5_tiny_generate.npz`` (the T5 twin: src/modeling_t5.py:560-690 with
+``past_key_values``, my_transformers/modeling_t5.py:588-613 for the cached value parallel adapter): state_dict, batch, the greedy
+token ids and the last-position logits of every step.
 HF's search machinery (logits processors, beam search) is the caller's and is not part of the fixture.
 """
 import os
@@ -27,7 +29,8 @@ MIN_LEN = 6      # HF MinLengthLogitsProcessor: the EOS logit is -inf while the 
 @torch.no_grad()
 def greedy(model, config, ids, vis_inputs, task, bias):
     B = ids.shape[0]
-    enc = model.model.encoder(input_ids=ids, vis_inputs=vis_inputs, return_dict=True, task=task)
+    encoder = model.model.encoder if hasattr(model, "model") else model.encoder
+    enc = encoder(input_ids=ids, vis_inputs=vis_inputs, return_dict=True, task=task)
     amask = ids.ne(config.pad_token_id).to(torch.float64)      # what HF generate passes along with encoder_outputs
     dec = torch.full((B, 1), config.decoder_start_token_id, dtype=torch.long)
     past, steps = None, []
@@ -55,6 +58,30 @@ def greedy(model, config, ids, vis_inputs, task, bias):
     return dec.numpy(), np.stack(steps, 1)
 
 
+def main_t5():
+    import make_golden_vlt5 as MT
+    model, config = MT.build()
+    model = model.double().eval()
+    g = torch.Generator().manual_seed(6)
+    B, Lt = 3, 7
+    out = {}
+    sd = model.state_dict()
+    out["meta_state_keys"] = np.array(list(sd.keys()))
+    for k, v in sd.items():
+        out["sd/" + k] = v.detach().cpu().numpy()
+    ids = torch.randint(3, 300, (B, Lt), generator=g)
+    feats = torch.randn(B, 49, MT.FEAT, generator=g, dtype=torch.float64)
+    boxes = torch.zeros(B, 49, 4, dtype=torch.float64)
+    bias = 4.0 * torch.randn(B, MAX_LEN, 300, generator=g, dtype=torch.float64)     # T5 logits are O(1)
+    tokens, logits = greedy(model, config, ids, (feats, boxes), "vqa", bias)
+    out["vqa/input_ids"], out["vqa/vis_feats"], out["vqa/boxes"] = ids.numpy(), feats.numpy(), boxes.numpy()
+    out["vqa/tokens"], out["vqa/step_logits"], out["vqa/logit_bias"] = tokens, logits, bias.numpy()
+    out["meta_max_length"], out["meta_min_length"] = np.array(MAX_LEN), np.array(MIN_LEN)
+    path = os.path.join(HERE, "vlt5_tiny_generate.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path) // 1024, "KB", "tokens", tokens.tolist(), "steps", logits.shape)
+
+
 def main():
     model, config = MV.build("large")
     g = torch.Generator().manual_seed(5)
@@ -79,4 +106,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "t5" in sys.argv[1:]:
+        main_t5()          # (separate processes: the BART and T5 import shims patch transformers differently)
+    else:
+        main()

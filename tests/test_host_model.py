@@ -83,9 +83,9 @@ def test_host_model_matches_reference_vlbart_cpu(H, gate):
             assert rel(params[n].grad.numpy(), z[f"{task}/grad/{n}"]) < 1e-9, (task, n)
 
 
-def _generate_case(H, dtype, device, eager):
-    z = np.load(os.path.join(GOLDEN, "vlbart_tiny_generate.npz"), allow_pickle=False)
-    model = H.VLBart(_cfg(H, "large"))
+def _generate_case(H, dtype, device, eager, arch="bart"):
+    z = np.load(os.path.join(GOLDEN, f"vl{arch}_tiny_generate.npz"), allow_pickle=False)
+    model = H.VLBart(_cfg(H, "large")) if arch == "bart" else H.VLT5(H.tiny_t5_test_config(dropout_rate=0.0, dropout=0.0))
     model = model.double() if dtype == torch.float64 else model
     if eager:
         from oracle.eager_ref import use_eager_pet
@@ -251,6 +251,37 @@ def test_host_model_matches_reference_vlt5_cpu(H):
         assert abs(loss.item() - float(z[f"{task}/loss"])) < 1e-7, (loss.item(), float(z[f"{task}/loss"]))
         for n in names:
             assert rel(params[n].grad.numpy(), z[f"{task}/grad/{n}"]) < 2e-6, (task, n)
+
+
+def test_t5_generate_matches_reference_cached_decode_cpu(H):
+    """T5 twin of test_generate_matches_reference_cached_decode_cpu (golden: the reference VLT5's forward with
+    past_key_values, tests/golden/make_golden_generate.py t5).  The reference takes softmax and RMS statistics in float32
+    inside an fp64 model (see test_host_model_matches_reference_vlt5_cpu): logits bar 1e-6, tokens identical."""
+    z, model, ids, vis, proc = _generate_case(H, torch.float64, "cpu", eager=True, arch="t5")
+    tokens, logits = model.generate(ids, vis, task="vqa", max_length=int(z["meta_max_length"]), min_length=int(z["meta_min_length"]),
+                                    logits_processor=proc, return_step_logits=True)
+    assert tokens.tolist() == z["vqa/tokens"].tolist()
+    assert rel(logits.numpy(), z["vqa/step_logits"]) < 1e-6
+    with torch.no_grad():          # the cached steps reproduce the model's own full teacher-forced pass
+        enc, mask = model.encoder(ids, vis, task="vqa")
+        h = model.decoder(tokens[:, :-1], enc, encoder_mask=mask, task="vqa")
+        full = model.lm_head(h * (model.model_dim ** -0.5))
+    assert rel(full.numpy(), logits.numpy()) < 1e-9
+    with pytest.raises(NotImplementedError):
+        model.generate(ids, vis, task="vqa", num_beams=5)
+
+
+@pytest.mark.gpu
+def test_t5_generate_with_cuda_vpa_matches_reference_cached_decode(H):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    z, model, ids, vis, proc = _generate_case(H, torch.float32, "cuda", eager=False, arch="t5")
+    tokens, logits = model.generate(ids, vis, task="vqa", max_length=int(z["meta_max_length"]), min_length=int(z["meta_min_length"]),
+                                    logits_processor=proc, return_step_logits=True)
+    assert tokens.cpu().tolist() == z["vqa/tokens"].tolist()
+    assert rel(logits.double().cpu().numpy(), z["vqa/step_logits"]) < 2e-4
 
 
 def test_t5_base_trainable_count_is_the_reference_checksum(H):

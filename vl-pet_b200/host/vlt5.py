@@ -83,6 +83,31 @@ class T5Attention(nn.Module):
         return self.o(o.transpose(1, 2).reshape(B, L, self.inner_dim))
 
 
+    # ---- KV-cached decode (my_transformers/modeling_t5.py:535-613) --------------------------------------
+    def _sh(self, t: torch.Tensor) -> torch.Tensor:
+        return t.view(t.shape[0], -1, self.n_heads, self.d_kv).transpose(1, 2)
+
+    def cross_kv(self, encoder_hidden_states, task=None):
+        """Cross-attention heads for a whole generation, the values through the value parallel adapter (K2, forward only):
+        the pair the reference keeps in ``past_key_value`` after the first step."""
+        k, v = self.k(encoder_hidden_states), self.v(encoder_hidden_states)
+        if self.attn_value_parallel_adapter is not None:
+            v = self.attn_value_parallel_adapter(encoder_hidden_states, task, y=v)                  # K2
+        return self._sh(k), self._sh(v)
+
+    def self_kv(self, hidden_states, past=None):
+        kh, vh = self._sh(self.k(hidden_states)), self._sh(self.v(hidden_states))
+        if past is not None:
+            kh, vh = torch.cat([past[0], kh], dim=2), torch.cat([past[1], vh], dim=2)
+        return kh, vh
+
+    def attend_cached(self, hidden_states, kh, vh, bias=None):
+        B, T, _ = hidden_states.shape
+        m = bias.to(hidden_states.dtype) if bias is not None else None
+        o = F.scaled_dot_product_attention(self._sh(self.q(hidden_states)), kh, vh, attn_mask=m, scale=1.0)
+        return self.o(o.transpose(1, 2).reshape(B, T, self.inner_dim))
+
+
 def _rms(ln: T5LayerNorm, x: torch.Tensor) -> torch.Tensor:
     """T5LayerNorm (my_transformers/modeling_t5.py:235-252: fp32 statistics, no mean subtraction, weight only).  Frozen-side
     plumbing: torch's fused rms_norm on the GPU (the weight is an fp32 master under --unfreeze_encoder_layer_norms)."""
@@ -192,6 +217,17 @@ class T5Block(nn.Module):
         return self.layer[-1](hidden_states)
 
 
+    @torch.no_grad()
+    def step(self, hidden_states, cross, self_past=None, bias=None, cross_bias=None):
+        """Incremental decoder block (eval mode): T new positions against the cached self-attention heads and the
+        generation-long cross-attention heads.  Returns (hidden_states, new self-attention cache)."""
+        sa, ca = self.layer[0], self.layer[1]
+        kv = sa.SelfAttention.self_kv(_rms(sa.layer_norm, hidden_states), self_past)
+        hidden_states = hidden_states + sa.SelfAttention.attend_cached(_rms(sa.layer_norm, hidden_states), kv[0], kv[1], bias)
+        hidden_states = hidden_states + ca.EncDecAttention.attend_cached(_rms(ca.layer_norm, hidden_states), cross[0], cross[1], cross_bias)
+        return self.layer[-1](hidden_states), kv
+
+
 def _additive(mask_2d: Optional[torch.Tensor], dtype):
     """[B, S] 1/0 -> additive [B, 1, 1, S] (0 / -1e4-style large negative; the reference uses -10000.0)."""
     if mask_2d is None:
@@ -269,6 +305,29 @@ class T5DecoderStack(nn.Module):
         return F.dropout(x, p=self.dropout, training=self.training)
 
 
+    @torch.no_grad()
+    def init_cache(self, encoder_hidden_states, encoder_mask=None, task=None):
+        cross = [blk.layer[1].EncDecAttention.cross_kv(encoder_hidden_states, task) for blk in self.block]
+        return {"cross": cross, "self": [None] * len(self.block), "len": 0, "mask": encoder_mask}
+
+    @torch.no_grad()
+    def step(self, input_ids, cache):
+        """``input_ids`` [B, T]: the positions after the ``cache['len']`` decoded ones -> normalised hidden states [B, T, d]."""
+        B, T = input_ids.shape
+        S = cache["len"] + T
+        x = self.embed_tokens(input_ids)
+        bias = self.block[0].layer[0].SelfAttention.compute_bias(S, S)[:, :, S - T:, :]
+        causal = torch.ones(T, S, dtype=torch.bool, device=x.device).tril(diagonal=S - T)
+        bias = (bias.float() + torch.where(causal, 0.0, -10000.0)[None, None]).to(x.dtype)
+        cross = None
+        if cache["mask"] is not None:
+            cross = ((1.0 - cache["mask"][:, None, None, :].float()) * -1e9).to(x.dtype).expand(B, 1, T, -1)
+        for i, blk in enumerate(self.block):
+            x, cache["self"][i] = blk.step(x, cache["cross"][i], cache["self"][i], bias, cross)
+        cache["len"] = S
+        return _rms(self.final_layer_norm, x)
+
+
 class VLT5(nn.Module):
     """LM head (tied, output scaled by d^-0.5) + token-level cross-entropy with reduction='none'
     (src/modeling_t5.py:655-690) and the per-task loss shaping of the reference task models."""
@@ -325,6 +384,58 @@ class VLT5(nn.Module):
                 lg = lg.float()
             loss = F.cross_entropy(lg, labels.reshape(-1), ignore_index=-100, reduction="none")
         return loss, logits
+
+    @torch.no_grad()
+    def generate(self, input_ids, vis_inputs, task=None, max_length: int = 20, min_length: int = 0, num_beams: int = 1,
+                 logits_processor=None, attention_mask=None, vis_attention_mask=None, return_step_logits: bool = False):
+        """Greedy decoding through the KV cache (src/modeling_t5.py:560-690 with ``past_key_values``; T5 twin of
+        host.VLBart.generate): encoder once, cross-attention heads -- values through the value parallel adapter (K2) -- once,
+        one new position per step.  ``num_beams > 1`` is the caller's search loop and raises."""
+        if num_beams != 1:
+            raise NotImplementedError("host.VLT5.generate: greedy decoding only (num_beams == 1)")
+        cfg = self.config
+        eos = getattr(cfg, "eos_token_id", 1)
+        was_training = self.training
+        self.eval()
+        try:
+            enc, mask = self.encoder(input_ids, vis_inputs, attention_mask, vis_attention_mask, task=task)
+            cache = self.decoder.init_cache(enc, mask, task=task)
+            B = input_ids.shape[0]
+            tokens = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=input_ids.device)
+            done = torch.zeros(B, dtype=torch.bool, device=input_ids.device)
+            steps = []
+            while tokens.shape[1] < max_length:
+                h = self.decoder.step(tokens if cache["len"] == 0 else tokens[:, -1:], cache)
+                scores = self.lm_head(h[:, -1] * (self.model_dim ** -0.5))
+                if scores.dtype in (torch.bfloat16, torch.float16):
+                    scores = scores.float()
+                if return_step_logits:
+                    steps.append(scores.clone())
+                if logits_processor is not None:
+                    scores = logits_processor(tokens.shape[1] - 1, tokens, scores)
+                if tokens.shape[1] < min_length:
+                    scores[:, eos] = -float("inf")
+                nxt = scores.argmax(-1)
+                nxt = torch.where(done, torch.full_like(nxt, cfg.pad_token_id), nxt)
+                done |= nxt == eos
+                tokens = torch.cat([tokens, nxt[:, None]], dim=1)
+                if bool(done.all()):
+                    break
+        finally:
+            self.train(was_training)
+        return (tokens, torch.stack(steps, 1)) if return_step_logits else tokens
+
+    @torch.no_grad()
+    def test_step(self, batch: dict, **gen_kwargs) -> dict:
+        """vqa_model.py:112-164 (the T5 task model's generative test_step): batch -> {'token_ids'}."""
+        dev = self.shared.weight.device
+        feats, boxes = batch["vis_feats"].to(dev, non_blocking=True), batch["boxes"].to(dev, non_blocking=True)
+        out = self.generate(batch["input_ids"].to(dev, non_blocking=True), (feats, boxes), task=batch["task"], **gen_kwargs)
+        result = {"token_ids": out}
+        tok = getattr(self, "tokenizer", None)
+        if tok is not None:
+            result["pred_ans"] = tok.batch_decode(out, skip_special_tokens=True)
+        return result
 
     def train_step(self, batch: dict) -> dict:
         """Same batch schema and loss shaping as host.VLBart.train_step (vqa_model.py:44-110 etc. are the T5 twins)."""
