@@ -755,6 +755,71 @@ int generic_k3_fwd(const VlpetK3Desc& D, const void* feats, const void* pos, con
   return 0;
 }
 
+// Every token-contracted [M, d] reduction of the K3 backward in ONE pass over dout, XF, XA, dF, dA (round 1 ran a column-sum or
+// CUDA-core GEMM launch per output: nine launches, each a full pass):
+//   dln_f_w = sum dout XF, dln_p_w = sum dout XA, dln_f_b = dln_p_b = sum dout, dbf = sum dF, dbp = sum dA,
+//   dE_img[i] = sum_{img == i} dout, dWp[c, k] = sum dA[., c] P5[., k]   (k < 5: the box features of the position projection)
+// A thread owns a column, a block a slab of rows; partial sums leave through one atomicAdd per output element and block.
+struct K3SumArgs {
+  const void* dout;
+  int bf16, n_img, d;
+  const float *XF, *XA, *dF, *dA, *P5;
+  const int64_t* img_ids;
+  int64_t M;
+  int rows_per_block;
+  float *dln_f_w, *dln_p_w, *dln_f_b, *dln_p_b, *dbf, *dbp, *dE_img, *dWp;
+};
+constexpr int K3S_MAX_IMG = 4;
+__global__ void __launch_bounds__(128) k3_sums_kernel(const K3SumArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.d) return;
+  int64_t m0 = (int64_t)blockIdx.y * a.rows_per_block, m1 = m0 + a.rows_per_block;
+  if (m1 > a.M) m1 = a.M;
+  float s_fw = 0.f, s_pw = 0.f, s_do = 0.f, s_df = 0.f, s_da = 0.f, s_img[K3S_MAX_IMG], s_wp[5];
+#pragma unroll
+  for (int i = 0; i < K3S_MAX_IMG; ++i) s_img[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) s_wp[k] = 0.f;
+  for (int64_t m = m0; m < m1; ++m) {
+    const int64_t i = m * a.d + c;
+    const float go = ld_as_float(a.dout, i, a.bf16), da = a.dA[i];
+    s_fw = fmaf(go, a.XF[i], s_fw);
+    s_pw = fmaf(go, a.XA[i], s_pw);
+    s_do += go;
+    s_df += a.dF[i];
+    s_da += da;
+    const int img = a.img_ids ? (int)a.img_ids[m] : 0;
+#pragma unroll
+    for (int q = 0; q < K3S_MAX_IMG; ++q)
+      if (img == q) s_img[q] += go;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) s_wp[k] = fmaf(da, __ldg(a.P5 + m * 5 + k), s_wp[k]);
+  }
+  if (a.dln_f_w) atomicAdd(a.dln_f_w + c, s_fw);
+  if (a.dln_p_w) atomicAdd(a.dln_p_w + c, s_pw);
+  if (a.dln_f_b) atomicAdd(a.dln_f_b + c, s_do);
+  if (a.dln_p_b) atomicAdd(a.dln_p_b + c, s_do);
+  if (a.dbf) atomicAdd(a.dbf + c, s_df);
+  if (a.dbp) atomicAdd(a.dbp + c, s_da);
+  if (a.dE_img)
+    for (int q = 0; q < a.n_img && q < K3S_MAX_IMG; ++q)
+      if (s_img[q] != 0.f) atomicAdd(a.dE_img + (size_t)q * a.d + c, s_img[q]);
+  if (a.dWp)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) atomicAdd(a.dWp + (size_t)c * 5 + k, s_wp[k]);
+}
+int launch_k3_sums(K3SumArgs a, cudaStream_t st) {
+  const int gx = (a.d + 127) / 128;
+  int64_t gy = (1184 + gx - 1) / gx;
+  int64_t rpb = (a.M + gy - 1) / gy;
+  if (rpb < 16) rpb = 16;
+  gy = (a.M + rpb - 1) / rpb;
+  a.rows_per_block = (int)rpb;
+  k3_sums_kernel<<<dim3(gx, (unsigned)gy), 128, 0, st>>>(a);
+  VLPET_LAUNCH_OK();
+  return 0;
+}
+
 int generic_k3_bwd(const VlpetK3Desc& D, const void* feats, const void* pos, const int64_t* img_ids, const void* dout,
                    const VlpetK3Params& w, const float* save, void* dfeats, const VlpetK3Grads& G, void* ws,
                    size_t ws_bytes, cudaStream_t st) {
@@ -773,11 +838,23 @@ int generic_k3_bwd(const VlpetK3Desc& D, const void* feats, const void* pos, con
   visproj_row_kernel<<<warp_rows_blocks(M), 256, 0, st>>>(save, pos, bf, img_ids, nullptr, w, M, D.N, d, D.V, D.rms,
                                                          D.eps, nullptr, dout, dF, dA, XF, XA, P5, dFb);
   VLPET_LAUNCH_OK();
+  const bool one_pass = D.n_img <= K3S_MAX_IMG;
+  if (one_pass) {
+    K3SumArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.dout = dout; sa.bf16 = bf; sa.n_img = (img_ids == nullptr) ? 1 : D.n_img; sa.d = d; sa.M = M;
+    sa.XF = XF; sa.XA = XA; sa.dF = dF; sa.dA = dA; sa.P5 = P5; sa.img_ids = img_ids;
+    sa.dln_f_w = G.dln_f_w; sa.dln_p_w = G.dln_p_w;
+    sa.dln_f_b = D.rms ? nullptr : G.dln_f_b; sa.dln_p_b = D.rms ? nullptr : G.dln_p_b;
+    sa.dbf = G.dbf; sa.dbp = G.dbp; sa.dE_img = G.dE_img; sa.dWp = G.dWp;
+    VLPET_TRY(launch_k3_sums(sa, st));
+  } else {
   VLPET_TRY(launch_colsum(dout, bf, XF, 0, nullptr, 0, M, d, 1.f, G.dln_f_w, st));
   VLPET_TRY(launch_colsum(dout, bf, XA, 0, nullptr, 0, M, d, 1.f, G.dln_p_w, st));
   if (!D.rms) {
     VLPET_TRY(launch_colsum(dout, bf, nullptr, 0, nullptr, 0, M, d, 1.f, G.dln_f_b, st));
     VLPET_TRY(launch_colsum(dout, bf, nullptr, 0, nullptr, 0, M, d, 1.f, G.dln_p_b, st));
+  }
   }
   if (tc) {
     // dWf[n, f] = sum_tok dF[tok, n] feats[tok, f], produced transposed (rows = f) in column blocks of nb outputs
@@ -795,10 +872,12 @@ int generic_k3_bwd(const VlpetK3Desc& D, const void* feats, const void* pos, con
   } else {
     VLPET_TRY(launch_wgrad(dF, 0, d, feats, bf, D.F, M, G.dWf, 1.f, st));
   }
+  if (!one_pass) {
   VLPET_TRY(launch_colsum(dF, 0, nullptr, 0, nullptr, 0, M, d, 1.f, G.dbf, st));
   VLPET_TRY(launch_wgrad(dA, 0, d, P5, 0, 5, M, G.dWp, 1.f, st));
   VLPET_TRY(launch_colsum(dA, 0, nullptr, 0, nullptr, 0, M, d, 1.f, G.dbp, st));
-  if (G.dE_img) {
+  }
+  if (G.dE_img && !one_pass) {
     for (int i = 0; i < D.n_img; ++i) {
       if (img_ids == nullptr && i > 0) break;  // default ids are all 0
       VLPET_TRY(launch_colsum(dout, bf, nullptr, 0, img_ids, i, M, d, 1.f, G.dE_img + (size_t)i * d, st));
