@@ -197,6 +197,18 @@ VLPET_API int vlpet_layernorm_fwd(const void* x, const float* w, const float* b,
 VLPET_API int vlpet_layernorm_bwd(const void* x, const void* dy, const float* w, const float* mean, const float* rstd, void* dx,
                         float* dw, float* db, int64_t M, int32_t d, int32_t dtype, void* stream);
 
+/* y = LayerNorm(res + dropout_p(h)) in one pass: the post-LN residual step of the frozen decoder blocks -- `F.dropout` ->
+ * `residual +` -> `LayerNorm` (my_transformers/modeling_bart.py:1663-1665, 1683-1685, 1697-1699), three kernels per sublayer in
+ * the reference.  bf16 activations, fp32 affine parameters and statistics; xs receives res + dropout(h) (bf16, rounded as the
+ * unfused sequence stores it) for the backward; the mask is the counter-based stream (seed + *seed_dev), regenerated by the
+ * backward: dres = LayerNorm backward, dh = dres * mask / (1 - p); dw / db accumulated into (NULL: frozen LayerNorm).      */
+VLPET_API int vlpet_dropout_add_layernorm_fwd(const void* h, const void* res, const float* w, const float* b, void* y, void* xs,
+                        float* mean, float* rstd, int64_t M, int32_t d, float eps, float p_drop, uint64_t seed,
+                        const uint64_t* seed_dev, void* stream);
+VLPET_API int vlpet_dropout_add_layernorm_bwd(const void* xs, const void* dy, const float* w, const float* mean, const float* rstd,
+                        void* dres, void* dh, float* dw, float* db, int64_t M, int32_t d, float p_drop, uint64_t seed,
+                        const uint64_t* seed_dev, void* stream);
+
 /* ---- FFN activation of the frozen blocks around the PET sites ---------------------------
  * y = dropout_p(gelu(x)) in one pass and its backward dx = dy * mask/(1-p) * gelu'(x) in one pass, replacing the
  * reference's `activation_fn(fc1(h))` + `F.dropout(.., p=activation_dropout)` pair (my_transformers/modeling_bart.py:

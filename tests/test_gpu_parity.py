@@ -771,6 +771,62 @@ def test_layernorm_kernels_match_fp64(V, M, d):
     assert rel(f(tb.grad), dyr.sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("M,d,train", [(700, 768, False), (4500, 768, True), (33, 256, True)])
+def test_dropout_add_layernorm_kernels(V, M, d, train):
+    """vlpet_dropout_add_layernorm_fwd / _bwd: LayerNorm(res + dropout(h)) of the frozen decoder blocks
+    (my_transformers/modeling_bart.py:1663-1665) in one pass each way.  Eval: equals the unfused sequence (bf16 add, then the
+    LayerNorm kernels' fp64 reference).  Training: the forward's mask is recovered from xs - res, the kept fraction is 1-p,
+    and the backward returns dres = LayerNorm backward and dh = dres * mask / (1-p) with the SAME mask."""
+    import vlpet_b200.functional as F_
+    rng = np.random.default_rng(M + d)
+    h, res, dy = rng.standard_normal((M, d)), rng.standard_normal((M, d)) * 1.5 + 0.3, rng.standard_normal((M, d))
+    w, b = 1 + 0.1 * rng.standard_normal(d), 0.1 * rng.standard_normal(d)
+    bf = torch.bfloat16
+    th, tr = dev(h, bf).requires_grad_(), dev(res, bf).requires_grad_()
+    tw, tb = dev(w, torch.float32).requires_grad_(), dev(b, torch.float32).requires_grad_()
+    p = 0.1
+    y = F_.dropout_add_layer_norm(th, tr, tw, tb, 1e-5, p, train)
+    y.backward(dev(dy, bf))
+    torch.cuda.synchronize()
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    hr, rr, dyr = bf16_round(h), bf16_round(res), bf16_round(dy)
+    wr, br = f(tw), f(tb)
+    dh_k, dres_k = f(th.grad), f(tr.grad)
+    if train:
+        # mask from the backward: dh = dres * m with m in {0, 1/(1-p)}; rows where dres is tiny are skipped
+        big = np.abs(dres_k) > 1e-2
+        ratio = dh_k[big] / dres_k[big]
+        kept = ratio > 0.5
+        assert abs(kept.mean() - (1 - p)) < 0.01
+        assert np.all(np.abs(ratio[kept] - 1 / (1 - p)) < 0.02) and np.all(ratio[~kept] == 0)
+        m = np.where(dh_k != 0, 1 / (1 - p), 0.0)
+        m[~big] = np.where(np.abs(dh_k[~big]) > 0, 1 / (1 - p), 0.0)        # best effort on the tiny entries (not asserted below)
+    else:
+        m = np.ones_like(hr)
+    x = bf16_round(rr + bf16_round(hr * m)) if not train else None
+    if not train:
+        mu = x.mean(1, keepdims=True)
+        rs = 1.0 / np.sqrt(((x - mu) ** 2).mean(1, keepdims=True) + 1e-5)
+        xh = (x - mu) * rs
+        bf16_check(f(y), xh * wr + br, TOL_BF16)
+        g = dyr * wr
+        dx = rs * (g - g.mean(1, keepdims=True) - xh * (g * xh).mean(1, keepdims=True))
+        bf16_check(dres_k, dx, TOL_BF16)
+        assert np.array_equal(dh_k, dres_k)                          # p = 0: dh is dres
+        assert rel(f(tw.grad), (dyr * xh).sum(0)) < 1e-5 and rel(f(tb.grad), dyr.sum(0)) < 1e-5
+    else:
+        # forward / backward mask agreement: with the backward's mask the unfused forward reproduces y
+        big_h = np.abs(hr) > 5e-2
+        xs = rr + hr * np.where(dh_k != 0, 1 / (1 - p), 0.0)
+        mu = xs.mean(1, keepdims=True)
+        rs = 1.0 / np.sqrt(((xs - mu) ** 2).mean(1, keepdims=True) + 1e-5)
+        ref_y = (xs - mu) * rs * wr + br
+        ok_rows = (np.abs(dres_k) > 1e-2).mean(1) > 0.97               # rows whose mask was fully recovered
+        assert ok_rows.mean() > 0.5
+        assert rel(f(y)[ok_rows], ref_y[ok_rows]) < 2e-2               # a wrong mask would give O(1) errors
+        assert big_h.any()
+
+
 def test_gelu_dropout_kernels(V):
     """Fused FFN activation: p = 0 equals F.gelu (exact erf form) forward and backward within bf16 rounding; p > 0 keeps
     1-p of the elements scaled by 1/(1-p), and the backward regenerates the forward's mask."""

@@ -117,6 +117,10 @@ SYMBOLS = {
     "vlpet_wgrad_bf16": (C.c_int, [C.POINTER(WgradPair), C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp]),
     "vlpet_layernorm_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_int32, _vp]),
     "vlpet_layernorm_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp]),
+    "vlpet_dropout_add_layernorm_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float,
+                                                  C.c_uint64, _vp, _vp]),
+    "vlpet_dropout_add_layernorm_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_float,
+                                                  C.c_uint64, _vp, _vp]),
     "vlpet_gelu_dropout_fwd": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, C.c_uint64, _vp, _vp]),
     "vlpet_gelu_dropout_bwd": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_float, C.c_uint64, _vp, _vp]),
     "vlpet_attn_fwd": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -183,6 +183,26 @@ int vlpet_layernorm_bwd(const void* x, const void* dy, const float* w, const flo
   return layernorm_bwd(x, dy, w, mean, rstd, dx, dw, db, M, d, static_cast<cudaStream_t>(stream));
 }
 
+int vlpet_dropout_add_layernorm_fwd(const void* h, const void* res, const float* w, const float* b, void* y, void* xs, float* mean,
+                                    float* rstd, int64_t M, int32_t d, float eps, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                                    void* stream) {
+  if (!h || !res || !w || !b || !y || !xs || !mean || !rstd || M <= 0) return fail(VLPET_E_BADARG, "dropout_add_layernorm_fwd: bad arguments");
+  if (!(p_drop >= 0.f && p_drop < 1.f)) return fail(VLPET_E_BADARG, "dropout_add_layernorm_fwd: p_drop must be in [0,1)");
+  if (!layernorm_supported(d, VLPET_BF16)) return fail(VLPET_E_UNSUPPORTED, "dropout_add_layernorm_fwd: needs d %% 256 == 0, d <= 1024 (d=%d)", d);
+  if (!aligned16(h) || !aligned16(res) || !aligned16(y) || !aligned16(xs) || !aligned16(w) || !aligned16(b))
+    return fail(VLPET_E_ALIGN, "dropout_add_layernorm_fwd: misaligned");
+  return dropout_add_layernorm_fwd(h, res, w, b, y, xs, mean, rstd, M, d, eps, p_drop, seed, seed_dev, static_cast<cudaStream_t>(stream));
+}
+int vlpet_dropout_add_layernorm_bwd(const void* xs, const void* dy, const float* w, const float* mean, const float* rstd, void* dres,
+                                    void* dh, float* dw, float* db, int64_t M, int32_t d, float p_drop, uint64_t seed,
+                                    const uint64_t* seed_dev, void* stream) {
+  if (!xs || !dy || !w || !mean || !rstd || !dres || !dh || M <= 0) return fail(VLPET_E_BADARG, "dropout_add_layernorm_bwd: bad arguments");
+  if (!layernorm_supported(d, VLPET_BF16)) return fail(VLPET_E_UNSUPPORTED, "dropout_add_layernorm_bwd: needs d %% 256 == 0, d <= 1024 (d=%d)", d);
+  if (!aligned16(xs) || !aligned16(dy) || !aligned16(dres) || !aligned16(dh) || !aligned16(w))
+    return fail(VLPET_E_ALIGN, "dropout_add_layernorm_bwd: misaligned");
+  return dropout_add_layernorm_bwd(xs, dy, w, mean, rstd, dres, dh, dw, db, M, d, p_drop, seed, seed_dev, static_cast<cudaStream_t>(stream));
+}
+
 // developer hook: a kernel that waits on a barrier nobody completes -- proves that the trap record reaches the host
 namespace vlpet {
 __global__ void selftest_trap_kernel(uint32_t* dbg) {

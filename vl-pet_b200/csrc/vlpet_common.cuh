@@ -253,6 +253,12 @@ int layernorm_fwd(const void* x, const float* w, const float* b, void* y, float*
                   float eps, cudaStream_t st);
 int layernorm_bwd(const void* x, const void* dy, const float* w, const float* mean, const float* rstd, void* dx, float* dw,
                   float* db, int64_t M, int d, cudaStream_t st);
+int dropout_add_layernorm_fwd(const void* h, const void* res, const float* w, const float* b, void* y, void* xs, float* mean,
+                              float* rstd, int64_t M, int d, float eps, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                              cudaStream_t st);
+int dropout_add_layernorm_bwd(const void* xs, const void* dy, const float* w, const float* mean, const float* rstd, void* dres, void* dh,
+                              float* dw, float* db, int64_t M, int d, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                              cudaStream_t st);
 // short-sequence attention, vlpet_attention.cu
 int attn_run(bool bwd, const void* q, const void* k, const void* v, int64_t q_rs, int64_t k_rs, int64_t v_rs, void* out, float* lse,
              const void* o, const void* dout, void* dq, void* dk, void* dv, int64_t dq_rs, int64_t dk_rs, int64_t dv_rs, int B, int H,

@@ -560,6 +560,63 @@ def layer_norm(x, weight, bias, eps: float = 1e-5):
     return LayerNormFn.apply(x, weight, bias, eps)
 
 
+class DropoutAddLayerNormFn(torch.autograd.Function):
+    """LayerNorm(res + dropout_p(h)) in one pass each way (include/vlpet.h vlpet_dropout_add_layernorm_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, h, res, weight, bias, eps: float, p: float, seed: int):
+        _require_cuda(h, res, weight, bias)
+        d = h.shape[-1]
+        hc, rc = h.contiguous(), res.contiguous()
+        M = hc.numel() // d
+        w32 = weight.detach() if weight.dtype == torch.float32 else weight.detach().float()
+        b32 = bias.detach() if bias.dtype == torch.float32 else bias.detach().float()
+        y, xs = torch.empty_like(hc), torch.empty_like(hc)
+        stats = torch.empty(2, M, dtype=torch.float32, device=h.device)
+        sd = _seed_dev.data_ptr() if (seed and _seed_dev is not None) else None
+        pd = float(p if seed else 0.0)
+        L.check(_call("ln_fwd", 4 * hc.numel() * 2, L.lib.vlpet_dropout_add_layernorm_fwd, _p(hc), _p(rc), _p(w32.contiguous()),
+                      _p(b32.contiguous()), _p(y), _p(xs), _p(stats[0]), _p(stats[1]), M, d, float(eps), pd, seed,
+                      C.c_void_p(sd) if sd else C.c_void_p(0), _stream()), "vlpet_dropout_add_layernorm_fwd")
+        ctx.save_for_backward(xs, w32, stats)
+        ctx.args = (pd, seed, sd)
+        ctx.meta = (weight.dtype, bias.dtype)
+        ctx.param_refs = (weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, w32, stats = ctx.saved_tensors
+        pd, seed, sd = ctx.args
+        d = xs.shape[-1]
+        M = xs.numel() // d
+        dy = dy.contiguous()
+        if dy.dtype != xs.dtype:
+            dy = dy.to(xs.dtype)
+        dres, dh = torch.empty_like(xs), torch.empty_like(xs)
+        need_w, need_b = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        direct = _direct_targets(ctx.param_refs, [[0], [1]]) if (need_w and need_b) else None
+        gbuf = None
+        if direct is not None:
+            pw, pb = C.c_void_p(direct[0]), C.c_void_p(direct[1])
+        else:
+            gbuf = torch.zeros(2, d, dtype=torch.float32, device=xs.device) if (need_w or need_b) else None
+            pw = _p(gbuf[0]) if need_w else C.c_void_p(0)
+            pb = _p(gbuf[1]) if need_b else C.c_void_p(0)
+        L.check(_call("ln_bwd", 4 * xs.numel() * 2, L.lib.vlpet_dropout_add_layernorm_bwd, _p(xs), _p(dy), _p(w32.contiguous()),
+                      _p(stats[0]), _p(stats[1]), _p(dres), _p(dh), pw, pb, M, d, pd, seed, C.c_void_p(sd) if sd else C.c_void_p(0),
+                      _stream()), "vlpet_dropout_add_layernorm_bwd")
+        dw = gbuf[0].to(ctx.meta[0]) if (gbuf is not None and need_w) else None
+        db = gbuf[1].to(ctx.meta[1]) if (gbuf is not None and need_b) else None
+        return dh, dres, dw, db, None, None, None
+
+
+def dropout_add_layer_norm(h, res, weight, bias, eps: float, p: float, training: bool):
+    """LayerNorm(res + dropout(h, p)) of a post-LN residual step, one kernel forward and one backward (bf16 CUDA tensors)."""
+    seed = next_dropout_seed() if (training and p > 0.0) else 0
+    return DropoutAddLayerNormFn.apply(h, res, weight, bias, eps, p, seed)
+
+
 def layer_norm_supported(x: torch.Tensor) -> bool:
     d = x.shape[-1]
     return x.is_cuda and x.dtype == torch.bfloat16 and d % 256 == 0 and 256 <= d <= 1024

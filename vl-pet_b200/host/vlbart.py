@@ -49,6 +49,14 @@ def _ln(ln: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
     return F.layer_norm(x, ln.normalized_shape, w, b, ln.eps)
 
 
+def _drop_add_ln(ln: nn.LayerNorm, res: torch.Tensor, h: torch.Tensor, p: float, training: bool) -> torch.Tensor:
+    """LayerNorm(res + dropout(h)): the post-LN residual step (my_transformers/modeling_bart.py:1663-1665 etc.).  On the GPU in
+    bf16 one kernel each way (vlpet_dropout_add_layernorm_fwd / _bwd) instead of dropout, add and LayerNorm."""
+    if h.is_cuda and h.dtype == torch.bfloat16 and res.dtype == torch.bfloat16 and F_.layer_norm_supported(h):
+        return F_.dropout_add_layer_norm(h, res, ln.weight, ln.bias, ln.eps, p, training)
+    return _ln(ln, res + F.dropout(h, p=p, training=training))
+
+
 def shift_tokens_right(input_ids: torch.Tensor, pad_token_id: int, decoder_start_token_id: int) -> torch.Tensor:
     """Decoder inputs from labels (my_transformers/modeling_bart.py:63-77): shift right, start token first,
     -100 -> pad."""
@@ -260,13 +268,12 @@ class BartDecoderLayer(nn.Module):
         self.final_layer_norm = nn.LayerNorm(d)
 
     def forward(self, hidden_states, encoder_hidden_states, self_mask=None, cross_mask=None, task=None):
-        drop = lambda t: F.dropout(t, p=self.dropout, training=self.training)  # noqa: E731
         h = self.self_attn(hidden_states, attn_mask=self_mask, is_causal=self_mask is None)
-        hidden_states = _ln(self.self_attn_layer_norm, hidden_states + drop(h))
+        hidden_states = _drop_add_ln(self.self_attn_layer_norm, hidden_states, h, self.dropout, self.training)
         h = self.encoder_attn(hidden_states, key_value_states=encoder_hidden_states, attn_mask=cross_mask, task=task)
-        hidden_states = _ln(self.encoder_attn_layer_norm, hidden_states + drop(h))
+        hidden_states = _drop_add_ln(self.encoder_attn_layer_norm, hidden_states, h, self.dropout, self.training)
         h = self.fc2(_ffn_act(self, self.fc1(hidden_states)))
-        return _ln(self.final_layer_norm, hidden_states + drop(h))
+        return _drop_add_ln(self.final_layer_norm, hidden_states, h, self.dropout, self.training)
 
     @torch.no_grad()
     def step(self, hidden_states, cross, self_past=None, cross_mask=None):
