@@ -113,7 +113,7 @@ class BartAttention(nn.Module):
         B, L, _ = t.shape
         return t.view(B, L, self.num_heads, self.head_dim).transpose(1, 2)
 
-    def forward(self, hidden_states, key_value_states=None, attn_mask=None, is_causal=False, task=None):
+    def forward(self, hidden_states, key_value_states=None, attn_mask=None, is_causal=False, task=None, k_override=None):
         src = hidden_states if key_value_states is None else key_value_states
         fused = self._fused_qkv() if key_value_states is None else None
         B, L, _ = hidden_states.shape
@@ -125,7 +125,7 @@ class BartAttention(nn.Module):
             q, k, v = qkv.unbind(2)
         else:
             q = self.q_proj(hidden_states)
-            k = self.k_proj(src)
+            k = k_override if k_override is not None else self.k_proj(src)      # (cross-attention keys of all layers: BartDecoder._cross_keys)
             v = self.v_proj(src)
             if key_value_states is not None and self.attn_value_parallel_adapter is not None:
                 v = self.attn_value_parallel_adapter(key_value_states, task, y=v)          # K2
@@ -267,10 +267,10 @@ class BartDecoderLayer(nn.Module):
         self.fc2 = nn.Linear(config.decoder_ffn_dim, d)
         self.final_layer_norm = nn.LayerNorm(d)
 
-    def forward(self, hidden_states, encoder_hidden_states, self_mask=None, cross_mask=None, task=None):
+    def forward(self, hidden_states, encoder_hidden_states, self_mask=None, cross_mask=None, task=None, cross_k=None):
         h = self.self_attn(hidden_states, attn_mask=self_mask, is_causal=self_mask is None)
         hidden_states = _drop_add_ln(self.self_attn_layer_norm, hidden_states, h, self.dropout, self.training)
-        h = self.encoder_attn(hidden_states, key_value_states=encoder_hidden_states, attn_mask=cross_mask, task=task)
+        h = self.encoder_attn(hidden_states, key_value_states=encoder_hidden_states, attn_mask=cross_mask, task=task, k_override=cross_k)
         hidden_states = _drop_add_ln(self.encoder_attn_layer_norm, hidden_states, h, self.dropout, self.training)
         h = self.fc2(_ffn_act(self, self.fc1(hidden_states)))
         return _drop_add_ln(self.final_layer_norm, hidden_states, h, self.dropout, self.training)
@@ -391,6 +391,25 @@ class BartDecoder(nn.Module):
         self.embed_positions = BartLearnedPositionalEmbedding(config.max_position_embeddings, d, config.pad_token_id)
         self.layers = nn.ModuleList([BartDecoderLayer(config) for _ in range(config.decoder_layers)])
         self.layernorm_embedding = nn.LayerNorm(d)
+        self._kcat = None          # (key, [layers * d, d] weight, [layers * d] bias): see _cross_keys
+
+    def _cross_keys(self, encoder_hidden_states):
+        """Cross-attention keys of ALL decoder layers in one GEMM over the row-concatenated (frozen) k_proj weights: every layer
+        projects the same encoder output, so 6 GEMMs forward and 6 dgrad GEMMs + 5 gradient-accumulation passes over
+        [tokens, d] backward become one GEMM each way (+ one stack of the per-layer key gradients).  The state-dict keeps the
+        reference's per-layer Linears; the concatenation is a cached copy."""
+        ks = [layer.encoder_attn.k_proj for layer in self.layers]
+        if any(k.weight.requires_grad or k.bias.requires_grad for k in ks):
+            return None
+        key = tuple((k.weight.data_ptr(), k.weight._version, k.weight.dtype, k.bias._version) for k in ks)
+        if self._kcat is None or self._kcat[0] != key:
+            self._kcat = (key, torch.cat([k.weight.detach() for k in ks], 0).contiguous(),
+                          torch.cat([k.bias.detach() for k in ks], 0).contiguous())
+        w, b = self._kcat[1], self._kcat[2]
+        if w.dtype != encoder_hidden_states.dtype and not torch.is_autocast_enabled():
+            return None
+        B, S, d = encoder_hidden_states.shape
+        return F.linear(encoder_hidden_states, w, b).view(B, S, len(ks), d).unbind(2)
 
     def forward(self, input_ids, encoder_hidden_states, encoder_mask=None, task=None):
         B, T = input_ids.shape
@@ -398,8 +417,9 @@ class BartDecoder(nn.Module):
         x = _ln(self.layernorm_embedding, x)
         x = F.dropout(x, p=self.dropout, training=self.training)
         cross = _pad_mask(encoder_mask, x.dtype, T)
-        for layer in self.layers:
-            x = layer(x, encoder_hidden_states, self_mask=None, cross_mask=cross, task=task)
+        keys = self._cross_keys(encoder_hidden_states)
+        for i, layer in enumerate(self.layers):
+            x = layer(x, encoder_hidden_states, self_mask=None, cross_mask=cross, task=task, cross_k=keys[i] if keys is not None else None)
         return x
 
 
