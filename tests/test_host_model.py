@@ -83,6 +83,43 @@ def test_host_model_matches_reference_vlbart_cpu(H, gate):
             assert rel(params[n].grad.numpy(), z[f"{task}/grad/{n}"]) < 1e-9, (task, n)
 
 
+def _freeze_backbone(H, model):
+    """What PetTrainer does before a step (trainer_base.py:268-270, 308-542): only the PET parameters stay trainable.  The
+    host models fuse frozen projections (q/k/v of a self-attention, the cross-attention keys of all decoder layers) only then."""
+    names = set(H.trainable_names(model, model.config))
+    for n, p in model.named_parameters():
+        p.requires_grad_(n in names)
+
+
+@pytest.mark.parametrize("arch", ["bart", "t5"])
+def test_frozen_backbone_fusions_match_reference_cpu(H, arch):
+    """With the backbone frozen the host models run their fused projections (one GEMM for q/k/v of a frozen self-attention,
+    one GEMM for the cross-attention keys of all decoder layers): loss and every trainable gradient still equal the
+    reference's (the goldens of make_golden_vlbart.py / make_golden_vlt5.py)."""
+    from oracle.eager_ref import use_eager_pet
+    if arch == "bart":
+        z = _load("large")
+        model = use_eager_pet(H.VLBart(_cfg(H, "large")).double().eval())
+        tl, tg = 1e-10, 1e-9
+    else:
+        z = _load_t5()
+        model = use_eager_pet(H.VLT5(_t5_cfg(H)).double().eval())
+        tl, tg = 1e-7, 2e-6
+    _load_state(model, z, torch.float64)
+    _freeze_backbone(H, model)
+    dec = model.model.decoder if arch == "bart" else model.decoder
+    names = [str(n) for n in z["meta_trainable"]]
+    params = dict(model.named_parameters())
+    for task in ("vqa", "nlvr"):
+        model.zero_grad()
+        loss = model.train_step(_batch(z, task, torch.float64))["loss"]
+        loss.backward()
+        assert dec._kcat is not None, "the batched cross-attention key projection did not run"
+        assert abs(loss.item() - float(z[f"{task}/loss"])) < tl
+        for n in names:
+            assert rel(params[n].grad.numpy(), z[f"{task}/grad/{n}"]) < tg, (task, n)
+
+
 def _generate_case(H, dtype, device, eager, arch="bart"):
     z = np.load(os.path.join(GOLDEN, f"vl{arch}_tiny_generate.npz"), allow_pickle=False)
     model = H.VLBart(_cfg(H, "large")) if arch == "bart" else H.VLT5(H.tiny_t5_test_config(dropout_rate=0.0, dropout=0.0))

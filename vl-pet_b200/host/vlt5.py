@@ -59,6 +59,7 @@ class T5Attention(nn.Module):
         if has_relative_attention_bias:
             self.relative_attention_bias = nn.Embedding(self.num_buckets, self.n_heads)
         self.attn_value_parallel_adapter = AdapterController(config.vpa_adapter_config()) if value_adapter else None
+        self._qkv = None      # (key, [3 * inner, d] weight): fused projection of a frozen self-attention, see _fused_qkv
 
     def compute_bias(self, q_len: int, k_len: int) -> torch.Tensor:
         dev = self.relative_attention_bias.weight.device
@@ -67,10 +68,26 @@ class T5Attention(nn.Module):
         bucket = relative_position_bucket(mem - ctx, bidirectional=not self.is_decoder, num_buckets=self.num_buckets)
         return self.relative_attention_bias(bucket).permute(2, 0, 1).unsqueeze(0)      # [1, H, q, k]
 
-    def forward(self, hidden_states, key_value_states=None, bias=None, task=None):
+    def _fused_qkv(self, dtype):
+        """Frozen self-attention: q, k, v out of ONE GEMM over the row-concatenated weights (a cached copy; the state-dict
+        keeps the reference's three Linears) -- and one dgrad GEMM + one stack instead of three + two accumulation passes."""
+        ws = (self.q.weight, self.k.weight, self.v.weight)
+        if any(t.requires_grad for t in ws):
+            return None
+        key = tuple((t.data_ptr(), t._version, t.dtype) for t in ws)
+        if self._qkv is None or self._qkv[0] != key:
+            self._qkv = (key, torch.cat([t.detach() for t in ws], 0).contiguous())
+        w = self._qkv[1]
+        return w if (w.dtype == dtype or torch.is_autocast_enabled()) else None
+
+    def forward(self, hidden_states, key_value_states=None, bias=None, task=None, k_override=None):
         B, L, _ = hidden_states.shape
         src = hidden_states if key_value_states is None else key_value_states
-        q, k, v = self.q(hidden_states), self.k(src), self.v(src)
+        wqkv = self._fused_qkv(hidden_states.dtype) if key_value_states is None else None
+        if wqkv is not None:
+            q, k, v = F.linear(hidden_states, wqkv).view(B, L, 3, self.inner_dim).unbind(2)
+        else:
+            q, k, v = self.q(hidden_states), (k_override if k_override is not None else self.k(src)), self.v(src)
         if key_value_states is not None and self.attn_value_parallel_adapter is not None:
             v = self.attn_value_parallel_adapter(key_value_states, task, y=v)                  # K2
         sh = lambda t: t.view(B, -1, self.n_heads, self.d_kv).transpose(1, 2)  # noqa: E731
@@ -167,8 +184,9 @@ class T5LayerCrossAttention(nn.Module):
         self.layer_norm = T5LayerNorm(config.d_model, eps=config.layer_norm_epsilon)
         self.dropout = config.dropout_rate
 
-    def forward(self, hidden_states, encoder_hidden_states, bias=None, task=None):
-        a = self.EncDecAttention(_rms(self.layer_norm, hidden_states), key_value_states=encoder_hidden_states, bias=bias, task=task)
+    def forward(self, hidden_states, encoder_hidden_states, bias=None, task=None, cross_k=None):
+        a = self.EncDecAttention(_rms(self.layer_norm, hidden_states), key_value_states=encoder_hidden_states, bias=bias, task=task,
+                                 k_override=cross_k)
         return hidden_states + F.dropout(a, p=self.dropout, training=self.training)
 
 
@@ -210,10 +228,10 @@ class T5Block(nn.Module):
         layers.append(T5LayerFF(config, is_decoder))
         self.layer = nn.ModuleList(layers)
 
-    def forward(self, hidden_states, bias=None, encoder_hidden_states=None, cross_bias=None, task=None):
+    def forward(self, hidden_states, bias=None, encoder_hidden_states=None, cross_bias=None, task=None, cross_k=None):
         hidden_states = self.layer[0](hidden_states, bias=bias)
         if self.is_decoder:
-            hidden_states = self.layer[1](hidden_states, encoder_hidden_states, bias=cross_bias, task=task)
+            hidden_states = self.layer[1](hidden_states, encoder_hidden_states, bias=cross_bias, task=task, cross_k=cross_k)
         return self.layer[-1](hidden_states)
 
 
@@ -289,6 +307,23 @@ class T5DecoderStack(nn.Module):
         self.block = nn.ModuleList([T5Block(config, True, i == 0) for i in range(config.num_decoder_layers)])
         self.final_layer_norm = T5LayerNorm(config.d_model, eps=config.layer_norm_epsilon)
         self.dropout = config.dropout_rate
+        self._kcat = None          # (key, [layers * inner, d] weight): see _cross_keys
+
+    def _cross_keys(self, encoder_hidden_states):
+        """Cross-attention keys of ALL decoder blocks in one GEMM over the row-concatenated frozen k weights (every block
+        projects the same encoder output): 12 GEMMs forward, 12 dgrad GEMMs + 11 accumulation passes over [tokens, d] backward
+        become one GEMM each way + one stack (T5 twin of host.vlbart.BartDecoder._cross_keys)."""
+        ks = [blk.layer[1].EncDecAttention.k for blk in self.block]
+        if any(k.weight.requires_grad for k in ks):
+            return None
+        key = tuple((k.weight.data_ptr(), k.weight._version, k.weight.dtype) for k in ks)
+        if self._kcat is None or self._kcat[0] != key:
+            self._kcat = (key, torch.cat([k.weight.detach() for k in ks], 0).contiguous())
+        w = self._kcat[1]
+        if w.dtype != encoder_hidden_states.dtype and not torch.is_autocast_enabled():
+            return None
+        B, S, _ = encoder_hidden_states.shape
+        return F.linear(encoder_hidden_states, w).view(B, S, len(ks), -1).unbind(2)
 
     def forward(self, input_ids, encoder_hidden_states, encoder_mask=None, task=None):
         B, T = input_ids.shape
@@ -299,8 +334,10 @@ class T5DecoderStack(nn.Module):
         cross = None
         if encoder_mask is not None:
             cross = ((1.0 - encoder_mask[:, None, None, :].float()) * -1e9).to(x.dtype).expand(B, 1, T, -1)
-        for blk in self.block:
-            x = blk(x, bias=bias, encoder_hidden_states=encoder_hidden_states, cross_bias=cross, task=task)
+        keys = self._cross_keys(encoder_hidden_states)
+        for i, blk in enumerate(self.block):
+            x = blk(x, bias=bias, encoder_hidden_states=encoder_hidden_states, cross_bias=cross, task=task,
+                    cross_k=keys[i] if keys is not None else None)
         x = _rms(self.final_layer_norm, x)
         return F.dropout(x, p=self.dropout, training=self.training)
 
