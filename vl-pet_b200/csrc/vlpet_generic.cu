@@ -2,9 +2,10 @@
 //
 // This is the correctness-first path (fp32 accumulate everywhere, exact tanhf/expf) that serves
 //   * the fp32 configuration (BASELINE config 1; 1e-5 parity bar, which rules out bf16/tf32 tensor cores),
-//   * shapes the fused tcgen05 kernel does not cover (r not a multiple of 16, r < 16: BASELINE config 4,
-//     the middle / small granularities), and
-//   * the on-device cross-check of the fused kernels in tests.
+//   * shapes none of the bf16 paths covers (d not a multiple of 128 / 256, ranks above 192; under VLPET_IMPL_AUTO everything
+//     else runs the tcgen05 kernels, the row-wise kernels of vlpet_rows.cu or the rank halves of vlpet_wide.cu), and
+//   * the on-device cross-check of the fused kernels in tests (VLPET_IMPL_GENERIC).
+// K3 (visual projection) keeps its row kernel and the one-pass reductions of its backward here; its GEMMs are tcgen05.
 // It runs the op sequence of SURVEY Appendix A as a handful of launches over fp32 workspace intermediates:
 // one strided tile GEMM (fp32 accumulate, fused bias / gelu_new / residual epilogue, split-K for the
 // token-contracted weight gradients) plus small row-wise kernels for the gates.
