@@ -3,6 +3,7 @@ graph).  Every function requires CUDA tensors and raises otherwise -- there is n
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -80,7 +81,20 @@ def profile_summary(records):
     return out
 
 
+_NVTX = os.environ.get("VLPET_NVTX", "0") not in ("", "0")     # NVTX ranges around every C-ABI compute call (ncu --nvtx filters on them)
+
+
 def _call(name: str, nbytes: int, fn, *args):
+    if _NVTX:
+        torch.cuda.nvtx.range_push("vlpet." + name)
+        try:
+            return _call_inner(name, nbytes, fn, *args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return _call_inner(name, nbytes, fn, *args)
+
+
+def _call_inner(name: str, nbytes: int, fn, *args):
     if _prof is None:
         return fn(*args)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
