@@ -152,9 +152,69 @@ def test_generate_matches_reference_cached_decode_cpu(H):
         h = model.model(ids, vis, tokens[:, :-1], task="vqa")
         full = model._logits(h)
     assert rel(full.numpy(), logits.numpy()) < 1e-9
-    with pytest.raises(NotImplementedError):
-        model.generate(ids, vis, task="vqa", num_beams=5)
     assert model.test_step({"task": "vqa", "input_ids": ids, "vis_feats": vis[0], "boxes": vis[1]}, max_length=4, min_length=4)["token_ids"].shape == (3, 4)
+
+
+@pytest.mark.parametrize("arch", ["bart", "t5"])
+def test_beam_search_over_the_cached_step_cpu(H, arch):
+    """host/generation.py (the caption task's generate(num_beams=5)): (1) one beam is greedy decoding; (2) on a vocabulary
+    restricted to 3 tokens and 4 generated positions, num_beams = 27 is exhaustive, so its result must be the sequence an
+    enumeration of all 81 continuations scores highest under a full teacher-forced pass; (3) the sum of log-probabilities the
+    search reports for a 4-beam run equals a teacher-forced re-scoring of its output -- the self-attention caches followed the
+    beam re-ordering."""
+    z, model, ids, vis, proc = _generate_case(H, torch.float64, "cpu", eager=True, arch=arch)
+    L, mn = int(z["meta_max_length"]), int(z["meta_min_length"])
+    eos = model.config.eos_token_id
+
+    def full_logp(tokens):                                   # log-probabilities of tokens[:, 1:] under one teacher-forced pass
+        B = tokens.shape[0]
+        rep = torch.arange(ids.shape[0]).repeat_interleave(B // ids.shape[0])
+        with torch.no_grad():
+            if arch == "bart":
+                h = model.model(ids[rep], tuple(v[rep] for v in vis), tokens[:, :-1], task="vqa")
+                lg = model._logits(h)
+            else:
+                enc, mask = model.encoder(ids[rep], tuple(v[rep] for v in vis), task="vqa")
+                lg = model.lm_head(model.decoder(tokens[:, :-1], enc, encoder_mask=mask, task="vqa") * (model.model_dim ** -0.5))
+        return torch.log_softmax(lg.double(), -1)
+
+    # (1) one beam == greedy (the processor adds the same bias to logits and to log-probabilities: argmax unchanged)
+    greedy = model.generate(ids, vis, task="vqa", max_length=L, min_length=L, logits_processor=proc)
+    one = model.generate(ids, vis, task="vqa", max_length=L, min_length=L, num_beams=1, logits_processor=proc)
+    beam1 = model.generate(ids[:1], (vis[0][:1], vis[1][:1]), task="vqa", max_length=L, min_length=L, num_beams=2,
+                           logits_processor=lambda s_, t_, sc: sc, length_penalty=1.0)
+    assert greedy.tolist() == one.tolist() and beam1.shape == (1, L)
+    # (2) exhaustive on 3 allowed tokens, 4 generated positions
+    allowed = torch.tensor([5, 17, 123])
+    Lx = 5
+
+    def restrict(step, tokens, scores):
+        m = torch.full_like(scores, -float("inf"))
+        m[:, allowed] = 0.0
+        return scores + m
+
+    out, rep_scores = model.generate(ids, vis, task="vqa", max_length=Lx, min_length=Lx, num_beams=27, logits_processor=restrict,
+                                     return_scores=True)
+    import itertools
+    cont = torch.tensor(list(itertools.product(allowed.tolist(), repeat=Lx - 1)))            # [81, 4]
+    B = ids.shape[0]
+    start = torch.full((cont.shape[0], 1), model.config.decoder_start_token_id, dtype=torch.long)
+    seqs = torch.cat([start, cont], 1).repeat(B, 1)                                          # sample-major
+    lp = full_logp(seqs)            # (the processor masks log-probabilities, as in HF: allowed tokens keep their full-vocabulary values)
+    tot = lp.gather(-1, seqs[:, 1:, None]).squeeze(-1).sum(-1).view(B, -1)
+    best = tot.argmax(-1)
+    for b in range(B):
+        assert out[b].tolist() == seqs[b * cont.shape[0] + int(best[b])].tolist(), b
+        assert abs(float(rep_scores[b]) - float(tot[b, best[b]])) < 1e-6 * max(1.0, abs(float(tot[b, best[b]])))
+    # (3) reported score == teacher-forced re-scoring (4 beams, full vocabulary, EOS suppressed so all hypotheses have length L)
+    out4, sc4 = model.generate(ids, vis, task="vqa", max_length=L, min_length=L, num_beams=4, return_scores=True)
+    lp4 = full_logp(out4)
+    lp4[..., eos] = -float("inf")                                                             # (what min_length did at every step)
+    re = lp4.gather(-1, out4[:, 1:, None]).squeeze(-1).sum(-1)
+    assert torch.allclose(re, sc4, rtol=1e-6, atol=1e-6), (re, sc4)
+    g = model.generate(ids, vis, task="vqa", max_length=L, min_length=L)                      # plain greedy, no processor
+    lpg = full_logp(g)
+    assert bool((sc4 >= lpg.gather(-1, g[:, 1:, None]).squeeze(-1).sum(-1) - 1e-9).all())     # 4 beams found at least the greedy path here
 
 
 @pytest.mark.gpu
@@ -304,8 +364,6 @@ def test_t5_generate_matches_reference_cached_decode_cpu(H):
         h = model.decoder(tokens[:, :-1], enc, encoder_mask=mask, task="vqa")
         full = model.lm_head(h * (model.model_dim ** -0.5))
     assert rel(full.numpy(), logits.numpy()) < 1e-9
-    with pytest.raises(NotImplementedError):
-        model.generate(ids, vis, task="vqa", num_beams=5)
 
 
 @pytest.mark.gpu

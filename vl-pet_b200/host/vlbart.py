@@ -537,23 +537,38 @@ class VLBart(nn.Module):
 
     @torch.no_grad()
     def generate(self, input_ids, vis_inputs, task=None, max_length: int = 20, min_length: int = 0, num_beams: int = 1,
-                 logits_processor=None, attention_mask=None, vis_attention_mask=None, return_step_logits: bool = False):
+                 logits_processor=None, attention_mask=None, vis_attention_mask=None, return_step_logits: bool = False,
+                 length_penalty: float = 1.0, early_stopping: bool = False, return_scores: bool = False):
         """Greedy decoding with the KV cache of the reference's decode path (src/modeling_bart.py:1522-1602 with
         ``past_key_values``; what ``test_step`` -> ``generate(num_beams=1)`` runs for VQA / GQA / NLVR, multitask.py:480, 516):
         the encoder runs once, every decoder layer's cross-attention keys / values -- the values through the value parallel
         adapter (K2) -- are formed once, each step feeds ONE new position.  ``logits_processor(step, tokens, scores)`` is the
-        caller's hook (HF's logits processors); ``min_length`` masks EOS as HF's MinLengthLogitsProcessor does.  Beam search
-        (caption: --num_beams 5) is HF search machinery above this path and is not built: ``num_beams > 1`` raises."""
-        if num_beams != 1:
-            raise NotImplementedError("host.VLBart.generate: greedy decoding only (num_beams == 1); beam search is the caller's "
-                                      "search loop over the same cached step")
+        caller's hook (HF's logits processors); ``min_length`` masks EOS as HF's MinLengthLogitsProcessor does.
+        ``num_beams > 1`` (caption: --num_beams 5, multitask.py:587) runs host/generation.py's beam search over the same
+        cached step (the processor then sees log-probabilities, as in HF)."""
         cfg = self.config
         was_training = self.training
         self.eval()
         try:
             enc, mask = self.model.encoder(input_ids, vis_inputs, attention_mask, vis_attention_mask, task=task)
-            cache = self.model.decoder.init_cache(enc, mask, task=task)
             B = input_ids.shape[0]
+            if num_beams > 1:
+                # beam search (caption: --num_beams 5): every sample's encoder output is expanded to num_beams rows, as the
+                # reference's _expand_inputs_for_generation does; the self-attention caches follow the beams
+                from .generation import beam_search
+                rep = torch.arange(B, device=input_ids.device).repeat_interleave(num_beams)
+                cache = self.model.decoder.init_cache(enc.index_select(0, rep), mask.index_select(0, rep) if mask is not None else None, task=task)
+
+                def _step(new_tokens):
+                    h = self.model.decoder.step(new_tokens, cache)
+                    return self._logits(h[:, -1])
+
+                def _reorder(beam_idx):
+                    cache["self"] = [(k.index_select(0, beam_idx), v.index_select(0, beam_idx)) for k, v in cache["self"]]
+
+                return beam_search(_step, _reorder, B, num_beams, input_ids.device, cfg.decoder_start_token_id, cfg.pad_token_id,
+                                   cfg.eos_token_id, max_length, min_length, length_penalty, early_stopping, logits_processor, return_scores)
+            cache = self.model.decoder.init_cache(enc, mask, task=task)
             tokens = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=input_ids.device)
             done = torch.zeros(B, dtype=torch.bool, device=input_ids.device)
             steps = []

@@ -424,20 +424,35 @@ class VLT5(nn.Module):
 
     @torch.no_grad()
     def generate(self, input_ids, vis_inputs, task=None, max_length: int = 20, min_length: int = 0, num_beams: int = 1,
-                 logits_processor=None, attention_mask=None, vis_attention_mask=None, return_step_logits: bool = False):
+                 logits_processor=None, attention_mask=None, vis_attention_mask=None, return_step_logits: bool = False,
+                 length_penalty: float = 1.0, early_stopping: bool = False, return_scores: bool = False):
         """Greedy decoding through the KV cache (src/modeling_t5.py:560-690 with ``past_key_values``; T5 twin of
         host.VLBart.generate): encoder once, cross-attention heads -- values through the value parallel adapter (K2) -- once,
-        one new position per step.  ``num_beams > 1`` is the caller's search loop and raises."""
-        if num_beams != 1:
-            raise NotImplementedError("host.VLT5.generate: greedy decoding only (num_beams == 1)")
+        one new position per step.  ``num_beams > 1``: host/generation.py's beam search over the same cached step."""
         cfg = self.config
         eos = getattr(cfg, "eos_token_id", 1)
         was_training = self.training
         self.eval()
         try:
             enc, mask = self.encoder(input_ids, vis_inputs, attention_mask, vis_attention_mask, task=task)
-            cache = self.decoder.init_cache(enc, mask, task=task)
             B = input_ids.shape[0]
+            if num_beams > 1:
+                # beam search (caption: --num_beams 5): every sample's encoder output is expanded to num_beams rows, as the
+                # reference's _expand_inputs_for_generation does; the self-attention caches follow the beams
+                from .generation import beam_search
+                rep = torch.arange(B, device=input_ids.device).repeat_interleave(num_beams)
+                cache = self.decoder.init_cache(enc.index_select(0, rep), mask.index_select(0, rep) if mask is not None else None, task=task)
+
+                def _step(new_tokens):
+                    h = self.decoder.step(new_tokens, cache)
+                    return self.lm_head(h[:, -1] * (self.model_dim ** -0.5))
+
+                def _reorder(beam_idx):
+                    cache["self"] = [(k.index_select(0, beam_idx), v.index_select(0, beam_idx)) for k, v in cache["self"]]
+
+                return beam_search(_step, _reorder, B, num_beams, input_ids.device, cfg.decoder_start_token_id, cfg.pad_token_id,
+                                   eos, max_length, min_length, length_penalty, early_stopping, logits_processor, return_scores)
+            cache = self.decoder.init_cache(enc, mask, task=task)
             tokens = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=input_ids.device)
             done = torch.zeros(B, dtype=torch.bool, device=input_ids.device)
             steps = []
