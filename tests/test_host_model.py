@@ -217,6 +217,20 @@ def test_beam_search_over_the_cached_step_cpu(H, arch):
     assert bool((sc4 >= lpg.gather(-1, g[:, 1:, None]).squeeze(-1).sum(-1) - 1e-9).all())     # 4 beams found at least the greedy path here
 
 
+def test_no_repeat_ngram_processor():
+    """host.generation.NoRepeatNGram == HF's NoRepeatNGramLogitsProcessor semantics: a token completing an n-gram that already
+    occurred is banned; nothing is banned before n - 1 tokens exist."""
+    from vlpet_b200.host.generation import NoRepeatNGram, chain
+    toks = torch.tensor([[7, 1, 2, 3, 1, 2], [7, 5, 5, 5, 5, 5], [7, 1, 2, 9, 4, 8]])
+    sc = NoRepeatNGram(3)(5, toks, torch.zeros(3, 12))
+    assert torch.isinf(sc[0, 3]) and torch.isinf(sc[0]).sum() == 1            # (1, 2) was followed by 3
+    assert torch.isinf(sc[1, 5]) and torch.isinf(sc[1]).sum() == 1            # (5, 5) was followed by 5
+    assert not torch.isinf(sc[2]).any()
+    assert not torch.isinf(NoRepeatNGram(3)(0, toks[:, :1], torch.zeros(3, 12))).any()
+    sc1 = chain(NoRepeatNGram(1), NoRepeatNGram(2))(5, toks, torch.zeros(3, 12))
+    assert set(torch.isinf(sc1[0]).nonzero().flatten().tolist()) == {7, 1, 2, 3}   # unigrams: every token seen so far
+
+
 @pytest.mark.gpu
 def test_generate_with_cuda_vpa_matches_reference_cached_decode(H):
     """The same on the GPU in fp32: the value parallel adapter inside ``cross_kv`` is the K2 CUDA kernel (forward only, once per

@@ -115,3 +115,35 @@ def beam_search(step: Callable[[torch.Tensor], torch.Tensor], reorder: Callable[
     if return_scores:
         return out, torch.tensor([sl for _, _, sl in best], dtype=torch.float64)
     return out
+
+
+class NoRepeatNGram:
+    """HF's NoRepeatNGramLogitsProcessor (``no_repeat_ngram_size``; 3 in facebook/bart-base's generation defaults, which the
+    reference's ``generate`` calls inherit): a token that would complete an n-gram already present in the sequence gets
+    -inf.  Usable as ``logits_processor=NoRepeatNGram(3)`` (or chained through ``chain``) in ``generate``."""
+
+    def __init__(self, n: int):
+        if n < 1:
+            raise ValueError("no_repeat_ngram_size must be >= 1")
+        self.n = n
+
+    def __call__(self, step: int, tokens: torch.Tensor, scores: torch.Tensor) -> torch.Tensor:
+        n, cur_len = self.n, tokens.shape[1]
+        if cur_len + 1 < n:
+            return scores
+        rows = tokens.tolist()
+        for i, seq in enumerate(rows):
+            prefix = tuple(seq[cur_len - n + 1:]) if n > 1 else ()
+            banned = [seq[j + n - 1] for j in range(cur_len - n + 1) if tuple(seq[j:j + n - 1]) == prefix]
+            if banned:
+                scores[i, banned] = -float("inf")
+        return scores
+
+
+def chain(*processors):
+    """Apply several ``logits_processor`` callables in order."""
+    def run(step, tokens, scores):
+        for p in processors:
+            scores = p(step, tokens, scores)
+        return scores
+    return run
