@@ -138,15 +138,20 @@ wgrad_sm100_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) {
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sl * NACC * 128);
       const int nacc = my_steps < NACC ? (int)my_steps : NACC;   // accumulators that were written at all
       for (int n0 = 0; n0 < p.NB; n0 += 16) {
-        uint32_t v[16];
+        // all round-robin accumulators of this column block are requested before ONE wait: at small M (one or two steps per
+        // CTA) the flush is most of the kernel, and four serial tcgen05.ld round trips per block were most of the flush
+        uint32_t v[16], w[NACC - 1][16];
         ptx::tmem_ld_32x32b_x16(taddr + n0, v);
-        ptx::tmem_ld_wait();
-        for (int a = 1; a < nacc; ++a) {
-          uint32_t w[16];
-          ptx::tmem_ld_32x32b_x16(taddr + a * 128 + n0, w);
-          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
+        for (int a = 1; a < NACC; ++a)
+          if (a < nacc) ptx::tmem_ld_32x32b_x16(taddr + a * 128 + n0, w[a - 1]);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int a = 1; a < NACC; ++a) {
+          if (a < nacc) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[a - 1][e]));
+          }
         }
         if (transposed) {
 #pragma unroll
