@@ -69,9 +69,39 @@ def stack_heads(head_weights, head_biases):
 
 
 # --------------------------------------------------------------------------------------------------------
+# Dropout stream of the CUDA kernels (vl-pet_b200/csrc/vlpet_common.cuh: drop_hash4 / drop_thr16), restated in numpy so that
+# a parity test can hand the oracle the SAME mask the kernels draw.  The reference's own dropout is torch's Philox stream
+# (modeling_bart.py:1259 `F.dropout`); which elements are dropped is not part of parity, the arithmetic around the mask is.
+# --------------------------------------------------------------------------------------------------------
+def dropout_mask(seed: int, p_drop: float, M: int, d: int) -> np.ndarray:
+    """Multiplicative mask [M, d] (0 or 1/(1-p')) of the counter-based stream: one 64-bit hash per 4 consecutive elements of
+    the flat [M*d] index, 16 bits per element, keep iff bits >= thr16 = round(p * 65536); p' = thr16 / 65536."""
+    if p_drop <= 0.0:
+        return np.ones((M, d))
+    t = np.float32(p_drop) * np.float32(65536.0) + np.float32(0.5)
+    thr16 = 0 if t <= 0 else (65535 if t >= 65535 else int(t))
+    n4 = (M * d + 3) // 4
+    idx4 = np.arange(n4, dtype=np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    c0 = idx4 & m32
+    c1 = (idx4 >> np.uint64(32)) ^ np.uint64((seed >> 32) & 0xFFFFFFFF)
+    k = seed & 0xFFFFFFFF
+    for _ in range(5):                                   # Philox-2x32-style rounds: 32x32 -> 64 multiply, xor, swap
+        prod = c0 * np.uint64(0xD256D193)
+        c0 = ((prod >> np.uint64(32)) ^ np.uint64(k) ^ c1) & m32
+        c1 = prod & m32
+        k = (k + 0x9E3779B9) & 0xFFFFFFFF
+    h = (c1 << np.uint64(32)) | c0
+    bits = np.stack([(h >> np.uint64(16 * j)) & np.uint64(0xFFFF) for j in range(4)], axis=1).reshape(-1)[:M * d]
+    keep = bits >= np.uint64(thr16)
+    inv_keep = 1.0 / (1.0 - thr16 / 65536.0) if thr16 else 1.0
+    return np.where(keep, np.float32(inv_keep).astype(np.float64), 0.0).reshape(M, d)
+
+
+# --------------------------------------------------------------------------------------------------------
 # K1: granularity-controlled PET module (encoder, after self-attention and after the FFN)
 # --------------------------------------------------------------------------------------------------------
-def gated_pet_fwd(x1, x2, p: Dict[str, np.ndarray], cfg: PetConfig, rnd=None):
+def gated_pet_fwd(x1, x2, p: Dict[str, np.ndarray], cfg: PetConfig, rnd=None, mask=None):
     """out = x1 + s * gate(x1, y1),  y1 = kappa*x2 + alpha*Up(gelu_new(Down(x2))).
 
     Restates my_transformers/modeling_bart.py:1145-1155 (adapter), 1195-1231 (gates), 1256-1260 (scale,
@@ -124,6 +154,9 @@ def gated_pet_fwd(x1, x2, p: Dict[str, np.ndarray], cfg: PetConfig, rnd=None):
         h = y1
     else:
         raise ValueError(g)
+    if mask is not None:
+        c["mask"] = mask
+        h = h * mask
     out = x1 + cfg.s * h
     return out, c
 
@@ -134,6 +167,8 @@ def gated_pet_bwd(dout, p: Dict[str, np.ndarray], cfg: PetConfig, c, rnd=None):
     x1, x2, a, z, y1 = c["x1"], c["x2"], c["a"], c["z"], c["y1"]
     R = rnd if (rnd is not None and cfg.gate in (GATE_LARGE, GATE_NONE)) else (lambda t: t)
     dh = cfg.s * dout
+    if c.get("mask") is not None:
+        dh = dh * c["mask"]
     gr: Dict[str, np.ndarray] = {}
     dx1 = dout.copy()
     g = cfg.gate

@@ -524,6 +524,60 @@ def test_k1_dropout_stream(V):
     assert abs(fwd_zero[sig].float().mean().item() - 0.1) < 0.01
 
 
+@pytest.mark.parametrize("gate,M,L,r,rg,tol_x", [
+    ("large", 1300, 0, 96, 96, 3e-3),          # fused tcgen05 kernels (dropout bits precomputed per tile row in the backward)
+    ("large", 700, 0, 192, 192, 4e-3),         # rank halves + element-wise gate kernel
+    ("large", 900, 0, 4, 4, 3e-3),             # row-wise kernels, both branches row-local
+    ("middle_x", 560, 56, 96, 0, 3e-3),        # row-wise gate kernel + tcgen05 adapter
+    ("small", 672, 56, 4, 0, 3e-3),            # row-wise kernels, one launch (+ the per-sample pre-pass)
+    ("none", 800, 0, 96, 0, 3e-3),             # ungated form
+])
+def test_k1_dropout_matches_oracle_with_the_same_mask(V, gate, M, L, r, rg, tol_x):
+    """Training-mode parity: the kernels' counter-based dropout stream is restated in numpy (oracle.pet_oracle.dropout_mask), so
+    the oracle is evaluated with the SAME mask the kernels draw (p = 0.1, fixed seed) and forward, dx1, dx2 and every parameter
+    gradient are held to the usual bars -- on every path: fused, rank halves, row-wise inline / composed, ungated."""
+    import vlpet_b200.functional as F_
+    d, seed, pdrop = 768, 424242, 0.1
+    rng = np.random.default_rng(M + r)
+    x1, x2, dout, p = random_large_case(rng, M, d, r, max(rg, 8))
+    names = ["Wd", "bd", "Wu", "bu"]
+    if gate == "large":
+        names += ["Gd", "gbd", "Gu", "gbu"]
+    else:
+        for k in ("Gd", "gbd", "Gu", "gbu"):
+            p.pop(k)
+        if gate in ("middle_x", "small"):
+            p["gw"] = rng.standard_normal(d if gate == "middle_x" else 2 * d) * 0.05
+            p["gb"] = np.asarray(rng.standard_normal() * 0.02)
+            names += ["gw", "gb"]
+    bf = torch.bfloat16
+    W = [dev(p[k], bf).float().requires_grad_() for k in names]
+    tx1, tx2 = dev(x1, bf).requires_grad_(), dev(x2, bf).requires_grad_()
+    cfg = V.PetSiteConfig(gate=gate, p_drop=pdrop)
+    out = F_.GatedPETFn.apply(cfg, seed, L, 1, tx1, tx2, *W)
+    out.backward(dev(dout, bf))
+    torch.cuda.synchronize()
+    f = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+    pr = {k: bf16_round(v).reshape(np.shape(v)) for k, v in p.items()}
+    ocfg = O.PetConfig(gate=gate, seq_len=L)
+    mask = O.dropout_mask(seed, pdrop, M, d)
+    ref, cx = O.gated_pet_fwd(bf16_round(x1), bf16_round(x2), pr, ocfg, mask=mask)
+    r_dx1, r_dx2, g_x = O.gated_pet_bwd(bf16_round(dout), pr, ocfg, cx)
+    dropped = (f(out) - f(tx1)) == 0
+    # every element the oracle's mask drops is dropped by the kernel (out == x1 exactly); the converse holds up to kept outputs
+    # that round back to x1 in bf16 (~1 % when the gated term is small)
+    assert bool(dropped[mask == 0].all()) and pdrop - 0.01 < dropped.mean() < pdrop + 0.03
+    errs = {"out": rel(f(out), ref), "dx1": rel(f(tx1.grad), r_dx1), "dx2": rel(f(tx2.grad), r_dx2)}
+    for k, w in zip(names, W):
+        errs["d" + k] = rel(f(w.grad), np.asarray(g_x[k]).reshape(np.shape(p[k])))
+    print({k: float("%.2e" % e) for k, e in errs.items()})
+    for k in ("out", "dx1", "dx2"):
+        assert errs[k] < tol_x, (k, errs[k])
+    for k, e in errs.items():
+        if k not in ("out", "dx1", "dx2"):
+            assert e < 6e-3, (k, e)
+
+
 # ------------------------------------------------------------------------------------------------ K2
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)])
 @pytest.mark.parametrize("path", golden_files("k2_"), ids=os.path.basename)

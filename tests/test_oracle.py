@@ -106,3 +106,25 @@ def test_lowrank_visual_projector_matches_reference(path):
     assert set(gr) == set(p) - {"E_obj"}
     for k, v in gr.items():
         assert rel(v, g["d" + k]) < TOL, k
+
+
+def test_dropout_stream_restatement_statistics():
+    """oracle.pet_oracle.dropout_mask restates the kernels' counter-based dropout stream (csrc/vlpet_common.cuh drop_hash4); the
+    GPU test test_k1_dropout_matches_oracle_with_the_same_mask holds the kernels to it bit for bit.  Here: kept fraction,
+    scale, determinism per seed, independence of consecutive seeds (CUDA-graph replays bump the seed by one)."""
+    from oracle import pet_oracle as O
+    m = O.dropout_mask(1234, 0.1, 512, 768)
+    assert m.shape == (512, 768) and abs((m == 0).mean() - 0.1) < 2e-3
+    assert np.allclose(np.unique(m), [0.0, 1.0 / (1.0 - 6554 / 65536.0)], rtol=1e-6)
+    assert np.array_equal(m, O.dropout_mask(1234, 0.1, 512, 768))
+    m2 = O.dropout_mask(1235, 0.1, 512, 768)
+    assert abs(((m == 0) & (m2 == 0)).mean() - 0.01) < 1e-3
+    assert np.array_equal(O.dropout_mask(7, 0.0, 3, 8), np.ones((3, 8)))
+    x = np.arange(24.0).reshape(3, 8)
+    p = {"Wd": np.zeros((2, 8)), "bd": np.zeros(2), "Wu": np.zeros((8, 2)), "bu": np.ones(8)}
+    mk = O.dropout_mask(3, 0.5, 3, 8)
+    out, c = O.gated_pet_fwd(x, x, p, O.PetConfig(gate="none", kappa=0.0), mask=mk)     # h = bu = 1 -> out - x1 = mask
+    assert np.array_equal(out - x, mk)
+    dx1, dx2, gr = O.gated_pet_bwd(np.ones((3, 8)), p, O.PetConfig(gate="none", kappa=0.0), c)
+    assert np.array_equal(gr["bu"], mk.sum(0))
+
