@@ -526,12 +526,9 @@ __global__ void __launch_bounds__(128) attn2_bwd_kernel(const AttnArgs a) {
 }
 
 int launch_attn2(bool bwd, const AttnArgs& a, cudaStream_t st) {
-  static bool set_b = false;
+  static int set_b[64] = {0};      // per device ordinal: the attribute applies to the current device's copy of the kernel
   constexpr int FWD_SMEM = 3 * T2, BWD_SMEM = 6 * T2;
-  if (bwd && !set_b) {
-    VLPET_CUDA_OK(cudaFuncSetAttribute(attn2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    set_b = true;
-  }
+  if (bwd) VLPET_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(attn2_bwd_kernel), set_b, BWD_SMEM));
   const unsigned grid = (unsigned)(a.B * a.H);
   if (bwd) attn2_bwd_kernel<<<grid, 128, BWD_SMEM, st>>>(a);
   else attn2_fwd_kernel<<<grid, 128, FWD_SMEM, st>>>(a);
@@ -542,15 +539,9 @@ int launch_attn2(bool bwd, const AttnArgs& a, cudaStream_t st) {
 template <int LP>
 int launch_attn(bool bwd, const AttnArgs& a, cudaStream_t st) {
   using C = AttnCfg<LP>;
-  static bool set_f = false, set_b = false;
-  if (!bwd && !set_f) {
-    VLPET_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::FWD_SMEM));
-    set_f = true;
-  }
-  if (bwd && !set_b) {
-    VLPET_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BWD_SMEM));
-    set_b = true;
-  }
+  static int set_f[64] = {0}, set_b[64] = {0};   // per device ordinal (one process may drive several GPUs)
+  if (!bwd) VLPET_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<LP>), set_f, C::FWD_SMEM));
+  else VLPET_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_kernel<LP>), set_b, C::BWD_SMEM));
   const unsigned grid = (unsigned)(a.B * a.H);
   if (bwd) attn_bwd_kernel<LP><<<grid, C::THREADS, C::BWD_SMEM, st>>>(a);
   else attn_fwd_kernel<LP><<<grid, C::THREADS, C::FWD_SMEM, st>>>(a);
