@@ -217,6 +217,46 @@ def test_beam_search_over_the_cached_step_cpu(H, arch):
     assert bool((sc4 >= lpg.gather(-1, g[:, 1:, None]).squeeze(-1).sum(-1) - 1e-9).all())     # 4 beams found at least the greedy path here
 
 
+def test_trainer_checkpoint_resume_round_trip_cpu(H, tmp_path):
+    """PetTrainer.save / load (trainer_base.py:764-781): a PET-only ``<name>.pth`` under the reference's key names + the
+    optimizer state a resume needs.  A second trainer on a freshly initialised model loads them: same parameters (masters still
+    pinned in the flat bucket), same AdamW moments, same update / LR counters, same loss; the key report is clean."""
+    from oracle.eager_ref import use_eager_pet
+    z = _load("large")
+
+    def make(seed):
+        torch.manual_seed(seed)
+        model = use_eager_pet(H.VLBart(_cfg(H, "large")).double().eval())
+        return model, H.PetTrainer(model, model.config, "cpu", compute_dtype=torch.float64)
+
+    m1, t1 = make(0)
+    _load_state(m1, z, torch.float64)
+    batch = _batch(z, "vqa", torch.float64)
+    loss1 = float(t1.forward_backward(batch))
+    g = torch.Generator().manual_seed(3)
+    t1.bucket.exp_avg.copy_(torch.randn(t1.bucket.numel, generator=g, dtype=torch.float64))
+    t1.bucket.exp_avg_sq.copy_(torch.rand(t1.bucket.numel, generator=g, dtype=torch.float64))
+    t1.opt_steps, _ = 17, t1.set_step(23)
+    path = str(tmp_path / "LAST")
+    t1.save(path)
+    saved = torch.load(path + ".pth")
+    assert set(saved) == set(t1.bucket.names) and all(v.dtype == torch.float64 for v in saved.values())
+    m2, t2 = make(1)                                             # different init: everything trainable must come from the file
+    for n, p in m2.named_parameters():                           # the frozen backbone comes from the pretrained weights, as in the reference
+        if n not in saved:
+            p.data.copy_(dict(m1.named_parameters())[n].data)
+    res = t2.load(path)
+    assert not res.unexpected_keys and set(res.missing_keys).isdisjoint(saved)
+    assert torch.equal(t2.bucket.flat_param, t1.bucket.flat_param)
+    for p, o in zip(t2.bucket.params, t2.bucket.offsets):        # still views of the bucket
+        assert p.data_ptr() == t2.bucket.flat_param.data_ptr() + 8 * o
+    assert torch.equal(t2.bucket.exp_avg, t1.bucket.exp_avg) and torch.equal(t2.bucket.exp_avg_sq, t1.bucket.exp_avg_sq)
+    assert (t2.opt_steps, t2.step_idx) == (17, 23)
+    assert abs(float(t2.forward_backward(batch)) - loss1) < 1e-12
+    t1.save(path + "_full", full=True, with_optimizer=False)
+    assert set(torch.load(path + "_full.pth")) == set(m1.state_dict())
+
+
 def test_no_repeat_ngram_processor():
     """host.generation.NoRepeatNGram == HF's NoRepeatNGramLogitsProcessor semantics: a token completing an n-gram that already
     occurred is banned; nothing is banned before n - 1 tokens exist."""

@@ -281,6 +281,49 @@ class PetTrainer:
         self._release(key)
         return loss
 
+    # -- checkpoint / resume (trainer_base.py:764-781: `save(name)` writes model.state_dict() to <name>.pth, `load(path)` reads
+    #    it back with strict=False)
+    def save(self, path: str, full: bool = False, with_optimizer: bool = True):
+        """Write ``<path>.pth`` under the reference's key names -- loadable by the reference's ``load`` (strict=False) and by
+        ``host.VLBart / VLT5.load_state_dict``.  Default: the trainable (PET) parameters only, from their fp32 masters: the frozen
+        backbone is held in the compute dtype here and would come back rounded; ``full=True`` writes every key as the reference
+        does.  ``with_optimizer`` adds ``<path>.opt.pth`` -- what a resume needs and the reference never saves: the AdamW
+        moments of the flat bucket, the update counter and the LR-schedule step."""
+        names = set(self.bucket.names)
+        sd = self.model.state_dict()
+        out = {k: v.detach().to("cpu").clone() for k, v in sd.items() if full or k in names}
+        torch.save(out, path + ".pth")
+        if with_optimizer:
+            b = self.bucket
+            torch.save({"names": list(b.names), "offsets": list(b.offsets), "numel": b.numel,
+                        "exp_avg": b.exp_avg.detach().to("cpu"), "exp_avg_sq": b.exp_avg_sq.detach().to("cpu"),
+                        "opt_steps": self._opt_steps_value(), "step_idx": self.step_idx}, path + ".opt.pth")
+
+    def load(self, path: str, with_optimizer: bool = True):
+        """Read ``<path>.pth`` (strict=False, as the reference), re-pin the masters / refresh the bf16 shadow, and -- if present
+        -- restore the optimizer state written by ``save``.  Returns torch's (missing, unexpected) key report."""
+        import os
+        state = torch.load(path + ".pth", map_location="cpu")
+        res = self.model.load_state_dict(state, strict=False)      # copy_ into the bucket views: the masters stay pinned
+        if self.device.type == "cuda":
+            self.bucket.refresh_shadow()
+        if with_optimizer and os.path.exists(path + ".opt.pth"):
+            o = torch.load(path + ".opt.pth", map_location="cpu")
+            b = self.bucket
+            if list(o["names"]) != list(b.names) or int(o["numel"]) != b.numel:
+                raise RuntimeError("PetTrainer.load: the optimizer state was written for a different trainable set")
+            b.exp_avg.copy_(o["exp_avg"].to(b.exp_avg.dtype))
+            b.exp_avg_sq.copy_(o["exp_avg_sq"].to(b.exp_avg_sq.dtype))
+            self._set_opt_steps(int(o["opt_steps"]))
+            self.set_step(int(o["step_idx"]))
+        return res
+
+    def _opt_steps_value(self) -> int:
+        return int(self.opt_steps)
+
+    def _set_opt_steps(self, n: int):
+        self.opt_steps = int(n)
+
 
 class GraphedPetTrainer(PetTrainer):
     """The same step replayed from CUDA graphs (static shapes make it possible): one
@@ -319,6 +362,13 @@ class GraphedPetTrainer(PetTrainer):
     def set_step(self, n: int):
         self.step_idx = int(n)
         self._t.fill_(float(n))
+
+    def _opt_steps_value(self) -> int:                  # the update counter of the graphed optimizer lives on the device
+        return int(self._k.item())
+
+    def _set_opt_steps(self, n: int):
+        self.opt_steps = int(n)
+        self._k.fill_(float(n))
 
     _signature = staticmethod(batch_signature)
 
