@@ -433,6 +433,21 @@ def test_t5_generate_with_cuda_vpa_matches_reference_cached_decode(H):
     assert rel(logits.double().cpu().numpy(), z["vqa/step_logits"]) < 2e-4
 
 
+def test_test_step_handles_nlvr_pairs_cpu(H):
+    """test_step on an NLVR batch (two images per sample, nlvr_model.py:156-176): both host models flatten the pair and add the
+    image-order ids, as their train_step does."""
+    from oracle.eager_ref import use_eager_pet
+    for arch in ("bart", "t5"):
+        z = _load("large") if arch == "bart" else _load_t5()
+        model = use_eager_pet((H.VLBart(_cfg(H, "large")) if arch == "bart" else H.VLT5(_t5_cfg(H))).double().eval())
+        _load_state(model, z, torch.float64)
+        b = _batch(z, "nlvr", torch.float64)
+        out = model.test_step({k: v for k, v in b.items() if k != "target_ids"}, max_length=5, min_length=5)["token_ids"]
+        assert out.shape == (b["input_ids"].shape[0], 5)
+        out5 = model.test_step({k: v for k, v in b.items() if k != "target_ids"}, max_length=5, min_length=5, num_beams=3)["token_ids"]
+        assert out5.shape == out.shape
+
+
 def test_t5_base_trainable_count_is_the_reference_checksum(H):
     """T5-base + VL-PET-large at r = rg = dec_r = 96 (BASELINE config 3): 10 499 712 trainable parameters, the count obtained
     by instantiating the reference VLT5."""

@@ -422,6 +422,21 @@ class VLT5(nn.Module):
             loss = F.cross_entropy(lg, labels.reshape(-1), ignore_index=-100, reduction="none")
         return loss, logits
 
+    def _vis_inputs(self, batch: dict, dev):
+        """(feats, boxes[, img_ids, obj_ids]) of a task batch on the device; NLVR pairs are flattened (nlvr_model.py:28-62)."""
+        feats = batch["vis_feats"].to(dev, non_blocking=True)
+        boxes = batch["boxes"].to(dev, non_blocking=True)
+        if batch["task"] != "nlvr":
+            return (feats, boxes)
+        B, V_L = feats.shape[0], feats.shape[2]
+        feats = feats.reshape(B, 2 * V_L, -1)
+        boxes = boxes.reshape(B, 2 * V_L, 4)
+        key = (V_L, str(dev))
+        if key not in self._nlvr_ids:
+            self._nlvr_ids[key] = (torch.tensor([0] * V_L + [1] * V_L, dtype=torch.long, device=dev).view(1, -1),
+                                   torch.arange(V_L, dtype=torch.long, device=dev).repeat(2).view(1, -1))
+        return (feats, boxes, self._nlvr_ids[key][0].expand(B, -1), self._nlvr_ids[key][1].expand(B, -1))
+
     @torch.no_grad()
     def generate(self, input_ids, vis_inputs, task=None, max_length: int = 20, min_length: int = 0, num_beams: int = 1,
                  logits_processor=None, attention_mask=None, vis_attention_mask=None, return_step_logits: bool = False,
@@ -481,8 +496,7 @@ class VLT5(nn.Module):
     def test_step(self, batch: dict, **gen_kwargs) -> dict:
         """vqa_model.py:112-164 (the T5 task model's generative test_step): batch -> {'token_ids'}."""
         dev = self.shared.weight.device
-        feats, boxes = batch["vis_feats"].to(dev, non_blocking=True), batch["boxes"].to(dev, non_blocking=True)
-        out = self.generate(batch["input_ids"].to(dev, non_blocking=True), (feats, boxes), task=batch["task"], **gen_kwargs)
+        out = self.generate(batch["input_ids"].to(dev, non_blocking=True), self._vis_inputs(batch, dev), task=batch["task"], **gen_kwargs)
         result = {"token_ids": out}
         tok = getattr(self, "tokenizer", None)
         if tok is not None:
@@ -494,21 +508,9 @@ class VLT5(nn.Module):
         dev = self.shared.weight.device
         task = batch["task"]
         input_ids = batch["input_ids"].to(dev, non_blocking=True)
-        feats = batch["vis_feats"].to(dev, non_blocking=True)
-        boxes = batch["boxes"].to(dev, non_blocking=True)
         labels = batch["target_ids"].to(dev, non_blocking=True)
         B = input_ids.shape[0]
-        if task == "nlvr":
-            V_L = feats.shape[2]
-            feats = feats.reshape(B, 2 * V_L, -1)
-            boxes = boxes.reshape(B, 2 * V_L, 4)
-            key = (V_L, str(dev))
-            if key not in self._nlvr_ids:
-                self._nlvr_ids[key] = (torch.tensor([0] * V_L + [1] * V_L, dtype=torch.long, device=dev).view(1, -1),
-                                       torch.arange(V_L, dtype=torch.long, device=dev).repeat(2).view(1, -1))
-            vis_inputs = (feats, boxes, self._nlvr_ids[key][0].expand(B, -1), self._nlvr_ids[key][1].expand(B, -1))
-        else:
-            vis_inputs = (feats, boxes)
+        vis_inputs = self._vis_inputs(batch, dev)
         loss, _ = self(input_ids, vis_inputs, labels, task=task)
         T = labels.shape[1]
         mask = (labels != -100).float()
