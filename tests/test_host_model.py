@@ -433,6 +433,29 @@ def test_t5_generate_with_cuda_vpa_matches_reference_cached_decode(H):
     assert rel(logits.double().cpu().numpy(), z["vqa/step_logits"]) < 2e-4
 
 
+def test_zero_init_flags_follow_the_reference_rules(H):
+    """host.weight_initialization restates trainer_base.py:544-599: with the T5 scripts' zero-init flags the up projections of
+    adapter, gate and decoder VPA start at zero, so the PET-augmented model computes the frozen backbone's function at step 0
+    (large gate: y1 = x2 and G = sigmoid(0) = 1/2 scaled by s; the VPA adds nothing)."""
+    from oracle.eager_ref import use_eager_pet
+    cfg = _t5_cfg(H, use_encoder_multihead_up_zero_init=True, use_encoder_gating_large_x_lowrank_up_zero_init=True,
+                  use_decoder_enc_vpa_up_zero_init=True)
+    model = use_eager_pet(H.VLT5(cfg).double().eval())
+    z = _load_t5()
+    _load_state(model, z, torch.float64)
+    done = H.weight_initialization(model, cfg)
+    keys = [str(k) for k in z["meta_state_keys"]]
+    want = [k for k in keys if "adapter_multihead_up" in k or "adapter_gating_large_x_up" in k or
+            ("attn_value_parallel_adapter" in k and "up_sampler" in k)]
+    params = dict(model.named_parameters())
+    assert done and set(done) <= set(want) and all(float(params[n].detach().abs().sum()) == 0.0 for n in done)
+    assert {params[n].data_ptr() for n in done} == {model.state_dict()[k].data_ptr() for k in want}     # aliased task keys included
+    assert H.weight_initialization(model, _t5_cfg(H)) == []
+    small = H.VLBart(_cfg(H, "small", use_encoder_gating_small_up_zero_init=True))
+    zs = H.weight_initialization(small, small.config)
+    assert zs and all("adapter_gating_small_xy_cat" in n for n in zs)
+
+
 def test_test_step_handles_nlvr_pairs_cpu(H):
     """test_step on an NLVR batch (two images per sample, nlvr_model.py:156-176): both host models flatten the pair and add the
     image-order ids, as their train_step does."""

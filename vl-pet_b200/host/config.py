@@ -61,6 +61,12 @@ class VLPetConfig:
     decoder_enc_attn_value_parallel_adapter_down_dim: int = 96
     use_single_adapter: bool = True
     freeze_vis_emb: bool = False
+    # zero-init flags of the T5 scripts (trainer_base.py:544-599 weight_initialization; scripts/image-text/T5-VL-PET-*.sh)
+    use_encoder_multihead_up_zero_init: bool = False
+    use_encoder_gating_large_x_lowrank_up_zero_init: bool = False
+    use_decoder_enc_vpa_up_zero_init: bool = False
+    use_encoder_gating_small_up_zero_init: bool = False
+    use_encoder_gating_middle_up_zero_init: bool = False
     # ---- T5-base (t5-base config.json; vocab 32 100 + 100 <vis_extra_id> tokens, tokenization.py:58-60); used when arch == "t5"
     arch: str = "bart"
     d_kv: int = 64
@@ -105,7 +111,8 @@ def t5_base_vlpet_large(r: int = 96, heads: int = 4, rg: int = 96, dec_r: int = 
     return VLPetConfig(arch="t5", vocab_size=32200, pad_token_id=0, decoder_start_token_id=0, eos_token_id=1,
                        adapter_down_dim=r, encoder_adapter_multihead_num_head=heads, adapter_gating_down_dim=rg,
                        decoder_enc_attn_value_parallel_adapter_down_dim=dec_r, use_encoder_gating_scaling=True,
-                       encoder_gating_scaling_factor=s).clone(**kw)
+                       encoder_gating_scaling_factor=s, use_encoder_multihead_up_zero_init=True,
+                       use_encoder_gating_large_x_lowrank_up_zero_init=True, use_decoder_enc_vpa_up_zero_init=True).clone(**kw)
 
 
 def bart_base_vlpet_small(r: int = 4, heads: int = 4, dec_r: int = 4, **kw) -> VLPetConfig:

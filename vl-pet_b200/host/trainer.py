@@ -58,6 +58,33 @@ def _align(n: int, a: int = 1024) -> int:
     return (n + a - 1) // a * a
 
 
+def weight_initialization(model: nn.Module, config) -> List[str]:
+    """The zero-init rules the reference applies by parameter-name substring after building the model
+    (trainer_base.py:544-599; the T5 scripts pass --use_encoder_multihead_up_zero_init,
+    --use_encoder_gating_large_x_lowrank_up_zero_init / --use_encoder_gating_small_up_zero_init and
+    --use_decoder_enc_vpa_up_zero_init so that training starts from the frozen backbone's function).  Call it before the
+    trainer is built (it writes through ``param.data``).  Returns the names it zeroed."""
+    rules = []
+    if getattr(config, "use_encoder_multihead_up_zero_init", False):
+        rules.append(lambda n: "adapter_multihead_up" in n)
+    if getattr(config, "use_encoder_gating_large_x_lowrank_up_zero_init", False):
+        rules.append(lambda n: "adapter_gating_large_x_up" in n)
+    if getattr(config, "use_decoder_enc_vpa_up_zero_init", False):
+        rules.append(lambda n: ("EncDecAttention.attn_value_parallel_adapter" in n or "encoder_attn.attn_value_parallel_adapter" in n)
+                     and "up_sampler" in n)
+    if getattr(config, "use_encoder_gating_small_up_zero_init", False):
+        rules.append(lambda n: "adapter_gating_small_xy_cat" in n)
+    if getattr(config, "use_encoder_gating_middle_up_zero_init", False):
+        rules.append(lambda n: "adapter_gating_middle_xy_add" in n)
+    done = []
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if any(r(n) for r in rules):
+                p.data.zero_()
+                done.append(n)
+    return done
+
+
 class PetBucket:
     """Flat fp32 parameter / gradient / AdamW-state buffers + bf16 shadow for the trainable set.
     Each parameter starts on a 1024-element boundary so the per-block weight-decay mask of vlpet_adamw_step applies
