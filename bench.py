@@ -361,7 +361,9 @@ def run_ours(a):
     torch.manual_seed(0)
     tasks, feat_dim, grid, vocab_hi = resolve_config(a)
     if a.config == 3:
-        cfg = H.t5_base_vlpet_large(r=a.rank_r, rg=a.rank_r, dec_r=a.rank_r, assume_no_padding=True)
+        # the T5 script ships r = r_g = 192 with a decoder adapter of 96 (T5-VL-PET-large.sh:46-57): the decoder rank follows
+        # --rank-r only up to that 96
+        cfg = H.t5_base_vlpet_large(r=a.rank_r, rg=a.rank_r, dec_r=min(a.rank_r, 96), assume_no_padding=True)
         model = H.VLT5(cfg).train()
     elif a.config == 4:
         cfg = H.bart_base_vlpet_small(r=a.rank_r, dec_r=a.rank_r, assume_no_padding=True)
