@@ -1,0 +1,161 @@
+"""SURVEY section 8 row f-4, data / wire formats: ``vlpet_b200.host.data`` against ``tests/golden/collate_cases.json`` -- the
+reference's own ``collate_fn`` of all eight tasks, the video loaders' ``resize`` and ``MultitaskLoader``'s task order, run
+unmodified on seeded entries by ``tests/golden/make_golden_collate.py``.  Integer and index work: bit-exact.  CPU only."""
+import json
+import os
+
+import pytest
+import torch
+
+from tests.helpers import GOLDEN
+
+
+@pytest.fixture(scope="module")
+def D():
+    try:
+        import vlpet_b200.host.data as D_
+    except Exception as e:                       # the package needs libvlpet.so (built in-tree by build())
+        pytest.skip(f"vlpet_b200 not importable: {e}")
+    return D_
+
+
+@pytest.fixture(scope="module")
+def cases():
+    with open(os.path.join(GOLDEN, "collate_cases.json")) as f:
+        return json.load(f)
+
+
+def _tensor(spec):
+    return torch.tensor(spec["data"], dtype=getattr(torch, spec["dtype"])).reshape(spec["shape"])
+
+
+def test_collate_matches_reference_collate_fn(D, cases):
+    seen = set()
+    for c in cases["collate"]:
+        got = D.collate(c["task"], c["entries"], c["pad_token_id"])
+        want = c["batch"]
+        assert set(got) == set(want), (c["task"], sorted(set(got) ^ set(want)))
+        for k, v in want.items():
+            if isinstance(v, dict) and "dtype" in v:
+                w = _tensor(v)
+                assert got[k].dtype == w.dtype and got[k].shape == w.shape, (c["task"], k, got[k].dtype, got[k].shape)
+                assert torch.equal(got[k], w), (c["task"], k)
+            else:
+                assert got[k] == v, (c["task"], k)
+        seen.add((c["task"], "target_ids" in want))
+    assert seen == {(t, f) for t in D.IMAGE_TASKS + D.VIDEO_TASKS for f in (True, False)}
+
+
+def test_collate_accepts_tensors_and_arrays_and_refuses_ragged_grids(D, cases):
+    import numpy as np
+    c = cases["collate"][0]
+    as_t = [dict(e, input_ids=torch.tensor(e["input_ids"]), vis_feats=np.asarray(e["vis_feats"], dtype=np.float32),
+                 boxes=torch.tensor(e["boxes"])) for e in c["entries"]]
+    a, b = D.collate("vqa", as_t, 1), D.collate("vqa", c["entries"], 1)
+    assert all(torch.equal(a[k], b[k]) for k in ("input_ids", "target_ids", "vis_feats", "boxes", "scores"))
+    bad = [dict(e) for e in c["entries"]]
+    bad[1]["vis_feats"] = bad[1]["vis_feats"][:-1]
+    with pytest.raises(ValueError):
+        D.collate("vqa", bad, 1)
+    with pytest.raises(ValueError):
+        D.collate("vqa", [], 1)
+    with pytest.raises(ValueError):
+        D.collate("okvqa", c["entries"], 1)
+
+
+def test_collate_feeds_the_host_model_schema(D, cases):
+    """The batch keys ``train_step`` reads (host/synthetic.py's schema) are a subset of what collate produces."""
+    for c in cases["collate"]:
+        if "target_ids" not in c["batch"]:
+            continue
+        got = D.collate(c["task"], c["entries"], c["pad_token_id"])
+        need = {"task", "input_ids", "vis_feats", "boxes", "target_ids"} | ({"scores"} if c["task"] in ("vqa", "gqa") else set())
+        assert need <= set(got)
+        assert int((got["target_ids"] == c["pad_token_id"]).sum()) == 0 and got["target_ids"].min() >= -100
+
+
+def test_resize_frames_matches_reference_resize(D, cases):
+    for c in cases["resize"]:
+        x = torch.tensor(c["input"], dtype=torch.float32)
+        y = D.resize_frames(x, c["length"])
+        assert y.shape == (c["length"], x.shape[1])
+        assert torch.equal(y, torch.tensor(c["output"], dtype=torch.float32)), (x.shape, c["length"])
+
+
+class _Loader:
+    def __init__(self, task, n):
+        self.task, self.n = task, n
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        return iter([(self.task, i) for i in range(self.n)])
+
+
+def test_multitask_loader_order_matches_reference(D, cases):
+    for c in cases["schedule"]:
+        ml = D.MultitaskLoader([_Loader(t, n) for t, n in c["lens"].items()], shuffle=c["shuffle"], sampling=c["sampling"],
+                               n_batches=c["n_batches"])
+        ml.set_epoch(c["epoch"])
+        assert len(ml) == c["len"]
+        if c["sampling"] == "roundrobin":
+            assert [list(b) for b in ml] == c["order"], c
+            assert len(ml) == 0
+        else:
+            assert [[t, None] for t in reversed(ml.epoch_tasks)] == c["order"], c
+
+
+def test_task_batches_split_like_distributed_sampler(D, cases):
+    from torch.utils.data.distributed import DistributedSampler
+    entries = [dict(cases["collate"][0]["entries"][i % 3], question_id=i) for i in range(11)]
+    for world in (1, 2, 3):
+        for shuffle in (False, True):
+            for epoch in (0, 2):
+                got = []
+                for rank in range(world):
+                    tb = D.TaskBatches("vqa", entries, batch_size=2, pad_token_id=1, rank=rank, world=world, shuffle=shuffle, seed=5)
+                    tb.sampler.set_epoch(epoch)
+                    ref = DistributedSampler(entries, num_replicas=world, rank=rank, shuffle=shuffle, seed=5)
+                    ref.set_epoch(epoch)
+                    ids = [q for b in tb for q in b["question_ids"]]
+                    assert ids == list(ref), (world, rank, shuffle, epoch)
+                    assert len(tb) == -(-len(ids) // 2)
+                    got += ids
+                assert set(got) == set(range(11))
+    ml = D.MultitaskLoader([D.TaskBatches("vqa", entries, 4, 1), D.TaskBatches("gqa", entries[:5], 4, 1)])
+    tasks = [b["task"] for b in ml]
+    assert sorted(tasks) == ["gqa", "gqa", "vqa", "vqa", "vqa"]
+
+
+def test_collated_batch_reproduces_reference_loss_cpu(D):
+    """Entries -> collate -> host.VLBart.train_step gives the loss the reference's VLBart gave on the same samples
+    (tests/golden/vlbart_tiny_large.npz): the wire format and the caller of the hot path agree end to end."""
+    import numpy as np
+    import vlpet_b200.host as H
+    from oracle.eager_ref import use_eager_pet
+    from tests.test_host_model import _batch, _cfg, _load, _load_state
+    z = _load("large")
+    model = use_eager_pet(H.VLBart(_cfg(H, "large")).double().eval())
+    _load_state(model, z, torch.float64)
+    pad = model.config.pad_token_id
+    for task in ("vqa", "nlvr"):
+        want = _batch(z, task, torch.float64)
+        entries = []
+        for i in range(want["input_ids"].shape[0]):
+            ids, tgt = want["input_ids"][i], want["target_ids"][i]
+            e = {"input_ids": ids[ids != pad].tolist(), "target_ids": tgt[tgt != -100].tolist(), "sent": "", "question_id": i,
+                 "vis_feats": z[f"{task}/vis_feats"][i], "boxes": z[f"{task}/boxes"][i], "label": None}
+            if "scores" in want:
+                e["score"] = float(want["scores"][i])
+            entries.append(e)
+        got = D.collate(task, entries, pad)
+        for k in ("input_ids", "target_ids"):
+            assert torch.equal(got[k], want[k]), (task, k)
+        assert np.array_equal(got["vis_feats"].numpy(), z[f"{task}/vis_feats"].astype(np.float32))
+        got["vis_feats"], got["boxes"] = want["vis_feats"], want["boxes"]          # fp64 model: keep the fixture's precision
+        if "scores" in want:
+            assert torch.equal(got["scores"], want["scores"].float())
+            got["scores"] = want["scores"]
+        loss = model.train_step(got)["loss"]
+        assert abs(loss.item() - float(z[f"{task}/loss"])) < 1e-9, task
