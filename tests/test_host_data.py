@@ -159,3 +159,69 @@ def test_collated_batch_reproduces_reference_loss_cpu(D):
             got["scores"] = want["scores"]
         loss = model.train_step(got)["loss"]
         assert abs(loss.item() - float(z[f"{task}/loss"])) < 1e-9, task
+
+
+def test_fit_and_predict_over_a_multitask_loader_cpu(D):
+    """entries -> TaskBatches -> MultitaskLoader -> PetTrainer.fit / predict (the epoch loop of multitask.py:189-345 and the
+    predict half of its ``*_evaluate``): task order and counts follow the loader, the per-task mean losses equal a hand-written
+    loop over the same loader, predictions equal ``test_step`` called batch by batch.  fp64 on CPU with the oracle on the PET
+    sites; the fused AdamW kernel is CUDA-only, so the test steps with plain SGD on the flat bucket."""
+    import vlpet_b200.host as H
+    from oracle.eager_ref import use_eager_pet
+    from tests.test_host_model import _cfg
+
+    class SgdTrainer(H.PetTrainer):
+        def optimizer_step(self):
+            lr = H.linear_warmup_lr(self.step_idx, self.total_steps, self.warmup_ratio, self.lr)
+            self.bucket.flat_param.add_(self.bucket.flat_grad, alpha=-lr)
+            self.step_idx += 1
+            self.opt_steps += 1
+
+    cfg = _cfg(H, "large")
+    g = torch.Generator().manual_seed(11)
+
+    def entry(task, i, target=True):
+        shape = (2, cfg.n_boxes) if task == "nlvr" else (cfg.n_boxes,)
+        e = {"input_ids": torch.randint(3, 290, (int(torch.randint(2, 7, (1,), generator=g)),), generator=g).tolist(),
+             "vis_feats": torch.randn(*shape, cfg.feat_dim, generator=g), "boxes": torch.zeros(*shape, 4),
+             "sent": f"s{i}", "question_id": f"{task}{i}", "label": None}
+        if target:
+            e.update(target_ids=torch.randint(3, 290, (int(torch.randint(1, 4, (1,), generator=g)),), generator=g).tolist(),
+                     answer=f"a{i}", score=1.0)
+        return e
+
+    data = {"vqa": [entry("vqa", i) for i in range(7)], "nlvr": [entry("nlvr", i) for i in range(4)]}
+
+    def loader():
+        return D.MultitaskLoader([D.TaskBatches(t, es, 3, cfg.pad_token_id) for t, es in data.items()])
+
+    def trainer():
+        torch.manual_seed(0)
+        model = use_eager_pet(H.VLBart(cfg).double())
+        return SgdTrainer(model, cfg, "cpu", lr=1e-2, total_steps=10, compute_dtype=torch.float64)
+
+    t1 = trainer()
+    hist = t1.fit(loader(), epochs=2)
+    assert [h["epoch"] for h in hist] == [0, 1] and all(h["task_counter"] == {"vqa": 3, "nlvr": 2} and h["steps"] == 5 for h in hist)
+    assert t1.step_idx == 10 and hist[1]["loss"] < hist[0]["loss"]
+    t2 = trainer()
+    ld = loader()
+    for epoch in range(2):
+        ld.set_epoch(epoch)
+        sums = {"vqa": 0.0, "nlvr": 0.0}
+        for b in ld:
+            sums[b["task"]] += float(t2.train_step(b))
+        assert abs(sums["vqa"] / 3 - hist[epoch]["task_loss"]["vqa"]) < 1e-12
+        assert abs(sums["nlvr"] / 2 - hist[epoch]["task_loss"]["nlvr"]) < 1e-12
+    assert torch.equal(t1.bucket.flat_param, t2.bucket.flat_param)
+    seen = []
+    t1.fit(loader(), epochs=1, start_epoch=2, on_epoch_end=lambda tr, rec: seen.append((tr is t1, rec["epoch"])))
+    assert seen == [(True, 2)]
+
+    test = D.TaskBatches("vqa", [entry("vqa", 100 + i, target=False) for i in range(4)], 3, cfg.pad_token_id)
+    pred = t1.predict(test, max_length=5)
+    assert set(pred) == {"vqa"} and sorted(pred["vqa"]) == [f"vqa{100 + i}" for i in range(4)]
+    t1.model.eval()
+    for b in test:
+        tok = t1.model.test_step(b, max_length=5)["token_ids"].tolist()
+        assert [pred["vqa"][q] for q in b["question_ids"]] == tok

@@ -170,7 +170,10 @@ class Prefetched:
 
 
 def batch_signature(batch: Dict):
-    return tuple((k, tuple(v.shape), str(v.dtype)) if torch.is_tensor(v) else (k, v) for k, v in sorted(batch.items()))
+    """What a captured step depends on: the shapes / dtypes of the tensors and the scalar fields (``task``).  The bookkeeping
+    lists a reference ``collate_fn`` adds (sentences, question ids, answers ...) never reach the device and are left out."""
+    return tuple((k, tuple(v.shape), str(v.dtype)) if torch.is_tensor(v) else (k, v) for k, v in sorted(batch.items())
+                 if torch.is_tensor(v) or isinstance(v, (str, int, float, bool)))
 
 
 class PetTrainer:
@@ -231,6 +234,8 @@ class PetTrainer:
             for k, v in batch.items():
                 if torch.is_tensor(v):
                     bufs[k].copy_(v, non_blocking=True)
+                else:
+                    bufs[k] = v                                 # bookkeeping fields travel with their batch
             ready = torch.cuda.Event()
             ready.record(self._copy_stream)
         return Prefetched(bufs, ready, key)
@@ -307,6 +312,67 @@ class PetTrainer:
         self.optimizer_step()
         self._release(key)
         return loss
+
+    # -- the epoch loop of multitask.py:189-345: set_epoch, one train_step per batch in the loader's task order, per-task
+    #    batch counts and mean losses.  The losses are summed on the device; the host reads them once per epoch.
+    def fit(self, loader, epochs: int = 1, start_epoch: int = 0, on_epoch_end=None) -> List[Dict]:
+        """``loader`` yields host batches (``host.MultitaskLoader``, a reference loader, or any iterable of batch dicts);
+        on CUDA the copy of batch i+1 is issued before the step of batch i (``prefetch``) when the batches are pinned.
+        Returns one dict per epoch: ``{'epoch', 'steps', 'loss', 'task_counter', 'task_loss'}``; ``on_epoch_end(trainer, dict)``
+        is where a caller validates or saves (multitask.py:347-412)."""
+        history = []
+        cuda = self.device.type == "cuda"
+        for epoch in range(start_epoch, start_epoch + epochs):
+            self.model.train()
+            if hasattr(loader, "set_epoch"):
+                loader.set_epoch(epoch)
+            sums: Dict[str, torch.Tensor] = {}
+            counter: Dict[str, int] = {}
+
+            def stage(b):
+                pinned = cuda and all(v.is_pinned() for v in b.values() if torch.is_tensor(v))
+                return self.prefetch(b) if pinned else b
+
+            it = iter(loader)
+            nxt = next(it, None)
+            cur = stage(nxt) if nxt is not None else None
+            while cur is not None:
+                task = (cur.batch if isinstance(cur, Prefetched) else cur)["task"]
+                nxt = next(it, None)
+                ahead = stage(nxt) if nxt is not None else None
+                loss = self.train_step(cur)
+                if task not in sums:
+                    sums[task] = torch.zeros((), dtype=torch.float64, device=loss.device)
+                sums[task] += loss.double()
+                counter[task] = counter.get(task, 0) + 1
+                cur = ahead
+            steps = sum(counter.values())
+            task_loss = {t: float(s) / counter[t] for t, s in sums.items()}
+            rec = {"epoch": epoch, "steps": steps, "task_counter": counter, "task_loss": task_loss,
+                   "loss": sum(task_loss[t] * counter[t] for t in counter) / max(1, steps)}
+            history.append(rec)
+            if on_epoch_end is not None:
+                on_epoch_end(self, rec)
+        return history
+
+    @torch.no_grad()
+    def predict(self, loader, **gen_kwargs) -> Dict[str, Dict]:
+        """The ``*_evaluate`` loops' first half (multitask.py:499-541 ``predict``): ``test_step`` over a loader ->
+        ``{task: {question_id: generated token ids (or text, when the model carries a tokenizer)}}``; ids come from the
+        batch's ``question_ids`` (``img_id`` for captions), else a running index."""
+        self.model.eval()
+        out: Dict[str, Dict] = {}
+        try:
+            for batch in loader:
+                res = self.model.test_step(batch, **gen_kwargs)
+                answers = res["pred_ans"] if "pred_ans" in res else res["token_ids"].tolist()
+                bucket = out.setdefault(batch["task"], {})
+                ids = batch.get("question_ids") or batch.get("img_id") or range(len(bucket), len(bucket) + len(answers))
+                for q, a in zip(ids, answers):
+                    bucket[q] = a
+        finally:
+            self.model.train()
+        return out
 
     # -- checkpoint / resume (trainer_base.py:764-781: `save(name)` writes model.state_dict() to <name>.pth, `load(path)` reads
     #    it back with strict=False)
