@@ -123,3 +123,21 @@ def test_host_only_entry_points(L):
     assert L.lib.vlpet_version() == int(m.group(1))
     assert isinstance(L.lib.vlpet_last_error(), bytes)
     assert L.launch_count() >= 0
+
+
+def test_integration_stub_is_current(L):
+    """The hand-written reference-side binding INTEGRATION.md shows is executed against the built library (definitions only,
+    no call) and compared with the complete mirror."""
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        md = f.read()
+    code = re.search(r"```python\n(# src/vlpet_ffi\.py.*?)```", md, flags=re.S).group(1)
+    assert '"/path/to/libvlpet.so"' in code
+    ns = {}
+    exec(compile(code.replace('"/path/to/libvlpet.so"', repr(L.LIB_PATH)), "INTEGRATION.md", "exec"), ns)
+    for name in ("K1Desc", "K1Params"):
+        stub, full = ns[name], getattr(L, name)
+        assert [n for n, _ in stub._fields_] == [n for n, _ in full._fields_]
+        assert C.sizeof(stub) == C.sizeof(full)
+        assert all(getattr(stub, n).offset == getattr(full, n).offset for n, _ in full._fields_)
+    assert len(ns["lib"].vlpet_k1_fwd.argtypes) == len(L.SYMBOLS["vlpet_k1_fwd"][1])
+    assert callable(ns["k1_forward"])
