@@ -18,8 +18,8 @@ Notation: M = B*L tokens, d = d_model, r = adapter rank, rg = gate rank.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
-from typing import Dict, Optional
+from dataclasses import dataclass
+from typing import Dict
 
 import numpy as np
 

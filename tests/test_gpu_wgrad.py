@@ -3,7 +3,6 @@ against a float64 matmul of the same bf16 values.  Products of bf16 values are e
 fp32 accumulation order: tolerance 2e-6 relative (Frobenius)."""
 import ctypes as C
 
-import numpy as np
 import pytest
 import torch
 

@@ -1,5 +1,5 @@
 """Where does a training step go?  torch.profiler over one task cycle: CUDA kernel time vs wall time, top kernels."""
-import os, sys, time, json
+import os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vlpet_b200.host as H

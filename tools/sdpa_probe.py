@@ -1,5 +1,5 @@
 """Which SDPA backend is fastest at the encoder shapes of the bench workload?  (host-side choice, stock PyTorch)"""
-import torch, time
+import torch
 from torch.nn.attention import sdpa_kernel, SDPBackend
 import torch.nn.functional as F
 def bench(B, H, L, S, D, backend, causal=False, p=0.1):

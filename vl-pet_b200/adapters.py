@@ -7,7 +7,7 @@ shared adapter across tasks, and error behaviour; the forward runs the fused CUD
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional
 
 import torch

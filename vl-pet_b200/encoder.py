@@ -12,7 +12,6 @@ released checkpoints keep working.
 from __future__ import annotations
 
 import types
-from typing import List, Tuple
 
 import torch
 import torch.nn as nn

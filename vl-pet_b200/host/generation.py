@@ -11,7 +11,7 @@ the self-attention caches).  Host-side plumbing: PyTorch, no kernels of its own;
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, List, Tuple
 
 import torch
 

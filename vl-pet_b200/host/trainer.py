@@ -17,7 +17,6 @@ weights are stored in bf16 once.
 from __future__ import annotations
 
 import ctypes as C
-import math
 from typing import Dict, List, Optional
 
 import torch
