@@ -507,3 +507,49 @@ def test_host_t5_with_cuda_pet_matches_reference_vlt5(H):
         for n in names:
             assert rel(params[n].grad.double().cpu().numpy(), z[f"{task}/grad/{n}"]) < 5e-4, (task, n)
     assert V.launch_count() - n0 >= 2 * (2 * 2 * 2 + 2 + 1), "PET sites did not run the CUDA kernels"
+
+
+def test_beam_search_equals_transformers_generate_on_a_stock_model():
+    """The search loop of host/generation.py against the installed transformers' own ``generate(num_beams=...)`` (the descendant of
+    the 4.2.1 loop the reference pins) on a stock, randomly initialised tiny BART: same tokens for several beam widths, length
+    penalties and both early-stopping modes, with hypotheses that end at different lengths.  A shared additive logits processor
+    makes a random-init model emit varied tokens and EOS.  Library model on CPU: no PET kernels involved."""
+    from transformers import BartConfig, BartForConditionalGeneration, LogitsProcessor, LogitsProcessorList
+    import vlpet_b200.host.generation as G
+    torch.manual_seed(0)
+    V, B, T = 30, 4, 9
+    cfg = BartConfig(vocab_size=V, d_model=32, encoder_layers=1, decoder_layers=1, encoder_attention_heads=2,
+                     decoder_attention_heads=2, encoder_ffn_dim=64, decoder_ffn_dim=64, max_position_embeddings=64, pad_token_id=1,
+                     bos_token_id=0, eos_token_id=2, decoder_start_token_id=2, forced_eos_token_id=None, forced_bos_token_id=None)
+    model = BartForConditionalGeneration(cfg).double().eval()
+    lengths = set()
+    for seed, nb, lp, es in ((1, 4, 1.0, False), (2, 4, 0.0, False), (3, 3, 1.0, True), (4, 5, 2.0, False), (5, 2, 0.5, True), (6, 1, 1.0, False)):
+        g = torch.Generator().manual_seed(seed)
+        ids = torch.randint(3, V, (B, 7), generator=g)
+        bias = torch.randn(T, V, generator=g, dtype=torch.float64) * 2.0
+        bias[:, 1] = -1e9                                        # never the pad token
+        bias[:, 2] += 2.5                                        # EOS often among the candidates: hypotheses finish early
+
+        class Bias(LogitsProcessor):
+            def __call__(self, input_ids, scores):
+                return scores + bias[input_ids.shape[1] - 1].to(scores.dtype)
+
+        with torch.no_grad():
+            want = model.generate(input_ids=ids, num_beams=nb, max_length=T, min_length=0, do_sample=False, early_stopping=es,
+                                  length_penalty=lp, no_repeat_ngram_size=0, logits_processor=LogitsProcessorList([Bias()]))
+            enc = model.get_encoder()(input_ids=ids).last_hidden_state.repeat_interleave(nb, 0)
+        state = {"tok": None}
+
+        def step(new):
+            state["tok"] = new if state["tok"] is None else torch.cat([state["tok"], new], 1)
+            return model(encoder_outputs=(enc,), decoder_input_ids=state["tok"]).logits[:, -1]
+
+        def reorder(idx):
+            state["tok"] = state["tok"].index_select(0, idx)
+
+        got = G.beam_search(step, reorder, B, nb, "cpu", 2, 1, 2, T, 0, lp, es, logits_processor=lambda s, t, x: x + bias[s])
+        w = max(want.shape[1], got.shape[1])
+        pad = lambda x: torch.cat([x, torch.full((x.shape[0], w - x.shape[1]), 1)], 1)    # noqa: E731
+        assert torch.equal(pad(want), pad(got)), (seed, nb, lp, es, want, got)
+        lengths |= {int((row != 1).sum()) for row in got}
+    assert len(lengths) >= 3, lengths                            # hypotheses of different lengths were compared

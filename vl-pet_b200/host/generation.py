@@ -5,9 +5,10 @@ The search loop restates the algorithm of the reference's pinned ``transformers`
 ``BeamSearchScorer`` / ``BeamHypotheses``): log-softmax scores, ``2 * num_beams`` candidates per sample and step, finished
 hypotheses ranked by ``sum_logprobs / len ** length_penalty``, a sample is done when its worst kept hypothesis beats the best
 score still reachable (or, with ``early_stopping``, as soon as ``num_beams`` hypotheses finished).  That library is not
-importable offline in this image (transformers 5.5 removed the scorer), so the test pins the loop by exhaustive enumeration on
-a restricted vocabulary and by re-scoring its output with a full teacher-forced pass (which also checks the beam re-ordering of
-the self-attention caches).  Host-side plumbing: PyTorch, no kernels of its own; the PET work inside a step is the model's.
+importable offline in this image (transformers 5.5 removed the scorer), so the tests pin the loop three ways: token-for-token
+against the installed transformers' own ``generate(num_beams=...)`` on a stock tiny BART (beam widths, length penalties, both
+early-stopping modes, hypotheses of different lengths), by exhaustive enumeration on a restricted vocabulary, and by re-scoring
+its output with a full teacher-forced pass (which also checks the beam re-ordering of the self-attention caches).  Host-side plumbing: PyTorch, no kernels of its own; the PET work inside a step is the model's.
 """
 from __future__ import annotations
 
