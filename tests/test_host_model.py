@@ -269,6 +269,13 @@ def test_no_repeat_ngram_processor():
     assert not torch.isinf(NoRepeatNGram(3)(0, toks[:, :1], torch.zeros(3, 12))).any()
     sc1 = chain(NoRepeatNGram(1), NoRepeatNGram(2))(5, toks, torch.zeros(3, 12))
     assert set(torch.isinf(sc1[0]).nonzero().flatten().tolist()) == {7, 1, 2, 3}   # unigrams: every token seen so far
+    from transformers import NoRepeatNGramLogitsProcessor                      # the library's processor on random sequences
+    g = torch.Generator().manual_seed(0)
+    for n in (1, 2, 3, 4):
+        for cur_len in (1, 2, 3, 6, 11):
+            rnd = torch.randint(0, 5, (6, cur_len), generator=g)
+            want = NoRepeatNGramLogitsProcessor(n)(rnd, torch.zeros(6, 5))
+            assert torch.equal(NoRepeatNGram(n)(cur_len - 1, rnd, torch.zeros(6, 5)), want), (n, cur_len)
 
 
 @pytest.mark.gpu
