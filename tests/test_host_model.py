@@ -319,6 +319,15 @@ def test_linear_warmup_schedule():
     assert abs(linear_warmup_lr(5, 100, 0.1, 1e-3) - 5e-4) < 1e-12
     assert abs(linear_warmup_lr(10, 100, 0.1, 1e-3) - 1e-3) < 1e-12
     assert abs(linear_warmup_lr(55, 100, 0.1, 1e-3) - 5e-4) < 1e-12
+    # the library scheduler the reference builds (trainer_base.py:722-730), stepped once per update
+    from transformers import get_linear_schedule_with_warmup
+    for total, ratio in ((37, 0.1), (100, 0.05), (10, 0.0), (64, 0.5)):
+        opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=3e-4)
+        sched = get_linear_schedule_with_warmup(opt, int(total * ratio), total)
+        for step in range(total + 3):
+            assert abs(linear_warmup_lr(step, total, ratio, 3e-4) - sched.get_last_lr()[0]) < 1e-15, (total, ratio, step)
+            opt.step()
+            sched.step()
 
 
 @pytest.mark.gpu
