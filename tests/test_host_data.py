@@ -225,3 +225,25 @@ def test_fit_and_predict_over_a_multitask_loader_cpu(D):
     for b in test:
         tok = t1.model.test_step(b, max_length=5)["token_ids"].tolist()
         assert [pred["vqa"][q] for q in b["question_ids"]] == tok
+
+
+def test_synthetic_cycle_ratios_and_shards():
+    """host/synthetic.py: the per-task batch ratios of multitask.py:682-695 (vqa b, gqa b*100/60, nlvr b*20/60, caption b*50/60;
+    the video tasks unscaled, multitask_video.py:740-743) and the per-rank shards of one global cycle."""
+    import vlpet_b200.host as H
+    assert H.task_batch_sizes(300) == {"vqa": 300, "gqa": 500, "nlvr": 100, "caption": 250}
+    assert H.task_batch_sizes(50, H.VIDEO_TASKS) == {t: 50 for t in H.VIDEO_TASKS}
+    tasks = ["vqa", "gqa", "nlvr", "caption"]
+    full = H.multitask_cycle(6, tasks, feat_dim=8, seed=3)
+    assert [b["task"] for b in full] == tasks and [b["input_ids"].shape[0] for b in full] == [6, 10, 2, 5]
+    assert full[2]["vis_feats"].shape == (2, 2, 49, 8) and full[0]["vis_feats"].shape == (6, 49, 8)
+    assert all(int((b["boxes"] != 0).sum()) == 0 for b in full)          # CLIP grid features carry no boxes (vqa_clip_data.py:198)
+    for world in (2, 4):
+        parts = [H.multitask_cycle(6, tasks, feat_dim=8, seed=3, rank=r, world=world) for r in range(world)]
+        for i, b in enumerate(full):
+            for k, v in b.items():
+                if torch.is_tensor(v):
+                    assert torch.equal(torch.cat([p[i][k] for p in parts]), v), (world, b["task"], k)
+    assert H.batch_nbytes(full[0]) == sum(v.numel() * v.element_size() for v in full[0].values() if torch.is_tensor(v))
+    again = H.multitask_cycle(6, tasks, feat_dim=8, seed=3)
+    assert all(torch.equal(a["input_ids"], b["input_ids"]) for a, b in zip(full, again))
