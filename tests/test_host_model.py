@@ -307,6 +307,22 @@ def test_bart_base_trainable_count_is_the_reference_checksum(H):
     assert n == 6052416
 
 
+def test_trainable_share_matches_the_published_table(H):
+    """The 'Trainable Params (%)' column of the reference's results table (README.md:357-360: small / middleX / middleY 2.98,
+    large 4.16; all at r = 96) from the host model's parameter names and the trainer's unfreeze rules."""
+    def share(cfg):
+        with torch.device("meta"):
+            model = H.VLBart(cfg)
+        names = set(H.trainable_names(model, cfg))
+        return 100.0 * sum(p.numel() for k, p in model.named_parameters() if k in names) / sum(p.numel() for p in model.parameters())
+
+    small = H.bart_base_vlpet_small(r=96, dec_r=96)
+    middle = [small.clone(use_encoder_adapter_gating_small_xy_cat=False, **{f: True})
+              for f in ("use_encoder_adapter_gating_middle_xy_add", "use_encoder_adapter_gating_middle_ia3_add")]
+    for cfg, want in ((H.bart_base_vlpet_large(), 4.16), (small, 2.98), (middle[0], 2.98), (middle[1], 2.98)):
+        assert round(share(cfg), 2) == want
+
+
 def test_task_batch_ratios_follow_the_reference():
     from vlpet_b200.host import task_batch_sizes
     assert task_batch_sizes(500) == {"vqa": 500, "gqa": 833, "nlvr": 166, "caption": 416}   # SURVEY Appendix D
