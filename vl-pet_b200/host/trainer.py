@@ -359,6 +359,7 @@ class PetTrainer:
         """The ``*_evaluate`` loops' first half (multitask.py:499-541 ``predict``): ``test_step`` over a loader ->
         ``{task: {question_id: generated token ids (or text, when the model carries a tokenizer)}}``; ids come from the
         batch's ``question_ids`` (``img_id`` for captions), else a running index."""
+        was_training = self.model.training
         self.model.eval()
         out: Dict[str, Dict] = {}
         try:
@@ -370,7 +371,7 @@ class PetTrainer:
                 for q, a in zip(ids, answers):
                     bucket[q] = a
         finally:
-            self.model.train()
+            self.model.train(was_training)
         return out
 
     # -- checkpoint / resume (trainer_base.py:764-781: `save(name)` writes model.state_dict() to <name>.pth, `load(path)` reads
