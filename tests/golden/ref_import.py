@@ -37,9 +37,20 @@ def install_shims():
     mp.assert_device_map = lambda *a, **k: None
     mp.get_device_map = lambda *a, **k: None
     sys.modules["transformers.utils.model_parallel_utils"] = mp
+    if not hasattr(mu.PreTrainedModel, "_vlpet_stock_init_weights"):
+        mu.PreTrainedModel._vlpet_stock_init_weights = mu.PreTrainedModel.init_weights
     mu.PreTrainedModel.init_weights = lambda self: self.apply(self._init_weights)
     if REF_SRC not in sys.path:
         sys.path.insert(0, REF_SRC)
+
+
+def remove_shims():
+    """Give stock transformers models their own ``init_weights`` back (it ties the LM head to the embeddings; the shim above
+    skips that).  The other shims only add names the installed transformers no longer has and stay."""
+    import transformers.modeling_utils as mu
+    stock = getattr(mu.PreTrainedModel, "_vlpet_stock_init_weights", None)
+    if stock is not None:
+        mu.PreTrainedModel.init_weights = stock
 
 
 def import_bart_backbone():

@@ -548,6 +548,9 @@ def test_beam_search_equals_transformers_generate_on_a_stock_model():
     makes a random-init model emit varied tokens and EOS.  Library model on CPU: no PET kernels involved."""
     from transformers import BartConfig, BartForConditionalGeneration, LogitsProcessor, LogitsProcessorList
     import vlpet_b200.host.generation as G
+    import sys
+    if "ref_import" in sys.modules:              # an earlier test imported the reference: undo the init_weights shim for stock models
+        sys.modules["ref_import"].remove_shims()
     torch.manual_seed(0)
     V, B, T = 30, 4, 9
     cfg = BartConfig(vocab_size=V, d_model=32, encoder_layers=1, decoder_layers=1, encoder_attention_heads=2,
