@@ -52,6 +52,19 @@ def _synthetic():
     return mod
 
 
+_PATCHED_METHODS = ("init_weights", "get_extended_attention_mask", "invert_attention_mask", "get_head_mask")
+_STOCK: dict = {}
+
+
+def remove_shims():
+    """Restore the ``PreTrainedModel`` methods install_shims replaced (for a process that goes on to use stock transformers
+    models, e.g. a test session); names that were only added stay."""
+    import transformers.modeling_utils as mu
+    for name, fn in _STOCK.items():
+        if fn is not None:
+            setattr(mu.PreTrainedModel, name, fn)
+
+
 def install_shims(src: str):
     import torch
     import transformers
@@ -72,6 +85,8 @@ def install_shims(src: str):
     mp.assert_device_map = lambda *a, **k: None
     mp.get_device_map = lambda *a, **k: None
     sys.modules["transformers.utils.model_parallel_utils"] = mp
+    for name in _PATCHED_METHODS:                       # remembered once, so remove_shims() can give stock models theirs back
+        _STOCK.setdefault(name, getattr(mu.PreTrainedModel, name, None))
     mu.PreTrainedModel.init_weights = lambda self: self.apply(self._init_weights)
 
     # transformers 4.2.1 semantics of the mask helpers the T5 wrapper calls (src/modeling_t5.py:282-292)

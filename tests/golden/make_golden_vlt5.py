@@ -23,10 +23,10 @@ from baseline import ref_arm as RA  # noqa: E402  (the T5 import shims of SURVEY
 D, R_, HEADS, FEAT = 64, 16, 4, 128
 
 
-def build():
+def build(gate: str = "large"):
     mm, transformers = RA._import_reference("t5")
     import param
-    flags = RA.BASE_FLAGS.split() + [RA.GATE_FLAG["large"], "--adapter_down_dim", str(R_), "--encoder_adapter_multihead_num_head",
+    flags = RA.BASE_FLAGS.split() + [RA.GATE_FLAG[gate], "--adapter_down_dim", str(R_), "--encoder_adapter_multihead_num_head",
                                      str(HEADS), "--adapter_gating_down_dim", str(R_),
                                      "--decoder_enc_attn_value_parallel_adapter_down_dim", str(R_), "--dropout", "0.0",
                                      "--use_encoder_gating_scaling", "--encoder_gating_scaling_factor", "0.3"]
